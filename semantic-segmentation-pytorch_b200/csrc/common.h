@@ -1,0 +1,43 @@
+// Host-side helpers shared by every translation unit of libsseg_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/sseg_b200.h"
+
+namespace sseg {
+
+// Error plumbing of the C ABI: every entry point returns 0 or a negative code and
+// leaves a message retrievable with sseg_last_error(). No exceptions cross the boundary.
+void set_error(const char* fmt, ...);
+int check_cuda(cudaError_t e, const char* what);
+void count_launch(int n);
+
+#define SSEG_CUDA(expr)                                  \
+  do {                                                   \
+    int _rc = ::sseg::check_cuda((expr), #expr);         \
+    if (_rc) return _rc;                                 \
+  } while (0)
+
+#define SSEG_REQUIRE(cond, ...)                          \
+  do {                                                   \
+    if (!(cond)) {                                       \
+      ::sseg::set_error(__VA_ARGS__);                    \
+      return SSEG_ERR_ARG;                               \
+    }                                                    \
+  } while (0)
+
+// TMA tensor-map construction (cuTensorMapEncodeTiled through the runtime's driver entry point,
+// so the library does not link libcuda). Maps are cached by their full geometry.
+//   rank-4 bf16/f32 activation view (C, W, H, N) with 128B swizzle, box (box_c, box_w, box_h, 1)
+int get_tmap_act(CUtensorMap* out, const void* ptr, int elem_bytes, int n, int h, int w, int c, int ld,
+                 int box_c, int box_w, int box_h);
+//   rank-2 matrix [rows][cols] (cols contiguous) with 128B swizzle, box (box_cols, box_rows)
+int get_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long rows, long cols, long ld, int box_cols,
+                int box_rows);
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace sseg

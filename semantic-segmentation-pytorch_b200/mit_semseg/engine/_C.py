@@ -1,0 +1,81 @@
+"""ctypes binding of libsseg_b200.so (the C ABI declared in include/sseg_b200.h).
+
+There is deliberately NO fallback: if the shared library is missing or a call fails, an exception is
+raised.  The product path never routes through the oracle or a CPU implementation.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.abspath(os.path.join(_HERE, "..", "..", "libsseg_b200.so"))
+
+MAX_SRCS = 5
+MAX_TAPS = 9
+
+
+class SsegError(RuntimeError):
+    pass
+
+
+class Act(Structure):
+    """sseg_act_t: NHWC activation view."""
+    _fields_ = [("ptr", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int), ("c", c_int), ("ld", c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SsegError(
+                "libsseg_b200.so not found at %s - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C semantic-segmentation-pytorch_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+        L = ctypes.CDLL(LIB_PATH)
+        _declare(L)
+        _lib = L
+    return _lib
+
+
+def _declare(L):
+    L.sseg_last_error.restype = c_char_p
+    L.sseg_last_error.argtypes = []
+    L.sseg_version.restype = c_int
+    L.sseg_launch_count.restype = c_long
+    L.sseg_launch_count_reset.restype = None
+    for name, args in _SIGNATURES.items():
+        fn = getattr(L, name)
+        fn.restype = c_int
+        fn.argtypes = args
+
+
+def check(rc):
+    if rc != 0:
+        raise SsegError("libsseg_b200 error %d: %s" % (rc, lib().sseg_last_error().decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+_p = c_void_p
+_ip = POINTER(c_int)
+_SIGNATURES = {
+    "sseg_conv_igemm": [POINTER(Act), c_int, _p, c_int, c_int, _ip, _ip, _p, c_int, c_int, c_int, _p, _p, c_int, _p,
+                        _p, _p],
+}
+
+EXPORTED_SYMBOLS = ["sseg_last_error", "sseg_version", "sseg_launch_count", "sseg_launch_count_reset"] + list(
+    _SIGNATURES)
+
+
+def int_array(vals):
+    return (c_int * len(vals))(*vals)
+
+
+def act_array(acts):
+    return (Act * len(acts))(*acts)

@@ -1,0 +1,97 @@
+"""-m gpu: the tcgen05 implicit-GEMM convolution (sseg_conv_igemm) against torch's fp32 convolution.
+
+Inputs are rounded to bf16 first, so the only differences are fp32 accumulation order and (for bf16
+outputs) the final rounding: tolerance 2^-8 relative to the output scale (bf16 half-ulp is 2^-9).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_conv(xs, w, dilation, bias=None):
+    x = torch.cat([t.float() for t in xs], dim=3).permute(0, 3, 1, 2)
+    k = w.shape[-1]
+    y = F.conv2d(x, w.float(), bias=bias, padding=dilation * (k // 2), dilation=dilation)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+def _run(n, h, w_, cins, cout, k, d, out_f32=False, bias=False, addend=False, stats=False, seed=0):
+    from mit_semseg.engine import ops
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    xs = [torch.randn(n, h, w_, c, device="cuda", generator=g).bfloat16() for c in cins]
+    cin = sum(cins)
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * (2.0 / (cin * k * k)) ** 0.5).bfloat16()
+    b = torch.randn(cout, device="cuda", generator=g) if bias else None
+    ref = _ref_conv(xs, wt, d, b)
+    n_store = (cout + 7) // 8 * 8
+    ld = n_store + 8 if out_f32 else n_store
+    out = torch.full((n, h, w_, ld), float("nan"), device="cuda", dtype=torch.float32 if out_f32 else torch.bfloat16)
+    add = None
+    if addend:
+        add = torch.randn(n, h, w_, n_store, device="cuda", generator=g).bfloat16()
+        ref = ref + add[..., :cout].float()
+    ssum = torch.zeros(cout, device="cuda") if stats else None
+    ssq = torch.zeros(cout, device="cuda") if stats else None
+    w_ohwi = wt.permute(0, 2, 3, 1).contiguous()
+    ops.conv_igemm(xs, w_ohwi, cout, ops.conv_taps(k, d), out, n_store=n_store, bias=b, addend=add, stat_sum=ssum,
+                   stat_sqsum=ssq)
+    torch.cuda.synchronize()
+    got = out[..., :cout].float()
+    scale = ref.abs().max().item()
+    err = (got - ref).abs().max().item()
+    assert torch.isfinite(got).all()
+    tol = (2 ** -8 if not out_f32 else 1e-4) * scale
+    assert err <= tol, "max err %g > tol %g (scale %g)" % (err, tol, scale)
+    if n_store > cout:
+        assert (out[..., cout:n_store].float().abs().max().item() == 0.0)
+    if stats:
+        rs, rq = ref.sum(dim=(0, 1, 2)), (ref * ref).sum(dim=(0, 1, 2))
+        assert (ssum - rs).abs().max().item() <= 1e-3 * max(1.0, rs.abs().max().item()) + 1e-2 * (n * h * w_) ** 0.5
+        assert (ssq - rq).abs().max().item() <= 1e-3 * rq.abs().max().item()
+
+
+def test_pointwise_basic():
+    _run(2, 64, 64, [256], 128, 1, 1)
+
+
+def test_pointwise_wide_k_and_stats():
+    _run(2, 64, 64, [2048], 512, 1, 1, stats=True)
+
+
+def test_pointwise_cout64_large_map():
+    _run(1, 128, 128, [128], 64, 1, 1, stats=True)
+
+
+@pytest.mark.parametrize("d", [1, 2, 4])
+def test_3x3_dilated(d):
+    _run(2, 64, 64, [128], 128, 3, d, stats=True)
+
+
+def test_3x3_cout256_cin512():
+    _run(2, 64, 64, [512], 256, 3, 1)
+
+
+def test_3x3_wide_rows():
+    _run(1, 32, 256, [64], 64, 3, 1, stats=True)
+
+
+def test_virtual_concat_3x3():
+    _run(2, 64, 64, [256, 64, 64, 128, 64], 128, 3, 1, stats=True)
+
+
+def test_classifier_f32_bias():
+    _run(2, 64, 64, [512], 150, 1, 1, out_f32=True, bias=True)
+
+
+def test_ragged_spatial():
+    _run(2, 38, 50, [64], 128, 3, 2, stats=True)
+    _run(3, 6, 6, [128], 64, 3, 1, stats=True)
+    _run(1, 5, 300, [64], 64, 1, 1, stats=True)
+
+
+def test_addend():
+    _run(2, 64, 64, [128], 256, 3, 1, addend=True)
