@@ -1,0 +1,360 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
+
+A CPU, fp32 restatement of the reference hot path (CSAILVision/semantic-segmentation-pytorch @ 8f27c9b):
+deep-stem dilated ResNet -> PPM / PPM_deepsup / C1 / UPerNet decoder -> log-softmax / NLL / pixel accuracy, with both
+batch-norm formulas of SynchronizedBatchNorm2d.  It is written functionally over a flat state dict that uses the
+reference's parameter names, so one weights file loads into the reference, this oracle and the B200 engine.
+
+Where the arithmetic lives: the reference has no kernels of its own; every primitive is a call into PyTorch ATen
+(CPU: oneDNN) — third-party, pinned only as `torch>=0.4.1` (reference setup.py:22); this container has torch 2.11.0.
+The primitives (conv2d, batch_norm, max_pool2d, adaptive_avg_pool2d, bilinear interpolate, log_softmax, nll_loss)
+are therefore the SAME library calls the reference makes, composed exactly as the reference composes them; their
+published algorithms are restated independently in numpy in `oracle/np_primitives.py` and cross-checked in
+tests/test_oracle.py.  Backward is torch autograd through these ops, as in the reference (batchnorm.py has no
+custom backward).
+
+Pinning: the reference ships no golden vectors for this path ("parity unpinned" by its tests), so the
+oracle is pinned against OUTPUTS OF THE REFERENCE ITSELF imported from /root/reference in the build container:
+`oracle/make_golden.py` generated tests/golden/*.npz; tests/test_oracle.py checks this file against them.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+# ----------------------------------------------------------------------------------------------
+# architecture tables (reference: models/resnet.py:165-203 layer counts; models/models.py:63-110 arch names)
+RESNET_LAYERS = {"resnet18": ("basic", [2, 2, 2, 2]), "resnet50": ("bottleneck", [3, 4, 6, 3]),
+                 "resnet101": ("bottleneck", [3, 4, 23, 3])}
+
+
+def parse_encoder_arch(arch):
+    arch = arch.lower()
+    dilated = arch.endswith("dilated")
+    base = arch[:-len("dilated")] if dilated else arch
+    if base not in RESNET_LAYERS:
+        raise Exception("Architecture undefined!")
+    return base, dilated
+
+
+def _conv_hparams(block, layer_idx, block_idx, conv_name, dilated):
+    """stride/dilation/padding of one ResNet conv after ResnetDilated._nostride_dilate
+    (reference models/models.py:238-251 applied with dilate=2 to layer3 and dilate=4 to layer4)."""
+    # original stride: first block of layers 2..4 carries stride 2 on conv1 (basic) / conv2 (bottleneck) / downsample
+    strided_name = "conv1" if block == "basic" else "conv2"
+    stride = 2 if (layer_idx >= 2 and block_idx == 0 and conv_name in (strided_name, "downsample.0")) else 1
+    is3x3 = (conv_name in ("conv1", "conv2")) if block == "basic" else (conv_name == "conv2")
+    dilation, padding = 1, (1 if is3x3 else 0)
+    if dilated and layer_idx in (3, 4):
+        dilate = 2 if layer_idx == 3 else 4
+        if stride == 2:
+            stride = 1
+            if is3x3:
+                dilation = padding = dilate // 2
+        elif is3x3:
+            dilation = padding = dilate
+    return stride, dilation, padding
+
+
+# ----------------------------------------------------------------------------------------------
+# batch norm: the two formulas of _SynchronizedBatchNorm.forward (reference lib/nn/modules/batchnorm.py:56-86)
+class BNState:
+    """How batch norm behaves for this forward pass.
+
+    training=False               -> running statistics (F.batch_norm eval; batchnorm.py:58-61)
+    training=True,  sync=False   -> F.batch_norm training: biased var + eps, momentum update (batchnorm.py:58-61)
+    training=True,  sync=True    -> the data-parallel branch: statistics pooled over ALL replicas' batches,
+                                    inv_std = clamp(var, eps)^-0.5 (batchnorm.py:123-139). The oracle is given the
+                                    concatenation of every replica's batch, which is the same pooling.
+    """
+
+    def __init__(self, training, sync=False, eps=1e-5, momentum=0.001, update_running=False):
+        self.training, self.sync, self.eps, self.momentum, self.update_running = training, sync, eps, momentum, update_running
+
+
+def batch_norm(x, sd, prefix, st):
+    w, b = sd[prefix + ".weight"], sd[prefix + ".bias"]
+    rm, rv = sd[prefix + ".running_mean"], sd[prefix + ".running_var"]
+    if not st.training:
+        return F.batch_norm(x, rm, rv, w, b, False, st.momentum, st.eps)
+    if not st.sync:
+        if st.update_running:
+            return F.batch_norm(x, rm, rv, w, b, True, st.momentum, st.eps)
+        return F.batch_norm(x, None, None, w, b, True, st.momentum, st.eps)
+    # batchnorm.py:63-81 + _compute_mean_std :123-139
+    shape = x.shape
+    xv = x.reshape(x.size(0), x.size(1), -1)
+    size = xv.size(0) * xv.size(2)
+    s = xv.sum(dim=0).sum(dim=-1)
+    ss = (xv ** 2).sum(dim=0).sum(dim=-1)
+    assert size > 1
+    mean = s / size
+    sumvar = ss - s * mean
+    bias_var = sumvar / size
+    if st.update_running:
+        unbias_var = sumvar / (size - 1)
+        frac = 1.0 - st.momentum
+        sd[prefix + "._tmp_running_mean"] = sd[prefix + "._tmp_running_mean"] * frac + mean.detach()
+        sd[prefix + "._tmp_running_var"] = sd[prefix + "._tmp_running_var"] * frac + unbias_var.detach()
+        sd[prefix + "._running_iter"] = sd[prefix + "._running_iter"] * frac + 1
+        sd[prefix + ".running_mean"] = sd[prefix + "._tmp_running_mean"] / sd[prefix + "._running_iter"]
+        sd[prefix + ".running_var"] = sd[prefix + "._tmp_running_var"] / sd[prefix + "._running_iter"]
+    inv_std = bias_var.clamp(st.eps) ** -0.5
+    out = (xv - mean.view(1, -1, 1)) * (inv_std * w).view(1, -1, 1) + b.view(1, -1, 1)
+    return out.view(shape)
+
+
+def _cbr(x, sd, conv, bn, st, stride=1, dilation=1, padding=0, relu=True):
+    x = F.conv2d(x, sd[conv + ".weight"], sd.get(conv + ".bias"), stride, padding, dilation)
+    x = batch_norm(x, sd, bn, st)
+    return F.relu(x) if relu else x
+
+
+# ----------------------------------------------------------------------------------------------
+# encoder (reference models/resnet.py:24-92 blocks, :96-160 ResNet; models/models.py:170-268 wrappers)
+def encoder_forward(x, sd, arch, st, prefix=""):
+    base, dilated = parse_encoder_arch(arch)
+    block, counts = RESNET_LAYERS[base]
+    P = prefix
+    x = _cbr(x, sd, P + "conv1", P + "bn1", st, stride=2, padding=1)
+    x = _cbr(x, sd, P + "conv2", P + "bn2", st, padding=1)
+    x = _cbr(x, sd, P + "conv3", P + "bn3", st, padding=1)
+    x = F.max_pool2d(x, 3, 2, 1)
+    outs = []
+    for li, nblocks in enumerate(counts, start=1):
+        for bi in range(nblocks):
+            p = "%slayer%d.%d." % (P, li, bi)
+            residual = x
+            if block == "basic":
+                s, d, pad = _conv_hparams(block, li, bi, "conv1", dilated)
+                out = _cbr(x, sd, p + "conv1", p + "bn1", st, s, d, pad)
+                s, d, pad = _conv_hparams(block, li, bi, "conv2", dilated)
+                out = _cbr(out, sd, p + "conv2", p + "bn2", st, s, d, pad, relu=False)
+            else:
+                out = _cbr(x, sd, p + "conv1", p + "bn1", st)
+                s, d, pad = _conv_hparams(block, li, bi, "conv2", dilated)
+                out = _cbr(out, sd, p + "conv2", p + "bn2", st, s, d, pad)
+                out = _cbr(out, sd, p + "conv3", p + "bn3", st, relu=False)
+            if (p + "downsample.0.weight") in sd:
+                s, _, _ = _conv_hparams(block, li, bi, "downsample.0", dilated)
+                residual = _cbr(x, sd, p + "downsample.0", p + "downsample.1", st, s, relu=False)
+            x = F.relu(out + residual)
+        outs.append(x)
+    return outs
+
+
+# ----------------------------------------------------------------------------------------------
+# decoders (reference models/models.py:327-586)
+def _dropout2d(x, p, training, mask=None):
+    """nn.Dropout2d: one Bernoulli(1-p) draw per (n, c), survivors scaled by 1/(1-p). `mask` (N x C of 0/1) injects
+    the draw so GPU and CPU runs can share it."""
+    if not training or p == 0.0:
+        return x
+    if mask is None:
+        return F.dropout2d(x, p, True)
+    return x * (mask.to(x.dtype) / (1.0 - p)).view(x.size(0), x.size(1), 1, 1)
+
+
+def _head(x, segSize, use_softmax):
+    if use_softmax:
+        x = F.interpolate(x, size=segSize, mode="bilinear", align_corners=False)
+        return F.softmax(x, dim=1)
+    return F.log_softmax(x, dim=1)
+
+
+def decoder_forward(conv_out, sd, arch, st, segSize=None, use_softmax=False, dropout_p=0.1, masks=None, prefix="",
+                    return_logits=False):
+    arch = arch.lower()
+    P = prefix
+    masks = masks or {}
+    conv5 = conv_out[-1]
+    if arch in ("ppm", "ppm_deepsup"):
+        H, W = conv5.shape[2:]
+        ppm_out = [conv5]
+        for i, scale in enumerate((1, 2, 3, 6)):
+            y = F.adaptive_avg_pool2d(conv5, scale)
+            y = _cbr(y, sd, "%sppm.%d.1" % (P, i), "%sppm.%d.2" % (P, i), st)
+            ppm_out.append(F.interpolate(y, (H, W), mode="bilinear", align_corners=False))
+        x = torch.cat(ppm_out, 1)
+        x = _cbr(x, sd, P + "conv_last.0", P + "conv_last.1", st, padding=1)
+        x = _dropout2d(x, dropout_p, st.training, masks.get("main"))
+        logits = F.conv2d(x, sd[P + "conv_last.4.weight"], sd[P + "conv_last.4.bias"])
+        if use_softmax:
+            return _head(logits, segSize, True)
+        if arch == "ppm":
+            return logits if return_logits else F.log_softmax(logits, dim=1)
+        y = _cbr(conv_out[-2], sd, P + "cbr_deepsup.0", P + "cbr_deepsup.1", st, padding=1)
+        y = _dropout2d(y, dropout_p, st.training, masks.get("deepsup"))
+        logits_ds = F.conv2d(y, sd[P + "conv_last_deepsup.weight"], sd[P + "conv_last_deepsup.bias"])
+        if return_logits:
+            return logits, logits_ds
+        return F.log_softmax(logits, dim=1), F.log_softmax(logits_ds, dim=1)
+    if arch in ("c1", "c1_deepsup"):
+        x = _cbr(conv5, sd, P + "cbr.0", P + "cbr.1", st, padding=1)
+        logits = F.conv2d(x, sd[P + "conv_last.weight"], sd[P + "conv_last.bias"])
+        if use_softmax:
+            return _head(logits, segSize, True)
+        if arch == "c1":
+            return logits if return_logits else F.log_softmax(logits, dim=1)
+        y = _cbr(conv_out[-2], sd, P + "cbr_deepsup.0", P + "cbr_deepsup.1", st, padding=1)
+        logits_ds = F.conv2d(y, sd[P + "conv_last_deepsup.weight"], sd[P + "conv_last_deepsup.bias"])
+        if return_logits:
+            return logits, logits_ds
+        return F.log_softmax(logits, dim=1), F.log_softmax(logits_ds, dim=1)
+    if arch in ("upernet", "upernet_lite"):
+        H, W = conv5.shape[2:]
+        ppm_out = [conv5]
+        for i, scale in enumerate((1, 2, 3, 6)):
+            y = F.interpolate(F.adaptive_avg_pool2d(conv5, scale), (H, W), mode="bilinear", align_corners=False)
+            ppm_out.append(_cbr(y, sd, "%sppm_conv.%d.0" % (P, i), "%sppm_conv.%d.1" % (P, i), st))
+        f = _cbr(torch.cat(ppm_out, 1), sd, P + "ppm_last_conv.0", P + "ppm_last_conv.1", st, padding=1)
+        feats = [f]
+        for i in reversed(range(len(conv_out) - 1)):
+            lat = _cbr(conv_out[i], sd, "%sfpn_in.%d.0" % (P, i), "%sfpn_in.%d.1" % (P, i), st)
+            f = lat + F.interpolate(f, size=lat.shape[2:], mode="bilinear", align_corners=False)
+            feats.append(_cbr(f, sd, "%sfpn_out.%d.0.0" % (P, i), "%sfpn_out.%d.0.1" % (P, i), st, padding=1))
+        feats.reverse()
+        size = feats[0].shape[2:]
+        fusion = [feats[0]] + [F.interpolate(t, size, mode="bilinear", align_corners=False) for t in feats[1:]]
+        x = _cbr(torch.cat(fusion, 1), sd, P + "conv_last.0.0", P + "conv_last.0.1", st, padding=1)
+        logits = F.conv2d(x, sd[P + "conv_last.1.weight"], sd[P + "conv_last.1.bias"])
+        if use_softmax:
+            return _head(logits, segSize, True)
+        return logits if return_logits else F.log_softmax(logits, dim=1)
+    raise Exception("Architecture undefined!")
+
+
+# ----------------------------------------------------------------------------------------------
+# SegmentationModule.forward (reference models/models.py:29-47) and pixel_acc (:12-18)
+def pixel_acc(pred, label):
+    _, preds = torch.max(pred, dim=1)
+    valid = (label >= 0).long()
+    acc_sum = torch.sum(valid * (preds == label).long())
+    pixel_sum = torch.sum(valid)
+    return acc_sum.float() / (pixel_sum.float() + 1e-10)
+
+
+def segmentation_forward(feed, enc_sd, dec_sd, enc_arch, dec_arch, st, deep_sup_scale=None, segSize=None,
+                         dropout_p=0.1, masks=None, return_aux=False):
+    """Training branch (segSize None) -> (loss, acc); inference branch -> probabilities [N, C, *segSize]."""
+    feats = encoder_forward(feed["img_data"], enc_sd, enc_arch, st)
+    if segSize is not None:
+        return decoder_forward(feats, dec_sd, dec_arch, st, segSize=segSize, use_softmax=True, dropout_p=dropout_p)
+    out = decoder_forward(feats, dec_sd, dec_arch, st, dropout_p=dropout_p, masks=masks)
+    label = feed["seg_label"]
+    if deep_sup_scale is not None:
+        pred, pred_ds = out
+        loss = F.nll_loss(pred, label, ignore_index=-1) + F.nll_loss(pred_ds, label, ignore_index=-1) * deep_sup_scale
+    else:
+        pred = out
+        loss = F.nll_loss(pred, label, ignore_index=-1)
+    acc = pixel_acc(pred, label)
+    if return_aux:
+        return loss, acc, feats, out
+    return loss, acc
+
+
+# ----------------------------------------------------------------------------------------------
+# deterministic synthetic weights shared by reference / oracle / engine (see oracle/make_golden.py)
+def encoder_param_shapes(arch):
+    base, _ = parse_encoder_arch(arch)
+    block, counts = RESNET_LAYERS[base]
+    exp = 1 if block == "basic" else 4
+    shapes = {}
+
+    def bn(name, c):
+        shapes[name] = ("bn", c)
+
+    def conv(name, co, ci, k):
+        shapes[name] = ("conv", (co, ci, k, k))
+
+    conv("conv1", 64, 3, 3), bn("bn1", 64), conv("conv2", 64, 64, 3), bn("bn2", 64), conv("conv3", 128, 64, 3), bn("bn3", 128)
+    inplanes = 128
+    for li, (planes, nb) in enumerate(zip((64, 128, 256, 512), counts), start=1):
+        for bi in range(nb):
+            p = "layer%d.%d." % (li, bi)
+            if block == "basic":
+                conv(p + "conv1", planes, inplanes, 3), bn(p + "bn1", planes)
+                conv(p + "conv2", planes, planes, 3), bn(p + "bn2", planes)
+            else:
+                conv(p + "conv1", planes, inplanes, 1), bn(p + "bn1", planes)
+                conv(p + "conv2", planes, planes, 3), bn(p + "bn2", planes)
+                conv(p + "conv3", planes * 4, planes, 1), bn(p + "bn3", planes * 4)
+            if bi == 0 and (li > 1 or inplanes != planes * exp):
+                conv(p + "downsample.0", planes * exp, inplanes, 1), bn(p + "downsample.1", planes * exp)
+            inplanes = planes * exp
+    return shapes
+
+
+def decoder_param_shapes(arch, fc_dim, num_class=150, fpn_inplanes=(256, 512, 1024, 2048)):
+    arch = arch.lower()
+    shapes = {}
+
+    def bn(name, c):
+        shapes[name] = ("bn", c)
+
+    def conv(name, co, ci, k, bias=False):
+        shapes[name] = ("convb" if bias else "conv", (co, ci, k, k))
+
+    if arch in ("ppm", "ppm_deepsup"):
+        for i in range(4):
+            conv("ppm.%d.1" % i, 512, fc_dim, 1), bn("ppm.%d.2" % i, 512)
+        conv("conv_last.0", 512, fc_dim + 4 * 512, 3), bn("conv_last.1", 512)
+        conv("conv_last.4", num_class, 512, 1, bias=True)
+        if arch == "ppm_deepsup":
+            conv("cbr_deepsup.0", fc_dim // 4, fc_dim // 2, 3), bn("cbr_deepsup.1", fc_dim // 4)
+            conv("conv_last_deepsup", num_class, fc_dim // 4, 1, bias=True)
+    elif arch in ("c1", "c1_deepsup"):
+        conv("cbr.0", fc_dim // 4, fc_dim, 3), bn("cbr.1", fc_dim // 4)
+        conv("conv_last", num_class, fc_dim // 4, 1, bias=True)
+        if arch == "c1_deepsup":
+            conv("cbr_deepsup.0", fc_dim // 4, fc_dim // 2, 3), bn("cbr_deepsup.1", fc_dim // 4)
+            conv("conv_last_deepsup", num_class, fc_dim // 4, 1, bias=True)
+    elif arch in ("upernet", "upernet_lite"):
+        fpn_dim = 512 if arch == "upernet" else 256
+        for i in range(4):
+            conv("ppm_conv.%d.0" % i, 512, fc_dim, 1), bn("ppm_conv.%d.1" % i, 512)
+        conv("ppm_last_conv.0", fpn_dim, fc_dim + 4 * 512, 3), bn("ppm_last_conv.1", fpn_dim)
+        for i, c in enumerate(fpn_inplanes[:-1]):
+            conv("fpn_in.%d.0" % i, fpn_dim, c, 1), bn("fpn_in.%d.1" % i, fpn_dim)
+            conv("fpn_out.%d.0.0" % i, fpn_dim, fpn_dim, 3), bn("fpn_out.%d.0.1" % i, fpn_dim)
+        conv("conv_last.0.0", fpn_dim, 4 * fpn_dim, 3), bn("conv_last.0.1", fpn_dim)
+        conv("conv_last.1", num_class, fpn_dim, 1, bias=True)
+    else:
+        raise Exception("Architecture undefined!")
+    return shapes
+
+
+def synth_state_dict(shapes, seed):
+    """Deterministic weights for a {name: (kind, shape)} table: He-scaled convs, non-trivial BN affine + running stats.
+    Uses a private CPU torch.Generator so it is reproducible wherever the same torch build runs."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    sd = {}
+    for name in sorted(shapes):
+        kind, shp = shapes[name]
+        if kind in ("conv", "convb"):
+            co, ci, k, _ = shp
+            sd[name + ".weight"] = torch.randn(shp, generator=g) * math.sqrt(2.0 / (ci * k * k))
+            if kind == "convb":
+                sd[name + ".bias"] = torch.randn(co, generator=g) * 0.1
+        else:
+            c = shp
+            sd[name + ".weight"] = 0.5 + torch.rand(c, generator=g)
+            sd[name + ".bias"] = torch.randn(c, generator=g) * 0.1
+            sd[name + ".running_mean"] = torch.randn(c, generator=g) * 0.1
+            sd[name + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+            sd[name + ".num_batches_tracked"] = torch.zeros((), dtype=torch.long)
+            sd[name + "._tmp_running_mean"] = sd[name + ".running_mean"].clone()
+            sd[name + "._tmp_running_var"] = sd[name + ".running_var"].clone()
+            sd[name + "._running_iter"] = torch.ones(1)
+    return sd
+
+
+def synth_batch(n, h, w, label_stride, seed, num_class=150):
+    """Synthetic ADE20K-shaped batch: img ~ N(0,1), labels uniform in {-1..num_class-1}."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    img = torch.randn(n, 3, h, w, generator=g)
+    label = torch.randint(-1, num_class, (n, h // label_stride, w // label_stride), generator=g)
+    return {"img_data": img, "seg_label": label}
