@@ -52,29 +52,54 @@ void sseg_launch_count_reset(void);
 
 /* ---- convolution as implicit GEMM on tcgen05 tensor cores ------------------------------- */
 /*
- * out[n,h,w,co] = sum_{t<ntaps} sum_{ci} X[n, h+tap_dh[t], w+tap_dw[t], ci] * Wt[co][t][ci]   (+bias[co]) (+addend)
- *
- * X is the virtual channel concatenation of `nsrc` NHWC bf16 sources (same n,h,w; every c a multiple
- * of 64): the K loop walks the sources, so torch.cat (models/models.py:476) is never materialised.
- * Out-of-range taps read zeros (TMA out-of-bounds fill) = the zero padding of nn.Conv2d.
- * Stride-1 only: a stride-2 conv is expressed by its caller over space-to-depth planes.
+ * Geometry of the input side of a stride-1 convolution.
+ *   tap t reads X[n, h + tap_dh[t], w + tap_dw[t], :] ; out-of-range pixels read zeros (TMA out-of-bounds
+ *   fill = the zero padding of nn.Conv2d).
+ *   tap_src[t] == -1 : X is the virtual channel concatenation of all `nsrc` sources (same n,h,w; every c a
+ *                      multiple of 64), so torch.cat (models/models.py:476) is never materialised.
+ *   tap_src[t] == k  : tap t reads source k only (all sources then have equal c). This is how a stride-2
+ *                      convolution is expressed over the 4 space-to-depth parity planes of its input.
+ *   tap_koff[t]      : element offset of tap t's K segment inside one weight row.
+ */
+typedef struct {
+  int nsrc;
+  sseg_act_t srcs[SSEG_MAX_SRCS];
+  int ntaps;
+  int tap_dh[SSEG_MAX_TAPS];
+  int tap_dw[SSEG_MAX_TAPS];
+  int tap_src[SSEG_MAX_TAPS];
+  int tap_koff[SSEG_MAX_TAPS];
+} sseg_conv_geom_t;
+
+/*
+ * out[n,h,w,co] = sum_t sum_ci X_t[n, h+dh_t, w+dw_t, ci] * W[co][tap_koff[t] + ci]   (+bias[co]) (+addend)
  *
  * Replaces: nn.Conv2d forward for every 1x1 / 3x3 (dilation 1,2,4) convolution of the path
  *   (models/resnet.py:18-21,61-66,130-131; models/models.py:160-167,449,454-462) and, with the
  *   transposed/flipped weight, the data-gradient of the same convolutions (autograd of those sites).
  *
- * w_bf16   : [cout][ntaps][cin_total] bf16 (K-major rows)
+ * w_bf16   : [cout][w_ld] bf16 rows (K-major)
  * out      : NHWC, out_f32 ? float : bf16, pixel stride ld_out; columns [0, n_store) are written
- *            (n_store multiple of 8, cout <= n_store <= ld_out; columns >= cout receive 0 (+bias 0)).
+ *            (n_store multiple of 8, cout <= n_store <= ld_out; columns >= cout receive 0).
  * bias     : optional float[cout]
  * addend   : optional bf16 NHWC tensor with pixel stride ld_addend added before the store
  * stat_sum / stat_sqsum : optional float[cout]; per-channel sum and sum of squares of the fp32
- *            results are ATOMICALLY ADDED (caller zeroes them) — the first half of
+ *            results are ATOMICALLY ADDED (caller zeroes them) - the first half of
  *            SynchronizedBatchNorm2d.forward (lib/nn/modules/batchnorm.py:68-70).
  */
-int sseg_conv_igemm(const sseg_act_t* srcs, int nsrc, const void* w_bf16, int cout, int ntaps, const int* tap_dh,
-                    const int* tap_dw, void* out, int out_f32, int ld_out, int n_store, const float* bias,
-                    const void* addend, int ld_addend, float* stat_sum, float* stat_sqsum, sseg_stream_t stream);
+int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld, int cout, void* out, int out_f32,
+                    int ld_out, int n_store, const float* bias, const void* addend, int ld_addend, float* stat_sum,
+                    float* stat_sqsum, sseg_stream_t stream);
+
+/*
+ * Weight gradient of the same convolution (autograd of nn.Conv2d w.r.t. weight):
+ *   dw[co][tap_koff[t] + ci] += sum_{n,h,w} dy[n,h,w,co] * X_t[n, h+dh_t, w+dw_t, ci]
+ * GEMM with K = pixels (both operands MN-major in shared memory), split over pixels across CTAs and
+ * accumulated with fp32 atomics: the caller zeroes dw (float [cout][dw_ld]). dy may carry zero padding channels
+ * beyond cout (dy->c >= cout, multiple of 8); rows >= cout are not written.
+ */
+int sseg_conv_wgrad(const sseg_conv_geom_t* geom, const sseg_act_t* dy, int cout, float* dw, long dw_ld,
+                    sseg_stream_t stream);
 
 #ifdef __cplusplus
 }

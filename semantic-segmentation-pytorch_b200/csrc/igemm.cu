@@ -28,7 +28,8 @@ struct IgemmParams {
   int src_blk_end[SSEG_MAX_SRCS];  // cumulative count of 64-channel blocks
   int blocks_per_tap;
   int ntaps;
-  int tap_dh[SSEG_MAX_TAPS], tap_dw[SSEG_MAX_TAPS];
+  int tap_dh[SSEG_MAX_TAPS], tap_dw[SSEG_MAX_TAPS], tap_src[SSEG_MAX_TAPS], tap_koff[SSEG_MAX_TAPS];
+  int num_k_steps;
   int N, H, W;
   int BH, BW, bw_shift;
   int tiles_h, tiles_w, n_tiles;
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
   const int th = m_tile % p.tiles_h;
   const int img = m_tile / p.tiles_h;
   const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
-  const int num_k_steps = p.ntaps * p.blocks_per_tap;
+  const int num_k_steps = p.num_k_steps;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -101,17 +102,21 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
       int stage = 0, phase = 0;
       for (int t = 0; t < p.ntaps; ++t) {
         const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
-        int src = 0, blk_begin = 0;
-        for (int b = 0; b < p.blocks_per_tap; ++b) {
-          while (b >= p.src_blk_end[src]) {
-            blk_begin = p.src_blk_end[src];
-            ++src;
+        const int fixed_src = p.tap_src[t];
+        const int nblk = fixed_src >= 0 ? p.src_blk_end[0] : p.blocks_per_tap;
+        int src = fixed_src >= 0 ? fixed_src : 0, blk_begin = 0;
+        for (int b = 0; b < nblk; ++b) {
+          if (fixed_src < 0) {
+            while (b >= p.src_blk_end[src]) {
+              blk_begin = p.src_blk_end[src];
+              ++src;
+            }
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
-          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], (t * p.blocks_per_tap + b) * kBlockK, n0);
+          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], p.tap_koff[t] + b * kBlockK, n0);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -260,66 +265,90 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
   return check_cuda(cudaGetLastError(), "igemm_kernel launch");
 }
 
+// Fills the geometry-derived part of the parameters shared by the forward and weight-gradient kernels.
+// `box_pixels` = pixels per TMA box (128 for igemm M tiles, 64 for wgrad K steps).
+struct GeomHost {
+  int vn, vh, vw, BH, BW, bw_shift, tiles_h, tiles_w;
+  int cin_total, blocks_per_tap, chan_per_src;
+};
+
+static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, GeomHost* gh, CUtensorMap* tmA, int* src_blk_end,
+                      const char* who) {
+  SSEG_REQUIRE(g != nullptr, "%s: null geometry", who);
+  SSEG_REQUIRE(g->nsrc >= 1 && g->nsrc <= SSEG_MAX_SRCS, "%s: nsrc=%d out of range", who, g->nsrc);
+  SSEG_REQUIRE(g->ntaps >= 1 && g->ntaps <= SSEG_MAX_TAPS, "%s: ntaps=%d out of range", who, g->ntaps);
+  const int N = g->srcs[0].n, H = g->srcs[0].h, W = g->srcs[0].w;
+  SSEG_REQUIRE(N >= 1 && H >= 1 && W >= 1, "%s: empty activation", who);
+  bool pointwise = true, any_fixed = false;
+  for (int t = 0; t < g->ntaps; ++t) {
+    if (g->tap_dh[t] != 0 || g->tap_dw[t] != 0) pointwise = false;
+    if (g->tap_src[t] >= 0) any_fixed = true;
+    SSEG_REQUIRE(g->tap_src[t] >= -1 && g->tap_src[t] < g->nsrc, "%s: tap_src[%d]=%d out of range", who, t,
+                 g->tap_src[t]);
+    SSEG_REQUIRE(g->tap_koff[t] >= 0 && g->tap_koff[t] % 8 == 0, "%s: tap_koff[%d]=%d invalid", who, t,
+                 g->tap_koff[t]);
+  }
+  // 1x1 convs see the whole batch as one long row of pixels (no halo, no per-image tiling waste)
+  gh->vn = N, gh->vh = H, gh->vw = W;
+  if (pointwise) gh->vn = 1, gh->vh = 1, gh->vw = N * H * W;
+  int BW = box_pixels;
+  while (BW > 8 && BW / 2 >= gh->vw) BW /= 2;  // smallest power of two >= W, in [8, box_pixels]
+  gh->BW = BW, gh->BH = box_pixels / BW;
+  gh->bw_shift = 0;
+  while ((1 << gh->bw_shift) < BW) ++gh->bw_shift;
+  gh->tiles_h = ceil_div(gh->vh, gh->BH), gh->tiles_w = ceil_div(gh->vw, BW);
+  int cin_total = 0;
+  for (int s = 0; s < g->nsrc; ++s) {
+    const sseg_act_t& a = g->srcs[s];
+    SSEG_REQUIRE(a.n == N && a.h == H && a.w == W, "%s: source %d shape mismatch", who, s);
+    SSEG_REQUIRE(a.c % kBlockK == 0 && a.c > 0, "%s: source %d channels %d not a multiple of 64", who, s, a.c);
+    SSEG_REQUIRE(a.ld % 8 == 0 && a.ld >= a.c, "%s: source %d ld %d invalid", who, s, a.ld);
+    SSEG_REQUIRE(!any_fixed || a.c == g->srcs[0].c, "%s: per-tap sources must have equal channels", who);
+    int rc = get_tmap_act(&tmA[s], a.ptr, 2, gh->vn, gh->vh, gh->vw, a.c, a.ld, kBlockK, BW, gh->BH);
+    if (rc) return rc;
+    cin_total += a.c;
+    src_blk_end[s] = cin_total / kBlockK;
+  }
+  gh->cin_total = cin_total;
+  gh->blocks_per_tap = cin_total / kBlockK;
+  gh->chan_per_src = g->srcs[0].c;
+  return 0;
+}
+
 }  // namespace sseg
 
 using namespace sseg;
 
-extern "C" int sseg_conv_igemm(const sseg_act_t* srcs, int nsrc, const void* w_bf16, int cout, int ntaps,
-                               const int* tap_dh, const int* tap_dw, void* out, int out_f32, int ld_out, int n_store,
-                               const float* bias, const void* addend, int ld_addend, float* stat_sum,
-                               float* stat_sqsum, sseg_stream_t stream_) {
+extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, void* out,
+                               int out_f32, int ld_out, int n_store, const float* bias, const void* addend,
+                               int ld_addend, float* stat_sum, float* stat_sqsum, sseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SSEG_REQUIRE(nsrc >= 1 && nsrc <= SSEG_MAX_SRCS, "sseg_conv_igemm: nsrc=%d out of range", nsrc);
-  SSEG_REQUIRE(ntaps >= 1 && ntaps <= SSEG_MAX_TAPS, "sseg_conv_igemm: ntaps=%d out of range", ntaps);
   SSEG_REQUIRE(cout >= 1 && n_store >= cout && n_store % 8 == 0 && n_store <= ld_out,
                "sseg_conv_igemm: need cout <= n_store (mult of 8) <= ld_out, got %d %d %d", cout, n_store, ld_out);
   SSEG_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "sseg_conv_igemm: stat_sum/stat_sqsum must pair");
-  const int N = srcs[0].n, H = srcs[0].h, W = srcs[0].w;
-  SSEG_REQUIRE(N >= 1 && H >= 1 && W >= 1, "sseg_conv_igemm: empty activation");
-
   IgemmParams p;
   memset(&p, 0, sizeof(p));
-  // M tile = BH x BW pixels of one image. 1x1 convs see the batch as one long row of pixels.
-  int vn = N, vh = H, vw = W;
-  const bool pointwise = (ntaps == 1 && tap_dh[0] == 0 && tap_dw[0] == 0);
-  if (pointwise) {
-    bool dense = true;  // all sources must be plain [pixels][ld] views (always true for NHWC)
-    if (dense) vn = 1, vh = 1, vw = N * H * W;
+  GeomHost gh;
+  int rc = setup_geom(g, kBlockM, &gh, p.tmA, p.src_blk_end, "sseg_conv_igemm");
+  if (rc) return rc;
+  p.BH = gh.BH, p.BW = gh.BW, p.bw_shift = gh.bw_shift;
+  p.N = gh.vn, p.H = gh.vh, p.W = gh.vw;
+  p.tiles_h = gh.tiles_h, p.tiles_w = gh.tiles_w;
+  p.nsrc = g->nsrc;
+  p.blocks_per_tap = gh.blocks_per_tap;
+  p.ntaps = g->ntaps;
+  p.num_k_steps = 0;
+  for (int t = 0; t < g->ntaps; ++t) {
+    p.tap_dh[t] = g->tap_dh[t], p.tap_dw[t] = g->tap_dw[t], p.tap_src[t] = g->tap_src[t];
+    p.tap_koff[t] = g->tap_koff[t];
+    const int span = g->tap_src[t] >= 0 ? gh.chan_per_src : gh.cin_total;
+    SSEG_REQUIRE(g->tap_koff[t] + span <= w_ld, "sseg_conv_igemm: tap %d K range exceeds w_ld", t);
+    p.num_k_steps += span / kBlockK;
   }
-  int BW = 128;
-  while (BW > 8 && BW / 2 >= vw) BW /= 2;  // smallest power of two >= W, capped to [8,128]
-  if (vw >= 128) BW = 128;
-  int BH = kBlockM / BW;
-  p.BH = BH, p.BW = BW;
-  p.bw_shift = 0;
-  while ((1 << p.bw_shift) < BW) ++p.bw_shift;
-  p.N = vn, p.H = vh, p.W = vw;
-  p.tiles_h = ceil_div(vh, BH), p.tiles_w = ceil_div(vw, BW);
-
-  int cin_total = 0;
-  for (int s = 0; s < nsrc; ++s) {
-    SSEG_REQUIRE(srcs[s].n == N && srcs[s].h == H && srcs[s].w == W, "sseg_conv_igemm: source %d shape mismatch", s);
-    SSEG_REQUIRE(srcs[s].c % kBlockK == 0 && srcs[s].c > 0, "sseg_conv_igemm: source %d channels %d not a multiple of 64",
-                 s, srcs[s].c);
-    SSEG_REQUIRE(srcs[s].ld % 8 == 0 && srcs[s].ld >= srcs[s].c, "sseg_conv_igemm: source %d ld %d invalid", s,
-                 srcs[s].ld);
-    int rc = get_tmap_act(&p.tmA[s], srcs[s].ptr, 2, vn, vh, vw, srcs[s].c, srcs[s].ld, kBlockK, BW, BH);
-    if (rc) return rc;
-    cin_total += srcs[s].c;
-    p.src_blk_end[s] = cin_total / kBlockK;
-  }
-  p.nsrc = nsrc;
-  p.blocks_per_tap = cin_total / kBlockK;
-  p.ntaps = ntaps;
-  for (int t = 0; t < ntaps; ++t) p.tap_dh[t] = tap_dh[t], p.tap_dw[t] = tap_dw[t];
-
   const int block_n = cout <= 64 ? 64 : 128;
   p.n_tiles = ceil_div(n_store, block_n);
-  {
-    const long K = static_cast<long>(ntaps) * cin_total;
-    int rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, K, K, kBlockK, block_n);
-    if (rc) return rc;
-  }
+  rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, block_n);
+  if (rc) return rc;
   p.out = out, p.out_f32 = out_f32, p.ld_out = ld_out, p.n_store = n_store, p.cout = cout;
   p.bias = bias;
   p.addend = static_cast<const __nv_bfloat16*>(addend);
@@ -329,8 +358,246 @@ extern "C" int sseg_conv_igemm(const sseg_act_t* srcs, int nsrc, const void* w_b
                "sseg_conv_igemm: output not 16B aligned");
   SSEG_REQUIRE(addend == nullptr || ((reinterpret_cast<uintptr_t>(addend) & 15) == 0 && ld_addend % 8 == 0),
                "sseg_conv_igemm: addend not 16B aligned");
-
-  const int grid = vn * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int grid = gh.vn * p.tiles_h * p.tiles_w * p.n_tiles;
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);
+}
+
+// =====================================================================================================
+// Weight gradient:  dW[co][koff_t + ci] += sum_pixels dY[pixel, co] * X_t[pixel shifted by tap t, ci]
+//
+//   GEMM with M = 128 output channels (co), N = BLOCK_N input channels (ci) of ONE tap, K = pixels.
+//   Both operands come straight from the NHWC tensors as TMA boxes of (64 channels x 64 pixels): the channel
+//   (M / N) index is the contiguous one, i.e. both are "MN-major" UMMA operands:
+//       canonical SWIZZLE_128B MN-major layout ((8,m),(8,k)) : ((1,LBO),(8,SBO))   [units of 16 bytes]
+//       -> 8 pixels x 128 B swizzle atoms, SBO = 1024 B between 8-pixel groups, LBO = 8 KB between 64-channel boxes.
+//   One K step = 64 pixels = 4 UMMA instructions (K=16 pixels each, +2 KB start-address advance).
+//   K is split across CTAs (blockIdx / num_tiles = split index); partial sums land with fp32 vector atomics.
+// =====================================================================================================
+namespace sseg {
+
+constexpr int kWgKPix = 64;                       // pixels per K step (one TMA box)
+constexpr int kWgBoxBytes = kWgKPix * 64 * 2;     // 8 KB: 64 pixels x 64 channels bf16
+
+struct WgradParams {
+  CUtensorMap tmX[SSEG_MAX_SRCS];
+  CUtensorMap tmDY;
+  int nsrc;
+  int src_blk_end[SSEG_MAX_SRCS];
+  int ntaps;
+  int tap_dh[SSEG_MAX_TAPS], tap_dw[SSEG_MAX_TAPS], tap_src[SSEG_MAX_TAPS], tap_koff[SSEG_MAX_TAPS];
+  int ci_tiles_per_tap;  // number of BLOCK_N-wide ci tiles per tap
+  int m_tiles;           // ceil(cout / 128)
+  int num_tiles;         // m_tiles * ntaps * ci_tiles_per_tap
+  int BH, BW, tiles_h, tiles_w;
+  int total_boxes, boxes_per_split;
+  int cout, ci_span;     // valid co rows; valid ci per tap
+  float* dw;
+  long dw_ld;
+};
+
+template <int BLOCK_N, int STAGES>
+struct WgradSmem {
+  static constexpr int kABytes_ = 2 * kWgBoxBytes;                 // 128 co
+  static constexpr int kBBytes_ = (BLOCK_N / 64) * kWgBoxBytes;    // BLOCK_N ci
+  static constexpr int kStageBytes = kABytes_ + kBBytes_;
+  static constexpr int kBarOff = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kDynBytes = kTotal + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using L = WgradSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int split = blockIdx.x / p.num_tiles;
+  int tile = blockIdx.x % p.num_tiles;
+  const int ci_tile = tile % p.ci_tiles_per_tap;
+  tile /= p.ci_tiles_per_tap;
+  const int tap = tile % p.ntaps;
+  const int m_tile = tile / p.ntaps;
+  const int co0 = m_tile * 128, ci0 = ci_tile * BLOCK_N;
+  const int box_begin = split * p.boxes_per_split;
+  const int box_end = min(box_begin + p.boxes_per_split, p.total_boxes);
+  const int num_k_steps = box_end - box_begin;  // host guarantees >= 1
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmX[s]);
+    tma_prefetch_desc(&p.tmDY);
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // resolve, once, which source / channel offset each 64-channel B box comes from
+      int bsrc[BLOCK_N / 64], bchan[BLOCK_N / 64];
+#pragma unroll
+      for (int j = 0; j < BLOCK_N / 64; ++j) {
+        const int blk = ci0 / 64 + j;
+        if (p.tap_src[tap] >= 0) {
+          bsrc[j] = p.tap_src[tap];
+          bchan[j] = blk * 64;
+        } else {
+          int s = 0, begin = 0;
+          while (s + 1 < p.nsrc && blk >= p.src_blk_end[s]) begin = p.src_blk_end[s], ++s;
+          bsrc[j] = s;
+          bchan[j] = (blk - begin) * 64;  // beyond the last source -> out of bounds -> zeros
+        }
+      }
+      const int dh = p.tap_dh[tap], dw = p.tap_dw[tap];
+      int stage = 0, phase = 0;
+      for (int box = box_begin; box < box_end; ++box) {
+        int r = box;
+        const int tw = r % p.tiles_w;
+        r /= p.tiles_w;
+        const int th = r % p.tiles_h;
+        const int img = r / p.tiles_h;
+        const int h0 = th * p.BH, w0 = tw * p.BW;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::kStageBytes;
+        uint8_t* sb = sa + L::kABytes_;
+        mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+        tma_load_4d(sa, &p.tmDY, &full_bar[stage], co0, w0, h0, img);
+        tma_load_4d(sa + kWgBoxBytes, &p.tmDY, &full_bar[stage], co0 + 64, w0, h0, img);
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 64; ++j)
+          tma_load_4d(sb + j * kWgBoxBytes, &p.tmX[bsrc[j]], &full_bar[stage], bchan[j], w0 + dw, h0 + dh, img);
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1, 128, BLOCK_N);
+      int stage = 0, phase = 0;
+      for (int ks = 0; ks < num_k_steps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t b_addr = a_addr + L::kABytes_;
+#pragma unroll
+        for (int k = 0; k < kWgKPix / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (ks | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+      umma_commit(tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    const int quarter = warp & 3;
+    const int co = co0 + quarter * 32 + lane;
+    const bool valid = co < p.cout;
+    float* drow = p.dw + static_cast<size_t>(co) * p.dw_ld + p.tap_koff[tap] + ci0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      uint32_t raw[32];
+      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + chunk * 32, raw);
+      tmem_ld_wait();
+      if (valid) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          if (ci0 + chunk * 32 + g * 4 < p.ci_span) {
+            float4 f = make_float4(__uint_as_float(raw[g * 4]), __uint_as_float(raw[g * 4 + 1]),
+                                   __uint_as_float(raw[g * 4 + 2]), __uint_as_float(raw[g * 4 + 3]));
+            atomicAdd(reinterpret_cast<float4*>(drow + chunk * 32 + g * 4), f);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<BLOCK_N>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_wgrad(const WgradParams& p, int grid, cudaStream_t stream) {
+  using L = WgradSmem<BLOCK_N, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  SSEG_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    SSEG_CUDA(cudaFuncSetAttribute(wgrad_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   L::kDynBytes));
+    configured[dev] = true;
+  }
+  wgrad_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kDynBytes, stream>>>(p);
+  count_launch(1);
+  return check_cuda(cudaGetLastError(), "wgrad_kernel launch");
+}
+
+}  // namespace sseg
+
+extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, int cout, float* dw, long dw_ld,
+                               sseg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  SSEG_REQUIRE(dy != nullptr && dw != nullptr, "sseg_conv_wgrad: null argument");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  GeomHost gh;
+  int rc = setup_geom(g, kWgKPix, &gh, p.tmX, p.src_blk_end, "sseg_conv_wgrad");
+  if (rc) return rc;
+  SSEG_REQUIRE(dy->n == g->srcs[0].n && dy->h == g->srcs[0].h && dy->w == g->srcs[0].w,
+               "sseg_conv_wgrad: dy shape mismatch");
+  SSEG_REQUIRE(dy->c % 8 == 0 && dy->ld % 8 == 0 && dy->ld >= dy->c, "sseg_conv_wgrad: dy channels/ld must be x8");
+  SSEG_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && dw_ld % 4 == 0, "sseg_conv_wgrad: dw not 16B aligned");
+  rc = get_tmap_act(&p.tmDY, dy->ptr, 2, gh.vn, gh.vh, gh.vw, dy->c, dy->ld, 64, gh.BW, gh.BH);
+  if (rc) return rc;
+  p.nsrc = g->nsrc;
+  p.ntaps = g->ntaps;
+  bool fixed = g->tap_src[0] >= 0;
+  p.ci_span = fixed ? gh.chan_per_src : gh.cin_total;
+  for (int t = 0; t < g->ntaps; ++t) {
+    p.tap_dh[t] = g->tap_dh[t], p.tap_dw[t] = g->tap_dw[t], p.tap_src[t] = g->tap_src[t];
+    p.tap_koff[t] = g->tap_koff[t];
+    SSEG_REQUIRE((g->tap_src[t] >= 0) == fixed, "sseg_conv_wgrad: taps must be all concat or all per-plane");
+    SSEG_REQUIRE(g->tap_koff[t] % 4 == 0 && g->tap_koff[t] + p.ci_span <= dw_ld, "sseg_conv_wgrad: tap %d K range", t);
+  }
+  const int block_n = (p.ci_span % 128 == 0) ? 128 : 64;
+  p.ci_tiles_per_tap = p.ci_span / block_n;
+  SSEG_REQUIRE(cout >= 1 && cout <= dy->c, "sseg_conv_wgrad: cout %d vs dy channels %d", cout, dy->c);
+  p.cout = cout;
+  p.m_tiles = ceil_div(p.cout, 128);
+  p.num_tiles = p.m_tiles * p.ntaps * p.ci_tiles_per_tap;
+  p.BH = gh.BH, p.BW = gh.BW, p.tiles_h = gh.tiles_h, p.tiles_w = gh.tiles_w;
+  p.total_boxes = gh.vn * gh.tiles_h * gh.tiles_w;
+  // split K (pixels) so that the grid is a few waves of 148 SMs x 2 resident CTAs, but keep >= 4 K steps per CTA
+  int splits = ceil_div(592, p.num_tiles);
+  splits = max(1, min(splits, ceil_div(p.total_boxes, 4)));
+  p.boxes_per_split = ceil_div(p.total_boxes, splits);
+  splits = ceil_div(p.total_boxes, p.boxes_per_split);
+  p.dw = dw, p.dw_ld = dw_ld;
+  const int grid = p.num_tiles * splits;
+  if (block_n == 64) return launch_wgrad<64, 4>(p, grid, stream);
+  return launch_wgrad<128, 3>(p, grid, stream);
 }

@@ -23,6 +23,12 @@ class Act(Structure):
     _fields_ = [("ptr", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int), ("c", c_int), ("ld", c_int)]
 
 
+class Geom(Structure):
+    """sseg_conv_geom_t: input-side geometry of a stride-1 convolution (sources, taps)."""
+    _fields_ = [("nsrc", c_int), ("srcs", Act * MAX_SRCS), ("ntaps", c_int), ("tap_dh", c_int * MAX_TAPS),
+                ("tap_dw", c_int * MAX_TAPS), ("tap_src", c_int * MAX_TAPS), ("tap_koff", c_int * MAX_TAPS)]
+
+
 _lib = None
 
 
@@ -65,8 +71,8 @@ def ptr(t):
 _p = c_void_p
 _ip = POINTER(c_int)
 _SIGNATURES = {
-    "sseg_conv_igemm": [POINTER(Act), c_int, _p, c_int, c_int, _ip, _ip, _p, c_int, c_int, c_int, _p, _p, c_int, _p,
-                        _p, _p],
+    "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, _p, c_int, c_int, c_int, _p, _p, c_int, _p, _p, _p],
+    "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
 }
 
 EXPORTED_SYMBOLS = ["sseg_last_error", "sseg_version", "sseg_launch_count", "sseg_launch_count_reset"] + list(

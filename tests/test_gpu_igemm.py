@@ -36,9 +36,9 @@ def _run(n, h, w_, cins, cout, k, d, out_f32=False, bias=False, addend=False, st
         ref = ref + add[..., :cout].float()
     ssum = torch.zeros(cout, device="cuda") if stats else None
     ssq = torch.zeros(cout, device="cuda") if stats else None
-    w_ohwi = wt.permute(0, 2, 3, 1).contiguous()
-    ops.conv_igemm(xs, w_ohwi, cout, ops.conv_taps(k, d), out, n_store=n_store, bias=b, addend=add, stat_sum=ssum,
-                   stat_sqsum=ssq)
+    w_ohwi = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    ops.conv_igemm(ops.make_geom(xs, ops.conv_taps(k, d)), w_ohwi, cout, out, n_store=n_store, bias=b, addend=add,
+                   stat_sum=ssum, stat_sqsum=ssq)
     torch.cuda.synchronize()
     got = out[..., :cout].float()
     scale = ref.abs().max().item()
@@ -95,3 +95,50 @@ def test_ragged_spatial():
 
 def test_addend():
     _run(2, 64, 64, [128], 256, 3, 1, addend=True)
+
+
+# ------------------------------------------------------------------ weight gradient (MN-major operands, split-K)
+def _run_wgrad(n, h, w_, cins, cout, k, d, cpad=0, seed=0):
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    xs = [torch.randn(n, h, w_, c, device="cuda", generator=g).bfloat16() for c in cins]
+    cin = sum(cins)
+    dy = torch.zeros(n, h, w_, cout + cpad, device="cuda", dtype=torch.bfloat16)
+    dy[..., :cout] = (torch.randn(n, h, w_, cout, device="cuda", generator=g) * 0.1).bfloat16()
+    x = torch.cat([t.float() for t in xs], dim=3).permute(0, 3, 1, 2).contiguous().requires_grad_(False)
+    wt = torch.zeros(cout, cin, k, k, device="cuda", requires_grad=True)
+    y = F.conv2d(x, wt, padding=d * (k // 2), dilation=d)
+    (ref,) = torch.autograd.grad(y, wt, dy[..., :cout].float().permute(0, 3, 1, 2))
+    ref = ref.permute(0, 2, 3, 1).reshape(cout, -1)
+    dw = torch.zeros(cout, k * k * cin, device="cuda")
+    ops.conv_wgrad(ops.make_geom(xs, ops.conv_taps(k, d)), dy, cout, dw)
+    torch.cuda.synchronize()
+    scale = ref.abs().max().item()
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-4 * scale + 1e-5, "wgrad max err %g (scale %g)" % (err, scale)
+
+
+def test_wgrad_pointwise():
+    _run_wgrad(2, 64, 64, [256], 128, 1, 1)
+
+
+@pytest.mark.parametrize("d", [1, 2, 4])
+def test_wgrad_3x3(d):
+    _run_wgrad(2, 64, 64, [128], 256, 3, d)
+
+
+def test_wgrad_cout64_cin64():
+    _run_wgrad(1, 128, 128, [64], 64, 3, 1)
+
+
+def test_wgrad_concat():
+    _run_wgrad(2, 32, 32, [256, 128, 128], 128, 3, 1)
+
+
+def test_wgrad_classifier_padded():
+    _run_wgrad(2, 64, 64, [512], 150, 1, 1, cpad=10)
+
+
+def test_wgrad_ragged():
+    _run_wgrad(2, 38, 50, [64], 128, 3, 2)
+    _run_wgrad(3, 6, 6, [128], 64, 3, 1)
