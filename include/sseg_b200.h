@@ -35,11 +35,16 @@ extern "C" {
 
 typedef void* sseg_stream_t; /* cudaStream_t */
 
-/* NHWC activation view. */
+/* NHWC activation view: element (n,h,w,c) lives at ptr + n*img_stride + h*row_stride + w*ld + c (in elements).
+ * Dense tensors have row_stride = w*ld and img_stride = h*row_stride; a strided view (e.g. the parity plane
+ * x[:, 1::2, 0::2, :] of a stride-2 convolution's input, or a channel slice of a wider buffer) is legal wherever
+ * a view is accepted. */
 typedef struct {
-  void* ptr; /* device pointer to element (n=0,h=0,w=0,c=0) */
+  void* ptr;
   int n, h, w, c;
-  int ld; /* elements between consecutive pixels */
+  int ld;          /* elements between consecutive pixels of a row */
+  long row_stride; /* elements between consecutive rows */
+  long img_stride; /* elements between consecutive images */
 } sseg_act_t;
 
 /* ---- library ---------------------------------------------------------------------------- */
@@ -79,17 +84,17 @@ typedef struct {
  *   transposed/flipped weight, the data-gradient of the same convolutions (autograd of those sites).
  *
  * w_bf16   : [cout][w_ld] bf16 rows (K-major)
- * out      : NHWC, out_f32 ? float : bf16, pixel stride ld_out; columns [0, n_store) are written
- *            (n_store multiple of 8, cout <= n_store <= ld_out; columns >= cout receive 0).
+ * out      : NHWC view (same n,h,w as the sources), out_f32 ? float : bf16; channels [0, out->c) are written
+ *            (out->c multiple of 8, cout <= out->c <= out->ld; channels >= cout receive 0).
  * bias     : optional float[cout]
- * addend   : optional bf16 NHWC tensor with pixel stride ld_addend added before the store
+ * addend   : optional bf16 NHWC view (c >= out->c) added before the store (may alias out)
  * stat_sum / stat_sqsum : optional float[cout]; per-channel sum and sum of squares of the fp32
  *            results are ATOMICALLY ADDED (caller zeroes them) - the first half of
  *            SynchronizedBatchNorm2d.forward (lib/nn/modules/batchnorm.py:68-70).
  */
-int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld, int cout, void* out, int out_f32,
-                    int ld_out, int n_store, const float* bias, const void* addend, int ld_addend, float* stat_sum,
-                    float* stat_sqsum, sseg_stream_t stream);
+int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
+                    int out_f32, const float* bias, const sseg_act_t* addend, float* stat_sum, float* stat_sqsum,
+                    sseg_stream_t stream);
 
 /*
  * Weight gradient of the same convolution (autograd of nn.Conv2d w.r.t. weight):
@@ -100,6 +105,89 @@ int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld,
  */
 int sseg_conv_wgrad(const sseg_conv_geom_t* geom, const sseg_act_t* dy, int cout, float* dw, long dw_ld,
                     sseg_stream_t stream);
+
+
+/* ---- weights ---------------------------------------------------------------------------- */
+/* fp32 OIHW master weight (nn.Conv2d.weight, T = kh*kw) -> bf16 GEMM operands:
+ *   w_fwd   [O][fwd_ld]    : w_fwd[o][t*I + i]          (forward; K ordered tap-major like sseg_conv_geom_t)
+ *   w_dgrad [I][dgrad_ld]  : w_dgrad[i][t*o_pad + o]    (data gradient; o_pad = O rounded up to 64, the caller
+ *                                                         zero-fills the buffer once so padding stays 0)
+ * Either output may be NULL. */
+int sseg_prep_conv_weight(const float* w_oihw, int O, int I, int T, void* w_fwd, long fwd_ld, void* w_dgrad,
+                          long dgrad_ld, int o_pad, sseg_stream_t stream);
+/* fp32 [O][g_ld] tap-major weight gradient (sseg_conv_wgrad output) -> fp32 OIHW: out (=|+=) scale * g. */
+int sseg_grad_to_oihw(const float* g, long g_ld, int O, int I, int T, float* out, float scale, int accumulate,
+                      sseg_stream_t stream);
+
+/* ---- stem convolution (Cin = 3, 3x3, stride 2, pad 1, Cout = 64): models/resnet.py:100 -------------- */
+/* img: fp32 NCHW [N,3,H,W]; w: fp32 OIHW [64,3,3,3]; out: bf16 NHWC [N,Ho,Wo,64] dense; optional BN statistics. */
+int sseg_stem_conv_fwd(const float* img, int N, int H, int W, const float* w, void* out, float* stat_sum,
+                       float* stat_sqsum, sseg_stream_t stream);
+/* dw (fp32 OIHW [64,3,3,3], caller-zeroed) += weight gradient; dy bf16 NHWC [N,Ho,Wo,64] dense. */
+int sseg_stem_conv_wgrad(const float* img, int N, int H, int W, const void* dy, float* dw, sseg_stream_t stream);
+
+/* ---- batch normalisation: lib/nn/modules/batchnorm.py:56-139 ---------------------------- */
+#define SSEG_BN_TRAIN 0      /* F.batch_norm training branch (:58-61): var + eps, torch running-stat update      */
+#define SSEG_BN_TRAIN_SYNC 1 /* data-parallel branch (:63-81, :123-139): clamp(var, eps), accumulator running stats */
+#define SSEG_BN_EVAL 2       /* running statistics (:58-61 with training=False)                                  */
+/* (sum, sqsum, count) -> mean, inv_std, scale = gamma*inv_std, shift = beta - mean*scale, + running-stat update.
+ * count: *count_dev if non-NULL (after a cross-rank all-reduce), else count_host. */
+int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_dev, float count_host, const float* gamma,
+                     const float* beta, float eps, float momentum, int mode, int update_running, float* running_mean,
+                     float* running_var, float* tmp_running_mean, float* tmp_running_var, float* running_iter,
+                     float* mean_out, float* invstd_out, float* scale, float* shift, int C, sseg_stream_t stream);
+/* out = [relu](y*scale + shift + res') * chanmul[n][c];  res' = res (*rscale + rshift if given).
+ * Fuses BN-apply, the residual add of Bottleneck/BasicBlock (models/resnet.py:45-53,84-92), ReLU and the
+ * Dropout2d channel mask (models/models.py:460). y/res/out: bf16 [P][ld]. chanmul: float [N][C] or NULL. */
+int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
+                  const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
+                  long pix_per_img, int C, int relu, sseg_stream_t stream);
+/* backward pass 1: s1[c] += sum g', s2[c] += sum g' * xhat, g' = g * chanmul * [a > 0] (a = saved output, NULL: no ReLU) */
+int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
+                       const float* invstd, const float* chanmul, float* s1, float* s2, long P, long pix_per_img, int C,
+                       sseg_stream_t stream);
+/* backward pass 2: dy = scale*(g' - s1/M - xhat*s2/M) (eval_mode: dy = scale*g'); dres (optional) = g' */
+int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
+                      const float* invstd, const float* scale, const float* chanmul, const float* s1, const float* s2,
+                      const float* count_dev, float count_host, void* dy, long dy_ld, void* dres, long dres_ld, long P,
+                      long pix_per_img, int C, int eval_mode, sseg_stream_t stream);
+
+/* ---- pooling / resize ------------------------------------------------------------------- */
+/* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109). Dense bf16 NHWC; idx (1 byte / output element) feeds the backward. */
+int sseg_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, void* idx, sseg_stream_t stream);
+int sseg_maxpool_bwd(const void* dout, const void* idx, void* dx, int N, int H, int W, int C, sseg_stream_t stream);
+/* nn.AdaptiveAvgPool2d(S) (models/models.py:447): x bf16 [N,H,W,C] (pixel stride x_ld) -> out dense [N,S,S,C]. */
+int sseg_avgpool_fwd(const void* x, long x_ld, int N, int H, int W, int C, int S, void* out, sseg_stream_t stream);
+/* dx = base + sum_k avgpool_backward_k(dpool[k]) for up to 4 scales in one pass (base may be NULL). */
+int sseg_avgpool_bwd(const void* base, long base_ld, const void* const* dpool, const int* scales, int nscales, void* dx,
+                     long dx_ld, int N, int H, int W, int C, sseg_stream_t stream);
+/* F.interpolate(mode='bilinear', align_corners=False) (models/models.py:472-475) and its adjoint (gather form). */
+int sseg_bilinear_fwd(const void* x, long x_ld, int N, int Hi, int Wi, int C, void* out, long out_ld, int Ho, int Wo,
+                      sseg_stream_t stream);
+int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int C, void* dx, long dx_ld, int Hi, int Wi,
+                      int accumulate, sseg_stream_t stream);
+
+/* ---- loss ------------------------------------------------------------------------------- */
+/* F.log_softmax + nn.NLLLoss(ignore_index=-1) + pixel_acc (models/models.py:12-18,37-42,492-493; train.py:154).
+ * logits fp32 [P][ld]; label int64 [P]; lse float [P] out; accum float[3] (caller-zeroed):
+ *   accum[0] += sum_valid(lse - logit[label]); accum[1] += #valid; accum[2] += #(valid and argmax == label). */
+int sseg_softmax_nll_fwd(const float* logits, long ld, int C, const long long* label, long P, float* lse, float* accum,
+                         sseg_stream_t stream);
+/* out[0] = main[0]/main[1] + ds_scale * ds[0]/ds[1] (ds may be NULL); out[1] = main[2]/(main[1] + 1e-10). */
+int sseg_nll_finalize(const float* accum_main, const float* accum_ds, float ds_scale, float* out, sseg_stream_t stream);
+/* dlogits bf16 [P][ld_out]: weight/accum[1] * (softmax - onehot) on valid pixels, else 0; columns [C, c_store) = 0. */
+int sseg_softmax_nll_bwd(const float* logits, long ld, int C, const long long* label, const float* lse, const float* accum,
+                         float weight, long P, void* dlogits, long ld_out, int c_store, sseg_stream_t stream);
+/* out[c] += sum_p x[p][c]  (bias gradients); x bf16 [P][ld]. */
+int sseg_colsum(const void* x, long ld, long P, int C, float* out, sseg_stream_t stream);
+/* Inference head (models/models.py:480-484; eval.py:71-72): bilinear-upsample fp32 NHWC logits [N,Hi,Wi,ld] to
+ * (Ho,Wo), softmax over C, write fp32 NCHW probs (= or +=) weight * softmax. */
+int sseg_upsample_softmax(const float* logits, long ld, int N, int Hi, int Wi, int C, float* probs, int Ho, int Wo,
+                          float weight, int accumulate, sseg_stream_t stream);
+
+/* ---- layout ----------------------------------------------------------------------------- */
+int sseg_nhwc_bf16_to_nchw_f32(const void* x, long ld, int N, int H, int W, int C, float* out, sseg_stream_t stream);
+int sseg_nchw_f32_to_nhwc_bf16(const float* x, int N, int H, int W, int C, void* out, long ld, sseg_stream_t stream);
 
 #ifdef __cplusplus
 }

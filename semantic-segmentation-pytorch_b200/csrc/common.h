@@ -32,8 +32,11 @@ void count_launch(int n);
 // TMA tensor-map construction (cuTensorMapEncodeTiled through the runtime's driver entry point,
 // so the library does not link libcuda). Maps are cached by their full geometry.
 //   rank-4 bf16/f32 activation view (C, W, H, N) with 128B swizzle, box (box_c, box_w, box_h, 1)
-int get_tmap_act(CUtensorMap* out, const void* ptr, int elem_bytes, int n, int h, int w, int c, int ld,
-                 int box_c, int box_w, int box_h);
+int get_tmap_act(CUtensorMap* out, const void* ptr, int elem_bytes, int n, int h, int w, int c, long ld,
+                 long row_stride, long img_stride, int box_c, int box_w, int box_h);
+inline bool act_is_dense(const sseg_act_t& a) {
+  return a.row_stride == (long)a.w * a.ld && a.img_stride == (long)a.h * a.row_stride;
+}
 //   rank-2 matrix [rows][cols] (cols contiguous) with 128B swizzle, box (box_cols, box_rows)
 int get_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long rows, long cols, long ld, int box_cols,
                 int box_rows);

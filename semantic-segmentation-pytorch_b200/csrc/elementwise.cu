@@ -1,0 +1,1056 @@
+// HBM-bound kernels of the path: batch-norm (finalize / apply / backward), max-pool, adaptive average pool,
+// bilinear resize, the stem convolution (Cin = 3), weight re-layout, log-softmax + NLL loss, column sums.
+// All activations are NHWC bf16 (C contiguous) accessed with 16-byte vectors (8 channels per thread).
+#include "common.h"
+#include <cuda_bf16.h>
+
+namespace sseg {
+
+struct alignas(16) BF8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 q = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x, f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 q;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<uint4*>(p) = q;
+}
+
+static inline int grid_for(long work, int block, int max_blocks = 148 * 16) {
+  long g = (work + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight re-layout: fp32 OIHW master weights -> bf16 [O][T*I] (forward) and bf16 [I][T*Opad] (data gradient)
+__global__ void prep_weight_kernel(const float* __restrict__ w, int O, int I, int T, __nv_bfloat16* __restrict__ wf,
+                                   long wf_ld, __nv_bfloat16* __restrict__ wd, long wd_ld, int o_pad) {
+  const long total = (long)O * I * T;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    // idx enumerates the forward layout (o, t, i) so the bf16 stores are coalesced
+    const int i = idx % I;
+    const long r = idx / I;
+    const int t = r % T;
+    const int o = r / T;
+    const float v = w[((long)o * I + i) * T + t];
+    const __nv_bfloat16 b = __float2bfloat16(v);
+    if (wf) wf[(long)o * wf_ld + (long)t * I + i] = b;
+    if (wd) wd[(long)i * wd_ld + (long)t * o_pad + o] = b;
+  }
+}
+
+// gradient re-layout: fp32 [O][T*I] (what wgrad produces) -> fp32 OIHW (+= or =), times scale
+__global__ void grad_to_oihw_kernel(const float* __restrict__ g, long g_ld, int O, int I, int T, float* __restrict__ out,
+                                    float scale, int accumulate) {
+  const long total = (long)O * I * T;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    // idx enumerates OIHW so the stores are coalesced
+    const int t = idx % T;
+    const long r = idx / T;
+    const int i = r % I;
+    const int o = r / I;
+    const float v = g[(long)o * g_ld + (long)t * I + i] * scale;
+    out[idx] = accumulate ? out[idx] + v : v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem conv: fp32 NCHW image [N,3,H,W] -> bf16 NHWC [N,Ho,Wo,64], 3x3 stride 2 pad 1 (models/resnet.py:100)
+// + batch-norm statistics. One thread per output pixel, 64 accumulators, weights broadcast from shared memory.
+__global__ void __launch_bounds__(128) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
+                                                            __nv_bfloat16* __restrict__ out, float* __restrict__ ssum,
+                                                            float* __restrict__ ssq, int N, int H, int W, int Ho,
+                                                            int Wo) {
+  __shared__ float sw[27][64];
+  __shared__ float bsum[64], bsq[64];
+  for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
+    const int co = i % 64, k = i / 64;  // k = ci*9 + r*3 + s, OIHW source index = co*27 + k
+    sw[k][co] = w[co * 27 + k];
+  }
+  if (threadIdx.x < 64) bsum[threadIdx.x] = 0.f, bsq[threadIdx.x] = 0.f;
+  __syncthreads();
+  const long P = (long)N * Ho * Wo;
+  const long pidx = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  const bool valid = pidx < P;
+  float acc[64];
+#pragma unroll
+  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+  if (valid) {
+    const int wo = pidx % Wo;
+    const long r = pidx / Wo;
+    const int ho = r % Ho;
+    const int n = r / Ho;
+#pragma unroll
+    for (int ci = 0; ci < 3; ++ci) {
+#pragma unroll
+      for (int kr = 0; kr < 3; ++kr) {
+        const int h = 2 * ho + kr - 1;
+#pragma unroll
+        for (int ks = 0; ks < 3; ++ks) {
+          const int ww = 2 * wo + ks - 1;
+          float x = 0.f;
+          if (h >= 0 && h < H && ww >= 0 && ww < W) x = __ldg(img + (((long)n * 3 + ci) * H + h) * W + ww);
+          const int k = ci * 9 + kr * 3 + ks;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) acc[c] = fmaf(x, sw[k][c], acc[c]);
+        }
+      }
+    }
+    __nv_bfloat16* op = out + pidx * 64;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = acc[g * 8 + e];
+      store8(op + g * 8, f);
+    }
+  }
+  if (ssum != nullptr) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 64; ++c) {
+      float s = valid ? acc[c] : 0.f, q = s * s;
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, off);
+        q += __shfl_xor_sync(0xffffffffu, q, off);
+      }
+      if (lane == 0) atomicAdd(&bsum[c], s), atomicAdd(&bsq[c], q);
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) atomicAdd(ssum + threadIdx.x, bsum[threadIdx.x]), atomicAdd(ssq + threadIdx.x, bsq[threadIdx.x]);
+  }
+}
+
+// stem conv weight gradient: dW[co][ci][r][s] += sum_pixels dy[p, co] * x[n, ci, 2ho+r-1, 2wo+s-1]
+// 256 threads = 64 co x 4 tap groups (7 of the 27 (ci,r,s) taps each); each block reduces a chunk of pixels.
+__global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img,
+                                                              const __nv_bfloat16* __restrict__ dy,
+                                                              float* __restrict__ dw, int N, int H, int W, int Ho, int Wo,
+                                                              int pix_per_block) {
+  const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  float acc[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
+  const long P = (long)N * Ho * Wo;
+  const long p0 = (long)blockIdx.x * pix_per_block;
+  const long p1 = min(p0 + pix_per_block, P);
+  for (long p = p0; p < p1; ++p) {
+    const int wo = p % Wo;
+    const long r = p / Wo;
+    const int ho = r % Ho;
+    const int n = r / Ho;
+    const float g = __bfloat162float(dy[p * 64 + co]);
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int k = grp * 7 + j;
+      if (k < 27) {
+        const int ci = k / 9, kr = (k % 9) / 3, ks = k % 3;
+        const int h = 2 * ho + kr - 1, ww = 2 * wo + ks - 1;
+        float x = 0.f;
+        if (h >= 0 && h < H && ww >= 0 && ww < W) x = __ldg(img + (((long)n * 3 + ci) * H + h) * W + ww);
+        acc[j] = fmaf(g, x, acc[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int k = grp * 7 + j;
+    if (k < 27) atomicAdd(dw + co * 27 + k, acc[j]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// batch norm
+//   finalize: (sum, sqsum, count) -> mean, inv_std, scale = gamma*inv_std, shift = beta - mean*scale; running stats.
+//   mode 0: F.batch_norm training  (inv_std = 1/sqrt(var+eps); running = (1-m)*running + m*{mean, unbiased var})
+//           [lib/nn/modules/batchnorm.py:58-61 -> torch native batch_norm]
+//   mode 1: SynchronizedBatchNorm parallel branch (inv_std = clamp(var,eps)^-0.5; accumulator-style running stats)
+//           [lib/nn/modules/batchnorm.py:123-139]
+//   mode 2: evaluation: statistics = running_mean / running_var (inv_std = 1/sqrt(var+eps))
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sqsum,
+                                   const float* __restrict__ count_dev, float count_host, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float eps, float momentum, int mode, int update_running,
+                                   float* running_mean, float* running_var, float* tmp_mean, float* tmp_var,
+                                   float* running_iter, float* __restrict__ mean_out, float* __restrict__ invstd_out,
+                                   float* __restrict__ scale, float* __restrict__ shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float mean, inv_std;
+  if (mode == 2) {
+    mean = running_mean[c];
+    inv_std = rsqrtf(running_var[c] + eps);
+  } else {
+    const float cnt = count_dev ? *count_dev : count_host;
+    mean = sum[c] / cnt;
+    const float sumvar = sqsum[c] - sum[c] * mean;
+    const float bias_var = sumvar / cnt;
+    const float unbias_var = sumvar / (cnt - 1.f);
+    if (mode == 0) {
+      inv_std = rsqrtf(fmaxf(bias_var, 0.f) + eps);
+      if (update_running) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbias_var;
+      }
+    } else {
+      inv_std = rsqrtf(fmaxf(bias_var, eps));
+      if (update_running) {
+        const float frac = 1.f - momentum;
+        const float it = running_iter[0] * frac + 1.f;  // every thread computes the same value; thread 0 stores it
+        const float tm = tmp_mean[c] * frac + mean;
+        const float tv = tmp_var[c] * frac + unbias_var;
+        tmp_mean[c] = tm, tmp_var[c] = tv;
+        running_mean[c] = tm / it, running_var[c] = tv / it;
+      }
+    }
+  }
+  const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean_out[c] = mean, invstd_out[c] = inv_std;
+  scale[c] = g * inv_std;
+  shift[c] = b - mean * g * inv_std;
+}
+__global__ void bn_iter_update_kernel(float* running_iter, float momentum) {
+  running_iter[0] = running_iter[0] * (1.f - momentum) + 1.f;
+}
+
+// apply: out = [relu]( y*scale + shift + residual' ) * chanmul[n][c];  residual' = r (* rscale + rshift)
+struct BnApplyParams {
+  const __nv_bfloat16* y;
+  long y_ld;
+  const float *scale, *shift;
+  const __nv_bfloat16* res;
+  long res_ld;
+  const float *rscale, *rshift;
+  const float* chanmul;  // [N][C] or null (Dropout2d keep-mask / (1-p))
+  __nv_bfloat16* out;
+  long out_ld;
+  long P;          // pixels
+  long pix_per_img;
+  int C, relu;
+};
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
+  const int cg = p.C >> 3;
+  const long total = p.P * cg;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    const long pix = idx / cg;
+    float v[8];
+    load8(p.y + pix * p.y_ld + c0, v);
+    const float4 s0 = *reinterpret_cast<const float4*>(p.scale + c0), s1 = *reinterpret_cast<const float4*>(p.scale + c0 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(p.shift + c0), b1 = *reinterpret_cast<const float4*>(p.shift + c0 + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
+    if (p.res) {
+      float r[8];
+      load8(p.res + pix * p.res_ld + c0, r);
+      if (p.rscale) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = fmaf(r[e], p.rscale[c0 + e], p.rshift[c0 + e]);
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] += r[e];
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+    }
+    if (p.chanmul) {
+      const float* m = p.chanmul + (pix / p.pix_per_img) * p.C + c0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] *= m[e];
+    }
+    store8(p.out + pix * p.out_ld + c0, v);
+  }
+}
+
+// backward, pass 1: per-channel S1 = sum g', S2 = sum g' * xhat, with g' = g * chanmul * [a > 0]
+// backward, pass 2: dy = scale * (g' - S1/M - xhat * S2/M);  optionally also stores g' (the residual-branch gradient)
+struct BnBwdParams {
+  const __nv_bfloat16* g;
+  long g_ld;
+  const __nv_bfloat16* a;  // saved block output (post-ReLU) or null when the layer has no ReLU
+  long a_ld;
+  const __nv_bfloat16* y;  // saved conv output (pre-BN)
+  long y_ld;
+  const float *mean, *invstd, *scale;  // scale = gamma * invstd
+  const float* chanmul;
+  float* s1;
+  float* s2;
+  const float* count_dev;
+  float count_host;
+  __nv_bfloat16* dy;
+  long dy_ld;
+  __nv_bfloat16* dres;
+  long dres_ld;
+  long P, pix_per_img;
+  int C;
+  int eval_mode;  // statistics were constants (running stats): dy = scale * g'
+};
+
+__device__ __forceinline__ void bn_bwd_gprime(const BnBwdParams& p, long pix, int c0, float (&g)[8]) {
+  load8(p.g + pix * p.g_ld + c0, g);
+  if (p.chanmul) {
+    const float* m = p.chanmul + (pix / p.pix_per_img) * p.C + c0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] *= m[e];
+  }
+  if (p.a) {
+    float a[8];
+    load8(p.a + pix * p.a_ld + c0, a);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] = a[e] > 0.f ? g[e] : 0.f;
+  }
+}
+
+// block = 256 threads arranged as (256/cgb) pixel rows x cgb channel groups, cgb = min(C/8, 256)
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
+  __shared__ float red[2][256][8];
+  const int cg = p.C >> 3;
+  const int cgb = cg < 256 ? cg : 256;
+  const int rows = 256 / cgb;
+  const int tcol = threadIdx.x % cgb, trow = threadIdx.x / cgb;
+  const int cgrp = blockIdx.y * cgb + tcol;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) s1[e] = 0.f, s2[e] = 0.f;
+  if (cgrp < cg && trow < rows) {
+    const int c0 = cgrp << 3;
+    float mu[8], is[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) mu[e] = p.mean[c0 + e], is[e] = p.invstd[c0 + e];
+    for (long pix = (long)blockIdx.x * rows + trow; pix < p.P; pix += (long)gridDim.x * rows) {
+      float g[8], y[8];
+      bn_bwd_gprime(p, pix, c0, g);
+      load8(p.y + pix * p.y_ld + c0, y);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1[e] += g[e];
+        s2[e] += g[e] * (y[e] - mu[e]) * is[e];
+      }
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[0][threadIdx.x][e] = s1[e], red[1][threadIdx.x][e] = s2[e];
+  __syncthreads();
+  if (trow == 0 && cgrp < cg) {
+    for (int r = 1; r < rows; ++r) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s1[e] += red[0][r * cgb + tcol][e], s2[e] += red[1][r * cgb + tcol][e];
+    }
+    const int c0 = cgrp << 3;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(p.s1 + c0 + e, s1[e]), atomicAdd(p.s2 + c0 + e, s2[e]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
+  const int cg = p.C >> 3;
+  const long total = p.P * cg;
+  const float inv_m = 1.f / (p.count_dev ? *p.count_dev : p.count_host);
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    const long pix = idx / cg;
+    float g[8];
+    bn_bwd_gprime(p, pix, c0, g);
+    if (p.dres) store8(p.dres + pix * p.dres_ld + c0, g);
+    float d[8];
+    if (p.eval_mode) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) d[e] = g[e] * p.scale[c0 + e];
+    } else {
+      float y[8];
+      load8(p.y + pix * p.y_ld + c0, y);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float xhat = (y[e] - p.mean[c0 + e]) * p.invstd[c0 + e];
+        d[e] = p.scale[c0 + e] * (g[e] - p.s1[c0 + e] * inv_m - xhat * p.s2[c0 + e] * inv_m);
+      }
+    }
+    store8(p.dy + pix * p.dy_ld + c0, d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// max pool 3x3 stride 2 pad 1 (models/resnet.py:109); the argmax tap (0..8, first maximum in scan order like torch)
+// is kept in one byte per output element for the backward gather.
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                   uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo) {
+  const int cg = C >> 3;
+  const long total = (long)N * Ho * Wo * cg;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c0 = (i % cg) << 3;
+    long r = i / cg;
+    const int wo = r % Wo;
+    r /= Wo;
+    const int ho = r % Ho;
+    const int n = r / Ho;
+    float best[8];
+    int bidx[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) best[e] = -INFINITY, bidx[e] = 0;
+#pragma unroll
+    for (int kr = 0; kr < 3; ++kr) {
+      const int h = 2 * ho + kr - 1;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) {
+        const int w = 2 * wo + ks - 1;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        load8(x + (((long)n * H + h) * W + w) * C + c0, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (v[e] > best[e]) best[e] = v[e], bidx[e] = kr * 3 + ks;
+      }
+    }
+    const long o = (((long)n * Ho + ho) * Wo + wo) * C + c0;
+    store8(out + o, best);
+    if (idx) {
+      uint2 packed;
+      packed.x = bidx[0] | (bidx[1] << 8) | (bidx[2] << 16) | (bidx[3] << 24);
+      packed.y = bidx[4] | (bidx[5] << 8) | (bidx[6] << 16) | (bidx[7] << 24);
+      *reinterpret_cast<uint2*>(idx + o) = packed;
+    }
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
+                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+  const int cg = C >> 3;
+  const long total = (long)N * H * W * cg;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c0 = (i % cg) << 3;
+    long r = i / cg;
+    const int w = r % W;
+    r /= W;
+    const int h = r % H;
+    const int n = r / H;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    // output windows containing (h, w): ho with 2ho-1 <= h <= 2ho+1
+    for (int ho = (h) / 2; ho <= (h + 1) / 2; ++ho) {
+      if (ho < 0 || ho >= Ho) continue;
+      const int kr = h - 2 * ho + 1;
+      for (int wo = (w) / 2; wo <= (w + 1) / 2; ++wo) {
+        if (wo < 0 || wo >= Wo) continue;
+        const int ks = w - 2 * wo + 1;
+        const int tap = kr * 3 + ks;
+        const long o = (((long)n * Ho + ho) * Wo + wo) * C + c0;
+        const uint2 packed = *reinterpret_cast<const uint2*>(idx + o);
+        float g[8];
+        load8(dout + o, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int b = ((e < 4 ? packed.x : packed.y) >> ((e & 3) * 8)) & 0xff;
+          if (b == tap) acc[e] += g[e];
+        }
+      }
+    }
+    store8(dx + i * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// adaptive average pool to s x s (models/models.py:447): bin i covers [floor(i*H/s), ceil((i+1)*H/s)).
+__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_ld, __nv_bfloat16* __restrict__ out, int N,
+                                   int H, int W, int C, int S) {
+  // grid: (N*S*S, ceil(C/8/blockDim)) ; one thread = 8 channels of one bin
+  const int cgi = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cgi >= (C >> 3)) return;
+  const int c0 = cgi << 3;
+  int b = blockIdx.x;
+  const int j = b % S;
+  b /= S;
+  const int i = b % S;
+  const int n = b / S;
+  const int h0 = (i * H) / S, h1 = ((i + 1) * H + S - 1) / S;
+  const int w0 = (j * W) / S, w1 = ((j + 1) * W + S - 1) / S;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int h = h0; h < h1; ++h)
+    for (int w = w0; w < w1; ++w) {
+      float v[8];
+      load8(x + (((long)n * H + h) * W + w) * x_ld + c0, v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += v[e];
+    }
+  const float inv = 1.f / ((h1 - h0) * (w1 - w0));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] *= inv;
+  store8(out + (((long)n * S + i) * S + j) * C + c0, acc);
+}
+
+// backward of up to 4 pooling scales at once, accumulated onto a base gradient:
+//   dx[n,h,w,c] = base[n,h,w,c] + sum_k sum_{bins of scale k containing (h,w)} dpool_k[n,i,j,c] / binsize
+struct AvgPoolBwdParams {
+  const __nv_bfloat16* base;
+  long base_ld;
+  const __nv_bfloat16* dpool[4];
+  int scales[4];
+  int nscales;
+  __nv_bfloat16* dx;
+  long dx_ld;
+  int N, H, W, C;
+};
+__global__ void avgpool_bwd_kernel(const AvgPoolBwdParams p) {
+  const int cg = p.C >> 3;
+  const long total = (long)p.N * p.H * p.W * cg;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    long r = idx / cg;
+    const int w = r % p.W;
+    r /= p.W;
+    const int h = r % p.H;
+    const int n = r / p.H;
+    const long pix = ((long)n * p.H + h) * p.W + w;
+    float acc[8];
+    if (p.base)
+      load8(p.base + pix * p.base_ld + c0, acc);
+    else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    }
+    for (int k = 0; k < p.nscales; ++k) {
+      const int S = p.scales[k];
+      // candidate bins: i with floor(i*H/S) <= h < ceil((i+1)*H/S)
+      const int ic = (int)(((long)h * S) / p.H);
+      for (int i = max(ic - 1, 0); i <= min(ic + 1, S - 1); ++i) {
+        const int h0 = (i * p.H) / S, h1 = ((i + 1) * p.H + S - 1) / S;
+        if (h < h0 || h >= h1) continue;
+        const int jc = (int)(((long)w * S) / p.W);
+        for (int j = max(jc - 1, 0); j <= min(jc + 1, S - 1); ++j) {
+          const int w0 = (j * p.W) / S, w1 = ((j + 1) * p.W + S - 1) / S;
+          if (w < w0 || w >= w1) continue;
+          float g[8];
+          load8(p.dpool[k] + (((long)n * S + i) * S + j) * p.C + c0, g);
+          const float inv = 1.f / ((h1 - h0) * (w1 - w0));
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += g[e] * inv;
+        }
+      }
+    }
+    store8(p.dx + pix * p.dx_ld + c0, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bilinear resize, align_corners=False (models/models.py:472-475): src = max((dst+0.5)*in/out - 0.5, 0)
+__device__ __forceinline__ void bilinear_coeff(int dst, int in, int out, int& i0, int& i1, float& lam) {
+  const float scale = (float)in / (float)out;
+  float src = ((float)dst + 0.5f) * scale - 0.5f;
+  src = src < 0.f ? 0.f : src;
+  i0 = (int)src;
+  i1 = i0 < in - 1 ? i0 + 1 : i0;
+  lam = src - (float)i0;
+}
+
+__global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_ld, int N, int Hi, int Wi, int C,
+                                    __nv_bfloat16* __restrict__ out, long out_ld, int Ho, int Wo) {
+  const int cg = C >> 3;
+  const long total = (long)N * Ho * Wo * cg;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    long r = idx / cg;
+    const int wo = r % Wo;
+    r /= Wo;
+    const int ho = r % Ho;
+    const int n = r / Ho;
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilinear_coeff(ho, Hi, Ho, h0, h1, lh);
+    bilinear_coeff(wo, Wi, Wo, w0, w1, lw);
+    float a[8], b[8], c[8], d[8], o[8];
+    load8(x + (((long)n * Hi + h0) * Wi + w0) * x_ld + c0, a);
+    load8(x + (((long)n * Hi + h0) * Wi + w1) * x_ld + c0, b);
+    load8(x + (((long)n * Hi + h1) * Wi + w0) * x_ld + c0, c);
+    load8(x + (((long)n * Hi + h1) * Wi + w1) * x_ld + c0, d);
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      o[e] = (1.f - lh) * ((1.f - lw) * a[e] + lw * b[e]) + lh * ((1.f - lw) * c[e] + lw * d[e]);
+    store8(out + (((long)n * Ho + ho) * Wo + wo) * out_ld + c0, o);
+  }
+}
+
+// backward (gather form): one thread = 8 channels of one INPUT pixel; walks the output pixels that reference it.
+__global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long dout_ld, int N, int Ho, int Wo, int C,
+                                    __nv_bfloat16* __restrict__ dx, long dx_ld, int Hi, int Wi, int accumulate) {
+  const int cg = C >> 3;
+  const long total = (long)N * Hi * Wi * cg;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    long r = idx / cg;
+    const int wi = r % Wi;
+    r /= Wi;
+    const int hi = r % Hi;
+    const int n = r / Hi;
+    // output rows whose source interval can touch hi: src in (hi-1, hi+1)
+    const float sh = (float)Ho / (float)Hi, sw = (float)Wo / (float)Wi;
+    const int ho_lo = max(0, (int)floorf(((float)hi - 1.f + 0.5f) * sh - 0.5f) - 1);
+    const int ho_hi = min(Ho - 1, (int)ceilf(((float)hi + 1.f + 0.5f) * sh - 0.5f) + 1);
+    const int wo_lo = max(0, (int)floorf(((float)wi - 1.f + 0.5f) * sw - 0.5f) - 1);
+    const int wo_hi = min(Wo - 1, (int)ceilf(((float)wi + 1.f + 0.5f) * sw - 0.5f) + 1);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+      int h0, h1;
+      float lh;
+      bilinear_coeff(ho, Hi, Ho, h0, h1, lh);
+      float wh = 0.f;
+      if (h0 == hi) wh += 1.f - lh;
+      if (h1 == hi) wh += lh;
+      if (wh == 0.f) continue;
+      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+        int w0, w1;
+        float lw;
+        bilinear_coeff(wo, Wi, Wo, w0, w1, lw);
+        float ww = 0.f;
+        if (w0 == wi) ww += 1.f - lw;
+        if (w1 == wi) ww += lw;
+        if (ww == 0.f) continue;
+        float g[8];
+        load8(dout + (((long)n * Ho + ho) * Wo + wo) * dout_ld + c0, g);
+        const float wgt = wh * ww;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(g[e], wgt, acc[e]);
+      }
+    }
+    __nv_bfloat16* dp = dx + (((long)n * Hi + hi) * Wi + wi) * dx_ld + c0;
+    if (accumulate) {
+      float o[8];
+      load8(dp, o);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += o[e];
+    }
+    store8(dp, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// log-softmax + NLLLoss(ignore_index=-1) + pixel accuracy (models/models.py:12-18,37-42,492-493; train.py:154)
+//   accum[0] += sum over valid pixels of -log p[label];  accum[1] += #valid;  accum[2] += #(valid & argmax==label)
+// One warp per pixel; logits fp32 [P][ld]. lse[p] is kept for the backward.
+__global__ void __launch_bounds__(256) softmax_nll_fwd_kernel(const float* __restrict__ logits, long ld, int C,
+                                                              const long long* __restrict__ label, long P,
+                                                              float* __restrict__ lse, float* __restrict__ accum) {
+  __shared__ float bl[8], bc[8], ba[8];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float loss = 0.f, cnt = 0.f, correct = 0.f;
+  for (long p = (long)blockIdx.x * 8 + warp; p < P; p += (long)gridDim.x * 8) {
+    const float* row = logits + p * ld;
+    float m = -INFINITY;
+    int am = 0;
+    for (int c = lane; c < C; c += 32) {
+      const float v = row[c];
+      if (v > m) m = v, am = c;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, m, off);
+      const int oa = __shfl_xor_sync(0xffffffffu, am, off);
+      if (om > m || (om == m && oa < am)) m = om, am = oa;  // first maximum wins, like torch.max
+    }
+    float s = 0.f;
+    for (int c = lane; c < C; c += 32) s += __expf(row[c] - m);
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float l = m + __logf(s);
+    if (lane == 0) {
+      lse[p] = l;
+      const long long lab = label[p];
+      if (lab >= 0) {
+        loss += l - row[lab];
+        cnt += 1.f;
+        if (am == (int)lab) correct += 1.f;
+      }
+    }
+  }
+  if (lane == 0) bl[warp] = loss, bc[warp] = cnt, ba[warp] = correct;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int i = 0; i < 8; ++i) a += bl[i], b += bc[i], c += ba[i];
+    atomicAdd(accum + 0, a), atomicAdd(accum + 1, b), atomicAdd(accum + 2, c);
+  }
+}
+
+// loss = main/cnt + ds_scale * ds/cnt ; acc = correct/(cnt + 1e-10)   (models/models.py:37-42, :12-18)
+__global__ void nll_finalize_kernel(const float* accum_main, const float* accum_ds, float ds_scale, float* out) {
+  float loss = accum_main[0] / accum_main[1];
+  if (accum_ds) loss += ds_scale * accum_ds[0] / accum_ds[1];
+  out[0] = loss;
+  out[1] = accum_main[2] / (accum_main[1] + 1e-10f);
+}
+
+// dlogits[p][c] = weight/cnt * (softmax - onehot) for valid pixels, 0 otherwise; bf16 [P][ld_out], columns >= C zeroed.
+__global__ void __launch_bounds__(256) softmax_nll_bwd_kernel(const float* __restrict__ logits, long ld, int C,
+                                                              const long long* __restrict__ label,
+                                                              const float* __restrict__ lse, const float* __restrict__ accum,
+                                                              float weight, long P, __nv_bfloat16* __restrict__ dlogits,
+                                                              long ld_out, int c_store) {
+  const float coef = weight / accum[1];
+  const long total = P * c_store;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c = idx % c_store;
+    const long p = idx / c_store;
+    float v = 0.f;
+    const long long lab = label[p];
+    if (c < C && lab >= 0) {
+      v = __expf(logits[p * ld + c] - lse[p]);
+      if (c == (int)lab) v -= 1.f;
+      v *= coef;
+    }
+    dlogits[p * ld_out + c] = __float2bfloat16(v);
+  }
+}
+
+// column sums of a bf16 [P][ld] matrix into fp32[C] (+=): bias gradients.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long ld, long P, int C,
+                                                     float* __restrict__ out) {
+  // block handles a slab of rows; thread t handles columns t, t+256, ...
+  const long rows_per_block = (P + gridDim.x - 1) / gridDim.x;
+  const long r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, P);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long r = r0; r < r1; ++r) s += __bfloat162float(x[r * ld + c]);
+    atomicAdd(out + c, s);
+  }
+}
+
+// inference head: bilinear upsample of fp32 NHWC logits to segSize + softmax -> fp32 NCHW probabilities,
+// optionally accumulated (scores += probs * weight): models/models.py:480-484, eval.py:71-72.
+__global__ void __launch_bounds__(256) upsample_softmax_kernel(const float* __restrict__ logits, long ld, int N, int Hi,
+                                                               int Wi, int C, float* __restrict__ probs, int Ho, int Wo,
+                                                               float weight, int accumulate) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long P = (long)N * Ho * Wo;
+  for (long p = (long)blockIdx.x * 8 + warp; p < P; p += (long)gridDim.x * 8) {
+    const int wo = p % Wo;
+    long r = p / Wo;
+    const int ho = r % Ho;
+    const int n = r / Ho;
+    int h0, h1, w0, w1;
+    float lh, lw;
+    bilinear_coeff(ho, Hi, Ho, h0, h1, lh);
+    bilinear_coeff(wo, Wi, Wo, w0, w1, lw);
+    const float* a = logits + (((long)n * Hi + h0) * Wi + w0) * ld;
+    const float* b = logits + (((long)n * Hi + h0) * Wi + w1) * ld;
+    const float* c = logits + (((long)n * Hi + h1) * Wi + w0) * ld;
+    const float* d = logits + (((long)n * Hi + h1) * Wi + w1) * ld;
+    float v[8];  // up to 256 classes
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = lane + 32 * k;
+      v[k] = -INFINITY;
+      if (ch < C) {
+        v[k] = (1.f - lh) * ((1.f - lw) * a[ch] + lw * b[ch]) + lh * ((1.f - lw) * c[ch] + lw * d[ch]);
+        m = fmaxf(m, v[k]);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = (lane + 32 * k < C) ? __expf(v[k] - m) : 0.f;
+      s += v[k];
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float inv = weight / s;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = lane + 32 * k;
+      if (ch < C) {
+        float* o = probs + (((long)n * C + ch) * Ho + ho) * Wo + wo;
+        *o = accumulate ? *o + v[k] * inv : v[k] * inv;
+      }
+    }
+  }
+}
+
+// layout conversion NHWC bf16 -> NCHW fp32 (feature maps handed back through the module-level API)
+__global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, long ld, int N, int H, int W, int C,
+                                             float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  // grid: (ceil(HW/32), ceil(C/32), N); block (32, 8)
+  const int n = blockIdx.z;
+  const long HW = (long)H * W;
+  const long p0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? __bfloat162float(x[((long)n * HW + p) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long p = p0 + threadIdx.x;
+    if (p < HW && c < C) out[((long)n * C + c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+__global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, int N, int H, int W, int C,
+                                             __nv_bfloat16* __restrict__ out, long ld) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const long HW = (long)H * W;
+  const long p0 = (long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? x[((long)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long p = p0 + i;
+    const int c = c0 + threadIdx.x;
+    if (p < HW && c < C) out[((long)n * HW + p) * ld + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+}  // namespace sseg
+
+using namespace sseg;
+#define LAUNCH_CHECK(name)   \
+  count_launch(1);           \
+  return check_cuda(cudaGetLastError(), name)
+
+extern "C" {
+
+int sseg_prep_conv_weight(const float* w_oihw, int O, int I, int T, void* w_fwd, long fwd_ld, void* w_dgrad,
+                          long dgrad_ld, int o_pad, sseg_stream_t st) {
+  SSEG_REQUIRE(w_oihw && (w_fwd || w_dgrad), "sseg_prep_conv_weight: null argument");
+  SSEG_REQUIRE(!w_fwd || fwd_ld >= (long)T * I, "sseg_prep_conv_weight: fwd_ld too small");
+  SSEG_REQUIRE(!w_dgrad || (o_pad >= O && dgrad_ld >= (long)T * o_pad), "sseg_prep_conv_weight: dgrad_ld too small");
+  const long total = (long)O * I * T;
+  prep_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)st>>>(
+      w_oihw, O, I, T, (__nv_bfloat16*)w_fwd, fwd_ld, (__nv_bfloat16*)w_dgrad, dgrad_ld, o_pad);
+  LAUNCH_CHECK("prep_weight_kernel");
+}
+
+int sseg_grad_to_oihw(const float* g, long g_ld, int O, int I, int T, float* out, float scale, int accumulate,
+                      sseg_stream_t st) {
+  SSEG_REQUIRE(g && out, "sseg_grad_to_oihw: null argument");
+  const long total = (long)O * I * T;
+  grad_to_oihw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)st>>>(g, g_ld, O, I, T, out, scale, accumulate);
+  LAUNCH_CHECK("grad_to_oihw_kernel");
+}
+
+int sseg_stem_conv_fwd(const float* img, int N, int H, int W, const float* w, void* out, float* stat_sum,
+                       float* stat_sqsum, sseg_stream_t st) {
+  SSEG_REQUIRE(img && w && out, "sseg_stem_conv_fwd: null argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long P = (long)N * Ho * Wo;
+  stem_conv_fwd_kernel<<<(int)((P + 127) / 128), 128, 0, (cudaStream_t)st>>>(img, w, (__nv_bfloat16*)out, stat_sum,
+                                                                             stat_sqsum, N, H, W, Ho, Wo);
+  LAUNCH_CHECK("stem_conv_fwd_kernel");
+}
+
+int sseg_stem_conv_wgrad(const float* img, int N, int H, int W, const void* dy, float* dw, sseg_stream_t st) {
+  SSEG_REQUIRE(img && dy && dw, "sseg_stem_conv_wgrad: null argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long P = (long)N * Ho * Wo;
+  const int ppb = 256;
+  stem_conv_wgrad_kernel<<<(int)((P + ppb - 1) / ppb), 256, 0, (cudaStream_t)st>>>(img, (const __nv_bfloat16*)dy, dw, N,
+                                                                                   H, W, Ho, Wo, ppb);
+  LAUNCH_CHECK("stem_conv_wgrad_kernel");
+}
+
+int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_dev, float count_host, const float* gamma,
+                     const float* beta, float eps, float momentum, int mode, int update_running, float* running_mean,
+                     float* running_var, float* tmp_mean, float* tmp_var, float* running_iter, float* mean_out,
+                     float* invstd_out, float* scale, float* shift, int C, sseg_stream_t st) {
+  SSEG_REQUIRE(mean_out && invstd_out && scale && shift && C > 0, "sseg_bn_finalize: null argument");
+  SSEG_REQUIRE(mode == 2 || (sum && sqsum), "sseg_bn_finalize: statistics required in training modes");
+  SSEG_REQUIRE(mode != 2 || (running_mean && running_var), "sseg_bn_finalize: running statistics required in eval mode");
+  SSEG_REQUIRE(!(update_running && mode == 1) || (tmp_mean && tmp_var && running_iter && running_mean && running_var),
+               "sseg_bn_finalize: sync-mode running buffers required");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)st>>>(
+      sum, sqsum, count_dev, count_host, gamma, beta, eps, momentum, mode, update_running, running_mean, running_var,
+      tmp_mean, tmp_var, running_iter, mean_out, invstd_out, scale, shift, C);
+  count_launch(1);
+  if (update_running && mode == 1) {
+    bn_iter_update_kernel<<<1, 1, 0, (cudaStream_t)st>>>(running_iter, momentum);
+    count_launch(1);
+  }
+  return check_cuda(cudaGetLastError(), "bn_finalize_kernel");
+}
+
+int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
+                  const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
+                  long pix_per_img, int C, int relu, sseg_stream_t st) {
+  SSEG_REQUIRE(y && scale && shift && out && C % 8 == 0 && y_ld % 8 == 0 && out_ld % 8 == 0 && (!res || res_ld % 8 == 0),
+               "sseg_bn_apply: bad argument (channels and strides must be multiples of 8)");
+  BnApplyParams p{(const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, rscale, rshift,
+                  chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu};
+  bn_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(p);
+  LAUNCH_CHECK("bn_apply_kernel");
+}
+
+static int fill_bwd(BnBwdParams& p, const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld,
+                    const float* mean, const float* invstd, const float* scale, const float* chanmul, float* s1, float* s2,
+                    const float* count_dev, float count_host, void* dy, long dy_ld, void* dres, long dres_ld, long P,
+                    long pix_per_img, int C, int eval_mode) {
+  SSEG_REQUIRE(g && C % 8 == 0 && g_ld % 8 == 0 && (!a || a_ld % 8 == 0) && (!y || y_ld % 8 == 0),
+               "sseg_bn_bwd: bad argument (channels and strides must be multiples of 8)");
+  p = BnBwdParams{(const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)a, a_ld, (const __nv_bfloat16*)y, y_ld, mean,
+                  invstd, scale, chanmul, s1, s2, count_dev, count_host, (__nv_bfloat16*)dy, dy_ld,
+                  (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode};
+  return 0;
+}
+
+int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
+                       const float* invstd, const float* chanmul, float* s1, float* s2, long P, long pix_per_img, int C,
+                       sseg_stream_t st) {
+  BnBwdParams p;
+  int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, nullptr, chanmul, s1, s2, nullptr, 1.f, nullptr, 0,
+                    nullptr, 0, P, pix_per_img, C, 0);
+  if (rc) return rc;
+  SSEG_REQUIRE(y && mean && invstd && s1 && s2, "sseg_bn_bwd_reduce: null argument");
+  const int cg = C / 8, cgb = cg < 256 ? cg : 256, rows = 256 / cgb;
+  SSEG_REQUIRE(256 % cgb == 0, "sseg_bn_bwd_reduce: C/8 must divide 256 or be a multiple of 256 (C=%d)", C);
+  dim3 grid(grid_for((P + rows - 1) / rows, 1, 148 * 4), (cg + cgb - 1) / cgb);
+  bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(p);
+  LAUNCH_CHECK("bn_bwd_reduce_kernel");
+}
+
+int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
+                      const float* invstd, const float* scale, const float* chanmul, const float* s1, const float* s2,
+                      const float* count_dev, float count_host, void* dy, long dy_ld, void* dres, long dres_ld, long P,
+                      long pix_per_img, int C, int eval_mode, sseg_stream_t st) {
+  BnBwdParams p;
+  int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, chanmul, const_cast<float*>(s1),
+                    const_cast<float*>(s2), count_dev, count_host, dy, dy_ld, dres, dres_ld, P, pix_per_img, C,
+                    eval_mode);
+  if (rc) return rc;
+  SSEG_REQUIRE(dy && scale && dy_ld % 8 == 0 && (!dres || dres_ld % 8 == 0), "sseg_bn_bwd_apply: bad argument");
+  SSEG_REQUIRE(eval_mode || (y && mean && invstd && s1 && s2), "sseg_bn_bwd_apply: training mode needs y/mean/invstd/s1/s2");
+  bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(p);
+  LAUNCH_CHECK("bn_bwd_apply_kernel");
+}
+
+int sseg_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, void* idx, sseg_stream_t st) {
+  SSEG_REQUIRE(x && out && C % 8 == 0, "sseg_maxpool_fwd: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool_fwd_kernel<<<grid_for((long)N * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint8_t*)idx, N, H, W, C, Ho, Wo);
+  LAUNCH_CHECK("maxpool_fwd_kernel");
+}
+
+int sseg_maxpool_bwd(const void* dout, const void* idx, void* dx, int N, int H, int W, int C, sseg_stream_t st) {
+  SSEG_REQUIRE(dout && idx && dx && C % 8 == 0, "sseg_maxpool_bwd: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  maxpool_bwd_kernel<<<grid_for((long)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(
+      (const __nv_bfloat16*)dout, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
+  LAUNCH_CHECK("maxpool_bwd_kernel");
+}
+
+int sseg_avgpool_fwd(const void* x, long x_ld, int N, int H, int W, int C, int S, void* out, sseg_stream_t st) {
+  SSEG_REQUIRE(x && out && C % 8 == 0 && x_ld % 8 == 0 && S >= 1, "sseg_avgpool_fwd: bad argument");
+  const int cg = C / 8;
+  const int block = cg < 128 ? ((cg + 31) / 32) * 32 : 128;
+  dim3 grid(N * S * S, (cg + block - 1) / block);
+  avgpool_fwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)out, N, H, W, C, S);
+  LAUNCH_CHECK("avgpool_fwd_kernel");
+}
+
+int sseg_avgpool_bwd(const void* base, long base_ld, const void* const* dpool, const int* scales, int nscales, void* dx,
+                     long dx_ld, int N, int H, int W, int C, sseg_stream_t st) {
+  SSEG_REQUIRE(dx && nscales >= 0 && nscales <= 4 && C % 8 == 0 && dx_ld % 8 == 0 && (!base || base_ld % 8 == 0),
+               "sseg_avgpool_bwd: bad argument");
+  AvgPoolBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.base = (const __nv_bfloat16*)base, p.base_ld = base_ld;
+  for (int k = 0; k < nscales; ++k) p.dpool[k] = (const __nv_bfloat16*)dpool[k], p.scales[k] = scales[k];
+  p.nscales = nscales, p.dx = (__nv_bfloat16*)dx, p.dx_ld = dx_ld, p.N = N, p.H = H, p.W = W, p.C = C;
+  avgpool_bwd_kernel<<<grid_for((long)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(p);
+  LAUNCH_CHECK("avgpool_bwd_kernel");
+}
+
+int sseg_bilinear_fwd(const void* x, long x_ld, int N, int Hi, int Wi, int C, void* out, long out_ld, int Ho, int Wo,
+                      sseg_stream_t st) {
+  SSEG_REQUIRE(x && out && C % 8 == 0 && x_ld % 8 == 0 && out_ld % 8 == 0, "sseg_bilinear_fwd: bad argument");
+  bilinear_fwd_kernel<<<grid_for((long)N * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(
+      (const __nv_bfloat16*)x, x_ld, N, Hi, Wi, C, (__nv_bfloat16*)out, out_ld, Ho, Wo);
+  LAUNCH_CHECK("bilinear_fwd_kernel");
+}
+
+int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int C, void* dx, long dx_ld, int Hi, int Wi,
+                      int accumulate, sseg_stream_t st) {
+  SSEG_REQUIRE(dout && dx && C % 8 == 0 && dout_ld % 8 == 0 && dx_ld % 8 == 0, "sseg_bilinear_bwd: bad argument");
+  bilinear_bwd_kernel<<<grid_for((long)N * Hi * Wi * (C / 8), 128), 128, 0, (cudaStream_t)st>>>(
+      (const __nv_bfloat16*)dout, dout_ld, N, Ho, Wo, C, (__nv_bfloat16*)dx, dx_ld, Hi, Wi, accumulate);
+  LAUNCH_CHECK("bilinear_bwd_kernel");
+}
+
+int sseg_softmax_nll_fwd(const float* logits, long ld, int C, const long long* label, long P, float* lse, float* accum,
+                         sseg_stream_t st) {
+  SSEG_REQUIRE(logits && label && lse && accum && C >= 1, "sseg_softmax_nll_fwd: bad argument");
+  softmax_nll_fwd_kernel<<<grid_for(P, 8, 148 * 8), 256, 0, (cudaStream_t)st>>>(logits, ld, C, label, P, lse, accum);
+  LAUNCH_CHECK("softmax_nll_fwd_kernel");
+}
+
+int sseg_nll_finalize(const float* accum_main, const float* accum_ds, float ds_scale, float* out, sseg_stream_t st) {
+  SSEG_REQUIRE(accum_main && out, "sseg_nll_finalize: bad argument");
+  nll_finalize_kernel<<<1, 1, 0, (cudaStream_t)st>>>(accum_main, accum_ds, ds_scale, out);
+  LAUNCH_CHECK("nll_finalize_kernel");
+}
+
+int sseg_softmax_nll_bwd(const float* logits, long ld, int C, const long long* label, const float* lse, const float* accum,
+                         float weight, long P, void* dlogits, long ld_out, int c_store, sseg_stream_t st) {
+  SSEG_REQUIRE(logits && label && lse && accum && dlogits && c_store >= C && c_store <= ld_out,
+               "sseg_softmax_nll_bwd: bad argument");
+  softmax_nll_bwd_kernel<<<grid_for(P * c_store, 256), 256, 0, (cudaStream_t)st>>>(
+      logits, ld, C, label, lse, accum, weight, P, (__nv_bfloat16*)dlogits, ld_out, c_store);
+  LAUNCH_CHECK("softmax_nll_bwd_kernel");
+}
+
+int sseg_colsum(const void* x, long ld, long P, int C, float* out, sseg_stream_t st) {
+  SSEG_REQUIRE(x && out, "sseg_colsum: bad argument");
+  colsum_kernel<<<grid_for(P, 64, 148 * 2), 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, ld, P, C, out);
+  LAUNCH_CHECK("colsum_kernel");
+}
+
+int sseg_upsample_softmax(const float* logits, long ld, int N, int Hi, int Wi, int C, float* probs, int Ho, int Wo,
+                          float weight, int accumulate, sseg_stream_t st) {
+  SSEG_REQUIRE(logits && probs && C >= 1 && C <= 256, "sseg_upsample_softmax: bad argument (C <= 256)");
+  upsample_softmax_kernel<<<grid_for((long)N * Ho * Wo, 8, 148 * 16), 256, 0, (cudaStream_t)st>>>(
+      logits, ld, N, Hi, Wi, C, probs, Ho, Wo, weight, accumulate);
+  LAUNCH_CHECK("upsample_softmax_kernel");
+}
+
+int sseg_nhwc_bf16_to_nchw_f32(const void* x, long ld, int N, int H, int W, int C, float* out, sseg_stream_t st) {
+  SSEG_REQUIRE(x && out, "sseg_nhwc_bf16_to_nchw_f32: bad argument");
+  dim3 grid((unsigned)(((long)H * W + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, ld, N, H, W, C, out);
+  LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
+}
+
+int sseg_nchw_f32_to_nhwc_bf16(const float* x, int N, int H, int W, int C, void* out, long ld, sseg_stream_t st) {
+  SSEG_REQUIRE(x && out, "sseg_nchw_f32_to_nhwc_bf16: bad argument");
+  dim3 grid((unsigned)(((long)H * W + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, (cudaStream_t)st>>>(x, N, H, W, C, (__nv_bfloat16*)out, ld);
+  LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
+}
+
+}  // extern "C"

@@ -35,9 +35,11 @@ struct IgemmParams {
   int tiles_h, tiles_w, n_tiles;
   void* out;
   int out_f32, ld_out, n_store, cout;
+  long out_row_stride, out_img_stride;
   const float* bias;
   const __nv_bfloat16* addend;
   int ld_addend;
+  long add_row_stride, add_img_stride;
   float* stat_sum;
   float* stat_sqsum;
 };
@@ -149,7 +151,8 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
     const int row = quarter * 32 + lane;
     const int hh = h0 + (row >> p.bw_shift), ww = w0 + (row & (p.BW - 1));
     const bool valid = (hh < p.H) && (ww < p.W);
-    const size_t pix = (static_cast<size_t>(img) * p.H + hh) * p.W + ww;
+    const size_t out_off = img * p.out_img_stride + hh * p.out_row_stride + static_cast<size_t>(ww) * p.ld_out;
+    const size_t add_off = img * p.add_img_stride + hh * p.add_row_stride + static_cast<size_t>(ww) * p.ld_addend;
     const bool do_stats = p.stat_sum != nullptr;
 
     mbar_wait(tmem_full_bar, 0);
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
           if (col0 + j < p.cout) v[j] += __ldg(p.bias + col0 + j);
       }
       if (p.addend != nullptr && valid) {
-        const __nv_bfloat16* ap = p.addend + pix * p.ld_addend + col0;
+        const __nv_bfloat16* ap = p.addend + add_off + col0;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (col0 + g * 8 < p.n_store) {
@@ -186,13 +189,13 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
       }
       if (valid) {
         if (p.out_f32) {
-          float* op = reinterpret_cast<float*>(p.out) + pix * p.ld_out + col0;
+          float* op = reinterpret_cast<float*>(p.out) + out_off + col0;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             if (col0 + g * 4 < p.n_store)
               *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
         } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + pix * p.ld_out + col0;
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + col0;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             if (col0 + g * 8 < p.n_store) {
@@ -270,10 +273,11 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
 struct GeomHost {
   int vn, vh, vw, BH, BW, bw_shift, tiles_h, tiles_w;
   int cin_total, blocks_per_tap, chan_per_src;
+  bool flat;
 };
 
-static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, GeomHost* gh, CUtensorMap* tmA, int* src_blk_end,
-                      const char* who) {
+static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, bool others_dense, GeomHost* gh, CUtensorMap* tmA,
+                      int* src_blk_end, const char* who) {
   SSEG_REQUIRE(g != nullptr, "%s: null geometry", who);
   SSEG_REQUIRE(g->nsrc >= 1 && g->nsrc <= SSEG_MAX_SRCS, "%s: nsrc=%d out of range", who, g->nsrc);
   SSEG_REQUIRE(g->ntaps >= 1 && g->ntaps <= SSEG_MAX_TAPS, "%s: ntaps=%d out of range", who, g->ntaps);
@@ -290,7 +294,10 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, GeomHost* gh, C
   }
   // 1x1 convs see the whole batch as one long row of pixels (no halo, no per-image tiling waste)
   gh->vn = N, gh->vh = H, gh->vw = W;
-  if (pointwise) gh->vn = 1, gh->vh = 1, gh->vw = N * H * W;
+  bool all_dense = others_dense;
+  for (int s = 0; s < g->nsrc; ++s) all_dense = all_dense && act_is_dense(g->srcs[s]);
+  gh->flat = pointwise && all_dense;
+  if (gh->flat) gh->vn = 1, gh->vh = 1, gh->vw = N * H * W;
   int BW = box_pixels;
   while (BW > 8 && BW / 2 >= gh->vw) BW /= 2;  // smallest power of two >= W, in [8, box_pixels]
   gh->BW = BW, gh->BH = box_pixels / BW;
@@ -304,7 +311,10 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, GeomHost* gh, C
     SSEG_REQUIRE(a.c % kBlockK == 0 && a.c > 0, "%s: source %d channels %d not a multiple of 64", who, s, a.c);
     SSEG_REQUIRE(a.ld % 8 == 0 && a.ld >= a.c, "%s: source %d ld %d invalid", who, s, a.ld);
     SSEG_REQUIRE(!any_fixed || a.c == g->srcs[0].c, "%s: per-tap sources must have equal channels", who);
-    int rc = get_tmap_act(&tmA[s], a.ptr, 2, gh->vn, gh->vh, gh->vw, a.c, a.ld, kBlockK, BW, gh->BH);
+    int rc = gh->flat ? get_tmap_act(&tmA[s], a.ptr, 2, 1, 1, gh->vw, a.c, a.ld, (long)gh->vw * a.ld,
+                                     (long)gh->vw * a.ld, kBlockK, BW, gh->BH)
+                      : get_tmap_act(&tmA[s], a.ptr, 2, N, H, W, a.c, a.ld, a.row_stride, a.img_stride, kBlockK, BW,
+                                     gh->BH);
     if (rc) return rc;
     cin_total += a.c;
     src_blk_end[s] = cin_total / kBlockK;
@@ -319,18 +329,23 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, GeomHost* gh, C
 
 using namespace sseg;
 
-extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, void* out,
-                               int out_f32, int ld_out, int n_store, const float* bias, const void* addend,
-                               int ld_addend, float* stat_sum, float* stat_sqsum, sseg_stream_t stream_) {
+extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                               const sseg_act_t* out, int out_f32, const float* bias, const sseg_act_t* addend,
+                               float* stat_sum, float* stat_sqsum, sseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  SSEG_REQUIRE(cout >= 1 && n_store >= cout && n_store % 8 == 0 && n_store <= ld_out,
-               "sseg_conv_igemm: need cout <= n_store (mult of 8) <= ld_out, got %d %d %d", cout, n_store, ld_out);
+  SSEG_REQUIRE(g != nullptr && out != nullptr && w_bf16 != nullptr, "sseg_conv_igemm: null argument");
+  const int n_store = out->c;
+  SSEG_REQUIRE(cout >= 1 && n_store >= cout && n_store % 8 == 0 && n_store <= out->ld,
+               "sseg_conv_igemm: need cout <= out->c (mult of 8) <= out->ld, got %d %d %d", cout, n_store, out->ld);
   SSEG_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "sseg_conv_igemm: stat_sum/stat_sqsum must pair");
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   GeomHost gh;
-  int rc = setup_geom(g, kBlockM, &gh, p.tmA, p.src_blk_end, "sseg_conv_igemm");
+  const bool others_dense = act_is_dense(*out) && (addend == nullptr || act_is_dense(*addend));
+  int rc = setup_geom(g, kBlockM, others_dense, &gh, p.tmA, p.src_blk_end, "sseg_conv_igemm");
   if (rc) return rc;
+  SSEG_REQUIRE(out->n == g->srcs[0].n && out->h == g->srcs[0].h && out->w == g->srcs[0].w,
+               "sseg_conv_igemm: output shape mismatch");
   p.BH = gh.BH, p.BW = gh.BW, p.bw_shift = gh.bw_shift;
   p.N = gh.vn, p.H = gh.vh, p.W = gh.vw;
   p.tiles_h = gh.tiles_h, p.tiles_w = gh.tiles_w;
@@ -349,15 +364,23 @@ extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, lo
   p.n_tiles = ceil_div(n_store, block_n);
   rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, block_n);
   if (rc) return rc;
-  p.out = out, p.out_f32 = out_f32, p.ld_out = ld_out, p.n_store = n_store, p.cout = cout;
+  const int esz = out_f32 ? 4 : 2;
+  p.out = out->ptr, p.out_f32 = out_f32, p.ld_out = out->ld, p.n_store = n_store, p.cout = cout;
+  p.out_row_stride = out->row_stride, p.out_img_stride = out->img_stride;
   p.bias = bias;
-  p.addend = static_cast<const __nv_bfloat16*>(addend);
-  p.ld_addend = ld_addend;
-  p.stat_sum = stat_sum, p.stat_sqsum = stat_sqsum;
-  SSEG_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ld_out * (out_f32 ? 4 : 2)) % 16 == 0,
+  SSEG_REQUIRE((reinterpret_cast<uintptr_t>(out->ptr) & 15) == 0 && (out->ld * esz) % 16 == 0 &&
+                   (out->row_stride * esz) % 16 == 0 && (out->img_stride * esz) % 16 == 0,
                "sseg_conv_igemm: output not 16B aligned");
-  SSEG_REQUIRE(addend == nullptr || ((reinterpret_cast<uintptr_t>(addend) & 15) == 0 && ld_addend % 8 == 0),
-               "sseg_conv_igemm: addend not 16B aligned");
+  if (addend != nullptr) {
+    SSEG_REQUIRE(addend->n == out->n && addend->h == out->h && addend->w == out->w && addend->c >= n_store,
+                 "sseg_conv_igemm: addend shape mismatch");
+    SSEG_REQUIRE((reinterpret_cast<uintptr_t>(addend->ptr) & 15) == 0 && addend->ld % 8 == 0 &&
+                     addend->row_stride % 8 == 0 && addend->img_stride % 8 == 0,
+                 "sseg_conv_igemm: addend not 16B aligned");
+    p.addend = static_cast<const __nv_bfloat16*>(addend->ptr);
+    p.ld_addend = addend->ld, p.add_row_stride = addend->row_stride, p.add_img_stride = addend->img_stride;
+  }
+  p.stat_sum = stat_sum, p.stat_sqsum = stat_sqsum;
   const int grid = gh.vn * p.tiles_h * p.tiles_w * p.n_tiles;
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);
@@ -565,13 +588,16 @@ extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, 
   WgradParams p;
   memset(&p, 0, sizeof(p));
   GeomHost gh;
-  int rc = setup_geom(g, kWgKPix, &gh, p.tmX, p.src_blk_end, "sseg_conv_wgrad");
+  int rc = setup_geom(g, kWgKPix, act_is_dense(*dy), &gh, p.tmX, p.src_blk_end, "sseg_conv_wgrad");
   if (rc) return rc;
   SSEG_REQUIRE(dy->n == g->srcs[0].n && dy->h == g->srcs[0].h && dy->w == g->srcs[0].w,
                "sseg_conv_wgrad: dy shape mismatch");
   SSEG_REQUIRE(dy->c % 8 == 0 && dy->ld % 8 == 0 && dy->ld >= dy->c, "sseg_conv_wgrad: dy channels/ld must be x8");
   SSEG_REQUIRE((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && dw_ld % 4 == 0, "sseg_conv_wgrad: dw not 16B aligned");
-  rc = get_tmap_act(&p.tmDY, dy->ptr, 2, gh.vn, gh.vh, gh.vw, dy->c, dy->ld, 64, gh.BW, gh.BH);
+  rc = gh.flat ? get_tmap_act(&p.tmDY, dy->ptr, 2, 1, 1, gh.vw, dy->c, dy->ld, (long)gh.vw * dy->ld,
+                              (long)gh.vw * dy->ld, 64, gh.BW, gh.BH)
+               : get_tmap_act(&p.tmDY, dy->ptr, 2, dy->n, dy->h, dy->w, dy->c, dy->ld, dy->row_stride, dy->img_stride,
+                              64, gh.BW, gh.BH);
   if (rc) return rc;
   p.nsrc = g->nsrc;
   p.ntaps = g->ntaps;

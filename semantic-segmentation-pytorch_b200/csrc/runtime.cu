@@ -114,10 +114,10 @@ static int encode(CUtensorMap* out, const void* ptr, int elem_bytes, int rank, c
   return 0;
 }
 
-int get_tmap_act(CUtensorMap* out, const void* ptr, int elem_bytes, int n, int h, int w, int c, int ld, int box_c,
-                 int box_w, int box_h) {
+int get_tmap_act(CUtensorMap* out, const void* ptr, int elem_bytes, int n, int h, int w, int c, long ld,
+                 long row_stride, long img_stride, int box_c, int box_w, int box_h) {
   uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-  uint64_t strides[3] = {(uint64_t)ld * elem_bytes, (uint64_t)w * ld * elem_bytes, (uint64_t)h * w * ld * elem_bytes};
+  uint64_t strides[3] = {(uint64_t)ld * elem_bytes, (uint64_t)row_stride * elem_bytes, (uint64_t)img_stride * elem_bytes};
   uint32_t box[4] = {(uint32_t)box_c, (uint32_t)box_w, (uint32_t)box_h, 1u};
   return encode(out, ptr, elem_bytes, 4, dims, strides, box);
 }

@@ -20,7 +20,8 @@ class SsegError(RuntimeError):
 
 class Act(Structure):
     """sseg_act_t: NHWC activation view."""
-    _fields_ = [("ptr", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int), ("c", c_int), ("ld", c_int)]
+    _fields_ = [("ptr", c_void_p), ("n", c_int), ("h", c_int), ("w", c_int), ("c", c_int), ("ld", c_int),
+                ("row_stride", c_long), ("img_stride", c_long)]
 
 
 class Geom(Structure):
@@ -71,8 +72,31 @@ def ptr(t):
 _p = c_void_p
 _ip = POINTER(c_int)
 _SIGNATURES = {
-    "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, _p, c_int, c_int, c_int, _p, _p, c_int, _p, _p, _p],
+    "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), c_int, _p, POINTER(Act), _p, _p, _p],
     "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
+    "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],
+    "sseg_grad_to_oihw": [_p, c_long, c_int, c_int, c_int, _p, c_float, c_int, _p],
+    "sseg_stem_conv_fwd": [_p, c_int, c_int, c_int, _p, _p, _p, _p, _p],
+    "sseg_stem_conv_wgrad": [_p, c_int, c_int, c_int, _p, _p, _p],
+    "sseg_bn_finalize": [_p, _p, _p, c_float, _p, _p, c_float, c_float, c_int, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p,
+                         c_int, _p],
+    "sseg_bn_apply": [_p, c_long, _p, _p, _p, c_long, _p, _p, _p, _p, c_long, c_long, c_long, c_int, c_int, _p],
+    "sseg_bn_bwd_reduce": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, c_long, c_long, c_int, _p],
+    "sseg_bn_bwd_apply": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, c_float, _p, c_long, _p, c_long,
+                          c_long, c_long, c_int, c_int, _p],
+    "sseg_maxpool_fwd": [_p, c_int, c_int, c_int, c_int, _p, _p, _p],
+    "sseg_maxpool_bwd": [_p, _p, _p, c_int, c_int, c_int, c_int, _p],
+    "sseg_avgpool_fwd": [_p, c_long, c_int, c_int, c_int, c_int, c_int, _p, _p],
+    "sseg_avgpool_bwd": [_p, c_long, POINTER(c_void_p), _ip, c_int, _p, c_long, c_int, c_int, c_int, c_int, _p],
+    "sseg_bilinear_fwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, _p],
+    "sseg_bilinear_bwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, c_int, _p],
+    "sseg_softmax_nll_fwd": [_p, c_long, c_int, _p, c_long, _p, _p, _p],
+    "sseg_nll_finalize": [_p, _p, c_float, _p, _p],
+    "sseg_softmax_nll_bwd": [_p, c_long, c_int, _p, _p, _p, c_float, c_long, _p, c_long, c_int, _p],
+    "sseg_colsum": [_p, c_long, c_long, c_int, _p, _p],
+    "sseg_upsample_softmax": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_int, c_int, c_float, c_int, _p],
+    "sseg_nhwc_bf16_to_nchw_f32": [_p, c_long, c_int, c_int, c_int, c_int, _p, _p],
+    "sseg_nchw_f32_to_nhwc_bf16": [_p, c_int, c_int, c_int, c_int, _p, c_long, _p],
 }
 
 EXPORTED_SYMBOLS = ["sseg_last_error", "sseg_version", "sseg_launch_count", "sseg_launch_count_reset"] + list(

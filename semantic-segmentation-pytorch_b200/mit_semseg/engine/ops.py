@@ -18,9 +18,7 @@ def act(t):
     """NHWC tensor (possibly a channel slice) -> sseg_act_t."""
     assert t.dim() == 4 and t.stride(3) == 1, "expected NHWC with contiguous channels"
     n, h, w, c = t.shape
-    ld = t.stride(2)
-    assert t.stride(1) == w * ld and t.stride(0) == h * w * ld, "expected dense NHWC pixels"
-    return _C.Act(_C.c_void_p(t.data_ptr()), n, h, w, c, ld)
+    return _C.Act(_C.c_void_p(t.data_ptr()), n, h, w, c, t.stride(2), t.stride(1), t.stride(0))
 
 
 def conv_taps(ksize, dilation):
@@ -58,9 +56,9 @@ def conv_igemm(geom, w_bf16, cout, out, n_store=None, bias=None, addend=None, st
         n_store = (cout + 7) // 8 * 8
     assert out.dtype in (torch.float32, torch.bfloat16) and w_bf16.dim() == 2 and w_bf16.stride(1) == 1
     out_f32 = 1 if out.dtype == torch.float32 else 0
-    ld_add = addend.stride(2) if addend is not None else 0
-    _C.check(_C.lib().sseg_conv_igemm(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, _C.ptr(out), out_f32,
-                                      out.stride(2), n_store, _C.ptr(bias), _C.ptr(addend), ld_add,
+    o = act(out[..., :n_store])
+    a = act(addend) if addend is not None else None
+    _C.check(_C.lib().sseg_conv_igemm(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, o, out_f32, _C.ptr(bias), a,
                                       _C.ptr(stat_sum), _C.ptr(stat_sqsum), _stream()))
     return out
 
@@ -71,3 +69,187 @@ def conv_wgrad(geom, dy, cout, dw):
     a = act(dy)
     _C.check(_C.lib().sseg_conv_wgrad(geom, a, cout, _C.ptr(dw), dw.stride(0), _stream()))
     return dw
+
+
+# ---------------------------------------------------------------------------------------------------------
+# helpers for dense [pixels][ld] views
+def _pix(t):
+    """(P, pixels-per-image, ld) of a pixel-dense NHWC tensor (channel slices allowed)."""
+    n, h, w, _ = t.shape
+    ld = t.stride(2)
+    assert t.stride(3) == 1 and t.stride(1) == w * ld and t.stride(0) == h * w * ld, "expected pixel-dense NHWC"
+    return n * h * w, h * w, ld
+
+
+def conv_s2_taps(ksize):
+    """Stride-2 'same' conv (pad = ksize//2) over the 4 parity planes x[:, hp::2, wp::2]: per tap (dh, dw, plane)."""
+    r = ksize // 2
+    dh, dw, src = [], [], []
+    for i in range(ksize):
+        for j in range(ksize):
+            oh, ow = i - r, j - r  # input row = 2*ho + oh
+            hp, wp = oh % 2, ow % 2
+            dh.append((oh - hp) // 2)
+            dw.append((ow - wp) // 2)
+            src.append(hp * 2 + wp)
+    return dh, dw, src
+
+
+def parity_planes(x):
+    """The 4 strided views x[:, hp::2, wp::2, :] (no copy), index hp*2+wp."""
+    return [x[:, hp::2, wp::2, :] for hp in (0, 1) for wp in (0, 1)]
+
+
+def prep_conv_weight(w, w_fwd=None, w_dgrad=None, o_pad=None):
+    """fp32 OIHW -> bf16 [O, T*I] and/or bf16 [I, T*o_pad] (w_dgrad must have been zero-initialised)."""
+    O, I, kh, kw = w.shape
+    T = kh * kw
+    assert w.is_contiguous() and w.dtype == torch.float32
+    if o_pad is None:
+        o_pad = (O + 63) // 64 * 64
+    _C.check(_C.lib().sseg_prep_conv_weight(_C.ptr(w), O, I, T, _C.ptr(w_fwd), w_fwd.stride(0) if w_fwd is not None else 0,
+                                            _C.ptr(w_dgrad), w_dgrad.stride(0) if w_dgrad is not None else 0, o_pad,
+                                            _stream()))
+
+
+def grad_to_oihw(g, O, I, T, out, scale=1.0, accumulate=False):
+    _C.check(_C.lib().sseg_grad_to_oihw(_C.ptr(g), g.stride(0), O, I, T, _C.ptr(out), scale, int(accumulate), _stream()))
+
+
+def stem_conv_fwd(img, w, out, stat_sum=None, stat_sqsum=None):
+    n, c, h, w_ = img.shape
+    assert c == 3 and img.is_contiguous() and img.dtype == torch.float32 and w.shape == (64, 3, 3, 3)
+    _C.check(_C.lib().sseg_stem_conv_fwd(_C.ptr(img), n, h, w_, _C.ptr(w), _C.ptr(out), _C.ptr(stat_sum),
+                                         _C.ptr(stat_sqsum), _stream()))
+
+
+def stem_conv_wgrad(img, dy, dw):
+    n, c, h, w_ = img.shape
+    assert dy.is_contiguous() and dw.is_contiguous()
+    _C.check(_C.lib().sseg_stem_conv_wgrad(_C.ptr(img), n, h, w_, _C.ptr(dy), _C.ptr(dw), _stream()))
+
+
+BN_TRAIN, BN_TRAIN_SYNC, BN_EVAL = 0, 1, 2
+
+
+def bn_finalize(ssum, ssq, count, gamma, beta, eps, momentum, mode, mean, invstd, scale, shift, running=None,
+                update_running=False, count_dev=None):
+    """running = (running_mean, running_var, tmp_running_mean, tmp_running_var, running_iter) or None."""
+    rm = rv = tm = tv = it = None
+    if running is not None:
+        rm, rv, tm, tv, it = running
+    _C.check(_C.lib().sseg_bn_finalize(_C.ptr(ssum), _C.ptr(ssq), _C.ptr(count_dev), float(count), _C.ptr(gamma),
+                                       _C.ptr(beta), eps, momentum, mode, int(update_running), _C.ptr(rm), _C.ptr(rv),
+                                       _C.ptr(tm), _C.ptr(tv), _C.ptr(it), _C.ptr(mean), _C.ptr(invstd), _C.ptr(scale),
+                                       _C.ptr(shift), scale.numel(), _stream()))
+
+
+def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None, chanmul=None):
+    P, ppi, y_ld = _pix(y)
+    _, _, out_ld = _pix(out)
+    res_ld = _pix(res)[2] if res is not None else 0
+    _C.check(_C.lib().sseg_bn_apply(_C.ptr(y), y_ld, _C.ptr(scale), _C.ptr(shift), _C.ptr(res), res_ld, _C.ptr(rscale),
+                                    _C.ptr(rshift), _C.ptr(chanmul), _C.ptr(out), out_ld, P, ppi, y.shape[3], int(relu),
+                                    _stream()))
+    return out
+
+
+def bn_bwd_reduce(g, a, y, mean, invstd, s1, s2, chanmul=None):
+    P, ppi, g_ld = _pix(g)
+    a_ld = _pix(a)[2] if a is not None else 0
+    _C.check(_C.lib().sseg_bn_bwd_reduce(_C.ptr(g), g_ld, _C.ptr(a), a_ld, _C.ptr(y), _pix(y)[2], _C.ptr(mean),
+                                         _C.ptr(invstd), _C.ptr(chanmul), _C.ptr(s1), _C.ptr(s2), P, ppi, g.shape[3],
+                                         _stream()))
+
+
+def bn_bwd_apply(g, a, y, mean, invstd, scale, s1, s2, count, dy, dres=None, chanmul=None, eval_mode=False,
+                 count_dev=None):
+    P, ppi, g_ld = _pix(g)
+    a_ld = _pix(a)[2] if a is not None else 0
+    y_ld = _pix(y)[2] if y is not None else 0
+    dres_ld = _pix(dres)[2] if dres is not None else 0
+    _C.check(_C.lib().sseg_bn_bwd_apply(_C.ptr(g), g_ld, _C.ptr(a), a_ld, _C.ptr(y), y_ld, _C.ptr(mean), _C.ptr(invstd),
+                                        _C.ptr(scale), _C.ptr(chanmul), _C.ptr(s1), _C.ptr(s2), _C.ptr(count_dev),
+                                        float(count), _C.ptr(dy), _pix(dy)[2], _C.ptr(dres), dres_ld, P, ppi, g.shape[3],
+                                        int(eval_mode), _stream()))
+
+
+def maxpool_fwd(x, out, idx):
+    n, h, w, c = x.shape
+    assert x.is_contiguous() and out.is_contiguous()
+    _C.check(_C.lib().sseg_maxpool_fwd(_C.ptr(x), n, h, w, c, _C.ptr(out), _C.ptr(idx), _stream()))
+
+
+def maxpool_bwd(dout, idx, dx):
+    n, h, w, c = dx.shape
+    assert dout.is_contiguous() and dx.is_contiguous()
+    _C.check(_C.lib().sseg_maxpool_bwd(_C.ptr(dout), _C.ptr(idx), _C.ptr(dx), n, h, w, c, _stream()))
+
+
+def avgpool_fwd(x, S, out):
+    n, h, w, c = x.shape
+    assert out.is_contiguous() and out.shape == (n, S, S, c)
+    _C.check(_C.lib().sseg_avgpool_fwd(_C.ptr(x), _pix(x)[2], n, h, w, c, S, _C.ptr(out), _stream()))
+
+
+def avgpool_bwd(base, dpools, scales, dx):
+    n, h, w, c = dx.shape
+    arr = (_C.c_void_p * len(dpools))(*[d.data_ptr() for d in dpools])
+    _C.check(_C.lib().sseg_avgpool_bwd(_C.ptr(base), _pix(base)[2] if base is not None else 0, arr,
+                                       _C.int_array(list(scales)), len(dpools), _C.ptr(dx), _pix(dx)[2], n, h, w, c,
+                                       _stream()))
+
+
+def bilinear_fwd(x, out):
+    n, hi, wi, c = x.shape
+    _, ho, wo, _ = out.shape
+    _C.check(_C.lib().sseg_bilinear_fwd(_C.ptr(x), _pix(x)[2], n, hi, wi, c, _C.ptr(out), _pix(out)[2], ho, wo, _stream()))
+
+
+def bilinear_bwd(dout, dx, accumulate=False):
+    n, ho, wo, c = dout.shape
+    _, hi, wi, _ = dx.shape
+    _C.check(_C.lib().sseg_bilinear_bwd(_C.ptr(dout), _pix(dout)[2], n, ho, wo, c, _C.ptr(dx), _pix(dx)[2], hi, wi,
+                                        int(accumulate), _stream()))
+
+
+def softmax_nll_fwd(logits, num_class, label, lse, accum):
+    P, _, ld = _pix(logits)
+    assert label.dtype == torch.int64 and label.is_contiguous() and label.numel() == P
+    _C.check(_C.lib().sseg_softmax_nll_fwd(_C.ptr(logits), ld, num_class, _C.ptr(label), P, _C.ptr(lse), _C.ptr(accum),
+                                           _stream()))
+
+
+def nll_finalize(accum_main, accum_ds, ds_scale, out):
+    _C.check(_C.lib().sseg_nll_finalize(_C.ptr(accum_main), _C.ptr(accum_ds), float(ds_scale or 0.0), _C.ptr(out),
+                                        _stream()))
+
+
+def softmax_nll_bwd(logits, num_class, label, lse, accum, weight, dlogits):
+    P, _, ld = _pix(logits)
+    _C.check(_C.lib().sseg_softmax_nll_bwd(_C.ptr(logits), ld, num_class, _C.ptr(label), _C.ptr(lse), _C.ptr(accum),
+                                           float(weight), P, _C.ptr(dlogits), _pix(dlogits)[2], dlogits.shape[3],
+                                           _stream()))
+
+
+def colsum(x, C, out):
+    P, _, ld = _pix(x)
+    _C.check(_C.lib().sseg_colsum(_C.ptr(x), ld, P, C, _C.ptr(out), _stream()))
+
+
+def upsample_softmax(logits, num_class, probs, weight=1.0, accumulate=False):
+    n, hi, wi, _ = logits.shape
+    _, c, ho, wo = probs.shape
+    assert c == num_class and probs.is_contiguous() and probs.dtype == torch.float32
+    _C.check(_C.lib().sseg_upsample_softmax(_C.ptr(logits), _pix(logits)[2], n, hi, wi, num_class, _C.ptr(probs), ho, wo,
+                                            float(weight), int(accumulate), _stream()))
+
+
+def nhwc_bf16_to_nchw_f32(x, out):
+    n, h, w, c = x.shape
+    _C.check(_C.lib().sseg_nhwc_bf16_to_nchw_f32(_C.ptr(x), _pix(x)[2], n, h, w, c, _C.ptr(out), _stream()))
+
+
+def nchw_f32_to_nhwc_bf16(x, out):
+    n, c, h, w = x.shape
+    _C.check(_C.lib().sseg_nchw_f32_to_nhwc_bf16(_C.ptr(x), n, h, w, c, _C.ptr(out), _pix(out)[2], _stream()))

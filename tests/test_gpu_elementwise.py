@@ -1,0 +1,259 @@
+"""-m gpu: the HBM-bound kernels (BN, pooling, resize, stem conv, loss, layout) against torch fp32 on the same device.
+Inputs are bf16-rounded first; outputs are compared within bf16 rounding (2^-8 relative to the tensor scale) unless
+the kernel's output is fp32, where 1e-4 relative applies."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _gen(seed=0):
+    return torch.Generator(device=DEV).manual_seed(seed)
+
+
+def _close(got, ref, rel, what=""):
+    scale = max(ref.abs().max().item(), 1e-6)
+    err = (got.float() - ref.float()).abs().max().item()
+    assert err <= rel * scale, "%s: max err %g > %g (scale %g)" % (what, err, rel * scale, scale)
+
+
+def nchw(t):
+    return t.float().permute(0, 3, 1, 2).contiguous()
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous()
+
+
+def test_prep_weight_and_grad_layout():
+    from mit_semseg.engine import ops
+    g = _gen()
+    w = torch.randn(150, 128, 3, 3, device=DEV, generator=g)
+    wf = torch.empty(150, 9 * 128, device=DEV, dtype=torch.bfloat16)
+    wd = torch.zeros(128, 9 * 192, device=DEV, dtype=torch.bfloat16)
+    ops.prep_conv_weight(w, wf, wd, o_pad=192)
+    ref_f = w.permute(0, 2, 3, 1).reshape(150, -1).bfloat16()
+    assert torch.equal(wf, ref_f)
+    ref_d = torch.zeros(128, 9, 192, device=DEV)
+    ref_d[:, :, :150] = w.permute(1, 2, 3, 0).reshape(128, 9, 150)
+    assert torch.equal(wd, ref_d.reshape(128, -1).bfloat16())
+    gsrc = torch.randn(150, 9 * 128, device=DEV, generator=g)
+    out = torch.ones(150, 128, 3, 3, device=DEV)
+    ops.grad_to_oihw(gsrc, 150, 128, 9, out, scale=0.5, accumulate=True)
+    ref = 1.0 + 0.5 * gsrc.reshape(150, 3, 3, 128).permute(0, 3, 1, 2)
+    _close(out, ref, 1e-6, "grad_to_oihw")
+
+
+def test_stem_conv_fwd_and_wgrad():
+    from mit_semseg.engine import ops
+    g = _gen(1)
+    img = torch.randn(2, 3, 70, 96, device=DEV, generator=g)
+    w = torch.randn(64, 3, 3, 3, device=DEV, generator=g) * 0.2
+    ref = F.conv2d(img, w, stride=2, padding=1)
+    ho, wo = ref.shape[2:]
+    out = torch.empty(2, ho, wo, 64, device=DEV, dtype=torch.bfloat16)
+    ssum, ssq = torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
+    ops.stem_conv_fwd(img, w, out, ssum, ssq)
+    _close(nchw(out), ref, 2 ** -8, "stem fwd")
+    _close(ssum, ref.sum(dim=(0, 2, 3)), 1e-3, "stem sum")
+    _close(ssq, (ref * ref).sum(dim=(0, 2, 3)), 1e-3, "stem sqsum")
+    dy = (torch.randn(2, ho, wo, 64, device=DEV, generator=g) * 0.1).bfloat16()
+    wp = w.clone().requires_grad_(True)
+    (gref,) = torch.autograd.grad(F.conv2d(img, wp, stride=2, padding=1), wp, nchw(dy))
+    dw = torch.zeros(64, 3, 3, 3, device=DEV)
+    ops.stem_conv_wgrad(img, dy, dw)
+    _close(dw, gref, 1e-4, "stem wgrad")
+
+
+@pytest.mark.parametrize("C,hw", [(64, 40), (256, 24), (2048, 8)])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_bn_forward_backward(C, hw, mode):
+    """conv-output y -> BN(train) -> (+res) -> ReLU -> dropout-mask; backward against autograd of the same graph."""
+    from mit_semseg.engine import ops
+    g = _gen(C + mode)
+    n = 2
+    y = (torch.randn(n, hw, hw, C, device=DEV, generator=g) * 2 + 0.5).bfloat16()
+    res = torch.randn(n, hw, hw, C, device=DEV, generator=g).bfloat16()
+    gamma = torch.rand(C, device=DEV, generator=g) + 0.5
+    beta = torch.randn(C, device=DEV, generator=g) * 0.1
+    mask = (torch.rand(n, C, device=DEV, generator=g) > 0.1).float() / 0.9
+    eps, mom = 1e-5, 0.001
+    yf = y.float()
+    ssum, ssq = yf.sum(dim=(0, 1, 2)), (yf * yf).sum(dim=(0, 1, 2))
+    cnt = n * hw * hw
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    tm, tv, it = rm.clone(), rv.clone(), torch.ones(1, device=DEV)
+    mean, invstd, scale, shift = [torch.empty(C, device=DEV) for _ in range(4)]
+    ops.bn_finalize(ssum, ssq, cnt, gamma, beta, eps, mom, mode, mean, invstd, scale, shift, running=(rm, rv, tm, tv, it),
+                    update_running=True)
+    # reference statistics
+    m_ref = yf.mean(dim=(0, 1, 2))
+    v_ref = yf.var(dim=(0, 1, 2), unbiased=False)
+    inv_ref = (v_ref + eps).rsqrt() if mode == 0 else v_ref.clamp(min=eps).rsqrt()
+    _close(mean, m_ref, 1e-4, "mean")
+    _close(invstd, inv_ref, 1e-3, "invstd")
+    unb = v_ref * cnt / (cnt - 1)
+    if mode == 0:
+        _close(rm, mom * m_ref, 1e-3, "running_mean")
+        _close(rv, (1 - mom) + mom * unb, 1e-4, "running_var")
+    else:
+        it_ref = 1 * (1 - mom) + 1
+        _close(rm, (0 * (1 - mom) + m_ref) / it_ref, 1e-3, "sync running_mean")
+        _close(rv, (1 * (1 - mom) + unb) / it_ref, 1e-3, "sync running_var")
+        _close(it, torch.full((1,), it_ref, device=DEV), 1e-6, "running_iter")
+    out = torch.empty_like(y)
+    ops.bn_apply(y, scale, shift, out, relu=True, res=res, chanmul=mask)
+    # autograd reference of the same graph, using the kernel's own (mean, invstd) definition
+    yv = yf.clone().requires_grad_(True)
+    rr = res.float().clone().requires_grad_(True)
+    mu = yv.mean(dim=(0, 1, 2))
+    var = yv.var(dim=(0, 1, 2), unbiased=False)
+    inv = (var + eps).rsqrt() if mode == 0 else var.clamp(min=eps).rsqrt()
+    z = torch.relu((yv - mu) * inv * gamma + beta + rr) * mask.view(n, 1, 1, C)
+    _close(out, z.detach(), 2 ** -7, "bn_apply")
+    gout = (torch.randn(n, hw, hw, C, device=DEV, generator=g)).bfloat16()
+    dy_ref, dres_ref = torch.autograd.grad(z, (yv, rr), gout.float())
+    s1, s2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+    ops.bn_bwd_reduce(gout, out, y, mean, invstd, s1, s2, chanmul=mask)
+    dy, dres = torch.empty_like(y), torch.empty_like(y)
+    ops.bn_bwd_apply(gout, out, y, mean, invstd, scale, s1, s2, cnt, dy, dres=dres, chanmul=mask)
+    # note: the kernel masks with the *stored bf16* output (a > 0); sub-ulp outputs can flip, hence the tolerance
+    _close(dres, dres_ref, 2 ** -6, "dres")
+    _close(dy, dy_ref, 2 ** -5, "dy")
+    # dgamma / dbeta are s2 / s1
+    gam = gamma.clone().requires_grad_(True)
+    bet = beta.clone().requires_grad_(True)
+    z2 = torch.relu((yf - m_ref) * inv_ref * gam + bet + res.float()) * mask.view(n, 1, 1, C)
+    dg, db = torch.autograd.grad(z2, (gam, bet), gout.float())
+    _close(s2, dg, 2e-2, "dgamma")
+    _close(s1, db, 2e-2, "dbeta")
+
+
+def test_bn_eval_mode():
+    from mit_semseg.engine import ops
+    g = _gen(5)
+    C = 128
+    y = torch.randn(2, 16, 16, C, device=DEV, generator=g).bfloat16()
+    gamma, beta = torch.rand(C, device=DEV, generator=g) + 0.5, torch.randn(C, device=DEV, generator=g)
+    rm, rv = torch.randn(C, device=DEV, generator=g) * 0.1, torch.rand(C, device=DEV, generator=g) + 0.5
+    mean, invstd, scale, shift = [torch.empty(C, device=DEV) for _ in range(4)]
+    ops.bn_finalize(None, None, 1, gamma, beta, 1e-5, 0.001, 2, mean, invstd, scale, shift, running=(rm, rv, None, None, None))
+    out = torch.empty_like(y)
+    ops.bn_apply(y, scale, shift, out, relu=False)
+    ref = F.batch_norm(nchw(y), rm, rv, gamma, beta, False, 0.0, 1e-5)
+    _close(nchw(out), ref, 2 ** -8, "bn eval")
+
+
+def test_maxpool():
+    from mit_semseg.engine import ops
+    g = _gen(2)
+    x = torch.randn(2, 37, 50, 128, device=DEV, generator=g).bfloat16()
+    xr = nchw(x).requires_grad_(True)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    ho, wo = ref.shape[2:]
+    out = torch.empty(2, ho, wo, 128, device=DEV, dtype=torch.bfloat16)
+    idx = torch.empty(2, ho, wo, 128, device=DEV, dtype=torch.uint8)
+    ops.maxpool_fwd(x, out, idx)
+    assert torch.equal(nchw(out), ref.detach())
+    dout = torch.randn(2, ho, wo, 128, device=DEV, generator=g).bfloat16()
+    (gref,) = torch.autograd.grad(ref, xr, nchw(dout))
+    dx = torch.empty_like(x)
+    ops.maxpool_bwd(dout, idx, dx)
+    _close(nchw(dx), gref, 2 ** -7, "maxpool bwd")
+
+
+@pytest.mark.parametrize("H,W", [(64, 64), (38, 50)])
+def test_adaptive_avgpool(H, W):
+    from mit_semseg.engine import ops
+    g = _gen(3)
+    C = 256
+    x = torch.randn(2, H, W, C, device=DEV, generator=g).bfloat16()
+    xr = nchw(x).requires_grad_(True)
+    scales = (1, 2, 3, 6)
+    dps, refs = [], []
+    for s in scales:
+        ref = F.adaptive_avg_pool2d(xr, s)
+        out = torch.empty(2, s, s, C, device=DEV, dtype=torch.bfloat16)
+        ops.avgpool_fwd(x, s, out)
+        _close(nchw(out), ref.detach(), 2 ** -8, "avgpool %d" % s)
+        refs.append(ref)
+        dps.append(torch.randn(2, s, s, C, device=DEV, generator=g).bfloat16())
+    base = torch.randn(2, H, W, C, device=DEV, generator=g).bfloat16()
+    gref = torch.autograd.grad(refs, xr, [nchw(d) for d in dps])[0] + nchw(base)
+    dx = torch.empty_like(x)
+    ops.avgpool_bwd(base, dps, scales, dx)
+    _close(nchw(dx), gref, 2 ** -7, "avgpool bwd")
+
+
+@pytest.mark.parametrize("hi,ho", [(1, 64), (2, 64), (3, 64), (6, 64), (6, 38), (16, 32), (8, 8)])
+def test_bilinear(hi, ho):
+    from mit_semseg.engine import ops
+    g = _gen(hi * 100 + ho)
+    C = 64
+    wi, wo = hi + (1 if hi > 2 else 0), ho + 4
+    x = torch.randn(2, hi, wi, C, device=DEV, generator=g).bfloat16()
+    xr = nchw(x).requires_grad_(True)
+    ref = F.interpolate(xr, (ho, wo), mode="bilinear", align_corners=False)
+    out = torch.empty(2, ho, wo, C, device=DEV, dtype=torch.bfloat16)
+    ops.bilinear_fwd(x, out)
+    _close(nchw(out), ref.detach(), 2 ** -7, "bilinear fwd")
+    dout = torch.randn(2, ho, wo, C, device=DEV, generator=g).bfloat16()
+    (gref,) = torch.autograd.grad(ref, xr, nchw(dout))
+    dx = torch.empty_like(x)
+    ops.bilinear_bwd(dout, dx)
+    _close(nchw(dx), gref, 2 ** -7, "bilinear bwd")
+    ops.bilinear_bwd(dout, dx, accumulate=True)
+    _close(nchw(dx), 2 * gref, 2 ** -6, "bilinear bwd accumulate")
+
+
+def test_softmax_nll_and_acc():
+    from mit_semseg.engine import ops
+    g = _gen(4)
+    n, h, w, C, ld = 2, 64, 64, 150, 160
+    logits = torch.zeros(n, h, w, ld, device=DEV)
+    logits[..., :C] = torch.randn(n, h, w, C, device=DEV, generator=g) * 3
+    lg = logits[..., :152]
+    label = torch.randint(-1, C, (n, h, w), device=DEV, generator=g)
+    lse = torch.empty(n * h * w, device=DEV)
+    acc = torch.zeros(3, device=DEV)
+    ops.softmax_nll_fwd(lg, C, label, lse, acc)
+    lr = logits[..., :C].permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    logp = F.log_softmax(lr, dim=1)
+    loss_ref = F.nll_loss(logp, label, ignore_index=-1)
+    valid = label >= 0
+    acc_ref = ((logp.argmax(1) == label) & valid).sum().float() / (valid.sum().float() + 1e-10)
+    out = torch.empty(2, device=DEV)
+    ops.nll_finalize(acc, acc, 0.4, out)
+    _close(out[0], 1.4 * loss_ref.detach(), 1e-5, "loss")
+    _close(out[1], acc_ref, 1e-6, "acc")
+    dl = torch.full((n, h, w, 192), float("nan"), device=DEV, dtype=torch.bfloat16)
+    ops.softmax_nll_bwd(lg, C, label, lse, acc, 0.4, dl)
+    (gref,) = torch.autograd.grad(0.4 * loss_ref, lr)
+    _close(dl[..., :C].float().permute(0, 3, 1, 2), gref, 2 ** -8, "dlogits")
+    assert dl[..., C:].float().abs().max().item() == 0.0
+    bias_g = torch.zeros(C, device=DEV)
+    ops.colsum(dl, C, bias_g)
+    _close(bias_g, dl[..., :C].float().sum(dim=(0, 1, 2)), 1e-4, "colsum")
+
+
+def test_upsample_softmax_and_layout():
+    from mit_semseg.engine import ops
+    g = _gen(6)
+    n, h, w, C = 1, 24, 32, 150
+    logits = torch.zeros(n, h, w, 160, device=DEV)
+    logits[..., :C] = torch.randn(n, h, w, C, device=DEV, generator=g) * 2
+    probs = torch.zeros(n, C, 100, 131, device=DEV)
+    ops.upsample_softmax(logits[..., :152], C, probs, weight=0.2, accumulate=False)
+    ops.upsample_softmax(logits[..., :152], C, probs, weight=0.2, accumulate=True)
+    ref = F.softmax(F.interpolate(logits[..., :C].permute(0, 3, 1, 2), size=(100, 131), mode="bilinear",
+                                  align_corners=False), dim=1) * 0.4
+    _close(probs, ref, 1e-4, "upsample_softmax")
+    x = torch.randn(2, 19, 23, 72, device=DEV, generator=g).bfloat16()
+    o = torch.empty(2, 72, 19, 23, device=DEV)
+    ops.nhwc_bf16_to_nchw_f32(x, o)
+    assert torch.equal(o, nchw(x))
+    back = torch.empty_like(x)
+    ops.nchw_f32_to_nhwc_bf16(o, back)
+    assert torch.equal(back, x)

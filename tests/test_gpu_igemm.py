@@ -142,3 +142,43 @@ def test_wgrad_classifier_padded():
 def test_wgrad_ragged():
     _run_wgrad(2, 38, 50, [64], 128, 3, 2)
     _run_wgrad(3, 6, 6, [128], 64, 3, 1)
+
+
+# ------------------------------------------------------------------ stride-2 convs over parity-plane views
+@pytest.mark.parametrize("k", [1, 3])
+def test_stride2_via_parity_planes(k):
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(7)
+    n, h, w_, cin, cout = 2, 64, 64, 128, 256
+    x = torch.randn(n, h, w_, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.05).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    wr = wt.float().requires_grad_(True)
+    ref = F.conv2d(xr, wr, stride=2, padding=k // 2)
+    dh, dw, src = ops.conv_s2_taps(k)
+    geom = ops.make_geom(ops.parity_planes(x), (dh, dw), tap_src=src, tap_koff=[t * cin for t in range(k * k)])
+    out = torch.empty(n, h // 2, w_ // 2, cout, device="cuda", dtype=torch.bfloat16)
+    ops.conv_igemm(geom, wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous(), cout, out)
+    ref_nhwc = ref.detach().permute(0, 2, 3, 1)
+    assert (out.float() - ref_nhwc).abs().max().item() <= 2 ** -8 * ref_nhwc.abs().max().item()
+    # weight gradient through the same geometry
+    dy = (torch.randn(n, h // 2, w_ // 2, cout, device="cuda", generator=g) * 0.1).bfloat16()
+    gx, gw = torch.autograd.grad(ref, (xr, wr), dy.float().permute(0, 3, 1, 2))
+    dwbuf = torch.zeros(cout, k * k * cin, device="cuda")
+    ops.conv_wgrad(geom, dy, cout, dwbuf)
+    gw_ref = gw.permute(0, 2, 3, 1).reshape(cout, -1)
+    assert (dwbuf - gw_ref).abs().max().item() <= 2e-4 * gw_ref.abs().max().item() + 1e-5
+    # data gradient: one launch per input parity plane, writing straight into the strided plane view of dx
+    wd = torch.zeros(cin, k * k * cout, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weight(wt.float().contiguous(), None, wd, o_pad=cout)
+    dx = torch.zeros(n, h, w_, cin, device="cuda", dtype=torch.bfloat16)
+    planes = ops.parity_planes(dx)
+    for pl in range(4):
+        taps = [t for t in range(k * k) if src[t] == pl]
+        if not taps:
+            continue
+        geom_d = ops.make_geom([dy], ([-dh[t] for t in taps], [-dw[t] for t in taps]),
+                               tap_koff=[t * cout for t in taps])
+        ops.conv_igemm(geom_d, wd, cin, planes[pl])
+    gx_nhwc = gx.permute(0, 2, 3, 1)
+    assert (dx.float() - gx_nhwc).abs().max().item() <= 2 ** -7 * gx_nhwc.abs().max().item()
