@@ -1,0 +1,107 @@
+"""Entry points the nn.Module classes call: they look up (or build) the step program for the input shape, run it, and
+connect its precomputed gradients to autograd.  See engine/program.py for what a program is."""
+import collections
+
+import torch
+
+from .program import SegProgram
+
+_MAX_PROGRAMS = 8  # per module; inference over many image sizes would otherwise pin GBs of activations
+
+
+def _programs(mod):
+    cache = mod.__dict__.get("_b200_programs")
+    if cache is None:
+        cache = collections.OrderedDict()
+        mod.__dict__["_b200_programs"] = cache  # not a Module attribute: invisible to state_dict / replicate
+    return cache
+
+
+def get_program(seg, img_shape, seg_size=None, with_grad=None, dropout_masks=None, capture=None):
+    if with_grad is None:
+        with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in seg.parameters())
+    bn_flags = tuple(m.training for m in seg.modules())
+    key = (tuple(img_shape), seg_size, bool(with_grad), hash(bn_flags), id(dropout_masks))
+    cache = _programs(seg)
+    prog = cache.get(key)
+    if prog is None:
+        prog = SegProgram(seg, tuple(img_shape), training=seg.training, with_grad=with_grad, seg_size=seg_size,
+                          dropout_masks=dropout_masks)
+        if capture if capture is not None else (seg_size is None):
+            prog.capture()  # fixed-shape training steps are replayed as one CUDA graph
+        cache[key] = prog
+        while len(cache) > _MAX_PROGRAMS:
+            cache.popitem(last=False)
+    else:
+        cache.move_to_end(key)
+    return prog
+
+
+class _TrainStep(torch.autograd.Function):
+    """forward = the whole fwd+bwd program (one CUDA-graph replay); backward = hand the gradients to autograd."""
+
+    @staticmethod
+    def forward(ctx, prog, *params):
+        prog.run()
+        ctx.prog, ctx.params = prog, params
+        out = prog.out.clone()
+        loss, acc = out[0], out[1]
+        ctx.mark_non_differentiable(acc)
+        return loss, acc
+
+    @staticmethod
+    def backward(ctx, g_loss, g_acc):
+        prog = ctx.prog
+        if not prog.with_grad:
+            raise RuntimeError("this program was built without a backward schedule")
+        grads = prog.param_grads()
+        gl = [grads[p] for p in ctx.params if p in grads]
+        scaled = torch._foreach_mul(gl, g_loss.to(torch.float32))
+        it = iter(scaled)
+        return (None,) + tuple(next(it) if p in grads else None for p in ctx.params)
+
+
+def segmentation_train_step(seg, img, label):
+    """SegmentationModule.forward, training branch (reference models/models.py:31-43) -> (loss, acc)."""
+    if not img.is_cuda:
+        raise RuntimeError("the B200 engine has no CPU path: move the module and the batch to a CUDA device")
+    prog = get_program(seg, img.shape)
+    prog.load_inputs(img, label)
+    if prog.with_grad:
+        params = [p for p in seg.parameters() if p.requires_grad]
+        return _TrainStep.apply(prog, *params)
+    prog.run()
+    out = prog.out.clone()
+    return out[0], out[1]
+
+
+def segmentation_inference(seg, img, seg_size):
+    """SegmentationModule.forward, inference branch (reference models/models.py:44-47): softmax probabilities of the
+    main head, bilinearly up-sampled to seg_size, fp32 NCHW."""
+    if not img.is_cuda:
+        raise RuntimeError("the B200 engine has no CPU path: move the module and the batch to a CUDA device")
+    if not getattr(seg.decoder, "use_softmax", False):
+        raise RuntimeError("inference (segSize=...) requires a decoder built with use_softmax=True")
+    prog = get_program(seg, img.shape, seg_size=tuple(seg_size), with_grad=False, capture=False)
+    prog.load_inputs(img)
+    prog.run()
+    return prog.probs.clone()
+
+
+def encoder_forward(enc, x):
+    raise NotImplementedError(
+        "calling the encoder on its own is not wired to the B200 engine yet; use SegmentationModule(enc, dec, crit) "
+        "(what train.py / eval.py do) - the fused program runs encoder+decoder+loss as one kernel schedule")
+
+
+def decoder_forward(dec, conv_out, seg_size):
+    raise NotImplementedError(
+        "calling the decoder on its own is not wired to the B200 engine yet; use SegmentationModule(enc, dec, crit)")
+
+
+def run_block(block, x):
+    raise NotImplementedError("residual blocks run inside a SegmentationModule program on the B200 engine")
+
+
+def batch_norm(bn, x):
+    raise NotImplementedError("SynchronizedBatchNorm runs inside a SegmentationModule program on the B200 engine")

@@ -1,0 +1,671 @@
+"""Step programs: a SegmentationModule + an input shape compiled into a fixed schedule of sm_100a kernel launches.
+
+A program is built ONCE per (module, input shape, mode): it walks the module tree (reading every conv's stride /
+dilation / padding from the nn.Conv2d that owns the weights, so ResnetDilated's rewrites are honoured), allocates all
+activations, statistics and gradient buffers up front, and records two lists of closures:
+
+    fwd : weight re-layout -> stem conv -> (conv [tcgen05 implicit GEMM, BN statistics in the epilogue]
+          -> [NCCL all-reduce of the statistics when synchronised] -> BN finalize -> fused BN/residual/ReLU/dropout apply)*
+          -> PPM cascade (adaptive pools, 1x1 convs, bilinear up-sampling, virtual concat) -> classifier(s)
+          -> fused log-softmax / NLL / pixel-accuracy
+    bwd : the exact adjoint, in reverse: loss gradient -> (BN backward reduce -> [all-reduce] -> BN backward apply
+          -> weight gradient GEMM (K = pixels, split-K) -> data gradient implicit GEMM)* -> gradient bucket all-reduce
+
+Running the program is just calling the closures in order on the current stream: no shapes are inspected, no memory
+is allocated, nothing synchronises — so a whole training step can be captured into ONE CUDA graph
+(`SegProgram.capture()`), which is how `bench.py` and `segmentation_train_step` run it.
+
+Activations are NHWC bf16, accumulation is fp32 (TMEM), BN statistics / loss / all parameter gradients are fp32.
+Reference call sites are cited on each record class.
+"""
+import math
+
+import torch
+import torch.nn as nn
+from torch.nn.modules.batchnorm import _BatchNorm
+
+from . import ops
+
+
+def _pad(x, m):
+    return (x + m - 1) // m * m
+
+
+def _dist():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist
+    return None
+
+
+class Act:
+    """An activation tensor (NHWC bf16) plus, during backward construction, its gradient buffer."""
+    __slots__ = ("t", "g", "gw")
+
+    def __init__(self, t):
+        self.t, self.g, self.gw = t, None, False
+
+
+class ConvW:
+    """Per-nn.Conv2d engine state: bf16 GEMM operands (forward / data-gradient layouts) and the fp32 gradient slot."""
+
+    def __init__(self, mod):
+        self.mod = mod
+        self.O, self.I, kh, kw = mod.weight.shape
+        assert kh == kw and mod.groups == 1, "square, ungrouped convolutions only"
+        self.k, self.T = kh, kh * kw
+        self.stride, self.dil, self.pad = mod.stride[0], mod.dilation[0], mod.padding[0]
+        assert mod.stride[0] == mod.stride[1] and self.pad == self.dil * (self.k // 2), "only 'same' padding is supported"
+        self.Opad = _pad(self.O, 64)
+        self.wf = self.wd = self.gw = self.gb = None  # views, assigned by SegProgram._alloc_params
+
+
+class BNS:
+    """Per-BatchNorm engine state: statistics / normalisation vectors and gradient slots (dgamma, dbeta)."""
+
+    def __init__(self, mod):
+        self.mod, self.C = mod, mod.num_features
+        self.stats = self.mean = self.invstd = self.scale = self.shift = self.dgamma = self.dbeta = None
+
+
+class SegProgram:
+    def __init__(self, seg, img_shape, training, with_grad=True, seg_size=None, dropout_masks=None):
+        """seg: SegmentationModule.  img_shape: (N, 3, H, W).  training: module.training (BN/dropout behaviour).
+        with_grad: also build the backward schedule.  seg_size: inference branch (probabilities at seg_size).
+        dropout_masks: optional {'main': [N,512] 0/1, 'deepsup': ...} to inject the Dropout2d draws (tests)."""
+        self.seg = seg
+        self.enc, self.dec = seg.encoder, seg.decoder
+        self.N, _, self.H, self.W = img_shape
+        self.training = bool(training)
+        self.inference = seg_size is not None
+        self.seg_size = seg_size
+        self.with_grad = bool(with_grad) and not self.inference
+        self.dev = next(seg.parameters()).device
+        assert self.dev.type == "cuda", "the B200 engine runs on CUDA devices only (no CPU fallback)"
+        self.injected_masks = dropout_masks
+        self.dist = _dist()
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.fwd, self.bwd, self.records = [], [], []
+        self.keep = []  # anything that must stay alive (geometry structs hold raw pointers)
+        self.graph = None
+
+        self.convs, self.bns = {}, {}
+        for m in list(self.enc.modules()) + list(self.dec.modules()):
+            if isinstance(m, nn.Conv2d):
+                self.convs[id(m)] = ConvW(m)
+            elif isinstance(m, _BatchNorm):
+                self.bns[id(m)] = BNS(m)
+        self._alloc_params()
+        self.img = torch.empty(img_shape, device=self.dev, dtype=torch.float32)
+        self._build_forward()
+        if self.with_grad:
+            self._build_backward()
+
+    # ------------------------------------------------------------------------------------------ buffers
+    def _alloc_params(self):
+        dev = self.dev
+        nf = sum(c.O * c.T * c.I for c in self.convs.values())
+        nd = sum(c.I * c.T * c.Opad for c in self.convs.values())
+        self.wf_flat = torch.empty(nf, device=dev, dtype=torch.bfloat16)
+        self.wd_flat = torch.zeros(nd if self.with_grad else 0, device=dev, dtype=torch.bfloat16)
+        small = sum(2 * b.C for b in self.bns.values()) + sum(_pad(c.O, 4) for c in self.convs.values()
+                                                               if c.mod.bias is not None)
+        self.g_small = small
+        self.gflat = torch.zeros((small + nf) if self.with_grad else 0, device=dev, dtype=torch.float32)
+        ns = sum(_pad(2 * b.C + 1, 4) for b in self.bns.values()) + 8
+        self.sflat = torch.zeros(ns, device=dev, dtype=torch.float32)
+        self.sinit = torch.zeros(ns, device=dev, dtype=torch.float32)
+        nv = sum(4 * b.C for b in self.bns.values())
+        self.vflat = torch.empty(nv, device=dev, dtype=torch.float32)
+        of = od = 0
+        og, ogs = small, 0
+        for c in self.convs.values():
+            c.wf = self.wf_flat[of:of + c.O * c.T * c.I].view(c.O, c.T * c.I)
+            of += c.O * c.T * c.I
+            if self.with_grad:
+                c.wd = self.wd_flat[od:od + c.I * c.T * c.Opad].view(c.I, c.T * c.Opad)
+                od += c.I * c.T * c.Opad
+                c.gw = self.gflat[og:og + c.O * c.T * c.I].view(c.O, c.T * c.I)
+                og += c.O * c.T * c.I
+                if c.mod.bias is not None:
+                    c.gb = self.gflat[ogs:ogs + c.O]
+                    ogs += _pad(c.O, 4)
+        os_, ov = 0, 0
+        for b in self.bns.values():
+            b.stats = self.sflat[os_:os_ + 2 * b.C + 1]
+            b.stats_off = os_
+            os_ += _pad(2 * b.C + 1, 4)
+            b.mean, b.invstd, b.scale, b.shift = (self.vflat[ov + i * b.C: ov + (i + 1) * b.C] for i in range(4))
+            ov += 4 * b.C
+            if self.with_grad:
+                b.dgamma = self.gflat[ogs:ogs + b.C]
+                b.dbeta = self.gflat[ogs + b.C:ogs + 2 * b.C]
+                ogs += 2 * b.C
+        self.acc_main = self.sflat[os_:os_ + 4]
+        self.acc_ds = self.sflat[os_ + 4:os_ + 8]
+        self.out = torch.zeros(2, device=dev, dtype=torch.float32)  # (loss, acc)
+
+    def _new(self, *shape, dtype=torch.bfloat16, zero=False):
+        f = torch.zeros if zero else torch.empty
+        return f(shape, device=self.dev, dtype=dtype)
+
+    def _bn_mode(self, bns):
+        if not self.training or not bns.mod.training:
+            return ops.BN_EVAL
+        sync = self.dist is not None or getattr(bns.mod, "_is_parallel", False)
+        return ops.BN_TRAIN_SYNC if sync else ops.BN_TRAIN
+
+    # ------------------------------------------------------------------------------------------ forward pieces
+    def _prep_weights(self):
+        for c in self.convs.values():
+            if c.I == 3:
+                continue  # the stem conv reads the fp32 master weight directly
+            w, wf, wd, op = c.mod.weight, c.wf, (c.wd if self.with_grad else None), c.Opad
+            self.fwd.append(lambda w=w, wf=wf, wd=wd, op=op: ops.prep_conv_weight(w.detach(), wf, wd, o_pad=op))
+
+    def _conv_geom(self, srcs, cw):
+        """Input-side geometry of conv `cw` over the (virtual concat of) NHWC tensors `srcs` -> (geom, out H, out W)."""
+        n, h, w, _ = srcs[0].shape
+        if cw.stride == 1:
+            geom = ops.make_geom(srcs, ops.conv_taps(cw.k, cw.dil))
+            ho, wo = h, w
+        else:
+            assert cw.stride == 2 and cw.dil == 1 and len(srcs) == 1 and h % 2 == 0 and w % 2 == 0, \
+                "stride-2 convolutions need even spatial sizes"
+            dh, dw, src = ops.conv_s2_taps(cw.k)
+            planes = ops.parity_planes(srcs[0])
+            geom = ops.make_geom(planes, (dh, dw), tap_src=src, tap_koff=[t * cw.I for t in range(cw.T)])
+            self.keep.append(planes)
+            ho, wo = h // 2, w // 2
+        self.keep.append(geom)
+        return geom, ho, wo
+
+    def conv_bn(self, xs, conv_mod, bn_mod, relu=True, res=None, chanmul=None, apply=True):
+        """conv -> BN(train/eval) -> (+res) -> ReLU -> (*chanmul).  xs: Act or list of Acts (virtual concat).
+        res: None | Act (identity shortcut) | ConvBNRec built with apply=False (projection shortcut)."""
+        rec = ConvBNRec(self, xs if isinstance(xs, list) else [xs], self.convs[id(conv_mod)], self.bns[id(bn_mod)], relu,
+                        res, chanmul, apply)
+        self.records.append(rec)
+        return rec if not apply else rec.a
+
+    def _build_forward(self):
+        from ..models import models as M
+        from ..models import resnet as R
+        N, H, W = self.N, self.H, self.W
+        self._prep_weights()
+        self.fwd.append(lambda: self.sflat.copy_(self.sinit))
+        enc = self.enc
+        # ---- stem (reference models/resnet.py:100-109, models/models.py:256-259)
+        stem = StemRec(self, self.convs[id(enc.conv1)], self.bns[id(enc.bn1)])
+        self.records.append(stem)
+        x = stem.a
+        x = self.conv_bn(x, enc.conv2, enc.bn2)
+        x = self.conv_bn(x, enc.conv3, enc.bn3)
+        mp = MaxPoolRec(self, x)
+        self.records.append(mp)
+        x = mp.a
+        feats = []
+        for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
+            for block in layer:
+                assert isinstance(block, (R.BasicBlock, R.Bottleneck))
+                inp = x
+                res = inp
+                if block.downsample is not None:
+                    res = self.conv_bn(inp, block.downsample[0], block.downsample[1], relu=False, apply=False)
+                stages = block.stages()
+                for i, (cv, bn) in enumerate(stages):
+                    last = i == len(stages) - 1
+                    x = self.conv_bn(x, cv, bn, relu=True, res=res if last else None)
+            feats.append(x)
+        self.feats = feats
+        # ---- decoder
+        dec = self.dec
+        self.logits_ds = None
+        p_drop_main = p_drop_ds = 0.0
+        if isinstance(dec, (M.PPM, M.PPMDeepsup)):
+            conv5 = feats[-1]
+            n, h, w, c5 = conv5.t.shape
+            srcs = [conv5]
+            for scale, branch in zip(dec.pool_scales, dec.ppm):
+                pr = AvgPoolRec(self, conv5, scale)
+                self.records.append(pr)
+                y = self.conv_bn(pr.a, branch[1], branch[2])
+                ur = UpsampleRec(self, y, h, w)
+                self.records.append(ur)
+                srcs.append(ur.a)
+            drop = dec.conv_last[3]
+            p_drop_main = drop.p if (self.training and drop.training) else 0.0
+            self.mask_main = self._new(n, 512, dtype=torch.float32) if p_drop_main > 0 else None
+            x = self.conv_bn(srcs, dec.conv_last[0], dec.conv_last[1], chanmul=self.mask_main)
+            cls = ClassifierRec(self, x, self.convs[id(dec.conv_last[4])])
+            self.records.append(cls)
+            self.logits = cls.logits
+            if isinstance(dec, M.PPMDeepsup) and not self.inference:
+                p_drop_ds = dec.dropout_deepsup.p if (self.training and dec.dropout_deepsup.training) else 0.0
+                self.mask_ds = self._new(n, dec.cbr_deepsup[0].out_channels, dtype=torch.float32) if p_drop_ds > 0 else None
+                y = self.conv_bn(feats[-2], dec.cbr_deepsup[0], dec.cbr_deepsup[1], chanmul=self.mask_ds)
+                cls2 = ClassifierRec(self, y, self.convs[id(dec.conv_last_deepsup)])
+                self.records.append(cls2)
+                self.logits_ds = cls2.logits
+        elif isinstance(dec, (M.C1, M.C1DeepSup)):
+            x = self.conv_bn(feats[-1], dec.cbr[0], dec.cbr[1])
+            cls = ClassifierRec(self, x, self.convs[id(dec.conv_last)])
+            self.records.append(cls)
+            self.logits = cls.logits
+            if isinstance(dec, M.C1DeepSup) and not self.inference:
+                y = self.conv_bn(feats[-2], dec.cbr_deepsup[0], dec.cbr_deepsup[1])
+                cls2 = ClassifierRec(self, y, self.convs[id(dec.conv_last_deepsup)])
+                self.records.append(cls2)
+                self.logits_ds = cls2.logits
+        else:
+            raise NotImplementedError("decoder %s is not built on the B200 engine yet" % type(dec).__name__)
+        self.p_drop = (p_drop_main, p_drop_ds)
+        self.num_class = cls.cw.O
+        # dropout masks are drawn at the START of the step (they only depend on the RNG)
+        if p_drop_main > 0 or p_drop_ds > 0:
+            self.fwd.insert(0, self._draw_masks)
+        # ---- head
+        if self.inference:
+            hs, ws = self.seg_size
+            self.probs = self._new(N, self.num_class, hs, ws, dtype=torch.float32)
+            self.fwd.append(lambda: ops.upsample_softmax(self.logits[..., :_pad(self.num_class, 8)], self.num_class,
+                                                         self.probs))
+        else:
+            n, h, w, _ = self.logits.shape
+            self.label = torch.empty(n, h, w, device=self.dev, dtype=torch.int64)
+            loss = LossRec(self)
+            self.records.append(loss)
+
+    def _draw_masks(self):
+        for name, mask, p in (("main", getattr(self, "mask_main", None), self.p_drop[0]),
+                              ("deepsup", getattr(self, "mask_ds", None), self.p_drop[1])):
+            if mask is None:
+                continue
+            if self.injected_masks is not None and name in self.injected_masks:
+                mask.copy_(self.injected_masks[name].to(mask.dtype) / (1.0 - p))
+            else:
+                # nn.Dropout2d (models/models.py:460,464): one Bernoulli(1-p) draw per (n, c), survivors scaled by 1/(1-p)
+                mask.uniform_().ge_(p).mul_(1.0 / (1.0 - p))
+
+    # ------------------------------------------------------------------------------------------ backward
+    def _build_backward(self):
+        self.bwd.append(lambda: self.gflat.zero_())
+        for rec in reversed(self.records):
+            rec.backward()
+        if self.dist is not None:
+            # the data-parallel gradient bucket (reference: backward of nn.DataParallel's Broadcast):
+            # one NCCL all-reduce of the flat fp32 gradient buffer
+            self.bwd.append(lambda: self.dist.all_reduce(self.gflat))
+
+    def grad_target(self, act, shape_like=None):
+        """(buffer, accumulate?) for writing a gradient contribution of `act`."""
+        if act.g is None:
+            act.g = torch.empty_like(act.t if shape_like is None else shape_like)
+        acc = act.gw
+        act.gw = True
+        return act.g, acc
+
+    # ------------------------------------------------------------------------------------------ execution
+    def load_inputs(self, img, label=None):
+        self.img.copy_(img, non_blocking=True)
+        if label is not None:
+            self.label.copy_(label, non_blocking=True)
+
+    def run_eager(self):
+        for f in self.fwd:
+            f()
+        for f in self.bwd:
+            f()
+
+    def capture(self):
+        """Capture the whole step into one CUDA graph (after a warm-up run on a side stream)."""
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(s):
+            self.run_eager()
+            self.run_eager()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self.run_eager()
+        self.graph = g
+        return g
+
+    def run(self):
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self.run_eager()
+
+    def num_launches(self):
+        """Kernel launches of libsseg_b200 per step (counted by the library on one eager run)."""
+        from . import _C
+        _C.lib().sseg_launch_count_reset()
+        self.run_eager()
+        return int(_C.lib().sseg_launch_count())
+
+    # ------------------------------------------------------------------------------------------ gradients
+    def param_grads(self, scale=1.0):
+        """{parameter: fp32 gradient tensor in the parameter's own layout} from the flat buffers.
+        `scale` multiplies every gradient (1/world_size after the bucket all-reduce = the reference's mean over GPUs)."""
+        out = {}
+        if self.world > 1:
+            scale = scale / self.world
+        if not hasattr(self, "_pg"):
+            self._pg = {id(c): torch.empty_like(c.mod.weight) for c in self.convs.values()}
+        if scale != 1.0:
+            self.gflat[:self.g_small].mul_(scale)
+        for c in self.convs.values():
+            g = self._pg[id(c)]
+            if c.I == 3:
+                g.copy_(c.gw.view_as(g))  # the stem kernel writes OIHW directly
+                if scale != 1.0:
+                    g.mul_(scale)
+            else:
+                ops.grad_to_oihw(c.gw, c.O, c.I, c.T, g, scale=scale)
+            out[c.mod.weight] = g
+            if c.mod.bias is not None:
+                out[c.mod.bias] = c.gb
+        for b in self.bns.values():
+            if b.mod.weight is not None:
+                out[b.mod.weight] = b.dgamma
+                out[b.mod.bias] = b.dbeta
+        return out
+
+
+# ======================================================================================================= records
+class StemRec:
+    """conv1 (3->64, 3x3, stride 2) + bn1 + relu1: models/resnet.py:100-102, :153."""
+
+    def __init__(self, P, cw, bns):
+        self.P, self.cw, self.bns = P, cw, bns
+        assert cw.I == 3 and cw.O == 64 and cw.k == 3 and cw.stride == 2, "deep-stem conv1 expected"
+        N, H, W = P.N, P.H, P.W
+        ho, wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+        self.y = P._new(N, ho, wo, 64)
+        self.a = Act(P._new(N, ho, wo, 64))
+        self.mode = P._bn_mode(bns)
+        self.count = N * ho * wo
+        w = cw.mod.weight
+        train = self.mode != ops.BN_EVAL
+        st = bns.stats
+        P.fwd.append(lambda: ops.stem_conv_fwd(P.img, w.detach(), self.y, st[:64] if train else None,
+                                               st[64:128] if train else None))
+        _emit_bn_forward(P, bns, self.mode, self.count, self.y, self.a.t, True, None, None, None, None)
+
+    def backward(self):
+        P, bns = self.P, self.bns
+        if self.a.g is None:
+            return
+        dy = torch.empty_like(self.y)
+        _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, self.a.t, self.y, dy, None, None)
+        gw = self.cw.gw
+        P.bwd.append(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3)))
+
+
+def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, chanmul):
+    m = bns.mod
+    C = bns.C
+    st = bns.stats
+    if mode == ops.BN_TRAIN_SYNC:
+        # local pixel count rides along with the sums so ranks with different batch shapes pool correctly
+        P.sinit[bns.stats_off + 2 * C] = float(count)
+        if P.dist is not None:
+            P.fwd.append(lambda: P.dist.all_reduce(st))
+    running = (m.running_mean, m.running_var, getattr(m, "_tmp_running_mean", None), getattr(m, "_tmp_running_var", None),
+               getattr(m, "_running_iter", None))
+    upd = mode != ops.BN_EVAL and m.track_running_stats and m.running_mean is not None
+    mom = m.momentum if m.momentum is not None else 0.1
+    cdev = st[2 * C:2 * C + 1] if mode == ops.BN_TRAIN_SYNC else None
+    w = m.weight.detach() if m.weight is not None else None
+    b = m.bias.detach() if m.bias is not None else None
+    P.fwd.append(lambda: ops.bn_finalize(st[:C], st[C:2 * C], count, w, b, m.eps, mom, mode, bns.mean, bns.invstd,
+                                         bns.scale, bns.shift, running=running, update_running=upd, count_dev=cdev))
+    if out is not None:
+        P.fwd.append(lambda: ops.bn_apply(y, bns.scale, bns.shift, out, relu=relu, res=res, rscale=rscale, rshift=rshift,
+                                          chanmul=chanmul))
+
+
+def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul):
+    """g: gradient w.r.t. the layer output; a: saved output if the layer has a ReLU (mask source) else None."""
+    C = bns.C
+    st = bns.stats
+    if mode == ops.BN_EVAL:
+        P.bwd.append(lambda: ops.bn_bwd_apply(g, a, None, None, None, bns.scale, None, None, 1.0, dy, dres=dres,
+                                              chanmul=chanmul, eval_mode=True))
+        # dgamma / dbeta of a frozen BN still exist in the reference (affine params stay trainable under fix_bn)
+        P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul))
+        return
+    P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul))
+    cdev = None
+    if mode == ops.BN_TRAIN_SYNC:
+        cdev = st[2 * C:2 * C + 1]
+        if P.dist is not None:
+            # dgamma|dbeta are adjacent in the flat gradient buffer: one all-reduce for both
+            both = P.gflat[bns.dgamma.storage_offset():bns.dgamma.storage_offset() + 2 * C]
+            P.bwd.append(lambda: P.dist.all_reduce(both))
+    P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, bns.scale, bns.dbeta, bns.dgamma, count, dy,
+                                          dres=dres, chanmul=chanmul, count_dev=cdev))
+    if mode == ops.BN_TRAIN_SYNC and P.dist is not None:
+        # the bucket all-reduce at the end sums gflat over ranks again: pre-divide the already-global dgamma/dbeta
+        both = P.gflat[bns.dgamma.storage_offset():bns.dgamma.storage_offset() + 2 * C]
+        P.bwd.append(lambda: both.mul_(1.0 / P.world))
+
+
+class ConvBNRec:
+    """Conv2d -> SynchronizedBatchNorm2d -> (+shortcut) -> ReLU -> (Dropout2d mask).
+    Reference: Bottleneck/BasicBlock.forward (models/resnet.py:37-53,72-92), conv3x3_bn_relu (models/models.py:160-167),
+    PPM branches / conv_last (models/models.py:443-462)."""
+
+    def __init__(self, P, xs, cw, bns, relu, res, chanmul, apply):
+        self.P, self.xs, self.cw, self.bns, self.relu, self.res, self.chanmul, self.apply = P, xs, cw, bns, relu, res, chanmul, apply
+        srcs = [x.t for x in xs]
+        assert sum(s.shape[3] for s in srcs) == cw.I
+        self.geom, ho, wo = P._conv_geom(srcs, cw)
+        n = srcs[0].shape[0]
+        self.y = P._new(n, ho, wo, cw.O)
+        self.mode = P._bn_mode(bns)
+        self.count = n * ho * wo
+        st = bns.stats
+        train = self.mode != ops.BN_EVAL
+        C = cw.O
+        geom, wf, y = self.geom, cw.wf, self.y
+        P.fwd.append(lambda: ops.conv_igemm(geom, wf, C, y, stat_sum=st[:C] if train else None,
+                                            stat_sqsum=st[C:2 * C] if train else None))
+        if apply:
+            self.a = Act(P._new(n, ho, wo, cw.O))
+            r = rs = rb = None
+            if isinstance(res, Act):
+                r = res.t
+            elif isinstance(res, ConvBNRec):
+                r, rs, rb = res.y, res.bns.scale, res.bns.shift
+            _emit_bn_forward(P, bns, self.mode, self.count, y, self.a.t, relu, r, rs, rb, chanmul)
+        else:
+            self.a = None
+            _emit_bn_forward(P, bns, self.mode, self.count, y, None, False, None, None, None, None)
+
+    def backward(self, g_override=None):
+        P, cw, bns = self.P, self.cw, self.bns
+        if not self.apply and g_override is None:
+            return  # projection shortcuts are driven by the record that consumed them
+        g = g_override if g_override is not None else self.a.g
+        if g is None:
+            return
+        dy = torch.empty_like(self.y)
+        dres = None
+        ds_rec = None
+        if isinstance(self.res, Act):
+            dres, acc = P.grad_target(self.res)
+            assert not acc, "identity shortcut must be the first gradient contribution of the block input"
+        elif isinstance(self.res, ConvBNRec):
+            ds_rec = self.res
+            dres = torch.empty_like(ds_rec.y)
+        a = self.a.t if (self.apply and self.relu) else None
+        _emit_bn_backward(P, bns, self.mode, self.count, g, a, self.y, dy, dres, self.chanmul)
+        if ds_rec is not None:
+            ds_rec.backward(g_override=dres)
+        # weight gradient: GEMM over pixels (sseg_conv_wgrad)
+        geom, gw, O = self.geom, cw.gw, cw.O
+        P.bwd.append(lambda: ops.conv_wgrad(geom, dy, O, gw))
+        # data gradient: implicit GEMM of dy with the transposed weight, taps mirrored
+        self._emit_dgrad(dy)
+
+    def _emit_dgrad(self, dy):
+        P, cw = self.P, self.cw
+        xs = self.xs
+        if cw.stride == 1:
+            dh, dw = ops.conv_taps(cw.k, cw.dil)
+            gd = ops.make_geom([dy], ([-v for v in dh], [-v for v in dw]), tap_koff=[t * cw.Opad for t in range(cw.T)])
+            P.keep.append(gd)
+            if len(xs) == 1:
+                buf, acc = P.grad_target(xs[0])
+            else:
+                # virtual concat: one gradient tensor, each source's gradient is a channel slice of it
+                n, h, w, _ = xs[0].t.shape
+                buf = P._new(n, h, w, cw.I)
+                off = 0
+                for x in xs:
+                    assert not x.gw, "concat sources must receive their first gradient from the concat conv"
+                    c = x.t.shape[3]
+                    x.g, x.gw = buf[..., off:off + c], True
+                    off += c
+                acc = False
+            wd, I = cw.wd, cw.I
+            P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=I, addend=buf if acc else None))
+        else:
+            x = xs[0]
+            buf, acc = P.grad_target(x)
+            dh, dw, src = ops.conv_s2_taps(cw.k)
+            planes = ops.parity_planes(buf)
+            P.keep.append(planes)
+            for pl in range(4):
+                taps = [t for t in range(cw.T) if src[t] == pl]
+                if not taps:
+                    if not acc:
+                        P.bwd.append(lambda v=planes[pl]: v.zero_())
+                    continue
+                gd = ops.make_geom([dy], ([-dh[t] for t in taps], [-dw[t] for t in taps]),
+                                   tap_koff=[t * cw.Opad for t in taps])
+                P.keep.append(gd)
+                wd, I, view = cw.wd, cw.I, planes[pl]
+                P.bwd.append(lambda gd=gd, view=view: ops.conv_igemm(gd, wd, I, view, n_store=I,
+                                                                     addend=view if acc else None))
+
+
+class MaxPoolRec:
+    """nn.MaxPool2d(3, 2, 1): models/resnet.py:109."""
+
+    def __init__(self, P, x):
+        self.P, self.x = P, x
+        n, h, w, c = x.t.shape
+        ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+        self.a = Act(P._new(n, ho, wo, c))
+        self.idx = P._new(n, ho, wo, c, dtype=torch.uint8) if P.with_grad else None
+        P.fwd.append(lambda: ops.maxpool_fwd(x.t, self.a.t, self.idx))
+
+    def backward(self):
+        P = self.P
+        if self.a.g is None:
+            return
+        buf, acc = P.grad_target(self.x)
+        assert not acc
+        g = self.a.g
+        assert g.is_contiguous()
+        P.bwd.append(lambda: ops.maxpool_bwd(g, self.idx, buf))
+
+
+class AvgPoolRec:
+    """nn.AdaptiveAvgPool2d(scale): models/models.py:447."""
+
+    def __init__(self, P, x, scale):
+        self.P, self.x, self.scale = P, x, scale
+        n, h, w, c = x.t.shape
+        self.a = Act(P._new(n, scale, scale, c))
+        P.fwd.append(lambda: ops.avgpool_fwd(x.t, scale, self.a.t))
+
+    def backward(self):
+        P = self.P
+        if self.a.g is None:
+            return
+        buf, acc = P.grad_target(self.x)
+        g, s = self.a.g, self.scale
+        P.bwd.append(lambda: ops.avgpool_bwd(buf if acc else None, [g], [s], buf))
+
+
+class UpsampleRec:
+    """F.interpolate(bilinear, align_corners=False) of a PPM branch to the conv5 size: models/models.py:472-475."""
+
+    def __init__(self, P, x, h, w):
+        self.P, self.x = P, x
+        n, _, _, c = x.t.shape
+        self.a = Act(P._new(n, h, w, c))
+        P.fwd.append(lambda: ops.bilinear_fwd(x.t, self.a.t))
+
+    def backward(self):
+        P = self.P
+        if self.a.g is None:
+            return
+        buf, acc = P.grad_target(self.x)
+        g = self.a.g
+        P.bwd.append(lambda: ops.bilinear_bwd(g, buf, accumulate=acc))
+
+
+class ClassifierRec:
+    """The num_class 1x1 conv with bias (conv_last[4] / conv_last_deepsup): models/models.py:462,465."""
+
+    def __init__(self, P, x, cw):
+        self.P, self.x, self.cw = P, x, cw
+        n, h, w, _ = x.t.shape
+        self.ld = _pad(cw.O, 8) + 8
+        self.logits = P._new(n, h, w, self.ld, dtype=torch.float32, zero=True)
+        self.geom, _, _ = P._conv_geom([x.t], cw)
+        self.dlogits = None
+        geom, wf, O, bias = self.geom, cw.wf, cw.O, cw.mod.bias
+        P.fwd.append(lambda: ops.conv_igemm(geom, wf, O, self.logits, n_store=_pad(O, 8),
+                                            bias=bias.detach() if bias is not None else None))
+
+    def backward(self):
+        P, cw = self.P, self.cw
+        if self.dlogits is None:
+            return
+        dl = self.dlogits  # bf16 [n,h,w,Opad], zero padded
+        geom, gw, O = self.geom, cw.gw, cw.O
+        P.bwd.append(lambda: ops.conv_wgrad(geom, dl, O, gw))
+        if cw.gb is not None:
+            gb = cw.gb
+            P.bwd.append(lambda: ops.colsum(dl, O, gb))
+        buf, acc = P.grad_target(self.x)
+        gd = ops.make_geom([dl], ([0], [0]), tap_koff=[0])
+        P.keep.append(gd)
+        wd, I = cw.wd, cw.I
+        P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=I, addend=buf if acc else None))
+
+
+class LossRec:
+    """log_softmax + NLLLoss(ignore_index=-1) (+ deep supervision) + pixel_acc: models/models.py:12-18,37-42,492-493."""
+
+    def __init__(self, P):
+        self.P = P
+        self.heads = [r for r in P.records if isinstance(r, ClassifierRec)]
+        n, h, w, _ = P.logits.shape
+        self.lse = [P._new(n * h * w, dtype=torch.float32) for _ in self.heads]
+        C = P.num_class
+        accs = [P.acc_main, P.acc_ds]
+        for head, lse, acc in zip(self.heads, self.lse, accs):
+            lg = head.logits[..., :_pad(C, 8)]
+            P.fwd.append(lambda lg=lg, lse=lse, acc=acc: ops.softmax_nll_fwd(lg, C, P.label, lse, acc))
+        ds = P.seg.deep_sup_scale if len(self.heads) > 1 else None
+        self.weights = [1.0] + ([float(ds)] if ds is not None else [])
+        P.fwd.append(lambda: ops.nll_finalize(P.acc_main, P.acc_ds if ds is not None else None, ds or 0.0, P.out))
+
+    def backward(self):
+        P = self.P
+        C = P.num_class
+        accs = [P.acc_main, P.acc_ds]
+        for head, lse, acc, wgt in zip(self.heads, self.lse, accs, self.weights):
+            n, h, w, _ = head.logits.shape
+            head.dlogits = P._new(n, h, w, head.cw.Opad)
+            lg, dl = head.logits[..., :_pad(C, 8)], head.dlogits
+            P.bwd.append(lambda lg=lg, lse=lse, acc=acc, wgt=wgt, dl=dl: ops.softmax_nll_bwd(lg, C, P.label, lse, acc,
+                                                                                            wgt, dl))

@@ -1,0 +1,131 @@
+"""Data-parallel wrappers with the reference's names.
+
+Reference: mit_semseg/lib/nn/parallel/data_parallel.py:13-112 and lib/nn/modules/replicate.py:27-94.
+
+The reference runs ONE process that replicates the module onto every GPU each iteration (param broadcast), runs one
+Python thread per GPU and reduces gradients back to GPU 0.  The B200 design is one process per GPU
+(torch.distributed / NCCL over NVLink): replicas are persistent, SyncBN statistics and the gradient bucket are
+all-reduced by the engine.  `UserScatteredDataParallel` therefore:
+
+  * stays an `nn.DataParallel` subclass (train.py wraps the model in it and replicate.py:84 asserts the type);
+  * `scatter` keeps the reference contract — the input is a list with one dict per GPU — and picks this rank's
+    entry (`rank` = torch.distributed rank, 0 without a process group), copying it to the device asynchronously;
+  * `forward` runs the wrapped module on this process's device and returns outputs with a leading dimension
+    (0-d -> 1-d, reference data_parallel.py:33-36), so `loss.mean()` / `acc.mean()` in train.py keep working.
+"""
+import collections.abc
+
+import torch
+import torch.cuda as cuda
+import torch.nn as nn
+from torch.nn.parallel import DataParallel
+
+__all__ = ['UserScatteredDataParallel', 'user_scattered_collate', 'async_copy_to', 'DataParallelWithCallback',
+           'patch_replication_callback']
+
+
+def async_copy_to(obj, dev, main_stream=None):
+    """Recursively copy tensors in dict/list structures to `dev` without blocking; non-tensors pass through."""
+    if torch.is_tensor(obj):
+        v = obj.cuda(dev, non_blocking=True)
+        if main_stream is not None:
+            v.record_stream(main_stream)
+        return v
+    if isinstance(obj, collections.abc.Mapping):
+        return {k: async_copy_to(o, dev, main_stream) for k, o in obj.items()}
+    if isinstance(obj, collections.abc.Sequence) and not isinstance(obj, (str, bytes)):
+        return [async_copy_to(o, dev, main_stream) for o in obj]
+    return obj
+
+
+def user_scattered_collate(batch):
+    return batch
+
+
+def _rank_world():
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def _lift(out):
+    """0-d tensors -> 1-d (reference dict_gather, data_parallel.py:33-36); recurse through dict/list/tuple."""
+    if torch.is_tensor(out):
+        return out.unsqueeze(0) if out.dim() == 0 else out
+    if out is None:
+        return None
+    if isinstance(out, collections.abc.Mapping):
+        return {k: _lift(v) for k, v in out.items()}
+    if isinstance(out, collections.abc.Sequence):
+        return type(out)(_lift(v) for v in out)
+    return out
+
+
+_copy_streams = {}
+
+
+def _copy_stream(device):
+    if device not in _copy_streams:
+        _copy_streams[device] = cuda.Stream(device)
+    return _copy_streams[device]
+
+
+class DictGatherDataParallel(DataParallel):
+    def gather(self, outputs, output_device):
+        return _lift(outputs[0]) if len(outputs) == 1 else super().gather(outputs, output_device)
+
+
+class UserScatteredDataParallel(DictGatherDataParallel):
+    def __init__(self, module, device_ids=None, output_device=None, dim=0):
+        # One process drives one GPU: keep only this process's device so nn.DataParallel never replicates.
+        if torch.cuda.is_available():
+            dev = torch.cuda.current_device()
+            super().__init__(module, device_ids=[dev], output_device=dev, dim=dim)
+        else:
+            nn.Module.__init__(self)
+            self.module, self.device_ids, self.dim, self.output_device = module, [], dim, None
+        self.requested_device_ids = device_ids
+
+    def scatter(self, inputs, kwargs, device_ids):
+        assert len(inputs) == 1 and len(kwargs) == 0
+        batches = inputs[0]
+        assert type(batches) in (tuple, list)
+        rank, world = _rank_world()
+        # the loader yields one dict per GPU of the job; a single-process run consumes entry `rank % len`
+        mine = batches[rank % len(batches)]
+        dev = device_ids[0]
+        with cuda.device(dev):
+            main = cuda.current_stream()
+            side = _copy_stream(dev)
+            with cuda.stream(side):
+                mine = async_copy_to(mine, dev, main_stream=main)
+            main.wait_stream(side)
+        return [[mine]], [{}]
+
+    def forward(self, *inputs, **kwargs):
+        if not self.device_ids:
+            return _lift(self.module(*inputs, **kwargs))
+        inputs, kwargs = self.scatter(inputs, kwargs, self.device_ids)
+        return _lift(self.module(*inputs[0], **kwargs[0]))
+
+
+class DataParallelWithCallback(DataParallel):
+    """nn.DataParallel that marks SyncBN modules as parallel (reference replicate.py:50-67)."""
+
+    def __init__(self, module, device_ids=None, output_device=None, dim=0):
+        super().__init__(module, device_ids=device_ids, output_device=output_device, dim=dim)
+        _mark_parallel(module)
+
+
+def _mark_parallel(module):
+    for m in module.modules():
+        if hasattr(m, '__data_parallel_replicate__'):
+            m.__data_parallel_replicate__(None, 0)
+
+
+def patch_replication_callback(data_parallel):
+    """Reference replicate.py:70-94: after this call the SyncBN layers of `data_parallel.module` use the
+    synchronised (pooled-statistics) formula while training."""
+    assert isinstance(data_parallel, DataParallel)
+    _mark_parallel(data_parallel.module)
