@@ -296,6 +296,23 @@ class SegProgram:
             # the data-parallel gradient bucket (reference: backward of nn.DataParallel's Broadcast):
             # one NCCL all-reduce of the flat fp32 gradient buffer
             self.bwd.append(lambda: self.dist.all_reduce(self.gflat))
+        # gradients into each parameter's own layout (static buffers, so they are part of the captured graph);
+        # 1/world_size = the reference's mean over per-GPU losses (train.py:42)
+        scale = 1.0 / self.world
+        self._pg = {}
+        if scale != 1.0:
+            self.bwd.append(lambda: self.gflat[:self.g_small].mul_(scale))
+        for c in self.convs.values():
+            g = torch.empty_like(c.mod.weight)
+            self._pg[id(c)] = g
+            if c.I == 3:
+                def stem_grad(g=g, c=c):
+                    g.copy_(c.gw.view_as(g))  # the stem kernel accumulates in OIHW directly
+                    if scale != 1.0:
+                        g.mul_(scale)
+                self.bwd.append(stem_grad)
+            else:
+                self.bwd.append(lambda g=g, c=c: ops.grad_to_oihw(c.gw, c.O, c.I, c.T, g, scale=scale))
 
     def grad_target(self, act, shape_like=None):
         """(buffer, accumulate?) for writing a gradient contribution of `act`."""
@@ -346,25 +363,12 @@ class SegProgram:
         return int(_C.lib().sseg_launch_count())
 
     # ------------------------------------------------------------------------------------------ gradients
-    def param_grads(self, scale=1.0):
-        """{parameter: fp32 gradient tensor in the parameter's own layout} from the flat buffers.
-        `scale` multiplies every gradient (1/world_size after the bucket all-reduce = the reference's mean over GPUs)."""
+    def param_grads(self):
+        """{parameter: fp32 gradient tensor in the parameter's own layout}. The tensors are the program's static
+        buffers, rewritten by every run (conv weights: `grad_to_oihw` outputs; BN / bias: views of the flat buffer)."""
         out = {}
-        if self.world > 1:
-            scale = scale / self.world
-        if not hasattr(self, "_pg"):
-            self._pg = {id(c): torch.empty_like(c.mod.weight) for c in self.convs.values()}
-        if scale != 1.0:
-            self.gflat[:self.g_small].mul_(scale)
         for c in self.convs.values():
-            g = self._pg[id(c)]
-            if c.I == 3:
-                g.copy_(c.gw.view_as(g))  # the stem kernel writes OIHW directly
-                if scale != 1.0:
-                    g.mul_(scale)
-            else:
-                ops.grad_to_oihw(c.gw, c.O, c.I, c.T, g, scale=scale)
-            out[c.mod.weight] = g
+            out[c.mod.weight] = self._pg[id(c)]
             if c.mod.bias is not None:
                 out[c.mod.bias] = c.gb
         for b in self.bns.values():
