@@ -119,6 +119,23 @@ int sseg_prep_conv_weight(const float* w_oihw, int O, int I, int T, void* w_fwd,
 int sseg_grad_to_oihw(const float* g, long g_ld, int O, int I, int T, float* out, float scale, int accumulate,
                       sseg_stream_t stream);
 
+/* Batched variants: one launch for every convolution of a model. `table_dev` is a DEVICE array of n descriptors
+ * (built once by the caller); descriptor k owns CTAs [first_tile, first_tile + ceil(O/32)*ceil(I/32)), T <= 9. */
+typedef struct {
+  const float* w; /* fp32 OIHW master weight (prep) */
+  void* wf;       /* bf16 [O][fwd_ld] or NULL */
+  void* wd;       /* bf16 [I][dgrad_ld] or NULL */
+  const float* g_src; /* fp32 [O][g_ld] tap-major gradient (grads) */
+  float* g_dst;       /* fp32 OIHW gradient */
+  long fwd_ld, dgrad_ld, g_ld;
+  int O, I, T, o_pad;
+  int first_tile;
+  int reserved;
+} sseg_weight_desc_t;
+int sseg_prep_conv_weights_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, sseg_stream_t stream);
+int sseg_grads_to_oihw_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, float scale,
+                               sseg_stream_t stream);
+
 /* ---- stem convolution (Cin = 3, 3x3, stride 2, pad 1, Cout = 64): models/resnet.py:100 -------------- */
 /* img: fp32 NCHW [N,3,H,W]; w: fp32 OIHW [64,3,3,3]; out: bf16 NHWC [N,Ho,Wo,64] dense; optional BN statistics. */
 int sseg_stem_conv_fwd(const float* img, int N, int H, int W, const float* w, void* out, float* stat_sum,
@@ -164,8 +181,9 @@ int sseg_avgpool_bwd(const void* base, long base_ld, const void* const* dpool, c
 /* F.interpolate(mode='bilinear', align_corners=False) (models/models.py:472-475) and its adjoint (gather form). */
 int sseg_bilinear_fwd(const void* x, long x_ld, int N, int Hi, int Wi, int C, void* out, long out_ld, int Ho, int Wo,
                       sseg_stream_t stream);
+/* scratch: float[N*Ho*Wi*C] (the W-pass intermediate of the separable adjoint) */
 int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int C, void* dx, long dx_ld, int Hi, int Wi,
-                      int accumulate, sseg_stream_t stream);
+                      int accumulate, float* scratch, sseg_stream_t stream);
 
 /* ---- loss ------------------------------------------------------------------------------- */
 /* F.log_softmax + nn.NLLLoss(ignore_index=-1) + pixel_acc (models/models.py:12-18,37-42,492-493; train.py:154).

@@ -59,6 +59,40 @@ def _conv_hparams(block, layer_idx, block_idx, conv_name, dilated):
 
 
 # ----------------------------------------------------------------------------------------------
+# optional storage-precision emulation: the engine keeps activations / activation-gradients / GEMM operands in bf16
+# (fp32 accumulation). `BNState(emulate="bf16")` rounds at the same points (conv output, applied block output, pooled /
+# resized maps, weights; and the corresponding gradients in backward), so engine-vs-oracle comparisons isolate kernel
+# errors from the (large, chaotic at random init) sensitivity of a 50-layer BN-ReLU net to bf16 rounding.
+class _RoundFB(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+class _RoundF(torch.autograd.Function):
+    """round in forward only (weights: the fp32 master receives the full-precision gradient)"""
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _q(x, st):
+    return _RoundFB.apply(x) if getattr(st, "emulate", None) == "bf16" else x
+
+
+def _qw(w, st):
+    return _RoundF.apply(w) if getattr(st, "emulate", None) == "bf16" else w
+
+
+# ----------------------------------------------------------------------------------------------
 # batch norm: the two formulas of _SynchronizedBatchNorm.forward (reference lib/nn/modules/batchnorm.py:56-86)
 class BNState:
     """How batch norm behaves for this forward pass.
@@ -70,8 +104,9 @@ class BNState:
                                     concatenation of every replica's batch, which is the same pooling.
     """
 
-    def __init__(self, training, sync=False, eps=1e-5, momentum=0.001, update_running=False):
+    def __init__(self, training, sync=False, eps=1e-5, momentum=0.001, update_running=False, emulate=None):
         self.training, self.sync, self.eps, self.momentum, self.update_running = training, sync, eps, momentum, update_running
+        self.emulate = emulate  # None (fp32, the reference) | "bf16" (engine storage precision, see _RoundFB)
 
 
 def batch_norm(x, sd, prefix, st):
@@ -107,9 +142,12 @@ def batch_norm(x, sd, prefix, st):
 
 
 def _cbr(x, sd, conv, bn, st, stride=1, dilation=1, padding=0, relu=True):
-    x = F.conv2d(x, sd[conv + ".weight"], sd.get(conv + ".bias"), stride, padding, dilation)
+    """conv -> BN -> (ReLU). With relu=False the caller finishes the block (residual add + ReLU) and rounds there."""
+    is_img = x.shape[1] == 3
+    w = sd[conv + ".weight"] if is_img else _qw(sd[conv + ".weight"], st)  # the stem kernel reads fp32 weights
+    x = _q(F.conv2d(x, w, sd.get(conv + ".bias"), stride, padding, dilation), st)
     x = batch_norm(x, sd, bn, st)
-    return F.relu(x) if relu else x
+    return _q(F.relu(x), st) if relu else x
 
 
 # ----------------------------------------------------------------------------------------------
@@ -121,7 +159,7 @@ def encoder_forward(x, sd, arch, st, prefix=""):
     x = _cbr(x, sd, P + "conv1", P + "bn1", st, stride=2, padding=1)
     x = _cbr(x, sd, P + "conv2", P + "bn2", st, padding=1)
     x = _cbr(x, sd, P + "conv3", P + "bn3", st, padding=1)
-    x = F.max_pool2d(x, 3, 2, 1)
+    x = F.max_pool2d(x, 3, 2, 1)  # max of bf16 values is exact
     outs = []
     for li, nblocks in enumerate(counts, start=1):
         for bi in range(nblocks):
@@ -140,7 +178,7 @@ def encoder_forward(x, sd, arch, st, prefix=""):
             if (p + "downsample.0.weight") in sd:
                 s, _, _ = _conv_hparams(block, li, bi, "downsample.0", dilated)
                 residual = _cbr(x, sd, p + "downsample.0", p + "downsample.1", st, s, relu=False)
-            x = F.relu(out + residual)
+            x = _q(F.relu(out + residual), st)
         outs.append(x)
     return outs
 
@@ -174,20 +212,20 @@ def decoder_forward(conv_out, sd, arch, st, segSize=None, use_softmax=False, dro
         H, W = conv5.shape[2:]
         ppm_out = [conv5]
         for i, scale in enumerate((1, 2, 3, 6)):
-            y = F.adaptive_avg_pool2d(conv5, scale)
+            y = _q(F.adaptive_avg_pool2d(conv5, scale), st)
             y = _cbr(y, sd, "%sppm.%d.1" % (P, i), "%sppm.%d.2" % (P, i), st)
-            ppm_out.append(F.interpolate(y, (H, W), mode="bilinear", align_corners=False))
+            ppm_out.append(_q(F.interpolate(y, (H, W), mode="bilinear", align_corners=False), st))
         x = torch.cat(ppm_out, 1)
         x = _cbr(x, sd, P + "conv_last.0", P + "conv_last.1", st, padding=1)
         x = _dropout2d(x, dropout_p, st.training, masks.get("main"))
-        logits = F.conv2d(x, sd[P + "conv_last.4.weight"], sd[P + "conv_last.4.bias"])
+        logits = F.conv2d(x, _qw(sd[P + "conv_last.4.weight"], st), sd[P + "conv_last.4.bias"])
         if use_softmax:
             return _head(logits, segSize, True)
         if arch == "ppm":
             return logits if return_logits else F.log_softmax(logits, dim=1)
         y = _cbr(conv_out[-2], sd, P + "cbr_deepsup.0", P + "cbr_deepsup.1", st, padding=1)
         y = _dropout2d(y, dropout_p, st.training, masks.get("deepsup"))
-        logits_ds = F.conv2d(y, sd[P + "conv_last_deepsup.weight"], sd[P + "conv_last_deepsup.bias"])
+        logits_ds = F.conv2d(y, _qw(sd[P + "conv_last_deepsup.weight"], st), sd[P + "conv_last_deepsup.bias"])
         if return_logits:
             return logits, logits_ds
         return F.log_softmax(logits, dim=1), F.log_softmax(logits_ds, dim=1)
@@ -327,9 +365,13 @@ def decoder_param_shapes(arch, fc_dim, num_class=150, fpn_inplanes=(256, 512, 10
     return shapes
 
 
-def synth_state_dict(shapes, seed):
+def synth_state_dict(shapes, seed, residual_gain=None):
     """Deterministic weights for a {name: (kind, shape)} table: He-scaled convs, non-trivial BN affine + running stats.
-    Uses a private CPU torch.Generator so it is reproducible wherever the same torch build runs."""
+    Uses a private CPU torch.Generator so it is reproducible wherever the same torch build runs.
+    residual_gain: if given, the gamma of the LAST BatchNorm of every residual block (bn3 of a Bottleneck, bn2 of a
+    BasicBlock) is multiplied by it.  Random-init BN-ReLU ResNets amplify perturbations ~8 %/layer (bf16 storage alone
+    moves layer4 by 55 % and decorrelates early-layer gradients); a gain of 0.25 gives the trained-network-like,
+    well-conditioned regime in which kernel bugs are distinguishable from rounding chaos (tools/debug_parity.py)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     sd = {}
     for name in sorted(shapes):
@@ -349,6 +391,14 @@ def synth_state_dict(shapes, seed):
             sd[name + "._tmp_running_mean"] = sd[name + ".running_mean"].clone()
             sd[name + "._tmp_running_var"] = sd[name + ".running_var"].clone()
             sd[name + "._running_iter"] = torch.ones(1)
+    if residual_gain is not None:
+        blocks = {}
+        for name in shapes:
+            if name.startswith("layer") and ".bn" in name and "downsample" not in name:
+                blk, bn = name.rsplit(".", 1)
+                blocks[blk] = max(blocks.get(blk, ""), bn)
+        for blk, bn in blocks.items():
+            sd["%s.%s.weight" % (blk, bn)] = sd["%s.%s.weight" % (blk, bn)] * residual_gain
     return sd
 
 

@@ -136,11 +136,14 @@ __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(const float* __restr
 }
 
 // stem conv weight gradient: dW[co][ci][r][s] += sum_pixels dy[p, co] * x[n, ci, 2ho+r-1, 2wo+s-1]
-// 256 threads = 64 co x 4 tap groups (7 of the 27 (ci,r,s) taps each); each block reduces a chunk of pixels.
+// 256 threads = 64 co x 4 tap groups (7 of the 27 (ci,r,s) taps each). Tiles of 64 pixels are staged in shared memory
+// (dy tile 64x64 bf16, input patch 64x27 fp32), so the inner product runs from smem with conflict-free / broadcast reads.
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img,
                                                               const __nv_bfloat16* __restrict__ dy,
                                                               float* __restrict__ dw, int N, int H, int W, int Ho, int Wo,
                                                               int pix_per_block) {
+  __shared__ __nv_bfloat16 s_dy[64][64];
+  __shared__ float s_x[64][28];
   const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
   float acc[7];
 #pragma unroll
@@ -148,22 +151,38 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __res
   const long P = (long)N * Ho * Wo;
   const long p0 = (long)blockIdx.x * pix_per_block;
   const long p1 = min(p0 + pix_per_block, P);
-  for (long p = p0; p < p1; ++p) {
-    const int wo = p % Wo;
-    const long r = p / Wo;
-    const int ho = r % Ho;
-    const int n = r / Ho;
-    const float g = __bfloat162float(dy[p * 64 + co]);
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const int k = grp * 7 + j;
-      if (k < 27) {
+  for (long base = p0; base < p1; base += 64) {
+    const int npx = (int)min((long)64, p1 - base);
+    __syncthreads();
+    // dy tile: 64 px x 64 co bf16 = 8 KB, 16-byte vectors
+    for (int v = threadIdx.x; v < 64 * 8; v += 256) {
+      const int px = v >> 3, part = v & 7;
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (px < npx) q = *reinterpret_cast<const uint4*>(dy + (base + px) * 64 + part * 8);
+      *reinterpret_cast<uint4*>(&s_dy[px][part * 8]) = q;
+    }
+    for (int v = threadIdx.x; v < 64 * 27; v += 256) {
+      const int px = v / 27, k = v % 27;
+      float x = 0.f;
+      if (px < npx) {
+        const long p = base + px;
+        const int wo = p % Wo;
+        const long r = p / Wo;
+        const int ho = r % Ho;
+        const int n = r / Ho;
         const int ci = k / 9, kr = (k % 9) / 3, ks = k % 3;
         const int h = 2 * ho + kr - 1, ww = 2 * wo + ks - 1;
-        float x = 0.f;
         if (h >= 0 && h < H && ww >= 0 && ww < W) x = __ldg(img + (((long)n * 3 + ci) * H + h) * W + ww);
-        acc[j] = fmaf(g, x, acc[j]);
       }
+      s_x[px][k] = x;
+    }
+    if (threadIdx.x < 64) s_x[threadIdx.x][27] = 0.f;
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < 64; ++px) {
+      const float g = __bfloat162float(s_dy[px][co]);
+#pragma unroll
+      for (int j = 0; j < 7; ++j) acc[j] = fmaf(g, s_x[px][grp * 7 + j], acc[j]);
     }
   }
 #pragma unroll
@@ -468,12 +487,13 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const
 
 // ------------------------------------------------------------------------------------------------
 // adaptive average pool to s x s (models/models.py:447): bin i covers [floor(i*H/s), ceil((i+1)*H/s)).
-__global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_ld, __nv_bfloat16* __restrict__ out, int N,
-                                   int H, int W, int C, int S) {
-  // grid: (N*S*S, ceil(C/8/blockDim)) ; one thread = 8 channels of one bin
-  const int cgi = blockIdx.y * blockDim.x + threadIdx.x;
-  if (cgi >= (C >> 3)) return;
-  const int c0 = cgi << 3;
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_ld,
+                                                          __nv_bfloat16* __restrict__ out, int N, int H, int W, int C,
+                                                          int S) {
+  // grid: (N*S*S bins, ceil(C/64)); block = 8 channel groups (64 channels) x 32 pixel lanes striding over the bin
+  __shared__ float red[32][8][8];
+  const int tcg = threadIdx.x & 7, lane = threadIdx.x >> 3;
+  const int c0 = (blockIdx.y * 8 + tcg) << 3;
   int b = blockIdx.x;
   const int j = b % S;
   b /= S;
@@ -481,20 +501,32 @@ __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_l
   const int n = b / S;
   const int h0 = (i * H) / S, h1 = ((i + 1) * H + S - 1) / S;
   const int w0 = (j * W) / S, w1 = ((j + 1) * W + S - 1) / S;
+  const int bw = w1 - w0, npix = (h1 - h0) * bw;
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-  for (int h = h0; h < h1; ++h)
-    for (int w = w0; w < w1; ++w) {
+  if (c0 < C) {
+    for (int p = lane; p < npix; p += 32) {
+      const int h = h0 + p / bw, w = w0 + p % bw;
       float v[8];
       load8(x + (((long)n * H + h) * W + w) * x_ld + c0, v);
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] += v[e];
     }
-  const float inv = 1.f / ((h1 - h0) * (w1 - w0));
+  }
 #pragma unroll
-  for (int e = 0; e < 8; ++e) acc[e] *= inv;
-  store8(out + (((long)n * S + i) * S + j) * C + c0, acc);
+  for (int e = 0; e < 8; ++e) red[lane][tcg][e] = acc[e];
+  __syncthreads();
+  if (lane == 0 && c0 < C) {
+    for (int l = 1; l < 32; ++l) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += red[l][tcg][e];
+    }
+    const float inv = 1.f / (float)npix;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] *= inv;
+    store8(out + (((long)n * S + i) * S + j) * C + c0, acc);
+  }
 }
 
 // backward of up to 4 pooling scales at once, accumulated onto a base gradient:
@@ -588,9 +620,53 @@ __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_
   }
 }
 
-// backward (gather form): one thread = 8 channels of one INPUT pixel; walks the output pixels that reference it.
-__global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long dout_ld, int N, int Ho, int Wo, int C,
-                                    __nv_bfloat16* __restrict__ dx, long dx_ld, int Hi, int Wi, int accumulate) {
+// backward = adjoint of the separable interpolation, in two gather passes (no atomics):
+//   pass 1 (along W): tmp[n,ho,wi,c] = sum_wo  ww(wo -> wi) * dout[n,ho,wo,c]        (fp32 scratch [N,Ho,Wi,C])
+//   pass 2 (along H): dx [n,hi,wi,c] (+)= sum_ho wh(ho -> hi) * tmp[n,ho,wi,c]
+// Each thread owns 8 channels of one destination element and walks only the source positions that reference it.
+__device__ __forceinline__ void bilinear_src_window(int i, int in, int out, int& lo, int& hi) {
+  const float s = (float)out / (float)in;
+  lo = max(0, (int)floorf(((float)i - 1.f + 0.5f) * s - 0.5f) - 1);
+  hi = min(out - 1, (int)ceilf(((float)i + 1.f + 0.5f) * s - 0.5f) + 1);
+}
+
+__global__ void bilinear_bwd_w_kernel(const __nv_bfloat16* __restrict__ dout, long dout_ld, int N, int Ho, int Wo, int C,
+                                      float* __restrict__ tmp, int Wi) {
+  const int cg = C >> 3;
+  const long total = (long)N * Ho * Wi * cg;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    long r = idx / cg;
+    const int wi = r % Wi;
+    r /= Wi;
+    const int ho = r % Ho;
+    const int n = r / Ho;
+    int lo, hi;
+    bilinear_src_window(wi, Wi, Wo, lo, hi);
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int wo = lo; wo <= hi; ++wo) {
+      int w0, w1;
+      float lw;
+      bilinear_coeff(wo, Wi, Wo, w0, w1, lw);
+      float ww = 0.f;
+      if (w0 == wi) ww += 1.f - lw;
+      if (w1 == wi) ww += lw;
+      if (ww == 0.f) continue;
+      float g[8];
+      load8(dout + (((long)n * Ho + ho) * Wo + wo) * dout_ld + c0, g);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaf(g[e], ww, acc[e]);
+    }
+    float4* tp = reinterpret_cast<float4*>(tmp + idx * 8);
+    tp[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    tp[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+}
+
+__global__ void bilinear_bwd_h_kernel(const float* __restrict__ tmp, int N, int Ho, int C, __nv_bfloat16* __restrict__ dx,
+                                      long dx_ld, int Hi, int Wi, int accumulate) {
   const int cg = C >> 3;
   const long total = (long)N * Hi * Wi * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -600,16 +676,12 @@ __global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long
     r /= Wi;
     const int hi = r % Hi;
     const int n = r / Hi;
-    // output rows whose source interval can touch hi: src in (hi-1, hi+1)
-    const float sh = (float)Ho / (float)Hi, sw = (float)Wo / (float)Wi;
-    const int ho_lo = max(0, (int)floorf(((float)hi - 1.f + 0.5f) * sh - 0.5f) - 1);
-    const int ho_hi = min(Ho - 1, (int)ceilf(((float)hi + 1.f + 0.5f) * sh - 0.5f) + 1);
-    const int wo_lo = max(0, (int)floorf(((float)wi - 1.f + 0.5f) * sw - 0.5f) - 1);
-    const int wo_hi = min(Wo - 1, (int)ceilf(((float)wi + 1.f + 0.5f) * sw - 0.5f) + 1);
+    int lo, hi_;
+    bilinear_src_window(hi, Hi, Ho, lo, hi_);
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    for (int ho = lo; ho <= hi_; ++ho) {
       int h0, h1;
       float lh;
       bilinear_coeff(ho, Hi, Ho, h0, h1, lh);
@@ -617,20 +689,11 @@ __global__ void bilinear_bwd_kernel(const __nv_bfloat16* __restrict__ dout, long
       if (h0 == hi) wh += 1.f - lh;
       if (h1 == hi) wh += lh;
       if (wh == 0.f) continue;
-      for (int wo = wo_lo; wo <= wo_hi; ++wo) {
-        int w0, w1;
-        float lw;
-        bilinear_coeff(wo, Wi, Wo, w0, w1, lw);
-        float ww = 0.f;
-        if (w0 == wi) ww += 1.f - lw;
-        if (w1 == wi) ww += lw;
-        if (ww == 0.f) continue;
-        float g[8];
-        load8(dout + (((long)n * Ho + ho) * Wo + wo) * dout_ld + c0, g);
-        const float wgt = wh * ww;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[e] = fmaf(g[e], wgt, acc[e]);
-      }
+      const float4* tp = reinterpret_cast<const float4*>(tmp + ((((long)n * Ho + ho) * Wi + wi) * cg + (c0 >> 3)) * 8);
+      const float4 a = tp[0], b = tp[1];
+      acc[0] = fmaf(a.x, wh, acc[0]), acc[1] = fmaf(a.y, wh, acc[1]), acc[2] = fmaf(a.z, wh, acc[2]);
+      acc[3] = fmaf(a.w, wh, acc[3]), acc[4] = fmaf(b.x, wh, acc[4]), acc[5] = fmaf(b.y, wh, acc[5]);
+      acc[6] = fmaf(b.z, wh, acc[6]), acc[7] = fmaf(b.w, wh, acc[7]);
     }
     __nv_bfloat16* dp = dx + (((long)n * Hi + hi) * Wi + wi) * dx_ld + c0;
     if (accumulate) {
@@ -967,10 +1030,8 @@ int sseg_maxpool_bwd(const void* dout, const void* idx, void* dx, int N, int H, 
 
 int sseg_avgpool_fwd(const void* x, long x_ld, int N, int H, int W, int C, int S, void* out, sseg_stream_t st) {
   SSEG_REQUIRE(x && out && C % 8 == 0 && x_ld % 8 == 0 && S >= 1, "sseg_avgpool_fwd: bad argument");
-  const int cg = C / 8;
-  const int block = cg < 128 ? ((cg + 31) / 32) * 32 : 128;
-  dim3 grid(N * S * S, (cg + block - 1) / block);
-  avgpool_fwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)out, N, H, W, C, S);
+  dim3 grid(N * S * S, (C / 8 + 7) / 8);
+  avgpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)out, N, H, W, C, S);
   LAUNCH_CHECK("avgpool_fwd_kernel");
 }
 
@@ -996,11 +1057,16 @@ int sseg_bilinear_fwd(const void* x, long x_ld, int N, int Hi, int Wi, int C, vo
 }
 
 int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int C, void* dx, long dx_ld, int Hi, int Wi,
-                      int accumulate, sseg_stream_t st) {
-  SSEG_REQUIRE(dout && dx && C % 8 == 0 && dout_ld % 8 == 0 && dx_ld % 8 == 0, "sseg_bilinear_bwd: bad argument");
-  bilinear_bwd_kernel<<<grid_for((long)N * Hi * Wi * (C / 8), 128), 128, 0, (cudaStream_t)st>>>(
-      (const __nv_bfloat16*)dout, dout_ld, N, Ho, Wo, C, (__nv_bfloat16*)dx, dx_ld, Hi, Wi, accumulate);
-  LAUNCH_CHECK("bilinear_bwd_kernel");
+                      int accumulate, float* scratch, sseg_stream_t st) {
+  SSEG_REQUIRE(dout && dx && scratch && C % 8 == 0 && dout_ld % 8 == 0 && dx_ld % 8 == 0,
+               "sseg_bilinear_bwd: bad argument (scratch = float[N*Ho*Wi*C] required)");
+  SSEG_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "sseg_bilinear_bwd: scratch not 16B aligned");
+  bilinear_bwd_w_kernel<<<grid_for((long)N * Ho * Wi * (C / 8), 128), 128, 0, (cudaStream_t)st>>>(
+      (const __nv_bfloat16*)dout, dout_ld, N, Ho, Wo, C, scratch, Wi);
+  bilinear_bwd_h_kernel<<<grid_for((long)N * Hi * Wi * (C / 8), 128), 128, 0, (cudaStream_t)st>>>(
+      scratch, N, Ho, C, (__nv_bfloat16*)dx, dx_ld, Hi, Wi, accumulate);
+  count_launch(2);
+  return check_cuda(cudaGetLastError(), "bilinear_bwd kernels");
 }
 
 int sseg_softmax_nll_fwd(const float* logits, long ld, int C, const long long* label, long P, float* lse, float* accum,

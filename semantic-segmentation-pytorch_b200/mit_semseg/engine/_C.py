@@ -30,6 +30,13 @@ class Geom(Structure):
                 ("tap_dw", c_int * MAX_TAPS), ("tap_src", c_int * MAX_TAPS), ("tap_koff", c_int * MAX_TAPS)]
 
 
+class WeightDesc(Structure):
+    """sseg_weight_desc_t"""
+    _fields_ = [("w", c_void_p), ("wf", c_void_p), ("wd", c_void_p), ("g_src", c_void_p), ("g_dst", c_void_p),
+                ("fwd_ld", c_long), ("dgrad_ld", c_long), ("g_ld", c_long), ("O", c_int), ("I", c_int), ("T", c_int),
+                ("o_pad", c_int), ("first_tile", c_int), ("reserved", c_int)]
+
+
 _lib = None
 
 
@@ -75,6 +82,8 @@ _SIGNATURES = {
     "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), c_int, _p, POINTER(Act), _p, _p, _p],
     "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
     "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],
+    "sseg_prep_conv_weights_batched": [_p, c_int, c_int, _p],
+    "sseg_grads_to_oihw_batched": [_p, c_int, c_int, c_float, _p],
     "sseg_grad_to_oihw": [_p, c_long, c_int, c_int, c_int, _p, c_float, c_int, _p],
     "sseg_stem_conv_fwd": [_p, c_int, c_int, c_int, _p, _p, _p, _p, _p],
     "sseg_stem_conv_wgrad": [_p, c_int, c_int, c_int, _p, _p, _p],
@@ -89,7 +98,7 @@ _SIGNATURES = {
     "sseg_avgpool_fwd": [_p, c_long, c_int, c_int, c_int, c_int, c_int, _p, _p],
     "sseg_avgpool_bwd": [_p, c_long, POINTER(c_void_p), _ip, c_int, _p, c_long, c_int, c_int, c_int, c_int, _p],
     "sseg_bilinear_fwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, _p],
-    "sseg_bilinear_bwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, c_int, _p],
+    "sseg_bilinear_bwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, c_int, _p, _p],
     "sseg_softmax_nll_fwd": [_p, c_long, c_int, _p, c_long, _p, _p, _p],
     "sseg_nll_finalize": [_p, _p, c_float, _p, _p],
     "sseg_softmax_nll_bwd": [_p, c_long, c_int, _p, _p, _p, c_float, c_long, _p, c_long, c_int, _p],

@@ -206,11 +206,15 @@ def bilinear_fwd(x, out):
     _C.check(_C.lib().sseg_bilinear_fwd(_C.ptr(x), _pix(x)[2], n, hi, wi, c, _C.ptr(out), _pix(out)[2], ho, wo, _stream()))
 
 
-def bilinear_bwd(dout, dx, accumulate=False):
+def bilinear_bwd(dout, dx, accumulate=False, scratch=None):
+    """scratch: fp32 tensor with >= N*Ho*Wi*C elements (allocated here when omitted - pass one on hot paths)."""
     n, ho, wo, c = dout.shape
     _, hi, wi, _ = dx.shape
+    if scratch is None:
+        scratch = torch.empty(n * ho * wi * c, device=dout.device, dtype=torch.float32)
+    assert scratch.numel() >= n * ho * wi * c and scratch.dtype == torch.float32
     _C.check(_C.lib().sseg_bilinear_bwd(_C.ptr(dout), _pix(dout)[2], n, ho, wo, c, _C.ptr(dx), _pix(dx)[2], hi, wi,
-                                        int(accumulate), _stream()))
+                                        int(accumulate), _C.ptr(scratch), _stream()))
 
 
 def softmax_nll_fwd(logits, num_class, label, lse, accum):
@@ -253,3 +257,36 @@ def nhwc_bf16_to_nchw_f32(x, out):
 def nchw_f32_to_nhwc_bf16(x, out):
     n, c, h, w = x.shape
     _C.check(_C.lib().sseg_nchw_f32_to_nhwc_bf16(_C.ptr(x), n, h, w, c, _C.ptr(out), _pix(out)[2], _stream()))
+
+
+class WeightTable:
+    """Device table of sseg_weight_desc_t for the batched weight re-layout / gradient re-layout kernels.
+    entries: list of dicts with keys w, wf, wd, g_src, g_dst (tensors or None), O, I, T, o_pad."""
+
+    def __init__(self, entries, device):
+        import ctypes
+        n = len(entries)
+        arr = (_C.WeightDesc * n)()
+        tiles = 0
+        for k, e in enumerate(entries):
+            d = arr[k]
+            for name in ("w", "wf", "wd", "g_src", "g_dst"):
+                t = e.get(name)
+                setattr(d, name, t.data_ptr() if t is not None else None)
+            d.fwd_ld = e["wf"].stride(0) if e.get("wf") is not None else 0
+            d.dgrad_ld = e["wd"].stride(0) if e.get("wd") is not None else 0
+            d.g_ld = e["g_src"].stride(0) if e.get("g_src") is not None else 0
+            d.O, d.I, d.T, d.o_pad = e["O"], e["I"], e["T"], e["o_pad"]
+            assert d.T <= 9
+            d.first_tile = tiles
+            tiles += ((d.O + 31) // 32) * ((d.I + 31) // 32)
+        raw = bytes(arr)
+        self.n, self.tiles = n, tiles
+        self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
+        self.keep = entries
+
+    def prep(self):
+        _C.check(_C.lib().sseg_prep_conv_weights_batched(_C.ptr(self.dev), self.n, self.tiles, _stream()))
+
+    def grads(self, scale=1.0):
+        _C.check(_C.lib().sseg_grads_to_oihw_batched(_C.ptr(self.dev), self.n, self.tiles, float(scale), _stream()))

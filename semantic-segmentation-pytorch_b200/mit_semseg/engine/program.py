@@ -157,11 +157,16 @@ class SegProgram:
 
     # ------------------------------------------------------------------------------------------ forward pieces
     def _prep_weights(self):
+        """One launch re-lays out every conv weight (fp32 OIHW master -> bf16 GEMM operands)."""
+        entries = []
         for c in self.convs.values():
             if c.I == 3:
                 continue  # the stem conv reads the fp32 master weight directly
-            w, wf, wd, op = c.mod.weight, c.wf, (c.wd if self.with_grad else None), c.Opad
-            self.fwd.append(lambda w=w, wf=wf, wd=wd, op=op: ops.prep_conv_weight(w.detach(), wf, wd, o_pad=op))
+            c.pg = torch.empty_like(c.mod.weight) if self.with_grad else None
+            entries.append(dict(w=c.mod.weight.detach(), wf=c.wf, wd=c.wd if self.with_grad else None,
+                                g_src=c.gw if self.with_grad else None, g_dst=c.pg, O=c.O, I=c.I, T=c.T, o_pad=c.Opad))
+        self.wtable = ops.WeightTable(entries, self.dev)
+        self.fwd.append(self.wtable.prep)
 
     def _conv_geom(self, srcs, cw):
         """Input-side geometry of conv `cw` over the (virtual concat of) NHWC tensors `srcs` -> (geom, out H, out W)."""
@@ -303,16 +308,18 @@ class SegProgram:
         if scale != 1.0:
             self.bwd.append(lambda: self.gflat[:self.g_small].mul_(scale))
         for c in self.convs.values():
-            g = torch.empty_like(c.mod.weight)
-            self._pg[id(c)] = g
             if c.I == 3:
+                g = torch.empty_like(c.mod.weight)
+                self._pg[id(c)] = g
+
                 def stem_grad(g=g, c=c):
                     g.copy_(c.gw.view_as(g))  # the stem kernel accumulates in OIHW directly
                     if scale != 1.0:
                         g.mul_(scale)
                 self.bwd.append(stem_grad)
             else:
-                self.bwd.append(lambda g=g, c=c: ops.grad_to_oihw(c.gw, c.O, c.I, c.T, g, scale=scale))
+                self._pg[id(c)] = c.pg
+        self.bwd.append(lambda: self.wtable.grads(scale))
 
     def grad_target(self, act, shape_like=None):
         """(buffer, accumulate?) for writing a gradient contribution of `act`."""
@@ -612,7 +619,9 @@ class UpsampleRec:
             return
         buf, acc = P.grad_target(self.x)
         g = self.a.g
-        P.bwd.append(lambda: ops.bilinear_bwd(g, buf, accumulate=acc))
+        n, ho, _, c = g.shape
+        scratch = P._new(n * ho * buf.shape[2] * c, dtype=torch.float32)
+        P.bwd.append(lambda: ops.bilinear_bwd(g, buf, accumulate=acc, scratch=scratch))
 
 
 class ClassifierRec:

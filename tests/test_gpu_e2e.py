@@ -14,7 +14,7 @@ import torch.nn as nn
 pytestmark = pytest.mark.gpu
 
 
-def _build(enc_arch, dec_arch, fc_dim, use_softmax=False, seed=304):
+def _build(enc_arch, dec_arch, fc_dim, use_softmax=False, seed=304, residual_gain=None):
     from mit_semseg.models import ModelBuilder, SegmentationModule
     from mit_semseg.models import models as M, resnet as R
     from oracle import segnet_oracle as O
@@ -22,7 +22,7 @@ def _build(enc_arch, dec_arch, fc_dim, use_softmax=False, seed=304):
     net = R.__dict__[base](pretrained=False)
     enc = M.ResnetDilated(net, 8) if dil else M.Resnet(net)
     dec = ModelBuilder.build_decoder(dec_arch, fc_dim=fc_dim, num_class=150, use_softmax=use_softmax)
-    esd = O.synth_state_dict(O.encoder_param_shapes(enc_arch), seed)
+    esd = O.synth_state_dict(O.encoder_param_shapes(enc_arch), seed, residual_gain)
     dsd = O.synth_state_dict(O.decoder_param_shapes(dec_arch, fc_dim), seed + 1)
     enc.load_state_dict(esd)
     dec.load_state_dict(dsd)

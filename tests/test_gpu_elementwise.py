@@ -257,3 +257,32 @@ def test_upsample_softmax_and_layout():
     back = torch.empty_like(x)
     ops.nchw_f32_to_nhwc_bf16(o, back)
     assert torch.equal(back, x)
+
+
+def test_batched_weight_prep_and_grad_layout():
+    from mit_semseg.engine import ops
+    g = _gen(9)
+    specs = [(150, 512, 1), (64, 64, 9), (256, 128, 9), (512, 4096, 9)]
+    entries, refs = [], []
+    for O_, I_, T_ in specs:
+        k = int(T_ ** 0.5)
+        w = torch.randn(O_, I_, k, k, device=DEV, generator=g)
+        opad = (O_ + 63) // 64 * 64
+        e = dict(w=w, wf=torch.empty(O_, T_ * I_, device=DEV, dtype=torch.bfloat16),
+                 wd=torch.zeros(I_, T_ * opad, device=DEV, dtype=torch.bfloat16),
+                 g_src=torch.randn(O_, T_ * I_, device=DEV, generator=g), g_dst=torch.empty_like(w),
+                 O=O_, I=I_, T=T_, o_pad=opad)
+        entries.append(e)
+    tab = ops.WeightTable(entries, DEV)
+    tab.prep()
+    tab.grads(0.5)
+    torch.cuda.synchronize()
+    for e in entries:
+        w, O_, I_, T_, opad = e["w"], e["O"], e["I"], e["T"], e["o_pad"]
+        assert torch.equal(e["wf"], w.permute(0, 2, 3, 1).reshape(O_, -1).bfloat16())
+        ref_d = torch.zeros(I_, T_, opad, device=DEV)
+        ref_d[:, :, :O_] = w.permute(1, 2, 3, 0).reshape(I_, T_, O_)
+        assert torch.equal(e["wd"], ref_d.reshape(I_, -1).bfloat16())
+        k = int(T_ ** 0.5)
+        ref_g = 0.5 * e["g_src"].reshape(O_, k, k, I_).permute(0, 3, 1, 2)
+        assert torch.equal(e["g_dst"], ref_g.contiguous())

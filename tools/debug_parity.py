@@ -25,11 +25,14 @@ def main():
     ap.add_argument("--fc", type=int, default=2048)
     ap.add_argument("--n", type=int, default=2)
     ap.add_argument("--hw", type=int, default=128)
+    ap.add_argument("--emulate", default=None, help="bf16: oracle rounds at the engine's storage points")
+    ap.add_argument("--gain", type=float, default=None, help="residual_gain of the synthetic weights")
+    ap.add_argument("--brief", action="store_true")
     args = ap.parse_args()
     from test_gpu_e2e import _build
     from mit_semseg.engine.program import SegProgram, ConvBNRec, StemRec, MaxPoolRec, ClassifierRec
     from oracle import segnet_oracle as O
-    seg, esd, dsd, ds = _build(args.enc, args.dec, args.fc)
+    seg, esd, dsd, ds = _build(args.enc, args.dec, args.fc, residual_gain=args.gain)
     for m in seg.modules():
         if isinstance(m, nn.Dropout2d):
             m.p = 0.0
@@ -44,16 +47,17 @@ def main():
     orig_cbr = O._cbr
 
     def cbr(x, sd, conv, bn, st, stride=1, dilation=1, padding=0, relu=True):
-        y = F.conv2d(x, sd[conv + ".weight"], sd.get(conv + ".bias"), stride, padding, dilation)
+        w = sd[conv + ".weight"] if x.shape[1] == 3 else O._qw(sd[conv + ".weight"], st)
+        y = O._q(F.conv2d(x, w, sd.get(conv + ".bias"), stride, padding, dilation), st)
         z = O.batch_norm(y, sd, bn, st)
         rec_o[conv] = (y.detach(), z.detach())
-        return F.relu(z) if relu else z
+        return O._q(F.relu(z), st) if relu else z
 
     O._cbr = cbr
     e = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in esd.items()}
     d = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in dsd.items()}
-    l_ref, a_ref, feats, out = O.segmentation_forward(feed, e, d, args.enc, args.dec, O.BNState(True), ds, dropout_p=0.0,
-                                                      return_aux=True)
+    l_ref, a_ref, feats, out = O.segmentation_forward(feed, e, d, args.enc, args.dec, O.BNState(True, emulate=args.emulate), ds,
+                                                      dropout_p=0.0, return_aux=True)
     l_ref.backward()
     O._cbr = orig_cbr
     print("loss %.5f vs %.5f ; acc %.4f vs %.4f" % (prog.out[0].item(), l_ref.item(), prog.out[1].item(), a_ref.item()))
@@ -62,8 +66,9 @@ def main():
     for prefix, net in (("", seg.encoder), ("", seg.decoder)):
         for n, m in net.named_modules():
             names[id(m)] = n
+    print("config: emulate=%s gain=%s %s+%s n=%d hw=%d" % (args.emulate, args.gain, args.enc, args.dec, args.n, args.hw))
     print("%-28s %10s %10s" % ("conv (raw y) / applied", "rel(y)", "rel(a)"))
-    for r in prog.records:
+    for r in ([] if args.brief else prog.records):
         if isinstance(r, (ConvBNRec, StemRec)):
             nm = names[id(r.cw.mod)]
             if nm not in rec_o:
@@ -94,7 +99,7 @@ def main():
             rows.append((rel(g, gr), prefix + n, gr.norm().item()))
     rows.sort(reverse=True)
     print("worst gradients:")
-    for r_, n, nr in rows[:25]:
+    for r_, n, nr in rows[:(8 if args.brief else 25)]:
         print("  %-40s rel %.4f  |g| %.3e" % (n, r_, nr))
     import statistics
     print("median grad rel %.4f" % statistics.median(r[0] for r in rows))

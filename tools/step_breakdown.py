@@ -84,6 +84,24 @@ def main():
         gem = [(e0.elapsed_time(e1), name, info) for name, e0, e1, info in recs if info]
         for ms, name, (fl, desc) in sorted(gem, key=lambda x: -x[0])[:60]:
             print("%-10s %8.3f ms %8.1f TFLOP/s  %s" % (name, ms, fl / ms / 1e9, desc))
+    # true per-kernel GPU durations (CUPTI via torch.profiler; unaffected by CPU launch gaps)
+    try:
+        from torch.profiler import profile, ProfilerActivity
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            prog.run_eager()
+            torch.cuda.synchronize()
+        kagg = collections.OrderedDict()
+        for ev in prof.events():
+            if ev.device_type.name == "CUDA" or "cuda" in str(ev.device_type).lower():
+                d = kagg.setdefault(ev.name[:70], [0, 0.0])
+                d[0] += 1
+                d[1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+        ktot = sum(v[1] for v in kagg.values())
+        print("\nprofiler: %d kernel names, total GPU busy %.3f ms" % (len(kagg), ktot / 1e3))
+        for name, (cnt, us) in sorted(kagg.items(), key=lambda kv: -kv[1][1])[:args.top]:
+            print("%-70s %5d %9.3f ms %5.1f%%" % (name, cnt, us / 1e3, 100 * us / ktot))
+    except Exception as exc:  # profiler availability varies
+        print("profiler unavailable:", exc)
     # graph replay for comparison
     prog.capture()
     torch.cuda.synchronize()
