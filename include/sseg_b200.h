@@ -159,15 +159,18 @@ int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_de
 int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
                   const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
                   long pix_per_img, int C, int relu, sseg_stream_t stream);
-/* backward pass 1: s1[c] += sum g', s2[c] += sum g' * xhat, g' = g * chanmul * [a > 0] (a = saved output, NULL: no ReLU) */
+/* backward.  g' = g * chanmul * [ReLU active].  The ReLU mask comes from the saved layer output (a > 0) or, for layers
+ * without a shortcut, is recomputed as (y*scale + fshift > 0) when `a` is NULL and `fshift` is given (one tensor less to
+ * read); both NULL = the layer has no ReLU.
+ * pass 1: s1[c] += sum g', s2[c] += sum g' * xhat          (= dbeta, dgamma; caller zeroes them) */
 int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
-                       const float* invstd, const float* chanmul, float* s1, float* s2, long P, long pix_per_img, int C,
-                       sseg_stream_t stream);
-/* backward pass 2: dy = scale*(g' - s1/M - xhat*s2/M) (eval_mode: dy = scale*g'); dres (optional) = g' */
+                       const float* invstd, const float* scale, const float* fshift, const float* chanmul, float* s1,
+                       float* s2, long P, long pix_per_img, int C, sseg_stream_t stream);
+/* pass 2: dy = scale*(g' - s1/M - xhat*s2/M) (eval_mode: dy = scale*g'); dres (optional) = g' */
 int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
-                      const float* invstd, const float* scale, const float* chanmul, const float* s1, const float* s2,
-                      const float* count_dev, float count_host, void* dy, long dy_ld, void* dres, long dres_ld, long P,
-                      long pix_per_img, int C, int eval_mode, sseg_stream_t stream);
+                      const float* invstd, const float* scale, const float* fshift, const float* chanmul, const float* s1,
+                      const float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
+                      long dres_ld, long P, long pix_per_img, int C, int eval_mode, sseg_stream_t stream);
 
 /* ---- pooling / resize ------------------------------------------------------------------- */
 /* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109). Dense bf16 NHWC; idx (1 byte / output element) feeds the backward. */

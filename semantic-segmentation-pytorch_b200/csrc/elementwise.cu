@@ -19,6 +19,15 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
     f[2 * i] = t.x, f[2 * i + 1] = t.y;
   }
 }
+__device__ __forceinline__ uint4 ldq(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x, f[2 * i + 1] = t.y;
+  }
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   uint4 q;
   __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
@@ -122,7 +131,7 @@ __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(const float* __restr
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int c = 0; c < 64; ++c) {
-      float s = valid ? acc[c] : 0.f, q = s * s;
+      float s = valid ? __bfloat162float(__float2bfloat16(acc[c])) : 0.f, q = s * s;  // statistics of the stored values
 #pragma unroll
       for (int off = 16; off >= 1; off >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -245,6 +254,28 @@ __global__ void bn_iter_update_kernel(float* running_iter, float momentum) {
   running_iter[0] = running_iter[0] * (1.f - momentum) + 1.f;
 }
 
+// The three streaming BN kernels share one decomposition: a block of 256 threads = CGB channel groups (8 channels
+// each) x ROWS pixel lanes; a thread keeps its per-channel coefficients in registers and walks pixels
+// (pix = first + k * stride), UNROLL pixels per iteration with all loads issued before any use.
+constexpr int kBnUnroll = 4;
+
+struct BnTiling {
+  int cgb, rows;    // channel groups per block, pixel lanes per block
+  int gx, gy;       // grid
+};
+static inline BnTiling bn_tiling(long P, int C) {
+  BnTiling t;
+  const int cg = C >> 3;
+  t.cgb = cg < 32 ? cg : 32;  // <= 32 groups (256 channels) per block keeps >= 8 pixel lanes
+  while (256 % t.cgb != 0) --t.cgb;
+  t.rows = 256 / t.cgb;
+  t.gy = (cg + t.cgb - 1) / t.cgb;
+  long want = (P + (long)t.rows * kBnUnroll * 2 - 1) / ((long)t.rows * kBnUnroll * 2);  // ~8 pixels per thread
+  long cap = (148L * 8 + t.gy - 1) / t.gy;
+  t.gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  return t;
+}
+
 // apply: out = [relu]( y*scale + shift + residual' ) * chanmul[n][c];  residual' = r (* rscale + rshift)
 struct BnApplyParams {
   const __nv_bfloat16* y;
@@ -258,55 +289,67 @@ struct BnApplyParams {
   long out_ld;
   long P;          // pixels
   long pix_per_img;
-  int C, relu;
+  int C, relu, cgb, rows;
 };
-__global__ void __launch_bounds__(256) bn_apply_kernel(const BnApplyParams p) {
-  const int cg = p.C >> 3;
-  const long total = p.P * cg;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c0 = (idx % cg) << 3;
-    const long pix = idx / cg;
-    float v[8];
-    load8(p.y + pix * p.y_ld + c0, v);
-    const float4 s0 = *reinterpret_cast<const float4*>(p.scale + c0), s1 = *reinterpret_cast<const float4*>(p.scale + c0 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(p.shift + c0), b1 = *reinterpret_cast<const float4*>(p.shift + c0 + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(const BnApplyParams p) {
+  const int tcol = threadIdx.x % p.cgb, trow = threadIdx.x / p.cgb;
+  const int cgrp = blockIdx.y * p.cgb + tcol;
+  if (cgrp >= (p.C >> 3)) return;
+  const int c0 = cgrp << 3;
+  float sc[8], sh[8], rs[8], rb[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = fmaf(v[e], sc[e], sh[e]);
-    if (p.res) {
-      float r[8];
-      load8(p.res + pix * p.res_ld + c0, r);
-      if (p.rscale) {
+  for (int e = 0; e < 8; ++e) {
+    sc[e] = p.scale[c0 + e], sh[e] = p.shift[c0 + e];
+    rs[e] = p.rscale ? p.rscale[c0 + e] : 1.f, rb[e] = p.rshift ? p.rshift[c0 + e] : 0.f;
+  }
+  const long stride = (long)gridDim.x * p.rows;
+  for (long pix0 = (long)blockIdx.x * p.rows + trow; pix0 < p.P; pix0 += stride * kBnUnroll) {
+    uint4 qv[kBnUnroll], qr[kBnUnroll];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) r[e] = fmaf(r[e], p.rscale[c0 + e], p.rshift[c0 + e]);
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long pix = pix0 + u * stride;
+      if (pix < p.P) {
+        qv[u] = ldq(p.y + pix * p.y_ld + c0);
+        if (p.res) qr[u] = ldq(p.res + pix * p.res_ld + c0);
       }
-#pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] += r[e];
     }
-    if (p.relu) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
-    }
-    if (p.chanmul) {
-      const float* m = p.chanmul + (pix / p.pix_per_img) * p.C + c0;
+    for (int u = 0; u < kBnUnroll; ++u) {
+      const long pix = pix0 + u * stride;
+      if (pix >= p.P) continue;
+      float v[8], r[8];
+      unpack8(qv[u], v);
+      if (p.res) unpack8(qr[u], r);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) v[e] *= m[e];
+      for (int e = 0; e < 8; ++e) {
+        float t = fmaf(v[e], sc[e], sh[e]);
+        if (p.res) t += fmaf(r[e], rs[e], rb[e]);
+        if (p.relu) t = fmaxf(t, 0.f);
+        v[e] = t;
+      }
+      if (p.chanmul) {
+        const float* m = p.chanmul + (pix / p.pix_per_img) * p.C + c0;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] *= m[e];
+      }
+      store8(p.out + pix * p.out_ld + c0, v);
     }
-    store8(p.out + pix * p.out_ld + c0, v);
   }
 }
 
-// backward, pass 1: per-channel S1 = sum g', S2 = sum g' * xhat, with g' = g * chanmul * [a > 0]
-// backward, pass 2: dy = scale * (g' - S1/M - xhat * S2/M);  optionally also stores g' (the residual-branch gradient)
+// backward.  g' = g * chanmul * [relu active]; relu active = (a > 0) from the saved output, or, for layers without a
+// shortcut, recomputed from y as (y*fscale + fshift > 0) so the saved output need not be read at all.
+//   pass 1 (reduce): s1 += sum g', s2 += sum g' * xhat            (xhat = (y - mean) * invstd)
+//   pass 2 (apply) : dy = scale * (g' - s1/M - xhat * s2/M)   (eval_mode: dy = scale * g');  dres (optional) = g'
 struct BnBwdParams {
   const __nv_bfloat16* g;
   long g_ld;
-  const __nv_bfloat16* a;  // saved block output (post-ReLU) or null when the layer has no ReLU
+  const __nv_bfloat16* a;  // saved block output (post-ReLU) or null
   long a_ld;
   const __nv_bfloat16* y;  // saved conv output (pre-BN)
   long y_ld;
-  const float *mean, *invstd, *scale;  // scale = gamma * invstd
+  const float *mean, *invstd, *scale;  // scale = gamma * invstd (forward scale)
+  const float* fshift;                 // forward shift; non-null (with a == null) => ReLU mask recomputed from y
   const float* chanmul;
   float* s1;
   float* s2;
@@ -319,88 +362,102 @@ struct BnBwdParams {
   long P, pix_per_img;
   int C;
   int eval_mode;  // statistics were constants (running stats): dy = scale * g'
+  int cgb, rows;
 };
 
-__device__ __forceinline__ void bn_bwd_gprime(const BnBwdParams& p, long pix, int c0, float (&g)[8]) {
-  load8(p.g + pix * p.g_ld + c0, g);
-  if (p.chanmul) {
-    const float* m = p.chanmul + (pix / p.pix_per_img) * p.C + c0;
+template <bool kApply>
+__global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
+  __shared__ float red[kApply ? 1 : 2][kApply ? 1 : 256][8];
+  const int tcol = threadIdx.x % p.cgb, trow = threadIdx.x / p.cgb;
+  const int cgrp = blockIdx.y * p.cgb + tcol;
+  const bool active = cgrp < (p.C >> 3);
+  const int c0 = (active ? cgrp : 0) << 3;
+  const bool need_y = !p.eval_mode || (p.a == nullptr && p.fshift != nullptr);
+  const bool mask_y = p.a == nullptr && p.fshift != nullptr;
+  // per-channel constants:  reduce: mu, inv ;  apply: dy = ka*g' + kb*y + kc
+  float mu[8], inv[8], fs[8], fb[8], ka[8], kb[8], kc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) g[e] *= m[e];
+  for (int e = 0; e < 8; ++e) {
+    mu[e] = p.mean ? p.mean[c0 + e] : 0.f, inv[e] = p.invstd ? p.invstd[c0 + e] : 1.f;
+    fs[e] = p.scale ? p.scale[c0 + e] : 1.f, fb[e] = p.fshift ? p.fshift[c0 + e] : 0.f;
   }
-  if (p.a) {
-    float a[8];
-    load8(p.a + pix * p.a_ld + c0, a);
+  if (kApply) {
+    const float inv_m = 1.f / (p.count_dev ? *p.count_dev : p.count_host);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) g[e] = a[e] > 0.f ? g[e] : 0.f;
+    for (int e = 0; e < 8; ++e) {
+      if (p.eval_mode) {
+        ka[e] = fs[e], kb[e] = 0.f, kc[e] = 0.f;
+      } else {
+        const float t = fs[e] * inv[e] * p.s2[c0 + e] * inv_m;
+        ka[e] = fs[e], kb[e] = -t, kc[e] = t * mu[e] - fs[e] * p.s1[c0 + e] * inv_m;
+      }
+    }
   }
-}
-
-// block = 256 threads arranged as (256/cgb) pixel rows x cgb channel groups, cgb = min(C/8, 256)
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdParams p) {
-  __shared__ float red[2][256][8];
-  const int cg = p.C >> 3;
-  const int cgb = cg < 256 ? cg : 256;
-  const int rows = 256 / cgb;
-  const int tcol = threadIdx.x % cgb, trow = threadIdx.x / cgb;
-  const int cgrp = blockIdx.y * cgb + tcol;
   float s1[8], s2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) s1[e] = 0.f, s2[e] = 0.f;
-  if (cgrp < cg && trow < rows) {
-    const int c0 = cgrp << 3;
-    float mu[8], is[8];
+  if (active) {
+    const long stride = (long)gridDim.x * p.rows;
+    for (long pix0 = (long)blockIdx.x * p.rows + trow; pix0 < p.P; pix0 += stride * kBnUnroll) {
+      uint4 qg[kBnUnroll], qy[kBnUnroll], qa[kBnUnroll];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) mu[e] = p.mean[c0 + e], is[e] = p.invstd[c0 + e];
-    for (long pix = (long)blockIdx.x * rows + trow; pix < p.P; pix += (long)gridDim.x * rows) {
-      float g[8], y[8];
-      bn_bwd_gprime(p, pix, c0, g);
-      load8(p.y + pix * p.y_ld + c0, y);
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const long pix = pix0 + u * stride;
+        if (pix < p.P) {
+          qg[u] = ldq(p.g + pix * p.g_ld + c0);
+          if (need_y) qy[u] = ldq(p.y + pix * p.y_ld + c0);
+          if (p.a) qa[u] = ldq(p.a + pix * p.a_ld + c0);
+        }
+      }
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        s1[e] += g[e];
-        s2[e] += g[e] * (y[e] - mu[e]) * is[e];
+      for (int u = 0; u < kBnUnroll; ++u) {
+        const long pix = pix0 + u * stride;
+        if (pix >= p.P) continue;
+        float g[8], y[8];
+        unpack8(qg[u], g);
+        if (need_y) unpack8(qy[u], y);
+        if (p.chanmul) {
+          const float* m = p.chanmul + (pix / p.pix_per_img) * p.C + c0;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] *= m[e];
+        }
+        if (p.a) {
+          float a[8];
+          unpack8(qa[u], a);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] = a[e] > 0.f ? g[e] : 0.f;
+        } else if (mask_y) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) g[e] = fmaf(y[e], fs[e], fb[e]) > 0.f ? g[e] : 0.f;
+        }
+        if (kApply) {
+          if (p.dres) store8(p.dres + pix * p.dres_ld + c0, g);
+          float d[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d[e] = p.eval_mode ? ka[e] * g[e] : fmaf(ka[e], g[e], fmaf(kb[e], y[e], kc[e]));
+          store8(p.dy + pix * p.dy_ld + c0, d);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            s1[e] += g[e];
+            s2[e] = fmaf(g[e], (y[e] - mu[e]) * inv[e], s2[e]);
+          }
+        }
       }
     }
   }
+  if (!kApply) {
 #pragma unroll
-  for (int e = 0; e < 8; ++e) red[0][threadIdx.x][e] = s1[e], red[1][threadIdx.x][e] = s2[e];
-  __syncthreads();
-  if (trow == 0 && cgrp < cg) {
-    for (int r = 1; r < rows; ++r) {
+    for (int e = 0; e < 8; ++e) red[0][threadIdx.x][e] = s1[e], red[1][threadIdx.x][e] = s2[e];
+    __syncthreads();
+    if (trow == 0 && active) {
+      for (int r = 1; r < p.rows; ++r) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) s1[e] += red[0][r * cgb + tcol][e], s2[e] += red[1][r * cgb + tcol][e];
-    }
-    const int c0 = cgrp << 3;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(p.s1 + c0 + e, s1[e]), atomicAdd(p.s2 + c0 + e, s2[e]);
-  }
-}
-
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdParams p) {
-  const int cg = p.C >> 3;
-  const long total = p.P * cg;
-  const float inv_m = 1.f / (p.count_dev ? *p.count_dev : p.count_host);
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c0 = (idx % cg) << 3;
-    const long pix = idx / cg;
-    float g[8];
-    bn_bwd_gprime(p, pix, c0, g);
-    if (p.dres) store8(p.dres + pix * p.dres_ld + c0, g);
-    float d[8];
-    if (p.eval_mode) {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) d[e] = g[e] * p.scale[c0 + e];
-    } else {
-      float y[8];
-      load8(p.y + pix * p.y_ld + c0, y);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float xhat = (y[e] - p.mean[c0 + e]) * p.invstd[c0 + e];
-        d[e] = p.scale[c0 + e] * (g[e] - p.s1[c0 + e] * inv_m - xhat * p.s2[c0 + e] * inv_m);
+        for (int e = 0; e < 8; ++e) s1[e] += red[0][r * p.cgb + tcol][e], s2[e] += red[1][r * p.cgb + tcol][e];
       }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) atomicAdd(p.s1 + c0 + e, s1[e]), atomicAdd(p.s2 + c0 + e, s2[e]);
     }
-    store8(p.dy + pix * p.dy_ld + c0, d);
   }
 }
 
@@ -964,51 +1021,54 @@ int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shi
                   long pix_per_img, int C, int relu, sseg_stream_t st) {
   SSEG_REQUIRE(y && scale && shift && out && C % 8 == 0 && y_ld % 8 == 0 && out_ld % 8 == 0 && (!res || res_ld % 8 == 0),
                "sseg_bn_apply: bad argument (channels and strides must be multiples of 8)");
+  const BnTiling t = bn_tiling(P, C);
   BnApplyParams p{(const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, rscale, rshift,
-                  chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu};
-  bn_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(p);
+                  chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu, t.cgb, t.rows};
+  bn_apply_kernel<<<dim3(t.gx, t.gy), 256, 0, (cudaStream_t)st>>>(p);
   LAUNCH_CHECK("bn_apply_kernel");
 }
 
 static int fill_bwd(BnBwdParams& p, const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld,
-                    const float* mean, const float* invstd, const float* scale, const float* chanmul, float* s1, float* s2,
-                    const float* count_dev, float count_host, void* dy, long dy_ld, void* dres, long dres_ld, long P,
-                    long pix_per_img, int C, int eval_mode) {
+                    const float* mean, const float* invstd, const float* scale, const float* fshift, const float* chanmul,
+                    float* s1, float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
+                    long dres_ld, long P, long pix_per_img, int C, int eval_mode, BnTiling* t) {
   SSEG_REQUIRE(g && C % 8 == 0 && g_ld % 8 == 0 && (!a || a_ld % 8 == 0) && (!y || y_ld % 8 == 0),
                "sseg_bn_bwd: bad argument (channels and strides must be multiples of 8)");
+  SSEG_REQUIRE(a == nullptr || fshift == nullptr, "sseg_bn_bwd: pass either the saved output `a` or fshift, not both");
+  SSEG_REQUIRE(fshift == nullptr || (scale != nullptr && y != nullptr), "sseg_bn_bwd: fshift needs scale and y");
+  *t = bn_tiling(P, C);
   p = BnBwdParams{(const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)a, a_ld, (const __nv_bfloat16*)y, y_ld, mean,
-                  invstd, scale, chanmul, s1, s2, count_dev, count_host, (__nv_bfloat16*)dy, dy_ld,
-                  (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode};
+                  invstd, scale, fshift, chanmul, s1, s2, count_dev, count_host, (__nv_bfloat16*)dy, dy_ld,
+                  (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode, t->cgb, t->rows};
   return 0;
 }
 
 int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
-                       const float* invstd, const float* chanmul, float* s1, float* s2, long P, long pix_per_img, int C,
-                       sseg_stream_t st) {
+                       const float* invstd, const float* scale, const float* fshift, const float* chanmul, float* s1,
+                       float* s2, long P, long pix_per_img, int C, sseg_stream_t st) {
   BnBwdParams p;
-  int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, nullptr, chanmul, s1, s2, nullptr, 1.f, nullptr, 0,
-                    nullptr, 0, P, pix_per_img, C, 0);
+  BnTiling t;
+  int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, fshift, chanmul, s1, s2, nullptr, 1.f, nullptr, 0,
+                    nullptr, 0, P, pix_per_img, C, 0, &t);
   if (rc) return rc;
   SSEG_REQUIRE(y && mean && invstd && s1 && s2, "sseg_bn_bwd_reduce: null argument");
-  const int cg = C / 8, cgb = cg < 256 ? cg : 256, rows = 256 / cgb;
-  SSEG_REQUIRE(256 % cgb == 0, "sseg_bn_bwd_reduce: C/8 must divide 256 or be a multiple of 256 (C=%d)", C);
-  dim3 grid(grid_for((P + rows - 1) / rows, 1, 148 * 4), (cg + cgb - 1) / cgb);
-  bn_bwd_reduce_kernel<<<grid, 256, 0, (cudaStream_t)st>>>(p);
+  bn_bwd_kernel<false><<<dim3(t.gx, t.gy), 256, 0, (cudaStream_t)st>>>(p);
   LAUNCH_CHECK("bn_bwd_reduce_kernel");
 }
 
 int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
-                      const float* invstd, const float* scale, const float* chanmul, const float* s1, const float* s2,
-                      const float* count_dev, float count_host, void* dy, long dy_ld, void* dres, long dres_ld, long P,
-                      long pix_per_img, int C, int eval_mode, sseg_stream_t st) {
+                      const float* invstd, const float* scale, const float* fshift, const float* chanmul, const float* s1,
+                      const float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
+                      long dres_ld, long P, long pix_per_img, int C, int eval_mode, sseg_stream_t st) {
   BnBwdParams p;
-  int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, chanmul, const_cast<float*>(s1),
-                    const_cast<float*>(s2), count_dev, count_host, dy, dy_ld, dres, dres_ld, P, pix_per_img, C,
-                    eval_mode);
+  BnTiling t;
+  int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, fshift, chanmul, const_cast<float*>(s1),
+                    const_cast<float*>(s2), count_dev, count_host, dy, dy_ld, dres, dres_ld, P, pix_per_img, C, eval_mode,
+                    &t);
   if (rc) return rc;
   SSEG_REQUIRE(dy && scale && dy_ld % 8 == 0 && (!dres || dres_ld % 8 == 0), "sseg_bn_bwd_apply: bad argument");
   SSEG_REQUIRE(eval_mode || (y && mean && invstd && s1 && s2), "sseg_bn_bwd_apply: training mode needs y/mean/invstd/s1/s2");
-  bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(p);
+  bn_bwd_kernel<true><<<dim3(t.gx, t.gy), 256, 0, (cudaStream_t)st>>>(p);
   LAUNCH_CHECK("bn_bwd_apply_kernel");
 }
 

@@ -213,7 +213,10 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         float s[32], q[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          s[j] = valid ? v[j] : 0.f;
+          // statistics of the values as STORED (bf16-rounded): mean/var then describe exactly the tensor that
+          // gets normalised, so sum(xhat) = 0 holds to fp32 accuracy even when inv_std is large (tiny batches)
+          const float r = p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]));
+          s[j] = valid ? r : 0.f;
           q[j] = s[j] * s[j];
         }
 #pragma unroll

@@ -154,24 +154,25 @@ def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None
     return out
 
 
-def bn_bwd_reduce(g, a, y, mean, invstd, s1, s2, chanmul=None):
+def bn_bwd_reduce(g, a, y, mean, invstd, s1, s2, chanmul=None, scale=None, fshift=None):
+    """a: saved output (ReLU mask) or None; (scale, fshift) with a=None: mask recomputed from y; all None: no ReLU."""
     P, ppi, g_ld = _pix(g)
     a_ld = _pix(a)[2] if a is not None else 0
     _C.check(_C.lib().sseg_bn_bwd_reduce(_C.ptr(g), g_ld, _C.ptr(a), a_ld, _C.ptr(y), _pix(y)[2], _C.ptr(mean),
-                                         _C.ptr(invstd), _C.ptr(chanmul), _C.ptr(s1), _C.ptr(s2), P, ppi, g.shape[3],
-                                         _stream()))
+                                         _C.ptr(invstd), _C.ptr(scale), _C.ptr(fshift), _C.ptr(chanmul), _C.ptr(s1),
+                                         _C.ptr(s2), P, ppi, g.shape[3], _stream()))
 
 
 def bn_bwd_apply(g, a, y, mean, invstd, scale, s1, s2, count, dy, dres=None, chanmul=None, eval_mode=False,
-                 count_dev=None):
+                 count_dev=None, fshift=None):
     P, ppi, g_ld = _pix(g)
     a_ld = _pix(a)[2] if a is not None else 0
     y_ld = _pix(y)[2] if y is not None else 0
     dres_ld = _pix(dres)[2] if dres is not None else 0
     _C.check(_C.lib().sseg_bn_bwd_apply(_C.ptr(g), g_ld, _C.ptr(a), a_ld, _C.ptr(y), y_ld, _C.ptr(mean), _C.ptr(invstd),
-                                        _C.ptr(scale), _C.ptr(chanmul), _C.ptr(s1), _C.ptr(s2), _C.ptr(count_dev),
-                                        float(count), _C.ptr(dy), _pix(dy)[2], _C.ptr(dres), dres_ld, P, ppi, g.shape[3],
-                                        int(eval_mode), _stream()))
+                                        _C.ptr(scale), _C.ptr(fshift), _C.ptr(chanmul), _C.ptr(s1), _C.ptr(s2),
+                                        _C.ptr(count_dev), float(count), _C.ptr(dy), _pix(dy)[2], _C.ptr(dres), dres_ld, P,
+                                        ppi, g.shape[3], int(eval_mode), _stream()))
 
 
 def maxpool_fwd(x, out, idx):

@@ -410,7 +410,7 @@ class StemRec:
         if self.a.g is None:
             return
         dy = torch.empty_like(self.y)
-        _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, self.a.t, self.y, dy, None, None)
+        _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, None, self.y, dy, None, None, mask_from_y=True)
         gw = self.cw.gw
         P.bwd.append(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3)))
 
@@ -438,17 +438,22 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
                                           chanmul=chanmul))
 
 
-def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul):
-    """g: gradient w.r.t. the layer output; a: saved output if the layer has a ReLU (mask source) else None."""
+def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from_y=False):
+    """g: gradient w.r.t. the layer output.  ReLU mask: `a` (saved output) if given, else recomputed from y when
+    mask_from_y (layers without a shortcut), else the layer has no ReLU."""
     C = bns.C
     st = bns.stats
+    sc = bns.scale
+    fs = bns.shift if (mask_from_y and a is None) else None
     if mode == ops.BN_EVAL:
-        P.bwd.append(lambda: ops.bn_bwd_apply(g, a, None, None, None, bns.scale, None, None, 1.0, dy, dres=dres,
-                                              chanmul=chanmul, eval_mode=True))
+        P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, None, None, sc, None, None, 1.0, dy, dres=dres, chanmul=chanmul,
+                                              eval_mode=True, fshift=fs))
         # dgamma / dbeta of a frozen BN still exist in the reference (affine params stay trainable under fix_bn)
-        P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul))
+        P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul,
+                                               scale=sc, fshift=fs))
         return
-    P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul))
+    P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul,
+                                           scale=sc, fshift=fs))
     cdev = None
     if mode == ops.BN_TRAIN_SYNC:
         cdev = st[2 * C:2 * C + 1]
@@ -456,8 +461,8 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul):
             # dgamma|dbeta are adjacent in the flat gradient buffer: one all-reduce for both
             both = P.gflat[bns.dgamma.storage_offset():bns.dgamma.storage_offset() + 2 * C]
             P.bwd.append(lambda: P.dist.all_reduce(both))
-    P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, bns.scale, bns.dbeta, bns.dgamma, count, dy,
-                                          dres=dres, chanmul=chanmul, count_dev=cdev))
+    P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, sc, bns.dbeta, bns.dgamma, count, dy, dres=dres,
+                                          chanmul=chanmul, count_dev=cdev, fshift=fs))
     if mode == ops.BN_TRAIN_SYNC and P.dist is not None:
         # the bucket all-reduce at the end sums gflat over ranks again: pre-divide the already-global dgamma/dbeta
         both = P.gflat[bns.dgamma.storage_offset():bns.dgamma.storage_offset() + 2 * C]
@@ -512,8 +517,10 @@ class ConvBNRec:
         elif isinstance(self.res, ConvBNRec):
             ds_rec = self.res
             dres = torch.empty_like(ds_rec.y)
-        a = self.a.t if (self.apply and self.relu) else None
-        _emit_bn_backward(P, bns, self.mode, self.count, g, a, self.y, dy, dres, self.chanmul)
+        has_relu = self.apply and self.relu
+        from_y = has_relu and self.res is None          # no shortcut: the mask is a function of y alone
+        a = self.a.t if (has_relu and not from_y) else None
+        _emit_bn_backward(P, bns, self.mode, self.count, g, a, self.y, dy, dres, self.chanmul, mask_from_y=from_y)
         if ds_rec is not None:
             ds_rec.backward(g_override=dres)
         # weight gradient: GEMM over pixels (sseg_conv_wgrad)

@@ -122,6 +122,18 @@ def test_bn_forward_backward(C, hw, mode):
     # note: the kernel masks with the *stored bf16* output (a > 0); sub-ulp outputs can flip, hence the tolerance
     _close(dres, dres_ref, 2 ** -6, "dres")
     _close(dy, dy_ref, 2 ** -5, "dy")
+    # no-shortcut layers: the ReLU mask recomputed from y must give the same result as the saved output
+    out2 = torch.empty_like(y)
+    ops.bn_apply(y, scale, shift, out2, relu=True, chanmul=mask)
+    s1a, s2a, s1b, s2b = [torch.zeros(C, device=DEV) for _ in range(4)]
+    ops.bn_bwd_reduce(gout, out2, y, mean, invstd, s1a, s2a, chanmul=mask)
+    ops.bn_bwd_reduce(gout, None, y, mean, invstd, s1b, s2b, chanmul=mask, scale=scale, fshift=shift)
+    _close(s1b, s1a, 1e-4, "mask-from-y s1")
+    _close(s2b, s2a, 1e-4, "mask-from-y s2")
+    dya, dyb = torch.empty_like(y), torch.empty_like(y)
+    ops.bn_bwd_apply(gout, out2, y, mean, invstd, scale, s1a, s2a, cnt, dya, chanmul=mask)
+    ops.bn_bwd_apply(gout, None, y, mean, invstd, scale, s1a, s2a, cnt, dyb, chanmul=mask, fshift=shift)
+    assert torch.equal(dya, dyb)
     # dgamma / dbeta are s2 / s1
     gam = gamma.clone().requires_grad_(True)
     bet = beta.clone().requires_grad_(True)
