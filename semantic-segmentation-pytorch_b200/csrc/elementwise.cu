@@ -263,7 +263,7 @@ struct BnTiling {
   int cgb, rows;    // channel groups per block, pixel lanes per block
   int gx, gy;       // grid
 };
-static inline BnTiling bn_tiling(long P, int C) {
+static inline BnTiling bn_tiling(long P, int C, bool reduce = false) {
   BnTiling t;
   const int cg = C >> 3;
   t.cgb = cg < 32 ? cg : 32;  // <= 32 groups (256 channels) per block keeps >= 8 pixel lanes
@@ -271,7 +271,8 @@ static inline BnTiling bn_tiling(long P, int C) {
   t.rows = 256 / t.cgb;
   t.gy = (cg + t.cgb - 1) / t.cgb;
   long want = (P + (long)t.rows * kBnUnroll * 2 - 1) / ((long)t.rows * kBnUnroll * 2);  // ~8 pixels per thread
-  long cap = (148L * 8 + t.gy - 1) / t.gy;
+  // the reduce kernel pays a block-level tail (smem reduction + atomics): keep its grid at ~2 waves of 2 blocks/SM
+  long cap = ((reduce ? 148L * 4 : 148L * 8) + t.gy - 1) / t.gy;
   t.gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   return t;
 }
@@ -1031,12 +1032,12 @@ int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shi
 static int fill_bwd(BnBwdParams& p, const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld,
                     const float* mean, const float* invstd, const float* scale, const float* fshift, const float* chanmul,
                     float* s1, float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
-                    long dres_ld, long P, long pix_per_img, int C, int eval_mode, BnTiling* t) {
+                    long dres_ld, long P, long pix_per_img, int C, int eval_mode, BnTiling* t, bool reduce = false) {
   SSEG_REQUIRE(g && C % 8 == 0 && g_ld % 8 == 0 && (!a || a_ld % 8 == 0) && (!y || y_ld % 8 == 0),
                "sseg_bn_bwd: bad argument (channels and strides must be multiples of 8)");
   SSEG_REQUIRE(a == nullptr || fshift == nullptr, "sseg_bn_bwd: pass either the saved output `a` or fshift, not both");
   SSEG_REQUIRE(fshift == nullptr || (scale != nullptr && y != nullptr), "sseg_bn_bwd: fshift needs scale and y");
-  *t = bn_tiling(P, C);
+  *t = bn_tiling(P, C, reduce);
   p = BnBwdParams{(const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)a, a_ld, (const __nv_bfloat16*)y, y_ld, mean,
                   invstd, scale, fshift, chanmul, s1, s2, count_dev, count_host, (__nv_bfloat16*)dy, dy_ld,
                   (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode, t->cgb, t->rows};
@@ -1049,7 +1050,7 @@ int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const
   BnBwdParams p;
   BnTiling t;
   int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, fshift, chanmul, s1, s2, nullptr, 1.f, nullptr, 0,
-                    nullptr, 0, P, pix_per_img, C, 0, &t);
+                    nullptr, 0, P, pix_per_img, C, 0, &t, true);
   if (rc) return rc;
   SSEG_REQUIRE(y && mean && invstd && s1 && s2, "sseg_bn_bwd_reduce: null argument");
   bn_bwd_kernel<false><<<dim3(t.gx, t.gy), 256, 0, (cudaStream_t)st>>>(p);

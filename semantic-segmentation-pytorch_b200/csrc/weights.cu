@@ -30,40 +30,43 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
   const int o0 = (local / tiles_i) * kTile, i0 = (local % tiles_i) * kTile;
   const int no = min(kTile, O - o0), ni = min(kTile, I - i0);
   const int row = ni * T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (mode == 0) {
     // ---- load OIHW: for a fixed o the (i, t) range is contiguous
     const float* w = d->w;
-    for (int idx = threadIdx.x; idx < no * row; idx += 256) {
-      const int ol = idx / row, r = idx % row;
-      tile[ol][r] = w[((long)(o0 + ol) * I + i0) * T + r];
+    for (int ol = warp; ol < no; ol += 8) {
+      const float* src = w + ((long)(o0 + ol) * I + i0) * T;
+      for (int r = lane; r < row; r += 32) tile[ol][r] = src[r];
     }
     __syncthreads();
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d->wf);
-    if (wf) {
-      for (int idx = threadIdx.x; idx < no * T * ni; idx += 256) {
-        const int il = idx % ni, t = (idx / ni) % T, ol = idx / (ni * T);
-        wf[(long)(o0 + ol) * d->fwd_ld + (long)t * I + i0 + il] = __float2bfloat16(tile[ol][il * T + t]);
+    if (wf && lane < ni) {
+      for (int ol = warp; ol < no; ol += 8) {
+        __nv_bfloat16* dst = wf + (long)(o0 + ol) * d->fwd_ld + i0 + lane;
+        for (int t = 0; t < T; ++t) dst[(long)t * I] = __float2bfloat16(tile[ol][lane * T + t]);
       }
     }
     __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d->wd);
-    if (wd) {
-      for (int idx = threadIdx.x; idx < ni * T * no; idx += 256) {
-        const int ol = idx % no, t = (idx / no) % T, il = idx / (no * T);
-        wd[(long)(i0 + il) * d->dgrad_ld + (long)t * d->o_pad + o0 + ol] = __float2bfloat16(tile[ol][il * T + t]);
+    if (wd && lane < no) {
+      for (int il = warp; il < ni; il += 8) {
+        __nv_bfloat16* dst = wd + (long)(i0 + il) * d->dgrad_ld + o0 + lane;
+        for (int t = 0; t < T; ++t) dst[(long)t * d->o_pad] = __float2bfloat16(tile[lane][il * T + t]);
       }
     }
   } else {
     // ---- gradients: load [O][T*I] (i fastest), store OIHW ((i,t) contiguous per o)
     const float* g = d->g_src;
-    for (int idx = threadIdx.x; idx < no * T * ni; idx += 256) {
-      const int il = idx % ni, t = (idx / ni) % T, ol = idx / (ni * T);
-      tile[ol][il * T + t] = g[(long)(o0 + ol) * d->g_ld + (long)t * I + i0 + il];
+    if (lane < ni) {
+      for (int ol = warp; ol < no; ol += 8) {
+        const float* src = g + (long)(o0 + ol) * d->g_ld + i0 + lane;
+        for (int t = 0; t < T; ++t) tile[ol][lane * T + t] = src[(long)t * I];
+      }
     }
     __syncthreads();
     float* out = d->g_dst;
-    for (int idx = threadIdx.x; idx < no * row; idx += 256) {
-      const int ol = idx / row, r = idx % row;
-      out[((long)(o0 + ol) * I + i0) * T + r] = tile[ol][r] * scale;
+    for (int ol = warp; ol < no; ol += 8) {
+      float* dst = out + ((long)(o0 + ol) * I + i0) * T;
+      for (int r = lane; r < row; r += 32) dst[r] = tile[ol][r] * scale;
     }
   }
 }

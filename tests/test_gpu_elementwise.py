@@ -57,8 +57,10 @@ def test_stem_conv_fwd_and_wgrad():
     ssum, ssq = torch.zeros(64, device=DEV), torch.zeros(64, device=DEV)
     ops.stem_conv_fwd(img, w, out, ssum, ssq)
     _close(nchw(out), ref, 2 ** -8, "stem fwd")
-    _close(ssum, ref.sum(dim=(0, 2, 3)), 1e-3, "stem sum")
-    _close(ssq, (ref * ref).sum(dim=(0, 2, 3)), 1e-3, "stem sqsum")
+    # statistics are those of the bf16-rounded stored values: compare with the rounded reference
+    rr = ref.bfloat16().float()
+    _close(ssum, rr.sum(dim=(0, 2, 3)), 2e-3, "stem sum")
+    _close(ssq, (rr * rr).sum(dim=(0, 2, 3)), 2e-3, "stem sqsum")
     dy = (torch.randn(2, ho, wo, 64, device=DEV, generator=g) * 0.1).bfloat16()
     wp = w.clone().requires_grad_(True)
     (gref,) = torch.autograd.grad(F.conv2d(img, wp, stride=2, padding=1), wp, nchw(dy))

@@ -49,7 +49,8 @@ def _run(n, h, w_, cins, cout, k, d, out_f32=False, bias=False, addend=False, st
     if n_store > cout:
         assert (out[..., cout:n_store].float().abs().max().item() == 0.0)
     if stats:
-        rs, rq = ref.sum(dim=(0, 1, 2)), (ref * ref).sum(dim=(0, 1, 2))
+        rr = ref if out_f32 else ref.bfloat16().float()  # statistics describe the stored (rounded) tensor
+        rs, rq = rr.sum(dim=(0, 1, 2)), (rr * rr).sum(dim=(0, 1, 2))
         assert (ssum - rs).abs().max().item() <= 1e-3 * max(1.0, rs.abs().max().item()) + 1e-2 * (n * h * w_) ** 0.5
         assert (ssq - rq).abs().max().item() <= 1e-3 * rq.abs().max().item()
 

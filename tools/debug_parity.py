@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--emulate", default=None, help="bf16: oracle rounds at the engine's storage points")
     ap.add_argument("--gain", type=float, default=None, help="residual_gain of the synthetic weights")
     ap.add_argument("--brief", action="store_true")
+    ap.add_argument("--bn-eval", action="store_true", help="BatchNorm layers in eval mode (fixed affine): removes the "
+                    "batch-statistics coupling, so gradient wiring errors are not masked by small-batch BN chaos")
     args = ap.parse_args()
     from test_gpu_e2e import _build
     from mit_semseg.engine.program import SegProgram, ConvBNRec, StemRec, MaxPoolRec, ClassifierRec
@@ -37,6 +39,10 @@ def main():
         if isinstance(m, nn.Dropout2d):
             m.p = 0.0
     seg.cuda().train()
+    if args.bn_eval:
+        for m in seg.modules():
+            if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                m.eval()
     feed = O.synth_batch(args.n, args.hw, args.hw, 8, 1)
     prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
     prog.load_inputs(feed["img_data"].cuda(), feed["seg_label"].cuda())
@@ -56,7 +62,7 @@ def main():
     O._cbr = cbr
     e = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in esd.items()}
     d = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in dsd.items()}
-    l_ref, a_ref, feats, out = O.segmentation_forward(feed, e, d, args.enc, args.dec, O.BNState(True, emulate=args.emulate), ds,
+    l_ref, a_ref, feats, out = O.segmentation_forward(feed, e, d, args.enc, args.dec, O.BNState(not args.bn_eval, emulate=args.emulate), ds,
                                                       dropout_p=0.0, return_aux=True)
     l_ref.backward()
     O._cbr = orig_cbr
@@ -66,7 +72,7 @@ def main():
     for prefix, net in (("", seg.encoder), ("", seg.decoder)):
         for n, m in net.named_modules():
             names[id(m)] = n
-    print("config: emulate=%s gain=%s %s+%s n=%d hw=%d" % (args.emulate, args.gain, args.enc, args.dec, args.n, args.hw))
+    print("config: bn_eval=%s emulate=%s gain=%s %s+%s n=%d hw=%d" % (args.bn_eval, args.emulate, args.gain, args.enc, args.dec, args.n, args.hw))
     print("%-28s %10s %10s" % ("conv (raw y) / applied", "rel(y)", "rel(a)"))
     for r in ([] if args.brief else prog.records):
         if isinstance(r, (ConvBNRec, StemRec)):
