@@ -271,8 +271,8 @@ static inline BnTiling bn_tiling(long P, int C, bool reduce = false) {
   t.rows = 256 / t.cgb;
   t.gy = (cg + t.cgb - 1) / t.cgb;
   long want = (P + (long)t.rows * kBnUnroll * 2 - 1) / ((long)t.rows * kBnUnroll * 2);  // ~8 pixels per thread
-  // the reduce kernel pays a block-level tail (smem reduction + atomics): keep its grid at ~2 waves of 2 blocks/SM
-  long cap = ((reduce ? 148L * 4 : 148L * 8) + t.gy - 1) / t.gy;
+  // the reduce kernel pays a block-level tail (smem reduction + atomics): keep its grid at one wave of 2 blocks/SM
+  long cap = ((reduce ? 148L * 2 : 148L * 8) + t.gy - 1) / t.gy;
   t.gx = (int)(want < 1 ? 1 : (want > cap ? cap : want));
   return t;
 }

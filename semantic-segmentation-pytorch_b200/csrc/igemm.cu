@@ -363,7 +363,10 @@ extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, lo
     SSEG_REQUIRE(g->tap_koff[t] + span <= w_ld, "sseg_conv_igemm: tap %d K range exceeds w_ld", t);
     p.num_k_steps += span / kBlockK;
   }
-  const int block_n = cout <= 64 ? 64 : 128;
+  // N tile: 128 unless that leaves most SMs without a CTA (148 SMs x 2 resident CTAs): then halve it to double the grid
+  const int m_tiles = gh.vn * gh.tiles_h * gh.tiles_w;
+  int block_n = cout <= 64 ? 64 : 128;
+  if (block_n == 128 && m_tiles * ceil_div(n_store, 128) <= 160) block_n = 64;
   p.n_tiles = ceil_div(n_store, block_n);
   rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, block_n);
   if (rc) return rc;

@@ -88,6 +88,9 @@ class SegProgram:
         self.fwd, self.bwd, self.records = [], [], []
         self.keep = []  # anything that must stay alive (geometry structs hold raw pointers)
         self.graph = None
+        # weight-gradient GEMMs are off the critical path of the backward pass (nothing downstream reads them until
+        # the gradient bucket): they run on a side stream and fill the SMs the data-gradient chain leaves idle
+        self.side = torch.cuda.Stream(self.dev)
 
         self.convs, self.bns = {}, {}
         for m in list(self.enc.modules()) + list(self.dec.modules()):
@@ -297,6 +300,7 @@ class SegProgram:
         self.bwd.append(lambda: self.gflat.zero_())
         for rec in reversed(self.records):
             rec.backward()
+        self.bwd.append(self.join_side)
         if self.dist is not None:
             # the data-parallel gradient bucket (reference: backward of nn.DataParallel's Broadcast):
             # one NCCL all-reduce of the flat fp32 gradient buffer
@@ -320,6 +324,20 @@ class SegProgram:
             else:
                 self._pg[id(c)] = c.pg
         self.bwd.append(lambda: self.wtable.grads(scale))
+
+    def on_side(self, fn):
+        """Closure that runs `fn` on the side stream, ordered after everything enqueued so far on the main stream."""
+        def run():
+            main = torch.cuda.current_stream(self.dev)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                fn()
+        return run
+
+    def join_side(self):
+        torch.cuda.current_stream(self.dev).wait_stream(self.side)
 
     def grad_target(self, act, shape_like=None):
         """(buffer, accumulate?) for writing a gradient contribution of `act`."""
@@ -412,7 +430,7 @@ class StemRec:
         dy = torch.empty_like(self.y)
         _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, None, self.y, dy, None, None, mask_from_y=True)
         gw = self.cw.gw
-        P.bwd.append(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3)))
+        P.bwd.append(P.on_side(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3))))
 
 
 def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, chanmul):
@@ -525,7 +543,7 @@ class ConvBNRec:
             ds_rec.backward(g_override=dres)
         # weight gradient: GEMM over pixels (sseg_conv_wgrad)
         geom, gw, O = self.geom, cw.gw, cw.O
-        P.bwd.append(lambda: ops.conv_wgrad(geom, dy, O, gw))
+        P.bwd.append(P.on_side(lambda: ops.conv_wgrad(geom, dy, O, gw)))
         # data gradient: implicit GEMM of dy with the transposed weight, taps mirrored
         self._emit_dgrad(dy)
 
@@ -651,10 +669,13 @@ class ClassifierRec:
             return
         dl = self.dlogits  # bf16 [n,h,w,Opad], zero padded
         geom, gw, O = self.geom, cw.gw, cw.O
-        P.bwd.append(lambda: ops.conv_wgrad(geom, dl, O, gw))
-        if cw.gb is not None:
-            gb = cw.gb
-            P.bwd.append(lambda: ops.colsum(dl, O, gb))
+        gb = cw.gb
+
+        def head_wgrad():
+            ops.conv_wgrad(geom, dl, O, gw)
+            if gb is not None:
+                ops.colsum(dl, O, gb)
+        P.bwd.append(P.on_side(head_wgrad))
         buf, acc = P.grad_target(self.x)
         gd = ops.make_geom([dl], ([0], [0]), tap_koff=[0])
         P.keep.append(gd)
