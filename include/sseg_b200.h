@@ -54,6 +54,11 @@ int sseg_version(void);
  * (bench.py's "gpu_launches"). */
 long sseg_launch_count(void);
 void sseg_launch_count_reset(void);
+/* Programmatic dependent launch: when enabled every kernel is launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization, so the prologue of kernel N+1 (barrier init, TMEM allocation,
+ * descriptor prefetch, coefficient loads) overlaps the tail of kernel N. Default: the SSEG_PDL environment variable. */
+void sseg_set_pdl(int enable);
+int sseg_get_pdl(void);
 
 /* ---- convolution as implicit GEMM on tcgen05 tensor cores ------------------------------- */
 /*

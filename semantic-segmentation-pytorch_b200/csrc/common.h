@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/sseg_b200.h"
 
@@ -42,5 +43,22 @@ int get_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long rows, lo
                 int box_rows);
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// Kernel launch with the programmatic-stream-serialization attribute (PDL) when enabled (SSEG_PDL=1 in the environment
+// or sseg_set_pdl(1)); otherwise a plain launch.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 }  // namespace sseg

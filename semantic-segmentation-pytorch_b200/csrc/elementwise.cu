@@ -2,6 +2,7 @@
 // bilinear resize, the stem convolution (Cin = 3), weight re-layout, log-softmax + NLL loss, column sums.
 // All activations are NHWC bf16 (C contiguous) accessed with 16-byte vectors (8 channels per thread).
 #include "common.h"
+#include "ptx.cuh"
 #include <cuda_bf16.h>
 
 namespace sseg {
@@ -47,6 +48,7 @@ static inline int grid_for(long work, int block, int max_blocks = 148 * 16) {
 // weight re-layout: fp32 OIHW master weights -> bf16 [O][T*I] (forward) and bf16 [I][T*Opad] (data gradient)
 __global__ void prep_weight_kernel(const float* __restrict__ w, int O, int I, int T, __nv_bfloat16* __restrict__ wf,
                                    long wf_ld, __nv_bfloat16* __restrict__ wd, long wd_ld, int o_pad) {
+  pdl_sync();
   const long total = (long)O * I * T;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     // idx enumerates the forward layout (o, t, i) so the bf16 stores are coalesced
@@ -64,6 +66,7 @@ __global__ void prep_weight_kernel(const float* __restrict__ w, int O, int I, in
 // gradient re-layout: fp32 [O][T*I] (what wgrad produces) -> fp32 OIHW (+= or =), times scale
 __global__ void grad_to_oihw_kernel(const float* __restrict__ g, long g_ld, int O, int I, int T, float* __restrict__ out,
                                     float scale, int accumulate) {
+  pdl_sync();
   const long total = (long)O * I * T;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
     // idx enumerates OIHW so the stores are coalesced
@@ -83,6 +86,7 @@ __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(const float* __restr
                                                             __nv_bfloat16* __restrict__ out, float* __restrict__ ssum,
                                                             float* __restrict__ ssq, int N, int H, int W, int Ho,
                                                             int Wo) {
+  pdl_sync();
   __shared__ float sw[27][64];
   __shared__ float bsum[64], bsq[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __res
                                                               const __nv_bfloat16* __restrict__ dy,
                                                               float* __restrict__ dw, int N, int H, int W, int Ho, int Wo,
                                                               int pix_per_block) {
+  pdl_sync();
   __shared__ __nv_bfloat16 s_dy[64][64];
   __shared__ float s_x[64][28];
   const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
@@ -215,6 +220,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
                                    float* running_mean, float* running_var, float* tmp_mean, float* tmp_var,
                                    float* running_iter, float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                    float* __restrict__ scale, float* __restrict__ shift, int C) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float mean, inv_std;
@@ -251,6 +257,7 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
   shift[c] = b - mean * g * inv_std;
 }
 __global__ void bn_iter_update_kernel(float* running_iter, float momentum) {
+  pdl_sync();
   running_iter[0] = running_iter[0] * (1.f - momentum) + 1.f;
 }
 
@@ -293,6 +300,7 @@ struct BnApplyParams {
   int C, relu, cgb, rows;
 };
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const BnApplyParams p) {
+  pdl_sync();
   const int tcol = threadIdx.x % p.cgb, trow = threadIdx.x / p.cgb;
   const int cgrp = blockIdx.y * p.cgb + tcol;
   if (cgrp >= (p.C >> 3)) return;
@@ -368,6 +376,7 @@ struct BnBwdParams {
 
 template <bool kApply>
 __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
+  pdl_sync();
   __shared__ float red[kApply ? 1 : 2][kApply ? 1 : 256][8];
   const int tcol = threadIdx.x % p.cgb, trow = threadIdx.x / p.cgb;
   const int cgrp = blockIdx.y * p.cgb + tcol;
@@ -467,6 +476,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
 // is kept in one byte per output element for the backward gather.
 __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                    uint8_t* __restrict__ idx, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_sync();
   const int cg = C >> 3;
   const long total = (long)N * Ho * Wo * cg;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -508,6 +518,7 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
 
 __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ idx,
                                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int Ho, int Wo) {
+  pdl_sync();
   const int cg = C >> 3;
   const long total = (long)N * H * W * cg;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -548,6 +559,7 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_ld,
                                                           __nv_bfloat16* __restrict__ out, int N, int H, int W, int C,
                                                           int S) {
+  pdl_sync();
   // grid: (N*S*S bins, ceil(C/64)); block = 8 channel groups (64 channels) x 32 pixel lanes striding over the bin
   __shared__ float red[32][8][8];
   const int tcg = threadIdx.x & 7, lane = threadIdx.x >> 3;
@@ -600,6 +612,7 @@ struct AvgPoolBwdParams {
   int N, H, W, C;
 };
 __global__ void avgpool_bwd_kernel(const AvgPoolBwdParams p) {
+  pdl_sync();
   const int cg = p.C >> 3;
   const long total = (long)p.N * p.H * p.W * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -653,6 +666,7 @@ __device__ __forceinline__ void bilinear_coeff(int dst, int in, int out, int& i0
 
 __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_ld, int N, int Hi, int Wi, int C,
                                     __nv_bfloat16* __restrict__ out, long out_ld, int Ho, int Wo) {
+  pdl_sync();
   const int cg = C >> 3;
   const long total = (long)N * Ho * Wo * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -690,6 +704,7 @@ __device__ __forceinline__ void bilinear_src_window(int i, int in, int out, int&
 
 __global__ void bilinear_bwd_w_kernel(const __nv_bfloat16* __restrict__ dout, long dout_ld, int N, int Ho, int Wo, int C,
                                       float* __restrict__ tmp, int Wi) {
+  pdl_sync();
   const int cg = C >> 3;
   const long total = (long)N * Ho * Wi * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -725,6 +740,7 @@ __global__ void bilinear_bwd_w_kernel(const __nv_bfloat16* __restrict__ dout, lo
 
 __global__ void bilinear_bwd_h_kernel(const float* __restrict__ tmp, int N, int Ho, int C, __nv_bfloat16* __restrict__ dx,
                                       long dx_ld, int Hi, int Wi, int accumulate) {
+  pdl_sync();
   const int cg = C >> 3;
   const long total = (long)N * Hi * Wi * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -771,6 +787,7 @@ __global__ void bilinear_bwd_h_kernel(const float* __restrict__ tmp, int N, int 
 __global__ void __launch_bounds__(256) softmax_nll_fwd_kernel(const float* __restrict__ logits, long ld, int C,
                                                               const long long* __restrict__ label, long P,
                                                               float* __restrict__ lse, float* __restrict__ accum) {
+  pdl_sync();
   __shared__ float bl[8], bc[8], ba[8];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float loss = 0.f, cnt = 0.f, correct = 0.f;
@@ -814,6 +831,7 @@ __global__ void __launch_bounds__(256) softmax_nll_fwd_kernel(const float* __res
 
 // loss = main/cnt + ds_scale * ds/cnt ; acc = correct/(cnt + 1e-10)   (models/models.py:37-42, :12-18)
 __global__ void nll_finalize_kernel(const float* accum_main, const float* accum_ds, float ds_scale, float* out) {
+  pdl_sync();
   float loss = accum_main[0] / accum_main[1];
   if (accum_ds) loss += ds_scale * accum_ds[0] / accum_ds[1];
   out[0] = loss;
@@ -826,6 +844,7 @@ __global__ void __launch_bounds__(256) softmax_nll_bwd_kernel(const float* __res
                                                               const float* __restrict__ lse, const float* __restrict__ accum,
                                                               float weight, long P, __nv_bfloat16* __restrict__ dlogits,
                                                               long ld_out, int c_store) {
+  pdl_sync();
   const float coef = weight / accum[1];
   const long total = P * c_store;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -845,6 +864,7 @@ __global__ void __launch_bounds__(256) softmax_nll_bwd_kernel(const float* __res
 // column sums of a bf16 [P][ld] matrix into fp32[C] (+=): bias gradients.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, long ld, long P, int C,
                                                      float* __restrict__ out) {
+  pdl_sync();
   // block handles a slab of rows; thread t handles columns t, t+256, ...
   const long rows_per_block = (P + gridDim.x - 1) / gridDim.x;
   const long r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, P);
@@ -860,6 +880,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) upsample_softmax_kernel(const float* __restrict__ logits, long ld, int N, int Hi,
                                                                int Wi, int C, float* __restrict__ probs, int Ho, int Wo,
                                                                float weight, int accumulate) {
+  pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long P = (long)N * Ho * Wo;
   for (long p = (long)blockIdx.x * 8 + warp; p < P; p += (long)gridDim.x * 8) {
@@ -911,6 +932,7 @@ __global__ void __launch_bounds__(256) upsample_softmax_kernel(const float* __re
 // layout conversion NHWC bf16 -> NCHW fp32 (feature maps handed back through the module-level API)
 __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, long ld, int N, int H, int W, int C,
                                              float* __restrict__ out) {
+  pdl_sync();
   __shared__ float tile[32][33];
   // grid: (ceil(HW/32), ceil(C/32), N); block (32, 8)
   const int n = blockIdx.z;
@@ -931,6 +953,7 @@ __global__ void nhwc_bf16_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x
 }
 __global__ void nchw_f32_to_nhwc_bf16_kernel(const float* __restrict__ x, int N, int H, int W, int C,
                                              __nv_bfloat16* __restrict__ out, long ld) {
+  pdl_sync();
   __shared__ float tile[32][33];
   const int n = blockIdx.z;
   const long HW = (long)H * W;
@@ -964,7 +987,7 @@ int sseg_prep_conv_weight(const float* w_oihw, int O, int I, int T, void* w_fwd,
   SSEG_REQUIRE(!w_fwd || fwd_ld >= (long)T * I, "sseg_prep_conv_weight: fwd_ld too small");
   SSEG_REQUIRE(!w_dgrad || (o_pad >= O && dgrad_ld >= (long)T * o_pad), "sseg_prep_conv_weight: dgrad_ld too small");
   const long total = (long)O * I * T;
-  prep_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)st>>>(
+  launch_k(prep_weight_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)st, 
       w_oihw, O, I, T, (__nv_bfloat16*)w_fwd, fwd_ld, (__nv_bfloat16*)w_dgrad, dgrad_ld, o_pad);
   LAUNCH_CHECK("prep_weight_kernel");
 }
@@ -973,7 +996,7 @@ int sseg_grad_to_oihw(const float* g, long g_ld, int O, int I, int T, float* out
                       sseg_stream_t st) {
   SSEG_REQUIRE(g && out, "sseg_grad_to_oihw: null argument");
   const long total = (long)O * I * T;
-  grad_to_oihw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)st>>>(g, g_ld, O, I, T, out, scale, accumulate);
+  launch_k(grad_to_oihw_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)st, g, g_ld, O, I, T, out, scale, accumulate);
   LAUNCH_CHECK("grad_to_oihw_kernel");
 }
 
@@ -982,7 +1005,7 @@ int sseg_stem_conv_fwd(const float* img, int N, int H, int W, const float* w, vo
   SSEG_REQUIRE(img && w && out, "sseg_stem_conv_fwd: null argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long P = (long)N * Ho * Wo;
-  stem_conv_fwd_kernel<<<(int)((P + 127) / 128), 128, 0, (cudaStream_t)st>>>(img, w, (__nv_bfloat16*)out, stat_sum,
+  launch_k(stem_conv_fwd_kernel, dim3((int)((P + 127) / 128)), dim3(128), 0, (cudaStream_t)st, img, w, (__nv_bfloat16*)out, stat_sum,
                                                                              stat_sqsum, N, H, W, Ho, Wo);
   LAUNCH_CHECK("stem_conv_fwd_kernel");
 }
@@ -992,7 +1015,7 @@ int sseg_stem_conv_wgrad(const float* img, int N, int H, int W, const void* dy, 
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long P = (long)N * Ho * Wo;
   const int ppb = 256;
-  stem_conv_wgrad_kernel<<<(int)((P + ppb - 1) / ppb), 256, 0, (cudaStream_t)st>>>(img, (const __nv_bfloat16*)dy, dw, N,
+  launch_k(stem_conv_wgrad_kernel, dim3((int)((P + ppb - 1) / ppb)), dim3(256), 0, (cudaStream_t)st, img, (const __nv_bfloat16*)dy, dw, N,
                                                                                    H, W, Ho, Wo, ppb);
   LAUNCH_CHECK("stem_conv_wgrad_kernel");
 }
@@ -1006,12 +1029,12 @@ int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_de
   SSEG_REQUIRE(mode != 2 || (running_mean && running_var), "sseg_bn_finalize: running statistics required in eval mode");
   SSEG_REQUIRE(!(update_running && mode == 1) || (tmp_mean && tmp_var && running_iter && running_mean && running_var),
                "sseg_bn_finalize: sync-mode running buffers required");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)st>>>(
+  launch_k(bn_finalize_kernel, dim3((C + 127) / 128), dim3(128), 0, (cudaStream_t)st, 
       sum, sqsum, count_dev, count_host, gamma, beta, eps, momentum, mode, update_running, running_mean, running_var,
       tmp_mean, tmp_var, running_iter, mean_out, invstd_out, scale, shift, C);
   count_launch(1);
   if (update_running && mode == 1) {
-    bn_iter_update_kernel<<<1, 1, 0, (cudaStream_t)st>>>(running_iter, momentum);
+    launch_k(bn_iter_update_kernel, dim3(1), dim3(1), 0, (cudaStream_t)st, running_iter, momentum);
     count_launch(1);
   }
   return check_cuda(cudaGetLastError(), "bn_finalize_kernel");
@@ -1025,7 +1048,7 @@ int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shi
   const BnTiling t = bn_tiling(P, C);
   BnApplyParams p{(const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, rscale, rshift,
                   chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu, t.cgb, t.rows};
-  bn_apply_kernel<<<dim3(t.gx, t.gy), 256, 0, (cudaStream_t)st>>>(p);
+  launch_k(bn_apply_kernel, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("bn_apply_kernel");
 }
 
@@ -1053,7 +1076,7 @@ int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const
                     nullptr, 0, P, pix_per_img, C, 0, &t, true);
   if (rc) return rc;
   SSEG_REQUIRE(y && mean && invstd && s1 && s2, "sseg_bn_bwd_reduce: null argument");
-  bn_bwd_kernel<false><<<dim3(t.gx, t.gy), 256, 0, (cudaStream_t)st>>>(p);
+  launch_k(bn_bwd_kernel<false>, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("bn_bwd_reduce_kernel");
 }
 
@@ -1069,14 +1092,14 @@ int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const 
   if (rc) return rc;
   SSEG_REQUIRE(dy && scale && dy_ld % 8 == 0 && (!dres || dres_ld % 8 == 0), "sseg_bn_bwd_apply: bad argument");
   SSEG_REQUIRE(eval_mode || (y && mean && invstd && s1 && s2), "sseg_bn_bwd_apply: training mode needs y/mean/invstd/s1/s2");
-  bn_bwd_kernel<true><<<dim3(t.gx, t.gy), 256, 0, (cudaStream_t)st>>>(p);
+  launch_k(bn_bwd_kernel<true>, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("bn_bwd_apply_kernel");
 }
 
 int sseg_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, void* idx, sseg_stream_t st) {
   SSEG_REQUIRE(x && out && C % 8 == 0, "sseg_maxpool_fwd: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool_fwd_kernel<<<grid_for((long)N * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(
+  launch_k(maxpool_fwd_kernel, dim3(grid_for((long)N * Ho * Wo * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st, 
       (const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint8_t*)idx, N, H, W, C, Ho, Wo);
   LAUNCH_CHECK("maxpool_fwd_kernel");
 }
@@ -1084,7 +1107,7 @@ int sseg_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, void*
 int sseg_maxpool_bwd(const void* dout, const void* idx, void* dx, int N, int H, int W, int C, sseg_stream_t st) {
   SSEG_REQUIRE(dout && idx && dx && C % 8 == 0, "sseg_maxpool_bwd: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  maxpool_bwd_kernel<<<grid_for((long)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(
+  launch_k(maxpool_bwd_kernel, dim3(grid_for((long)N * H * W * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st, 
       (const __nv_bfloat16*)dout, (const uint8_t*)idx, (__nv_bfloat16*)dx, N, H, W, C, Ho, Wo);
   LAUNCH_CHECK("maxpool_bwd_kernel");
 }
@@ -1092,7 +1115,7 @@ int sseg_maxpool_bwd(const void* dout, const void* idx, void* dx, int N, int H, 
 int sseg_avgpool_fwd(const void* x, long x_ld, int N, int H, int W, int C, int S, void* out, sseg_stream_t st) {
   SSEG_REQUIRE(x && out && C % 8 == 0 && x_ld % 8 == 0 && S >= 1, "sseg_avgpool_fwd: bad argument");
   dim3 grid(N * S * S, (C / 8 + 7) / 8);
-  avgpool_fwd_kernel<<<grid, 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)out, N, H, W, C, S);
+  launch_k(avgpool_fwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st, (const __nv_bfloat16*)x, x_ld, (__nv_bfloat16*)out, N, H, W, C, S);
   LAUNCH_CHECK("avgpool_fwd_kernel");
 }
 
@@ -1105,14 +1128,14 @@ int sseg_avgpool_bwd(const void* base, long base_ld, const void* const* dpool, c
   p.base = (const __nv_bfloat16*)base, p.base_ld = base_ld;
   for (int k = 0; k < nscales; ++k) p.dpool[k] = (const __nv_bfloat16*)dpool[k], p.scales[k] = scales[k];
   p.nscales = nscales, p.dx = (__nv_bfloat16*)dx, p.dx_ld = dx_ld, p.N = N, p.H = H, p.W = W, p.C = C;
-  avgpool_bwd_kernel<<<grid_for((long)N * H * W * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(p);
+  launch_k(avgpool_bwd_kernel, dim3(grid_for((long)N * H * W * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("avgpool_bwd_kernel");
 }
 
 int sseg_bilinear_fwd(const void* x, long x_ld, int N, int Hi, int Wi, int C, void* out, long out_ld, int Ho, int Wo,
                       sseg_stream_t st) {
   SSEG_REQUIRE(x && out && C % 8 == 0 && x_ld % 8 == 0 && out_ld % 8 == 0, "sseg_bilinear_fwd: bad argument");
-  bilinear_fwd_kernel<<<grid_for((long)N * Ho * Wo * (C / 8), 256), 256, 0, (cudaStream_t)st>>>(
+  launch_k(bilinear_fwd_kernel, dim3(grid_for((long)N * Ho * Wo * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st, 
       (const __nv_bfloat16*)x, x_ld, N, Hi, Wi, C, (__nv_bfloat16*)out, out_ld, Ho, Wo);
   LAUNCH_CHECK("bilinear_fwd_kernel");
 }
@@ -1122,9 +1145,9 @@ int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int
   SSEG_REQUIRE(dout && dx && scratch && C % 8 == 0 && dout_ld % 8 == 0 && dx_ld % 8 == 0,
                "sseg_bilinear_bwd: bad argument (scratch = float[N*Ho*Wi*C] required)");
   SSEG_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "sseg_bilinear_bwd: scratch not 16B aligned");
-  bilinear_bwd_w_kernel<<<grid_for((long)N * Ho * Wi * (C / 8), 128), 128, 0, (cudaStream_t)st>>>(
+  launch_k(bilinear_bwd_w_kernel, dim3(grid_for((long)N * Ho * Wi * (C / 8), 128)), dim3(128), 0, (cudaStream_t)st, 
       (const __nv_bfloat16*)dout, dout_ld, N, Ho, Wo, C, scratch, Wi);
-  bilinear_bwd_h_kernel<<<grid_for((long)N * Hi * Wi * (C / 8), 128), 128, 0, (cudaStream_t)st>>>(
+  launch_k(bilinear_bwd_h_kernel, dim3(grid_for((long)N * Hi * Wi * (C / 8), 128)), dim3(128), 0, (cudaStream_t)st, 
       scratch, N, Ho, C, (__nv_bfloat16*)dx, dx_ld, Hi, Wi, accumulate);
   count_launch(2);
   return check_cuda(cudaGetLastError(), "bilinear_bwd kernels");
@@ -1133,13 +1156,13 @@ int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int
 int sseg_softmax_nll_fwd(const float* logits, long ld, int C, const long long* label, long P, float* lse, float* accum,
                          sseg_stream_t st) {
   SSEG_REQUIRE(logits && label && lse && accum && C >= 1, "sseg_softmax_nll_fwd: bad argument");
-  softmax_nll_fwd_kernel<<<grid_for(P, 8, 148 * 8), 256, 0, (cudaStream_t)st>>>(logits, ld, C, label, P, lse, accum);
+  launch_k(softmax_nll_fwd_kernel, dim3(grid_for(P, 8, 148 * 8)), dim3(256), 0, (cudaStream_t)st, logits, ld, C, label, P, lse, accum);
   LAUNCH_CHECK("softmax_nll_fwd_kernel");
 }
 
 int sseg_nll_finalize(const float* accum_main, const float* accum_ds, float ds_scale, float* out, sseg_stream_t st) {
   SSEG_REQUIRE(accum_main && out, "sseg_nll_finalize: bad argument");
-  nll_finalize_kernel<<<1, 1, 0, (cudaStream_t)st>>>(accum_main, accum_ds, ds_scale, out);
+  launch_k(nll_finalize_kernel, dim3(1), dim3(1), 0, (cudaStream_t)st, accum_main, accum_ds, ds_scale, out);
   LAUNCH_CHECK("nll_finalize_kernel");
 }
 
@@ -1147,21 +1170,21 @@ int sseg_softmax_nll_bwd(const float* logits, long ld, int C, const long long* l
                          float weight, long P, void* dlogits, long ld_out, int c_store, sseg_stream_t st) {
   SSEG_REQUIRE(logits && label && lse && accum && dlogits && c_store >= C && c_store <= ld_out,
                "sseg_softmax_nll_bwd: bad argument");
-  softmax_nll_bwd_kernel<<<grid_for(P * c_store, 256), 256, 0, (cudaStream_t)st>>>(
+  launch_k(softmax_nll_bwd_kernel, dim3(grid_for(P * c_store, 256)), dim3(256), 0, (cudaStream_t)st, 
       logits, ld, C, label, lse, accum, weight, P, (__nv_bfloat16*)dlogits, ld_out, c_store);
   LAUNCH_CHECK("softmax_nll_bwd_kernel");
 }
 
 int sseg_colsum(const void* x, long ld, long P, int C, float* out, sseg_stream_t st) {
   SSEG_REQUIRE(x && out, "sseg_colsum: bad argument");
-  colsum_kernel<<<grid_for(P, 64, 148 * 2), 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, ld, P, C, out);
+  launch_k(colsum_kernel, dim3(grid_for(P, 64, 148 * 2)), dim3(256), 0, (cudaStream_t)st, (const __nv_bfloat16*)x, ld, P, C, out);
   LAUNCH_CHECK("colsum_kernel");
 }
 
 int sseg_upsample_softmax(const float* logits, long ld, int N, int Hi, int Wi, int C, float* probs, int Ho, int Wo,
                           float weight, int accumulate, sseg_stream_t st) {
   SSEG_REQUIRE(logits && probs && C >= 1 && C <= 256, "sseg_upsample_softmax: bad argument (C <= 256)");
-  upsample_softmax_kernel<<<grid_for((long)N * Ho * Wo, 8, 148 * 16), 256, 0, (cudaStream_t)st>>>(
+  launch_k(upsample_softmax_kernel, dim3(grid_for((long)N * Ho * Wo, 8, 148 * 16)), dim3(256), 0, (cudaStream_t)st, 
       logits, ld, N, Hi, Wi, C, probs, Ho, Wo, weight, accumulate);
   LAUNCH_CHECK("upsample_softmax_kernel");
 }
@@ -1169,14 +1192,14 @@ int sseg_upsample_softmax(const float* logits, long ld, int N, int Hi, int Wi, i
 int sseg_nhwc_bf16_to_nchw_f32(const void* x, long ld, int N, int H, int W, int C, float* out, sseg_stream_t st) {
   SSEG_REQUIRE(x && out, "sseg_nhwc_bf16_to_nchw_f32: bad argument");
   dim3 grid((unsigned)(((long)H * W + 31) / 32), (C + 31) / 32, N), block(32, 8);
-  nhwc_bf16_to_nchw_f32_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, ld, N, H, W, C, out);
+  launch_k(nhwc_bf16_to_nchw_f32_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)st, (const __nv_bfloat16*)x, ld, N, H, W, C, out);
   LAUNCH_CHECK("nhwc_bf16_to_nchw_f32_kernel");
 }
 
 int sseg_nchw_f32_to_nhwc_bf16(const float* x, int N, int H, int W, int C, void* out, long ld, sseg_stream_t st) {
   SSEG_REQUIRE(x && out, "sseg_nchw_f32_to_nhwc_bf16: bad argument");
   dim3 grid((unsigned)(((long)H * W + 31) / 32), (C + 31) / 32, N), block(32, 8);
-  nchw_f32_to_nhwc_bf16_kernel<<<grid, block, 0, (cudaStream_t)st>>>(x, N, H, W, C, (__nv_bfloat16*)out, ld);
+  launch_k(nchw_f32_to_nhwc_bf16_kernel, dim3(grid), dim3(block), 0, (cudaStream_t)st, x, N, H, W, C, (__nv_bfloat16*)out, ld);
   LAUNCH_CHECK("nchw_f32_to_nhwc_bf16_kernel");
 }
 

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -266,9 +267,9 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
                                    L::kDynBytes));
     configured[dev] = true;
   }
-  igemm_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kDynBytes, stream>>>(p);
   count_launch(1);
-  return check_cuda(cudaGetLastError(), "igemm_kernel launch");
+  return check_cuda(launch_k(igemm_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, p),
+                    "igemm_kernel launch");
 }
 
 // Fills the geometry-derived part of the parameters shared by the forward and weight-gradient kernels.
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -580,9 +582,9 @@ static int launch_wgrad(const WgradParams& p, int grid, cudaStream_t stream) {
                                    L::kDynBytes));
     configured[dev] = true;
   }
-  wgrad_kernel<BLOCK_N, STAGES><<<grid, kNumThreads, L::kDynBytes, stream>>>(p);
   count_launch(1);
-  return check_cuda(cudaGetLastError(), "wgrad_kernel launch");
+  return check_cuda(launch_k(wgrad_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, p),
+                    "wgrad_kernel launch");
 }
 
 }  // namespace sseg

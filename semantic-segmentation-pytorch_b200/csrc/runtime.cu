@@ -1,5 +1,6 @@
 // Library runtime: error reporting, launch accounting, TMA tensor-map factory + cache.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -27,6 +28,15 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("SSEG_PDL");
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl == 1;
+}
 
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -137,4 +147,6 @@ const char* sseg_last_error(void) { return sseg::g_err; }
 int sseg_version(void) { return 100; }
 long sseg_launch_count(void) { return sseg::g_launches; }
 void sseg_launch_count_reset(void) { sseg::g_launches = 0; }
+void sseg_set_pdl(int enable) { sseg::g_pdl = enable ? 1 : 0; }
+int sseg_get_pdl(void) { return sseg::pdl_enabled() ? 1 : 0; }
 }

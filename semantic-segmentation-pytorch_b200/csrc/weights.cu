@@ -4,6 +4,7 @@
 // Each CTA owns a 32(o) x 32(i) x T tile, staged through shared memory so that global reads AND writes are coalesced
 // in both layouts. The per-conv descriptors live in a device table built once by the caller.
 #include "common.h"
+#include "ptx.cuh"
 #include <cuda_bf16.h>
 
 namespace sseg {
@@ -22,6 +23,7 @@ __device__ __forceinline__ const sseg_weight_desc_t* find_desc(const sseg_weight
 
 __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_desc_t* __restrict__ table, int n,
                                                               int mode, float scale) {
+  pdl_sync();
   __shared__ float tile[kTile][kTile * kMaxT + 1];
   int local;
   const sseg_weight_desc_t* d = find_desc(table, n, blockIdx.x, local);
@@ -78,7 +80,7 @@ using namespace sseg;
 static int launch_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, int mode, float scale,
                           cudaStream_t st, const char* who) {
   SSEG_REQUIRE(table_dev != nullptr && n >= 1 && total_tiles >= 1, "%s: bad argument", who);
-  weights_batched_kernel<<<total_tiles, 256, 0, st>>>(table_dev, n, mode, scale);
+  launch_k(weights_batched_kernel, dim3(total_tiles), dim3(256), 0, st, table_dev, n, mode, scale);
   count_launch(1);
   return check_cuda(cudaGetLastError(), who);
 }
