@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(256) softmax_nll_fwd_kernel(const float* __res
     if (lane == 0) {
       lse[p] = l;
       const long long lab = label[p];
-      if (lab >= 0) {
+      if (lab >= 0 && lab < C) {  // labels >= C would be an error in the reference; never index out of bounds
         loss += l - row[lab];
         cnt += 1.f;
         if (am == (int)lab) correct += 1.f;
@@ -852,7 +852,7 @@ __global__ void __launch_bounds__(256) softmax_nll_bwd_kernel(const float* __res
     const long p = idx / c_store;
     float v = 0.f;
     const long long lab = label[p];
-    if (c < C && lab >= 0) {
+    if (c < C && lab >= 0 && lab < C) {
       v = __expf(logits[p * ld + c] - lse[p]);
       if (c == (int)lab) v -= 1.f;
       v *= coef;

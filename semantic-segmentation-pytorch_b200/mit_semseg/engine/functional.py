@@ -17,7 +17,7 @@ def _programs(mod):
     return cache
 
 
-def get_program(seg, img_shape, seg_size=None, with_grad=None, dropout_masks=None, capture=None):
+def get_program(seg, img_shape, seg_size=None, with_grad=None, dropout_masks=None, capture=None, inputs=None):
     if with_grad is None:
         with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in seg.parameters())
     bn_flags = tuple(m.training for m in seg.modules())
@@ -27,6 +27,8 @@ def get_program(seg, img_shape, seg_size=None, with_grad=None, dropout_masks=Non
     if prog is None:
         prog = SegProgram(seg, tuple(img_shape), training=seg.training, with_grad=with_grad, seg_size=seg_size,
                           dropout_masks=dropout_masks)
+        if inputs is not None:
+            prog.load_inputs(*inputs)  # the capture warm-up runs the step: give it real data, not uninitialised memory
         if capture if capture is not None else (seg_size is None):
             prog.capture()  # fixed-shape training steps are replayed as one CUDA graph
         cache[key] = prog
@@ -65,7 +67,7 @@ def segmentation_train_step(seg, img, label):
     """SegmentationModule.forward, training branch (reference models/models.py:31-43) -> (loss, acc)."""
     if not img.is_cuda:
         raise RuntimeError("the B200 engine has no CPU path: move the module and the batch to a CUDA device")
-    prog = get_program(seg, img.shape)
+    prog = get_program(seg, img.shape, inputs=(img, label))
     prog.load_inputs(img, label)
     if prog.with_grad:
         params = [p for p in seg.parameters() if p.requires_grad]

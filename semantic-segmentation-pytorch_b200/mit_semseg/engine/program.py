@@ -99,7 +99,7 @@ class SegProgram:
             elif isinstance(m, _BatchNorm):
                 self.bns[id(m)] = BNS(m)
         self._alloc_params()
-        self.img = torch.empty(img_shape, device=self.dev, dtype=torch.float32)
+        self.img = torch.zeros(img_shape, device=self.dev, dtype=torch.float32)
         self._build_forward()
         if self.with_grad:
             self._build_backward()
@@ -280,7 +280,7 @@ class SegProgram:
                                                          self.probs))
         else:
             n, h, w, _ = self.logits.shape
-            self.label = torch.empty(n, h, w, device=self.dev, dtype=torch.int64)
+            self.label = torch.full((n, h, w), -1, device=self.dev, dtype=torch.int64)
             loss = LossRec(self)
             self.records.append(loss)
 
