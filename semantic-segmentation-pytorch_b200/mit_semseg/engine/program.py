@@ -361,6 +361,10 @@ class SegProgram:
 
     def capture(self):
         """Capture the whole step into one CUDA graph (after a warm-up run on a side stream)."""
+        # the warm-up executes the step: keep it side-effect free on the module (BN running statistics)
+        bufs = [b for m in list(self.enc.modules()) + list(self.dec.modules()) if isinstance(m, _BatchNorm)
+                for b in m.buffers(recurse=False)]
+        saved = [b.clone() for b in bufs]
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(s):
@@ -368,6 +372,8 @@ class SegProgram:
             self.run_eager()
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
+        for b, v in zip(bufs, saved):
+            b.copy_(v)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.run_eager()
