@@ -87,7 +87,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -259,7 +259,6 @@ def conv_roofline(prog, world):
     gradient, weight gradient); achieved = their algorithmic FLOPs / their summed durations."""
     from mit_semseg.engine import ops
     sustained, burst, which = measured_peaks()
-    stream = torch.cuda.current_stream()
     records = []
     orig_igemm, orig_wgrad = ops.conv_igemm, ops.conv_wgrad
 
@@ -270,6 +269,7 @@ def conv_roofline(prog, world):
         return 2.0 * n * h * w * cout * k
 
     def timed(kind, fn, fl):
+        stream = torch.cuda.current_stream()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         fn()
@@ -287,13 +287,19 @@ def conv_roofline(prog, world):
         return dw
 
     ops.conv_igemm, ops.conv_wgrad = igemm, wgrad
+    prog.serial = True  # weight gradients inline on the main stream: one kernel at a time between each event pair
     try:
+        stream = torch.cuda.current_stream()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # keep the GPU busy for ~40 ms first so the whole eager pass is queued ahead of execution: the event pairs then
+        # bracket kernel execution only, not CPU launch latency
+        torch.cuda._sleep(int(0.04 * 1.9e9))
         t0.record(stream)
         prog.run_eager()
         t1.record(stream)
         torch.cuda.synchronize()
     finally:
+        prog.serial = False
         ops.conv_igemm, ops.conv_wgrad = orig_igemm, orig_wgrad
     tot = {"igemm": [0.0, 0.0, 0], "wgrad": [0.0, 0.0, 0]}
     for kind, a, b, fl in records:
@@ -314,6 +320,12 @@ def conv_roofline(prog, world):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_threads():
+    """oneDNN convolutions scale poorly past ~32 threads on many-core hosts (128-thread runs were 3x slower on the
+    B200 box); use every core up to 32."""
+    return max(1, min(os.cpu_count() or 1, 32))
+
+
 def oracle_train_setup(n, crop, threads):
     from oracle import segnet_oracle as O
     torch.set_num_threads(threads)
@@ -343,7 +355,7 @@ def oracle_train_setup(n, crop, threads):
 def cpu_baseline(max_seconds=25.0):
     """The reference's CPU path (oracle port: same torch-CPU ops in the reference's order) on this box's host cores:
     bounded sample = one warm-up + up to 3 training steps of the same 2x3x512x512 batch."""
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     step, fwd_only = oracle_train_setup(BATCH, CROP, cores)
     t0 = time.perf_counter()
     step()
@@ -367,7 +379,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     n, crop = BATCH, CROP
     step, _ = oracle_train_setup(n, crop, cores)
     t0 = time.perf_counter()
@@ -393,10 +405,11 @@ def run_reference(args):
            "config": {"workload": "configs[2]: ResNet50dilated+PPM_deepsup train step (fwd+bwd+SGD) on the host CPU, "
                                   "%d x 3x%dx%d per step" % (n, crop, crop), "global_batch": n, "parallelism": "cpu"},
            "cpu_baseline": {"value": round(value, 4), "unit": "images/s", "cores": cores, "kind": "port",
-                            "sample": "%d steps of %dx3x%dx%d, all %d host threads; the reference is pure Python over "
+                            "sample": "%d steps of %dx3x%dx%d, %d host threads (of %d logical CPUs); the reference is pure Python over "
                                       "torch CPU ops and cannot travel to the box, so the oracle port (same ops, same "
                                       "order, bit-identical in the build container) stands in" % (args.steps, n, crop,
-                                                                                                   crop, cores)},
+                                                                                                   crop, cores,
+                                                                                                   os.cpu_count() or 1)},
            "e2e": {"value": round(value, 4), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "loss_last": round(last, 5)}
     print(json.dumps(out))
@@ -405,7 +418,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -328,6 +328,8 @@ class SegProgram:
     def on_side(self, fn):
         """Closure that runs `fn` on the side stream, ordered after everything enqueued so far on the main stream."""
         def run():
+            if getattr(self, "serial", False):
+                return fn()
             main = torch.cuda.current_stream(self.dev)
             ev = torch.cuda.Event()
             ev.record(main)
