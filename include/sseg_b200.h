@@ -56,7 +56,7 @@ long sseg_launch_count(void);
 void sseg_launch_count_reset(void);
 /* Programmatic dependent launch: when enabled every kernel is launched with
  * cudaLaunchAttributeProgrammaticStreamSerialization, so the prologue of kernel N+1 (barrier init, TMEM allocation,
- * descriptor prefetch, coefficient loads) overlaps the tail of kernel N. Default: the SSEG_PDL environment variable. */
+ * descriptor prefetch, coefficient loads) overlaps the tail of kernel N. Default: on (SSEG_PDL=0 disables). */
 void sseg_set_pdl(int enable);
 int sseg_get_pdl(void);
 
@@ -93,9 +93,9 @@ typedef struct {
  *            (out->c multiple of 8, cout <= out->c <= out->ld; channels >= cout receive 0).
  * bias     : optional float[cout]
  * addend   : optional bf16 NHWC view (c >= out->c) added before the store (may alias out)
- * stat_sum / stat_sqsum : optional float[cout]; per-channel sum and sum of squares of the fp32
- *            results are ATOMICALLY ADDED (caller zeroes them) - the first half of
- *            SynchronizedBatchNorm2d.forward (lib/nn/modules/batchnorm.py:68-70).
+ * stat_sum / stat_sqsum : optional float[cout] (bf16 outputs only); per-channel sum and sum of squares of the
+ *            results AS STORED (bf16-rounded, accumulated in fp32) are ATOMICALLY ADDED (caller zeroes them) - the
+ *            first half of SynchronizedBatchNorm2d.forward (lib/nn/modules/batchnorm.py:68-70).
  */
 int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
                     int out_f32, const float* bias, const sseg_act_t* addend, float* stat_sum, float* stat_sqsum,

@@ -44,8 +44,8 @@ int get_tmap_2d(CUtensorMap* out, const void* ptr, int elem_bytes, long rows, lo
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
-// Kernel launch with the programmatic-stream-serialization attribute (PDL) when enabled (SSEG_PDL=1 in the environment
-// or sseg_set_pdl(1)); otherwise a plain launch.
+// Kernel launch with the programmatic-stream-serialization attribute (PDL) unless disabled (SSEG_PDL=0 in the
+// environment or sseg_set_pdl(0)); then a plain launch.
 bool pdl_enabled();
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,

@@ -63,8 +63,6 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_sum = reinterpret_cast<float*>(smem + L::kStatOff);
-  float* s_sq = s_sum + BLOCK_N;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -87,7 +85,6 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
     mbar_init(tmem_full_bar, 1);
     fence_barrier_init();
   }
-  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kNumThreads) s_sum[i] = 0.f;
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
     tma_prefetch_desc(&p.tmB);
@@ -158,6 +155,11 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
 
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    // bf16 outputs are staged through shared memory (the pipeline stages are idle once the accumulator is complete):
+    // rows are then stored with full 16-byte-per-lane coalescing and the per-channel statistics are column sums of the
+    // staged (bf16-rounded = as stored) tile. fp32 outputs (classifier logits) are written straight from registers.
+    constexpr int kPitch = BLOCK_N * 2 + 16;  // +16 B: consecutive rows start in different 16-byte bank groups
+    uint8_t* stg = smem;
 #pragma unroll 1
     for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
       uint32_t raw[32];
@@ -188,61 +190,61 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
           }
         }
       }
-      if (valid) {
-        if (p.out_f32) {
+      if (p.out_f32) {
+        if (valid) {
           float* op = reinterpret_cast<float*>(p.out) + out_off + col0;
 #pragma unroll
           for (int g = 0; g < 8; ++g)
             if (col0 + g * 4 < p.n_store)
               *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + out_off + col0;
+        }
+      } else {
+        uint8_t* sp = stg + row * kPitch + chunk * 64;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            if (col0 + g * 8 < p.n_store) {
-              uint4 q;
-              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+        for (int g = 0; g < 4; ++g) {
+          uint4 q = make_uint4(0u, 0u, 0u, 0u);  // rows outside the image contribute zeros to the statistics
+          if (valid) {
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
-              *reinterpret_cast<uint4*>(op + g * 8) = q;
-            }
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
           }
+          *reinterpret_cast<uint4*>(sp + g * 16) = q;
         }
-      }
-      if (do_stats) {
-        // Column sums over the warp's 32 rows by a transposing butterfly: after the loop lane l holds column l.
-        float s[32], q[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          // statistics of the values as STORED (bf16-rounded): mean/var then describe exactly the tensor that
-          // gets normalised, so sum(xhat) = 0 holds to fp32 accuracy even when inv_std is large (tiny batches)
-          const float r = p.out_f32 ? v[j] : __bfloat162float(__float2bfloat16(v[j]));
-          s[j] = valid ? r : 0.f;
-          q[j] = s[j] * s[j];
-        }
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int j = 0; j < off; ++j) {
-            const float send_s = upper ? s[j] : s[j + off];
-            const float keep_s = upper ? s[j + off] : s[j];
-            s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, off);
-            const float send_q = upper ? q[j] : q[j + off];
-            const float keep_q = upper ? q[j + off] : q[j];
-            q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, off);
-          }
-        }
-        atomicAdd(&s_sum[chunk * 32 + lane], s[0]);
-        atomicAdd(&s_sq[chunk * 32 + lane], q[0]);
       }
     }
-    if (do_stats) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only
-      for (int c = threadIdx.x - 64; c < BLOCK_N; c += 128) {
-        if (n0 + c < p.cout) {
-          atomicAdd(p.stat_sum + n0 + c, s_sum[c]);
-          atomicAdd(p.stat_sqsum + n0 + c, s_sq[c]);
+    if (!p.out_f32) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only: the staged tile is complete
+      const int t = threadIdx.x - 64;
+      if (do_stats) {
+        // thread = one pair of adjacent columns x one slab of rows; fp32 sums of the bf16 values as stored
+        constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
+        const int cp = t % kPairs, slab = t / kPairs;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const uint8_t* base = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll 8
+        for (int r = 0; r < kRowsPerSlab; ++r) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + r * kPitch));
+          s0 += f.x, s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0), q1 = fmaf(f.y, f.y, q1);
+        }
+        const int col = n0 + cp * 2;
+        if (col < p.cout) atomicAdd(p.stat_sum + col, s0), atomicAdd(p.stat_sqsum + col, q0);
+        if (col + 1 < p.cout) atomicAdd(p.stat_sum + col + 1, s1), atomicAdd(p.stat_sqsum + col + 1, q1);
+      }
+      // coalesced store: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass
+      constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
+      const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+      if (n0 + seg * 8 < p.n_store) {
+#pragma unroll 4
+        for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
+          const int r = pass * kRowsPerPass + r0;
+          const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+          if (rh < p.H && rw < p.W) {
+            const uint4 q = *reinterpret_cast<const uint4*>(stg + r * kPitch + seg * 16);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride + rh * p.out_row_stride +
+                                static_cast<size_t>(rw) * p.ld_out + n0 + seg * 8;
+            *reinterpret_cast<uint4*>(op) = q;
+          }
         }
       }
     }
@@ -342,6 +344,7 @@ extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, lo
   SSEG_REQUIRE(cout >= 1 && n_store >= cout && n_store % 8 == 0 && n_store <= out->ld,
                "sseg_conv_igemm: need cout <= out->c (mult of 8) <= out->ld, got %d %d %d", cout, n_store, out->ld);
   SSEG_REQUIRE((stat_sum == nullptr) == (stat_sqsum == nullptr), "sseg_conv_igemm: stat_sum/stat_sqsum must pair");
+  SSEG_REQUIRE(!(out_f32 && stat_sum != nullptr), "sseg_conv_igemm: BN statistics are produced for bf16 outputs only");
   IgemmParams p;
   memset(&p, 0, sizeof(p));
   GeomHost gh;

@@ -33,7 +33,7 @@ static int g_pdl = -1;
 bool pdl_enabled() {
   if (g_pdl < 0) {
     const char* e = getenv("SSEG_PDL");
-    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;  // on by default; SSEG_PDL=0 turns it off
   }
   return g_pdl == 1;
 }

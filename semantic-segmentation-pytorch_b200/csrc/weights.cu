@@ -38,21 +38,29 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
     const float* w = d->w;
     for (int ol = warp; ol < no; ol += 8) {
       const float* src = w + ((long)(o0 + ol) * I + i0) * T;
-      for (int r = lane; r < row; r += 32) tile[ol][r] = src[r];
+#pragma unroll
+      for (int k = 0; k < kMaxT; ++k) {  // row <= 32 * kMaxT: all loads of a row are issued back to back
+        const int r = lane + 32 * k;
+        if (r < row) tile[ol][r] = src[r];
+      }
     }
     __syncthreads();
     __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d->wf);
     if (wf && lane < ni) {
       for (int ol = warp; ol < no; ol += 8) {
         __nv_bfloat16* dst = wf + (long)(o0 + ol) * d->fwd_ld + i0 + lane;
-        for (int t = 0; t < T; ++t) dst[(long)t * I] = __float2bfloat16(tile[ol][lane * T + t]);
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t)
+          if (t < T) dst[(long)t * I] = __float2bfloat16(tile[ol][lane * T + t]);
       }
     }
     __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d->wd);
     if (wd && lane < no) {
       for (int il = warp; il < ni; il += 8) {
         __nv_bfloat16* dst = wd + (long)(i0 + il) * d->dgrad_ld + o0 + lane;
-        for (int t = 0; t < T; ++t) dst[(long)t * d->o_pad] = __float2bfloat16(tile[lane][il * T + t]);
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t)
+          if (t < T) dst[(long)t * d->o_pad] = __float2bfloat16(tile[lane][il * T + t]);
       }
     }
   } else {
@@ -61,14 +69,20 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
     if (lane < ni) {
       for (int ol = warp; ol < no; ol += 8) {
         const float* src = g + (long)(o0 + ol) * d->g_ld + i0 + lane;
-        for (int t = 0; t < T; ++t) tile[ol][lane * T + t] = src[(long)t * I];
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t)
+          if (t < T) tile[ol][lane * T + t] = src[(long)t * I];
       }
     }
     __syncthreads();
     float* out = d->g_dst;
     for (int ol = warp; ol < no; ol += 8) {
       float* dst = out + ((long)(o0 + ol) * I + i0) * T;
-      for (int r = lane; r < row; r += 32) dst[r] = tile[ol][r] * scale;
+#pragma unroll
+      for (int k = 0; k < kMaxT; ++k) {
+        const int r = lane + 32 * k;
+        if (r < row) dst[r] = tile[ol][r] * scale;
+      }
     }
   }
 }
