@@ -207,9 +207,10 @@ int sseg_softmax_nll_bwd(const float* logits, long ld, int C, const long long* l
 /* out[c] += sum_p x[p][c]  (bias gradients); x bf16 [P][ld]. */
 int sseg_colsum(const void* x, long ld, long P, int C, float* out, sseg_stream_t stream);
 /* Inference head (models/models.py:480-484; eval.py:71-72): bilinear-upsample fp32 NHWC logits [N,Hi,Wi,ld] to
- * (Ho,Wo), softmax over C, write fp32 NCHW probs (= or +=) weight * softmax. */
+ * (Ho,Wo), softmax over C, write fp32 NCHW probs (= or +=) weight * softmax.  log_output = 1 writes log-softmax
+ * instead (F.log_softmax, models/models.py:492-493; with Ho,Wo = Hi,Wi the resize is the identity). */
 int sseg_upsample_softmax(const float* logits, long ld, int N, int Hi, int Wi, int C, float* probs, int Ho, int Wo,
-                          float weight, int accumulate, sseg_stream_t stream);
+                          float weight, int accumulate, int log_output, sseg_stream_t stream);
 
 /* ---- layout ----------------------------------------------------------------------------- */
 int sseg_nhwc_bf16_to_nchw_f32(const void* x, long ld, int N, int H, int W, int C, float* out, sseg_stream_t stream);

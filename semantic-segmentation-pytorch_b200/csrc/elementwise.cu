@@ -879,7 +879,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 // optionally accumulated (scores += probs * weight): models/models.py:480-484, eval.py:71-72.
 __global__ void __launch_bounds__(256) upsample_softmax_kernel(const float* __restrict__ logits, long ld, int N, int Hi,
                                                                int Wi, int C, float* __restrict__ probs, int Ho, int Wo,
-                                                               float weight, int accumulate) {
+                                                               float weight, int accumulate, int log_output) {
   pdl_sync();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long P = (long)N * Ho * Wo;
@@ -909,21 +909,23 @@ __global__ void __launch_bounds__(256) upsample_softmax_kernel(const float* __re
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
-    float s = 0.f;
+    float s = 0.f, dm[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      v[k] = (lane + 32 * k < C) ? __expf(v[k] - m) : 0.f;
+      dm[k] = v[k] - m;
+      v[k] = (lane + 32 * k < C) ? __expf(dm[k]) : 0.f;
       s += v[k];
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-    const float inv = weight / s;
+    const float inv = weight / s, logs = __logf(s);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int ch = lane + 32 * k;
       if (ch < C) {
         float* o = probs + (((long)n * C + ch) * Ho + ho) * Wo + wo;
-        *o = accumulate ? *o + v[k] * inv : v[k] * inv;
+        const float r = log_output ? (dm[k] - logs) * weight : v[k] * inv;  // log-softmax = (x - m) - log(sum)
+        *o = accumulate ? *o + r : r;
       }
     }
   }
@@ -1182,10 +1184,10 @@ int sseg_colsum(const void* x, long ld, long P, int C, float* out, sseg_stream_t
 }
 
 int sseg_upsample_softmax(const float* logits, long ld, int N, int Hi, int Wi, int C, float* probs, int Ho, int Wo,
-                          float weight, int accumulate, sseg_stream_t st) {
+                          float weight, int accumulate, int log_output, sseg_stream_t st) {
   SSEG_REQUIRE(logits && probs && C >= 1 && C <= 256, "sseg_upsample_softmax: bad argument (C <= 256)");
   launch_k(upsample_softmax_kernel, dim3(grid_for((long)N * Ho * Wo, 8, 148 * 16)), dim3(256), 0, (cudaStream_t)st, 
-      logits, ld, N, Hi, Wi, C, probs, Ho, Wo, weight, accumulate);
+      logits, ld, N, Hi, Wi, C, probs, Ho, Wo, weight, accumulate, log_output);
   LAUNCH_CHECK("upsample_softmax_kernel");
 }
 

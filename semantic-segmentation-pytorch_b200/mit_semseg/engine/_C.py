@@ -103,7 +103,7 @@ _SIGNATURES = {
     "sseg_nll_finalize": [_p, _p, c_float, _p, _p],
     "sseg_softmax_nll_bwd": [_p, c_long, c_int, _p, _p, _p, c_float, c_long, _p, c_long, c_int, _p],
     "sseg_colsum": [_p, c_long, c_long, c_int, _p, _p],
-    "sseg_upsample_softmax": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_int, c_int, c_float, c_int, _p],
+    "sseg_upsample_softmax": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_int, c_int, c_float, c_int, c_int, _p],
     "sseg_nhwc_bf16_to_nchw_f32": [_p, c_long, c_int, c_int, c_int, c_int, _p, _p],
     "sseg_nchw_f32_to_nhwc_bf16": [_p, c_int, c_int, c_int, c_int, _p, c_long, _p],
 }

@@ -90,15 +90,54 @@ def segmentation_inference(seg, img, seg_size):
     return prog.probs.clone()
 
 
+def _cached(mod, key, build):
+    cache = _programs(mod)
+    prog = cache.get(key)
+    if prog is None:
+        prog = build()
+        cache[key] = prog
+        while len(cache) > _MAX_PROGRAMS:
+            cache.popitem(last=False)
+    else:
+        cache.move_to_end(key)
+    return prog
+
+
+def _flags(mod):
+    return hash(tuple(m.training for m in mod.modules()))
+
+
 def encoder_forward(enc, x):
-    raise NotImplementedError(
-        "calling the encoder on its own is not wired to the B200 engine yet; use SegmentationModule(enc, dec, crit) "
-        "(what train.py / eval.py do) - the fused program runs encoder+decoder+loss as one kernel schedule")
+    """Resnet / ResnetDilated called on their own (reference models/models.py:190-205,253-268): the four stage outputs
+    as fp32 NCHW tensors. Forward only: gradients flow through the fused SegmentationModule program, not through
+    module-level calls."""
+    if not x.is_cuda:
+        raise RuntimeError("the B200 engine has no CPU path: move the module and the batch to a CUDA device")
+    prog = _cached(enc, ("enc", tuple(x.shape), _flags(enc)),
+                   lambda: SegProgram(None, tuple(x.shape), training=enc.training, with_grad=False, part="encoder", enc=enc))
+    prog.load_inputs(x)
+    prog.run()
+    return [t.clone() for t in prog.feat_out]
 
 
 def decoder_forward(dec, conv_out, seg_size):
-    raise NotImplementedError(
-        "calling the decoder on its own is not wired to the B200 engine yet; use SegmentationModule(enc, dec, crit)")
+    """PPM / PPMDeepsup / C1 / C1DeepSup called on their own (reference models/models.py:339-385,408-495) with fp32
+    NCHW feature maps: log-probabilities at feature resolution (a tuple with the deep-supervision head for *_deepsup),
+    or, for use_softmax decoders, probabilities up-sampled to seg_size. Forward only."""
+    if not conv_out[-1].is_cuda:
+        raise RuntimeError("the B200 engine has no CPU path: move the module and the batch to a CUDA device")
+    infer = bool(getattr(dec, "use_softmax", False))
+    if infer and seg_size is None:
+        raise RuntimeError("a use_softmax decoder needs segSize")
+    shapes = tuple(tuple(t.shape) for t in conv_out)
+    key = ("dec", shapes, tuple(seg_size) if infer else None, _flags(dec))
+    prog = _cached(dec, key, lambda: SegProgram(None, None, training=dec.training, with_grad=False,
+                                                seg_size=tuple(seg_size) if infer else None, part="decoder", dec=dec,
+                                                feat_shapes=shapes))
+    prog.load_features(conv_out)
+    prog.run()
+    outs = [t.clone() for t in prog.outputs]
+    return outs[0] if len(outs) == 1 else tuple(outs)
 
 
 def run_block(block, x):

@@ -242,12 +242,12 @@ def colsum(x, C, out):
     _C.check(_C.lib().sseg_colsum(_C.ptr(x), ld, P, C, _C.ptr(out), _stream()))
 
 
-def upsample_softmax(logits, num_class, probs, weight=1.0, accumulate=False):
+def upsample_softmax(logits, num_class, probs, weight=1.0, accumulate=False, log_output=False):
     n, hi, wi, _ = logits.shape
     _, c, ho, wo = probs.shape
     assert c == num_class and probs.is_contiguous() and probs.dtype == torch.float32
     _C.check(_C.lib().sseg_upsample_softmax(_C.ptr(logits), _pix(logits)[2], n, hi, wi, num_class, _C.ptr(probs), ho, wo,
-                                            float(weight), int(accumulate), _stream()))
+                                            float(weight), int(accumulate), int(log_output), _stream()))
 
 
 def nhwc_bf16_to_nchw_f32(x, out):

@@ -69,18 +69,34 @@ class BNS:
 
 
 class SegProgram:
-    def __init__(self, seg, img_shape, training, with_grad=True, seg_size=None, dropout_masks=None):
+    def __init__(self, seg, img_shape, training, with_grad=True, seg_size=None, dropout_masks=None, part="full",
+                 enc=None, dec=None, feat_shapes=None):
         """seg: SegmentationModule.  img_shape: (N, 3, H, W).  training: module.training (BN/dropout behaviour).
         with_grad: also build the backward schedule.  seg_size: inference branch (probabilities at seg_size).
-        dropout_masks: optional {'main': [N,512] 0/1, 'deepsup': ...} to inject the Dropout2d draws (tests)."""
+        dropout_masks: optional {'main': [N,512] 0/1, 'deepsup': ...} to inject the Dropout2d draws (tests).
+        part: "full" (encoder + decoder + loss/head) | "encoder" (module called on its own: fp32 NCHW feature maps out)
+              | "decoder" (fp32 NCHW feature maps of `feat_shapes` in, log-probs / probabilities out); the partial
+              programs are forward-only."""
         self.seg = seg
-        self.enc, self.dec = seg.encoder, seg.decoder
+        self.part = part
+        self.enc = enc if enc is not None else (seg.encoder if seg is not None else None)
+        self.dec = dec if dec is not None else (seg.decoder if seg is not None else None)
+        if part == "encoder":
+            self.dec = None
+        elif part == "decoder":
+            self.enc = None
+        if part != "full":
+            with_grad = False
+        self.feat_shapes = feat_shapes
+        if part == "decoder":
+            img_shape = (feat_shapes[0][0], 3, 0, 0)
+            # use only the maps the decoder reads (the last one, and the one before it for deep supervision)
         self.N, _, self.H, self.W = img_shape
         self.training = bool(training)
         self.inference = seg_size is not None
         self.seg_size = seg_size
         self.with_grad = bool(with_grad) and not self.inference
-        self.dev = next(seg.parameters()).device
+        self.dev = next((self.enc if self.enc is not None else self.dec).parameters()).device
         assert self.dev.type == "cuda", "the B200 engine runs on CUDA devices only (no CPU fallback)"
         self.injected_masks = dropout_masks
         self.dist = _dist()
@@ -93,16 +109,23 @@ class SegProgram:
         self.side = torch.cuda.Stream(self.dev)
 
         self.convs, self.bns = {}, {}
-        for m in list(self.enc.modules()) + list(self.dec.modules()):
+        for m in self._modules():
             if isinstance(m, nn.Conv2d):
                 self.convs[id(m)] = ConvW(m)
             elif isinstance(m, _BatchNorm):
                 self.bns[id(m)] = BNS(m)
         self._alloc_params()
-        self.img = torch.zeros(img_shape, device=self.dev, dtype=torch.float32)
+        self.img = torch.zeros(img_shape, device=self.dev, dtype=torch.float32) if part != "decoder" else None
         self._build_forward()
         if self.with_grad:
             self._build_backward()
+
+    def _modules(self):
+        mods = []
+        for net in (self.enc, self.dec):
+            if net is not None:
+                mods += list(net.modules())
+        return mods
 
     # ------------------------------------------------------------------------------------------ buffers
     def _alloc_params(self):
@@ -202,30 +225,28 @@ class SegProgram:
         N, H, W = self.N, self.H, self.W
         self._prep_weights()
         self.fwd.append(lambda: self.sflat.copy_(self.sinit))
-        enc = self.enc
-        # ---- stem (reference models/resnet.py:100-109, models/models.py:256-259)
-        stem = StemRec(self, self.convs[id(enc.conv1)], self.bns[id(enc.bn1)])
-        self.records.append(stem)
-        x = stem.a
-        x = self.conv_bn(x, enc.conv2, enc.bn2)
-        x = self.conv_bn(x, enc.conv3, enc.bn3)
-        mp = MaxPoolRec(self, x)
-        self.records.append(mp)
-        x = mp.a
-        feats = []
-        for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
-            for block in layer:
-                assert isinstance(block, (R.BasicBlock, R.Bottleneck))
-                inp = x
-                res = inp
-                if block.downsample is not None:
-                    res = self.conv_bn(inp, block.downsample[0], block.downsample[1], relu=False, apply=False)
-                stages = block.stages()
-                for i, (cv, bn) in enumerate(stages):
-                    last = i == len(stages) - 1
-                    x = self.conv_bn(x, cv, bn, relu=True, res=res if last else None)
-            feats.append(x)
+        if self.part == "decoder":
+            # module-level call decoder(conv_out): fp32 NCHW feature maps in -> engine layout
+            self.feat_in, feats = [], []
+            for shp in self.feat_shapes:
+                n, c, h, w = shp
+                src = self._new(n, c, h, w, dtype=torch.float32)
+                act = Act(self._new(n, h, w, c))
+                self.fwd.append(lambda src=src, act=act: ops.nchw_f32_to_nhwc_bf16(src, act.t))
+                self.feat_in.append(src)
+                feats.append(act)
+        else:
+            feats = self._build_encoder(R)
         self.feats = feats
+        if self.part == "encoder":
+            # module-level call encoder(x, return_feature_maps=True): hand the maps back as fp32 NCHW tensors
+            self.feat_out = []
+            for f in feats:
+                n, h, w, c = f.t.shape
+                dst = self._new(n, c, h, w, dtype=torch.float32)
+                self.fwd.append(lambda f=f, dst=dst: ops.nhwc_bf16_to_nchw_f32(f.t, dst))
+                self.feat_out.append(dst)
+            return
         # ---- decoder
         dec = self.dec
         self.logits_ds = None
@@ -273,16 +294,57 @@ class SegProgram:
         if p_drop_main > 0 or p_drop_ds > 0:
             self.fwd.insert(0, self._draw_masks)
         # ---- head
-        if self.inference:
+        C8 = _pad(self.num_class, 8)
+        if self.part == "decoder":
+            # module-level call: probabilities at seg_size (use_softmax) or log-probabilities at feature resolution
+            n, h, w, _ = self.logits.shape
+            if self.inference:
+                hs, ws = self.seg_size
+                self.probs = self._new(n, self.num_class, hs, ws, dtype=torch.float32)
+                self.fwd.append(lambda: ops.upsample_softmax(self.logits[..., :C8], self.num_class, self.probs))
+                self.outputs = [self.probs]
+            else:
+                self.outputs = []
+                for lg in [self.logits] + ([self.logits_ds] if self.logits_ds is not None else []):
+                    o = self._new(n, self.num_class, h, w, dtype=torch.float32)
+                    self.fwd.append(lambda lg=lg, o=o: ops.upsample_softmax(lg[..., :C8], self.num_class, o,
+                                                                             log_output=True))
+                    self.outputs.append(o)
+        elif self.inference:
             hs, ws = self.seg_size
-            self.probs = self._new(N, self.num_class, hs, ws, dtype=torch.float32)
-            self.fwd.append(lambda: ops.upsample_softmax(self.logits[..., :_pad(self.num_class, 8)], self.num_class,
-                                                         self.probs))
+            self.probs = self._new(self.N, self.num_class, hs, ws, dtype=torch.float32)
+            self.fwd.append(lambda: ops.upsample_softmax(self.logits[..., :C8], self.num_class, self.probs))
         else:
             n, h, w, _ = self.logits.shape
             self.label = torch.full((n, h, w), -1, device=self.dev, dtype=torch.int64)
             loss = LossRec(self)
             self.records.append(loss)
+
+    def _build_encoder(self, R):
+        enc = self.enc
+        # ---- stem (reference models/resnet.py:100-109, models/models.py:256-259)
+        stem = StemRec(self, self.convs[id(enc.conv1)], self.bns[id(enc.bn1)])
+        self.records.append(stem)
+        x = stem.a
+        x = self.conv_bn(x, enc.conv2, enc.bn2)
+        x = self.conv_bn(x, enc.conv3, enc.bn3)
+        mp = MaxPoolRec(self, x)
+        self.records.append(mp)
+        x = mp.a
+        feats = []
+        for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
+            for block in layer:
+                assert isinstance(block, (R.BasicBlock, R.Bottleneck))
+                inp = x
+                res = inp
+                if block.downsample is not None:
+                    res = self.conv_bn(inp, block.downsample[0], block.downsample[1], relu=False, apply=False)
+                stages = block.stages()
+                for i, (cv, bn) in enumerate(stages):
+                    last = i == len(stages) - 1
+                    x = self.conv_bn(x, cv, bn, relu=True, res=res if last else None)
+            feats.append(x)
+        return feats
 
     def _draw_masks(self):
         for name, mask, p in (("main", getattr(self, "mask_main", None), self.p_drop[0]),
@@ -350,6 +412,10 @@ class SegProgram:
         return act.g, acc
 
     # ------------------------------------------------------------------------------------------ execution
+    def load_features(self, feats):
+        for dst, src in zip(self.feat_in, feats):
+            dst.copy_(src, non_blocking=True)
+
     def load_inputs(self, img, label=None):
         self.img.copy_(img, non_blocking=True)
         if label is not None:
@@ -364,8 +430,7 @@ class SegProgram:
     def capture(self):
         """Capture the whole step into one CUDA graph (after a warm-up run on a side stream)."""
         # the warm-up executes the step: keep it side-effect free on the module (BN running statistics)
-        bufs = [b for m in list(self.enc.modules()) + list(self.dec.modules()) if isinstance(m, _BatchNorm)
-                for b in m.buffers(recurse=False)]
+        bufs = [b for m in self._modules() if isinstance(m, _BatchNorm) for b in m.buffers(recurse=False)]
         saved = [b.clone() for b in bufs]
         s = torch.cuda.Stream(self.dev)
         s.wait_stream(torch.cuda.current_stream(self.dev))

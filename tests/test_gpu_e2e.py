@@ -225,3 +225,29 @@ def test_inference_matches_oracle():
     err = (probs - ref).abs().max().item()
     print("inference argmax agreement %.4f max prob err %.4f" % (agree, err))
     assert agree >= 0.98 and err <= 5e-2, (agree, err)
+
+
+def test_modules_called_on_their_own_match_the_fused_path():
+    """encoder(x, return_feature_maps=True) and decoder(conv_out[, segSize]) as the notebook / a user would call them."""
+    from oracle import segnet_oracle as O
+    seg, esd, dsd, ds = _build("resnet18dilated", "ppm_deepsup", 512, residual_gain=0.25)
+    seg.cuda().eval()
+    feed = O.synth_batch(2, 96, 128, 8, 6)
+    x = feed["img_data"].cuda()
+    with torch.no_grad():
+        feats = seg.encoder(x, return_feature_maps=True)
+        assert [tuple(f.shape) for f in feats] == [(2, 64, 24, 32), (2, 128, 12, 16), (2, 256, 12, 16), (2, 512, 12, 16)]
+        assert len(seg.encoder(x)) == 1
+        ref_feats = O.encoder_forward(feed["img_data"], esd, "resnet18dilated", O.BNState(False, emulate="bf16"))
+        for f, r in zip(feats, ref_feats):
+            assert _rel(f.cpu(), r) <= 2e-2
+        out = seg.decoder(feats)
+        assert isinstance(out, tuple) and out[0].shape == (2, 150, 12, 16)
+        ref = O.decoder_forward(ref_feats, dsd, "ppm_deepsup", O.BNState(False, emulate="bf16"))
+        assert _rel(out[0].cpu(), ref[0]) <= 2e-2 and _rel(out[1].cpu(), ref[1]) <= 2e-2
+        assert (out[0].exp().sum(1) - 1).abs().max().item() < 1e-3
+        seg.decoder.use_softmax = True
+        probs = seg.decoder(feats, segSize=(96, 128))
+        assert probs.shape == (2, 150, 96, 128) and (probs.sum(1) - 1).abs().max().item() < 1e-3
+        fused = seg({"img_data": x}, segSize=(96, 128))
+        assert (probs - fused).abs().max().item() <= 2e-2
