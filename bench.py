@@ -226,6 +226,8 @@ def run_gpu(args):
     e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
     e2e_value = BATCH * world * args.steps / (e2e_ms / 1e3)
 
+    prog.graph = None
+    seg.__dict__.pop("_b200_programs", None)
     if rank != 0:
         return
     sustained, burst, which = measured_peaks()
@@ -432,8 +434,27 @@ def main():
                              "CPU arm)")
         run_gpu(args)
         if int(os.environ.get("WORLD_SIZE", "1")) > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+            shutdown_distributed()
+
+
+def shutdown_distributed():
+    """Tear the process group down without hanging: CUDA graphs that captured NCCL kernels keep the communicator busy
+    at exit (observed: destroy_process_group never returns), so release them first and never wait more than a few
+    seconds - the JSON line is already printed."""
+    import gc
+    import threading
+    import torch.distributed as dist
+    sys.stdout.flush()
+    sys.stderr.flush()
+    threading.Timer(15.0, lambda: os._exit(0)).start()
+    try:
+        torch.cuda.synchronize()
+        dist.barrier()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+    finally:
+        os._exit(0)
 
 
 if __name__ == "__main__":
