@@ -195,9 +195,9 @@ def run_gpu(args):
     loss_dev = prog.out[0].item()
 
     # ---------------- roofline of the tensor-core kernels: CUDA events around every conv GEMM launch (eager pass)
-    roof = None
-    if rank == 0:
-        roof = conv_roofline(prog, world)
+    # every rank runs the pass (the program contains the SyncBN / bucket all-reduces); rank 0 reports its own numbers
+    roof = conv_roofline(prog, world)
+    barrier(world)
 
     # ---------------- end-to-end arm: the public API with host inputs (H2D) and a loss read-back (D2H) every step
     for p in seg.parameters():
