@@ -32,6 +32,7 @@ extern "C" {
 
 #define SSEG_MAX_SRCS 5
 #define SSEG_MAX_TAPS 9
+#define SSEG_MAX_PEERS 8
 
 typedef void* sseg_stream_t; /* cudaStream_t */
 
@@ -176,6 +177,28 @@ int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const 
                       const float* invstd, const float* scale, const float* fshift, const float* chanmul, const float* s1,
                       const float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
                       long dres_ld, long P, long pix_per_img, int C, int eval_mode, sseg_stream_t stream);
+
+/* ---- SyncBN over NVLink peer memory (world_size > 1) ------------------------------------- */
+/* One cudaMalloc'ed, zero-initialised arena per rank, exported with CUDA IPC (64-byte handle) and mapped by the peers.
+ * Offsets below are in 4-byte units from the arena base. */
+int sseg_peer_alloc(size_t bytes, void** ptr, unsigned char* handle64);
+int sseg_peer_open(const unsigned char* handle64, void** ptr);
+int sseg_peer_close(void* ptr);
+int sseg_peer_free(void* ptr);
+/* *step += 1 (once per training step; the handshake flags carry step numbers and are never reset) */
+int sseg_peer_step(int* step, sseg_stream_t stream);
+/* Forward of the synchronised branch (lib/nn/modules/batchnorm.py:98-139) without a collective call: handshake with all
+ * peers on flag slots [flag_off, flag_off + world), then pool [sum C | sqsum C | count] found at stats_off in EVERY
+ * rank's arena and finish like sseg_bn_finalize(SSEG_BN_TRAIN_SYNC). count_out receives the pooled pixel count. */
+int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_off, long flag_off, const int* step,
+                          const float* gamma, const float* beta, float eps, float momentum, int update_running,
+                          float* running_mean, float* running_var, float* tmp_running_mean, float* tmp_running_var,
+                          float* running_iter, float* mean_out, float* invstd_out, float* scale, float* shift,
+                          float* count_out, int C, sseg_stream_t stream);
+/* Backward: pool [s1 C | s2 C] partials at part_off over the ranks -> s1_tot, s2_tot; dbeta = s1_tot/world,
+ * dgamma = s2_tot/world (the gradient-bucket all-reduce sums them over ranks again). */
+int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
+                         float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, int C, sseg_stream_t stream);
 
 /* ---- pooling / resize ------------------------------------------------------------------- */
 /* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109). Dense bf16 NHWC; idx (1 byte / output element) feeds the backward. */

@@ -93,6 +93,14 @@ _SIGNATURES = {
     "sseg_bn_bwd_reduce": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, c_long, c_long, c_int, _p],
     "sseg_bn_bwd_apply": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, _p, c_float, _p, c_long, _p,
                           c_long, c_long, c_long, c_int, c_int, _p],
+    "sseg_peer_alloc": [ctypes.c_size_t, POINTER(c_void_p), _p],
+    "sseg_peer_open": [_p, POINTER(c_void_p)],
+    "sseg_peer_close": [_p],
+    "sseg_peer_free": [_p],
+    "sseg_peer_step": [_p, _p],
+    "sseg_bn_finalize_peer": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, c_float, c_float, c_int, _p, _p,
+                              _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p],
+    "sseg_bn_bwd_peer_sum": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, _p, _p, c_int, _p],
     "sseg_maxpool_fwd": [_p, c_int, c_int, c_int, c_int, _p, _p, _p],
     "sseg_maxpool_bwd": [_p, _p, _p, c_int, c_int, c_int, c_int, _p],
     "sseg_avgpool_fwd": [_p, c_long, c_int, c_int, c_int, c_int, c_int, _p, _p],

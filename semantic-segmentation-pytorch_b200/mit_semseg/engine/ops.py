@@ -144,6 +144,27 @@ def bn_finalize(ssum, ssq, count, gamma, beta, eps, momentum, mode, mean, invstd
                                        _C.ptr(shift), scale.numel(), _stream()))
 
 
+def peer_step(step):
+    _C.check(_C.lib().sseg_peer_step(_C.ptr(step), _stream()))
+
+
+def bn_finalize_peer(arena, stats_off, flag_off, step, gamma, beta, eps, momentum, mean, invstd, scale, shift, count_out,
+                     running=None, update_running=False):
+    rm = rv = tm = tv = it = None
+    if running is not None:
+        rm, rv, tm, tv, it = running
+    _C.check(_C.lib().sseg_bn_finalize_peer(arena.bases, arena.world, arena.rank, stats_off, flag_off, _C.ptr(step),
+                                            _C.ptr(gamma), _C.ptr(beta), eps, momentum, int(update_running), _C.ptr(rm),
+                                            _C.ptr(rv), _C.ptr(tm), _C.ptr(tv), _C.ptr(it), _C.ptr(mean), _C.ptr(invstd),
+                                            _C.ptr(scale), _C.ptr(shift), _C.ptr(count_out), scale.numel(), _stream()))
+
+
+def bn_bwd_peer_sum(arena, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgamma):
+    _C.check(_C.lib().sseg_bn_bwd_peer_sum(arena.bases, arena.world, arena.rank, part_off, flag_off, _C.ptr(step),
+                                           _C.ptr(s1_tot), _C.ptr(s2_tot), _C.ptr(dbeta), _C.ptr(dgamma),
+                                           s1_tot.numel(), _stream()))
+
+
 def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None, chanmul=None):
     P, ppi, y_ld = _pix(y)
     _, _, out_ld = _pix(out)

@@ -119,6 +119,11 @@ class SegProgram:
         self._build_forward()
         if self.with_grad:
             self._build_backward()
+        elif self.peer is not None:
+            # forward-only synchronised steps have no gradient-bucket all-reduce to separate them: a one-float
+            # all-reduce keeps a fast rank from re-zeroing statistics a slow peer is still reading
+            fence = torch.zeros(1, device=self.dev)
+            self.fwd.append(lambda: self.dist.all_reduce(fence))
 
     def _modules(self):
         mods = []
@@ -139,8 +144,20 @@ class SegProgram:
         self.g_small = small
         self.gflat = torch.zeros((small + nf) if self.with_grad else 0, device=dev, dtype=torch.float32)
         ns = sum(_pad(2 * b.C + 1, 4) for b in self.bns.values()) + 8
-        self.sflat = torch.zeros(ns, device=dev, dtype=torch.float32)
-        self.sinit = torch.zeros(ns, device=dev, dtype=torch.float32)
+        # with several ranks the statistics live in a peer-mapped arena (SyncBN without NCCL calls, csrc/peer.cu):
+        # [per-BN sum|sqsum|count ... loss accumulators | per-BN s1|s2 partials ... | flags (int) | step (int)]
+        self.peer = None
+        npart = sum(2 * b.C for b in self.bns.values())
+        import os
+        if self.dist is not None and self.training and os.environ.get("SSEG_PEER_SYNC", "1") != "0":
+            from .peer import PeerArena
+            nflag = 16 * len(self.bns) + 16
+            self.peer = PeerArena(ns + npart + nflag, self.dist, dev)
+            self.sflat = self.peer.floats[:ns + npart]
+            self.sflat.zero_()
+        else:
+            self.sflat = torch.zeros(ns, device=dev, dtype=torch.float32)
+        self.sinit = torch.zeros(self.sflat.numel(), device=dev, dtype=torch.float32)
         nv = sum(4 * b.C for b in self.bns.values())
         self.vflat = torch.empty(nv, device=dev, dtype=torch.float32)
         of = od = 0
@@ -157,10 +174,17 @@ class SegProgram:
                     c.gb = self.gflat[ogs:ogs + c.O]
                     ogs += _pad(c.O, 4)
         os_, ov = 0, 0
+        op_, ofl = ns, ns + npart
         for b in self.bns.values():
             b.stats = self.sflat[os_:os_ + 2 * b.C + 1]
             b.stats_off = os_
             os_ += _pad(2 * b.C + 1, 4)
+            if self.peer is not None:
+                b.part = self.sflat[op_:op_ + 2 * b.C]  # [s1 | s2] partial sums of the backward pass
+                b.part_off, b.flag_off = op_, ofl
+                op_ += 2 * b.C
+                ofl += 16
+                b.tot = torch.zeros(2 * b.C + 1, device=dev, dtype=torch.float32)  # s1_tot | s2_tot | pooled count
             b.mean, b.invstd, b.scale, b.shift = (self.vflat[ov + i * b.C: ov + (i + 1) * b.C] for i in range(4))
             ov += 4 * b.C
             if self.with_grad:
@@ -169,6 +193,8 @@ class SegProgram:
                 ogs += 2 * b.C
         self.acc_main = self.sflat[os_:os_ + 4]
         self.acc_ds = self.sflat[os_ + 4:os_ + 8]
+        if self.peer is not None:
+            self.peer_step = self.peer.ints[ofl:ofl + 1]
         self.out = torch.zeros(2, device=dev, dtype=torch.float32)  # (loss, acc)
 
     def _new(self, *shape, dtype=torch.bfloat16, zero=False):
@@ -225,6 +251,8 @@ class SegProgram:
         N, H, W = self.N, self.H, self.W
         self._prep_weights()
         self.fwd.append(lambda: self.sflat.copy_(self.sinit))
+        if self.peer is not None:
+            self.fwd.append(lambda: ops.peer_step(self.peer_step))
         if self.part == "decoder":
             # module-level call decoder(conv_out): fp32 NCHW feature maps in -> engine layout
             self.feat_in, feats = [], []
@@ -510,20 +538,26 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
     m = bns.mod
     C = bns.C
     st = bns.stats
-    if mode == ops.BN_TRAIN_SYNC:
-        # local pixel count rides along with the sums so ranks with different batch shapes pool correctly
-        P.sinit[bns.stats_off + 2 * C] = float(count)
-        if P.dist is not None:
-            P.fwd.append(lambda: P.dist.all_reduce(st))
     running = (m.running_mean, m.running_var, getattr(m, "_tmp_running_mean", None), getattr(m, "_tmp_running_var", None),
                getattr(m, "_running_iter", None))
     upd = mode != ops.BN_EVAL and m.track_running_stats and m.running_mean is not None
     mom = m.momentum if m.momentum is not None else 0.1
-    cdev = st[2 * C:2 * C + 1] if mode == ops.BN_TRAIN_SYNC else None
     w = m.weight.detach() if m.weight is not None else None
     b = m.bias.detach() if m.bias is not None else None
-    P.fwd.append(lambda: ops.bn_finalize(st[:C], st[C:2 * C], count, w, b, m.eps, mom, mode, bns.mean, bns.invstd,
-                                         bns.scale, bns.shift, running=running, update_running=upd, count_dev=cdev))
+    if mode == ops.BN_TRAIN_SYNC:
+        # local pixel count rides along with the sums so ranks with different batch shapes pool correctly
+        P.sinit[bns.stats_off + 2 * C] = float(count)
+    if mode == ops.BN_TRAIN_SYNC and P.peer is not None:
+        cnt_out = bns.tot[2 * C:2 * C + 1]
+        P.fwd.append(lambda: ops.bn_finalize_peer(P.peer, bns.stats_off, bns.flag_off, P.peer_step, w, b, m.eps, mom,
+                                                  bns.mean, bns.invstd, bns.scale, bns.shift, cnt_out, running=running,
+                                                  update_running=upd))
+    else:
+        if mode == ops.BN_TRAIN_SYNC and P.dist is not None:
+            P.fwd.append(lambda: P.dist.all_reduce(st))
+        cdev = st[2 * C:2 * C + 1] if mode == ops.BN_TRAIN_SYNC else None
+        P.fwd.append(lambda: ops.bn_finalize(st[:C], st[C:2 * C], count, w, b, m.eps, mom, mode, bns.mean, bns.invstd,
+                                             bns.scale, bns.shift, running=running, update_running=upd, count_dev=cdev))
     if out is not None:
         P.fwd.append(lambda: ops.bn_apply(y, bns.scale, bns.shift, out, relu=relu, res=res, rscale=rscale, rshift=rshift,
                                           chanmul=chanmul))
@@ -542,6 +576,16 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from
         # dgamma / dbeta of a frozen BN still exist in the reference (affine params stay trainable under fix_bn)
         P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul,
                                                scale=sc, fshift=fs))
+        return
+    if mode == ops.BN_TRAIN_SYNC and P.peer is not None:
+        # partial sums into the peer-mapped arena -> handshake + pooled totals (csrc/peer.cu) -> apply
+        p1, p2 = bns.part[:C], bns.part[C:2 * C]
+        t1, t2, cnt = bns.tot[:C], bns.tot[C:2 * C], bns.tot[2 * C:2 * C + 1]
+        P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, p1, p2, chanmul=chanmul, scale=sc, fshift=fs))
+        P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, t1, t2, bns.dbeta,
+                                                 bns.dgamma))
+        P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, sc, t1, t2, count, dy, dres=dres,
+                                              chanmul=chanmul, count_dev=cnt, fshift=fs))
         return
     P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, bns.dbeta, bns.dgamma, chanmul=chanmul,
                                            scale=sc, fshift=fs))
