@@ -126,7 +126,8 @@ int sseg_grad_to_oihw(const float* g, long g_ld, int O, int I, int T, float* out
                       sseg_stream_t stream);
 
 /* Batched variants: one launch for every convolution of a model. `table_dev` is a DEVICE array of n descriptors
- * (built once by the caller); descriptor k owns CTAs [first_tile, first_tile + ceil(O/32)*ceil(I/32)), T <= 9. */
+ * (built once by the caller); descriptor k owns CTAs [first_tile, first_tile + ceil(O/32)*ceil(ceil(I/32)/r)) with
+ * r = 8 for T == 1 (a CTA walks 8 consecutive 32-wide I tiles of a pointwise conv) else 1; T <= 9. */
 typedef struct {
   const float* w; /* fp32 OIHW master weight (prep) */
   void* wf;       /* bf16 [O][fwd_ld] or NULL */

@@ -14,12 +14,17 @@ constexpr int kMaxT = 9;
 
 __device__ __forceinline__ const sseg_weight_desc_t* find_desc(const sseg_weight_desc_t* table, int n, int tile,
                                                                int& local) {
-  int lo = 0;
-  for (int k = 1; k < n; ++k)
-    if (table[k].first_tile <= tile) lo = k;
-  local = tile - table[lo].first_tile;
+  int lo = 0, hi = n - 1;  // last descriptor whose first_tile <= tile (binary search: ~6 dependent loads, not n)
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&table[mid].first_tile) <= tile) lo = mid; else hi = mid - 1;
+  }
+  local = tile - __ldg(&table[lo].first_tile);
   return table + lo;
 }
+
+// i-tiles handled by one CTA: pointwise convs (T = 1) have tiny 32x32 tiles, so a CTA walks 8 of them
+__host__ __device__ inline int i_tiles_per_cta(int T) { return T == 1 ? 8 : 1; }
 
 __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_desc_t* __restrict__ table, int n,
                                                               int mode, float scale) {
@@ -29,9 +34,15 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
   const sseg_weight_desc_t* d = find_desc(table, n, blockIdx.x, local);
   const int O = d->O, I = d->I, T = d->T;
   const int tiles_i = (I + kTile - 1) / kTile;
-  const int o0 = (local / tiles_i) * kTile, i0 = (local % tiles_i) * kTile;
-  const int no = min(kTile, O - o0), ni = min(kTile, I - i0);
+  const int rep = i_tiles_per_cta(T);
+  const int ctas_i = (tiles_i + rep - 1) / rep;
+  const int o0 = (local / ctas_i) * kTile;
+  const int no = min(kTile, O - o0);
+  for (int it = (local % ctas_i) * rep; it < min(tiles_i, (local % ctas_i) * rep + rep); ++it) {
+  const int i0 = it * kTile;
+  const int ni = min(kTile, I - i0);
   const int row = ni * T;
+  __syncthreads();  // the shared tile is reused across iterations
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (mode == 0) {
     // ---- load OIHW: for a fixed o the (i, t) range is contiguous
@@ -85,6 +96,7 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
       }
     }
   }
+  }  // i-tile loop
 }
 
 }  // namespace sseg

@@ -301,7 +301,8 @@ class WeightTable:
             d.O, d.I, d.T, d.o_pad = e["O"], e["I"], e["T"], e["o_pad"]
             assert d.T <= 9
             d.first_tile = tiles
-            tiles += ((d.O + 31) // 32) * ((d.I + 31) // 32)
+            rep = 8 if d.T == 1 else 1  # i-tiles per CTA, must match i_tiles_per_cta() in csrc/weights.cu
+            tiles += ((d.O + 31) // 32) * ((((d.I + 31) // 32) + rep - 1) // rep)
         raw = bytes(arr)
         self.n, self.tiles = n, tiles
         self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)

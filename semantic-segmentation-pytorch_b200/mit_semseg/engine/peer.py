@@ -27,16 +27,22 @@ class PeerArena:
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle))
         self.bases = (ctypes.c_void_p * self.world)()
+        err = None
         for r, h in enumerate(handles):
             if r == self.rank:
                 self.bases[r] = self.local_ptr
             else:
                 p = ctypes.c_void_p()
                 buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-                _C.check(L.sseg_peer_open(buf, ctypes.byref(p)))
-                self.bases[r] = p.value
+                try:
+                    _C.check(L.sseg_peer_open(buf, ctypes.byref(p)))
+                    self.bases[r] = p.value
+                except _C.SsegError as exc:  # keep going: every rank must reach the barrier below
+                    err = exc
         self._raw_f = _RawCuda(self.local_ptr, self.nbytes // 4, "<f4")
         self._raw_i = _RawCuda(self.local_ptr, self.nbytes // 4, "<i4")
         self.floats = torch.as_tensor(self._raw_f, device=device)
         self.ints = torch.as_tensor(self._raw_i, device=device)
         dist.barrier()  # every rank has mapped every arena before anyone starts signalling
+        if err is not None:
+            raise err

@@ -152,7 +152,18 @@ class SegProgram:
         if self.dist is not None and self.training and os.environ.get("SSEG_PEER_SYNC", "1") != "0":
             from .peer import PeerArena
             nflag = 16 * len(self.bns) + 16
-            self.peer = PeerArena(ns + npart + nflag, self.dist, dev)
+            try:
+                self.peer = PeerArena(ns + npart + nflag, self.dist, dev)
+                ok = 1.0
+            except Exception as exc:  # e.g. CUDA IPC unavailable between the ranks
+                self.peer, ok = None, 0.0
+                import warnings
+                warnings.warn("peer-memory SyncBN unavailable (%s); using NCCL all-reduces" % exc)
+            agree = torch.tensor([ok], device=dev)
+            self.dist.all_reduce(agree, op=self.dist.ReduceOp.MIN)  # every rank takes the same path
+            if agree.item() < 1.0:
+                self.peer = None
+        if self.peer is not None:
             self.sflat = self.peer.floats[:ns + npart]
             self.sflat.zero_()
         else:
