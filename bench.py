@@ -70,7 +70,11 @@ def build_model(device):
     return seg.to(device).train()
 
 
-def make_optimizers(seg):
+def make_optimizers(seg, fused=False):
+    """train.py:115-127: one SGD per net. fused=True: the engine's one-launch multi-tensor SGD (same arithmetic)."""
+    if fused:
+        from mit_semseg.engine.optim import FusedSGD
+        return [FusedSGD(group_weight(net), lr=LR, momentum=MOMENTUM, weight_decay=WD) for net in (seg.encoder, seg.decoder)]
     return [torch.optim.SGD(group_weight(net), lr=LR, momentum=MOMENTUM, weight_decay=WD)
             for net in (seg.encoder, seg.decoder)]
 
@@ -157,7 +161,7 @@ def run_gpu(args):
     from oracle import segnet_oracle as O  # synthetic batch generator only (no oracle compute on this arm)
 
     seg = build_model(dev)
-    opts = make_optimizers(seg)
+    opts = make_optimizers(seg, fused=True)   # device-resident arm: engine optimizer (2 launches / step)
     feed = O.synth_batch(BATCH, CROP, CROP, LABEL_STRIDE, 304 + rank, NUM_CLASS)
     img_h, lab_h = feed["img_data"].pin_memory(), feed["seg_label"].pin_memory()
     img_d, lab_d = img_h.to(dev), lab_h.to(dev)
@@ -202,6 +206,7 @@ def run_gpu(args):
     # ---------------- end-to-end arm: the public API with host inputs (H2D) and a loss read-back (D2H) every step
     for p in seg.parameters():
         p.grad = None
+    opts = make_optimizers(seg)               # end-to-end arm: exactly train.py's torch.optim.SGD pair
     feed_host = {"img_data": img_h, "seg_label": lab_h}
 
     def e2e_step():
@@ -246,8 +251,8 @@ def run_gpu(args):
         "e2e": {"value": round(e2e_value, 3), "unit": "images/s", "ms_per_step": round(e2e_ms / args.steps, 4),
                 "h2d_bytes_per_step": img_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
                 "loss_last": round(last, 5)},
-        "gpu_launches": launches_per_step * args.steps,
-        "launches_per_step": launches_per_step,
+        "gpu_launches": (launches_per_step + 2) * args.steps,
+        "launches_per_step": launches_per_step + 2,
         "model_flops_frac": round(value / world * TRAIN_GFLOP_PER_IMG / 1e3 / sustained, 4),
         "roofline": roof,
     }

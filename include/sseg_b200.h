@@ -143,6 +143,22 @@ int sseg_prep_conv_weights_batched(const sseg_weight_desc_t* table_dev, int n, i
 int sseg_grads_to_oihw_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, float scale,
                                sseg_stream_t stream);
 
+/* ---- optimizer -------------------------------------------------------------------------- */
+/* torch.optim.SGD(momentum, weight_decay) step for every parameter in ONE launch (train.py:115-127, :47-48).
+ * chunks_dev: DEVICE array; each chunk is a contiguous piece (n <= 65536 elements) of one parameter tensor with its
+ * gradient and momentum buffer; vec4 = 1 when the three pointers are 16-byte aligned and n % 4 == 0. */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* momentum_buf;
+  float weight_decay;
+  int n;
+  int vec4;
+  int reserved;
+} sseg_sgd_chunk_t;
+int sseg_sgd_step(const sseg_sgd_chunk_t* chunks_dev, int nchunks, float lr, float momentum, int first_step,
+                  sseg_stream_t stream);
+
 /* ---- stem convolution (Cin = 3, 3x3, stride 2, pad 1, Cout = 64): models/resnet.py:100 -------------- */
 /* img: fp32 NCHW [N,3,H,W]; w: fp32 OIHW [64,3,3,3]; out: bf16 NHWC [N,Ho,Wo,64] dense; optional BN statistics. */
 int sseg_stem_conv_fwd(const float* img, int N, int H, int W, const float* w, void* out, float* stat_sum,

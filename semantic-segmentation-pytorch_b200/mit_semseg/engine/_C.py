@@ -37,6 +37,12 @@ class WeightDesc(Structure):
                 ("o_pad", c_int), ("first_tile", c_int), ("reserved", c_int)]
 
 
+class SgdChunk(Structure):
+    """sseg_sgd_chunk_t"""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("momentum_buf", c_void_p), ("weight_decay", c_float),
+                ("n", c_int), ("vec4", c_int), ("reserved", c_int)]
+
+
 _lib = None
 
 
@@ -84,6 +90,7 @@ _SIGNATURES = {
     "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],
     "sseg_prep_conv_weights_batched": [_p, c_int, c_int, _p],
     "sseg_grads_to_oihw_batched": [_p, c_int, c_int, c_float, _p],
+    "sseg_sgd_step": [_p, c_int, c_float, c_float, c_int, _p],
     "sseg_grad_to_oihw": [_p, c_long, c_int, c_int, c_int, _p, c_float, c_int, _p],
     "sseg_stem_conv_fwd": [_p, c_int, c_int, c_int, _p, _p, _p, _p, _p],
     "sseg_stem_conv_wgrad": [_p, c_int, c_int, c_int, _p, _p, _p],

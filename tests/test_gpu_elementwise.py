@@ -300,3 +300,31 @@ def test_batched_weight_prep_and_grad_layout():
         k = int(T_ ** 0.5)
         ref_g = 0.5 * e["g_src"].reshape(O_, k, k, I_).permute(0, 3, 1, 2)
         assert torch.equal(e["g_dst"], ref_g.contiguous())
+
+
+def test_fused_sgd_matches_torch_sgd():
+    """One-launch multi-tensor SGD == torch.optim.SGD(momentum, weight_decay) with train.py's two parameter groups."""
+    from mit_semseg.engine.optim import FusedSGD
+    g = _gen(11)
+    shapes = [(512, 4096, 3, 3), (150, 512, 1, 1), (150,), (64,), (2048,), (64, 3, 3, 3), (7,)]
+    ref_p = [torch.randn(s, device=DEV, generator=g).requires_grad_(True) for s in shapes]
+    my_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    decay = [0, 1, 5]
+    mk = lambda ps: [dict(params=[ps[i] for i in decay]), dict(params=[ps[i] for i in range(len(ps)) if i not in decay],
+                                                            weight_decay=0.0)]
+    ref = torch.optim.SGD(mk(ref_p), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    mine = FusedSGD(mk(my_p), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    grads = [torch.empty_like(p) for p in my_p]     # static gradient buffers, as the engine provides
+    for step in range(4):
+        for i, (a, b) in enumerate(zip(ref_p, my_p)):
+            gr = torch.randn(a.shape, device=DEV, generator=g)
+            a.grad = gr.clone()
+            grads[i].copy_(gr)
+            b.grad = grads[i]
+        for grp_r, grp_m in zip(ref.param_groups, mine.param_groups):
+            grp_r["lr"] = grp_m["lr"] = 0.02 * (1 - step / 10) ** 0.9   # train.py:130-139 poly schedule
+        ref.step()
+        mine.step()
+    torch.cuda.synchronize()
+    for a, b in zip(ref_p, my_p):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (a - b).abs().max().item()
