@@ -176,12 +176,13 @@ int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_de
                      const float* beta, float eps, float momentum, int mode, int update_running, float* running_mean,
                      float* running_var, float* tmp_running_mean, float* tmp_running_var, float* running_iter,
                      float* mean_out, float* invstd_out, float* scale, float* shift, int C, sseg_stream_t stream);
-/* out = [relu](y*scale + shift + res') * chanmul[n][c];  res' = res (*rscale + rshift if given).
+/* out = [relu](y*scale + shift + res') * chanmul[n][c];  res' = res (*rscale + rshift if given);
+ * res_after_relu = 1: out = relu(y*scale + shift) + res' (UPerNet lateral + top-down add, models/models.py:557-563).
  * Fuses BN-apply, the residual add of Bottleneck/BasicBlock (models/resnet.py:45-53,84-92), ReLU and the
  * Dropout2d channel mask (models/models.py:460). y/res/out: bf16 [P][ld]. chanmul: float [N][C] or NULL. */
 int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
                   const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
-                  long pix_per_img, int C, int relu, sseg_stream_t stream);
+                  long pix_per_img, int C, int relu, int res_after_relu, sseg_stream_t stream);
 /* backward.  g' = g * chanmul * [ReLU active].  The ReLU mask comes from the saved layer output (a > 0) or, for layers
  * without a shortcut, is recomputed as (y*scale + fshift > 0) when `a` is NULL and `fshift` is given (one tensor less to
  * read); both NULL = the layer has no ReLU.

@@ -245,19 +245,21 @@ def decoder_forward(conv_out, sd, arch, st, segSize=None, use_softmax=False, dro
         H, W = conv5.shape[2:]
         ppm_out = [conv5]
         for i, scale in enumerate((1, 2, 3, 6)):
-            y = F.interpolate(F.adaptive_avg_pool2d(conv5, scale), (H, W), mode="bilinear", align_corners=False)
+            y = _q(F.interpolate(_q(F.adaptive_avg_pool2d(conv5, scale), st), (H, W), mode="bilinear",
+                                 align_corners=False), st)
             ppm_out.append(_cbr(y, sd, "%sppm_conv.%d.0" % (P, i), "%sppm_conv.%d.1" % (P, i), st))
         f = _cbr(torch.cat(ppm_out, 1), sd, P + "ppm_last_conv.0", P + "ppm_last_conv.1", st, padding=1)
         feats = [f]
         for i in reversed(range(len(conv_out) - 1)):
-            lat = _cbr(conv_out[i], sd, "%sfpn_in.%d.0" % (P, i), "%sfpn_in.%d.1" % (P, i), st)
-            f = lat + F.interpolate(f, size=lat.shape[2:], mode="bilinear", align_corners=False)
+            lat = _cbr(conv_out[i], sd, "%sfpn_in.%d.0" % (P, i), "%sfpn_in.%d.1" % (P, i), st, relu=False)
+            up = _q(F.interpolate(f, size=lat.shape[2:], mode="bilinear", align_corners=False), st)
+            f = _q(F.relu(lat) + up, st)   # conv_x + f (models.py:563); the engine stores only the sum
             feats.append(_cbr(f, sd, "%sfpn_out.%d.0.0" % (P, i), "%sfpn_out.%d.0.1" % (P, i), st, padding=1))
         feats.reverse()
         size = feats[0].shape[2:]
-        fusion = [feats[0]] + [F.interpolate(t, size, mode="bilinear", align_corners=False) for t in feats[1:]]
+        fusion = [feats[0]] + [_q(F.interpolate(t, size, mode="bilinear", align_corners=False), st) for t in feats[1:]]
         x = _cbr(torch.cat(fusion, 1), sd, P + "conv_last.0.0", P + "conv_last.0.1", st, padding=1)
-        logits = F.conv2d(x, sd[P + "conv_last.1.weight"], sd[P + "conv_last.1.bias"])
+        logits = F.conv2d(x, _qw(sd[P + "conv_last.1.weight"], st), sd[P + "conv_last.1.bias"])
         if use_softmax:
             return _head(logits, segSize, True)
         return logits if return_logits else F.log_softmax(logits, dim=1)

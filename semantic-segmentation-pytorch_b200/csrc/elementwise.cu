@@ -298,6 +298,7 @@ struct BnApplyParams {
   long P;          // pixels
   long pix_per_img;
   int C, relu, cgb, rows;
+  int res_after_relu;  // out = relu(y*scale+shift) + res  (FPN lateral + top-down add) instead of relu(... + res)
 };
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const BnApplyParams p) {
   pdl_sync();
@@ -332,8 +333,10 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const BnApplyParams p)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         float t = fmaf(v[e], sc[e], sh[e]);
-        if (p.res) t += fmaf(r[e], rs[e], rb[e]);
+        const float rr = p.res ? fmaf(r[e], rs[e], rb[e]) : 0.f;
+        if (!p.res_after_relu) t += rr;
         if (p.relu) t = fmaxf(t, 0.f);
+        if (p.res_after_relu) t += rr;
         v[e] = t;
       }
       if (p.chanmul) {
@@ -1044,12 +1047,12 @@ int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_de
 
 int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
                   const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
-                  long pix_per_img, int C, int relu, sseg_stream_t st) {
+                  long pix_per_img, int C, int relu, int res_after_relu, sseg_stream_t st) {
   SSEG_REQUIRE(y && scale && shift && out && C % 8 == 0 && y_ld % 8 == 0 && out_ld % 8 == 0 && (!res || res_ld % 8 == 0),
                "sseg_bn_apply: bad argument (channels and strides must be multiples of 8)");
   const BnTiling t = bn_tiling(P, C);
   BnApplyParams p{(const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, rscale, rshift,
-                  chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu, t.cgb, t.rows};
+                  chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu, t.cgb, t.rows, res_after_relu};
   launch_k(bn_apply_kernel, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("bn_apply_kernel");
 }

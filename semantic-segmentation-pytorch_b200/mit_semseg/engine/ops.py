@@ -165,13 +165,13 @@ def bn_bwd_peer_sum(arena, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgam
                                            s1_tot.numel(), _stream()))
 
 
-def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None, chanmul=None):
+def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None, chanmul=None, res_after_relu=False):
     P, ppi, y_ld = _pix(y)
     _, _, out_ld = _pix(out)
     res_ld = _pix(res)[2] if res is not None else 0
     _C.check(_C.lib().sseg_bn_apply(_C.ptr(y), y_ld, _C.ptr(scale), _C.ptr(shift), _C.ptr(res), res_ld, _C.ptr(rscale),
                                     _C.ptr(rshift), _C.ptr(chanmul), _C.ptr(out), out_ld, P, ppi, y.shape[3], int(relu),
-                                    _stream()))
+                                    int(res_after_relu), _stream()))
     return out
 
 

@@ -248,11 +248,12 @@ class SegProgram:
         self.keep.append(geom)
         return geom, ho, wo
 
-    def conv_bn(self, xs, conv_mod, bn_mod, relu=True, res=None, chanmul=None, apply=True):
-        """conv -> BN(train/eval) -> (+res) -> ReLU -> (*chanmul).  xs: Act or list of Acts (virtual concat).
-        res: None | Act (identity shortcut) | ConvBNRec built with apply=False (projection shortcut)."""
+    def conv_bn(self, xs, conv_mod, bn_mod, relu=True, res=None, chanmul=None, apply=True, post_add=None):
+        """conv -> BN(train/eval) -> (+res) -> ReLU -> (*chanmul) (+post_add).  xs: Act or list of Acts (virtual concat).
+        res: None | Act (identity shortcut) | ConvBNRec built with apply=False (projection shortcut).
+        post_add: Act added AFTER the ReLU (FPN top-down path, models/models.py:561-563)."""
         rec = ConvBNRec(self, xs if isinstance(xs, list) else [xs], self.convs[id(conv_mod)], self.bns[id(bn_mod)], relu,
-                        res, chanmul, apply)
+                        res, chanmul, apply, post_add)
         self.records.append(rec)
         return rec if not apply else rec.a
 
@@ -325,6 +326,37 @@ class SegProgram:
                 cls2 = ClassifierRec(self, y, self.convs[id(dec.conv_last_deepsup)])
                 self.records.append(cls2)
                 self.logits_ds = cls2.logits
+        elif isinstance(dec, M.UPerNet):
+            # reference models/models.py:543-586
+            conv5 = feats[-1]
+            n, h, w, c5 = conv5.t.shape
+            srcs = [conv5]
+            for scale, branch in zip(dec.pool_scales, dec.ppm_conv):
+                pr = AvgPoolRec(self, conv5, scale)
+                self.records.append(pr)
+                ur = UpsampleRec(self, pr.a, h, w)       # here the 1x1 conv comes AFTER the up-sampling (:548-552)
+                self.records.append(ur)
+                srcs.append(self.conv_bn(ur.a, branch[0], branch[1]))
+            f = self.conv_bn(srcs, dec.ppm_last_conv[0], dec.ppm_last_conv[1])
+            levels = [f]
+            for i in reversed(range(len(feats) - 1)):
+                lat_in = feats[i]
+                _, hi, wi, _ = lat_in.t.shape
+                up = UpsampleRec(self, f, hi, wi)          # top-down branch (:560-561)
+                self.records.append(up)
+                f = self.conv_bn(lat_in, dec.fpn_in[i][0], dec.fpn_in[i][1], post_add=up.a)   # lateral + add (:557-563)
+                levels.append(self.conv_bn(f, dec.fpn_out[i][0][0], dec.fpn_out[i][0][1]))
+            levels.reverse()                                # [P2 .. P5]
+            _, h2, w2, _ = levels[0].t.shape
+            fusion = [levels[0]]
+            for lv in levels[1:]:
+                ur = UpsampleRec(self, lv, h2, w2)
+                self.records.append(ur)
+                fusion.append(ur.a)
+            x = self.conv_bn(fusion, dec.conv_last[0][0], dec.conv_last[0][1])
+            cls = ClassifierRec(self, x, self.convs[id(dec.conv_last[1])])
+            self.records.append(cls)
+            self.logits = cls.logits
         else:
             raise NotImplementedError("decoder %s is not built on the B200 engine yet" % type(dec).__name__)
         self.p_drop = (p_drop_main, p_drop_ds)
@@ -545,7 +577,7 @@ class StemRec:
         P.bwd.append(P.on_side(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3))))
 
 
-def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, chanmul):
+def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, chanmul, res_after_relu=False):
     m = bns.mod
     C = bns.C
     st = bns.stats
@@ -571,7 +603,7 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
                                              bns.scale, bns.shift, running=running, update_running=upd, count_dev=cdev))
     if out is not None:
         P.fwd.append(lambda: ops.bn_apply(y, bns.scale, bns.shift, out, relu=relu, res=res, rscale=rscale, rshift=rshift,
-                                          chanmul=chanmul))
+                                          chanmul=chanmul, res_after_relu=res_after_relu))
 
 
 def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from_y=False):
@@ -620,8 +652,10 @@ class ConvBNRec:
     Reference: Bottleneck/BasicBlock.forward (models/resnet.py:37-53,72-92), conv3x3_bn_relu (models/models.py:160-167),
     PPM branches / conv_last (models/models.py:443-462)."""
 
-    def __init__(self, P, xs, cw, bns, relu, res, chanmul, apply):
+    def __init__(self, P, xs, cw, bns, relu, res, chanmul, apply, post_add=None):
         self.P, self.xs, self.cw, self.bns, self.relu, self.res, self.chanmul, self.apply = P, xs, cw, bns, relu, res, chanmul, apply
+        self.post_add = post_add
+        assert post_add is None or (res is None and relu and apply and chanmul is None)
         srcs = [x.t for x in xs]
         assert sum(s.shape[3] for s in srcs) == cw.I
         self.geom, ho, wo = P._conv_geom(srcs, cw)
@@ -642,7 +676,10 @@ class ConvBNRec:
                 r = res.t
             elif isinstance(res, ConvBNRec):
                 r, rs, rb = res.y, res.bns.scale, res.bns.shift
-            _emit_bn_forward(P, bns, self.mode, self.count, y, self.a.t, relu, r, rs, rb, chanmul)
+            if post_add is not None:
+                r = post_add.t
+            _emit_bn_forward(P, bns, self.mode, self.count, y, self.a.t, relu, r, rs, rb, chanmul,
+                             res_after_relu=post_add is not None)
         else:
             self.a = None
             _emit_bn_forward(P, bns, self.mode, self.count, y, None, False, None, None, None, None)
@@ -657,6 +694,10 @@ class ConvBNRec:
         dy = torch.empty_like(self.y)
         dres = None
         ds_rec = None
+        if self.post_add is not None:
+            # d(out)/d(post_add) = identity: the top-down branch reads the very same gradient tensor (no copy)
+            assert self.post_add.g is None and not self.post_add.gw, "post-add input must have a single consumer"
+            self.post_add.g, self.post_add.gw = g, True
         if isinstance(self.res, Act):
             dres, acc = P.grad_target(self.res)
             assert not acc, "identity shortcut must be the first gradient contribution of the block input"

@@ -7,8 +7,8 @@ and, for `SegmentationModule`, the backward as well — is a schedule of sm_100a
 `mit_semseg.engine.program` (implicit-GEMM convolutions on tcgen05, fused BN/ReLU/residual, PPM cascade with a
 virtual concat, fused log-softmax/NLL/accuracy).  There is no PyTorch-operator fallback.
 
-Supported on the engine in this build: resnet18/50/101 (+dilated) encoders; ppm, ppm_deepsup, c1, c1_deepsup
-decoders.  Other reference arch names are recognised and raise NotImplementedError with an explanation
+Supported on the engine in this build: resnet18/50/101 (+dilated) encoders; ppm, ppm_deepsup, c1, c1_deepsup,
+upernet, upernet_lite decoders.  Other reference arch names are recognised and raise NotImplementedError with an explanation
 (unknown names raise the reference's Exception('Architecture undefined!')).
 """
 from functools import partial
@@ -99,10 +99,10 @@ class ModelBuilder:
             net_decoder = PPM(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax)
         elif arch == 'ppm_deepsup':
             net_decoder = PPMDeepsup(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax)
-        elif arch in ('upernet_lite', 'upernet'):
-            raise NotImplementedError(
-                "decoder '%s' is part of the reference API but not yet built on the B200 engine "
-                "(next row after the PPM path; see DESIGN.md)" % arch)
+        elif arch == 'upernet_lite':
+            net_decoder = UPerNet(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax, fpn_dim=256)
+        elif arch == 'upernet':
+            net_decoder = UPerNet(num_class=num_class, fc_dim=fc_dim, use_softmax=use_softmax, fpn_dim=512)
         else:
             raise Exception('Architecture undefined!')
         net_decoder.apply(ModelBuilder.weights_init)
@@ -229,3 +229,39 @@ class PPMDeepsup(_Decoder):
         self.conv_last = _ppm_head(fc_dim, pool_scales, num_class)
         self.conv_last_deepsup = nn.Conv2d(fc_dim // 4, num_class, 1, 1, 0)
         self.dropout_deepsup = nn.Dropout2d(0.1)
+
+
+class UPerNet(_Decoder):
+    """Reference models.py:499-586: PPM on conv5 (1x1 conv AFTER the up-sampling) -> top-down FPN with lateral 1x1 convs
+    -> all levels up-sampled to the 1/4-resolution map, concatenated, fused by a 3x3 conv -> classifier."""
+
+    def __init__(self, num_class=150, fc_dim=4096, use_softmax=False, pool_scales=(1, 2, 3, 6),
+                 fpn_inplanes=(256, 512, 1024, 2048), fpn_dim=256):
+        super().__init__()
+        self.use_softmax = use_softmax
+        self.pool_scales = tuple(pool_scales)
+        # construction order = the reference's (same RNG stream for the default initialisers)
+        ppm_pooling, ppm_conv = [], []
+        for scale in pool_scales:
+            ppm_pooling.append(nn.AdaptiveAvgPool2d(scale))
+            ppm_conv.append(nn.Sequential(
+                nn.Conv2d(fc_dim, 512, kernel_size=1, bias=False),
+                BatchNorm2d(512),
+                nn.ReLU(inplace=True)))
+        self.ppm_pooling = nn.ModuleList(ppm_pooling)
+        self.ppm_conv = nn.ModuleList(ppm_conv)
+        self.ppm_last_conv = conv3x3_bn_relu(fc_dim + len(pool_scales) * 512, fpn_dim, 1)
+        fpn_in = []
+        for fpn_inplane in fpn_inplanes[:-1]:
+            fpn_in.append(nn.Sequential(
+                nn.Conv2d(fpn_inplane, fpn_dim, kernel_size=1, bias=False),
+                BatchNorm2d(fpn_dim),
+                nn.ReLU(inplace=True)))
+        self.fpn_in = nn.ModuleList(fpn_in)
+        fpn_out = []
+        for _ in range(len(fpn_inplanes) - 1):
+            fpn_out.append(nn.Sequential(conv3x3_bn_relu(fpn_dim, fpn_dim, 1)))
+        self.fpn_out = nn.ModuleList(fpn_out)
+        self.conv_last = nn.Sequential(
+            conv3x3_bn_relu(len(fpn_inplanes) * fpn_dim, fpn_dim, 1),
+            nn.Conv2d(fpn_dim, num_class, kernel_size=1))

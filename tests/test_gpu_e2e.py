@@ -251,3 +251,42 @@ def test_modules_called_on_their_own_match_the_fused_path():
         assert probs.shape == (2, 150, 96, 128) and (probs.sum(1) - 1).abs().max().item() < 1e-3
         fused = seg({"img_data": x}, segSize=(96, 128))
         assert (probs - fused).abs().max().item() <= 2e-2
+
+
+def test_upernet_resnet50_backward_wiring_and_train_loss():
+    """non-dilated ResNet (stride-2 stages through parity planes) + UPerNet (PPM with the 1x1 conv
+    after the up-sampling, FPN lateral 1x1 + top-down add, 4-level fusion over a virtual concat), labels at 1/4."""
+    from mit_semseg.engine.program import SegProgram
+    from oracle import segnet_oracle as O
+
+    def run(bn_eval):
+        seg, esd, dsd, ds = _build("resnet50", "upernet", 2048, residual_gain=0.25)
+        seg.cuda().train()
+        if bn_eval:
+            for m in seg.modules():
+                if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                    m.eval()
+        feed = O.synth_batch(2, 128, 128, 4, 2)
+        prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
+        prog.load_inputs(feed["img_data"].cuda(), feed["seg_label"].cuda())
+        prog.run_eager()
+        torch.cuda.synchronize()
+        e = {k: v.clone().requires_grad_(v.is_floating_point() and ("running" not in k)) for k, v in esd.items()}
+        d = {k: v.clone().requires_grad_(v.is_floating_point() and ("running" not in k)) for k, v in dsd.items()}
+        l_ref, a_ref = O.segmentation_forward(feed, e, d, "resnet50", "upernet", O.BNState(not bn_eval, emulate="bf16"), None)
+        l_ref.backward()
+        grads = prog.param_grads()
+        rels = {}
+        for prefix, net, sd in (("enc.", seg.encoder, e), ("dec.", seg.decoder, d)):
+            for name, p in net.named_parameters():
+                rels[prefix + name] = _rel(grads[p].float().cpu(), sd[name].grad)
+        print("upernet bn_eval=%s loss %.5f vs %.5f; grad rel median %.4f max %.4f (%s)" % (
+            bn_eval, prog.out[0].item(), l_ref.item(), statistics.median(rels.values()), max(rels.values()),
+            max(rels, key=rels.get)))
+        return prog.out[0].item(), l_ref.item(), rels
+
+    loss, ref, rels = run(bn_eval=True)
+    assert abs(loss - ref) <= 3e-3 * abs(ref)
+    assert max(rels.values()) <= 0.12 and statistics.median(rels.values()) <= 0.03, max(rels, key=rels.get)
+    loss, ref, rels = run(bn_eval=False)
+    assert abs(loss - ref) <= 5e-3 * abs(ref)
