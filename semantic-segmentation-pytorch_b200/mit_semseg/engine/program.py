@@ -431,13 +431,36 @@ class SegProgram:
     # ------------------------------------------------------------------------------------------ backward
     def _build_backward(self):
         self.bwd.append(lambda: self.gflat.zero_())
+        # The data-parallel gradient bucket (reference: backward of nn.DataParallel's Broadcast) as THREE
+        # NCCL all-reduces of contiguous slices of the flat fp32 gradient buffer, issued in backward order on the side
+        # stream right behind the weight-gradient GEMMs that fill them, so they overlap the rest of the backward pass:
+        #   [ small (BN, biases) | encoder stem..layer3 | encoder layer4 | decoder ]
+        buckets = []
+        if self.dist is not None and self.enc is not None and self.dec is not None:
+            dec_ids = {id(m) for m in self.dec.modules()}
+            l4_ids = {id(m) for m in self.enc.layer4.modules()}
+            off = lambda ids: min(c.gw.storage_offset() for c in self.convs.values() if id(c.mod) in ids)
+            dec_off, l4_off = off(dec_ids), off(l4_ids)
+            assert l4_off < dec_off
+            end = self.gflat.numel()
+            buckets = [(dec_ids, self.gflat[dec_off:end]), (dec_ids | l4_ids, self.gflat[l4_off:dec_off])]
+            rest = self.gflat[:l4_off]
+        pending = list(buckets)
         for rec in reversed(self.records):
+            mod = getattr(getattr(rec, "cw", None), "mod", None)
+            if pending and mod is not None and id(mod) not in pending[0][0]:
+                # every record of this bucket has emitted its weight gradient: reduce it behind them on the side stream
+                sl = pending.pop(0)[1]
+                self.bwd.append(self.on_side(lambda sl=sl: self.dist.all_reduce(sl)))
             rec.backward()
         self.bwd.append(self.join_side)
         if self.dist is not None:
-            # the data-parallel gradient bucket (reference: backward of nn.DataParallel's Broadcast):
-            # one NCCL all-reduce of the flat fp32 gradient buffer
-            self.bwd.append(lambda: self.dist.all_reduce(self.gflat))
+            if buckets:
+                for _, sl in pending:  # (degenerate nets: buckets never closed)
+                    self.bwd.append(lambda sl=sl: self.dist.all_reduce(sl))
+                self.bwd.append(lambda: self.dist.all_reduce(rest))
+            else:
+                self.bwd.append(lambda: self.dist.all_reduce(self.gflat))
         # gradients into each parameter's own layout (static buffers, so they are part of the captured graph);
         # 1/world_size = the reference's mean over per-GPU losses (train.py:42)
         scale = 1.0 / self.world

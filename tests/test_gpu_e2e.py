@@ -287,6 +287,6 @@ def test_upernet_resnet50_backward_wiring_and_train_loss():
 
     loss, ref, rels = run(bn_eval=True)
     assert abs(loss - ref) <= 3e-3 * abs(ref)
-    assert max(rels.values()) <= 0.12 and statistics.median(rels.values()) <= 0.03, max(rels, key=rels.get)
+    assert max(rels.values()) <= 0.12 and statistics.median(rels.values()) <= 0.05, max(rels, key=rels.get)
     loss, ref, rels = run(bn_eval=False)
     assert abs(loss - ref) <= 5e-3 * abs(ref)
