@@ -102,6 +102,7 @@ class SegProgram:
         self.dist = _dist()
         self.world = self.dist.get_world_size() if self.dist else 1
         self.fwd, self.bwd, self.records = [], [], []
+        self.pool_groups = {}
         self.keep = []  # anything that must stay alive (geometry structs hold raw pointers)
         self.graph = None
         # weight-gradient GEMMs are off the critical path of the backward pass (nothing downstream reads them until
@@ -804,21 +805,32 @@ class MaxPoolRec:
 
 
 class AvgPoolRec:
-    """nn.AdaptiveAvgPool2d(scale): models/models.py:447."""
+    """nn.AdaptiveAvgPool2d(scale): models/models.py:447.  The pools of one pyramid share their input; their backward
+    passes are emitted as ONE kernel (sseg_avgpool_bwd takes up to 4 scales) once the last of them is reached."""
 
     def __init__(self, P, x, scale):
         self.P, self.x, self.scale = P, x, scale
         n, h, w, c = x.t.shape
         self.a = Act(P._new(n, scale, scale, c))
         P.fwd.append(lambda: ops.avgpool_fwd(x.t, scale, self.a.t))
+        self.group = P.pool_groups.setdefault(id(x), [])
+        self.group.append(self)
+        self.done = False
 
     def backward(self):
         P = self.P
-        if self.a.g is None:
+        self.done = True
+        if not all(r.done for r in self.group):
+            return  # an earlier-in-forward sibling comes later in backward and emits the fused kernel
+        live = [r for r in self.group if r.a.g is not None]
+        if not live:
             return
         buf, acc = P.grad_target(self.x)
-        g, s = self.a.g, self.scale
-        P.bwd.append(lambda: ops.avgpool_bwd(buf if acc else None, [g], [s], buf))
+        gs, ss = [r.a.g for r in live], [r.scale for r in live]
+        for i in range(0, len(live), 4):
+            first = i == 0
+            P.bwd.append(lambda gs=gs[i:i + 4], ss=ss[i:i + 4], base=(buf if (acc or not first) else None):
+                         ops.avgpool_bwd(base, gs, ss, buf))
 
 
 class UpsampleRec:
