@@ -170,7 +170,8 @@ def api_case():
     """State-dict keys/shapes and seed-304 initialisation checksums of the reference builders."""
     out = {}
     for enc_arch, dec_arch, fc in (("resnet50dilated", "ppm_deepsup", 2048), ("resnet18dilated", "ppm_deepsup", 512),
-                                   ("resnet101", "c1_deepsup", 2048), ("resnet50", "ppm", 2048), ("resnet18", "c1", 512)):
+                                   ("resnet101", "c1_deepsup", 2048), ("resnet50", "ppm", 2048), ("resnet18", "c1", 512),
+                                   ("resnet50", "upernet", 2048), ("resnet18", "upernet_lite", 512)):
         torch.manual_seed(304)
         enc, dec = build_ref(enc_arch, dec_arch, fc)
         rec = {"enc_keys": {k: list(v.shape) for k, v in enc.state_dict().items()},
@@ -188,6 +189,9 @@ def api_case():
 
 if __name__ == "__main__":
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "api":
+        api_case()
+        sys.exit(0)
     train_case("train_r50dilated_ppm_deepsup_96", "resnet50dilated", "ppm_deepsup", 2048, 2, 96, 8,
                ["enc.conv1.weight", "enc.bn1.weight", "enc.layer2.0.conv2.weight", "enc.layer3.1.conv2.weight",
                 "enc.layer4.2.conv3.weight", "dec.conv_last.0.weight", "dec.conv_last.4.bias", "dec.ppm.0.2.weight",

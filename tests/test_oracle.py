@@ -188,7 +188,8 @@ def _build_mine(enc_arch, dec_arch, fc):
 
 
 @pytest.mark.parametrize("combo,fc", [("resnet50dilated+ppm_deepsup", 2048), ("resnet18dilated+ppm_deepsup", 512),
-                                      ("resnet101+c1_deepsup", 2048), ("resnet50+ppm", 2048), ("resnet18+c1", 512)])
+                                      ("resnet101+c1_deepsup", 2048), ("resnet50+ppm", 2048), ("resnet18+c1", 512),
+                                      ("resnet50+upernet", 2048), ("resnet18+upernet_lite", 512)])
 def test_module_tree_matches_reference_state_dict_init_and_hparams(combo, fc):
     enc_arch, dec_arch = combo.split("+")
     ref = API[combo]
