@@ -86,6 +86,10 @@ def segmentation_inference(seg, img, seg_size):
         raise RuntimeError("inference (segSize=...) requires a decoder built with use_softmax=True")
     prog = get_program(seg, img.shape, seg_size=tuple(seg_size), with_grad=False, capture=False)
     prog.load_inputs(img)
+    # image sizes vary during evaluation, so a program is only captured into a CUDA graph once its shape recurs
+    prog.uses = getattr(prog, "uses", 0) + 1
+    if prog.uses == 2 and prog.graph is None:
+        prog.capture()
     prog.run()
     return prog.probs.clone()
 
