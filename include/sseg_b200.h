@@ -103,6 +103,18 @@ int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld,
                     sseg_stream_t stream);
 
 /*
+ * Data gradient with the BN-backward reduction of the PRODUCER layer fused into the epilogue.  `out` is the gradient
+ * w.r.t. the producer's output a = relu(y*fscale + fshift); while the tile is still on chip the epilogue also accumulates
+ *     s1[c] += sum g',   s2_raw[c] += sum g' * y,     g' = out * [y*fscale + fshift > 0]
+ * (caller zeroes s1/s2_raw; y: the producer's saved conv output, same n,h,w as out, c >= cout). This replaces
+ * sseg_bn_bwd_reduce for layers with a single consumer and no shortcut; s2_raw is converted to sum g'*xhat by
+ * sseg_bn_bwd_apply(..., s2_raw = 1) / sseg_bn_bwd_peer_sum(..., s2_raw = 1).
+ */
+int sseg_conv_igemm_bnbwd(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
+                          const sseg_act_t* addend, const sseg_act_t* y, const float* fscale, const float* fshift,
+                          float* s1, float* s2_raw, sseg_stream_t stream);
+
+/*
  * Weight gradient of the same convolution (autograd of nn.Conv2d w.r.t. weight):
  *   dw[co][tap_koff[t] + ci] += sum_{n,h,w} dy[n,h,w,co] * X_t[n, h+dh_t, w+dw_t, ci]
  * GEMM with K = pixels (both operands MN-major in shared memory), split over pixels across CTAs and
@@ -190,11 +202,14 @@ int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shi
 int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
                        const float* invstd, const float* scale, const float* fshift, const float* chanmul, float* s1,
                        float* s2, long P, long pix_per_img, int C, sseg_stream_t stream);
-/* pass 2: dy = scale*(g' - s1/M - xhat*s2/M) (eval_mode: dy = scale*g'); dres (optional) = g' */
+/* pass 2: dy = scale*(g' - s1/M - xhat*s2/M) (eval_mode: dy = scale*g'); dres (optional) = g'.
+ * s2_raw = 1: s2 holds sum g'*y (sseg_conv_igemm_bnbwd); it is converted as invstd*(s2 - mean*s1) and the converted
+ * value (= dgamma) is stored to dgamma_out (optional). */
 int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
                       const float* invstd, const float* scale, const float* fshift, const float* chanmul, const float* s1,
                       const float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
-                      long dres_ld, long P, long pix_per_img, int C, int eval_mode, sseg_stream_t stream);
+                      long dres_ld, long P, long pix_per_img, int C, int eval_mode, int s2_raw, float* dgamma_out,
+                      sseg_stream_t stream);
 
 /* ---- SyncBN over NVLink peer memory (world_size > 1) ------------------------------------- */
 /* One cudaMalloc'ed, zero-initialised arena per rank, exported with CUDA IPC (64-byte handle) and mapped by the peers.
@@ -216,7 +231,8 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
 /* Backward: pool [s1 C | s2 C] partials at part_off over the ranks -> s1_tot, s2_tot; dbeta = s1_tot/world,
  * dgamma = s2_tot/world (the gradient-bucket all-reduce sums them over ranks again). */
 int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
-                         float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, int C, sseg_stream_t stream);
+                         float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
+                         int s2_raw, int C, sseg_stream_t stream);
 
 /* ---- pooling / resize ------------------------------------------------------------------- */
 /* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109). Dense bf16 NHWC; idx (1 byte / output element) feeds the backward. */

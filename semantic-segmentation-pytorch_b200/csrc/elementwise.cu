@@ -375,6 +375,10 @@ struct BnBwdParams {
   int C;
   int eval_mode;  // statistics were constants (running stats): dy = scale * g'
   int cgb, rows;
+  // s2 holds RAW sums (sum g'*y, from the fused dgrad epilogue) instead of sum g'*xhat: the kernel converts
+  // s2 = invstd * (s2_raw - mean * s1) on the fly and block column 0 stores the converted value to dgamma_out
+  int s2_raw;
+  float* dgamma_out;
 };
 
 template <bool kApply>
@@ -398,10 +402,16 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
     const float inv_m = 1.f / (p.count_dev ? *p.count_dev : p.count_host);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
+      float s2v = 0.f;
+      if (p.s2 != nullptr && active) {
+        s2v = p.s2[c0 + e];
+        if (p.s2_raw) s2v = inv[e] * (s2v - mu[e] * p.s1[c0 + e]);
+      }
+      if (p.s2_raw && p.dgamma_out != nullptr && active && blockIdx.x == 0 && trow == 0) p.dgamma_out[c0 + e] = s2v;
       if (p.eval_mode) {
         ka[e] = fs[e], kb[e] = 0.f, kc[e] = 0.f;
       } else {
-        const float t = fs[e] * inv[e] * p.s2[c0 + e] * inv_m;
+        const float t = fs[e] * inv[e] * s2v * inv_m;
         ka[e] = fs[e], kb[e] = -t, kc[e] = t * mu[e] - fs[e] * p.s1[c0 + e] * inv_m;
       }
     }
@@ -1060,7 +1070,8 @@ int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shi
 static int fill_bwd(BnBwdParams& p, const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld,
                     const float* mean, const float* invstd, const float* scale, const float* fshift, const float* chanmul,
                     float* s1, float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
-                    long dres_ld, long P, long pix_per_img, int C, int eval_mode, BnTiling* t, bool reduce = false) {
+                    long dres_ld, long P, long pix_per_img, int C, int eval_mode, BnTiling* t, bool reduce = false,
+                    int s2_raw = 0, float* dgamma_out = nullptr) {
   SSEG_REQUIRE(g && C % 8 == 0 && g_ld % 8 == 0 && (!a || a_ld % 8 == 0) && (!y || y_ld % 8 == 0),
                "sseg_bn_bwd: bad argument (channels and strides must be multiples of 8)");
   SSEG_REQUIRE(a == nullptr || fshift == nullptr, "sseg_bn_bwd: pass either the saved output `a` or fshift, not both");
@@ -1068,7 +1079,7 @@ static int fill_bwd(BnBwdParams& p, const void* g, long g_ld, const void* a, lon
   *t = bn_tiling(P, C, reduce);
   p = BnBwdParams{(const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)a, a_ld, (const __nv_bfloat16*)y, y_ld, mean,
                   invstd, scale, fshift, chanmul, s1, s2, count_dev, count_host, (__nv_bfloat16*)dy, dy_ld,
-                  (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode, t->cgb, t->rows};
+                  (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode, t->cgb, t->rows, s2_raw, dgamma_out};
   return 0;
 }
 
@@ -1088,13 +1099,15 @@ int sseg_bn_bwd_reduce(const void* g, long g_ld, const void* a, long a_ld, const
 int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
                       const float* invstd, const float* scale, const float* fshift, const float* chanmul, const float* s1,
                       const float* s2, const float* count_dev, float count_host, void* dy, long dy_ld, void* dres,
-                      long dres_ld, long P, long pix_per_img, int C, int eval_mode, sseg_stream_t st) {
+                      long dres_ld, long P, long pix_per_img, int C, int eval_mode, int s2_raw, float* dgamma_out,
+                      sseg_stream_t st) {
   BnBwdParams p;
   BnTiling t;
   int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, fshift, chanmul, const_cast<float*>(s1),
                     const_cast<float*>(s2), count_dev, count_host, dy, dy_ld, dres, dres_ld, P, pix_per_img, C, eval_mode,
-                    &t);
+                    &t, false, s2_raw, dgamma_out);
   if (rc) return rc;
+  SSEG_REQUIRE(!s2_raw || (s1 && s2 && mean && invstd), "sseg_bn_bwd_apply: raw s2 needs s1, mean and invstd");
   SSEG_REQUIRE(dy && scale && dy_ld % 8 == 0 && (!dres || dres_ld % 8 == 0), "sseg_bn_bwd_apply: bad argument");
   SSEG_REQUIRE(eval_mode || (y && mean && invstd && s1 && s2), "sseg_bn_bwd_apply: training mode needs y/mean/invstd/s1/s2");
   launch_k(bn_bwd_kernel<true>, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);

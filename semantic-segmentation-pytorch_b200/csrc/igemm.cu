@@ -42,6 +42,15 @@ struct IgemmParams {
   long add_row_stride, add_img_stride;
   float* stat_sum;
   float* stat_sqsum;
+  // fused BN-backward reduction of the layer that PRODUCED the tensor whose gradient this launch writes (dgrad):
+  //   g' = out * [bw_y * bw_fscale + bw_fshift > 0] ;  bw_s1[c] += sum g' ;  bw_s2[c] += sum g' * bw_y
+  const __nv_bfloat16* bw_y;
+  int bw_ld;
+  long bw_row_stride, bw_img_stride;
+  const float* bw_fscale;
+  const float* bw_fshift;
+  float* bw_s1;
+  float* bw_s2;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -231,6 +240,35 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         if (col < p.cout) atomicAdd(p.stat_sum + col, s0), atomicAdd(p.stat_sqsum + col, q0);
         if (col + 1 < p.cout) atomicAdd(p.stat_sum + col + 1, s1), atomicAdd(p.stat_sqsum + col + 1, q1);
       }
+      if (p.bw_s1 != nullptr) {
+        // BN-backward partial sums of the producer layer, from the staged gradient tile and that layer's saved y
+        constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
+        const int cp = t % kPairs, slab = t / kPairs;
+        const int col = n0 + cp * 2;
+        if (col < p.cout) {
+          const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
+          const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          const uint8_t* base = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll 4
+          for (int r = 0; r < kRowsPerSlab; ++r) {
+            const int rr = slab * kRowsPerSlab + r;
+            const int rh = h0 + (rr >> p.bw_shift), rw = w0 + (rr & (p.BW - 1));
+            if (rh < p.H && rw < p.W) {
+              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + r * kPitch));
+              const __nv_bfloat16* yp = p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
+                                        static_cast<size_t>(rw) * p.bw_ld + col;
+              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yp));
+              const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
+              const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
+              a0 += g0, a1 += g1;
+              b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
+            }
+          }
+          atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
+          if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
+        }
+      }
       // coalesced store: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass
       constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
       const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
@@ -335,9 +373,10 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, bool others_den
 
 using namespace sseg;
 
-extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
-                               const sseg_act_t* out, int out_f32, const float* bias, const sseg_act_t* addend,
-                               float* stat_sum, float* stat_sqsum, sseg_stream_t stream_) {
+static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
+                           int out_f32, const float* bias, const sseg_act_t* addend, float* stat_sum, float* stat_sqsum,
+                           const sseg_act_t* bw_y, const float* bw_fscale, const float* bw_fshift, float* bw_s1,
+                           float* bw_s2, sseg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SSEG_REQUIRE(g != nullptr && out != nullptr && w_bf16 != nullptr, "sseg_conv_igemm: null argument");
   const int n_store = out->c;
@@ -391,9 +430,34 @@ extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, lo
     p.ld_addend = addend->ld, p.add_row_stride = addend->row_stride, p.add_img_stride = addend->img_stride;
   }
   p.stat_sum = stat_sum, p.stat_sqsum = stat_sqsum;
+  if (bw_y != nullptr) {
+    SSEG_REQUIRE(!out_f32 && bw_fscale && bw_fshift && bw_s1 && bw_s2, "sseg_conv_igemm_bnbwd: null argument");
+    SSEG_REQUIRE(bw_y->n == out->n && bw_y->h == out->h && bw_y->w == out->w && bw_y->c >= cout && cout % 2 == 0,
+                 "sseg_conv_igemm_bnbwd: y shape mismatch");
+    SSEG_REQUIRE(gh.flat == act_is_dense(*bw_y) || !gh.flat, "sseg_conv_igemm_bnbwd: y must be dense for 1x1 launches");
+    p.bw_y = static_cast<const __nv_bfloat16*>(bw_y->ptr);
+    p.bw_ld = bw_y->ld, p.bw_row_stride = bw_y->row_stride, p.bw_img_stride = bw_y->img_stride;
+    p.bw_fscale = bw_fscale, p.bw_fshift = bw_fshift, p.bw_s1 = bw_s1, p.bw_s2 = bw_s2;
+  }
   const int grid = gh.vn * p.tiles_h * p.tiles_w * p.n_tiles;
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);
+}
+
+extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                               const sseg_act_t* out, int out_f32, const float* bias, const sseg_act_t* addend,
+                               float* stat_sum, float* stat_sqsum, sseg_stream_t stream) {
+  return conv_igemm_impl(g, w_bf16, w_ld, cout, out, out_f32, bias, addend, stat_sum, stat_sqsum, nullptr, nullptr, nullptr,
+                         nullptr, nullptr, stream);
+}
+
+extern "C" int sseg_conv_igemm_bnbwd(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                                     const sseg_act_t* out, const sseg_act_t* addend, const sseg_act_t* y,
+                                     const float* fscale, const float* fshift, float* s1, float* s2_raw,
+                                     sseg_stream_t stream) {
+  SSEG_REQUIRE(y != nullptr, "sseg_conv_igemm_bnbwd: y required");
+  return conv_igemm_impl(g, w_bf16, w_ld, cout, out, 0, nullptr, addend, nullptr, nullptr, y, fscale, fshift, s1, s2_raw,
+                         stream);
 }
 
 // =====================================================================================================

@@ -104,7 +104,8 @@ __global__ void bn_running_from_tmp_kernel(const float* tmp_mean, const float* t
 __global__ void __launch_bounds__(256) bn_bwd_peer_sum_kernel(const PeerTable pt, long part_off, long flag_off,
                                                               const int* step_ptr, float* __restrict__ s1_tot,
                                                               float* __restrict__ s2_tot, float* __restrict__ dbeta,
-                                                              float* __restrict__ dgamma, int C) {
+                                                              float* __restrict__ dgamma, const float* __restrict__ mean,
+                                                              const float* __restrict__ invstd, int s2_raw, int C) {
   pdl_sync();
   peer_handshake(pt, flag_off, *step_ptr);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,6 +115,7 @@ __global__ void __launch_bounds__(256) bn_bwd_peer_sum_kernel(const PeerTable pt
     a += __ldcv(pt.base[r] + part_off + c);
     b += __ldcv(pt.base[r] + part_off + C + c);
   }
+  if (s2_raw) b = invstd[c] * (b - mean[c] * a);  // partials were sum g'*y (fused dgrad epilogue): convert to sum g'*xhat
   s1_tot[c] = a, s2_tot[c] = b;
   const float inv_w = 1.f / (float)pt.world;
   dbeta[c] = a * inv_w, dgamma[c] = b * inv_w;
@@ -200,14 +202,16 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
 }
 
 int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
-                         float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, int C, sseg_stream_t st) {
+                         float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
+                         int s2_raw, int C, sseg_stream_t st) {
   PeerTable t;
   int rc = make_table(&t, bases, world, rank, "sseg_bn_bwd_peer_sum");
   if (rc) return rc;
   SSEG_REQUIRE(step && s1_tot && s2_tot && dbeta && dgamma && C > 0, "sseg_bn_bwd_peer_sum: null");
+  SSEG_REQUIRE(!s2_raw || (mean && invstd), "sseg_bn_bwd_peer_sum: raw partials need mean and invstd");
   count_launch(1);
   return check_cuda(launch_k(bn_bwd_peer_sum_kernel, dim3((C + 255) / 256), dim3(256), 0, (cudaStream_t)st, t, part_off,
-                             flag_off, step, s1_tot, s2_tot, dbeta, dgamma, C),
+                             flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean, invstd, s2_raw, C),
                     "bn_bwd_peer_sum_kernel");
 }
 

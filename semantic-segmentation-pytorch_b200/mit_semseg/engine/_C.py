@@ -86,6 +86,7 @@ _p = c_void_p
 _ip = POINTER(c_int)
 _SIGNATURES = {
     "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), c_int, _p, POINTER(Act), _p, _p, _p],
+    "sseg_conv_igemm_bnbwd": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(Act), _p, _p, _p, _p, _p],
     "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
     "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],
     "sseg_prep_conv_weights_batched": [_p, c_int, c_int, _p],
@@ -99,7 +100,7 @@ _SIGNATURES = {
     "sseg_bn_apply": [_p, c_long, _p, _p, _p, c_long, _p, _p, _p, _p, c_long, c_long, c_long, c_int, c_int, c_int, _p],
     "sseg_bn_bwd_reduce": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, c_long, c_long, c_int, _p],
     "sseg_bn_bwd_apply": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, _p, c_float, _p, c_long, _p,
-                          c_long, c_long, c_long, c_int, c_int, _p],
+                          c_long, c_long, c_long, c_int, c_int, c_int, _p, _p],
     "sseg_peer_alloc": [ctypes.c_size_t, POINTER(c_void_p), _p],
     "sseg_peer_open": [_p, POINTER(c_void_p)],
     "sseg_peer_close": [_p],
@@ -107,7 +108,7 @@ _SIGNATURES = {
     "sseg_peer_step": [_p, _p],
     "sseg_bn_finalize_peer": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, c_float, c_float, c_int, _p, _p,
                               _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p],
-    "sseg_bn_bwd_peer_sum": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, _p, _p, c_int, _p],
+    "sseg_bn_bwd_peer_sum": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, _p, _p, _p, _p, c_int, c_int, _p],
     "sseg_maxpool_fwd": [_p, c_int, c_int, c_int, c_int, _p, _p, _p],
     "sseg_maxpool_bwd": [_p, _p, _p, c_int, c_int, c_int, c_int, _p],
     "sseg_avgpool_fwd": [_p, c_long, c_int, c_int, c_int, c_int, c_int, _p, _p],

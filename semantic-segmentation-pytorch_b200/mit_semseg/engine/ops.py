@@ -63,6 +63,17 @@ def conv_igemm(geom, w_bf16, cout, out, n_store=None, bias=None, addend=None, st
     return out
 
 
+def conv_igemm_bnbwd(geom, w_bf16, cout, out, y, fscale, fshift, s1, s2_raw, addend=None):
+    """Data gradient into `out` + the producer layer's BN-backward partial sums (see sseg_conv_igemm_bnbwd)."""
+    assert out.dtype == torch.bfloat16 and w_bf16.dim() == 2 and w_bf16.stride(1) == 1
+    n_store = (cout + 7) // 8 * 8
+    o = act(out[..., :n_store])
+    a = act(addend) if addend is not None else None
+    _C.check(_C.lib().sseg_conv_igemm_bnbwd(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, o, a, act(y), _C.ptr(fscale),
+                                            _C.ptr(fshift), _C.ptr(s1), _C.ptr(s2_raw), _stream()))
+    return out
+
+
 def conv_wgrad(geom, dy, cout, dw):
     """dw[co, koff_t + ci] += sum_pixels dy[.., co] * x_t[.., ci]; dw: fp32 2-D [cout, K], pre-zeroed by the caller."""
     assert dw.dtype == torch.float32 and dw.dim() == 2 and dw.stride(1) == 1
@@ -159,10 +170,10 @@ def bn_finalize_peer(arena, stats_off, flag_off, step, gamma, beta, eps, momentu
                                             _C.ptr(scale), _C.ptr(shift), _C.ptr(count_out), scale.numel(), _stream()))
 
 
-def bn_bwd_peer_sum(arena, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgamma):
+def bn_bwd_peer_sum(arena, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean=None, invstd=None, s2_raw=False):
     _C.check(_C.lib().sseg_bn_bwd_peer_sum(arena.bases, arena.world, arena.rank, part_off, flag_off, _C.ptr(step),
-                                           _C.ptr(s1_tot), _C.ptr(s2_tot), _C.ptr(dbeta), _C.ptr(dgamma),
-                                           s1_tot.numel(), _stream()))
+                                           _C.ptr(s1_tot), _C.ptr(s2_tot), _C.ptr(dbeta), _C.ptr(dgamma), _C.ptr(mean),
+                                           _C.ptr(invstd), int(s2_raw), s1_tot.numel(), _stream()))
 
 
 def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None, chanmul=None, res_after_relu=False):
@@ -185,7 +196,7 @@ def bn_bwd_reduce(g, a, y, mean, invstd, s1, s2, chanmul=None, scale=None, fshif
 
 
 def bn_bwd_apply(g, a, y, mean, invstd, scale, s1, s2, count, dy, dres=None, chanmul=None, eval_mode=False,
-                 count_dev=None, fshift=None):
+                 count_dev=None, fshift=None, s2_raw=False, dgamma_out=None):
     P, ppi, g_ld = _pix(g)
     a_ld = _pix(a)[2] if a is not None else 0
     y_ld = _pix(y)[2] if y is not None else 0
@@ -193,7 +204,7 @@ def bn_bwd_apply(g, a, y, mean, invstd, scale, s1, s2, count, dy, dres=None, cha
     _C.check(_C.lib().sseg_bn_bwd_apply(_C.ptr(g), g_ld, _C.ptr(a), a_ld, _C.ptr(y), y_ld, _C.ptr(mean), _C.ptr(invstd),
                                         _C.ptr(scale), _C.ptr(fshift), _C.ptr(chanmul), _C.ptr(s1), _C.ptr(s2),
                                         _C.ptr(count_dev), float(count), _C.ptr(dy), _pix(dy)[2], _C.ptr(dres), dres_ld, P,
-                                        ppi, g.shape[3], int(eval_mode), _stream()))
+                                        ppi, g.shape[3], int(eval_mode), int(s2_raw), _C.ptr(dgamma_out), _stream()))
 
 
 def maxpool_fwd(x, out, idx):

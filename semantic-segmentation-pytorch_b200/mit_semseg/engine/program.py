@@ -40,10 +40,12 @@ def _dist():
 
 class Act:
     """An activation tensor (NHWC bf16) plus, during backward construction, its gradient buffer."""
-    __slots__ = ("t", "g", "gw")
+    __slots__ = ("t", "g", "gw", "uses", "producer")
 
     def __init__(self, t):
         self.t, self.g, self.gw = t, None, False
+        self.uses = 0          # number of consumers in the forward schedule
+        self.producer = None   # the ConvBNRec / StemRec that wrote it (if any)
 
 
 class ConvW:
@@ -103,6 +105,8 @@ class SegProgram:
         self.world = self.dist.get_world_size() if self.dist else 1
         self.fwd, self.bwd, self.records = [], [], []
         self.pool_groups = {}
+        import os as _os
+        self.fuse_bnbwd = _os.environ.get("SSEG_FUSE_BNBWD", "1") != "0"
         self.keep = []  # anything that must stay alive (geometry structs hold raw pointers)
         self.graph = None
         # weight-gradient GEMMs are off the critical path of the backward pass (nothing downstream reads them until
@@ -144,7 +148,7 @@ class SegProgram:
                                                                if c.mod.bias is not None)
         self.g_small = small
         self.gflat = torch.zeros((small + nf) if self.with_grad else 0, device=dev, dtype=torch.float32)
-        ns = sum(_pad(2 * b.C + 1, 4) for b in self.bns.values()) + 8
+        ns = sum(_pad(2 * b.C + 1, 4) + b.C for b in self.bns.values()) + 8   # + C: raw sum g'*y of the fused dgrad
         # with several ranks the statistics live in a peer-mapped arena (SyncBN without NCCL calls, csrc/peer.cu):
         # [per-BN sum|sqsum|count ... loss accumulators | per-BN s1|s2 partials ... | flags (int) | step (int)]
         self.peer = None
@@ -191,6 +195,8 @@ class SegProgram:
             b.stats = self.sflat[os_:os_ + 2 * b.C + 1]
             b.stats_off = os_
             os_ += _pad(2 * b.C + 1, 4)
+            b.s2y = self.sflat[os_:os_ + b.C]
+            os_ += b.C
             if self.peer is not None:
                 b.part = self.sflat[op_:op_ + 2 * b.C]  # [s1 | s2] partial sums of the backward pass
                 b.part_off, b.flag_off = op_, ofl
@@ -253,8 +259,10 @@ class SegProgram:
         """conv -> BN(train/eval) -> (+res) -> ReLU -> (*chanmul) (+post_add).  xs: Act or list of Acts (virtual concat).
         res: None | Act (identity shortcut) | ConvBNRec built with apply=False (projection shortcut).
         post_add: Act added AFTER the ReLU (FPN top-down path, models/models.py:561-563)."""
-        rec = ConvBNRec(self, xs if isinstance(xs, list) else [xs], self.convs[id(conv_mod)], self.bns[id(bn_mod)], relu,
-                        res, chanmul, apply, post_add)
+        xs = xs if isinstance(xs, list) else [xs]
+        for a in xs + [r for r in (res, post_add) if isinstance(r, Act)]:
+            a.uses += 1
+        rec = ConvBNRec(self, xs, self.convs[id(conv_mod)], self.bns[id(bn_mod)], relu, res, chanmul, apply, post_add)
         self.records.append(rec)
         return rec if not apply else rec.a
 
@@ -582,6 +590,8 @@ class StemRec:
         ho, wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
         self.y = P._new(N, ho, wo, 64)
         self.a = Act(P._new(N, ho, wo, 64))
+        self.a.producer = self
+        self.relu, self.res, self.post_add, self.chanmul, self.apply, self.fused = True, None, None, None, True, False
         self.mode = P._bn_mode(bns)
         self.count = N * ho * wo
         w = cw.mod.weight
@@ -596,7 +606,8 @@ class StemRec:
         if self.a.g is None:
             return
         dy = torch.empty_like(self.y)
-        _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, None, self.y, dy, None, None, mask_from_y=True)
+        _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, None, self.y, dy, None, None, mask_from_y=True,
+                          fused=self.fused)
         gw = self.cw.gw
         P.bwd.append(P.on_side(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3))))
 
@@ -630,13 +641,27 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
                                           chanmul=chanmul, res_after_relu=res_after_relu))
 
 
-def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from_y=False):
+def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from_y=False, fused=False):
     """g: gradient w.r.t. the layer output.  ReLU mask: `a` (saved output) if given, else recomputed from y when
     mask_from_y (layers without a shortcut), else the layer has no ReLU."""
     C = bns.C
     st = bns.stats
     sc = bns.scale
     fs = bns.shift if (mask_from_y and a is None) else None
+    if fused:
+        # the consumer's dgrad epilogue already accumulated s1 (= dbeta) and the raw sum g'*y (sseg_conv_igemm_bnbwd)
+        assert a is None and fs is not None and chanmul is None and dres is None
+        if mode == ops.BN_TRAIN_SYNC and P.peer is not None:
+            t1, t2, cnt = bns.tot[:C], bns.tot[C:2 * C], bns.tot[2 * C:2 * C + 1]
+            P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, t1, t2, bns.dbeta,
+                                                     bns.dgamma, mean=bns.mean, invstd=bns.invstd, s2_raw=True))
+            P.bwd.append(lambda: ops.bn_bwd_apply(g, None, y, bns.mean, bns.invstd, sc, t1, t2, count, dy, count_dev=cnt,
+                                                  fshift=fs))
+        else:
+            P.bwd.append(lambda: ops.bn_bwd_apply(g, None, y, bns.mean, bns.invstd, sc, bns.dbeta, bns.s2y, count, dy,
+                                                  eval_mode=(mode == ops.BN_EVAL), fshift=fs, s2_raw=True,
+                                                  dgamma_out=bns.dgamma))
+        return
     if mode == ops.BN_EVAL:
         P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, None, None, sc, None, None, 1.0, dy, dres=dres, chanmul=chanmul,
                                               eval_mode=True, fshift=fs))
@@ -693,8 +718,10 @@ class ConvBNRec:
         geom, wf, y = self.geom, cw.wf, self.y
         P.fwd.append(lambda: ops.conv_igemm(geom, wf, C, y, stat_sum=st[:C] if train else None,
                                             stat_sqsum=st[C:2 * C] if train else None))
+        self.fused = False  # set by the (single) consumer when its dgrad epilogue does this layer's BN-backward reduce
         if apply:
             self.a = Act(P._new(n, ho, wo, cw.O))
+            self.a.producer = self
             r = rs = rb = None
             if isinstance(res, Act):
                 r = res.t
@@ -731,7 +758,8 @@ class ConvBNRec:
         has_relu = self.apply and self.relu
         from_y = has_relu and self.res is None          # no shortcut: the mask is a function of y alone
         a = self.a.t if (has_relu and not from_y) else None
-        _emit_bn_backward(P, bns, self.mode, self.count, g, a, self.y, dy, dres, self.chanmul, mask_from_y=from_y)
+        _emit_bn_backward(P, bns, self.mode, self.count, g, a, self.y, dy, dres, self.chanmul, mask_from_y=from_y,
+                          fused=self.fused)
         if ds_rec is not None:
             ds_rec.backward(g_override=dres)
         # weight gradient: GEMM over pixels (sseg_conv_wgrad)
@@ -761,7 +789,22 @@ class ConvBNRec:
                     off += c
                 acc = False
             wd, I = cw.wd, cw.I
-            P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=I, addend=buf if acc else None))
+            prod = xs[0].producer if len(xs) == 1 else None
+            fuse = (P.fuse_bnbwd and prod is not None and not acc and xs[0].uses == 1 and prod.apply and prod.relu and
+                    prod.res is None and prod.post_add is None and prod.chanmul is None and I % 2 == 0 and
+                    not (prod.mode == ops.BN_TRAIN_SYNC and P.peer is None and P.dist is not None))
+            if fuse:
+                # single consumer, no shortcut: the BN-backward reduction of the producer rides in this dgrad's epilogue
+                prod.fused = True
+                pb = prod.bns
+                if prod.mode == ops.BN_TRAIN_SYNC and P.peer is not None:
+                    s1, s2 = pb.part[:pb.C], pb.part[pb.C:2 * pb.C]
+                else:
+                    s1, s2 = pb.dbeta, pb.s2y
+                py = prod.y
+                P.bwd.append(lambda: ops.conv_igemm_bnbwd(gd, wd, I, buf, py, pb.scale, pb.shift, s1, s2))
+            else:
+                P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=I, addend=buf if acc else None))
         else:
             x = xs[0]
             buf, acc = P.grad_target(x)
@@ -787,6 +830,7 @@ class MaxPoolRec:
 
     def __init__(self, P, x):
         self.P, self.x = P, x
+        x.uses += 1
         n, h, w, c = x.t.shape
         ho, wo = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
         self.a = Act(P._new(n, ho, wo, c))
@@ -810,6 +854,7 @@ class AvgPoolRec:
 
     def __init__(self, P, x, scale):
         self.P, self.x, self.scale = P, x, scale
+        x.uses += 1
         n, h, w, c = x.t.shape
         self.a = Act(P._new(n, scale, scale, c))
         P.fwd.append(lambda: ops.avgpool_fwd(x.t, scale, self.a.t))
@@ -838,6 +883,7 @@ class UpsampleRec:
 
     def __init__(self, P, x, h, w):
         self.P, self.x = P, x
+        x.uses += 1
         n, _, _, c = x.t.shape
         self.a = Act(P._new(n, h, w, c))
         P.fwd.append(lambda: ops.bilinear_fwd(x.t, self.a.t))
@@ -858,6 +904,7 @@ class ClassifierRec:
 
     def __init__(self, P, x, cw):
         self.P, self.x, self.cw = P, x, cw
+        x.uses += 1
         n, h, w, _ = x.t.shape
         self.ld = _pad(cw.O, 8) + 8
         self.logits = P._new(n, h, w, self.ld, dtype=torch.float32, zero=True)

@@ -183,3 +183,44 @@ def test_stride2_via_parity_planes(k):
         ops.conv_igemm(geom_d, wd, cin, planes[pl])
     gx_nhwc = gx.permute(0, 2, 3, 1)
     assert (dx.float() - gx_nhwc).abs().max().item() <= 2 ** -7 * gx_nhwc.abs().max().item()
+
+
+# ------------------------------------------------------------------ dgrad with the producer's BN-backward reduce fused
+@pytest.mark.parametrize("k,hw", [(1, 64), (3, 64), (3, 38)])
+def test_dgrad_with_fused_bn_backward_reduce(k, hw):
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(21)
+    n, cprod, cout_next = 2, 128, 256          # producer layer has 128 channels; the consumer conv maps 128 -> 256
+    y = torch.randn(n, hw, hw, cprod, device="cuda", generator=g).bfloat16()       # producer's saved conv output
+    fscale = torch.rand(cprod, device="cuda", generator=g) + 0.5
+    fshift = torch.randn(cprod, device="cuda", generator=g) * 0.3
+    dy_next = (torch.randn(n, hw, hw, cout_next, device="cuda", generator=g) * 0.1).bfloat16()
+    w = (torch.randn(cout_next, cprod, k, k, device="cuda", generator=g) * 0.05).bfloat16()
+    wd = torch.zeros(cprod, k * k * cout_next, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weight(w.float().contiguous(), None, wd, o_pad=cout_next)
+    dh, dw = ops.conv_taps(k, 1)
+    gd = ops.make_geom([dy_next], ([-v for v in dh], [-v for v in dw]), tap_koff=[t * cout_next for t in range(k * k)])
+    gout = torch.empty(n, hw, hw, cprod, device="cuda", dtype=torch.bfloat16)
+    s1, s2 = torch.zeros(cprod, device="cuda"), torch.zeros(cprod, device="cuda")
+    ops.conv_igemm_bnbwd(gd, wd, cprod, gout, y, fscale, fshift, s1, s2)
+    ref_g = torch.empty_like(gout)
+    ops.conv_igemm(gd, wd, cprod, ref_g, n_store=cprod)
+    torch.cuda.synchronize()
+    assert torch.equal(gout, ref_g)
+    mask = (y.float() * fscale + fshift) > 0
+    gp = ref_g.float() * mask
+    r1, r2 = gp.sum(dim=(0, 1, 2)), (gp * y.float()).sum(dim=(0, 1, 2))
+    assert (s1 - r1).abs().max().item() <= 1e-3 * r1.abs().max().item() + 1e-4
+    assert (s2 - r2).abs().max().item() <= 1e-3 * r2.abs().max().item() + 1e-4
+    # raw -> xhat conversion inside bn_bwd_apply reproduces the two-pass result (dy and dgamma)
+    mean = torch.randn(cprod, device="cuda", generator=g) * 0.2
+    invstd = torch.rand(cprod, device="cuda", generator=g) + 0.5
+    s1b, s2b = torch.zeros(cprod, device="cuda"), torch.zeros(cprod, device="cuda")
+    ops.bn_bwd_reduce(ref_g, None, y, mean, invstd, s1b, s2b, scale=fscale, fshift=fshift)
+    dya, dyb, dgam = torch.empty_like(y), torch.empty_like(y), torch.zeros(cprod, device="cuda")
+    cnt = n * hw * hw
+    ops.bn_bwd_apply(ref_g, None, y, mean, invstd, fscale, s1b, s2b, cnt, dya, fshift=fshift)
+    ops.bn_bwd_apply(gout, None, y, mean, invstd, fscale, s1, s2, cnt, dyb, fshift=fshift, s2_raw=True, dgamma_out=dgam)
+    torch.cuda.synchronize()
+    assert (dgam - s2b).abs().max().item() <= 2e-3 * s2b.abs().max().item() + 1e-3
+    assert (dya.float() - dyb.float()).abs().max().item() <= 2 ** -6 * dya.float().abs().max().item()
