@@ -241,7 +241,28 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         if (col + 1 < p.cout) atomicAdd(p.stat_sum + col + 1, s1), atomicAdd(p.stat_sqsum + col + 1, q1);
       }
       if (p.bw_s1 != nullptr) {
-        // BN-backward partial sums of the producer layer, from the staged gradient tile and that layer's saved y
+        // BN-backward partial sums of the producer layer. Its saved conv output y (same tile geometry) is first copied
+        // into shared memory with fully coalesced 16-byte loads (all loads of a thread in flight together), then the
+        // per-channel sums run from shared memory next to the staged gradient tile.
+        uint8_t* ytile = stg + 128 * kPitch;
+        {
+          constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow, kPasses = 128 / kRowsPerPass;
+          const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+          uint4 q[kPasses];
+#pragma unroll
+          for (int pass = 0; pass < kPasses; ++pass) {
+            const int r = pass * kRowsPerPass + r0;
+            const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+            q[pass] = make_uint4(0u, 0u, 0u, 0u);
+            if (rh < p.H && rw < p.W && n0 + seg * 8 < p.cout)
+              q[pass] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
+                                                             static_cast<size_t>(rw) * p.bw_ld + n0 + seg * 8));
+          }
+#pragma unroll
+          for (int pass = 0; pass < kPasses; ++pass)
+            *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = q[pass];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
         constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
         const int cp = t % kPairs, slab = t / kPairs;
         const int col = n0 + cp * 2;
@@ -249,21 +270,17 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
           const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
           const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
           float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-          const uint8_t* base = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
-#pragma unroll 4
+          const uint8_t* gbase = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+          const uint8_t* ybase = ytile + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll 8
           for (int r = 0; r < kRowsPerSlab; ++r) {
-            const int rr = slab * kRowsPerSlab + r;
-            const int rh = h0 + (rr >> p.bw_shift), rw = w0 + (rr & (p.BW - 1));
-            if (rh < p.H && rw < p.W) {
-              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + r * kPitch));
-              const __nv_bfloat16* yp = p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
-                                        static_cast<size_t>(rw) * p.bw_ld + col;
-              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(yp));
-              const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
-              const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
-              a0 += g0, a1 += g1;
-              b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
-            }
+            // rows outside the image hold zeros in the staged gradient tile: they contribute nothing
+            const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
+            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
+            const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
+            const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
+            a0 += g0, a1 += g1;
+            b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
           }
           atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
           if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
@@ -432,8 +449,9 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   p.stat_sum = stat_sum, p.stat_sqsum = stat_sqsum;
   if (bw_y != nullptr) {
     SSEG_REQUIRE(!out_f32 && bw_fscale && bw_fshift && bw_s1 && bw_s2, "sseg_conv_igemm_bnbwd: null argument");
-    SSEG_REQUIRE(bw_y->n == out->n && bw_y->h == out->h && bw_y->w == out->w && bw_y->c >= cout && cout % 2 == 0,
-                 "sseg_conv_igemm_bnbwd: y shape mismatch");
+    SSEG_REQUIRE(bw_y->n == out->n && bw_y->h == out->h && bw_y->w == out->w && bw_y->c >= cout && cout % 8 == 0 &&
+                     bw_y->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(bw_y->ptr) & 15) == 0,
+                 "sseg_conv_igemm_bnbwd: y shape / alignment mismatch");
     SSEG_REQUIRE(gh.flat == act_is_dense(*bw_y) || !gh.flat, "sseg_conv_igemm_bnbwd: y must be dense for 1x1 launches");
     p.bw_y = static_cast<const __nv_bfloat16*>(bw_y->ptr);
     p.bw_ld = bw_y->ld, p.bw_row_stride = bw_y->row_stride, p.bw_img_stride = bw_y->img_stride;
