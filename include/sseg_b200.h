@@ -195,6 +195,15 @@ int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_de
 int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
                   const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
                   long pix_per_img, int C, int relu, int res_after_relu, sseg_stream_t stream);
+/* sseg_bn_finalize(SSEG_BN_TRAIN) + sseg_bn_apply in ONE launch (single-GPU training: F.batch_norm semantics,
+ * lib/nn/modules/batchnorm.py:58-61): every thread derives scale/shift for its channels from (sum, sqsum, count);
+ * mean/invstd/scale/shift are also stored for the backward pass and the running statistics (optional) are updated. */
+int sseg_bn_finalize_apply(const float* sum, const float* sqsum, float count, const float* gamma, const float* beta,
+                           float eps, float momentum, float* running_mean, float* running_var, float* mean_out,
+                           float* invstd_out, float* scale_out, float* shift_out, const void* y, long y_ld, const void* res,
+                           long res_ld, const float* rscale, const float* rshift, const float* chanmul, void* out,
+                           long out_ld, long P, long pix_per_img, int C, int relu, int res_after_relu,
+                           sseg_stream_t stream);
 /* backward.  g' = g * chanmul * [ReLU active].  The ReLU mask comes from the saved layer output (a > 0) or, for layers
  * without a shortcut, is recomputed as (y*scale + fshift > 0) when `a` is NULL and `fshift` is given (one tensor less to
  * read); both NULL = the layer has no ReLU.

@@ -299,6 +299,12 @@ struct BnApplyParams {
   long pix_per_img;
   int C, relu, cgb, rows;
   int res_after_relu;  // out = relu(y*scale+shift) + res  (FPN lateral + top-down add) instead of relu(... + res)
+  // fused finalize (F.batch_norm training branch, SSEG_BN_TRAIN): when fin_sum != null every thread derives scale / shift
+  // for its 8 channels from the statistics instead of reading them, and block column 0 publishes mean / invstd / scale /
+  // shift (for the backward pass) and updates the running statistics - one kernel boundary less per layer.
+  const float *fin_sum, *fin_sqsum, *fin_gamma, *fin_beta;
+  float fin_count, fin_eps, fin_momentum;
+  float *fin_mean, *fin_invstd, *fin_scale, *fin_shift, *fin_running_mean, *fin_running_var;
 };
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const BnApplyParams p) {
   pdl_sync();
@@ -309,7 +315,23 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(const BnApplyParams p)
   float sc[8], sh[8], rs[8], rb[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
-    sc[e] = p.scale[c0 + e], sh[e] = p.shift[c0 + e];
+    if (p.fin_sum != nullptr) {
+      const int c = c0 + e;
+      const float s = p.fin_sum[c], mean = s / p.fin_count;
+      const float sumvar = p.fin_sqsum[c] - s * mean;
+      const float inv_std = rsqrtf(fmaxf(sumvar / p.fin_count, 0.f) + p.fin_eps);
+      const float g = p.fin_gamma ? p.fin_gamma[c] : 1.f, b = p.fin_beta ? p.fin_beta[c] : 0.f;
+      sc[e] = g * inv_std, sh[e] = b - mean * g * inv_std;
+      if (blockIdx.x == 0 && trow == 0) {
+        p.fin_mean[c] = mean, p.fin_invstd[c] = inv_std, p.fin_scale[c] = sc[e], p.fin_shift[c] = sh[e];
+        if (p.fin_running_mean != nullptr) {
+          p.fin_running_mean[c] = (1.f - p.fin_momentum) * p.fin_running_mean[c] + p.fin_momentum * mean;
+          p.fin_running_var[c] = (1.f - p.fin_momentum) * p.fin_running_var[c] + p.fin_momentum * sumvar / (p.fin_count - 1.f);
+        }
+      }
+    } else {
+      sc[e] = p.scale[c0 + e], sh[e] = p.shift[c0 + e];
+    }
     rs[e] = p.rscale ? p.rscale[c0 + e] : 1.f, rb[e] = p.rshift ? p.rshift[c0 + e] : 0.f;
   }
   const long stride = (long)gridDim.x * p.rows;
@@ -1055,16 +1077,43 @@ int sseg_bn_finalize(const float* sum, const float* sqsum, const float* count_de
   return check_cuda(cudaGetLastError(), "bn_finalize_kernel");
 }
 
+static int bn_apply_impl(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
+                         const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
+                         long pix_per_img, int C, int relu, int res_after_relu, const float* fin_sum,
+                         const float* fin_sqsum, const float* gamma, const float* beta, float count, float eps,
+                         float momentum, float* mean_out, float* invstd_out, float* scale_out, float* shift_out,
+                         float* running_mean, float* running_var, sseg_stream_t st) {
+  SSEG_REQUIRE(y && out && C % 8 == 0 && y_ld % 8 == 0 && out_ld % 8 == 0 && (!res || res_ld % 8 == 0),
+               "sseg_bn_apply: bad argument (channels and strides must be multiples of 8)");
+  SSEG_REQUIRE(fin_sum != nullptr || (scale && shift), "sseg_bn_apply: scale/shift required");
+  const BnTiling t = bn_tiling(P, C);
+  BnApplyParams p{(const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, rscale, rshift,
+                  chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu, t.cgb, t.rows, res_after_relu,
+                  fin_sum, fin_sqsum, gamma, beta, count, eps, momentum, mean_out, invstd_out, scale_out, shift_out,
+                  running_mean, running_var};
+  launch_k(bn_apply_kernel, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
+  LAUNCH_CHECK("bn_apply_kernel");
+}
+
 int sseg_bn_apply(const void* y, long y_ld, const float* scale, const float* shift, const void* res, long res_ld,
                   const float* rscale, const float* rshift, const float* chanmul, void* out, long out_ld, long P,
                   long pix_per_img, int C, int relu, int res_after_relu, sseg_stream_t st) {
-  SSEG_REQUIRE(y && scale && shift && out && C % 8 == 0 && y_ld % 8 == 0 && out_ld % 8 == 0 && (!res || res_ld % 8 == 0),
-               "sseg_bn_apply: bad argument (channels and strides must be multiples of 8)");
-  const BnTiling t = bn_tiling(P, C);
-  BnApplyParams p{(const __nv_bfloat16*)y, y_ld, scale, shift, (const __nv_bfloat16*)res, res_ld, rscale, rshift,
-                  chanmul, (__nv_bfloat16*)out, out_ld, P, pix_per_img, C, relu, t.cgb, t.rows, res_after_relu};
-  launch_k(bn_apply_kernel, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
-  LAUNCH_CHECK("bn_apply_kernel");
+  return bn_apply_impl(y, y_ld, scale, shift, res, res_ld, rscale, rshift, chanmul, out, out_ld, P, pix_per_img, C, relu,
+                       res_after_relu, nullptr, nullptr, nullptr, nullptr, 1.f, 0.f, 0.f, nullptr, nullptr, nullptr, nullptr,
+                       nullptr, nullptr, st);
+}
+
+int sseg_bn_finalize_apply(const float* sum, const float* sqsum, float count, const float* gamma, const float* beta,
+                           float eps, float momentum, float* running_mean, float* running_var, float* mean_out,
+                           float* invstd_out, float* scale_out, float* shift_out, const void* y, long y_ld, const void* res,
+                           long res_ld, const float* rscale, const float* rshift, const float* chanmul, void* out,
+                           long out_ld, long P, long pix_per_img, int C, int relu, int res_after_relu, sseg_stream_t st) {
+  SSEG_REQUIRE(sum && sqsum && mean_out && invstd_out && scale_out && shift_out && count > 1.f,
+               "sseg_bn_finalize_apply: null argument");
+  SSEG_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "sseg_bn_finalize_apply: running stats must pair");
+  return bn_apply_impl(y, y_ld, nullptr, nullptr, res, res_ld, rscale, rshift, chanmul, out, out_ld, P, pix_per_img, C,
+                       relu, res_after_relu, sum, sqsum, gamma, beta, count, eps, momentum, mean_out, invstd_out, scale_out,
+                       shift_out, running_mean, running_var, st);
 }
 
 static int fill_bwd(BnBwdParams& p, const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld,

@@ -98,6 +98,8 @@ _SIGNATURES = {
     "sseg_bn_finalize": [_p, _p, _p, c_float, _p, _p, c_float, c_float, c_int, c_int, _p, _p, _p, _p, _p, _p, _p, _p, _p,
                          c_int, _p],
     "sseg_bn_apply": [_p, c_long, _p, _p, _p, c_long, _p, _p, _p, _p, c_long, c_long, c_long, c_int, c_int, c_int, _p],
+    "sseg_bn_finalize_apply": [_p, _p, c_float, _p, _p, c_float, c_float, _p, _p, _p, _p, _p, _p, _p, c_long, _p, c_long, _p,
+                               _p, _p, _p, c_long, c_long, c_long, c_int, c_int, c_int, _p],
     "sseg_bn_bwd_reduce": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, c_long, c_long, c_int, _p],
     "sseg_bn_bwd_apply": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, _p, c_float, _p, c_long, _p,
                           c_long, c_long, c_long, c_int, c_int, c_int, _p, _p],

@@ -186,6 +186,21 @@ def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None
     return out
 
 
+def bn_finalize_apply(ssum, ssq, count, gamma, beta, eps, momentum, mean, invstd, scale, shift, y, out, relu=True,
+                      res=None, rscale=None, rshift=None, chanmul=None, res_after_relu=False, running_mean=None,
+                      running_var=None):
+    """bn_finalize(BN_TRAIN) + bn_apply in one launch."""
+    P, ppi, y_ld = _pix(y)
+    _, _, out_ld = _pix(out)
+    res_ld = _pix(res)[2] if res is not None else 0
+    _C.check(_C.lib().sseg_bn_finalize_apply(_C.ptr(ssum), _C.ptr(ssq), float(count), _C.ptr(gamma), _C.ptr(beta), eps,
+                                             momentum, _C.ptr(running_mean), _C.ptr(running_var), _C.ptr(mean),
+                                             _C.ptr(invstd), _C.ptr(scale), _C.ptr(shift), _C.ptr(y), y_ld, _C.ptr(res),
+                                             res_ld, _C.ptr(rscale), _C.ptr(rshift), _C.ptr(chanmul), _C.ptr(out), out_ld,
+                                             P, ppi, y.shape[3], int(relu), int(res_after_relu), _stream()))
+    return out
+
+
 def bn_bwd_reduce(g, a, y, mean, invstd, s1, s2, chanmul=None, scale=None, fshift=None):
     """a: saved output (ReLU mask) or None; (scale, fshift) with a=None: mask recomputed from y; all None: no ReLU."""
     P, ppi, g_ld = _pix(g)

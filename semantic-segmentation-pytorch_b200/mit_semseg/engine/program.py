@@ -107,6 +107,7 @@ class SegProgram:
         self.pool_groups = {}
         import os as _os
         self.fuse_bnbwd = _os.environ.get("SSEG_FUSE_BNBWD", "1") != "0"
+        self.fuse_finalize = _os.environ.get("SSEG_FUSE_FINALIZE", "1") != "0"
         self.keep = []  # anything that must stay alive (geometry structs hold raw pointers)
         self.graph = None
         # weight-gradient GEMMs are off the critical path of the backward pass (nothing downstream reads them until
@@ -630,6 +631,14 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
         P.fwd.append(lambda: ops.bn_finalize_peer(P.peer, bns.stats_off, bns.flag_off, P.peer_step, w, b, m.eps, mom,
                                                   bns.mean, bns.invstd, bns.scale, bns.shift, cnt_out, running=running,
                                                   update_running=upd))
+    elif mode == ops.BN_TRAIN and out is not None and P.fuse_finalize:
+        # single-GPU training: finalize fused into the apply kernel (one kernel boundary less per layer)
+        rmean, rvar = (m.running_mean, m.running_var) if upd else (None, None)
+        P.fwd.append(lambda: ops.bn_finalize_apply(st[:C], st[C:2 * C], count, w, b, m.eps, mom, bns.mean, bns.invstd,
+                                                   bns.scale, bns.shift, y, out, relu=relu, res=res, rscale=rscale,
+                                                   rshift=rshift, chanmul=chanmul, res_after_relu=res_after_relu,
+                                                   running_mean=rmean, running_var=rvar))
+        return
     else:
         if mode == ops.BN_TRAIN_SYNC and P.dist is not None:
             P.fwd.append(lambda: P.dist.all_reduce(st))

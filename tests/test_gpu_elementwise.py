@@ -328,3 +328,30 @@ def test_fused_sgd_matches_torch_sgd():
     torch.cuda.synchronize()
     for a, b in zip(ref_p, my_p):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6), (a - b).abs().max().item()
+
+
+def test_bn_finalize_apply_fused_equals_two_kernels():
+    from mit_semseg.engine import ops
+    g = _gen(13)
+    n, hw, C = 2, 24, 256
+    y = (torch.randn(n, hw, hw, C, device=DEV, generator=g) * 1.5 + 0.3).bfloat16()
+    res = torch.randn(n, hw, hw, C, device=DEV, generator=g).bfloat16()
+    gamma, beta = torch.rand(C, device=DEV, generator=g) + 0.5, torch.randn(C, device=DEV, generator=g) * 0.1
+    yf = y.float()
+    ssum, ssq, cnt = yf.sum(dim=(0, 1, 2)), (yf * yf).sum(dim=(0, 1, 2)), n * hw * hw
+    outs = []
+    for fused in (False, True):
+        rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+        mean, invstd, scale, shift = [torch.empty(C, device=DEV) for _ in range(4)]
+        out = torch.empty_like(y)
+        if fused:
+            ops.bn_finalize_apply(ssum, ssq, cnt, gamma, beta, 1e-5, 0.001, mean, invstd, scale, shift, y, out, relu=True,
+                                  res=res, running_mean=rm, running_var=rv)
+        else:
+            ops.bn_finalize(ssum, ssq, cnt, gamma, beta, 1e-5, 0.001, ops.BN_TRAIN, mean, invstd, scale, shift,
+                            running=(rm, rv, None, None, None), update_running=True)
+            ops.bn_apply(y, scale, shift, out, relu=True, res=res)
+        torch.cuda.synchronize()
+        outs.append((out, mean, invstd, scale, shift, rm, rv))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6)
