@@ -107,7 +107,10 @@ class SegProgram:
         self.pool_groups = {}
         import os as _os
         self.fuse_bnbwd = _os.environ.get("SSEG_FUSE_BNBWD", "1") != "0"
-        self.fuse_finalize = _os.environ.get("SSEG_FUSE_FINALIZE", "1") != "0"
+        # measured on B200: fusing finalize into apply does NOT pay (6.92 vs 6.79 ms/step): with programmatic dependent
+        # launch the tiny finalize kernel already overlaps the conv's tail, while the fused prologue delays every
+        # block's streaming phase. Kept as an opt-in.
+        self.fuse_finalize = _os.environ.get("SSEG_FUSE_FINALIZE", "0") == "1"
         self.keep = []  # anything that must stay alive (geometry structs hold raw pointers)
         self.graph = None
         # weight-gradient GEMMs are off the critical path of the backward pass (nothing downstream reads them until
