@@ -11,6 +11,8 @@
 //   Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM alloc), warps 2..5 = epilogue.
 //   Epilogue fusions: +bias, +addend (residual / gradient accumulation), per-channel sum & sum-of-squares
 //   (batch-norm statistics, lib/nn/modules/batchnorm.py:68-70 of the reference) and bf16 / fp32 store.
+#include <stdlib.h>
+
 #include "common.h"
 #include "ptx.cuh"
 
@@ -329,6 +331,11 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
                     "igemm_kernel launch");
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
+}
+
 // Fills the geometry-derived part of the parameters shared by the forward and weight-gradient kernels.
 // `box_pixels` = pixels per TMA box (128 for igemm M tiles, 64 for wgrad K steps).
 struct GeomHost {
@@ -426,7 +433,8 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   // N tile: 128 unless that leaves most SMs without a CTA (148 SMs x 2 resident CTAs): then halve it to double the grid
   const int m_tiles = gh.vn * gh.tiles_h * gh.tiles_w;
   int block_n = cout <= 64 ? 64 : 128;
-  if (block_n == 128 && m_tiles * ceil_div(n_store, 128) <= 160) block_n = 64;
+  static const int ntile_thresh = env_int("SSEG_NTILE_THRESH", 160);
+  if (block_n == 128 && m_tiles * ceil_div(n_store, 128) <= ntile_thresh) block_n = 64;
   p.n_tiles = ceil_div(n_store, block_n);
   rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, block_n);
   if (rc) return rc;
@@ -711,7 +719,8 @@ extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, 
   p.BH = gh.BH, p.BW = gh.BW, p.tiles_h = gh.tiles_h, p.tiles_w = gh.tiles_w;
   p.total_boxes = gh.vn * gh.tiles_h * gh.tiles_w;
   // split K (pixels) so that the grid is a few waves of 148 SMs x 2 resident CTAs, but keep >= 4 K steps per CTA
-  int splits = ceil_div(592, p.num_tiles);
+  static const int wgrad_ctas = env_int("SSEG_WGRAD_CTAS", 592);
+  int splits = ceil_div(wgrad_ctas, p.num_tiles);
   splits = max(1, min(splits, ceil_div(p.total_boxes, 4)));
   p.boxes_per_split = ceil_div(p.total_boxes, splits);
   splits = ceil_div(p.total_boxes, p.boxes_per_split);

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--crop", type=int, default=512)
     ap.add_argument("--top", type=int, default=30)
     ap.add_argument("--detail", action="store_true", help="list every conv GEMM launch with shape and TFLOP/s")
+    ap.add_argument("--replay-only", action="store_true", help="only print the CUDA-graph replay time")
     args = ap.parse_args()
     from mit_semseg.engine import ops
     from mit_semseg.engine.program import SegProgram
@@ -34,6 +35,20 @@ def main():
     prog.run_eager()
     torch.cuda.synchronize()
     stream = torch.cuda.current_stream()
+    if args.replay_only:
+        prog.capture()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        best = 1e9
+        for _ in range(3):
+            t0.record(stream)
+            for _ in range(10):
+                prog.run()
+            t1.record(stream)
+            torch.cuda.synchronize()
+            best = min(best, t0.elapsed_time(t1) / 10)
+        print("CUDA-graph replay: %.3f ms / step (best of 3x10)" % best)
+        return
     recs = []
     names = [n for n in dir(ops) if callable(getattr(ops, n)) and not n.startswith("_") and
              n not in ("act", "make_geom", "conv_taps", "conv_s2_taps", "parity_planes")]
