@@ -36,6 +36,15 @@ TRAIN_GFLOP_PER_IMG = 1224.2  # fwd + dgrad + wgrad conv 
 LR, MOMENTUM, WD = 0.02, 0.9, 1e-4  # config/ade20k-resnet50dilated-ppm_deepsup.yaml:17-27
 
 
+def synth_batch(n, h, w, label_stride, seed, num_class=NUM_CLASS):
+    """Synthetic ADE20K-shaped batch: img ~ N(0,1), labels uniform in {-1 .. num_class-1} (-1 = ignore).
+    Same generator as oracle.segnet_oracle.synth_batch, restated here so the GPU arm never imports the oracle."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    img = torch.randn(n, 3, h, w, generator=g)
+    label = torch.randint(-1, num_class, (n, h // label_stride, w // label_stride), generator=g)
+    return {"img_data": img, "seg_label": label}
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -158,11 +167,10 @@ def run_gpu(args):
     dev = torch.device("cuda", local)
     from mit_semseg.engine import _C, ops
     from mit_semseg.engine.program import SegProgram
-    from oracle import segnet_oracle as O  # synthetic batch generator only (no oracle compute on this arm)
 
     seg = build_model(dev)
     opts = make_optimizers(seg, fused=True)   # device-resident arm: engine optimizer (2 launches / step)
-    feed = O.synth_batch(BATCH, CROP, CROP, LABEL_STRIDE, 304 + rank, NUM_CLASS)
+    feed = synth_batch(BATCH, CROP, CROP, LABEL_STRIDE, 304 + rank, NUM_CLASS)
     img_h, lab_h = feed["img_data"].pin_memory(), feed["seg_label"].pin_memory()
     img_d, lab_d = img_h.to(dev), lab_h.to(dev)
 

@@ -14,10 +14,9 @@ import bench  # noqa: E402
 def main():
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     from mit_semseg.engine.program import SegProgram
-    from oracle import segnet_oracle as O
     dev = torch.device("cuda", 0)
     seg = bench.build_model(dev)
-    feed = O.synth_batch(bench.BATCH, bench.CROP, bench.CROP, 8, 304)
+    feed = bench.synth_batch(bench.BATCH, bench.CROP, bench.CROP, 8, 304)
     prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
     prog.load_inputs(feed["img_data"].to(dev), feed["seg_label"].to(dev))
     for _ in range(runs):

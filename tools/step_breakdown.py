@@ -25,10 +25,9 @@ def main():
     args = ap.parse_args()
     from mit_semseg.engine import ops
     from mit_semseg.engine.program import SegProgram
-    from oracle import segnet_oracle as O
     dev = torch.device("cuda", 0)
     seg = bench.build_model(dev)
-    feed = O.synth_batch(args.batch, args.crop, args.crop, 8, 304)
+    feed = bench.synth_batch(args.batch, args.crop, args.crop, 8, 304)
     prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
     prog.load_inputs(feed["img_data"].to(dev), feed["seg_label"].to(dev))
     prog.run_eager()
