@@ -430,10 +430,11 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     SSEG_REQUIRE(g->tap_koff[t] + span <= w_ld, "sseg_conv_igemm: tap %d K range exceeds w_ld", t);
     p.num_k_steps += span / kBlockK;
   }
-  // N tile: 128 unless that leaves most SMs without a CTA (148 SMs x 2 resident CTAs): then halve it to double the grid
+  // N tile: 128 unless that leaves most SMs without a CTA: then halve it to double the grid. Threshold swept on B200
+  // (whole training step, CUDA-graph replay): 0 -> 6.58 ms, 80 -> 6.56, 160 -> 6.80, 300 -> 7.17, 600 -> 7.36.
   const int m_tiles = gh.vn * gh.tiles_h * gh.tiles_w;
   int block_n = cout <= 64 ? 64 : 128;
-  static const int ntile_thresh = env_int("SSEG_NTILE_THRESH", 160);
+  static const int ntile_thresh = env_int("SSEG_NTILE_THRESH", 80);
   if (block_n == 128 && m_tiles * ceil_div(n_store, 128) <= ntile_thresh) block_n = 64;
   p.n_tiles = ceil_div(n_store, block_n);
   rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, block_n);
@@ -718,8 +719,10 @@ extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, 
   p.num_tiles = p.m_tiles * p.ntaps * p.ci_tiles_per_tap;
   p.BH = gh.BH, p.BW = gh.BW, p.tiles_h = gh.tiles_h, p.tiles_w = gh.tiles_w;
   p.total_boxes = gh.vn * gh.tiles_h * gh.tiles_w;
-  // split K (pixels) so that the grid is a few waves of 148 SMs x 2 resident CTAs, but keep >= 4 K steps per CTA
-  static const int wgrad_ctas = env_int("SSEG_WGRAD_CTAS", 592);
+  // split K (pixels) only until the grid covers the 148 SMs once, and keep >= 4 K steps per CTA: every extra split
+  // costs a full fp32 atomic pass over the tile. Swept on B200 (step time): 74 -> 6.50 ms, 148 -> 6.44, 200 -> 6.46,
+  // 296 -> 6.56, 592 -> 6.80, 1184 -> 7.11.
+  static const int wgrad_ctas = env_int("SSEG_WGRAD_CTAS", 148);
   int splits = ceil_div(wgrad_ctas, p.num_tiles);
   splits = max(1, min(splits, ceil_div(p.total_boxes, 4)));
   p.boxes_per_split = ceil_div(p.total_boxes, splits);
