@@ -301,7 +301,15 @@ def conv_roofline(prog, world):
         timed("wgrad", lambda: orig_wgrad(geom, dy, cout, dw), flops_geom(geom, cout, n, h, w))
         return dw
 
-    ops.conv_igemm, ops.conv_wgrad = igemm, wgrad
+    orig_bnbwd = ops.conv_igemm_bnbwd
+
+    def igemm_bnbwd(geom, w_bf16, cout, out, *a, **kw):
+        # data-gradient launch with the producer's BN-backward reduction fused in its epilogue: same GEMM FLOPs
+        n, h, w = out.shape[0], out.shape[1], out.shape[2]
+        timed("igemm", lambda: orig_bnbwd(geom, w_bf16, cout, out, *a, **kw), flops_geom(geom, cout, n, h, w))
+        return out
+
+    ops.conv_igemm, ops.conv_wgrad, ops.conv_igemm_bnbwd = igemm, wgrad, igemm_bnbwd
     prog.serial = True  # weight gradients inline on the main stream: one kernel at a time between each event pair
     try:
         stream = torch.cuda.current_stream()
@@ -315,7 +323,7 @@ def conv_roofline(prog, world):
         torch.cuda.synchronize()
     finally:
         prog.serial = False
-        ops.conv_igemm, ops.conv_wgrad = orig_igemm, orig_wgrad
+        ops.conv_igemm, ops.conv_wgrad, ops.conv_igemm_bnbwd = orig_igemm, orig_wgrad, orig_bnbwd
     tot = {"igemm": [0.0, 0.0, 0], "wgrad": [0.0, 0.0, 0]}
     top = None
     for kind, a, b, fl in records:
