@@ -29,8 +29,13 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_sync() {
+#ifdef SSEG_PDL_EARLY
+  pdl_launch_dependents();  // let the next kernel get scheduled even before our own prerequisites have finished
+  pdl_wait();
+#else
   pdl_wait();
   pdl_launch_dependents();
+#endif
 }
 
 // ---------------------------------------------------------------- mbarrier

@@ -8,7 +8,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_long, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.abspath(os.path.join(_HERE, "..", "..", "libsseg_b200.so"))
+LIB_PATH = os.path.abspath(os.path.join(_HERE, "..", "..", os.environ.get("SSEG_LIB", "libsseg_b200.so")))
 
 MAX_SRCS = 5
 MAX_TAPS = 9
