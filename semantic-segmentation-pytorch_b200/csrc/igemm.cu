@@ -315,6 +315,318 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
   }
 }
 
+// Persistent variant: one CTA per SM walks tiles (tile = blockIdx.x + i * gridDim.x). Two TMEM accumulator buffers let the
+// MMA warp start tile i+1 while the epilogue warps still drain / reduce / store tile i, and the TMA producer runs ahead
+// across tile boundaries, so the pipeline-fill and epilogue latencies are paid once per CTA instead of once per tile.
+template <int BLOCK_N, int STAGES>
+struct IgemmPersistSmem {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPitch = BLOCK_N * 2 + 16;
+  static constexpr int kStgOff = STAGES * kStageBytes;                    // staged output tile + staged y tile
+  static constexpr int kBarOff = kStgOff + ((2 * 128 * kPitch + 1023) / 1024) * 1024;
+  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kDynBytes = kTotal + 1024;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const __grid_constant__ IgemmParams p,
+                                                                          const int num_tiles) {
+  using L = IgemmPersistSmem<BLOCK_N, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]: accumulator buffer b holds a finished tile
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]: the epilogue has drained accumulator buffer b
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_k_steps = p.num_k_steps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) tmem_alloc<2 * BLOCK_N>(tmem_ptr_smem);  // two accumulator buffers
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      // tile decode: N-tile fastest so CTAs sharing an activation tile run together (L2 reuse)
+      const int n_tile = tile % p.n_tiles;
+      int m_tile = tile / p.n_tiles;
+      const int tw = m_tile % p.tiles_w;
+      m_tile /= p.tiles_w;
+      const int th = m_tile % p.tiles_h;
+      const int img = m_tile / p.tiles_h;
+      const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
+      (void)n0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
+        const int fixed_src = p.tap_src[t];
+        const int nblk = fixed_src >= 0 ? p.src_blk_end[0] : p.blocks_per_tap;
+        int src = fixed_src >= 0 ? fixed_src : 0, blk_begin = 0;
+        for (int b = 0; b < nblk; ++b) {
+          if (fixed_src < 0) {
+            while (b >= p.src_blk_end[src]) {
+              blk_begin = p.src_blk_end[src];
+              ++src;
+            }
+          }
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
+          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], p.tap_koff[t] + b * kBlockK, n0);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+      }  // tile loop
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, kBlockM, BLOCK_N);
+      int stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1, use = it >> 1;
+      mbar_wait(&tmem_empty_bar[buf], (use & 1) ^ 1);  // the epilogue has drained this accumulator buffer
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+      for (int ks = 0; ks < num_k_steps; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+          umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
+        }
+        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+      umma_commit(&tmem_full_bar[buf]);  // accumulator of this tile complete
+      }  // tile loop
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = quarter * 32 + lane;
+    const bool do_stats = p.stat_sum != nullptr;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    // tile decode: N-tile fastest so CTAs sharing an activation tile run together (L2 reuse)
+    const int n_tile = tile % p.n_tiles;
+    int m_tile = tile / p.n_tiles;
+    const int tw = m_tile % p.tiles_w;
+    m_tile /= p.tiles_w;
+    const int th = m_tile % p.tiles_h;
+    const int img = m_tile / p.tiles_h;
+    const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
+    const int buf = it & 1, use = it >> 1;
+    const uint32_t d_tmem = tmem_base + buf * BLOCK_N;
+    const int hh = h0 + (row >> p.bw_shift), ww = w0 + (row & (p.BW - 1));
+    const bool valid = (hh < p.H) && (ww < p.W);
+    const size_t out_off = img * p.out_img_stride + hh * p.out_row_stride + static_cast<size_t>(ww) * p.ld_out;
+    const size_t add_off = img * p.add_img_stride + hh * p.add_row_stride + static_cast<size_t>(ww) * p.ld_addend;
+    (void)out_off;
+
+    mbar_wait(&tmem_full_bar[buf], use & 1);
+    tc_fence_after();
+    // bf16 outputs are staged through shared memory (the pipeline stages are idle once the accumulator is complete):
+    // rows are then stored with full 16-byte-per-lane coalescing and the per-channel statistics are column sums of the
+    // staged (bf16-rounded = as stored) tile. fp32 outputs (classifier logits) are written straight from registers.
+    constexpr int kPitch = BLOCK_N * 2 + 16;  // +16 B: consecutive rows start in different 16-byte bank groups
+    uint8_t* stg = smem + L::kStgOff;  // dedicated staging: the pipeline stages already carry the next tile
+#pragma unroll 1
+    for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      uint32_t raw[32];
+      tmem_ld_32x32(d_tmem + (static_cast<uint32_t>(quarter * 32) << 16) + chunk * 32, raw);
+      tmem_ld_wait();
+      float v[32];
+      const int col0 = n0 + chunk * 32;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.cout) v[j] += __ldg(p.bias + col0 + j);
+      }
+      if (p.addend != nullptr && valid) {
+        const __nv_bfloat16* ap = p.addend + add_off + col0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (col0 + g * 8 < p.n_store) {
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(ap + g * 8));
+            const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __bfloat1622float2(h2[e]);
+              v[g * 8 + 2 * e] += f.x;
+              v[g * 8 + 2 * e + 1] += f.y;
+            }
+          }
+        }
+      }
+      if (p.out_f32) {
+        if (valid) {
+          float* op = reinterpret_cast<float*>(p.out) + out_off + col0;
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            if (col0 + g * 4 < p.n_store)
+              *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
+      } else {
+        uint8_t* sp = stg + row * kPitch + chunk * 64;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 q = make_uint4(0u, 0u, 0u, 0u);  // rows outside the image contribute zeros to the statistics
+          if (valid) {
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&q);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g * 8 + 2 * e], v[g * 8 + 2 * e + 1]);
+          }
+          *reinterpret_cast<uint4*>(sp + g * 16) = q;
+        }
+      }
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps: all tcgen05.ld of this tile are done
+    if (threadIdx.x == 64) mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may refill this accumulator buffer
+    if (!p.out_f32) {
+      const int t = threadIdx.x - 64;
+      if (do_stats) {
+        // thread = one pair of adjacent columns x one slab of rows; fp32 sums of the bf16 values as stored
+        constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
+        const int cp = t % kPairs, slab = t / kPairs;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        const uint8_t* base = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll 8
+        for (int r = 0; r < kRowsPerSlab; ++r) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + r * kPitch));
+          s0 += f.x, s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0), q1 = fmaf(f.y, f.y, q1);
+        }
+        const int col = n0 + cp * 2;
+        if (col < p.cout) atomicAdd(p.stat_sum + col, s0), atomicAdd(p.stat_sqsum + col, q0);
+        if (col + 1 < p.cout) atomicAdd(p.stat_sum + col + 1, s1), atomicAdd(p.stat_sqsum + col + 1, q1);
+      }
+      if (p.bw_s1 != nullptr) {
+        // BN-backward partial sums of the producer layer. Its saved conv output y (same tile geometry) is first copied
+        // into shared memory with fully coalesced 16-byte loads (all loads of a thread in flight together), then the
+        // per-channel sums run from shared memory next to the staged gradient tile.
+        uint8_t* ytile = stg + 128 * kPitch;
+        {
+          constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow, kPasses = 128 / kRowsPerPass;
+          const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+          uint4 q[kPasses];
+#pragma unroll
+          for (int pass = 0; pass < kPasses; ++pass) {
+            const int r = pass * kRowsPerPass + r0;
+            const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+            q[pass] = make_uint4(0u, 0u, 0u, 0u);
+            if (rh < p.H && rw < p.W && n0 + seg * 8 < p.cout)
+              q[pass] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
+                                                             static_cast<size_t>(rw) * p.bw_ld + n0 + seg * 8));
+          }
+#pragma unroll
+          for (int pass = 0; pass < kPasses; ++pass)
+            *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = q[pass];
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
+        const int cp = t % kPairs, slab = t / kPairs;
+        const int col = n0 + cp * 2;
+        if (col < p.cout) {
+          const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
+          const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
+          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+          const uint8_t* gbase = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+          const uint8_t* ybase = ytile + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll 8
+          for (int r = 0; r < kRowsPerSlab; ++r) {
+            // rows outside the image hold zeros in the staged gradient tile: they contribute nothing
+            const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
+            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
+            const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
+            const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
+            a0 += g0, a1 += g1;
+            b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
+          }
+          atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
+          if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
+        }
+      }
+      // coalesced store: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass
+      constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
+      const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+      if (n0 + seg * 8 < p.n_store) {
+#pragma unroll 4
+        for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
+          const int r = pass * kRowsPerPass + r0;
+          const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+          if (rh < p.H && rw < p.W) {
+            const uint4 q = *reinterpret_cast<const uint4*>(stg + r * kPitch + seg * 16);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride + rh * p.out_row_stride +
+                                static_cast<size_t>(rw) * p.ld_out + n0 + seg * 8;
+            *reinterpret_cast<uint4*>(op) = q;
+          }
+        }
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile fully consumed before the next tile overwrites it
+    }  // tile loop
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<2 * BLOCK_N>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_persistent(const IgemmParams& p, int num_tiles, int grid, cudaStream_t stream) {
+  using L = IgemmPersistSmem<BLOCK_N, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  SSEG_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    SSEG_CUDA(cudaFuncSetAttribute(igemm_persistent_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   L::kDynBytes));
+    configured[dev] = true;
+  }
+  count_launch(1);
+  return check_cuda(launch_k(igemm_persistent_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream,
+                             p, num_tiles),
+                    "igemm_persistent_kernel launch");
+}
+
 template <int BLOCK_N, int STAGES>
 static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
   using L = IgemmSmem<BLOCK_N, STAGES>;
@@ -467,6 +779,21 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     p.bw_fscale = bw_fscale, p.bw_fshift = bw_fshift, p.bw_s1 = bw_s1, p.bw_s2 = bw_s2;
   }
   const int grid = gh.vn * p.tiles_h * p.tiles_w * p.n_tiles;
+  // persistent CTAs (one per SM, double-buffered accumulators) once there are clearly more tiles than SMs
+  static const int persistent_min_tiles = env_int("SSEG_IGEMM_PERSISTENT", 0);  // 0 = off; e.g. 200 = on for >= 200 tiles
+  if (persistent_min_tiles > 0 && grid >= persistent_min_tiles) {
+    static int num_sms = 0;
+    if (num_sms == 0) {
+      int dev = 0;
+      SSEG_CUDA(cudaGetDevice(&dev));
+      SSEG_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    static const int max_ctas = env_int("SSEG_IGEMM_PERSISTENT_CTAS", 0);  // test knob: force many tiles per CTA
+    const int cap = max_ctas > 0 ? max_ctas : num_sms;
+    const int pgrid = grid < cap ? grid : cap;
+    if (block_n == 64) return launch_persistent<64, 6>(p, grid, pgrid, stream);
+    return launch_persistent<128, 4>(p, grid, pgrid, stream);
+  }
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);
 }
