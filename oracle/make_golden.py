@@ -26,7 +26,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 from mit_semseg.lib.nn import SynchronizedBatchNorm2d  # noqa: E402  (reference)
 from mit_semseg.models import ModelBuilder, SegmentationModule  # noqa: E402  (reference)
-from mit_semseg.models import models as rmodels, resnet as rresnet  # noqa: E402
+from mit_semseg.models import models as rmodels, resnet as rresnet, hrnet as rhrnet  # noqa: E402
 
 from oracle import segnet_oracle as O  # noqa: E402
 
@@ -37,8 +37,11 @@ assert "/root/reference" in rmodels.__file__, "must import the REFERENCE mit_sem
 
 def build_ref(enc_arch, dec_arch, fc_dim, use_softmax=False):
     base, dil = O.parse_encoder_arch(enc_arch)
-    net = rresnet.__dict__[base](pretrained=False)
-    enc = rmodels.ResnetDilated(net, 8) if dil else rmodels.Resnet(net)
+    if base == "hrnetv2":
+        enc = rhrnet.hrnetv2(pretrained=False)
+    else:
+        net = rresnet.__dict__[base](pretrained=False)
+        enc = rmodels.ResnetDilated(net, 8) if dil else rmodels.Resnet(net)
     dec = ModelBuilder.build_decoder(dec_arch, fc_dim=fc_dim, num_class=150, use_softmax=use_softmax)
     return enc, dec
 
@@ -85,7 +88,7 @@ def train_case(name, enc_arch, dec_arch, fc, n, hw, label_stride, keep_grads):
     rec = {"loss": np.float32(loss.item()), "acc": np.float32(acc.item()), "pred": pred.detach().numpy(),
            "feat_mean": np.array([f.mean().item() for f in feats], np.float32),
            "feat_absmean": np.array([f.abs().mean().item() for f in feats], np.float32),
-           "feat3_sample": feats[3].detach()[:, ::64, ::3, ::3].numpy()}
+           "feat3_sample": feats[-1].detach()[:, ::64, ::3, ::3].numpy()}
     if isinstance(out, tuple):
         rec["pred_deepsup_sample"] = out[1].detach()[:, ::5].numpy()
     for k in keep_grads:
@@ -171,7 +174,8 @@ def api_case():
     out = {}
     for enc_arch, dec_arch, fc in (("resnet50dilated", "ppm_deepsup", 2048), ("resnet18dilated", "ppm_deepsup", 512),
                                    ("resnet101", "c1_deepsup", 2048), ("resnet50", "ppm", 2048), ("resnet18", "c1", 512),
-                                   ("resnet50", "upernet", 2048), ("resnet18", "upernet_lite", 512)):
+                                   ("resnet50", "upernet", 2048), ("resnet18", "upernet_lite", 512),
+                                   ("hrnetv2", "c1", 720)):
         torch.manual_seed(304)
         enc, dec = build_ref(enc_arch, dec_arch, fc)
         rec = {"enc_keys": {k: list(v.shape) for k, v in enc.state_dict().items()},
@@ -192,6 +196,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "api":
         api_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "hrnet":
+        train_case("train_hrnetv2_c1_64", "hrnetv2", "c1", 720, 2, 64, 4,
+                   ["enc.conv1.weight", "enc.stage2.0.fuse_layers.0.1.0.weight", "enc.stage4.2.fuse_layers.3.0.2.0.weight",
+                    "enc.stage3.1.branches.2.3.conv2.weight", "enc.transition2.2.0.0.weight", "dec.cbr.0.weight",
+                    "dec.conv_last.bias"])
+        infer_case("infer_hrnetv2_c1_64x96", "hrnetv2", "c1", 720, 1, 64, 96)
+        sys.exit(0)
     train_case("train_r50dilated_ppm_deepsup_96", "resnet50dilated", "ppm_deepsup", 2048, 2, 96, 8,
                ["enc.conv1.weight", "enc.bn1.weight", "enc.layer2.0.conv2.weight", "enc.layer3.1.conv2.weight",
                 "enc.layer4.2.conv3.weight", "dec.conv_last.0.weight", "dec.conv_last.4.bias", "dec.ppm.0.2.weight",
@@ -200,6 +211,11 @@ if __name__ == "__main__":
                ["enc.conv1.weight", "dec.cbr.0.weight"])
     train_case("train_r50_upernet_128", "resnet50", "upernet", 2048, 2, 128, 4, ["dec.conv_last.1.bias"])
     infer_case("infer_r18dilated_ppm_deepsup_96x128", "resnet18dilated", "ppm_deepsup", 512, 2, 96, 128)
+    train_case("train_hrnetv2_c1_64", "hrnetv2", "c1", 720, 2, 64, 4,
+               ["enc.conv1.weight", "enc.stage2.0.fuse_layers.0.1.0.weight", "enc.stage4.2.fuse_layers.3.0.2.0.weight",
+                "enc.stage3.1.branches.2.3.conv2.weight", "enc.transition2.2.0.0.weight", "dec.cbr.0.weight",
+                "dec.conv_last.bias"])
+    infer_case("infer_hrnetv2_c1_64x96", "hrnetv2", "c1", 720, 1, 64, 96)
     syncbn_case()
     dropout_case()
     api_case()

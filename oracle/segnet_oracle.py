@@ -1,7 +1,7 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
 
 A CPU, fp32 restatement of the reference hot path (CSAILVision/semantic-segmentation-pytorch @ 8f27c9b):
-deep-stem dilated ResNet -> PPM / PPM_deepsup / C1 / UPerNet decoder -> log-softmax / NLL / pixel accuracy, with both
+deep-stem (dilated) ResNet or HRNetV2-W48 -> PPM / PPM_deepsup / C1 / UPerNet decoder -> log-softmax / NLL / pixel accuracy, with both
 batch-norm formulas of SynchronizedBatchNorm2d.  It is written functionally over a flat state dict that uses the
 reference's parameter names, so one weights file loads into the reference, this oracle and the B200 engine.
 
@@ -30,8 +30,13 @@ RESNET_LAYERS = {"resnet18": ("basic", [2, 2, 2, 2]), "resnet50": ("bottleneck",
                  "resnet101": ("bottleneck", [3, 4, 23, 3])}
 
 
+HRNET_STAGES = ((1, (48, 96)), (4, (48, 96, 192)), (3, (48, 96, 192, 384)))  # (modules, branch widths): hrnet.py:257-262
+
+
 def parse_encoder_arch(arch):
     arch = arch.lower()
+    if arch == "hrnetv2":
+        return "hrnetv2", False
     dilated = arch.endswith("dilated")
     base = arch[:-len("dilated")] if dilated else arch
     if base not in RESNET_LAYERS:
@@ -82,6 +87,21 @@ class _RoundF(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         return g
+
+
+class _RoundB(torch.autograd.Function):
+    """identity in forward, round the gradient (the engine stores that gradient tensor in bf16)"""
+    @staticmethod
+    def forward(ctx, x):
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
+def _qb(x, st):
+    return _RoundB.apply(x) if getattr(st, "emulate", None) == "bf16" else x
 
 
 def _q(x, st):
@@ -152,8 +172,79 @@ def _cbr(x, sd, conv, bn, st, stride=1, dilation=1, padding=0, relu=True):
 
 # ----------------------------------------------------------------------------------------------
 # encoder (reference models/resnet.py:24-92 blocks, :96-160 ResNet; models/models.py:170-268 wrappers)
+def _residual_block(x, sd, p, st, kind, stride=1):
+    """BasicBlock / Bottleneck with stride-1 3x3s and 'same' padding (the HRNet blocks, hrnet.py:34-102)."""
+    residual = x
+    if kind == "basic":
+        out = _cbr(x, sd, p + "conv1", p + "bn1", st, stride, 1, 1)
+        out = _cbr(out, sd, p + "conv2", p + "bn2", st, 1, 1, 1, relu=False)
+    else:
+        out = _cbr(x, sd, p + "conv1", p + "bn1", st)
+        out = _cbr(out, sd, p + "conv2", p + "bn2", st, stride, 1, 1)
+        out = _cbr(out, sd, p + "conv3", p + "bn3", st, relu=False)
+    if (p + "downsample.0.weight") in sd:
+        residual = _cbr(x, sd, p + "downsample.0", p + "downsample.1", st, stride, relu=False)
+    return _q(F.relu(out + residual), st)
+
+
+def hrnet_forward(x, sd, st, prefix=""):
+    """HRNetV2.forward (reference models/hrnet.py:395-437) with HighResolutionModule.forward (:225-250) inlined.
+    Rounding emulation follows the engine: an exchange output is ONE fused kernel (sum of the branch tensor, affine
+    BN terms and bilinearly sampled affine BN terms, then ReLU), so only its result is rounded."""
+    P = prefix
+    x = _cbr(x, sd, P + "conv1", P + "bn1", st, stride=2, padding=1)
+    x = _cbr(x, sd, P + "conv2", P + "bn2", st, stride=2, padding=1)
+    for b in range(4):
+        x = _residual_block(x, sd, "%slayer1.%d." % (P, b), st, "bottleneck")
+    ys = [x]
+    for si, (nmod, widths) in enumerate(HRNET_STAGES, start=2):
+        # transition (hrnet.py:307-341, :405-432): new branches hang off the LAST previous output
+        tr = "%stransition%d." % (P, si - 1)
+        xs = []
+        for i in range(len(widths)):
+            if i < len(ys):
+                if (tr + "%d.0.weight" % i) in sd:
+                    xs.append(_cbr(ys[-1] if si > 2 else ys[i], sd, tr + "%d.0" % i, tr + "%d.1" % i, st, 1, 1, 1))
+                else:
+                    xs.append(ys[i])
+            else:
+                t = ys[-1]
+                for k in range(i + 1 - len(ys)):
+                    t = _cbr(t, sd, tr + "%d.%d.0" % (i, k), tr + "%d.%d.1" % (i, k), st, 2, 1, 1)
+                xs.append(t)
+        for m in range(nmod):
+            mp = "%sstage%d.%d." % (P, si, m)
+            for i in range(len(widths)):
+                for b in range(4):
+                    xs[i] = _residual_block(xs[i], sd, "%sbranches.%d.%d." % (mp, i, b), st, "basic")
+            fused = []
+            for i in range(len(widths)):
+                size = xs[i].shape[2:]
+                y = None
+                for j in range(len(widths)):
+                    fp = "%sfuse_layers.%d.%d." % (mp, i, j)
+                    if j == i:
+                        t = xs[j]
+                    elif j > i:
+                        t = _cbr(xs[j], sd, fp + "0", fp + "1", st, relu=False)
+                        t = F.interpolate(_qb(t, st), size=size, mode="bilinear", align_corners=False)
+                    else:
+                        t = xs[j]
+                        for k in range(i - j):
+                            t = _cbr(t, sd, fp + "%d.0" % k, fp + "%d.1" % k, st, 2, 1, 1, relu=(k != i - j - 1))
+                    y = t if y is None else y + t
+                fused.append(_q(F.relu(y), st))
+            xs = fused
+        ys = xs
+    size = ys[0].shape[2:]
+    ups = [ys[0]] + [_q(F.interpolate(t, size=size, mode="bilinear", align_corners=False), st) for t in ys[1:]]
+    return [torch.cat(ups, 1)]
+
+
 def encoder_forward(x, sd, arch, st, prefix=""):
     base, dilated = parse_encoder_arch(arch)
+    if base == "hrnetv2":
+        return hrnet_forward(x, sd, st, prefix)
     block, counts = RESNET_LAYERS[base]
     P = prefix
     x = _cbr(x, sd, P + "conv1", P + "bn1", st, stride=2, padding=1)
@@ -231,13 +322,13 @@ def decoder_forward(conv_out, sd, arch, st, segSize=None, use_softmax=False, dro
         return F.log_softmax(logits, dim=1), F.log_softmax(logits_ds, dim=1)
     if arch in ("c1", "c1_deepsup"):
         x = _cbr(conv5, sd, P + "cbr.0", P + "cbr.1", st, padding=1)
-        logits = F.conv2d(x, sd[P + "conv_last.weight"], sd[P + "conv_last.bias"])
+        logits = F.conv2d(x, _qw(sd[P + "conv_last.weight"], st), sd[P + "conv_last.bias"])
         if use_softmax:
             return _head(logits, segSize, True)
         if arch == "c1":
             return logits if return_logits else F.log_softmax(logits, dim=1)
         y = _cbr(conv_out[-2], sd, P + "cbr_deepsup.0", P + "cbr_deepsup.1", st, padding=1)
-        logits_ds = F.conv2d(y, sd[P + "conv_last_deepsup.weight"], sd[P + "conv_last_deepsup.bias"])
+        logits_ds = F.conv2d(y, _qw(sd[P + "conv_last_deepsup.weight"], st), sd[P + "conv_last_deepsup.bias"])
         if return_logits:
             return logits, logits_ds
         return F.log_softmax(logits, dim=1), F.log_softmax(logits_ds, dim=1)
@@ -298,8 +389,53 @@ def segmentation_forward(feed, enc_sd, dec_sd, enc_arch, dec_arch, st, deep_sup_
 
 # ----------------------------------------------------------------------------------------------
 # deterministic synthetic weights shared by reference / oracle / engine (see oracle/make_golden.py)
+def hrnet_param_shapes():
+    shapes = {}
+
+    def cb(name_conv, name_bn, co, ci, k):
+        shapes[name_conv] = ("conv", (co, ci, k, k))
+        shapes[name_bn] = ("bn", co)
+
+    cb("conv1", "bn1", 64, 3, 3), cb("conv2", "bn2", 64, 64, 3)
+    for b in range(4):
+        p = "layer1.%d." % b
+        cb(p + "conv1", p + "bn1", 64, 64 if b == 0 else 256, 1)
+        cb(p + "conv2", p + "bn2", 64, 64, 3), cb(p + "conv3", p + "bn3", 256, 64, 1)
+        if b == 0:
+            cb(p + "downsample.0", p + "downsample.1", 256, 64, 1)
+    pre = [256]
+    for si, (nmod, widths) in enumerate(HRNET_STAGES, start=2):
+        tr = "transition%d." % (si - 1)
+        for i, c in enumerate(widths):
+            if i < len(pre):
+                if pre[i] != c:
+                    cb(tr + "%d.0" % i, tr + "%d.1" % i, c, pre[i], 3)
+            else:
+                steps = i + 1 - len(pre)
+                for k in range(steps):
+                    cb(tr + "%d.%d.0" % (i, k), tr + "%d.%d.1" % (i, k), c if k == steps - 1 else pre[-1], pre[-1], 3)
+        for m in range(nmod):
+            mp = "stage%d.%d." % (si, m)
+            for i, c in enumerate(widths):
+                for b in range(4):
+                    p = "%sbranches.%d.%d." % (mp, i, b)
+                    cb(p + "conv1", p + "bn1", c, c, 3), cb(p + "conv2", p + "bn2", c, c, 3)
+            for i, ci_ in enumerate(widths):
+                for j, cj in enumerate(widths):
+                    fp = "%sfuse_layers.%d.%d." % (mp, i, j)
+                    if j > i:
+                        cb(fp + "0", fp + "1", ci_, cj, 1)
+                    elif j < i:
+                        for k in range(i - j):
+                            cb(fp + "%d.0" % k, fp + "%d.1" % k, ci_ if k == i - j - 1 else cj, cj, 3)
+        pre = list(widths)
+    return shapes
+
+
 def encoder_param_shapes(arch):
     base, _ = parse_encoder_arch(arch)
+    if base == "hrnetv2":
+        return hrnet_param_shapes()
     block, counts = RESNET_LAYERS[base]
     exp = 1 if block == "basic" else 4
     shapes = {}
@@ -396,7 +532,7 @@ def synth_state_dict(shapes, seed, residual_gain=None):
     if residual_gain is not None:
         blocks = {}
         for name in shapes:
-            if name.startswith("layer") and ".bn" in name and "downsample" not in name:
+            if (name.startswith("layer") or ".branches." in name) and ".bn" in name and "downsample" not in name:
                 blk, bn = name.rsplit(".", 1)
                 blocks[blk] = max(blocks.get(blk, ""), bn)
         for blk, bn in blocks.items():

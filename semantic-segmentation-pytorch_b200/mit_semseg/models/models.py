@@ -7,7 +7,7 @@ and, for `SegmentationModule`, the backward as well — is a schedule of sm_100a
 `mit_semseg.engine.program` (implicit-GEMM convolutions on tcgen05, fused BN/ReLU/residual, PPM cascade with a
 virtual concat, fused log-softmax/NLL/accuracy).  There is no PyTorch-operator fallback.
 
-Supported on the engine in this build: resnet18/50/101 (+dilated) encoders; ppm, ppm_deepsup, c1, c1_deepsup,
+Supported on the engine in this build: resnet18/50/101 (+dilated) and hrnetv2 encoders; ppm, ppm_deepsup, c1, c1_deepsup,
 upernet, upernet_lite decoders.  Other reference arch names are recognised and raise NotImplementedError with an explanation
 (unknown names raise the reference's Exception('Architecture undefined!')).
 """
@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from ..lib.nn import SynchronizedBatchNorm2d
-from . import resnet
+from . import hrnet, resnet
 
 BatchNorm2d = SynchronizedBatchNorm2d
 
@@ -77,10 +77,12 @@ class ModelBuilder:
             net_encoder = ResnetDilated(orig, dilate_scale=8) if resnets[arch] else Resnet(orig)
         elif arch in ('resnet34', 'resnet34dilated'):
             raise NotImplementedError
-        elif arch in ('mobilenetv2dilated', 'resnext101', 'hrnetv2'):
+        elif arch == 'hrnetv2':
+            net_encoder = hrnet.__dict__['hrnetv2'](pretrained=pretrained)
+        elif arch in ('mobilenetv2dilated', 'resnext101'):
             raise NotImplementedError(
-                "encoder '%s' is part of the reference API but not yet built on the B200 engine "
-                "(hot path = ResNet-dilated + PPM; see DESIGN.md 'out of scope / next')" % arch)
+                "encoder '%s' is part of the reference API but not built on the B200 engine "
+                "(grouped / depthwise convolutions; see DESIGN.md 'out of scope')" % arch)
         else:
             raise Exception('Architecture undefined!')
         if len(weights) > 0:

@@ -37,6 +37,7 @@ def _oracle_train(enc_arch, dec_arch, fc, n, hw, stride):
     ("train_r50dilated_ppm_deepsup_96", "resnet50dilated", "ppm_deepsup", 2048, 96, 8),
     ("train_r18dilated_c1_deepsup_96", "resnet18dilated", "c1_deepsup", 512, 96, 8),
     ("train_r50_upernet_128", "resnet50", "upernet", 2048, 128, 4),
+    ("train_hrnetv2_c1_64", "hrnetv2", "c1", 720, 64, 4),
 ])
 def test_oracle_training_matches_reference_golden(name, enc, dec, fc, hw, stride):
     g = _gold(name)
@@ -47,7 +48,7 @@ def test_oracle_training_matches_reference_golden(name, enc, dec, fc, hw, stride
     pred = out[0] if isinstance(out, tuple) else out
     np.testing.assert_allclose(pred.detach().numpy(), g["pred"], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose([f.mean().item() for f in feats], g["feat_mean"], rtol=1e-4, atol=1e-6)
-    np.testing.assert_allclose(feats[3].detach()[:, ::64, ::3, ::3].numpy(), g["feat3_sample"], rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(feats[-1].detach()[:, ::64, ::3, ::3].numpy(), g["feat3_sample"], rtol=1e-3, atol=1e-4)
     for key in [k for k in g.files if k.startswith("gradnorm:")]:
         pname = key[len("gradnorm:"):]
         sd = e if pname.startswith("enc.") else d
@@ -58,14 +59,17 @@ def test_oracle_training_matches_reference_golden(name, enc, dec, fc, hw, stride
         np.testing.assert_allclose(got, ref, rtol=2e-3, atol=1e-5 * float(g[key]))
 
 
-def test_oracle_inference_matches_reference_golden():
-    g = _gold("infer_r18dilated_ppm_deepsup_96x128")
-    esd = O.synth_state_dict(O.encoder_param_shapes("resnet18dilated"), 304)
-    dsd = O.synth_state_dict(O.decoder_param_shapes("ppm_deepsup", 512), 305)
-    feed = O.synth_batch(2, 96, 128, 8, 2)
+@pytest.mark.parametrize("name,enc,dec,fc,n,h,w", [
+    ("infer_r18dilated_ppm_deepsup_96x128", "resnet18dilated", "ppm_deepsup", 512, 2, 96, 128),
+    ("infer_hrnetv2_c1_64x96", "hrnetv2", "c1", 720, 1, 64, 96),
+])
+def test_oracle_inference_matches_reference_golden(name, enc, dec, fc, n, h, w):
+    g = _gold(name)
+    esd = O.synth_state_dict(O.encoder_param_shapes(enc), 304)
+    dsd = O.synth_state_dict(O.decoder_param_shapes(dec, fc), 305)
+    feed = O.synth_batch(n, h, w, 8, 2)
     with torch.no_grad():
-        probs = O.segmentation_forward(feed, esd, dsd, "resnet18dilated", "ppm_deepsup", O.BNState(False), None,
-                                       segSize=(96, 128))
+        probs = O.segmentation_forward(feed, esd, dsd, enc, dec, O.BNState(False), None, segSize=(h, w))
     assert (probs.argmax(1).numpy().astype(np.uint8) == g["argmax"]).mean() > 0.9999
     np.testing.assert_allclose(probs[:, ::7, ::5, ::5].numpy(), g["probs_sample"], rtol=1e-4, atol=1e-6)
 
@@ -181,15 +185,20 @@ def _build_mine(enc_arch, dec_arch, fc):
     from mit_semseg.models import ModelBuilder
     from mit_semseg.models import models as M, resnet as R
     base, dil = O.parse_encoder_arch(enc_arch)
-    net = R.__dict__[base](pretrained=False)
-    enc = M.ResnetDilated(net, 8) if dil else M.Resnet(net)
+    if base == "hrnetv2":
+        from mit_semseg.models import hrnet as HR
+        enc = HR.hrnetv2(pretrained=False)
+    else:
+        net = R.__dict__[base](pretrained=False)
+        enc = M.ResnetDilated(net, 8) if dil else M.Resnet(net)
     dec = ModelBuilder.build_decoder(dec_arch, fc_dim=fc, num_class=150)
     return enc, dec
 
 
 @pytest.mark.parametrize("combo,fc", [("resnet50dilated+ppm_deepsup", 2048), ("resnet18dilated+ppm_deepsup", 512),
                                       ("resnet101+c1_deepsup", 2048), ("resnet50+ppm", 2048), ("resnet18+c1", 512),
-                                      ("resnet50+upernet", 2048), ("resnet18+upernet_lite", 512)])
+                                      ("resnet50+upernet", 2048), ("resnet18+upernet_lite", 512),
+                                      ("hrnetv2+c1", 720)])
 def test_module_tree_matches_reference_state_dict_init_and_hparams(combo, fc):
     enc_arch, dec_arch = combo.split("+")
     ref = API[combo]
@@ -209,6 +218,11 @@ def test_module_tree_matches_reference_state_dict_init_and_hparams(combo, fc):
     assert hp == ref["conv_hparams"]
     # oracle's own table of hyper-parameters (used by encoder_forward) agrees as well
     base, dil = O.parse_encoder_arch(enc_arch)
+    # the oracle's parameter table names exactly the reference's parameters
+    shapes = O.synth_state_dict(O.encoder_param_shapes(enc_arch), 1)
+    assert {k: list(v.shape) for k, v in shapes.items()} == ref["enc_keys"]
+    if base == "hrnetv2":
+        return
     block, counts = O.RESNET_LAYERS[base]
     for li, nb in enumerate(counts, start=1):
         for bi in range(nb):
