@@ -33,6 +33,7 @@ extern "C" {
 #define SSEG_MAX_SRCS 5
 #define SSEG_MAX_TAPS 9
 #define SSEG_MAX_PEERS 8
+#define SSEG_MAX_SUM_TERMS 4
 
 typedef void* sseg_stream_t; /* cudaStream_t */
 
@@ -67,7 +68,8 @@ int sseg_get_pdl(void);
  *   tap t reads X[n, h + tap_dh[t], w + tap_dw[t], :] ; out-of-range pixels read zeros (TMA out-of-bounds
  *   fill = the zero padding of nn.Conv2d).
  *   tap_src[t] == -1 : X is the virtual channel concatenation of all `nsrc` sources (same n,h,w; every c a
- *                      multiple of 64), so torch.cat (models/models.py:476) is never materialised.
+ *                      multiple of 8 - HRNet's 48/96-channel branches run as zero-filled partial 64-blocks), so
+ *                      torch.cat (models/models.py:476, models/hrnet.py:434) is never materialised.
  *   tap_src[t] == k  : tap t reads source k only (all sources then have equal c). This is how a stride-2
  *                      convolution is expressed over the 4 space-to-depth parity planes of its input.
  *   tap_koff[t]      : element offset of tap t's K segment inside one weight row.
@@ -258,6 +260,25 @@ int sseg_bilinear_fwd(const void* x, long x_ld, int N, int Hi, int Wi, int C, vo
 /* scratch: float[N*Ho*Wi*C] (the W-pass intermediate of the separable adjoint) */
 int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int C, void* dx, long dx_ld, int Hi, int Wi,
                       int accumulate, float* scratch, sseg_stream_t stream);
+
+/* HRNet exchange unit (models/hrnet.py:225-250: `y = y + x[j]` / `+ fuse_layers[i][j](x[j])` /
+ * `+ F.interpolate(fuse_layers[i][j](x[j]), ...)`, then ReLU) as ONE pass:
+ *   out[n,ho,wo,c] = relu?( sum_k ( scale_k[c] * sample_k(x_k)[n,ho,wo,c] + shift_k[c] ) )
+ * x: bf16 NHWC [N,h,w,C] dense with pixel stride ld. (h,w) == (Ho,Wo): read in place; otherwise sampled bilinearly
+ * (align_corners=False) on the fly. scale/shift: float[C] (the term's batch-norm affine, 16B aligned) or both NULL. */
+typedef struct {
+  const void* x;
+  int h, w;
+  long ld;
+  const float* scale;
+  const float* shift;
+} sseg_sum_term_t;
+int sseg_sum_terms(const sseg_sum_term_t* terms, int nterms, int N, int Ho, int Wo, int C, void* out, long out_ld, int relu,
+                   sseg_stream_t stream);
+/* Backward of that ReLU: ds = g * [out > 0] (bf16 [P][*_ld], C channels); optionally acc_out (+)= ds in the same pass
+ * (the identity term's gradient; accumulate = 0 overwrites). autograd of models/hrnet.py:248. */
+int sseg_relu_mask_bwd(const void* g, long g_ld, const void* out, long out_ld, void* ds, long ds_ld, void* acc_out,
+                       long acc_ld, int accumulate, long P, int C, sseg_stream_t stream);
 
 /* ---- loss ------------------------------------------------------------------------------- */
 /* F.log_softmax + nn.NLLLoss(ignore_index=-1) + pixel_acc (models/models.py:12-18,37-42,492-493; train.py:154).

@@ -727,6 +727,114 @@ __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// HRNet exchange unit (models/hrnet.py:225-250): out = ReLU( sum_k affine_k( resample_k( x_k ) ) ) in ONE pass.
+//   term k = a branch tensor at the output resolution (identity),
+//          | scale*y + shift of a conv output y (the term's batch norm) at the output resolution (stride-2 chains),
+//          | the same affine of a LOWER-resolution conv output, bilinearly sampled (align_corners=False) on the fly:
+//            interpolation weights sum to one, so BN-then-upsample == upsample-then-BN and the up-sampled tensor
+//            never exists in memory.
+struct SumTermsParams {
+  const __nv_bfloat16* x[SSEG_MAX_SUM_TERMS];
+  const float* scale[SSEG_MAX_SUM_TERMS];
+  const float* shift[SSEG_MAX_SUM_TERMS];
+  int h[SSEG_MAX_SUM_TERMS], w[SSEG_MAX_SUM_TERMS];
+  long ld[SSEG_MAX_SUM_TERMS];
+  int nterms, N, Ho, Wo, C, relu;
+  __nv_bfloat16* out;
+  long out_ld;
+};
+
+__global__ void __launch_bounds__(256) sum_terms_kernel(const SumTermsParams p) {
+  pdl_sync();
+  const int cg = p.C >> 3;
+  const long total = (long)p.N * p.Ho * p.Wo * cg;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    long r = idx / cg;
+    const int wo = r % p.Wo;
+    r /= p.Wo;
+    const int ho = r % p.Ho;
+    const int n = r / p.Ho;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < SSEG_MAX_SUM_TERMS; ++k) {
+      if (k >= p.nterms) break;
+      const __nv_bfloat16* x = p.x[k];
+      const int Hi = p.h[k], Wi = p.w[k];
+      const long ld = p.ld[k];
+      float v[8];
+      if (Hi == p.Ho && Wi == p.Wo) {
+        load8(x + (((long)n * Hi + ho) * Wi + wo) * ld + c0, v);
+      } else {
+        int h0, h1, w0, w1;
+        float lh, lw;
+        bilinear_coeff(ho, Hi, p.Ho, h0, h1, lh);
+        bilinear_coeff(wo, Wi, p.Wo, w0, w1, lw);
+        float a[8], b[8], c[8], d[8];
+        load8(x + (((long)n * Hi + h0) * Wi + w0) * ld + c0, a);
+        load8(x + (((long)n * Hi + h0) * Wi + w1) * ld + c0, b);
+        load8(x + (((long)n * Hi + h1) * Wi + w0) * ld + c0, c);
+        load8(x + (((long)n * Hi + h1) * Wi + w1) * ld + c0, d);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          v[e] = (1.f - lh) * ((1.f - lw) * a[e] + lw * b[e]) + lh * ((1.f - lw) * c[e] + lw * d[e]);
+      }
+      if (p.scale[k] != nullptr) {
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.scale[k] + c0));
+        const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.scale[k] + c0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.shift[k] + c0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.shift[k] + c0 + 4));
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += fmaf(v[e], sc[e], sh[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += v[e];
+      }
+    }
+    if (p.relu) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = fmaxf(acc[e], 0.f);
+    }
+    store8(p.out + (((long)n * p.Ho + ho) * p.Wo + wo) * p.out_ld + c0, acc);
+  }
+}
+
+// backward of the ReLU of an exchange output: ds = g * [out > 0] (the gradient every term of the sum receives), and the
+// identity term's share in the same pass: acc_out (+)= ds.
+__global__ void __launch_bounds__(256) relu_mask_bwd_kernel(const __nv_bfloat16* __restrict__ g, long g_ld,
+                                                            const __nv_bfloat16* __restrict__ out, long out_ld,
+                                                            __nv_bfloat16* __restrict__ ds, long ds_ld,
+                                                            __nv_bfloat16* __restrict__ acc_out, long acc_ld, int accumulate,
+                                                            long P, int C) {
+  pdl_sync();
+  const int cg = C >> 3;
+  const long total = P * cg;
+  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int c0 = (idx % cg) << 3;
+    const long pix = idx / cg;
+    float gv[8], ov[8];
+    load8(g + pix * g_ld + c0, gv);
+    load8(out + pix * out_ld + c0, ov);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) gv[e] = ov[e] > 0.f ? gv[e] : 0.f;
+    store8(ds + pix * ds_ld + c0, gv);
+    if (acc_out != nullptr) {
+      if (accumulate) {
+        float av[8];
+        load8(acc_out + pix * acc_ld + c0, av);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) av[e] += gv[e];
+        store8(acc_out + pix * acc_ld + c0, av);
+      } else {
+        store8(acc_out + pix * acc_ld + c0, gv);
+      }
+    }
+  }
+}
+
 // backward = adjoint of the separable interpolation, in two gather passes (no atomics):
 //   pass 1 (along W): tmp[n,ho,wi,c] = sum_wo  ww(wo -> wi) * dout[n,ho,wo,c]        (fp32 scratch [N,Ho,Wi,C])
 //   pass 2 (along H): dx [n,hi,wi,c] (+)= sum_ho wh(ho -> hi) * tmp[n,ho,wi,c]
@@ -1205,6 +1313,38 @@ int sseg_bilinear_fwd(const void* x, long x_ld, int N, int Hi, int Wi, int C, vo
   launch_k(bilinear_fwd_kernel, dim3(grid_for((long)N * Ho * Wo * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st, 
       (const __nv_bfloat16*)x, x_ld, N, Hi, Wi, C, (__nv_bfloat16*)out, out_ld, Ho, Wo);
   LAUNCH_CHECK("bilinear_fwd_kernel");
+}
+
+int sseg_sum_terms(const sseg_sum_term_t* terms, int nterms, int N, int Ho, int Wo, int C, void* out, long out_ld, int relu,
+                   sseg_stream_t st) {
+  SSEG_REQUIRE(terms && out && nterms >= 1 && nterms <= SSEG_MAX_SUM_TERMS, "sseg_sum_terms: 1..%d terms", SSEG_MAX_SUM_TERMS);
+  SSEG_REQUIRE(C % 8 == 0 && out_ld % 8 == 0 && N >= 1 && Ho >= 1 && Wo >= 1, "sseg_sum_terms: bad shape");
+  SumTermsParams p;
+  memset(&p, 0, sizeof(p));
+  for (int k = 0; k < nterms; ++k) {
+    const sseg_sum_term_t& t = terms[k];
+    SSEG_REQUIRE(t.x && t.h >= 1 && t.w >= 1 && t.ld % 8 == 0 && t.ld >= C, "sseg_sum_terms: term %d invalid", k);
+    SSEG_REQUIRE((t.scale == nullptr) == (t.shift == nullptr), "sseg_sum_terms: term %d scale/shift must pair", k);
+    SSEG_REQUIRE(!t.scale || ((reinterpret_cast<uintptr_t>(t.scale) | reinterpret_cast<uintptr_t>(t.shift)) & 15) == 0,
+                 "sseg_sum_terms: term %d scale/shift not 16B aligned", k);
+    p.x[k] = static_cast<const __nv_bfloat16*>(t.x), p.scale[k] = t.scale, p.shift[k] = t.shift;
+    p.h[k] = t.h, p.w[k] = t.w, p.ld[k] = t.ld;
+  }
+  p.nterms = nterms, p.N = N, p.Ho = Ho, p.Wo = Wo, p.C = C, p.relu = relu;
+  p.out = static_cast<__nv_bfloat16*>(out), p.out_ld = out_ld;
+  launch_k(sum_terms_kernel, dim3(grid_for((long)N * Ho * Wo * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st, p);
+  LAUNCH_CHECK("sum_terms_kernel");
+}
+
+int sseg_relu_mask_bwd(const void* g, long g_ld, const void* out, long out_ld, void* ds, long ds_ld, void* acc_out,
+                       long acc_ld, int accumulate, long P, int C, sseg_stream_t st) {
+  SSEG_REQUIRE(g && out && ds && C % 8 == 0 && g_ld % 8 == 0 && out_ld % 8 == 0 && ds_ld % 8 == 0 &&
+                   (!acc_out || acc_ld % 8 == 0) && P >= 1,
+               "sseg_relu_mask_bwd: bad argument");
+  launch_k(relu_mask_bwd_kernel, dim3(grid_for(P * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st,
+           (const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)out, out_ld, (__nv_bfloat16*)ds, ds_ld,
+           (__nv_bfloat16*)acc_out, acc_ld, accumulate, P, C);
+  LAUNCH_CHECK("relu_mask_bwd_kernel");
 }
 
 int sseg_bilinear_bwd(const void* dout, long dout_ld, int N, int Ho, int Wo, int C, void* dx, long dx_ld, int Hi, int Wi,

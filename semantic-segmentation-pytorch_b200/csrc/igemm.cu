@@ -1,6 +1,7 @@
 // Convolution forward / data-gradient as implicit GEMM on tcgen05 tensor cores (sm_100a).
 //
 //   D[pixel, co] = sum over K-steps (tap t, 64-channel block b) of  A_tb[pixel, 64] . B[co, t, b*64 : b*64+64]
+//   (source channel counts need not be multiples of 64: a partial block is zero-filled by TMA)
 //
 //   M = 128 output pixels (a BH x BW spatial box of one image), N = BLOCK_N output channels, K-step = 64 channels.
 //   A tile: ONE 4-D TMA box load (64 ch, BW, BH, 1) from the NHWC activation at the tap-shifted coordinate
@@ -27,7 +28,8 @@ struct IgemmParams {
   CUtensorMap tmA[SSEG_MAX_SRCS];
   CUtensorMap tmB;
   int nsrc;
-  int src_blk_end[SSEG_MAX_SRCS];  // cumulative count of 64-channel blocks
+  int src_blk_end[SSEG_MAX_SRCS];  // cumulative count of 64-channel blocks (a source's last block may be partial)
+  int src_choff[SSEG_MAX_SRCS];    // channel offset of each source inside the virtual concat (= its weight K offset)
   int blocks_per_tap;
   int ntaps;
   int tap_dh[SSEG_MAX_TAPS], tap_dw[SSEG_MAX_TAPS], tap_src[SSEG_MAX_TAPS], tap_koff[SSEG_MAX_TAPS];
@@ -127,7 +129,10 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
           uint8_t* sa = smem + stage * L::kStageBytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
-          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], p.tap_koff[t] + b * kBlockK, n0);
+          // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
+          // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
+          const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -398,7 +403,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
           uint8_t* sa = smem + stage * L::kStageBytes;
           mbar_expect_tx(&full_bar[stage], L::kStageBytes);
           tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
-          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], p.tap_koff[t] + b * kBlockK, n0);
+          // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
+          // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
+          const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
@@ -654,6 +662,8 @@ struct GeomHost {
   int vn, vh, vw, BH, BW, bw_shift, tiles_h, tiles_w;
   int cin_total, blocks_per_tap, chan_per_src;
   bool flat;
+  bool ragged;  // some source's channel count is not a multiple of 64
+  int src_choff[SSEG_MAX_SRCS], src_c[SSEG_MAX_SRCS];
 };
 
 static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, bool others_dense, GeomHost* gh, CUtensorMap* tmA,
@@ -684,11 +694,12 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, bool others_den
   gh->bw_shift = 0;
   while ((1 << gh->bw_shift) < BW) ++gh->bw_shift;
   gh->tiles_h = ceil_div(gh->vh, gh->BH), gh->tiles_w = ceil_div(gh->vw, BW);
-  int cin_total = 0;
+  int cin_total = 0, blocks = 0;
+  gh->ragged = false;
   for (int s = 0; s < g->nsrc; ++s) {
     const sseg_act_t& a = g->srcs[s];
     SSEG_REQUIRE(a.n == N && a.h == H && a.w == W, "%s: source %d shape mismatch", who, s);
-    SSEG_REQUIRE(a.c % kBlockK == 0 && a.c > 0, "%s: source %d channels %d not a multiple of 64", who, s, a.c);
+    SSEG_REQUIRE(a.c % 8 == 0 && a.c > 0, "%s: source %d channels %d not a multiple of 8", who, s, a.c);
     SSEG_REQUIRE(a.ld % 8 == 0 && a.ld >= a.c, "%s: source %d ld %d invalid", who, s, a.ld);
     SSEG_REQUIRE(!any_fixed || a.c == g->srcs[0].c, "%s: per-tap sources must have equal channels", who);
     int rc = gh->flat ? get_tmap_act(&tmA[s], a.ptr, 2, 1, 1, gh->vw, a.c, a.ld, (long)gh->vw * a.ld,
@@ -696,11 +707,14 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, bool others_den
                       : get_tmap_act(&tmA[s], a.ptr, 2, N, H, W, a.c, a.ld, a.row_stride, a.img_stride, kBlockK, BW,
                                      gh->BH);
     if (rc) return rc;
+    gh->src_choff[s] = cin_total, gh->src_c[s] = a.c;
+    if (a.c % kBlockK != 0) gh->ragged = true;
     cin_total += a.c;
-    src_blk_end[s] = cin_total / kBlockK;
+    blocks += ceil_div(a.c, kBlockK);
+    src_blk_end[s] = blocks;
   }
   gh->cin_total = cin_total;
-  gh->blocks_per_tap = cin_total / kBlockK;
+  gh->blocks_per_tap = blocks;
   gh->chan_per_src = g->srcs[0].c;
   return 0;
 }
@@ -740,8 +754,9 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     p.tap_koff[t] = g->tap_koff[t];
     const int span = g->tap_src[t] >= 0 ? gh.chan_per_src : gh.cin_total;
     SSEG_REQUIRE(g->tap_koff[t] + span <= w_ld, "sseg_conv_igemm: tap %d K range exceeds w_ld", t);
-    p.num_k_steps += span / kBlockK;
+    p.num_k_steps += g->tap_src[t] >= 0 ? ceil_div(gh.chan_per_src, kBlockK) : gh.blocks_per_tap;
   }
+  for (int s = 0; s < g->nsrc; ++s) p.src_choff[s] = gh.src_choff[s];
   // N tile: 128 unless that leaves most SMs without a CTA: then halve it to double the grid. Threshold swept on B200
   // (whole training step, CUDA-graph replay): 0 -> 6.58 ms, 80 -> 6.56, 160 -> 6.80, 300 -> 7.17, 600 -> 7.36.
   const int m_tiles = gh.vn * gh.tiles_h * gh.tiles_w;
@@ -843,6 +858,8 @@ struct WgradParams {
   int BH, BW, tiles_h, tiles_w;
   int total_boxes, boxes_per_split;
   int cout, ci_span;     // valid co rows; valid ci per tap
+  int ragged;            // some source has channels % 64 != 0: ci tiles are single 64-blocks of ONE source
+  int src_choff[SSEG_MAX_SRCS], src_c[SSEG_MAX_SRCS];
   float* dw;
   long dw_ld;
 };
@@ -963,7 +980,17 @@ __global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constan
     const int quarter = warp & 3;
     const int co = co0 + quarter * 32 + lane;
     const bool valid = co < p.cout;
-    float* drow = p.dw + static_cast<size_t>(co) * p.dw_ld + p.tap_koff[tap] + ci0;
+    // columns of dW this tile owns: [colbase, colbase + width) inside the tap (width may exceed BLOCK_N: no clipping)
+    int colbase = ci0, width = p.ci_span - ci0;
+    if (p.tap_src[tap] < 0) {
+      const int blk0 = ci0 / 64;
+      int s = 0, begin = 0;
+      while (s + 1 < p.nsrc && blk0 >= p.src_blk_end[s]) begin = p.src_blk_end[s], ++s;
+      const int chan = (blk0 - begin) * 64;
+      colbase = p.src_choff[s] + chan;
+      width = p.ragged ? p.src_c[s] - chan : p.ci_span - colbase;
+    }
+    float* drow = p.dw + static_cast<size_t>(co) * p.dw_ld + p.tap_koff[tap] + colbase;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -974,7 +1001,7 @@ __global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constan
       if (valid) {
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
-          if (ci0 + chunk * 32 + g * 4 < p.ci_span) {
+          if (chunk * 32 + g * 4 < width) {
             float4 f = make_float4(__uint_as_float(raw[g * 4]), __uint_as_float(raw[g * 4 + 1]),
                                    __uint_as_float(raw[g * 4 + 2]), __uint_as_float(raw[g * 4 + 3]));
             atomicAdd(reinterpret_cast<float4*>(drow + chunk * 32 + g * 4), f);
@@ -1038,8 +1065,10 @@ extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, 
     SSEG_REQUIRE((g->tap_src[t] >= 0) == fixed, "sseg_conv_wgrad: taps must be all concat or all per-plane");
     SSEG_REQUIRE(g->tap_koff[t] % 4 == 0 && g->tap_koff[t] + p.ci_span <= dw_ld, "sseg_conv_wgrad: tap %d K range", t);
   }
-  const int block_n = (p.ci_span % 128 == 0) ? 128 : 64;
-  p.ci_tiles_per_tap = p.ci_span / block_n;
+  p.ragged = gh.ragged ? 1 : 0;
+  for (int s = 0; s < g->nsrc; ++s) p.src_choff[s] = gh.src_choff[s], p.src_c[s] = gh.src_c[s];
+  const int block_n = (!gh.ragged && p.ci_span % 128 == 0) ? 128 : 64;
+  p.ci_tiles_per_tap = fixed ? ceil_div(gh.chan_per_src, block_n) : (gh.ragged ? gh.blocks_per_tap : p.ci_span / block_n);
   SSEG_REQUIRE(cout >= 1 && cout <= dy->c, "sseg_conv_wgrad: cout %d vs dy channels %d", cout, dy->c);
   p.cout = cout;
   p.m_tiles = ceil_div(p.cout, 128);

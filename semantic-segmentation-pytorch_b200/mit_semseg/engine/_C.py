@@ -12,6 +12,7 @@ LIB_PATH = os.path.abspath(os.path.join(_HERE, "..", "..", os.environ.get("SSEG_
 
 MAX_SRCS = 5
 MAX_TAPS = 9
+MAX_SUM_TERMS = 4
 
 
 class SsegError(RuntimeError):
@@ -35,6 +36,11 @@ class WeightDesc(Structure):
     _fields_ = [("w", c_void_p), ("wf", c_void_p), ("wd", c_void_p), ("g_src", c_void_p), ("g_dst", c_void_p),
                 ("fwd_ld", c_long), ("dgrad_ld", c_long), ("g_ld", c_long), ("O", c_int), ("I", c_int), ("T", c_int),
                 ("o_pad", c_int), ("first_tile", c_int), ("reserved", c_int)]
+
+
+class SumTerm(Structure):
+    """sseg_sum_term_t: one term of an HRNet exchange-unit sum."""
+    _fields_ = [("x", c_void_p), ("h", c_int), ("w", c_int), ("ld", c_long), ("scale", c_void_p), ("shift", c_void_p)]
 
 
 class SgdChunk(Structure):
@@ -117,6 +123,8 @@ _SIGNATURES = {
     "sseg_avgpool_bwd": [_p, c_long, POINTER(c_void_p), _ip, c_int, _p, c_long, c_int, c_int, c_int, c_int, _p],
     "sseg_bilinear_fwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, _p],
     "sseg_bilinear_bwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, c_int, _p, _p],
+    "sseg_sum_terms": [POINTER(SumTerm), c_int, c_int, c_int, c_int, c_int, _p, c_long, c_int, _p],
+    "sseg_relu_mask_bwd": [_p, c_long, _p, c_long, _p, c_long, _p, c_long, c_int, c_long, c_int, _p],
     "sseg_softmax_nll_fwd": [_p, c_long, c_int, _p, c_long, _p, _p, _p],
     "sseg_nll_finalize": [_p, _p, c_float, _p, _p],
     "sseg_softmax_nll_bwd": [_p, c_long, c_int, _p, _p, _p, c_float, c_long, _p, c_long, c_int, _p],

@@ -265,6 +265,35 @@ def bilinear_bwd(dout, dx, accumulate=False, scratch=None):
                                         int(accumulate), _C.ptr(scratch), _stream()))
 
 
+def make_sum_terms(terms):
+    """[(x NHWC bf16, scale or None, shift or None), ...] -> ctypes array of sseg_sum_term_t (keep the tensors alive)."""
+    arr = (_C.SumTerm * len(terms))()
+    for k, (x, scale, shift) in enumerate(terms):
+        _, _, ld = _pix(x)
+        arr[k].x, arr[k].h, arr[k].w, arr[k].ld = x.data_ptr(), x.shape[1], x.shape[2], ld
+        arr[k].scale = scale.data_ptr() if scale is not None else None
+        arr[k].shift = shift.data_ptr() if shift is not None else None
+    return arr
+
+
+def sum_terms(terms, out, relu=True):
+    """out = relu?(sum_k scale_k * resample(x_k) + shift_k); `terms` from make_sum_terms or a list of tuples."""
+    if isinstance(terms, (list, tuple)):
+        terms = make_sum_terms(terms)
+    n, ho, wo, c = out.shape
+    _C.check(_C.lib().sseg_sum_terms(terms, len(terms), n, ho, wo, c, _C.ptr(out), _pix(out)[2], int(relu), _stream()))
+    return out
+
+
+def relu_mask_bwd(g, out, ds, acc_out=None, accumulate=False):
+    """ds = g * [out > 0]; acc_out (+)= ds."""
+    P, _, g_ld = _pix(g)
+    _C.check(_C.lib().sseg_relu_mask_bwd(_C.ptr(g), g_ld, _C.ptr(out), _pix(out)[2], _C.ptr(ds), _pix(ds)[2],
+                                         _C.ptr(acc_out), _pix(acc_out)[2] if acc_out is not None else 0,
+                                         int(accumulate), P, g.shape[3], _stream()))
+    return ds
+
+
 def softmax_nll_fwd(logits, num_class, label, lse, accum):
     P, _, ld = _pix(logits)
     assert label.dtype == torch.int64 and label.is_contiguous() and label.numel() == P

@@ -40,10 +40,13 @@ def _dist():
 
 class Act:
     """An activation tensor (NHWC bf16) plus, during backward construction, its gradient buffer."""
-    __slots__ = ("t", "g", "gw", "uses", "producer")
+    __slots__ = ("t", "tp", "g", "gw", "uses", "producer")
 
-    def __init__(self, t):
-        self.t, self.g, self.gw = t, None, False
+    def __init__(self, t, tp=None):
+        # t: the logical tensor (c channels; what convolutions read). tp: the same storage with the channel count
+        # rounded up to 8 (zero pad channels) — what the 8-channel-vectorised elementwise kernels and gradient
+        # writers see. They differ only for widths like HRNet+C1's 180-channel hidden layer.
+        self.t, self.tp, self.g, self.gw = t, (t if tp is None else tp), None, False
         self.uses = 0          # number of consumers in the forward schedule
         self.producer = None   # the ConvBNRec / StemRec that wrote it (if any)
 
@@ -59,6 +62,7 @@ class ConvW:
         self.stride, self.dil, self.pad = mod.stride[0], mod.dilation[0], mod.padding[0]
         assert mod.stride[0] == mod.stride[1] and self.pad == self.dil * (self.k // 2), "only 'same' padding is supported"
         self.Opad = _pad(self.O, 64)
+        self.ldf = _pad(self.T * self.I, 8)   # forward operand row pitch (TMA wants 16-byte multiples)
         self.wf = self.wd = self.gw = self.gb = None  # views, assigned by SegProgram._alloc_params
 
 
@@ -67,18 +71,22 @@ class BNS:
 
     def __init__(self, mod):
         self.mod, self.C = mod, mod.num_features
+        self.Cp = _pad(self.C, 8)  # vector length seen by the 8-channel-vectorised kernels (pad entries stay 0)
         self.stats = self.mean = self.invstd = self.scale = self.shift = self.dgamma = self.dbeta = None
 
 
 class SegProgram:
     def __init__(self, seg, img_shape, training, with_grad=True, seg_size=None, dropout_masks=None, part="full",
-                 enc=None, dec=None, feat_shapes=None):
+                 enc=None, dec=None, feat_shapes=None, dry_run=False):
         """seg: SegmentationModule.  img_shape: (N, 3, H, W).  training: module.training (BN/dropout behaviour).
         with_grad: also build the backward schedule.  seg_size: inference branch (probabilities at seg_size).
         dropout_masks: optional {'main': [N,512] 0/1, 'deepsup': ...} to inject the Dropout2d draws (tests).
         part: "full" (encoder + decoder + loss/head) | "encoder" (module called on its own: fp32 NCHW feature maps out)
               | "decoder" (fp32 NCHW feature maps of `feat_shapes` in, log-probs / probabilities out); the partial
-              programs are forward-only."""
+              programs are forward-only.
+        dry_run: build the schedule only (shape inference, buffer plan, record wiring) — used by the CPU tests of the
+              host logic; such a program refuses to run."""
+        self.dry_run = bool(dry_run)
         self.seg = seg
         self.part = part
         self.enc = enc if enc is not None else (seg.encoder if seg is not None else None)
@@ -99,7 +107,7 @@ class SegProgram:
         self.seg_size = seg_size
         self.with_grad = bool(with_grad) and not self.inference
         self.dev = next((self.enc if self.enc is not None else self.dec).parameters()).device
-        assert self.dev.type == "cuda", "the B200 engine runs on CUDA devices only (no CPU fallback)"
+        assert self.dev.type == "cuda" or self.dry_run, "the B200 engine runs on CUDA devices only (no CPU fallback)"
         self.injected_masks = dropout_masks
         self.dist = _dist()
         self.world = self.dist.get_world_size() if self.dist else 1
@@ -115,7 +123,7 @@ class SegProgram:
         self.graph = None
         # weight-gradient GEMMs are off the critical path of the backward pass (nothing downstream reads them until
         # the gradient bucket): they run on a side stream and fill the SMs the data-gradient chain leaves idle
-        self.side = torch.cuda.Stream(self.dev)
+        self.side = torch.cuda.Stream(self.dev) if self.dev.type == "cuda" else None
 
         self.convs, self.bns = {}, {}
         for m in self._modules():
@@ -145,18 +153,19 @@ class SegProgram:
     def _alloc_params(self):
         dev = self.dev
         nf = sum(c.O * c.T * c.I for c in self.convs.values())
+        nff = sum(c.O * c.ldf for c in self.convs.values())
         nd = sum(c.I * c.T * c.Opad for c in self.convs.values())
-        self.wf_flat = torch.empty(nf, device=dev, dtype=torch.bfloat16)
+        self.wf_flat = torch.zeros(nff, device=dev, dtype=torch.bfloat16)
         self.wd_flat = torch.zeros(nd if self.with_grad else 0, device=dev, dtype=torch.bfloat16)
-        small = sum(2 * b.C for b in self.bns.values()) + sum(_pad(c.O, 4) for c in self.convs.values()
+        small = sum(2 * b.Cp for b in self.bns.values()) + sum(_pad(c.O, 4) for c in self.convs.values()
                                                                if c.mod.bias is not None)
         self.g_small = small
         self.gflat = torch.zeros((small + nf) if self.with_grad else 0, device=dev, dtype=torch.float32)
-        ns = sum(_pad(2 * b.C + 1, 4) + b.C for b in self.bns.values()) + 8   # + C: raw sum g'*y of the fused dgrad
+        ns = sum(_pad(2 * b.C + 1, 4) + b.Cp for b in self.bns.values()) + 8  # + Cp: raw sum g'*y of the fused dgrad
         # with several ranks the statistics live in a peer-mapped arena (SyncBN without NCCL calls, csrc/peer.cu):
         # [per-BN sum|sqsum|count ... loss accumulators | per-BN s1|s2 partials ... | flags (int) | step (int)]
         self.peer = None
-        npart = sum(2 * b.C for b in self.bns.values())
+        npart = sum(2 * b.Cp for b in self.bns.values())
         import os
         if self.dist is not None and self.training and os.environ.get("SSEG_PEER_SYNC", "1") != "0":
             from .peer import PeerArena
@@ -178,13 +187,13 @@ class SegProgram:
         else:
             self.sflat = torch.zeros(ns, device=dev, dtype=torch.float32)
         self.sinit = torch.zeros(self.sflat.numel(), device=dev, dtype=torch.float32)
-        nv = sum(4 * b.C for b in self.bns.values())
-        self.vflat = torch.empty(nv, device=dev, dtype=torch.float32)
+        nv = sum(4 * b.Cp for b in self.bns.values())
+        self.vflat = torch.zeros(nv, device=dev, dtype=torch.float32)
         of = od = 0
         og, ogs = small, 0
         for c in self.convs.values():
-            c.wf = self.wf_flat[of:of + c.O * c.T * c.I].view(c.O, c.T * c.I)
-            of += c.O * c.T * c.I
+            c.wf = self.wf_flat[of:of + c.O * c.ldf].view(c.O, c.ldf)[:, :c.T * c.I]
+            of += c.O * c.ldf
             if self.with_grad:
                 c.wd = self.wd_flat[od:od + c.I * c.T * c.Opad].view(c.I, c.T * c.Opad)
                 od += c.I * c.T * c.Opad
@@ -199,20 +208,20 @@ class SegProgram:
             b.stats = self.sflat[os_:os_ + 2 * b.C + 1]
             b.stats_off = os_
             os_ += _pad(2 * b.C + 1, 4)
-            b.s2y = self.sflat[os_:os_ + b.C]
-            os_ += b.C
+            b.s2y = self.sflat[os_:os_ + b.Cp]
+            os_ += b.Cp
             if self.peer is not None:
-                b.part = self.sflat[op_:op_ + 2 * b.C]  # [s1 | s2] partial sums of the backward pass
+                b.part = self.sflat[op_:op_ + 2 * b.Cp]  # [s1 | s2] partial sums of the backward pass
                 b.part_off, b.flag_off = op_, ofl
-                op_ += 2 * b.C
+                op_ += 2 * b.Cp
                 ofl += 16
-                b.tot = torch.zeros(2 * b.C + 1, device=dev, dtype=torch.float32)  # s1_tot | s2_tot | pooled count
-            b.mean, b.invstd, b.scale, b.shift = (self.vflat[ov + i * b.C: ov + (i + 1) * b.C] for i in range(4))
-            ov += 4 * b.C
+                b.tot = torch.zeros(2 * b.Cp + 1, device=dev, dtype=torch.float32)  # s1_tot | s2_tot | pooled count
+            b.mean, b.invstd, b.scale, b.shift = (self.vflat[ov + i * b.Cp: ov + (i + 1) * b.Cp] for i in range(4))
+            ov += 4 * b.Cp
             if self.with_grad:
-                b.dgamma = self.gflat[ogs:ogs + b.C]
-                b.dbeta = self.gflat[ogs + b.C:ogs + 2 * b.C]
-                ogs += 2 * b.C
+                b.dgamma = self.gflat[ogs:ogs + b.Cp]
+                b.dbeta = self.gflat[ogs + b.Cp:ogs + 2 * b.Cp]
+                ogs += 2 * b.Cp
         self.acc_main = self.sflat[os_:os_ + 4]
         self.acc_ds = self.sflat[os_ + 4:os_ + 8]
         if self.peer is not None:
@@ -222,6 +231,12 @@ class SegProgram:
     def _new(self, *shape, dtype=torch.bfloat16, zero=False):
         f = torch.zeros if zero else torch.empty
         return f(shape, device=self.dev, dtype=dtype)
+
+    def _new_act(self, n, h, w, c):
+        """Activation with its channel count rounded up to 8 in storage (zero pad channels)."""
+        cp = _pad(c, 8)
+        buf = self._new(n, h, w, cp, zero=(cp != c))
+        return Act(buf[..., :c] if cp != c else buf, buf)
 
     def _bn_mode(self, bns):
         if not self.training or not bns.mod.training:
@@ -295,15 +310,27 @@ class SegProgram:
             # module-level call encoder(x, return_feature_maps=True): hand the maps back as fp32 NCHW tensors
             self.feat_out = []
             for f in feats:
-                n, h, w, c = f.t.shape
-                dst = self._new(n, c, h, w, dtype=torch.float32)
-                self.fwd.append(lambda f=f, dst=dst: ops.nhwc_bf16_to_nchw_f32(f.t, dst))
+                parts = f if isinstance(f, list) else [f]   # HRNet hands back one map = concat of its 4 branches
+                n, h, w, _ = parts[0].t.shape
+                dst = self._new(n, sum(q.t.shape[3] for q in parts), h, w, dtype=torch.float32)
+                off = 0
+                for q in parts:
+                    c = q.t.shape[3]
+                    if len(parts) == 1:
+                        self.fwd.append(lambda q=q, dst=dst: ops.nhwc_bf16_to_nchw_f32(q.t, dst))
+                    else:
+                        tmp = self._new(n, c, h, w, dtype=torch.float32)
+                        self.fwd.append(lambda q=q, tmp=tmp, sl=dst[:, off:off + c]: (ops.nhwc_bf16_to_nchw_f32(q.t, tmp),
+                                                                                    sl.copy_(tmp)))
+                    off += c
                 self.feat_out.append(dst)
             return
         # ---- decoder
         dec = self.dec
         self.logits_ds = None
         p_drop_main = p_drop_ds = 0.0
+        if not isinstance(dec, (M.C1, M.C1DeepSup)) and any(isinstance(f, list) for f in feats):
+            raise NotImplementedError("HRNetV2 features (a virtual concat of 4 branches) feed the C1 decoders only")
         if isinstance(dec, (M.PPM, M.PPMDeepsup)):
             conv5 = feats[-1]
             n, h, w, c5 = conv5.t.shape
@@ -404,8 +431,81 @@ class SegProgram:
             loss = LossRec(self)
             self.records.append(loss)
 
+    def _residual_chain(self, x, blocks):
+        """nn.Sequential of BasicBlock / Bottleneck: (conv, bn) stages, identity or projected shortcut, ReLU."""
+        for block in blocks:
+            inp = x
+            res = inp
+            if block.downsample is not None:
+                res = self.conv_bn(inp, block.downsample[0], block.downsample[1], relu=False, apply=False)
+            stages = block.stages()
+            for i, (cv, bn) in enumerate(stages):
+                last = i == len(stages) - 1
+                x = self.conv_bn(x, cv, bn, relu=True, res=res if last else None)
+        return x
+
+    def _build_hrnet(self):
+        """HRNetV2.forward / HighResolutionModule.forward (reference models/hrnet.py:395-437, :225-250)."""
+        enc = self.enc
+        assert self.H % 32 == 0 and self.W % 32 == 0, "HRNetV2 needs H, W multiples of 32 (five stride-2 levels)"
+        stem = StemRec(self, self.convs[id(enc.conv1)], self.bns[id(enc.bn1)])
+        self.records.append(stem)
+        x = self.conv_bn(stem.a, enc.conv2, enc.bn2)
+        x = self._residual_chain(x, enc.layer1)
+        ys = [x]
+        for si in (2, 3, 4):
+            trans, stage = getattr(enc, "transition%d" % (si - 1)), getattr(enc, "stage%d" % si)
+            xs = []
+            for i, tr in enumerate(trans):
+                if i < len(ys):
+                    if tr is None:
+                        xs.append(ys[i])
+                    else:  # the reference feeds y_list[-1] here from stage 3 on (hrnet.py:414-430); None for W48
+                        xs.append(self.conv_bn(ys[-1] if si > 2 else ys[i], tr[0], tr[1]))
+                else:
+                    t = ys[-1]
+                    for link in tr:
+                        t = self.conv_bn(t, link[0], link[1])
+                    xs.append(t)
+            for module in stage:
+                xs = self._hr_module(module, xs)
+            ys = xs
+        _, h, w, _ = ys[0].t.shape
+        srcs = [ys[0]]
+        for y in ys[1:]:
+            ur = UpsampleRec(self, y, h, w)
+            self.records.append(ur)
+            srcs.append(ur.a)
+        return [srcs]   # one feature map: the virtual concat of the four branches (torch.cat at hrnet.py:434)
+
+    def _hr_module(self, module, xs):
+        nb = module.num_branches
+        xs = [self._residual_chain(xs[i], module.branches[i]) for i in range(nb)]
+        if module.fuse_layers is None:
+            return xs
+        outs = []
+        for i, row in enumerate(module.fuse_layers):
+            terms = []
+            for j in range(nb):
+                if j == i:
+                    terms.append(("id", xs[j]))
+                elif j > i:   # 1x1 conv + BN at the low resolution; the up-sampling happens inside the sum kernel
+                    terms.append(("up", self.conv_bn(xs[j], row[j][0], row[j][1], relu=False, apply=False)))
+                else:         # chain of stride-2 3x3 convs, ReLU between the links only
+                    t, links = xs[j], list(row[j])
+                    for link in links[:-1]:
+                        t = self.conv_bn(t, link[0], link[1])
+                    terms.append(("same", self.conv_bn(t, links[-1][0], links[-1][1], relu=False, apply=False)))
+            sr = SumRec(self, terms)
+            self.records.append(sr)
+            outs.append(sr.a)
+        return outs
+
     def _build_encoder(self, R):
         enc = self.enc
+        from ..models import hrnet as HR
+        if isinstance(enc, HR.HRNetV2):
+            return self._build_hrnet()
         # ---- stem (reference models/resnet.py:100-109, models/models.py:256-259)
         stem = StemRec(self, self.convs[id(enc.conv1)], self.bns[id(enc.bn1)])
         self.records.append(stem)
@@ -417,16 +517,7 @@ class SegProgram:
         x = mp.a
         feats = []
         for layer in (enc.layer1, enc.layer2, enc.layer3, enc.layer4):
-            for block in layer:
-                assert isinstance(block, (R.BasicBlock, R.Bottleneck))
-                inp = x
-                res = inp
-                if block.downsample is not None:
-                    res = self.conv_bn(inp, block.downsample[0], block.downsample[1], relu=False, apply=False)
-                stages = block.stages()
-                for i, (cv, bn) in enumerate(stages):
-                    last = i == len(stages) - 1
-                    x = self.conv_bn(x, cv, bn, relu=True, res=res if last else None)
+            x = self._residual_chain(x, layer)
             feats.append(x)
         return feats
 
@@ -451,7 +542,8 @@ class SegProgram:
         buckets = []
         if self.dist is not None and self.enc is not None and self.dec is not None:
             dec_ids = {id(m) for m in self.dec.modules()}
-            l4_ids = {id(m) for m in self.enc.layer4.modules()}
+            late = self.enc.layer4 if hasattr(self.enc, "layer4") else self.enc.stage4   # the encoder's last stage
+            l4_ids = {id(m) for m in late.modules()}
             off = lambda ids: min(c.gw.storage_offset() for c in self.convs.values() if id(c.mod) in ids)
             dec_off, l4_off = off(dec_ids), off(l4_ids)
             assert l4_off < dec_off
@@ -513,7 +605,7 @@ class SegProgram:
     def grad_target(self, act, shape_like=None):
         """(buffer, accumulate?) for writing a gradient contribution of `act`."""
         if act.g is None:
-            act.g = torch.empty_like(act.t if shape_like is None else shape_like)
+            act.g = torch.empty_like(act.tp if shape_like is None else shape_like)
         acc = act.gw
         act.gw = True
         return act.g, acc
@@ -529,6 +621,8 @@ class SegProgram:
             self.label.copy_(label, non_blocking=True)
 
     def run_eager(self):
+        if self.dry_run:
+            raise RuntimeError("a dry-run program only describes the schedule; there is no CPU execution path")
         for f in self.fwd:
             f()
         for f in self.bwd:
@@ -578,8 +672,8 @@ class SegProgram:
                 out[c.mod.bias] = c.gb
         for b in self.bns.values():
             if b.mod.weight is not None:
-                out[b.mod.weight] = b.dgamma
-                out[b.mod.bias] = b.dbeta
+                out[b.mod.weight] = b.dgamma[:b.C]
+                out[b.mod.bias] = b.dbeta[:b.C]
         return out
 
 
@@ -618,8 +712,10 @@ class StemRec:
 
 def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, chanmul, res_after_relu=False):
     m = bns.mod
-    C = bns.C
+    C, Cp = bns.C, bns.Cp
     st = bns.stats
+    # finalize works on the C real channels; apply / backward kernels on the Cp-long (zero padded) vectors
+    mean, invstd, scale, shift = bns.mean[:C], bns.invstd[:C], bns.scale[:C], bns.shift[:C]
     running = (m.running_mean, m.running_var, getattr(m, "_tmp_running_mean", None), getattr(m, "_tmp_running_var", None),
                getattr(m, "_running_iter", None))
     upd = mode != ops.BN_EVAL and m.track_running_stats and m.running_mean is not None
@@ -630,11 +726,11 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
         # local pixel count rides along with the sums so ranks with different batch shapes pool correctly
         P.sinit[bns.stats_off + 2 * C] = float(count)
     if mode == ops.BN_TRAIN_SYNC and P.peer is not None:
-        cnt_out = bns.tot[2 * C:2 * C + 1]
+        cnt_out = bns.tot[2 * Cp:2 * Cp + 1]
         P.fwd.append(lambda: ops.bn_finalize_peer(P.peer, bns.stats_off, bns.flag_off, P.peer_step, w, b, m.eps, mom,
-                                                  bns.mean, bns.invstd, bns.scale, bns.shift, cnt_out, running=running,
+                                                  mean, invstd, scale, shift, cnt_out, running=running,
                                                   update_running=upd))
-    elif mode == ops.BN_TRAIN and out is not None and P.fuse_finalize:
+    elif mode == ops.BN_TRAIN and out is not None and P.fuse_finalize and C == Cp:
         # single-GPU training: finalize fused into the apply kernel (one kernel boundary less per layer)
         rmean, rvar = (m.running_mean, m.running_var) if upd else (None, None)
         P.fwd.append(lambda: ops.bn_finalize_apply(st[:C], st[C:2 * C], count, w, b, m.eps, mom, bns.mean, bns.invstd,
@@ -646,8 +742,8 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
         if mode == ops.BN_TRAIN_SYNC and P.dist is not None:
             P.fwd.append(lambda: P.dist.all_reduce(st))
         cdev = st[2 * C:2 * C + 1] if mode == ops.BN_TRAIN_SYNC else None
-        P.fwd.append(lambda: ops.bn_finalize(st[:C], st[C:2 * C], count, w, b, m.eps, mom, mode, bns.mean, bns.invstd,
-                                             bns.scale, bns.shift, running=running, update_running=upd, count_dev=cdev))
+        P.fwd.append(lambda: ops.bn_finalize(st[:C], st[C:2 * C], count, w, b, m.eps, mom, mode, mean, invstd,
+                                             scale, shift, running=running, update_running=upd, count_dev=cdev))
     if out is not None:
         P.fwd.append(lambda: ops.bn_apply(y, bns.scale, bns.shift, out, relu=relu, res=res, rscale=rscale, rshift=rshift,
                                           chanmul=chanmul, res_after_relu=res_after_relu))
@@ -656,7 +752,7 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
 def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from_y=False, fused=False):
     """g: gradient w.r.t. the layer output.  ReLU mask: `a` (saved output) if given, else recomputed from y when
     mask_from_y (layers without a shortcut), else the layer has no ReLU."""
-    C = bns.C
+    C = bns.Cp  # vector length of the backward kernels (= channels of g / y / dy in storage)
     st = bns.stats
     sc = bns.scale
     fs = bns.shift if (mask_from_y and a is None) else None
@@ -695,7 +791,7 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from
                                            scale=sc, fshift=fs))
     cdev = None
     if mode == ops.BN_TRAIN_SYNC:
-        cdev = st[2 * C:2 * C + 1]
+        cdev = st[2 * bns.C:2 * bns.C + 1]
         if P.dist is not None:
             # dgamma|dbeta are adjacent in the flat gradient buffer: one all-reduce for both
             both = P.gflat[bns.dgamma.storage_offset():bns.dgamma.storage_offset() + 2 * C]
@@ -721,7 +817,8 @@ class ConvBNRec:
         assert sum(s.shape[3] for s in srcs) == cw.I
         self.geom, ho, wo = P._conv_geom(srcs, cw)
         n = srcs[0].shape[0]
-        self.y = P._new(n, ho, wo, cw.O)
+        assert bns.C == cw.O
+        self.y = P._new(n, ho, wo, bns.Cp)   # channels >= cw.O are written as zeros by the conv kernel
         self.mode = P._bn_mode(bns)
         self.count = n * ho * wo
         st = bns.stats
@@ -732,16 +829,16 @@ class ConvBNRec:
                                             stat_sqsum=st[C:2 * C] if train else None))
         self.fused = False  # set by the (single) consumer when its dgrad epilogue does this layer's BN-backward reduce
         if apply:
-            self.a = Act(P._new(n, ho, wo, cw.O))
+            self.a = P._new_act(n, ho, wo, cw.O)
             self.a.producer = self
             r = rs = rb = None
             if isinstance(res, Act):
-                r = res.t
+                r = res.tp
             elif isinstance(res, ConvBNRec):
                 r, rs, rb = res.y, res.bns.scale, res.bns.shift
             if post_add is not None:
-                r = post_add.t
-            _emit_bn_forward(P, bns, self.mode, self.count, y, self.a.t, relu, r, rs, rb, chanmul,
+                r = post_add.tp
+            _emit_bn_forward(P, bns, self.mode, self.count, y, self.a.tp, relu, r, rs, rb, chanmul,
                              res_after_relu=post_add is not None)
         else:
             self.a = None
@@ -769,7 +866,7 @@ class ConvBNRec:
             dres = torch.empty_like(ds_rec.y)
         has_relu = self.apply and self.relu
         from_y = has_relu and self.res is None          # no shortcut: the mask is a function of y alone
-        a = self.a.t if (has_relu and not from_y) else None
+        a = self.a.tp if (has_relu and not from_y) else None
         _emit_bn_backward(P, bns, self.mode, self.count, g, a, self.y, dy, dres, self.chanmul, mask_from_y=from_y,
                           fused=self.fused)
         if ds_rec is not None:
@@ -803,7 +900,7 @@ class ConvBNRec:
             wd, I = cw.wd, cw.I
             prod = xs[0].producer if len(xs) == 1 else None
             fuse = (P.fuse_bnbwd and prod is not None and not acc and xs[0].uses == 1 and prod.apply and prod.relu and
-                    prod.res is None and prod.post_add is None and prod.chanmul is None and I % 2 == 0 and
+                    prod.res is None and prod.post_add is None and prod.chanmul is None and I % 8 == 0 and
                     not (prod.mode == ops.BN_TRAIN_SYNC and P.peer is None and P.dist is not None))
             if fuse:
                 # single consumer, no shortcut: the BN-backward reduction of the producer rides in this dgrad's epilogue
@@ -816,7 +913,7 @@ class ConvBNRec:
                 py = prod.y
                 P.bwd.append(lambda: ops.conv_igemm_bnbwd(gd, wd, I, buf, py, pb.scale, pb.shift, s1, s2))
             else:
-                P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=I, addend=buf if acc else None))
+                P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=_pad(I, 8), addend=buf if acc else None))
         else:
             x = xs[0]
             buf, acc = P.grad_target(x)
@@ -833,8 +930,54 @@ class ConvBNRec:
                                    tap_koff=[t * cw.Opad for t in taps])
                 P.keep.append(gd)
                 wd, I, view = cw.wd, cw.I, planes[pl]
-                P.bwd.append(lambda gd=gd, view=view: ops.conv_igemm(gd, wd, I, view, n_store=I,
+                P.bwd.append(lambda gd=gd, view=view: ops.conv_igemm(gd, wd, I, view, n_store=_pad(I, 8),
                                                                      addend=view if acc else None))
+
+
+class SumRec:
+    """One output of an HRNet exchange unit: a = ReLU(sum of terms), models/hrnet.py:225-250.
+    terms: ("id", Act) the branch's own tensor | ("same", ConvBNRec apply=False) conv+BN at this resolution |
+    ("up", ConvBNRec apply=False) conv+BN at a lower resolution, bilinearly sampled inside the sum kernel."""
+
+    def __init__(self, P, terms):
+        self.P, self.terms = P, terms
+        ident = [t for k, t in terms if k == "id"]
+        assert len(ident) == 1 and 2 <= len(terms) <= 4
+        self.ident = ident[0]
+        self.ident.uses += 1
+        n, h, w, c = self.ident.t.shape
+        self.a = Act(P._new(n, h, w, c))
+        tup = []
+        for kind, t in terms:
+            if kind == "id":
+                tup.append((t.t, None, None))
+            else:
+                assert t.bns.C == c and t.bns.Cp == c
+                tup.append((t.y, t.bns.scale, t.bns.shift))
+        arr = ops.make_sum_terms(tup)
+        P.keep.append((arr, tup))
+        out = self.a.t
+        P.fwd.append(lambda: ops.sum_terms(arr, out, relu=True))
+
+    def backward(self):
+        P = self.P
+        g = self.a.g
+        if g is None:
+            return
+        ds = torch.empty_like(self.a.t)   # gradient w.r.t. the pre-ReLU sum = gradient of every term
+        idbuf, acc = P.grad_target(self.ident)
+        out = self.a.t
+        P.bwd.append(lambda: ops.relu_mask_bwd(g, out, ds, idbuf, accumulate=acc))
+        for kind, rec in self.terms:
+            if kind == "same":
+                rec.backward(g_override=ds)
+            elif kind == "up":
+                glow = torch.empty_like(rec.y)   # adjoint of the bilinear sampling, at the term's own resolution
+                n, ho, _, c = ds.shape
+                scratch = P._new(n * ho * glow.shape[2] * c, dtype=torch.float32)
+                P.bwd.append(lambda glow=glow, scratch=scratch: ops.bilinear_bwd(ds, glow, accumulate=False,
+                                                                                 scratch=scratch))
+                rec.backward(g_override=glow)
 
 
 class MaxPoolRec:
@@ -943,7 +1086,7 @@ class ClassifierRec:
         gd = ops.make_geom([dl], ([0], [0]), tap_koff=[0])
         P.keep.append(gd)
         wd, I = cw.wd, cw.I
-        P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=I, addend=buf if acc else None))
+        P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=_pad(I, 8), addend=buf if acc else None))
 
 
 class LossRec:

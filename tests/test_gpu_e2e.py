@@ -29,8 +29,12 @@ def _build(enc_arch, dec_arch, fc_dim, use_softmax=False, seed=304, residual_gai
     from mit_semseg.models import models as M, resnet as R
     from oracle import segnet_oracle as O
     base, dil = O.parse_encoder_arch(enc_arch)
-    net = R.__dict__[base](pretrained=False)
-    enc = M.ResnetDilated(net, 8) if dil else M.Resnet(net)
+    if base == "hrnetv2":
+        from mit_semseg.models import hrnet as HR
+        enc = HR.hrnetv2(pretrained=False)
+    else:
+        net = R.__dict__[base](pretrained=False)
+        enc = M.ResnetDilated(net, 8) if dil else M.Resnet(net)
     dec = ModelBuilder.build_decoder(dec_arch, fc_dim=fc_dim, num_class=150, use_softmax=use_softmax)
     esd = O.synth_state_dict(O.encoder_param_shapes(enc_arch), seed, residual_gain)
     dsd = O.synth_state_dict(O.decoder_param_shapes(dec_arch, fc_dim), seed + 1)
@@ -46,11 +50,20 @@ def _rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-30)).item()
 
 
-def _step_metrics(enc_arch, dec_arch, fc_dim, n, hw, gain=0.25, emulate="bf16", bn_eval=False, seed=1):
-    """Run one engine step and the oracle; return comparison metrics."""
+def _step_metrics(enc_arch, dec_arch, fc_dim, n, hw, gain=0.25, emulate="bf16", bn_eval=False, seed=1, label_stride=8,
+                  calibrate=False):
+    """Run one engine step and the oracle; return comparison metrics.
+    calibrate: first set every BN's running statistics to this batch's statistics (one oracle pass, momentum 1), so a
+    frozen-BN run sits in the normalised regime of a trained network instead of drifting with synthetic statistics."""
     from mit_semseg.engine.program import SegProgram
     from oracle import segnet_oracle as O
     seg, esd, dsd, ds = _build(enc_arch, dec_arch, fc_dim, residual_gain=gain)
+    if calibrate:
+        with torch.no_grad():
+            O.segmentation_forward(O.synth_batch(n, hw, hw, label_stride, seed), esd, dsd, enc_arch, dec_arch,
+                                   O.BNState(True, update_running=True, momentum=1.0), ds, dropout_p=0.0)
+        seg.encoder.load_state_dict(esd)
+        seg.decoder.load_state_dict(dsd)
     for m in seg.modules():
         if isinstance(m, nn.Dropout2d):
             m.p = 0.0
@@ -59,12 +72,14 @@ def _step_metrics(enc_arch, dec_arch, fc_dim, n, hw, gain=0.25, emulate="bf16", 
         for m in seg.modules():
             if isinstance(m, nn.modules.batchnorm._BatchNorm):
                 m.eval()
-    feed = O.synth_batch(n, hw, hw, 8, seed)
+    feed = O.synth_batch(n, hw, hw, label_stride, seed)
     prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
     prog.load_inputs(feed["img_data"].cuda(), feed["seg_label"].cuda())
     prog.run_eager()
     torch.cuda.synchronize()
     loss, acc = prog.out.tolist()
+    # a feature map may be a virtual concat of several tensors (HRNetV2)
+    prog_feats = [torch.cat([q.t for q in f], 3) if isinstance(f, list) else f.t for f in prog.feats]
     e = {k: v.clone().requires_grad_(v.is_floating_point() and ("running" not in k)) for k, v in esd.items()}
     d = {k: v.clone().requires_grad_(v.is_floating_point() and ("running" not in k)) for k, v in dsd.items()}
     st = O.BNState(training=not bn_eval, emulate=emulate)
@@ -84,7 +99,7 @@ def _step_metrics(enc_arch, dec_arch, fc_dim, n, hw, gain=0.25, emulate="bf16", 
             dots[2] += torch.dot(gr, gr).item()
     m = {"loss": loss, "loss_ref": l_ref.item(), "acc": acc, "acc_ref": a_ref.item(),
          "logp_rel": _rel(torch.log_softmax(logits, 1), pred.detach()),
-         "feat_rel": [_rel(f.t.float().cpu().permute(0, 3, 1, 2), fo.detach()) for f, fo in zip(prog.feats, feats)],
+         "feat_rel": [_rel(f.float().cpu().permute(0, 3, 1, 2), fo.detach()) for f, fo in zip(prog_feats, feats)],
          "grad_rel": grel, "grad_rel_median": statistics.median(grel.values()), "grad_rel_max": max(grel.values()),
          "grad_cos": dots[0] / (dots[1] ** 0.5 * dots[2] ** 0.5 + 1e-30)}
     print({k: (v if k != "grad_rel" else sorted(v.items(), key=lambda kv: -kv[1])[:4]) for k, v in m.items()})
@@ -290,3 +305,43 @@ def test_upernet_resnet50_backward_wiring_and_train_loss():
     assert max(rels.values()) <= 0.12 and statistics.median(rels.values()) <= 0.05, max(rels, key=rels.get)
     loss, ref, rels = run(bn_eval=False)
     assert abs(loss - ref) <= 5e-3 * abs(ref)
+
+
+# ------------------------------------------------------------------------------------------- HRNetV2-W48 + C1 (config 5)
+def test_hrnetv2_c1_backward_wiring_bn_eval():
+    """305 encoder convolutions on 48/96/192/384-channel branches (partial 64-channel K blocks),
+    26 exchange outputs (fused sum / bilinear-sample / ReLU kernel and its adjoint), stride-2 chains over parity planes,
+    the 720-channel virtual concat and C1's 180-channel hidden layer (8-padded storage). BN frozen: every parameter
+    gradient is comparable (module docstring)."""
+    m = _step_metrics("hrnetv2", "c1", 720, 2, 64, bn_eval=True, label_stride=4, calibrate=True)
+    assert abs(m["loss"] - m["loss_ref"]) <= 3e-3 * abs(m["loss_ref"])
+    assert m["logp_rel"] <= 2e-2 and max(m["feat_rel"]) <= 3e-2
+    assert m["grad_rel_max"] <= 0.15 and m["grad_rel_median"] <= 0.04 and m["grad_cos"] >= 0.998, m["grad_rel_max"]
+
+
+def test_hrnetv2_c1_train_mode_bn_forward_and_loss():
+    m = _step_metrics("hrnetv2", "c1", 720, 2, 128, label_stride=4)
+    assert abs(m["loss"] - m["loss_ref"]) <= 5e-3 * abs(m["loss_ref"])
+    assert abs(m["acc"] - m["acc_ref"]) <= 1e-2
+    assert m["logp_rel"] <= 5e-2 and max(m["feat_rel"]) <= 0.1
+    assert m["grad_cos"] >= 0.5, m["grad_cos"]
+
+
+def test_hrnetv2_c1_inference_and_module_level_encoder():
+    from oracle import segnet_oracle as O
+    seg, esd, dsd, ds = _build("hrnetv2", "c1", 720, use_softmax=True, residual_gain=0.25)
+    seg.cuda().eval()
+    feed = O.synth_batch(1, 64, 96, 8, 5)
+    x = feed["img_data"].cuda()
+    with torch.no_grad():
+        probs = seg({"img_data": x}, segSize=(64, 96)).cpu()
+        ref = O.segmentation_forward(feed, esd, dsd, "hrnetv2", "c1", O.BNState(False, emulate="bf16"), ds, segSize=(64, 96))
+        feats = seg.encoder(x, return_feature_maps=True)
+        ref_feats = O.encoder_forward(feed["img_data"], esd, "hrnetv2", O.BNState(False, emulate="bf16"))
+    assert probs.shape == ref.shape and (probs.sum(1) - 1).abs().max().item() < 1e-3
+    agree = (probs.argmax(1) == ref.argmax(1)).float().mean().item()
+    err = (probs - ref).abs().max().item()
+    print("hrnet inference argmax agreement %.4f max prob err %.4f" % (agree, err))
+    assert agree >= 0.97 and err <= 5e-2, (agree, err)
+    assert len(feats) == 1 and tuple(feats[0].shape) == (1, 720, 16, 24)
+    assert _rel(feats[0].cpu(), ref_feats[0]) <= 3e-2

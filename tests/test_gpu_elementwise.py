@@ -355,3 +355,44 @@ def test_bn_finalize_apply_fused_equals_two_kernels():
         outs.append((out, mean, invstd, scale, shift, rm, rv))
     for a, b in zip(outs[0], outs[1]):
         assert torch.allclose(a.float(), b.float(), rtol=1e-5, atol=1e-6)
+
+
+def test_exchange_unit_sum_terms_and_relu_backward():
+    """sseg_sum_terms / sseg_relu_mask_bwd against torch (models/hrnet.py:225-250): identity + affine same-resolution
+    term + two bilinearly sampled lower-resolution affine terms, ReLU; then the ReLU adjoint with the identity share."""
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n, h, w, c = 2, 24, 40, 48
+    x0 = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+    y1 = torch.randn(n, h, w, c, device="cuda", generator=g).bfloat16()
+    y2 = torch.randn(n, h // 2, w // 2, c, device="cuda", generator=g).bfloat16()
+    y3buf = torch.randn(n, h // 8, w // 8, c + 16, device="cuda", generator=g).bfloat16()
+    y3 = y3buf[..., :c]                                        # pixel stride wider than the channel count
+    sc = [torch.rand(c, device="cuda", generator=g) + 0.5 for _ in range(3)]
+    sh = [torch.randn(c, device="cuda", generator=g) * 0.3 for _ in range(3)]
+    out = torch.empty(n, h, w, c, device="cuda", dtype=torch.bfloat16)
+    ops.sum_terms([(x0, None, None), (y1, sc[0], sh[0]), (y2, sc[1], sh[1]), (y3, sc[2], sh[2])], out, relu=True)
+
+    def up(t):
+        return F.interpolate(t.float().permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+    ref = x0.float() + (y1.float() * sc[0] + sh[0]) + (up(y2) * sc[1] + sh[1]) + (up(y3) * sc[2] + sh[2])
+    ref = torch.relu(ref)
+    torch.cuda.synchronize()
+    assert (out.float() - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+    # two terms, no ReLU
+    out2 = torch.empty_like(out)
+    ops.sum_terms([(x0, None, None), (y2, sc[1], sh[1])], out2, relu=False)
+    ref2 = x0.float() + up(y2) * sc[1] + sh[1]
+    assert (out2.float() - ref2).abs().max().item() <= 2 ** -8 * ref2.abs().max().item()
+    # ReLU adjoint + identity share (overwrite, then accumulate)
+    gr = (torch.randn(n, h, w, c, device="cuda", generator=g) * 0.1).bfloat16()
+    ds = torch.empty_like(gr)
+    acc = torch.full_like(gr, float("nan"))
+    ops.relu_mask_bwd(gr, out, ds, acc, accumulate=False)
+    ref_ds = gr.float() * (out.float() > 0)
+    assert torch.equal(ds.float(), ref_ds) and torch.equal(acc, ds)
+    ops.relu_mask_bwd(gr, out, ds, acc, accumulate=True)
+    assert (acc.float() - 2 * ref_ds).abs().max().item() <= 2 ** -8 * ref_ds.abs().max().item()
+    ds2 = torch.empty_like(gr)
+    ops.relu_mask_bwd(gr, out, ds2)
+    assert torch.equal(ds2, ds)

@@ -17,12 +17,22 @@ def _ref_conv(xs, w, dilation, bias=None):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
+def _acts(n, h, w_, cins, g, scale=1.0):
+    """bf16 NHWC sources; channel counts that are not multiples of 8 live in a wider (x8) zero-padded buffer."""
+    xs = []
+    for c in cins:
+        buf = torch.zeros(n, h, w_, (c + 7) // 8 * 8, device="cuda", dtype=torch.bfloat16)
+        buf[..., :c] = (torch.randn(n, h, w_, c, device="cuda", generator=g) * scale).bfloat16()
+        xs.append(buf[..., :c])
+    return xs
+
+
 def _run(n, h, w_, cins, cout, k, d, out_f32=False, bias=False, addend=False, stats=False, seed=0):
     from mit_semseg.engine import ops
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     g = torch.Generator(device="cuda").manual_seed(seed)
-    xs = [torch.randn(n, h, w_, c, device="cuda", generator=g).bfloat16() for c in cins]
+    xs = _acts(n, h, w_, cins, g)
     cin = sum(cins)
     wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * (2.0 / (cin * k * k)) ** 0.5).bfloat16()
     b = torch.randn(cout, device="cuda", generator=g) if bias else None
@@ -36,7 +46,10 @@ def _run(n, h, w_, cins, cout, k, d, out_f32=False, bias=False, addend=False, st
         ref = ref + add[..., :cout].float()
     ssum = torch.zeros(cout, device="cuda") if stats else None
     ssq = torch.zeros(cout, device="cuda") if stats else None
-    w_ohwi = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    K = k * k * cin
+    w_ohwi = torch.zeros(cout, (K + 7) // 8 * 8, device="cuda", dtype=torch.bfloat16)   # row pitch: 16-byte multiple
+    w_ohwi[:, :K] = wt.permute(0, 2, 3, 1).reshape(cout, -1)
+    w_ohwi = w_ohwi[:, :K]
     ops.conv_igemm(ops.make_geom(xs, ops.conv_taps(k, d)), w_ohwi, cout, out, n_store=n_store, bias=b, addend=add,
                    stat_sum=ssum, stat_sqsum=ssq)
     torch.cuda.synchronize()
@@ -98,11 +111,22 @@ def test_addend():
     _run(2, 64, 64, [128], 256, 3, 1, addend=True)
 
 
+def test_channel_counts_not_multiple_of_64():
+    """HRNetV2 widths (48 / 96 / 192 / 384, concat 720, C1 hidden 180): partial 64-channel K blocks are zero-filled by
+    TMA, partial N tiles masked in the epilogue (models/hrnet.py:257-262, models/models.py:327-346)."""
+    _run(2, 32, 32, [48], 48, 3, 1, stats=True)
+    _run(2, 16, 16, [96], 96, 3, 1, stats=True)
+    _run(2, 16, 16, [96], 48, 1, 1, stats=True)            # exchange unit, branch 1 -> branch 0
+    _run(1, 32, 32, [48, 96, 192, 384], 180, 3, 1, stats=True)   # C1 on the 720-channel concat
+    _run(2, 16, 16, [180], 150, 1, 1, out_f32=True, bias=True)   # classifier over the 180-channel hidden layer
+    _run(2, 8, 8, [384], 384, 3, 1, addend=True)
+
+
 # ------------------------------------------------------------------ weight gradient (MN-major operands, split-K)
 def _run_wgrad(n, h, w_, cins, cout, k, d, cpad=0, seed=0):
     from mit_semseg.engine import ops
     g = torch.Generator(device="cuda").manual_seed(seed)
-    xs = [torch.randn(n, h, w_, c, device="cuda", generator=g).bfloat16() for c in cins]
+    xs = _acts(n, h, w_, cins, g)
     cin = sum(cins)
     dy = torch.zeros(n, h, w_, cout + cpad, device="cuda", dtype=torch.bfloat16)
     dy[..., :cout] = (torch.randn(n, h, w_, cout, device="cuda", generator=g) * 0.1).bfloat16()
@@ -145,12 +169,20 @@ def test_wgrad_ragged():
     _run_wgrad(3, 6, 6, [128], 64, 3, 1)
 
 
+def test_wgrad_channel_counts_not_multiple_of_64():
+    _run_wgrad(2, 32, 32, [48], 48, 3, 1)
+    _run_wgrad(2, 16, 16, [96], 48, 1, 1)
+    _run_wgrad(2, 16, 16, [192], 96, 3, 1)
+    _run_wgrad(1, 32, 32, [48, 96, 192, 384], 180, 3, 1, cpad=4)
+    _run_wgrad(2, 16, 16, [180], 150, 1, 1, cpad=42)
+
+
 # ------------------------------------------------------------------ stride-2 convs over parity-plane views
-@pytest.mark.parametrize("k", [1, 3])
-def test_stride2_via_parity_planes(k):
+@pytest.mark.parametrize("k,cin,cout", [(1, 128, 256), (3, 128, 256), (3, 48, 96), (3, 96, 96), (3, 192, 384)])
+def test_stride2_via_parity_planes(k, cin, cout):
     from mit_semseg.engine import ops
     g = torch.Generator(device="cuda").manual_seed(7)
-    n, h, w_, cin, cout = 2, 64, 64, 128, 256
+    n, h, w_ = 2, 64, 64
     x = torch.randn(n, h, w_, cin, device="cuda", generator=g).bfloat16()
     wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.05).bfloat16()
     xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
@@ -186,11 +218,12 @@ def test_stride2_via_parity_planes(k):
 
 
 # ------------------------------------------------------------------ dgrad with the producer's BN-backward reduce fused
-@pytest.mark.parametrize("k,hw", [(1, 64), (3, 64), (3, 38)])
-def test_dgrad_with_fused_bn_backward_reduce(k, hw):
+@pytest.mark.parametrize("k,hw,cprod,cout_next", [(1, 64, 128, 256), (3, 64, 128, 256), (3, 38, 128, 256),
+                                                  (3, 32, 48, 48), (3, 16, 96, 192)])
+def test_dgrad_with_fused_bn_backward_reduce(k, hw, cprod, cout_next):
     from mit_semseg.engine import ops
     g = torch.Generator(device="cuda").manual_seed(21)
-    n, cprod, cout_next = 2, 128, 256          # producer layer has 128 channels; the consumer conv maps 128 -> 256
+    n = 2          # producer layer has cprod channels; the consumer conv maps cprod -> cout_next
     y = torch.randn(n, hw, hw, cprod, device="cuda", generator=g).bfloat16()       # producer's saved conv output
     fscale = torch.rand(cprod, device="cuda", generator=g) + 0.5
     fshift = torch.randn(cprod, device="cuda", generator=g) * 0.3

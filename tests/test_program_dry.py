@@ -1,0 +1,77 @@
+"""CPU: the host-side schedule builder (engine/program.py) in dry-run mode — module tree + input shape -> records,
+buffers and closures, without a GPU and without executing anything (a dry-run program refuses to run: there is no CPU
+execution path).  Checks the wiring invariants the backward pass relies on: every convolution gets exactly one
+weight-gradient task, every applied activation receives a gradient buffer of its own (8-padded) shape."""
+import pytest
+import torch
+import torch.nn as nn
+
+
+def _seg(enc_arch, dec_arch, fc):
+    from mit_semseg.models import ModelBuilder, SegmentationModule
+    from mit_semseg.models import hrnet as HR, models as M, resnet as R
+    if enc_arch == "hrnetv2":
+        enc = HR.hrnetv2(pretrained=False)
+    else:
+        dil = enc_arch.endswith("dilated")
+        net = R.__dict__[enc_arch.replace("dilated", "")](pretrained=False)
+        enc = M.ResnetDilated(net, 8) if dil else M.Resnet(net)
+    dec = ModelBuilder.build_decoder(dec_arch, fc_dim=fc, num_class=150)
+    ds = 0.4 if dec_arch.endswith("deepsup") else None
+    return SegmentationModule(enc, dec, nn.NLLLoss(ignore_index=-1), ds)
+
+
+@pytest.mark.parametrize("enc,dec,fc,hw,nsum", [("resnet50dilated", "ppm_deepsup", 2048, 64, 0),
+                                                 ("resnet50", "upernet_lite", 2048, 64, 0),
+                                                 ("hrnetv2", "c1", 720, 64, 26)])
+def test_training_schedule_wiring(enc, dec, fc, hw, nsum, monkeypatch):
+    from mit_semseg.engine import program as PR
+    seg = _seg(enc, dec, fc)
+    seg.train()
+    side = [0]
+    orig = PR.SegProgram.on_side
+
+    def counting(self, fn):
+        side[0] += 1
+        return orig(self, fn)
+    monkeypatch.setattr(PR.SegProgram, "on_side", counting)
+    P = PR.SegProgram(seg, (2, 3, hw, hw), training=True, with_grad=True, dry_run=True)
+    nconv = sum(isinstance(m, nn.Conv2d) for m in seg.modules())
+    assert side[0] == nconv                      # one weight-gradient task per convolution (stem and classifiers included)
+    assert sum(isinstance(r, PR.SumRec) for r in P.records) == nsum
+    for r in P.records:
+        a = getattr(r, "a", None)
+        if a is None:
+            continue
+        if isinstance(r, (PR.ConvBNRec, PR.SumRec, PR.StemRec)):
+            assert a.g is not None, type(r)
+        if a.g is not None:
+            assert a.g.shape[:3] == a.tp.shape[:3] and a.g.shape[3] in (a.t.shape[3], a.tp.shape[3])
+    grads = P.param_grads()
+    assert all(p in grads and grads[p].shape == p.shape for p in seg.parameters())
+    with pytest.raises(RuntimeError, match="dry-run"):
+        P.run_eager()
+
+
+def test_hrnet_c1_hidden_layer_is_stored_8_padded():
+    """fc_dim 720 -> C1 hidden width 180 (models/models.py:353): storage is 184 wide with zero pad channels, the BN
+    vectors the 8-channel-vectorised kernels read are 184 long, parameter gradients keep the parameter's 180."""
+    from mit_semseg.engine import program as PR
+    seg = _seg("hrnetv2", "c1", 720)
+    seg.train()
+    P = PR.SegProgram(seg, (1, 3, 32, 32), training=True, with_grad=True, dry_run=True)
+    rec = [r for r in P.records if isinstance(r, PR.ConvBNRec) and r.cw.mod is seg.decoder.cbr[0]][0]
+    assert rec.y.shape[3] == 184 and rec.a.t.shape[3] == 180 and rec.a.tp.shape[3] == 184 and rec.a.g.shape[3] == 184
+    assert rec.bns.scale.numel() == 184 and P.param_grads()[seg.decoder.cbr[1].weight].numel() == 180
+    assert len(rec.xs) == 4 and [x.t.shape[3] for x in rec.xs] == [48, 96, 192, 384]   # virtual concat, never materialised
+    cls = [r for r in P.records if isinstance(r, PR.ClassifierRec)][0]
+    assert cls.cw.wf.shape == (150, 180) and cls.cw.wf.stride(0) == 184              # 16-byte row pitch for TMA
+
+
+def test_inference_schedule_builds_for_every_encoder():
+    from mit_semseg.engine import program as PR
+    for enc, dec, fc in (("resnet18dilated", "ppm_deepsup", 512), ("hrnetv2", "c1", 720)):
+        seg = _seg(enc, dec, fc)
+        seg.eval()
+        P = PR.SegProgram(seg, (1, 3, 64, 96), training=False, with_grad=False, seg_size=(64, 96), dry_run=True)
+        assert P.probs.shape == (1, 150, 64, 96) and not P.bwd
