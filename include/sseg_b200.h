@@ -68,7 +68,8 @@ int sseg_get_pdl(void);
  *   tap t reads X[n, h + tap_dh[t], w + tap_dw[t], :] ; out-of-range pixels read zeros (TMA out-of-bounds
  *   fill = the zero padding of nn.Conv2d).
  *   tap_src[t] == -1 : X is the virtual channel concatenation of all `nsrc` sources (same n,h,w; every c a
- *                      multiple of 8 - HRNet's 48/96-channel branches run as zero-filled partial 64-blocks), so
+ *                      multiple of 4 with a pixel stride `ld` multiple of 8 - HRNet's 48/96-channel branches and C1's 180-channel
+ *                      hidden layer run as zero-filled partial 64-blocks), so
  *                      torch.cat (models/models.py:476, models/hrnet.py:434) is never materialised.
  *   tap_src[t] == k  : tap t reads source k only (all sources then have equal c). This is how a stride-2
  *                      convolution is expressed over the 4 space-to-depth parity planes of its input.

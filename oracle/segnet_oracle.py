@@ -30,7 +30,11 @@ RESNET_LAYERS = {"resnet18": ("basic", [2, 2, 2, 2]), "resnet50": ("bottleneck",
                  "resnet101": ("bottleneck", [3, 4, 23, 3])}
 
 
-HRNET_STAGES = ((1, (48, 96)), (4, (48, 96, 192)), (3, (48, 96, 192, 384)))  # (modules, branch widths): hrnet.py:257-262
+# HRNetV2-W48 (reference hrnet.py:257-262, :271): (modules, branch widths) per stage, BasicBlocks per branch, Bottlenecks
+# in layer1. Module-level so a test can also run a shallower net of the same topology (the reference hard-codes these).
+HRNET_STAGES = ((1, (48, 96)), (4, (48, 96, 192)), (3, (48, 96, 192, 384)))
+HRNET_BRANCH_BLOCKS = 4
+HRNET_LAYER1_BLOCKS = 4
 
 
 def parse_encoder_arch(arch):
@@ -194,7 +198,7 @@ def hrnet_forward(x, sd, st, prefix=""):
     P = prefix
     x = _cbr(x, sd, P + "conv1", P + "bn1", st, stride=2, padding=1)
     x = _cbr(x, sd, P + "conv2", P + "bn2", st, stride=2, padding=1)
-    for b in range(4):
+    for b in range(HRNET_LAYER1_BLOCKS):
         x = _residual_block(x, sd, "%slayer1.%d." % (P, b), st, "bottleneck")
     ys = [x]
     for si, (nmod, widths) in enumerate(HRNET_STAGES, start=2):
@@ -215,7 +219,7 @@ def hrnet_forward(x, sd, st, prefix=""):
         for m in range(nmod):
             mp = "%sstage%d.%d." % (P, si, m)
             for i in range(len(widths)):
-                for b in range(4):
+                for b in range(HRNET_BRANCH_BLOCKS):
                     xs[i] = _residual_block(xs[i], sd, "%sbranches.%d.%d." % (mp, i, b), st, "basic")
             fused = []
             for i in range(len(widths)):
@@ -397,7 +401,7 @@ def hrnet_param_shapes():
         shapes[name_bn] = ("bn", co)
 
     cb("conv1", "bn1", 64, 3, 3), cb("conv2", "bn2", 64, 64, 3)
-    for b in range(4):
+    for b in range(HRNET_LAYER1_BLOCKS):
         p = "layer1.%d." % b
         cb(p + "conv1", p + "bn1", 64, 64 if b == 0 else 256, 1)
         cb(p + "conv2", p + "bn2", 64, 64, 3), cb(p + "conv3", p + "bn3", 256, 64, 1)
@@ -417,7 +421,7 @@ def hrnet_param_shapes():
         for m in range(nmod):
             mp = "stage%d.%d." % (si, m)
             for i, c in enumerate(widths):
-                for b in range(4):
+                for b in range(HRNET_BRANCH_BLOCKS):
                     p = "%sbranches.%d.%d." % (mp, i, b)
                     cb(p + "conv1", p + "bn1", c, c, 3), cb(p + "conv2", p + "bn2", c, c, 3)
             for i, ci_ in enumerate(widths):

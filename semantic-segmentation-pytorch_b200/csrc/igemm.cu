@@ -699,7 +699,7 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, bool others_den
   for (int s = 0; s < g->nsrc; ++s) {
     const sseg_act_t& a = g->srcs[s];
     SSEG_REQUIRE(a.n == N && a.h == H && a.w == W, "%s: source %d shape mismatch", who, s);
-    SSEG_REQUIRE(a.c % 8 == 0 && a.c > 0, "%s: source %d channels %d not a multiple of 8", who, s, a.c);
+    SSEG_REQUIRE(a.c % 4 == 0 && a.c > 0, "%s: source %d channels %d not a multiple of 4", who, s, a.c);
     SSEG_REQUIRE(a.ld % 8 == 0 && a.ld >= a.c, "%s: source %d ld %d invalid", who, s, a.ld);
     SSEG_REQUIRE(!any_fixed || a.c == g->srcs[0].c, "%s: per-tap sources must have equal channels", who);
     int rc = gh->flat ? get_tmap_act(&tmA[s], a.ptr, 2, 1, 1, gh->vw, a.c, a.ld, (long)gh->vw * a.ld,

@@ -27,7 +27,8 @@ model_urls = {
     'hrnetv2': 'http://sceneparsing.csail.mit.edu/model/pretrained_resnet/hrnetv2_w48-imagenet.pth',
 }
 
-# (modules, blocks per branch, channels per branch) of stages 2..4 — hrnet.py:257-262
+# (modules, blocks per branch, channels per branch) of stages 2..4 — hrnet.py:257-262; Bottlenecks in layer1 — :271
+_LAYER1_BLOCKS = 4
 _STAGES = {
     'STAGE2': dict(NUM_MODULES=1, NUM_BRANCHES=2, BLOCK='BASIC', NUM_BLOCKS=(4, 4), NUM_CHANNELS=(48, 96),
                    FUSE_METHOD='SUM'),
@@ -164,7 +165,7 @@ class HRNetV2(nn.Module):
         self.conv2 = _conv(64, 64, 3, 2)
         self.bn2 = _bn(64)
         self.relu = nn.ReLU(inplace=True)
-        self.layer1 = _block_chain(Bottleneck, 64, 64, 4)
+        self.layer1 = _block_chain(Bottleneck, 64, 64, _LAYER1_BLOCKS)
 
         pre = [256]
         for idx, key in ((2, 'STAGE2'), (3, 'STAGE3'), (4, 'STAGE4')):
