@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-kernel-family time breakdown of one training step (CUDA events around every C-ABI call of an eager run).
-Usage (GPU box):  python tools/step_breakdown.py [--arch resnet50dilated] [--batch 2] [--crop 512] [--top 25]
+Usage (GPU box):  python tools/step_breakdown.py [--net r50ppm|hrnet|r101upernet] [--batch 2] [--crop 512] [--top 25]
 Writes a table to stdout; used to decide what to optimise next and to cross-check ncu launch lists."""
 import argparse
 import collections
@@ -22,12 +22,28 @@ def main():
     ap.add_argument("--top", type=int, default=30)
     ap.add_argument("--detail", action="store_true", help="list every conv GEMM launch with shape and TFLOP/s")
     ap.add_argument("--replay-only", action="store_true", help="only print the CUDA-graph replay time")
+    ap.add_argument("--net", default="r50ppm", choices=["r50ppm", "hrnet", "r101upernet"],
+                    help="r50ppm = the bench network (config 3); hrnet = HRNetV2+C1 (config 5); r101upernet = config 4")
     args = ap.parse_args()
     from mit_semseg.engine import ops
     from mit_semseg.engine.program import SegProgram
     dev = torch.device("cuda", 0)
-    seg = bench.build_model(dev)
-    feed = bench.synth_batch(args.batch, args.crop, args.crop, 8, 304)
+    stride = 8
+    if args.net == "r50ppm":
+        seg = bench.build_model(dev)
+    else:
+        import torch.nn as nn
+        from mit_semseg.models import ModelBuilder, SegmentationModule
+        from mit_semseg.models import hrnet as HR, models as M, resnet as R
+        torch.manual_seed(304)
+        if args.net == "hrnet":
+            enc, dec = HR.hrnetv2(pretrained=False), ModelBuilder.build_decoder("c1", fc_dim=720, num_class=150)
+        else:
+            enc = M.Resnet(R.resnet101(pretrained=False))
+            dec = ModelBuilder.build_decoder("upernet", fc_dim=2048, num_class=150)
+        stride = 4
+        seg = SegmentationModule(enc, dec, nn.NLLLoss(ignore_index=-1), None).to(dev).train()
+    feed = bench.synth_batch(args.batch, args.crop, args.crop, stride, 304)
     prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
     prog.load_inputs(feed["img_data"].to(dev), feed["seg_label"].to(dev))
     prog.run_eager()
