@@ -17,16 +17,18 @@ def _programs(mod):
     return cache
 
 
-def get_program(seg, img_shape, seg_size=None, with_grad=None, dropout_masks=None, capture=None, inputs=None):
+def get_program(seg, img_shape, seg_size=None, with_grad=None, dropout_masks=None, capture=None, inputs=None,
+                head_out=None, head_weight=1.0):
     if with_grad is None:
         with_grad = torch.is_grad_enabled() and any(p.requires_grad for p in seg.parameters())
     bn_flags = tuple(m.training for m in seg.modules())
-    key = (tuple(img_shape), seg_size, bool(with_grad), hash(bn_flags), id(dropout_masks))
+    head = None if head_out is None else (head_out.data_ptr(), float(head_weight))
+    key = (tuple(img_shape), seg_size, bool(with_grad), hash(bn_flags), id(dropout_masks), head)
     cache = _programs(seg)
     prog = cache.get(key)
     if prog is None:
         prog = SegProgram(seg, tuple(img_shape), training=seg.training, with_grad=with_grad, seg_size=seg_size,
-                          dropout_masks=dropout_masks)
+                          dropout_masks=dropout_masks, head_out=head_out, head_weight=head_weight)
         if inputs is not None:
             prog.load_inputs(*inputs)  # the capture warm-up runs the step: give it real data, not uninitialised memory
         if capture if capture is not None else (seg_size is None):
@@ -92,6 +94,59 @@ def segmentation_inference(seg, img, seg_size):
         prog.capture()
     prog.run()
     return prog.probs.clone()
+
+
+def shard_scales(num_scales, world, rank):
+    """Scale k runs on rank k mod world: the scales are independent units."""
+    return [k for k in range(num_scales) if k % world == rank]
+
+
+def multiscale_inference(seg, imgs, seg_size, group=None, _run_scale=None):
+    """eval.py:58-75 — `scores = sum_k segmentation_module({img_k}, segSize) / len(imgs)` for the resized copies `imgs`
+    (list of [N,3,h_k,w_k] tensors) of one image — without the three full passes over the 150-channel score map the
+    reference spends per scale: every scale's head kernel adds `softmax / len(imgs)` straight into ONE score map.
+
+    With torch.distributed initialised (world size G) the scales are sharded k -> rank k mod G and the partial score
+    maps summed with one all-reduce, so every rank returns the full [N,C,*seg_size] map (argmax it like eval.py:74).
+    `_run_scale(img, scores, weight)` replaces the engine call in the CPU tests of this host logic."""
+    import torch.distributed as dist
+    seg_size = tuple(seg_size)
+    sharded = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    world, rank = (dist.get_world_size(group), dist.get_rank(group)) if sharded else (1, 0)
+    if _run_scale is None:
+        if not imgs[0].is_cuda:
+            raise RuntimeError("the B200 engine has no CPU path: move the module and the images to a CUDA device")
+        if not getattr(seg.decoder, "use_softmax", False):
+            raise RuntimeError("inference (segSize=...) requires a decoder built with use_softmax=True")
+        num_class = [m for m in seg.decoder.modules() if isinstance(m, torch.nn.Conv2d)][-1].out_channels
+    else:
+        num_class = seg.num_class
+    n = imgs[0].shape[0]
+    bufs = seg.__dict__.setdefault("_b200_scores", {})
+    shape = (n, num_class) + seg_size
+    scores = bufs.get((shape, imgs[0].device))
+    if scores is None:
+        if len(bufs) >= 4:
+            bufs.clear()   # evaluation images come in many sizes: do not pin a score map per size forever
+        scores = bufs[(shape, imgs[0].device)] = torch.empty(shape, device=imgs[0].device, dtype=torch.float32)
+    scores.zero_()
+    weight = 1.0 / len(imgs)
+    for k in shard_scales(len(imgs), world, rank):
+        if _run_scale is not None:
+            _run_scale(imgs[k], scores, weight)
+            continue
+        prog = get_program(seg, imgs[k].shape, seg_size=seg_size, with_grad=False, capture=False, head_out=scores,
+                           head_weight=weight)
+        prog.load_inputs(imgs[k])
+        prog.uses = getattr(prog, "uses", 0) + 1
+        if prog.uses == 2 and prog.graph is None:
+            saved = scores.clone()   # the capture warm-up executes the (accumulating) step: undo its contribution
+            prog.capture()
+            scores.copy_(saved)
+        prog.run()
+    if sharded:
+        dist.all_reduce(scores, group=group)
+    return scores.clone()
 
 
 def _cached(mod, key, build):

@@ -77,16 +77,19 @@ class BNS:
 
 class SegProgram:
     def __init__(self, seg, img_shape, training, with_grad=True, seg_size=None, dropout_masks=None, part="full",
-                 enc=None, dec=None, feat_shapes=None, dry_run=False):
+                 enc=None, dec=None, feat_shapes=None, dry_run=False, head_out=None, head_weight=1.0):
         """seg: SegmentationModule.  img_shape: (N, 3, H, W).  training: module.training (BN/dropout behaviour).
         with_grad: also build the backward schedule.  seg_size: inference branch (probabilities at seg_size).
         dropout_masks: optional {'main': [N,512] 0/1, 'deepsup': ...} to inject the Dropout2d draws (tests).
         part: "full" (encoder + decoder + loss/head) | "encoder" (module called on its own: fp32 NCHW feature maps out)
               | "decoder" (fp32 NCHW feature maps of `feat_shapes` in, log-probs / probabilities out); the partial
               programs are forward-only.
+        head_out / head_weight: inference only — accumulate head_weight * probabilities into this fp32 [N,C,*seg_size]
+              tensor instead of writing a fresh one (`scores += pred / len(scales)`, eval.py:72).
         dry_run: build the schedule only (shape inference, buffer plan, record wiring) — used by the CPU tests of the
               host logic; such a program refuses to run."""
         self.dry_run = bool(dry_run)
+        self.head_out, self.head_weight = head_out, float(head_weight)
         self.seg = seg
         self.part = part
         self.enc = enc if enc is not None else (seg.encoder if seg is not None else None)
@@ -423,8 +426,15 @@ class SegProgram:
                     self.outputs.append(o)
         elif self.inference:
             hs, ws = self.seg_size
-            self.probs = self._new(self.N, self.num_class, hs, ws, dtype=torch.float32)
-            self.fwd.append(lambda: ops.upsample_softmax(self.logits[..., :C8], self.num_class, self.probs))
+            if self.head_out is not None:
+                # multi-scale evaluation (eval.py:63-72): this scale ADDS weight * softmax into a shared score map
+                assert tuple(self.head_out.shape) == (self.N, self.num_class, hs, ws)
+                self.probs = self.head_out
+            else:
+                self.probs = self._new(self.N, self.num_class, hs, ws, dtype=torch.float32)
+            wgt, acc = self.head_weight, self.head_out is not None
+            self.fwd.append(lambda: ops.upsample_softmax(self.logits[..., :C8], self.num_class, self.probs, weight=wgt,
+                                                         accumulate=acc))
         else:
             n, h, w, _ = self.logits.shape
             self.label = torch.full((n, h, w), -1, device=self.dev, dtype=torch.int64)

@@ -86,6 +86,21 @@ def _worker(rank, world, port, ret):
         dist.all_reduce(bucket)
         bucket /= world
         assert torch.allclose(bucket, torch.full((3,), 1.5))
+        # ---- multi-scale evaluation sharded over ranks (eval.py:63-72): scale k -> rank k mod G,
+        #      one all-reduce of the partial score maps == the serial `scores += pred / len(scales)` loop
+        from mit_semseg.engine import functional as EF
+        assert EF.shard_scales(5, 2, 0) == [0, 2, 4] and EF.shard_scales(5, 2, 1) == [1, 3]
+
+        class FakeSeg:   # stands in for a SegmentationModule: the engine call itself is replaced by _run_scale below
+            num_class = 3
+        gs = torch.Generator().manual_seed(1)
+        imgs = [torch.randn(1, 3, 4 + k, 5 + k, generator=gs) for k in range(5)]
+
+        def fake_scale(img, scores, weight):   # any deterministic per-scale "probability map"
+            scores += weight * torch.sigmoid(img.mean()) * torch.ones_like(scores)
+        got = EF.multiscale_inference(FakeSeg(), imgs, (6, 7), _run_scale=fake_scale)
+        ref = sum(torch.sigmoid(im.mean()) for im in imgs) / 5 * torch.ones(1, 3, 6, 7)
+        assert got.shape == (1, 3, 6, 7) and torch.allclose(got, ref, atol=1e-6)
         ret[rank] = True
     finally:
         dist.destroy_process_group()

@@ -65,3 +65,20 @@ def test_hrnetv2_c1_inference_and_module_level_encoder():
     assert agree >= 0.93 and err <= 5e-2, (agree, err)
     assert len(feats) == 1 and tuple(feats[0].shape) == (1, 720, 16, 24)
     assert _rel(feats[0].cpu(), ref_feats[0]) <= 1e-2
+
+
+def test_multiscale_inference_equals_the_reference_loop():
+    """eval.py:63-72: scores = sum_k module({img_k}, segSize) / len(scales) — here accumulated inside the head kernel."""
+    import torch.nn.functional as F
+    from mit_semseg.engine import functional as EF
+    from oracle import segnet_oracle as O
+    seg, esd, dsd, ds = _build("resnet18dilated", "ppm_deepsup", 512, use_softmax=True, residual_gain=0.25)
+    seg.cuda().eval()
+    img = O.synth_batch(1, 96, 128, 8, 7)["img_data"].cuda()
+    imgs = [F.interpolate(img, size=s, mode="bilinear", align_corners=False) for s in ((64, 96), (96, 128), (128, 160))]
+    with torch.no_grad():
+        loop = sum(seg({"img_data": im}, segSize=(96, 128)) for im in imgs) / len(imgs)
+        for _ in range(3):   # third call replays captured graphs: the capture warm-up must not leak into the scores
+            fused = EF.multiscale_inference(seg, imgs, (96, 128))
+            assert (fused - loop).abs().max().item() <= 1e-5
+    assert (fused.sum(1) - 1).abs().max().item() < 1e-3

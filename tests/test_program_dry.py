@@ -75,3 +75,16 @@ def test_inference_schedule_builds_for_every_encoder():
         seg.eval()
         P = PR.SegProgram(seg, (1, 3, 64, 96), training=False, with_grad=False, seg_size=(64, 96), dry_run=True)
         assert P.probs.shape == (1, 150, 64, 96) and not P.bwd
+
+
+def test_multiscale_head_accumulates_into_a_shared_score_map():
+    """eval.py:72 `scores = scores + scores_tmp / len(imgSizes)`: each scale's program writes into the same buffer."""
+    from mit_semseg.engine import program as PR
+    seg = _seg("resnet18dilated", "ppm_deepsup", 512)
+    seg.eval()
+    scores = torch.zeros(1, 150, 64, 96)
+    progs = [PR.SegProgram(seg, (1, 3, h, w), training=False, with_grad=False, seg_size=(64, 96), dry_run=True,
+                           head_out=scores, head_weight=0.5) for h, w in ((64, 96), (96, 128))]
+    assert all(p.probs is scores for p in progs)
+    with pytest.raises(AssertionError):
+        PR.SegProgram(seg, (1, 3, 64, 96), training=False, with_grad=False, seg_size=(32, 32), dry_run=True, head_out=scores)
