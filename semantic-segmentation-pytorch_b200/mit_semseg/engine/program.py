@@ -127,6 +127,13 @@ class SegProgram:
         # weight-gradient GEMMs are off the critical path of the backward pass (nothing downstream reads them until
         # the gradient bucket): they run on a side stream and fill the SMs the data-gradient chain leaves idle
         self.side = torch.cuda.Stream(self.dev) if self.dev.type == "cuda" else None
+        # Independent sub-chains of small kernels (the four PPM pyramid branches; the parallel branches of an HRNet
+        # module) can run on streams of their own inside the step graph instead of back to back: each chain is a
+        # handful of latency-bound launches (8..200 CTAs) that leave most of the 148 SMs idle.
+        # Opt-in until measured on B200: SSEG_BRANCH_STREAMS=1.
+        self.use_branches = _os.environ.get("SSEG_BRANCH_STREAMS", "0") == "1"
+        self._branch_streams = {}
+        self._open_branches = []   # branches forked since the last join (build-time bookkeeping)
 
         self.convs, self.bns = {}, {}
         for m in self._modules():
@@ -338,13 +345,15 @@ class SegProgram:
             conv5 = feats[-1]
             n, h, w, c5 = conv5.t.shape
             srcs = [conv5]
-            for scale, branch in zip(dec.pool_scales, dec.ppm):
-                pr = AvgPoolRec(self, conv5, scale)
-                self.records.append(pr)
-                y = self.conv_bn(pr.a, branch[1], branch[2])
-                ur = UpsampleRec(self, y, h, w)
-                self.records.append(ur)
+            for bi, (scale, branch) in enumerate(zip(dec.pool_scales, dec.ppm)):
+                with self.branch(bi):
+                    pr = AvgPoolRec(self, conv5, scale)
+                    self.records.append(pr)
+                    y = self.conv_bn(pr.a, branch[1], branch[2])
+                    ur = UpsampleRec(self, y, h, w)
+                    self.records.append(ur)
                 srcs.append(ur.a)
+            self.join_branches()
             drop = dec.conv_last[3]
             p_drop_main = drop.p if (self.training and drop.training) else 0.0
             self.mask_main = self._new(n, 512, dtype=torch.float32) if p_drop_main > 0 else None
@@ -490,7 +499,12 @@ class SegProgram:
 
     def _hr_module(self, module, xs):
         nb = module.num_branches
-        xs = [self._residual_chain(xs[i], module.branches[i]) for i in range(nb)]
+        outs_ = []
+        for i in range(nb):
+            with self.branch(i):
+                outs_.append(self._residual_chain(xs[i], module.branches[i]))
+        self.join_branches()
+        xs = outs_
         if module.fuse_layers is None:
             return xs
         outs = []
@@ -567,7 +581,24 @@ class SegProgram:
                 # every record of this bucket has emitted its weight gradient: reduce it behind them on the side stream
                 sl = pending.pop(0)[1]
                 self.bwd.append(self.on_side(lambda sl=sl: self.dist.all_reduce(sl)))
+            k = getattr(rec, "branch", None) if self.use_branches else None
+            if isinstance(rec, AvgPoolRec):
+                k = None   # the pyramid's pools share ONE grouped backward kernel: it runs on the main stream
+            b0 = len(self.bwd)
             rec.backward()
+            if len(self.bwd) == b0:
+                continue   # nothing emitted (e.g. a record driven by its consumer): no ordering point
+            if k is None:
+                if self._open_branches:   # main-stream work that may read what the branches produced: join first
+                    joins = [self._join(j) for j in self._open_branches]
+                    self._open_branches = []
+                    self.bwd[b0:b0] = joins
+            else:
+                seg = self.bwd[b0:]
+                self.bwd[b0:] = ([] if k in self._open_branches else [self._fork(k)]) + [self._on_branch(k, f) for f in seg]
+                if k not in self._open_branches:
+                    self._open_branches.append(k)
+        self.join_branches(into=self.bwd)
         self.bwd.append(self.join_side)
         if self.dist is not None:
             if buckets:
@@ -611,6 +642,65 @@ class SegProgram:
 
     def join_side(self):
         torch.cuda.current_stream(self.dev).wait_stream(self.side)
+
+    # ---- branch streams (fork / run / join closures; all no-ops with prog.serial, like the side stream)
+    def _bstream(self, k):
+        s = self._branch_streams.get(k)
+        if s is None:
+            s = self._branch_streams[k] = torch.cuda.Stream(self.dev)
+        return s
+
+    def _fork(self, k):
+        def run():
+            if getattr(self, "serial", False):
+                return
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.dev))
+            self._bstream(k).wait_event(ev)
+        return run
+
+    def _on_branch(self, k, fn):
+        def run():
+            if getattr(self, "serial", False):
+                return fn()
+            with torch.cuda.stream(self._bstream(k)):
+                fn()
+        return run
+
+    def _join(self, k):
+        def run():
+            if not getattr(self, "serial", False):
+                torch.cuda.current_stream(self.dev).wait_stream(self._bstream(k))
+        return run
+
+    def branch(self, k):
+        """Context manager for the FORWARD schedule: closures and records created inside run on branch stream k
+        (forked from the main stream at the point of entry). Call join_branches() before anything consumes them."""
+        P = self
+
+        class _Scope:
+            def __enter__(self_):
+                self_.f0, self_.r0 = len(P.fwd), len(P.records)
+
+            def __exit__(self_, *exc):
+                if not P.use_branches or exc[0] is not None:
+                    return False
+                seg = P.fwd[self_.f0:]
+                if seg:
+                    P.fwd[self_.f0:] = [P._fork(k)] + [P._on_branch(k, f) for f in seg]
+                    if k not in P._open_branches:
+                        P._open_branches.append(k)
+                for r in P.records[self_.r0:]:
+                    r.branch = k
+                return False
+        return _Scope()
+
+    def join_branches(self, into=None):
+        """Append the joins of every open branch to `into` (default: the forward schedule)."""
+        lst = self.fwd if into is None else into
+        for k in self._open_branches:
+            lst.append(self._join(k))
+        self._open_branches = []
 
     def grad_target(self, act, shape_like=None):
         """(buffer, accumulate?) for writing a gradient contribution of `act`."""

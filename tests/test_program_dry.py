@@ -88,3 +88,27 @@ def test_multiscale_head_accumulates_into_a_shared_score_map():
     assert all(p.probs is scores for p in progs)
     with pytest.raises(AssertionError):
         PR.SegProgram(seg, (1, 3, 64, 96), training=False, with_grad=False, seg_size=(32, 32), dry_run=True, head_out=scores)
+
+
+@pytest.mark.parametrize("enc,dec,fc,nfork_fwd", [("resnet18dilated", "ppm_deepsup", 512, 4), ("hrnetv2", "c1", 720, 2 + 4 * 3 + 3 * 4)])
+def test_branch_streams_fork_and_join_symmetrically(enc, dec, fc, nfork_fwd, monkeypatch):
+    """SSEG_BRANCH_STREAMS=1 (opt-in): the pyramid branches / HRNet branches get fork + join closures; every fork is
+    joined before the schedule ends, in the forward and in the backward list."""
+    from mit_semseg.engine import program as PR
+    monkeypatch.setenv("SSEG_BRANCH_STREAMS", "1")
+    counts = {"fork": 0, "join": 0}
+    for name in ("_fork", "_join"):
+        orig = getattr(PR.SegProgram, name)
+
+        def counting(self, k, _orig=orig, _name=name[1:]):
+            counts[_name] += 1
+            return _orig(self, k)
+        monkeypatch.setattr(PR.SegProgram, name, counting)
+    seg = _seg(enc, dec, fc)
+    seg.train()
+    P = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+    assert not P._open_branches
+    assert counts["fork"] == counts["join"] == 2 * nfork_fwd, counts   # forward + backward
+    monkeypatch.setenv("SSEG_BRANCH_STREAMS", "0")
+    Q = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+    assert len(P.fwd) == len(Q.fwd) + 2 * nfork_fwd and len(P.bwd) == len(Q.bwd) + 2 * nfork_fwd
