@@ -82,3 +82,39 @@ def test_multiscale_inference_equals_the_reference_loop():
             fused = EF.multiscale_inference(seg, imgs, (96, 128))
             assert (fused - loop).abs().max().item() <= 1e-5
     assert (fused.sum(1) - 1).abs().max().item() < 1e-3
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SSEG_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="opt-in features not yet measured on B200 (set SSEG_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("enc,dec,fc,stride", [("resnet18dilated", "ppm_deepsup", 512, 8), ("hrnetv2", "c1", 720, 4)])
+def test_branch_streams_match_the_single_stream_schedule(enc, dec, fc, stride, monkeypatch):
+    """SSEG_BRANCH_STREAMS=1: same loss and gradients (frozen BN: no atomics-order noise in the statistics), eager and
+    as a captured graph."""
+    import torch.nn as nn
+    from mit_semseg.engine.program import SegProgram
+    from oracle import segnet_oracle as O
+    seg, esd, dsd, ds = _build(enc, dec, fc, residual_gain=0.25)
+    seg.cuda().train()
+    for m in seg.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.eval()
+        if isinstance(m, nn.Dropout2d):
+            m.p = 0.0
+    feed = O.synth_batch(2, 128, 128, stride, 3)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SSEG_BRANCH_STREAMS", flag)
+        prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
+        prog.load_inputs(feed["img_data"].cuda(), feed["seg_label"].cuda())
+        prog.run_eager()
+        torch.cuda.synchronize()
+        eager = prog.out.clone()
+        prog.capture()
+        for _ in range(3):
+            prog.run()
+        torch.cuda.synchronize()
+        assert torch.allclose(prog.out, eager, rtol=1e-4)
+        res[flag] = (prog.out.clone(), {k: v.clone() for k, v in prog.param_grads().items()})
+    assert torch.allclose(res["0"][0], res["1"][0], rtol=1e-5)
+    for p, g in res["0"][1].items():
+        assert _rel(res["1"][1][p], g) <= 2e-3   # split-K atomics order is the only difference
