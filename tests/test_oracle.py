@@ -206,7 +206,6 @@ def test_module_tree_matches_reference_state_dict_init_and_hparams(combo, fc):
     enc, dec = _build_mine(enc_arch, dec_arch, fc)
     assert {k: list(v.shape) for k, v in enc.state_dict().items()} == ref["enc_keys"]
     assert {k: list(v.shape) for k, v in dec.state_dict().items()} == ref["dec_keys"]
-    assert list(enc.state_dict().keys()) == list(ref["enc_keys"].keys()) or True
     # same constructor order + same initialisers => same RNG stream => identical weights under the same seed
     for k, (s, a) in ref["enc_init"].items():
         v = enc.state_dict()[k].double()
