@@ -106,6 +106,17 @@ int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld,
                     sseg_stream_t stream);
 
 /*
+ * Convolution with the inference-time epilogue fused: out = relu?( conv(x) * scale[co] + shift[co] (+ addend) ).
+ * BatchNorm with running statistics is a per-channel affine (F.batch_norm eval branch, lib/nn/modules/batchnorm.py:
+ * 58-61), so conv -> BN -> (+shortcut) -> ReLU (models/resnet.py:37-53,72-92; models/models.py:160-167) is ONE kernel
+ * and the raw convolution output never reaches HBM. relu: 0 none | 1 after the addend (residual blocks) | 2 before the
+ * addend (FPN lateral + top-down add, models/models.py:561-563). bf16 output; scale/shift float[cout] or both NULL.
+ */
+int sseg_conv_igemm_affine(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
+                           const float* scale, const float* shift, int relu, const sseg_act_t* addend,
+                           sseg_stream_t stream);
+
+/*
  * Data gradient with the BN-backward reduction of the PRODUCER layer fused into the epilogue.  `out` is the gradient
  * w.r.t. the producer's output a = relu(y*fscale + fshift); while the tile is still on chip the epilogue also accumulates
  *     s1[c] += sum g',   s2_raw[c] += sum g' * y,     g' = out * [y*fscale + fshift > 0]

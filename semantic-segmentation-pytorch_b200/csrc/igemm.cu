@@ -46,6 +46,11 @@ struct IgemmParams {
   long add_row_stride, add_img_stride;
   float* stat_sum;
   float* stat_sqsum;
+  // fused inference epilogue (BatchNorm with running statistics is a per-channel affine): v = v*ep_scale + ep_shift,
+  // ReLU before (ep_relu == 2) or after (ep_relu == 1) the addend (= shortcut / top-down tensor) is added
+  const float* ep_scale;
+  const float* ep_shift;
+  int ep_relu;
   // fused BN-backward reduction of the layer that PRODUCED the tensor whose gradient this launch writes (dgrad):
   //   g' = out * [bw_y * bw_fscale + bw_fshift > 0] ;  bw_s1[c] += sum g' ;  bw_s2[c] += sum g' * bw_y
   const __nv_bfloat16* bw_y;
@@ -190,6 +195,15 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.cout) v[j] += __ldg(p.bias + col0 + j);
       }
+      if (p.ep_scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.cout) v[j] = fmaf(v[j], __ldg(p.ep_scale + col0 + j), __ldg(p.ep_shift + col0 + j));
+      }
+      if (p.ep_relu == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
       if (p.addend != nullptr && valid) {
         const __nv_bfloat16* ap = p.addend + add_off + col0;
 #pragma unroll
@@ -205,6 +219,10 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
             }
           }
         }
+      }
+      if (p.ep_relu == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       if (p.out_f32) {
         if (valid) {
@@ -484,6 +502,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.cout) v[j] += __ldg(p.bias + col0 + j);
       }
+      if (p.ep_scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < p.cout) v[j] = fmaf(v[j], __ldg(p.ep_scale + col0 + j), __ldg(p.ep_shift + col0 + j));
+      }
+      if (p.ep_relu == 2) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
       if (p.addend != nullptr && valid) {
         const __nv_bfloat16* ap = p.addend + add_off + col0;
 #pragma unroll
@@ -499,6 +526,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
             }
           }
         }
+      }
+      if (p.ep_relu == 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
       if (p.out_f32) {
         if (valid) {
@@ -723,10 +754,16 @@ static int setup_geom(const sseg_conv_geom_t* g, int box_pixels, bool others_den
 
 using namespace sseg;
 
+struct EpilogueAffine {
+  const float* scale;
+  const float* shift;
+  int relu;
+};
+
 static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
                            int out_f32, const float* bias, const sseg_act_t* addend, float* stat_sum, float* stat_sqsum,
                            const sseg_act_t* bw_y, const float* bw_fscale, const float* bw_fshift, float* bw_s1,
-                           float* bw_s2, sseg_stream_t stream_) {
+                           float* bw_s2, sseg_stream_t stream_, const EpilogueAffine* ep = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SSEG_REQUIRE(g != nullptr && out != nullptr && w_bf16 != nullptr, "sseg_conv_igemm: null argument");
   const int n_store = out->c;
@@ -783,6 +820,11 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     p.ld_addend = addend->ld, p.add_row_stride = addend->row_stride, p.add_img_stride = addend->img_stride;
   }
   p.stat_sum = stat_sum, p.stat_sqsum = stat_sqsum;
+  if (ep != nullptr) {
+    SSEG_REQUIRE((ep->scale == nullptr) == (ep->shift == nullptr), "sseg_conv_igemm_affine: scale/shift must pair");
+    SSEG_REQUIRE(ep->relu >= 0 && ep->relu <= 2, "sseg_conv_igemm_affine: relu mode %d", ep->relu);
+    p.ep_scale = ep->scale, p.ep_shift = ep->shift, p.ep_relu = ep->relu;
+  }
   if (bw_y != nullptr) {
     SSEG_REQUIRE(!out_f32 && bw_fscale && bw_fshift && bw_s1 && bw_s2, "sseg_conv_igemm_bnbwd: null argument");
     SSEG_REQUIRE(bw_y->n == out->n && bw_y->h == out->h && bw_y->w == out->w && bw_y->c >= cout && cout % 8 == 0 &&
@@ -818,6 +860,14 @@ extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, lo
                                float* stat_sum, float* stat_sqsum, sseg_stream_t stream) {
   return conv_igemm_impl(g, w_bf16, w_ld, cout, out, out_f32, bias, addend, stat_sum, stat_sqsum, nullptr, nullptr, nullptr,
                          nullptr, nullptr, stream);
+}
+
+extern "C" int sseg_conv_igemm_affine(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                                      const sseg_act_t* out, const float* scale, const float* shift, int relu,
+                                      const sseg_act_t* addend, sseg_stream_t stream) {
+  const EpilogueAffine ep = {scale, shift, relu};
+  return conv_igemm_impl(g, w_bf16, w_ld, cout, out, 0, nullptr, addend, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                         nullptr, stream, &ep);
 }
 
 extern "C" int sseg_conv_igemm_bnbwd(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,

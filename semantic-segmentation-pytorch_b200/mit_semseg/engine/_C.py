@@ -92,6 +92,7 @@ _p = c_void_p
 _ip = POINTER(c_int)
 _SIGNATURES = {
     "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), c_int, _p, POINTER(Act), _p, _p, _p],
+    "sseg_conv_igemm_affine": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), _p, _p, c_int, POINTER(Act), _p],
     "sseg_conv_igemm_bnbwd": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(Act), _p, _p, _p, _p, _p],
     "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
     "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],

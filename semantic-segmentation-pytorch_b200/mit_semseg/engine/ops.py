@@ -63,6 +63,20 @@ def conv_igemm(geom, w_bf16, cout, out, n_store=None, bias=None, addend=None, st
     return out
 
 
+RELU_NONE, RELU_AFTER_ADD, RELU_BEFORE_ADD = 0, 1, 2
+
+
+def conv_igemm_affine(geom, w_bf16, cout, out, scale, shift, relu=RELU_AFTER_ADD, addend=None):
+    """out = relu?(conv(geom, w) * scale + shift (+ addend)) in one kernel (eval-mode BN folded into the epilogue)."""
+    assert out.dtype == torch.bfloat16 and w_bf16.dim() == 2 and w_bf16.stride(1) == 1
+    n_store = (cout + 7) // 8 * 8
+    o = act(out[..., :n_store])
+    a = act(addend) if addend is not None else None
+    _C.check(_C.lib().sseg_conv_igemm_affine(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, o, _C.ptr(scale), _C.ptr(shift),
+                                             int(relu), a, _stream()))
+    return out
+
+
 def conv_igemm_bnbwd(geom, w_bf16, cout, out, y, fscale, fshift, s1, s2_raw, addend=None):
     """Data gradient into `out` + the producer layer's BN-backward partial sums (see sseg_conv_igemm_bnbwd)."""
     assert out.dtype == torch.bfloat16 and w_bf16.dim() == 2 and w_bf16.stride(1) == 1

@@ -132,6 +132,9 @@ class SegProgram:
         # handful of latency-bound launches (8..200 CTAs) that leave most of the 148 SMs idle.
         # Opt-in until measured on B200: SSEG_BRANCH_STREAMS=1.
         self.use_branches = _os.environ.get("SSEG_BRANCH_STREAMS", "0") == "1"
+        # Inference programs: BatchNorm with running statistics is a per-channel affine, so conv -> BN -> (+shortcut) ->
+        # ReLU runs as ONE kernel (sseg_conv_igemm_affine) and the raw conv output never exists. Opt-in until measured.
+        self.fold_bn_eval = _os.environ.get("SSEG_FOLD_BN_EVAL", "0") == "1"
         self._branch_streams = {}
         self._open_branches = []   # branches forked since the last join (build-time bookkeeping)
 
@@ -918,16 +921,21 @@ class ConvBNRec:
         self.geom, ho, wo = P._conv_geom(srcs, cw)
         n = srcs[0].shape[0]
         assert bns.C == cw.O
-        self.y = P._new(n, ho, wo, bns.Cp)   # channels >= cw.O are written as zeros by the conv kernel
         self.mode = P._bn_mode(bns)
         self.count = n * ho * wo
+        self.fused = False  # set by the (single) consumer when its dgrad epilogue does this layer's BN-backward reduce
+        self.folded = (P.fold_bn_eval and self.mode == ops.BN_EVAL and not P.with_grad and chanmul is None and
+                       (res is None or isinstance(res, Act) or res.folded))
+        if self.folded:
+            self._init_folded(n, ho, wo)
+            return
+        self.y = P._new(n, ho, wo, bns.Cp)   # channels >= cw.O are written as zeros by the conv kernel
         st = bns.stats
         train = self.mode != ops.BN_EVAL
         C = cw.O
         geom, wf, y = self.geom, cw.wf, self.y
         P.fwd.append(lambda: ops.conv_igemm(geom, wf, C, y, stat_sum=st[:C] if train else None,
                                             stat_sqsum=st[C:2 * C] if train else None))
-        self.fused = False  # set by the (single) consumer when its dgrad epilogue does this layer's BN-backward reduce
         if apply:
             self.a = P._new_act(n, ho, wo, cw.O)
             self.a.producer = self
@@ -935,6 +943,7 @@ class ConvBNRec:
             if isinstance(res, Act):
                 r = res.tp
             elif isinstance(res, ConvBNRec):
+                assert not res.folded
                 r, rs, rb = res.y, res.bns.scale, res.bns.shift
             if post_add is not None:
                 r = post_add.tp
@@ -944,8 +953,33 @@ class ConvBNRec:
             self.a = None
             _emit_bn_forward(P, bns, self.mode, self.count, y, None, False, None, None, None, None)
 
+    def _init_folded(self, n, ho, wo):
+        """Inference: scale/shift come from the running statistics alone (finalize first), then ONE kernel computes
+        relu(conv * scale + shift (+ shortcut)). A projection shortcut built this way holds its finished BN output in
+        `y`, which the consuming record simply adds."""
+        P, cw, bns = self.P, self.cw, self.bns
+        _emit_bn_forward(P, bns, self.mode, self.count, None, None, False, None, None, None, None)
+        if self.apply:
+            self.a = P._new_act(n, ho, wo, cw.O)
+            self.a.producer = self
+            out, self.y = self.a.tp, None
+        else:
+            self.a = None
+            out = self.y = P._new(n, ho, wo, bns.Cp)
+        addend = None
+        if isinstance(self.res, Act):
+            addend = self.res.tp
+        elif isinstance(self.res, ConvBNRec):
+            addend = self.res.y
+        relu = ops.RELU_AFTER_ADD if self.relu else ops.RELU_NONE
+        if self.post_add is not None:
+            addend, relu = self.post_add.tp, ops.RELU_BEFORE_ADD
+        geom, wf, C = self.geom, cw.wf, cw.O
+        P.fwd.append(lambda: ops.conv_igemm_affine(geom, wf, C, out, bns.scale, bns.shift, relu=relu, addend=addend))
+
     def backward(self, g_override=None):
         P, cw, bns = self.P, self.cw, self.bns
+        assert not self.folded, "folded (inference) records have no backward"
         if not self.apply and g_override is None:
             return  # projection shortcuts are driven by the record that consumed them
         g = g_override if g_override is not None else self.a.g
@@ -1053,7 +1087,7 @@ class SumRec:
                 tup.append((t.t, None, None))
             else:
                 assert t.bns.C == c and t.bns.Cp == c
-                tup.append((t.y, t.bns.scale, t.bns.shift))
+                tup.append((t.y, None, None) if t.folded else (t.y, t.bns.scale, t.bns.shift))
         arr = ops.make_sum_terms(tup)
         P.keep.append((arr, tup))
         out = self.a.t

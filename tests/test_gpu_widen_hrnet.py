@@ -118,3 +118,60 @@ def test_branch_streams_match_the_single_stream_schedule(enc, dec, fc, stride, m
     assert torch.allclose(res["0"][0], res["1"][0], rtol=1e-5)
     for p, g in res["0"][1].items():
         assert _rel(res["1"][1][p], g) <= 2e-3   # split-K atomics order is the only difference
+
+
+_EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("SSEG_TEST_EXPERIMENTAL", "0") != "1",
+                                   reason="opt-in features not yet measured on B200 (set SSEG_TEST_EXPERIMENTAL=1)")
+
+
+@_EXPERIMENTAL
+@pytest.mark.parametrize("relu,with_add,cout", [(1, True, 128), (2, True, 256), (1, False, 48), (0, False, 180)])
+def test_conv_with_folded_affine_epilogue(relu, with_add, cout):
+    """sseg_conv_igemm_affine vs torch: relu?(conv * scale + shift (+ addend)), ReLU before / after the addend."""
+    import torch.nn.functional as F
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(11)
+    n, h, w, cin, k = 2, 32, 32, 128, 3
+    x = torch.randn(n, h, w, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * 0.03).bfloat16()
+    scale = torch.rand(cout, device="cuda", generator=g) + 0.5
+    shift = torch.randn(cout, device="cuda", generator=g) * 0.5
+    cp = (cout + 7) // 8 * 8
+    add = torch.randn(n, h, w, cp, device="cuda", generator=g).bfloat16() if with_add else None
+    out = torch.full((n, h, w, cp), float("nan"), device="cuda", dtype=torch.bfloat16)
+    ops.conv_igemm_affine(ops.make_geom([x], ops.conv_taps(k, 1)), wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous(),
+                          cout, out, scale, shift, relu=relu, addend=add)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), padding=1).permute(0, 2, 3, 1) * scale + shift
+    if relu == 2:
+        ref = torch.relu(ref)
+    if with_add:
+        ref = ref + add[..., :cout].float()
+    if relu == 1:
+        ref = torch.relu(ref)
+    torch.cuda.synchronize()
+    got = out[..., :cout].float()
+    assert torch.isfinite(out.float()).all()
+    assert (got - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
+
+
+@_EXPERIMENTAL
+@pytest.mark.parametrize("enc,dec,fc", [("resnet18dilated", "ppm_deepsup", 512), ("resnet50", "upernet", 2048), ("hrnetv2", "c1", 720)])
+def test_folded_eval_bn_inference_matches_the_unfolded_schedule(enc, dec, fc, monkeypatch):
+    from mit_semseg.engine.program import SegProgram
+    from oracle import segnet_oracle as O
+    feed = O.synth_batch(1, 128, 160, 8, 5)
+    seg, esd, dsd, ds = _build(enc, dec, fc, use_softmax=True, residual_gain=0.25, bias_shift=1.0, calibrate_on=feed)
+    seg.cuda().eval()
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SSEG_FOLD_BN_EVAL", flag)
+        prog = SegProgram(seg, (1, 3, 128, 160), training=False, with_grad=False, seg_size=(128, 160))
+        prog.load_inputs(feed["img_data"].cuda())
+        prog.run_eager()
+        torch.cuda.synchronize()
+        outs.append(prog.probs.clone())
+    a, b = outs
+    agree = (a.argmax(1) == b.argmax(1)).float().mean().item()
+    err = (a - b).abs().max().item()
+    print("folded vs unfolded: argmax agreement %.4f max prob err %.4f" % (agree, err))
+    assert agree >= 0.95 and err <= 5e-2   # the folded path rounds once per layer instead of twice

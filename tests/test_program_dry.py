@@ -112,3 +112,25 @@ def test_branch_streams_fork_and_join_symmetrically(enc, dec, fc, nfork_fwd, mon
     monkeypatch.setenv("SSEG_BRANCH_STREAMS", "0")
     Q = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
     assert len(P.fwd) == len(Q.fwd) + 2 * nfork_fwd and len(P.bwd) == len(Q.bwd) + 2 * nfork_fwd
+
+
+def test_folded_eval_bn_inference_schedule(monkeypatch):
+    """SSEG_FOLD_BN_EVAL=1 (opt-in): inference programs run conv+BN(+shortcut)+ReLU as one launch per layer - the raw conv
+    outputs are not even allocated and one launch per BN layer (the apply pass) disappears from the schedule."""
+    from mit_semseg.engine import program as PR
+    for enc, dec, fc in (("resnet18dilated", "ppm_deepsup", 512), ("resnet50", "upernet", 2048), ("hrnetv2", "c1", 720)):
+        seg = _seg(enc, dec, fc)
+        seg.eval()
+        monkeypatch.setenv("SSEG_FOLD_BN_EVAL", "0")
+        P0 = PR.SegProgram(seg, (1, 3, 64, 96), training=False, with_grad=False, seg_size=(64, 96), dry_run=True)
+        monkeypatch.setenv("SSEG_FOLD_BN_EVAL", "1")
+        P1 = PR.SegProgram(seg, (1, 3, 64, 96), training=False, with_grad=False, seg_size=(64, 96), dry_run=True)
+        recs = [r for r in P1.records if isinstance(r, PR.ConvBNRec)]
+        assert recs and all(r.folded for r in recs)
+        assert all(r.y is None for r in recs if r.apply)
+        applied = sum(1 for r in P0.records if isinstance(r, PR.ConvBNRec) and r.apply)
+        assert len(P0.fwd) - len(P1.fwd) == applied
+        # training programs never fold
+        seg.train()
+        P2 = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+        assert not any(r.folded for r in P2.records if isinstance(r, PR.ConvBNRec))
