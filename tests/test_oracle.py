@@ -261,3 +261,28 @@ def test_train_py_group_weight_contract():
             elif isinstance(m, nn.modules.batchnorm._BatchNorm):
                 n += (m.weight is not None) + (m.bias is not None)
         assert n == len(list(module.parameters()))
+
+
+def test_checkpoint_round_trip_through_the_builders(tmp_path):
+    """train.py:74-89 saves `encoder_epoch_N.pth` / `decoder_epoch_N.pth` as raw state dicts; eval.py / test.py hand the
+    paths to build_encoder / build_decoder (models.py:104-108,151-155: torch.load to CPU, load_state_dict strict=False).
+    The synthetic state dicts carry exactly the reference's keys (checked against reference_api.json above), so this is
+    the reference's checkpoint format."""
+    from mit_semseg.models import ModelBuilder
+    for enc_arch, dec_arch, fc in (("resnet18dilated", "ppm_deepsup", 512), ("hrnetv2", "c1", 720)):
+        esd = O.synth_state_dict(O.encoder_param_shapes(enc_arch), 7)
+        dsd = O.synth_state_dict(O.decoder_param_shapes(dec_arch, fc), 8)
+        pe, pd = str(tmp_path / ("encoder_%s.pth" % enc_arch)), str(tmp_path / ("decoder_%s.pth" % dec_arch))
+        torch.save(esd, pe)
+        torch.save(dsd, pd)
+        enc = ModelBuilder.build_encoder(enc_arch, fc_dim=fc, weights=pe)
+        dec = ModelBuilder.build_decoder(dec_arch, fc_dim=fc, num_class=150, weights=pd, use_softmax=True)
+        for net, sd in ((enc, esd), (dec, dsd)):
+            got = net.state_dict()
+            assert set(got) == set(sd)
+            assert all(torch.equal(got[k], sd[k]) for k in sd)
+        # and back: what train.py's checkpoint() writes loads into a fresh net bit for bit
+        torch.save(enc.state_dict(), pe)
+        enc2 = ModelBuilder.build_encoder(enc_arch, fc_dim=fc, weights=pe)
+        assert all(torch.equal(v, enc2.state_dict()[k]) for k, v in enc.state_dict().items())
+        assert dec.use_softmax
