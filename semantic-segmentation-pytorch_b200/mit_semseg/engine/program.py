@@ -135,6 +135,10 @@ class SegProgram:
         # Inference programs: BatchNorm with running statistics is a per-channel affine, so conv -> BN -> (+shortcut) ->
         # ReLU runs as ONE kernel (sseg_conv_igemm_affine) and the raw conv output never exists. Opt-in until measured.
         self.fold_bn_eval = _os.environ.get("SSEG_FOLD_BN_EVAL", "0") == "1"
+        # Weight re-layout off the critical path (opt-in until measured): the forward operands of everything but the first
+        # layers and ALL data-gradient operands are produced on the side stream while the stem / first stages run, and
+        # the gradient re-layout of a bucket follows its weight-gradient GEMMs on the side stream instead of the end.
+        self.overlap_relayout = _os.environ.get("SSEG_OVERLAP_RELAYOUT", "0") == "1" and part == "full"
         self._branch_streams = {}
         self._open_branches = []   # branches forked since the last join (build-time bookkeeping)
 
@@ -258,17 +262,56 @@ class SegProgram:
         return ops.BN_TRAIN_SYNC if sync else ops.BN_TRAIN
 
     # ------------------------------------------------------------------------------------------ forward pieces
+    def _wentry(self, c, wf=True, wd=True):
+        return dict(w=c.mod.weight.detach(), wf=c.wf if wf else None, wd=c.wd if (wd and self.with_grad) else None,
+                    g_src=c.gw if self.with_grad else None, g_dst=c.pg, O=c.O, I=c.I, T=c.T, o_pad=c.Opad)
+
     def _prep_weights(self):
         """One launch re-lays out every conv weight (fp32 OIHW master -> bf16 GEMM operands)."""
-        entries = []
-        for c in self.convs.values():
-            if c.I == 3:
-                continue  # the stem conv reads the fp32 master weight directly
+        convs = [c for c in self.convs.values() if c.I != 3]  # the stem conv reads the fp32 master weight directly
+        for c in convs:
             c.pg = torch.empty_like(c.mod.weight) if self.with_grad else None
-            entries.append(dict(w=c.mod.weight.detach(), wf=c.wf, wd=c.wd if self.with_grad else None,
-                                g_src=c.gw if self.with_grad else None, g_dst=c.pg, O=c.O, I=c.I, T=c.T, o_pad=c.Opad))
-        self.wtable = ops.WeightTable(entries, self.dev)
-        self.fwd.append(self.wtable.prep)
+        self._late_convs, self._late_pending = set(), False
+        if not self.overlap_relayout:
+            self.wtable = ops.WeightTable([self._wentry(c) for c in convs], self.dev)
+            self.fwd.append(self.wtable.prep)
+            return
+        # early = the first ~2 M weight elements in execution (= module) order: stem, layer1, layer2 of a ResNet
+        early, acc = [], 0
+        for c in convs:
+            acc += c.O * c.T * c.I
+            if acc > 2_000_000 and early:
+                break
+            early.append(c)
+        late = convs[len(early):]
+        self._late_convs = {id(c) for c in late}
+        t_early = ops.WeightTable([self._wentry(c, wd=False) for c in early], self.dev)
+        t_late = ops.WeightTable([self._wentry(c, wd=False) for c in late], self.dev) if late else None
+        t_dgrad = ops.WeightTable([self._wentry(c, wf=False) for c in convs], self.dev) if self.with_grad else None
+        self._prep_tables = (t_early, t_late, t_dgrad)
+        self.fwd.append(t_early.prep)
+
+        def rest():
+            if t_late is not None:
+                t_late.prep()
+            if not getattr(self, "serial", False):
+                self._ev_late = torch.cuda.Event()
+                self._ev_late.record(torch.cuda.current_stream(self.dev))
+            if t_dgrad is not None:
+                t_dgrad.prep()
+        self.fwd.append(self.on_side(rest))
+        self._late_pending = t_late is not None
+
+    def _need_weights(self, cw):
+        """Called before a convolution is scheduled: the first one whose forward operand is produced on the side stream
+        makes the main stream wait for that (and only that) part of the side stream's work."""
+        if self._late_pending and id(cw) in self._late_convs:
+            self._late_pending = False
+
+            def wait():
+                if not getattr(self, "serial", False):
+                    torch.cuda.current_stream(self.dev).wait_event(self._ev_late)
+            self.fwd.append(wait)
 
     def _conv_geom(self, srcs, cw):
         """Input-side geometry of conv `cw` over the (virtual concat of) NHWC tensors `srcs` -> (geom, out H, out W)."""
@@ -567,7 +610,9 @@ class SegProgram:
         # stream right behind the weight-gradient GEMMs that fill them, so they overlap the rest of the backward pass:
         #   [ small (BN, biases) | encoder stem..layer3 | encoder layer4 | decoder ]
         buckets = []
-        if self.dist is not None and self.enc is not None and self.dec is not None:
+        if self.overlap_relayout:
+            self.bwd.append(self.join_side)   # the data-gradient operands were produced on the side stream
+        if (self.dist is not None or self.overlap_relayout) and self.enc is not None and self.dec is not None:
             dec_ids = {id(m) for m in self.dec.modules()}
             late = self.enc.layer4 if hasattr(self.enc, "layer4") else self.enc.stage4   # the encoder's last stage
             l4_ids = {id(m) for m in late.modules()}
@@ -577,13 +622,32 @@ class SegProgram:
             end = self.gflat.numel()
             buckets = [(dec_ids, self.gflat[dec_off:end]), (dec_ids | l4_ids, self.gflat[l4_off:dec_off])]
             rest = self.gflat[:l4_off]
+        scale = 1.0 / self.world
+        gtables = None
+        if self.overlap_relayout and buckets:
+            # gradient re-layout tables per bucket (decoder | last encoder stage | rest), same partition as the all-reduces
+            parts = ([], [], [])
+            for c in self.convs.values():
+                if c.I == 3:
+                    continue
+                parts[0 if id(c.mod) in dec_ids else (1 if id(c.mod) in l4_ids else 2)].append(self._wentry(c))
+            gtables = [ops.WeightTable(e, self.dev) if e else None for e in parts]
         pending = list(buckets)
+        nclosed = 0
         for rec in reversed(self.records):
             mod = getattr(getattr(rec, "cw", None), "mod", None)
             if pending and mod is not None and id(mod) not in pending[0][0]:
                 # every record of this bucket has emitted its weight gradient: reduce it behind them on the side stream
                 sl = pending.pop(0)[1]
-                self.bwd.append(self.on_side(lambda sl=sl: self.dist.all_reduce(sl)))
+                gt = gtables[nclosed] if gtables is not None else None
+                nclosed += 1
+
+                def close_bucket(sl=sl, gt=gt):
+                    if self.dist is not None:
+                        self.dist.all_reduce(sl)
+                    if gt is not None:
+                        gt.grads(scale)
+                self.bwd.append(self.on_side(close_bucket))
             k = getattr(rec, "branch", None) if self.use_branches else None
             if isinstance(rec, AvgPoolRec):
                 k = None   # the pyramid's pools share ONE grouped backward kernel: it runs on the main stream
@@ -612,7 +676,6 @@ class SegProgram:
                 self.bwd.append(lambda: self.dist.all_reduce(self.gflat))
         # gradients into each parameter's own layout (static buffers, so they are part of the captured graph);
         # 1/world_size = the reference's mean over per-GPU losses (train.py:42)
-        scale = 1.0 / self.world
         self._pg = {}
         if scale != 1.0:
             self.bwd.append(lambda: self.gflat[:self.g_small].mul_(scale))
@@ -628,7 +691,12 @@ class SegProgram:
                 self.bwd.append(stem_grad)
             else:
                 self._pg[id(c)] = c.pg
-        self.bwd.append(lambda: self.wtable.grads(scale))
+        if gtables is None:
+            self.bwd.append(lambda: self.wtable.grads(scale))
+        else:
+            for gt in gtables[nclosed:]:   # buckets whose re-layout has not been issued behind their GEMMs
+                if gt is not None:
+                    self.bwd.append(lambda gt=gt: gt.grads(scale))
 
     def on_side(self, fn):
         """Closure that runs `fn` on the side stream, ordered after everything enqueued so far on the main stream."""
@@ -934,6 +1002,7 @@ class ConvBNRec:
         train = self.mode != ops.BN_EVAL
         C = cw.O
         geom, wf, y = self.geom, cw.wf, self.y
+        P._need_weights(cw)
         P.fwd.append(lambda: ops.conv_igemm(geom, wf, C, y, stat_sum=st[:C] if train else None,
                                             stat_sqsum=st[C:2 * C] if train else None))
         if apply:
@@ -975,6 +1044,7 @@ class ConvBNRec:
         if self.post_add is not None:
             addend, relu = self.post_add.tp, ops.RELU_BEFORE_ADD
         geom, wf, C = self.geom, cw.wf, cw.O
+        P._need_weights(cw)
         P.fwd.append(lambda: ops.conv_igemm_affine(geom, wf, C, out, bns.scale, bns.shift, relu=relu, addend=addend))
 
     def backward(self, g_override=None):
@@ -1200,6 +1270,7 @@ class ClassifierRec:
         self.geom, _, _ = P._conv_geom([x.t], cw)
         self.dlogits = None
         geom, wf, O, bias = self.geom, cw.wf, cw.O, cw.mod.bias
+        P._need_weights(cw)
         P.fwd.append(lambda: ops.conv_igemm(geom, wf, O, self.logits, n_store=_pad(O, 8),
                                             bias=bias.detach() if bias is not None else None))
 

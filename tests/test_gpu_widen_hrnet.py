@@ -86,10 +86,11 @@ def test_multiscale_inference_equals_the_reference_loop():
 
 @pytest.mark.skipif(__import__("os").environ.get("SSEG_TEST_EXPERIMENTAL", "0") != "1",
                     reason="opt-in features not yet measured on B200 (set SSEG_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("switch", ["SSEG_BRANCH_STREAMS", "SSEG_OVERLAP_RELAYOUT"])
 @pytest.mark.parametrize("enc,dec,fc,stride", [("resnet18dilated", "ppm_deepsup", 512, 8), ("hrnetv2", "c1", 720, 4)])
-def test_branch_streams_match_the_single_stream_schedule(enc, dec, fc, stride, monkeypatch):
-    """SSEG_BRANCH_STREAMS=1: same loss and gradients (frozen BN: no atomics-order noise in the statistics), eager and
-    as a captured graph."""
+def test_opt_in_schedules_match_the_default_schedule(enc, dec, fc, stride, switch, monkeypatch):
+    """Branch streams / overlapped re-layout: same loss and gradients as the default schedule (frozen BN: no atomics-order
+    noise in the statistics), eager and as a captured graph."""
     import torch.nn as nn
     from mit_semseg.engine.program import SegProgram
     from oracle import segnet_oracle as O
@@ -103,7 +104,7 @@ def test_branch_streams_match_the_single_stream_schedule(enc, dec, fc, stride, m
     feed = O.synth_batch(2, 128, 128, stride, 3)
     res = {}
     for flag in ("0", "1"):
-        monkeypatch.setenv("SSEG_BRANCH_STREAMS", flag)
+        monkeypatch.setenv(switch, flag)
         prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
         prog.load_inputs(feed["img_data"].cuda(), feed["seg_label"].cuda())
         prog.run_eager()

@@ -7,6 +7,12 @@ import torch
 import torch.nn as nn
 
 
+@pytest.fixture(autouse=True)
+def _default_switches(monkeypatch):
+    for name in ("SSEG_BRANCH_STREAMS", "SSEG_FOLD_BN_EVAL", "SSEG_OVERLAP_RELAYOUT"):
+        monkeypatch.delenv(name, raising=False)
+
+
 def _seg(enc_arch, dec_arch, fc):
     from mit_semseg.models import ModelBuilder, SegmentationModule
     from mit_semseg.models import hrnet as HR, models as M, resnet as R
@@ -134,3 +140,21 @@ def test_folded_eval_bn_inference_schedule(monkeypatch):
         seg.train()
         P2 = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
         assert not any(r.folded for r in P2.records if isinstance(r, PR.ConvBNRec))
+
+
+def test_overlapped_relayout_schedule(monkeypatch):
+    """SSEG_OVERLAP_RELAYOUT=1 (opt-in): forward operands of the late layers + all data-gradient operands are produced on
+    the side stream (one wait before the first late convolution), gradient re-layout follows each bucket's GEMMs."""
+    from mit_semseg.engine import program as PR
+    seg = _seg("resnet50dilated", "ppm_deepsup", 2048)
+    seg.train()
+    Q = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+    monkeypatch.setenv("SSEG_OVERLAP_RELAYOUT", "1")
+    P = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+    t_early, t_late, t_dgrad = P._prep_tables
+    assert t_early.n + t_late.n == t_dgrad.n == len(P.convs) - 1            # every conv but the 3-channel stem conv
+    early = [c for c in P.convs.values() if c.I != 3 and id(c) not in P._late_convs]
+    assert sum(c.O * c.T * c.I for c in early) <= 2_000_000 and not P._late_pending
+    assert len(P.fwd) == len(Q.fwd) + 2      # side-stream prep + one wait
+    assert len(P.bwd) == len(Q.bwd) + 3      # join for the dgrad operands, 2 bucket closes + rest instead of one re-layout
+    assert set(P.param_grads()) == set(Q.param_grads())
