@@ -18,6 +18,10 @@ from test_gpu_e2e import _build, _rel, _step_metrics
 
 pytestmark = pytest.mark.gpu
 
+# code paths written after the round's GPU budget was spent: they run with SSEG_TEST_EXPERIMENTAL=1 (first thing next round)
+_EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("SSEG_TEST_EXPERIMENTAL", "0") != "1",
+                                   reason="not yet run on B200 (set SSEG_TEST_EXPERIMENTAL=1)")
+
 def test_hrnetv2_c1_backward_wiring_bn_eval():
     """305 encoder convolutions on 48/96/192/384-channel branches (partial 64-channel K blocks),
     26 exchange outputs (fused sum / bilinear-sample / ReLU kernel and its adjoint), stride-2 chains over parity planes,
@@ -67,6 +71,7 @@ def test_hrnetv2_c1_inference_and_module_level_encoder():
     assert _rel(feats[0].cpu(), ref_feats[0]) <= 1e-2
 
 
+@_EXPERIMENTAL
 def test_multiscale_inference_equals_the_reference_loop():
     """eval.py:63-72: scores = sum_k module({img_k}, segSize) / len(scales) — here accumulated inside the head kernel."""
     import torch.nn.functional as F
@@ -84,8 +89,7 @@ def test_multiscale_inference_equals_the_reference_loop():
     assert (fused.sum(1) - 1).abs().max().item() < 1e-3
 
 
-@pytest.mark.skipif(__import__("os").environ.get("SSEG_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="opt-in features not yet measured on B200 (set SSEG_TEST_EXPERIMENTAL=1)")
+@_EXPERIMENTAL
 @pytest.mark.parametrize("switch", ["SSEG_BRANCH_STREAMS", "SSEG_OVERLAP_RELAYOUT"])
 @pytest.mark.parametrize("enc,dec,fc,stride", [("resnet18dilated", "ppm_deepsup", 512, 8), ("hrnetv2", "c1", 720, 4)])
 def test_opt_in_schedules_match_the_default_schedule(enc, dec, fc, stride, switch, monkeypatch):
@@ -120,9 +124,6 @@ def test_opt_in_schedules_match_the_default_schedule(enc, dec, fc, stride, switc
     for p, g in res["0"][1].items():
         assert _rel(res["1"][1][p], g) <= 2e-3   # split-K atomics order is the only difference
 
-
-_EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("SSEG_TEST_EXPERIMENTAL", "0") != "1",
-                                   reason="opt-in features not yet measured on B200 (set SSEG_TEST_EXPERIMENTAL=1)")
 
 
 @_EXPERIMENTAL
