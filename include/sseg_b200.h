@@ -106,6 +106,43 @@ int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld,
                     sseg_stream_t stream);
 
 /*
+ * Convolution + TRAIN-mode BatchNorm (+ shortcut, ReLU, Dropout2d mask) in one kernel (single-GPU F.batch_norm branch,
+ * lib/nn/modules/batchnorm.py:58-61): conv -> batch statistics -> normalise -> (+residual) -> ReLU of
+ * models/resnet.py:37-53,72-92 / models/models.py:160-167 without sseg_bn_finalize / sseg_bn_apply launches.
+ * One persistent CTA per SM keeps all its accumulators in tensor memory across an in-kernel grid barrier, so the layer
+ * must fit: ceil(tiles / #SMs) * tile_columns <= 512 (sseg_conv_bn_train_fits returns 1 / 0 for the same arguments).
+ *   y        : optional bf16 tensor receiving the raw convolution output (the backward pass reads it)
+ *   a_out    : bf16 activation, same shape as y
+ *   stat_sum / stat_sqsum : float[cout], zeroed by the caller; counter: one zeroed uint32 (the grid barrier)
+ *   mean_out .. shift_out : float[cout] written for the backward pass; running_* updated with `momentum` if given
+ *   res (+ rscale/rshift) : shortcut tensor (and, for projection shortcuts, its own BN affine); res_after_relu as in
+ *                           sseg_bn_apply; chanmul: float[N][cout] Dropout2d keep-mask/(1-p) or NULL
+ */
+typedef struct {
+  const float* gamma;
+  const float* beta;
+  float eps, momentum, count;
+  float* stat_sum;
+  float* stat_sqsum;
+  unsigned int* counter;
+  float* mean_out;
+  float* invstd_out;
+  float* scale_out;
+  float* shift_out;
+  float* running_mean;
+  float* running_var;
+  const sseg_act_t* res;
+  const float* rscale;
+  const float* rshift;
+  const float* chanmul;
+  int relu, res_after_relu;
+} sseg_bn_fused_t;
+int sseg_conv_bn_train(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                       const sseg_act_t* a_out, const sseg_bn_fused_t* bn, sseg_stream_t stream);
+int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                            const sseg_act_t* a_out, const sseg_bn_fused_t* bn);
+
+/*
  * Convolution with the inference-time epilogue fused: out = relu?( conv(x) * scale[co] + shift[co] (+ addend) ).
  * BatchNorm with running statistics is a per-channel affine (F.batch_norm eval branch, lib/nn/modules/batchnorm.py:
  * 58-61), so conv -> BN -> (+shortcut) -> ReLU (models/resnet.py:37-53,72-92; models/models.py:160-167) is ONE kernel

@@ -682,6 +682,351 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
                     "igemm_kernel launch");
 }
 
+// =====================================================================================================
+// Convolution + train-mode BatchNorm (+ shortcut, ReLU, Dropout2d mask) in ONE kernel.
+//
+// BatchNorm needs the statistics of the WHOLE layer between "accumulate" and "normalise". One persistent CTA per SM
+// keeps the fp32 accumulators of ALL its tiles in tensor memory (512 columns = 4 tiles of 128 or 8 tiles of 64):
+//   phase 1  per tile: main loop -> tcgen05.ld -> bf16 rounding -> (store y, which the backward pass reads) ->
+//            per-channel sum / sum of squares of the rounded values -> atomics into the layer's statistics
+//   barrier  every CTA arrives on one global counter (the grid is at most one CTA per SM, so all CTAs are resident)
+//   phase 2  per tile: scale / shift from the now complete statistics (the CTA owning the first M tile of a channel
+//            block publishes mean / inv_std / scale / shift and updates the running statistics) -> second tcgen05.ld
+//            of the still-resident accumulator -> affine (+ shortcut, ReLU, dropout mask) -> store of the activation.
+// Replaces sseg_conv_igemm(stats) + sseg_bn_finalize(SSEG_BN_TRAIN) + sseg_bn_apply: two launches and one full read
+// of y per layer (reference: conv -> F.batch_norm(training) -> (+residual) -> ReLU, models/resnet.py:37-53,72-92;
+// lib/nn/modules/batchnorm.py:58-61).
+// =====================================================================================================
+struct IgemmBnParams {
+  IgemmParams g;  // operands / geometry; g.out = y (bf16) or null; g.stat_sum / g.stat_sqsum = the layer's statistics
+  __nv_bfloat16* a_out;  // activation, same geometry as y
+  int ld_a;
+  long a_row_stride, a_img_stride;
+  const float* gamma;
+  const float* beta;
+  float eps, momentum, count;
+  float *mean_out, *invstd_out, *scale_out, *shift_out;
+  float *running_mean, *running_var;  // null: no running-statistics update
+  const __nv_bfloat16* res;           // shortcut / top-down tensor or null
+  int ld_res;
+  long res_row_stride, res_img_stride;
+  const float *rscale, *rshift;  // the shortcut's own BN affine (projection shortcut) or null
+  const float* chanmul;          // [N][cout] Dropout2d keep-mask / (1-p) or null
+  int relu, res_after_relu;
+  long pix_per_img;  // to find the image of a pixel when the batch is viewed as one row of pixels (1x1 convs)
+  unsigned int* counter;  // zeroed by the caller before every launch
+  int num_tiles, tiles_per_cta;
+};
+
+template <int BLOCK_N, int STAGES>
+struct IgemmBnSmem {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPitch = BLOCK_N * 2 + 16;
+  static constexpr int kStgOff = STAGES * kStageBytes;
+  static constexpr int kCoefOff = kStgOff + ((128 * kPitch + 1023) / 1024) * 1024;  // scale | shift | rscale | rshift
+  static constexpr int kBarOff = kCoefOff + 4 * BLOCK_N * 4;
+  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kDynBytes = kTotal + 1024;
+  static constexpr int kMaxTiles = 512 / BLOCK_N;  // accumulators that fit the SM's tensor memory
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_constant__ IgemmBnParams q) {
+  using L = IgemmBnSmem<BLOCK_N, STAGES>;
+  const IgemmParams& p = q.g;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;  // [kMaxTiles]: accumulator i is complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + L::kMaxTiles);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k_steps = p.num_k_steps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < L::kMaxTiles; ++b) mbar_init(&tmem_full_bar[b], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);  // every accumulator of this CTA stays resident until phase 2
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();
+
+  if (warp == 0) {
+    // ===================== TMA producer: runs ahead across tile boundaries =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int th = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
+          const int fixed_src = p.tap_src[t];
+          const int nblk = fixed_src >= 0 ? p.src_blk_end[0] : p.blocks_per_tap;
+          int src = fixed_src >= 0 ? fixed_src : 0, blk_begin = 0;
+          for (int b = 0; b < nblk; ++b) {
+            if (fixed_src < 0) {
+              while (b >= p.src_blk_end[src]) {
+                blk_begin = p.src_blk_end[src];
+                ++src;
+              }
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
+            const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+            tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: accumulator i lives at TMEM columns [i*BLOCK_N, +BLOCK_N) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, kBlockM, BLOCK_N);
+      int stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t d_tmem = tmem_base + it * BLOCK_N;
+        for (int ks = 0; ks < num_k_steps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        umma_commit(&tmem_full_bar[it]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps: phase 1, grid barrier, phase 2 =====================
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = quarter * 32 + lane;
+    const int t = threadIdx.x - 64;  // 0..127
+    constexpr int kPitch = L::kPitch;
+    uint8_t* stg = smem + L::kStgOff;
+    float* coef = reinterpret_cast<float*>(smem + L::kCoefOff);  // [scale | shift | rscale | rshift][BLOCK_N]
+    constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
+    const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+
+    for (int phase2 = 0; phase2 < 2; ++phase2) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, ++it) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const bool first_m_tile = m_tile == 0;
+        const int tw = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int th = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + it * BLOCK_N;
+        const int hh = h0 + (row >> p.bw_shift), ww = w0 + (row & (p.BW - 1));
+        const bool valid = (hh < p.H) && (ww < p.W);
+
+        if (phase2) {
+          // per-channel coefficients of this tile's channel block from the complete statistics
+          if (t < BLOCK_N) {
+            const int c = n0 + t;
+            float sc = 0.f, sh = 0.f, rs = 1.f, rb = 0.f;
+            if (c < p.cout) {
+              const float sum = __ldcg(p.stat_sum + c), sq = __ldcg(p.stat_sqsum + c);
+              const float mean = sum / q.count;
+              const float sumvar = sq - sum * mean;
+              const float inv_std = rsqrtf(fmaxf(sumvar / q.count, 0.f) + q.eps);
+              const float gm = q.gamma ? q.gamma[c] : 1.f, bt = q.beta ? q.beta[c] : 0.f;
+              sc = gm * inv_std, sh = bt - mean * gm * inv_std;
+              if (q.rscale != nullptr) rs = q.rscale[c], rb = q.rshift[c];
+              if (first_m_tile) {  // exactly one tile per channel block publishes (the backward pass reads these)
+                q.mean_out[c] = mean, q.invstd_out[c] = inv_std, q.scale_out[c] = sc, q.shift_out[c] = sh;
+                if (q.running_mean != nullptr) {
+                  q.running_mean[c] = (1.f - q.momentum) * q.running_mean[c] + q.momentum * mean;
+                  q.running_var[c] = (1.f - q.momentum) * q.running_var[c] + q.momentum * sumvar / (q.count - 1.f);
+                }
+              }
+            }
+            coef[t] = sc, coef[BLOCK_N + t] = sh, coef[2 * BLOCK_N + t] = rs, coef[3 * BLOCK_N + t] = rb;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          tc_fence_after();
+        } else {
+          mbar_wait(&tmem_full_bar[it], 0);
+          tc_fence_after();
+        }
+
+        const long pix_off_a = img * q.a_img_stride + hh * q.a_row_stride + static_cast<long>(ww) * q.ld_a;
+        const long pix_off_r = img * q.res_img_stride + hh * q.res_row_stride + static_cast<long>(ww) * q.ld_res;
+        // image of this pixel (Dropout2d draws one value per image and channel)
+        const long img_of_pix = q.pix_per_img > 0 ? (static_cast<long>(hh) * p.W + ww) / q.pix_per_img : img;
+        (void)pix_off_a;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+          uint32_t raw[32];
+          tmem_ld_32x32(d_tmem + (static_cast<uint32_t>(quarter * 32) << 16) + chunk * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+          const int col0 = n0 + chunk * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)  // y as stored: one bf16 rounding of the fp32 accumulator
+            v[j] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[j])));
+          if (phase2) {
+            const float* sc = coef + chunk * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], sc[j], sc[BLOCK_N + j]);
+            float rr[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) rr[j] = 0.f;
+            if (q.res != nullptr && valid) {
+              const __nv_bfloat16* rp = q.res + pix_off_r + col0;
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                if (col0 + g8 * 8 < p.n_store) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(rp + g8 * 8));
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    rr[g8 * 8 + 2 * e] = fmaf(f.x, sc[2 * BLOCK_N + g8 * 8 + 2 * e], sc[3 * BLOCK_N + g8 * 8 + 2 * e]);
+                    rr[g8 * 8 + 2 * e + 1] =
+                        fmaf(f.y, sc[2 * BLOCK_N + g8 * 8 + 2 * e + 1], sc[3 * BLOCK_N + g8 * 8 + 2 * e + 1]);
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = v[j];
+              if (!q.res_after_relu) x += rr[j];
+              if (q.relu) x = fmaxf(x, 0.f);
+              if (q.res_after_relu) x += rr[j];
+              v[j] = x;
+            }
+            if (q.chanmul != nullptr) {
+              const float* m = q.chanmul + img_of_pix * p.cout + col0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.cout) v[j] *= __ldg(m + j);
+            }
+          }
+          uint8_t* sp = stg + row * kPitch + chunk * 64;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);  // rows outside the image contribute zeros to the statistics
+            if (valid) {
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g8 * 8 + 2 * e], v[g8 * 8 + 2 * e + 1]);
+            }
+            *reinterpret_cast<uint4*>(sp + g8 * 16) = u;
+          }
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the staged tile is complete
+
+        if (!phase2) {
+          // statistics of the values as stored: thread = one pair of adjacent columns x one slab of rows
+          constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
+          const int cp = t % kPairs, slab = t / kPairs;
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const uint8_t* base = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll 8
+          for (int r = 0; r < kRowsPerSlab; ++r) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + r * kPitch));
+            s0 += f.x, s1 += f.y;
+            q0 = fmaf(f.x, f.x, q0), q1 = fmaf(f.y, f.y, q1);
+          }
+          const int col = n0 + cp * 2;
+          if (col < p.cout) atomicAdd(p.stat_sum + col, s0), atomicAdd(p.stat_sqsum + col, q0);
+          if (col + 1 < p.cout) atomicAdd(p.stat_sum + col + 1, s1), atomicAdd(p.stat_sqsum + col + 1, q1);
+        }
+        // coalesced store of the staged tile: y in phase 1 (if requested), the activation in phase 2
+        __nv_bfloat16* dst = phase2 ? q.a_out : reinterpret_cast<__nv_bfloat16*>(p.out);
+        if (dst != nullptr && n0 + seg * 8 < p.n_store) {
+          const long istr = phase2 ? q.a_img_stride : p.out_img_stride, rstr = phase2 ? q.a_row_stride : p.out_row_stride;
+          const long ld = phase2 ? q.ld_a : p.ld_out;
+#pragma unroll 4
+          for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
+            const int r = pass * kRowsPerPass + r0;
+            const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+            if (rh < p.H && rw < p.W) {
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + r * kPitch + seg * 16);
+              *reinterpret_cast<uint4*>(dst + img * istr + rh * rstr + static_cast<long>(rw) * ld + n0 + seg * 8) = u;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile (and coefficients) free for the next tile
+      }
+      if (!phase2) {
+        // ---- grid barrier: the layer's statistics are complete once every CTA has arrived
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t == 0) {
+          atomicAdd(q.counter, 1u);
+          while (ld_acquire_gpu(q.counter) < gridDim.x) {
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_bn(const IgemmBnParams& q, int grid, cudaStream_t stream) {
+  using L = IgemmBnSmem<BLOCK_N, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  SSEG_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    SSEG_CUDA(cudaFuncSetAttribute(igemm_bn_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   L::kDynBytes));
+    configured[dev] = true;
+  }
+  count_launch(1);
+  return check_cuda(launch_coop(igemm_bn_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, q),
+                    "igemm_bn_kernel launch");
+}
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
@@ -763,7 +1108,8 @@ struct EpilogueAffine {
 static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
                            int out_f32, const float* bias, const sseg_act_t* addend, float* stat_sum, float* stat_sqsum,
                            const sseg_act_t* bw_y, const float* bw_fscale, const float* bw_fshift, float* bw_s1,
-                           float* bw_s2, sseg_stream_t stream_, const EpilogueAffine* ep = nullptr) {
+                           float* bw_s2, sseg_stream_t stream_, const EpilogueAffine* ep = nullptr,
+                           IgemmParams* params_out = nullptr, int* block_n_out = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SSEG_REQUIRE(g != nullptr && out != nullptr && w_bf16 != nullptr, "sseg_conv_igemm: null argument");
   const int n_store = out->c;
@@ -836,6 +1182,11 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     p.bw_fscale = bw_fscale, p.bw_fshift = bw_fshift, p.bw_s1 = bw_s1, p.bw_s2 = bw_s2;
   }
   const int grid = gh.vn * p.tiles_h * p.tiles_w * p.n_tiles;
+  if (params_out != nullptr) {  // the caller launches a different kernel over the same operands / geometry
+    *params_out = p;
+    *block_n_out = block_n;
+    return grid;
+  }
   // persistent CTAs (one per SM, double-buffered accumulators) once there are clearly more tiles than SMs
   static const int persistent_min_tiles = env_int("SSEG_IGEMM_PERSISTENT", 0);  // 0 = off; e.g. 200 = on for >= 200 tiles
   if (persistent_min_tiles > 0 && grid >= persistent_min_tiles) {
@@ -877,6 +1228,90 @@ extern "C" int sseg_conv_igemm_bnbwd(const sseg_conv_geom_t* g, const void* w_bf
   SSEG_REQUIRE(y != nullptr, "sseg_conv_igemm_bnbwd: y required");
   return conv_igemm_impl(g, w_bf16, w_ld, cout, out, 0, nullptr, addend, nullptr, nullptr, y, fscale, fshift, s1, s2_raw,
                          stream);
+}
+
+static int num_sms_of_current_device(int* out) {
+  static int cached[64] = {};
+  int dev = 0;
+  SSEG_CUDA(cudaGetDevice(&dev));
+  if (dev >= 64 || cached[dev] == 0) {
+    int n = 0;
+    SSEG_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 64) cached[dev] = n;
+    *out = n;
+    return 0;
+  }
+  *out = cached[dev];
+  return 0;
+}
+
+static int conv_bn_train_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                              const sseg_act_t* a_out, const sseg_bn_fused_t* bn, int query_only, sseg_stream_t stream_) {
+  SSEG_REQUIRE(a_out != nullptr && bn != nullptr, "sseg_conv_bn_train: null argument");
+  SSEG_REQUIRE(bn->stat_sum && bn->stat_sqsum && bn->counter && bn->mean_out && bn->invstd_out && bn->scale_out &&
+                   bn->shift_out && bn->count > 1.f,
+               "sseg_conv_bn_train: statistics / output vectors required");
+  SSEG_REQUIRE((bn->running_mean == nullptr) == (bn->running_var == nullptr), "sseg_conv_bn_train: running stats must pair");
+  SSEG_REQUIRE((bn->rscale == nullptr) == (bn->rshift == nullptr), "sseg_conv_bn_train: rscale/rshift must pair");
+  // geometry / operand set-up is the plain convolution's; `y` may be omitted (inference-like use), then the activation
+  // tensor stands in for the shape checks
+  IgemmBnParams q;
+  memset(&q, 0, sizeof(q));
+  int block_n = 0;
+  const sseg_act_t* shape_ref = y != nullptr ? y : a_out;
+  const int tiles = conv_igemm_impl(g, w_bf16, w_ld, cout, shape_ref, 0, nullptr, nullptr, bn->stat_sum, bn->stat_sqsum, nullptr,
+                                    nullptr, nullptr, nullptr, nullptr, stream_, nullptr, &q.g, &block_n);
+  if (tiles < 0) return tiles;
+  if (y == nullptr) q.g.out = nullptr;
+  int sms = 0;
+  int rc = num_sms_of_current_device(&sms);
+  if (rc) return rc;
+  const int max_tiles = 512 / block_n;
+  const int per_cta = ceil_div(tiles, sms);
+  if (query_only) return per_cta <= max_tiles ? 1 : 0;
+  SSEG_REQUIRE(per_cta <= max_tiles, "sseg_conv_bn_train: %d tiles do not fit the tensor memory of %d SMs", tiles, sms);
+  SSEG_REQUIRE(a_out->n == shape_ref->n && a_out->h == shape_ref->h && a_out->w == shape_ref->w && a_out->c == shape_ref->c &&
+                   a_out->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(a_out->ptr) & 15) == 0 &&
+                   a_out->row_stride % 8 == 0 && a_out->img_stride % 8 == 0,
+               "sseg_conv_bn_train: activation output shape / alignment");
+  // 1x1 launches view the batch as one row of pixels (conv_igemm_impl decides; it needs every operand dense)
+  const bool flat = q.g.N == 1 && q.g.H == 1 && (shape_ref->n != 1 || shape_ref->h != 1);
+  SSEG_REQUIRE(!flat || (act_is_dense(*a_out) && (bn->res == nullptr || act_is_dense(*bn->res))),
+               "sseg_conv_bn_train: 1x1 launches need dense activation / shortcut tensors");
+  q.a_out = static_cast<__nv_bfloat16*>(a_out->ptr);
+  q.ld_a = a_out->ld, q.a_row_stride = a_out->row_stride, q.a_img_stride = a_out->img_stride;
+  q.gamma = bn->gamma, q.beta = bn->beta, q.eps = bn->eps, q.momentum = bn->momentum, q.count = bn->count;
+  q.mean_out = bn->mean_out, q.invstd_out = bn->invstd_out, q.scale_out = bn->scale_out, q.shift_out = bn->shift_out;
+  q.running_mean = bn->running_mean, q.running_var = bn->running_var;
+  if (bn->res != nullptr) {
+    const sseg_act_t* r = bn->res;
+    SSEG_REQUIRE(r->n == a_out->n && r->h == a_out->h && r->w == a_out->w && r->c >= a_out->c && r->ld % 8 == 0 &&
+                     (reinterpret_cast<uintptr_t>(r->ptr) & 15) == 0 && r->row_stride % 8 == 0 && r->img_stride % 8 == 0,
+                 "sseg_conv_bn_train: shortcut shape / alignment");
+    q.res = static_cast<const __nv_bfloat16*>(r->ptr);
+    q.ld_res = r->ld, q.res_row_stride = r->row_stride, q.res_img_stride = r->img_stride;
+    q.rscale = bn->rscale, q.rshift = bn->rshift;
+  }
+  q.chanmul = bn->chanmul;
+  q.relu = bn->relu, q.res_after_relu = bn->res_after_relu;
+  q.pix_per_img = flat ? (long)shape_ref->h * shape_ref->w : 0;
+  q.counter = bn->counter;
+  q.num_tiles = tiles;
+  q.tiles_per_cta = per_cta;
+  const int grid = ceil_div(tiles, per_cta);  // <= number of SMs: every CTA is resident, the in-kernel barrier is safe
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (block_n == 64) return launch_bn<64, 6>(q, grid, stream);
+  return launch_bn<128, 4>(q, grid, stream);
+}
+
+extern "C" int sseg_conv_bn_train(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                                  const sseg_act_t* a_out, const sseg_bn_fused_t* bn, sseg_stream_t stream) {
+  return conv_bn_train_impl(g, w_bf16, w_ld, cout, y, a_out, bn, 0, stream);
+}
+
+extern "C" int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                                       const sseg_act_t* y, const sseg_act_t* a_out, const sseg_bn_fused_t* bn) {
+  return conv_bn_train_impl(g, w_bf16, w_ld, cout, y, a_out, bn, 1, nullptr);
 }
 
 // =====================================================================================================

@@ -43,6 +43,15 @@ class SumTerm(Structure):
     _fields_ = [("x", c_void_p), ("h", c_int), ("w", c_int), ("ld", c_long), ("scale", c_void_p), ("shift", c_void_p)]
 
 
+class BnFused(Structure):
+    """sseg_bn_fused_t: the BatchNorm half of sseg_conv_bn_train."""
+    _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("momentum", c_float), ("count", c_float),
+                ("stat_sum", c_void_p), ("stat_sqsum", c_void_p), ("counter", c_void_p), ("mean_out", c_void_p),
+                ("invstd_out", c_void_p), ("scale_out", c_void_p), ("shift_out", c_void_p), ("running_mean", c_void_p),
+                ("running_var", c_void_p), ("res", POINTER(Act)), ("rscale", c_void_p), ("rshift", c_void_p),
+                ("chanmul", c_void_p), ("relu", c_int), ("res_after_relu", c_int)]
+
+
 class SgdChunk(Structure):
     """sseg_sgd_chunk_t"""
     _fields_ = [("param", c_void_p), ("grad", c_void_p), ("momentum_buf", c_void_p), ("weight_decay", c_float),
@@ -93,6 +102,8 @@ _ip = POINTER(c_int)
 _SIGNATURES = {
     "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), c_int, _p, POINTER(Act), _p, _p, _p],
     "sseg_conv_igemm_affine": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), _p, _p, c_int, POINTER(Act), _p],
+    "sseg_conv_bn_train": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(BnFused), _p],
+    "sseg_conv_bn_train_fits": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(BnFused)],
     "sseg_conv_igemm_bnbwd": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(Act), _p, _p, _p, _p, _p],
     "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
     "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],

@@ -77,6 +77,42 @@ def conv_igemm_affine(geom, w_bf16, cout, out, scale, shift, relu=RELU_AFTER_ADD
     return out
 
 
+def make_bn_fused(gamma, beta, eps, momentum, count, stat_sum, stat_sqsum, counter, mean, invstd, scale, shift,
+                  running_mean=None, running_var=None, res=None, rscale=None, rshift=None, chanmul=None, relu=True,
+                  res_after_relu=False):
+    """sseg_bn_fused_t for conv_bn_train (keep the returned object and the tensors alive while it is in use)."""
+    b = _C.BnFused()
+    b.gamma, b.beta = _C.ptr(gamma), _C.ptr(beta)
+    b.eps, b.momentum, b.count = float(eps), float(momentum), float(count)
+    b.stat_sum, b.stat_sqsum, b.counter = _C.ptr(stat_sum), _C.ptr(stat_sqsum), _C.ptr(counter)
+    b.mean_out, b.invstd_out, b.scale_out, b.shift_out = _C.ptr(mean), _C.ptr(invstd), _C.ptr(scale), _C.ptr(shift)
+    b.running_mean, b.running_var = _C.ptr(running_mean), _C.ptr(running_var)
+    b._res_act = act(res) if res is not None else None   # the struct only holds a pointer to it
+    b.res = _C.ctypes.pointer(b._res_act) if res is not None else None
+    b.rscale, b.rshift, b.chanmul = _C.ptr(rscale), _C.ptr(rshift), _C.ptr(chanmul)
+    b.relu, b.res_after_relu = int(relu), int(res_after_relu)
+    return b
+
+
+def conv_bn_train(geom, w_bf16, cout, y, a_out, bn):
+    """conv + train-mode BN (+shortcut, ReLU, dropout mask) in one kernel; y may be None. bn: make_bn_fused(...)."""
+    n_store = (cout + 7) // 8 * 8
+    yo = act(y[..., :n_store]) if y is not None else None
+    _C.check(_C.lib().sseg_conv_bn_train(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, yo, act(a_out[..., :n_store]), bn,
+                                         _stream()))
+    return a_out
+
+
+def conv_bn_train_fits(geom, w_bf16, cout, y, a_out, bn):
+    """True when the layer's tiles fit the tensor memory of one persistent CTA per SM (needs a CUDA device)."""
+    n_store = (cout + 7) // 8 * 8
+    yo = act(y[..., :n_store]) if y is not None else None
+    rc = _C.lib().sseg_conv_bn_train_fits(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, yo, act(a_out[..., :n_store]), bn)
+    if rc < 0:
+        _C.check(rc)
+    return rc == 1
+
+
 def conv_igemm_bnbwd(geom, w_bf16, cout, out, y, fscale, fshift, s1, s2_raw, addend=None):
     """Data gradient into `out` + the producer layer's BN-backward partial sums (see sseg_conv_igemm_bnbwd)."""
     assert out.dtype == torch.bfloat16 and w_bf16.dim() == 2 and w_bf16.stride(1) == 1

@@ -139,6 +139,10 @@ class SegProgram:
         # layers and ALL data-gradient operands are produced on the side stream while the stem / first stages run, and
         # the gradient re-layout of a bucket follows its weight-gradient GEMMs on the side stream instead of the end.
         self.overlap_relayout = _os.environ.get("SSEG_OVERLAP_RELAYOUT", "0") == "1" and part == "full"
+        # conv + train-mode BN (+shortcut, ReLU, dropout) as ONE persistent kernel with an in-kernel grid barrier
+        # (sseg_conv_bn_train) for every layer whose tiles fit the SMs' tensor memory; single-GPU F.batch_norm branch only.
+        # Opt-in until it has run on B200.
+        self.coop_bn = _os.environ.get("SSEG_COOP_BN", "0") == "1"
         self._branch_streams = {}
         self._open_branches = []   # branches forked since the last join (build-time bookkeeping)
 
@@ -224,6 +228,9 @@ class SegProgram:
         for b in self.bns.values():
             b.stats = self.sflat[os_:os_ + 2 * b.C + 1]
             b.stats_off = os_
+            # the padding slot behind [sum | sqsum | count] doubles as the grid-barrier counter of the fused conv+BN kernel
+            # (an all-zero float is an all-zero uint32; the per-step copy from `sinit` re-zeroes it)
+            b.counter = self.sflat[os_ + 2 * b.C + 1:os_ + 2 * b.C + 2] if (2 * b.C + 1) % 4 != 0 else None
             os_ += _pad(2 * b.C + 1, 4)
             b.s2y = self.sflat[os_:os_ + b.Cp]
             os_ += b.Cp
@@ -992,10 +999,13 @@ class ConvBNRec:
         self.mode = P._bn_mode(bns)
         self.count = n * ho * wo
         self.fused = False  # set by the (single) consumer when its dgrad epilogue does this layer's BN-backward reduce
+        self.coop = False   # conv + train-mode BN as one persistent kernel (_try_coop)
         self.folded = (P.fold_bn_eval and self.mode == ops.BN_EVAL and not P.with_grad and chanmul is None and
                        (res is None or isinstance(res, Act) or res.folded))
         if self.folded:
             self._init_folded(n, ho, wo)
+            return
+        if self._try_coop(n, ho, wo):
             return
         self.y = P._new(n, ho, wo, bns.Cp)   # channels >= cw.O are written as zeros by the conv kernel
         st = bns.stats
@@ -1021,6 +1031,55 @@ class ConvBNRec:
         else:
             self.a = None
             _emit_bn_forward(P, bns, self.mode, self.count, y, None, False, None, None, None, None)
+
+    def _try_coop(self, n, ho, wo):
+        """Training, single-GPU BN: conv + statistics + normalise (+shortcut, ReLU, dropout mask) in one launch when the
+        layer fits (sseg_conv_bn_train). Returns False to fall back to conv / finalize / apply."""
+        P, cw, bns = self.P, self.cw, self.bns
+        self.coop = False
+        if not (P.coop_bn and self.mode == ops.BN_TRAIN and self.apply and bns.counter is not None and P.peer is None):
+            return False
+        if isinstance(self.res, ConvBNRec) and getattr(self.res, "coop", False):
+            return False
+        m = bns.mod
+        C = cw.O
+        y = P._new(n, ho, wo, bns.Cp) if P.with_grad else None   # the backward pass reads the raw conv output
+        a = P._new_act(n, ho, wo, C)
+        r = rs = rb = None
+        if isinstance(self.res, Act):
+            r = self.res.tp
+        elif isinstance(self.res, ConvBNRec):
+            r, rs, rb = self.res.y, self.res.bns.scale, self.res.bns.shift
+        if self.post_add is not None:
+            r = self.post_add.tp
+        upd = m.track_running_stats and m.running_mean is not None
+        st = bns.stats
+        bn = ops.make_bn_fused(m.weight.detach() if m.weight is not None else None,
+                               m.bias.detach() if m.bias is not None else None, m.eps,
+                               m.momentum if m.momentum is not None else 0.1, self.count, st[:C], st[C:2 * C], bns.counter,
+                               bns.mean[:C], bns.invstd[:C], bns.scale[:C], bns.shift[:C],
+                               running_mean=m.running_mean if upd else None, running_var=m.running_var if upd else None,
+                               res=r, rscale=rs, rshift=rb, chanmul=self.chanmul, relu=self.relu,
+                               res_after_relu=self.post_add is not None)
+        geom, wf = self.geom, cw.wf
+        if P.dry_run:
+            # no device: same rule as the library (tiles of 128 pixels x 64|128 channels, at most 512 TMEM columns per SM)
+            pix = n * ho * wo if cw.k == 1 else n * math.ceil(ho / max(1, 128 // min(128, 1 << (wo - 1).bit_length()))) * \
+                math.ceil(wo / min(128, 1 << max(3, (wo - 1).bit_length()))) * 128
+            tiles128 = math.ceil(pix / 128) * math.ceil(bns.Cp / 128)
+            bn_cols = 64 if (C <= 64 or tiles128 <= 80) else 128
+            tiles = math.ceil(pix / 128) * math.ceil(bns.Cp / bn_cols)
+            fits = math.ceil(tiles / 148) * bn_cols <= 512
+        else:
+            fits = ops.conv_bn_train_fits(geom, wf, C, y, a.tp, bn)
+        if not fits:
+            return False
+        self.coop, self.y, self.a = True, y, a
+        self.a.producer = self
+        P.keep.append(bn)
+        P._need_weights(cw)
+        P.fwd.append(lambda: ops.conv_bn_train(geom, wf, C, y, a.tp, bn))
+        return True
 
     def _init_folded(self, n, ho, wo):
         """Inference: scale/shift come from the running statistics alone (finalize first), then ONE kernel computes

@@ -177,3 +177,74 @@ def test_folded_eval_bn_inference_matches_the_unfolded_schedule(enc, dec, fc, mo
     err = (a - b).abs().max().item()
     print("folded vs unfolded: argmax agreement %.4f max prob err %.4f" % (agree, err))
     assert agree >= 0.95 and err <= 5e-2   # the folded path rounds once per layer instead of twice
+
+
+@_EXPERIMENTAL
+@pytest.mark.parametrize("k,cin,cout,hw,res,relu", [(1, 256, 128, 64, False, True), (3, 128, 256, 64, True, True),
+                                                     (3, 64, 64, 128, False, True), (1, 512, 2048, 16, True, False),
+                                                     (3, 96, 48, 32, False, True)])
+def test_fused_conv_bn_train_kernel_matches_the_three_kernel_sequence(k, cin, cout, hw, res, relu):
+    """sseg_conv_bn_train (persistent CTAs, accumulators resident in TMEM across an in-kernel grid barrier) against
+    sseg_conv_igemm(stats) + sseg_bn_finalize(train) + sseg_bn_apply on the same operands."""
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 2
+    x = torch.randn(n, hw, hw, cin, device="cuda", generator=g).bfloat16()
+    wt = (torch.randn(cout, cin, k, k, device="cuda", generator=g) * (2.0 / (cin * k * k)) ** 0.5).bfloat16()
+    w2 = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    gamma = torch.rand(cout, device="cuda", generator=g) + 0.5
+    beta = torch.randn(cout, device="cuda", generator=g) * 0.2
+    r = torch.randn(n, hw, hw, cout, device="cuda", generator=g).bfloat16() if res else None
+    mask = (torch.rand(n, cout, device="cuda", generator=g) > 0.2).float() / 0.8
+    geom = ops.make_geom([x], ops.conv_taps(k, 1))
+    count = n * hw * hw
+    # reference sequence
+    y0, a0 = torch.empty(n, hw, hw, cout, device="cuda", dtype=torch.bfloat16), torch.empty(n, hw, hw, cout, device="cuda", dtype=torch.bfloat16)
+    st0 = torch.zeros(2 * cout, device="cuda")
+    v0 = torch.zeros(4, cout, device="cuda")
+    rm0, rv0 = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    ops.conv_igemm(geom, w2, cout, y0, stat_sum=st0[:cout], stat_sqsum=st0[cout:])
+    ops.bn_finalize(st0[:cout], st0[cout:], count, gamma, beta, 1e-5, 0.1, ops.BN_TRAIN, v0[0], v0[1], v0[2], v0[3],
+                    running=(rm0, rv0, None, None, None), update_running=True)
+    ops.bn_apply(y0, v0[2], v0[3], a0, relu=relu, res=r, chanmul=mask)
+    # fused kernel
+    y1, a1 = torch.full_like(y0, float("nan")), torch.full_like(a0, float("nan"))
+    st1 = torch.zeros(2 * cout + 4, device="cuda")
+    v1 = torch.zeros(4, cout, device="cuda")
+    rm1, rv1 = torch.zeros(cout, device="cuda"), torch.ones(cout, device="cuda")
+    bn = ops.make_bn_fused(gamma, beta, 1e-5, 0.1, count, st1[:cout], st1[cout:2 * cout], st1[2 * cout:2 * cout + 1], v1[0], v1[1],
+                           v1[2], v1[3], running_mean=rm1, running_var=rv1, res=r, chanmul=mask, relu=relu)
+    assert ops.conv_bn_train_fits(geom, w2, cout, y1, a1, bn)
+    ops.conv_bn_train(geom, w2, cout, y1, a1, bn)
+    torch.cuda.synchronize()
+    assert torch.equal(y1, y0)                                   # same accumulators, same rounding
+    assert torch.allclose(st1[:2 * cout], st0, rtol=1e-4, atol=1e-2)
+    assert torch.allclose(v1, v0, rtol=1e-4, atol=1e-5) and torch.allclose(rm1, rm0, atol=1e-6) and torch.allclose(rv1, rv0, rtol=1e-4)
+    assert (a1.float() - a0.float()).abs().max().item() <= 2 ** -7 * a0.float().abs().max().item()
+    assert (a1 != a0).float().mean().item() < 1e-2               # differences only where a last-bit scale difference flips a rounding
+
+
+@_EXPERIMENTAL
+def test_fused_conv_bn_train_schedule_matches_the_default_step(monkeypatch):
+    """SSEG_COOP_BN=1 on a train-mode step (ResNet18dilated + C1_deepsup: no tiny-batch BN): same loss, features, running
+    statistics and gradient direction as the three-kernel BN forward."""
+    from mit_semseg.engine.program import ConvBNRec, SegProgram
+    from oracle import segnet_oracle as O
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("SSEG_COOP_BN", flag)
+        seg, esd, dsd, ds = _build("resnet18dilated", "c1_deepsup", 512, residual_gain=0.25)
+        seg.cuda().train()
+        feed = O.synth_batch(4, 128, 128, 8, 3)
+        prog = SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True)
+        if flag == "1":
+            assert sum(getattr(r, "coop", False) for r in prog.records if isinstance(r, ConvBNRec)) >= 15
+        prog.load_inputs(feed["img_data"].cuda(), feed["seg_label"].cuda())
+        prog.run_eager()
+        torch.cuda.synchronize()
+        grads = torch.cat([g.flatten().float() for g in prog.param_grads().values()])
+        res[flag] = (prog.out.clone(), prog.feats[-1].t.float().clone(), seg.encoder.layer3[0].bn1.running_mean.clone(), grads)
+    (o0, f0, r0, g0), (o1, f1, r1, g1) = res["0"], res["1"]
+    assert abs(o0[0].item() - o1[0].item()) <= 2e-3 * abs(o0[0].item())
+    assert _rel(f1, f0) <= 3e-2 and torch.allclose(r1, r0, atol=1e-5)
+    assert torch.dot(g0, g1).item() / (g0.norm() * g1.norm()).item() >= 0.98

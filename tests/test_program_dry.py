@@ -158,3 +158,27 @@ def test_overlapped_relayout_schedule(monkeypatch):
     assert len(P.fwd) == len(Q.fwd) + 2      # side-stream prep + one wait
     assert len(P.bwd) == len(Q.bwd) + 3      # join for the dgrad operands, 2 bucket closes + rest instead of one re-layout
     assert set(P.param_grads()) == set(Q.param_grads())
+
+
+def test_fused_conv_bn_schedule(monkeypatch):
+    """SSEG_COOP_BN=1 (opt-in): single-GPU train-mode layers whose tiles fit the SMs' tensor memory run conv + statistics +
+    normalise + shortcut + ReLU as ONE launch; projection shortcuts, the 256x256 stem conv3 and layer4's 2048-channel
+    convolutions keep the three-kernel sequence. The backward schedule is unchanged."""
+    from mit_semseg.engine import program as PR
+    seg = _seg("resnet50dilated", "ppm_deepsup", 2048)
+    seg.train()
+    Q = PR.SegProgram(seg, (2, 3, 512, 512), training=True, with_grad=True, dry_run=True)
+    monkeypatch.setenv("SSEG_COOP_BN", "1")
+    P = PR.SegProgram(seg, (2, 3, 512, 512), training=True, with_grad=True, dry_run=True)
+    recs = [r for r in P.records if isinstance(r, PR.ConvBNRec)]
+    coop = [r for r in recs if r.coop]
+    assert len(recs) == 60 and len(coop) == 52
+    assert all(r.apply and r.y is not None for r in coop)           # y is kept: the backward pass reads it
+    assert not any(r.coop for r in recs if r.cw.O == 2048)
+    assert len(Q.fwd) - len(P.fwd) == 2 * len(coop) and len(Q.bwd) == len(P.bwd)
+    # every BN of a fused layer has a barrier counter slot that the per-step statistics reset zeroes
+    assert all(r.bns.counter is not None and r.bns.counter.numel() == 1 for r in coop)
+    # frozen BN (eval) and inference never take the fused training kernel
+    seg.eval()
+    R = PR.SegProgram(seg, (1, 3, 64, 64), training=False, with_grad=False, seg_size=(64, 64), dry_run=True)
+    assert not any(getattr(r, "coop", False) for r in R.records if isinstance(r, PR.ConvBNRec))

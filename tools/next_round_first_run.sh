@@ -9,7 +9,7 @@ SSEG_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_widen_hrnet
 grep -E "passed|failed" gpurun_out/experimental_tests.log | tail -2
 grep -E "^FAILED|^ERROR|^E  " gpurun_out/experimental_tests.log | head -30
 echo "== training step, CUDA-graph replay"
-for sw in "" "SSEG_BRANCH_STREAMS=1" "SSEG_OVERLAP_RELAYOUT=1" "SSEG_BRANCH_STREAMS=1 SSEG_OVERLAP_RELAYOUT=1"; do
+for sw in "" "SSEG_BRANCH_STREAMS=1" "SSEG_OVERLAP_RELAYOUT=1" "SSEG_COOP_BN=1" "SSEG_BRANCH_STREAMS=1 SSEG_OVERLAP_RELAYOUT=1 SSEG_COOP_BN=1"; do
   echo "[$sw]"; env $sw timeout 120 python tools/step_breakdown.py --replay-only 2>&1 | tail -1
 done
 echo "== HRNetV2+C1 training step"
