@@ -719,7 +719,8 @@ class SegProgram:
         return run
 
     def join_side(self):
-        torch.cuda.current_stream(self.dev).wait_stream(self.side)
+        if not getattr(self, "serial", False):
+            torch.cuda.current_stream(self.dev).wait_stream(self.side)
 
     # ---- branch streams (fork / run / join closures; all no-ops with prog.serial, like the side stream)
     def _bstream(self, k):
