@@ -101,6 +101,34 @@ def _worker(rank, world, port, ret):
         got = EF.multiscale_inference(FakeSeg(), imgs, (6, 7), _run_scale=fake_scale)
         ref = sum(torch.sigmoid(im.mean()) for im in imgs) / 5 * torch.ones(1, 3, 6, 7)
         assert got.shape == (1, 3, 6, 7) and torch.allclose(got, ref, atol=1e-6)
+        # ---- the data-parallel training schedule itself, kernels replaced by argument-checking no-ops
+        #      (tests/test_program_null_run.py): every collective of the step really runs, over gloo - SyncBN statistics
+        #      (forward + backward), the three gradient buckets, with and without the side-stream re-layout
+        import torch.nn as nn
+        from mit_semseg.engine import _C, ops, program as PR
+        from test_program_dry import _seg
+        from test_program_null_run import _NullLib
+        lib = _NullLib(_C._SIGNATURES)
+        _C.lib = lambda: lib
+        ops._stream = lambda: None
+        os.environ["SSEG_PEER_SYNC"] = "0"          # the peer arena needs CUDA IPC; this is the NCCL-collective schedule
+        torch.manual_seed(0)
+        seg = _seg("resnet18dilated", "ppm_deepsup", 512)
+        seg.train()
+        for overlap in ("0", "1"):
+            os.environ["SSEG_OVERLAP_RELAYOUT"] = overlap
+            P = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+            assert P.world == 2 and P.peer is None
+            assert all(r.mode == ops.BN_TRAIN_SYNC for r in P.records if isinstance(r, PR.ConvBNRec))
+            P.load_inputs(torch.randn(2, 3, 64, 64), torch.randint(-1, 150, (2, 8, 8)))
+            P.dry_run, P.serial = False, True
+            P.gflat.fill_(float(rank + 1))           # stands in for this rank's weight gradients
+            P.bwd = P.bwd[1:]                        # (skip the memset of the gradient buffer for this check)
+            P.run_eager()
+            # every slice of the flat gradient buffer went through exactly one all-reduce: 1 + 2 = 3 on both ranks
+            nsmall = P.g_small
+            assert torch.all(P.gflat[nsmall:] == 3.0), "conv gradient buckets must be summed over the ranks exactly once"
+        os.environ.pop("SSEG_OVERLAP_RELAYOUT")
         ret[rank] = True
     finally:
         dist.destroy_process_group()
