@@ -562,20 +562,24 @@ class SegProgram:
             return xs
         outs = []
         for i, row in enumerate(module.fuse_layers):
-            terms = []
-            for j in range(nb):
-                if j == i:
-                    terms.append(("id", xs[j]))
-                elif j > i:   # 1x1 conv + BN at the low resolution; the up-sampling happens inside the sum kernel
-                    terms.append(("up", self.conv_bn(xs[j], row[j][0], row[j][1], relu=False, apply=False)))
-                else:         # chain of stride-2 3x3 convs, ReLU between the links only
-                    t, links = xs[j], list(row[j])
-                    for link in links[:-1]:
-                        t = self.conv_bn(t, link[0], link[1])
-                    terms.append(("same", self.conv_bn(t, links[-1][0], links[-1][1], relu=False, apply=False)))
-            sr = SumRec(self, terms)
-            self.records.append(sr)
+            # the rows of an exchange unit only READ the branch outputs: independent in the forward pass. Their backward
+            # passes accumulate into the same branch gradients, so they stay in order on the main stream.
+            with self.branch(i, backward=False):
+                terms = []
+                for j in range(nb):
+                    if j == i:
+                        terms.append(("id", xs[j]))
+                    elif j > i:   # 1x1 conv + BN at the low resolution; the up-sampling happens inside the sum kernel
+                        terms.append(("up", self.conv_bn(xs[j], row[j][0], row[j][1], relu=False, apply=False)))
+                    else:         # chain of stride-2 3x3 convs, ReLU between the links only
+                        t, links = xs[j], list(row[j])
+                        for link in links[:-1]:
+                            t = self.conv_bn(t, link[0], link[1])
+                        terms.append(("same", self.conv_bn(t, links[-1][0], links[-1][1], relu=False, apply=False)))
+                sr = SumRec(self, terms)
+                self.records.append(sr)
             outs.append(sr.a)
+        self.join_branches()
         return outs
 
     def _build_encoder(self, R):
@@ -752,9 +756,11 @@ class SegProgram:
                 torch.cuda.current_stream(self.dev).wait_stream(self._bstream(k))
         return run
 
-    def branch(self, k):
+    def branch(self, k, backward=True):
         """Context manager for the FORWARD schedule: closures and records created inside run on branch stream k
-        (forked from the main stream at the point of entry). Call join_branches() before anything consumes them."""
+        (forked from the main stream at the point of entry). Call join_branches() before anything consumes them.
+        backward=False: only the forward closures branch; the records' backward closures stay on the main stream (needed
+        when different branches ACCUMULATE into the same gradient buffers)."""
         P = self
 
         class _Scope:
@@ -769,8 +775,9 @@ class SegProgram:
                     P.fwd[self_.f0:] = [P._fork(k)] + [P._on_branch(k, f) for f in seg]
                     if k not in P._open_branches:
                         P._open_branches.append(k)
-                for r in P.records[self_.r0:]:
-                    r.branch = k
+                if backward:
+                    for r in P.records[self_.r0:]:
+                        r.branch = k
                 return False
         return _Scope()
 

@@ -114,10 +114,11 @@ def test_branch_streams_fork_and_join_symmetrically(enc, dec, fc, nfork_fwd, mon
     seg.train()
     P = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
     assert not P._open_branches
-    assert counts["fork"] == counts["join"] == 2 * nfork_fwd, counts   # forward + backward
+    nrows = 26 if enc == "hrnetv2" else 0    # exchange-unit rows branch in the forward schedule only
+    assert counts["fork"] == counts["join"] == 2 * nfork_fwd + nrows, counts   # forward + backward
     monkeypatch.setenv("SSEG_BRANCH_STREAMS", "0")
     Q = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
-    assert len(P.fwd) == len(Q.fwd) + 2 * nfork_fwd and len(P.bwd) == len(Q.bwd) + 2 * nfork_fwd
+    assert len(P.fwd) == len(Q.fwd) + 2 * (nfork_fwd + nrows) and len(P.bwd) == len(Q.bwd) + 2 * nfork_fwd
 
 
 def test_folded_eval_bn_inference_schedule(monkeypatch):
