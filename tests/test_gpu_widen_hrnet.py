@@ -182,7 +182,8 @@ def test_folded_eval_bn_inference_matches_the_unfolded_schedule(enc, dec, fc, mo
 @_EXPERIMENTAL
 @pytest.mark.parametrize("k,cin,cout,hw,res,relu", [(1, 256, 128, 64, False, True), (3, 128, 256, 64, True, True),
                                                      (3, 64, 64, 128, False, True), (1, 512, 2048, 16, True, False),
-                                                     (3, 96, 48, 32, False, True)])
+                                                     (3, 96, 48, 32, False, True),
+                                                     (3, 64, 64, 256, True, True)])   # 1024 tiles: 7 accumulators per CTA
 def test_fused_conv_bn_train_kernel_matches_the_three_kernel_sequence(k, cin, cout, hw, res, relu):
     """sseg_conv_bn_train (persistent CTAs, accumulators resident in TMEM across an in-kernel grid barrier) against
     sseg_conv_igemm(stats) + sseg_bn_finalize(train) + sseg_bn_apply on the same operands."""
