@@ -1,15 +1,30 @@
 #!/bin/bash
-# First GPU call of the next round (run under gpurun from the repo root, ~6 GPU-minutes):
+# First GPU call of the next round (run under gpurun from the repo root, ~7 GPU-minutes):
 # everything that was written after this round's GPU budget was spent gets its first run, then each opt-in switch is
 # timed against the default schedule so the defaults can be flipped on evidence.
 mkdir -p gpurun_out
-echo "== gated tests"
-SSEG_TEST_EXPERIMENTAL=1 timeout 400 python -m pytest tests/test_gpu_widen_hrnet.py -m gpu -q -p no:cacheprovider -s \
-  > gpurun_out/experimental_tests.log 2>&1
+export SSEG_TEST_EXPERIMENTAL=1
+PYT="python -m pytest tests/test_gpu_widen_hrnet.py -m gpu -q -p no:cacheprovider -s"
+
+echo "== fused conv+BN kernel (in-kernel grid barrier): alone first, short timeout - a hang here must not take the rest down"
+timeout 90 $PYT -k "fused_conv_bn_train_kernel" > gpurun_out/experimental_coop_kernel.log 2>&1
+COOP_RC=$?
+grep -E "passed|failed" gpurun_out/experimental_coop_kernel.log | tail -1
+grep -E "^FAILED|^ERROR|^E  " gpurun_out/experimental_coop_kernel.log | head -10
+if [ $COOP_RC -eq 0 ]; then COOP_OK=1; else COOP_OK=0; echo "fused conv+BN kernel NOT ok (rc=$COOP_RC): skipping everything that uses it"; fi
+nvidia-smi --query-gpu=name,memory.used --format=csv,noheader    # the GPU must still answer
+
+echo "== remaining gated tests"
+if [ $COOP_OK -eq 1 ]; then SEL="not fused_conv_bn_train_kernel"; else SEL="not fused_conv_bn"; fi
+timeout 400 $PYT -k "$SEL" > gpurun_out/experimental_tests.log 2>&1
 grep -E "passed|failed" gpurun_out/experimental_tests.log | tail -2
 grep -E "^FAILED|^ERROR|^E  " gpurun_out/experimental_tests.log | head -30
+grep -E "folded vs unfolded" gpurun_out/experimental_tests.log
+
 echo "== training step, CUDA-graph replay"
-for sw in "" "SSEG_BRANCH_STREAMS=1" "SSEG_OVERLAP_RELAYOUT=1" "SSEG_COOP_BN=1" "SSEG_BRANCH_STREAMS=1 SSEG_OVERLAP_RELAYOUT=1 SSEG_COOP_BN=1"; do
+SWS=("" "SSEG_BRANCH_STREAMS=1" "SSEG_OVERLAP_RELAYOUT=1" "SSEG_BRANCH_STREAMS=1 SSEG_OVERLAP_RELAYOUT=1")
+if [ $COOP_OK -eq 1 ]; then SWS+=("SSEG_COOP_BN=1" "SSEG_BRANCH_STREAMS=1 SSEG_OVERLAP_RELAYOUT=1 SSEG_COOP_BN=1"); fi
+for sw in "${SWS[@]}"; do
   echo "[$sw]"; env $sw timeout 120 python tools/step_breakdown.py --replay-only 2>&1 | tail -1
 done
 echo "== HRNetV2+C1 training step"
