@@ -143,6 +143,27 @@ int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_bf16, long 
                             const sseg_act_t* a_out, const sseg_bn_fused_t* bn);
 
 /*
+ * Backward twin of sseg_conv_bn_train: the data gradient of the CONSUMER convolution and the complete BatchNorm backward
+ * of the PRODUCER layer (train-mode statistics, single GPU) in one persistent kernel - the gradient with respect to the
+ * producer's activation stays in tensor memory across the grid barrier and only dy (the gradient with respect to the
+ * producer's convolution output) is written. Replaces sseg_conv_igemm_bnbwd + sseg_bn_bwd_apply; same restrictions as
+ * sseg_conv_igemm_bnbwd (producer has one consumer, ReLU, no shortcut / dropout mask), same fit rule as
+ * sseg_conv_bn_train (sseg_conv_dgrad_bn_fits). autograd of models/resnet.py:37-43,72-82 + lib/nn/modules/batchnorm.py:58-61.
+ *   g, w_bf16, cout : as for sseg_conv_igemm with the transposed / tap-mirrored weight (cout = the producer's channels)
+ *   y        : the producer's saved convolution output; fscale / fshift its forward scale / shift (ReLU mask)
+ *   mean, invstd, count : the producer's batch statistics;  s1 (= dbeta), s2_raw : float[cout], zeroed by the caller
+ *   dgamma_out : float[cout] or NULL;  counter : one zeroed uint32;  dy_out : bf16, shape of y
+ */
+int sseg_conv_dgrad_bn(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                       const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
+                       const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,
+                       unsigned int* counter, sseg_stream_t stream);
+int sseg_conv_dgrad_bn_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                            const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
+                            const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,
+                            unsigned int* counter);
+
+/*
  * Convolution with the inference-time epilogue fused: out = relu?( conv(x) * scale[co] + shift[co] (+ addend) ).
  * BatchNorm with running statistics is a per-channel affine (F.batch_norm eval branch, lib/nn/modules/batchnorm.py:
  * 58-61), so conv -> BN -> (+shortcut) -> ReLU (models/resnet.py:37-53,72-92; models/models.py:160-167) is ONE kernel

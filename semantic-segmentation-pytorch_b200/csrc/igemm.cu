@@ -1027,6 +1027,335 @@ static int launch_bn(const IgemmBnParams& q, int grid, cudaStream_t stream) {
                     "igemm_bn_kernel launch");
 }
 
+// Backward twin: the data-gradient GEMM of the CONSUMER layer + the whole BatchNorm backward of the PRODUCER layer.
+//   phase 1  g = conv^T(dy_next) per tile (kept in TMEM) -> partial sums  s1 += g', s2raw += g'*y  (g' = g * ReLU mask
+//            recomputed from the producer's saved conv output y)
+//   barrier
+//   phase 2  dy = ka*g' + kb*y + kc per channel from the complete sums (bn_bwd_apply's formula) -> only dy is written.
+// Replaces sseg_conv_igemm_bnbwd + sseg_bn_bwd_apply for producers with a single consumer and no shortcut.
+struct IgemmDgradBnParams {
+  IgemmParams g;  // operands / geometry of the data gradient; g.bw_* = producer's y, forward scale / shift, sum slots
+  __nv_bfloat16* dy_out;
+  int ld_dy;
+  long dy_row_stride, dy_img_stride;
+  const float* mean;
+  const float* invstd;
+  float count;
+  float* dgamma_out;
+  unsigned int* counter;
+  int num_tiles, tiles_per_cta;
+};
+
+template <int BLOCK_N, int STAGES>
+struct IgemmDgradBnSmem {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPitch = BLOCK_N * 2 + 16;
+  static constexpr int kTileBytes = ((128 * kPitch + 1023) / 1024) * 1024;
+  static constexpr int kStgOff = STAGES * kStageBytes;
+  static constexpr int kYOff = kStgOff + kTileBytes;
+  static constexpr int kCoefOff = kYOff + kTileBytes;
+  static constexpr int kBarOff = kCoefOff + 4 * BLOCK_N * 4;
+  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kDynBytes = kTotal + 1024;
+  static constexpr int kMaxTiles = 512 / BLOCK_N;
+};
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __grid_constant__ IgemmDgradBnParams q) {
+  using L = IgemmDgradBnSmem<BLOCK_N, STAGES>;
+  const IgemmParams& p = q.g;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;  // [kMaxTiles]: accumulator i is complete
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + L::kMaxTiles);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_k_steps = p.num_k_steps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < L::kMaxTiles; ++b) mbar_init(&tmem_full_bar[b], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_ptr_smem);  // every accumulator of this CTA stays resident until phase 2
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();
+
+  if (warp == 0) {
+    // ===================== TMA producer: runs ahead across tile boundaries =====================
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const int tw = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int th = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
+        for (int t = 0; t < p.ntaps; ++t) {
+          const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
+          const int fixed_src = p.tap_src[t];
+          const int nblk = fixed_src >= 0 ? p.src_blk_end[0] : p.blocks_per_tap;
+          int src = fixed_src >= 0 ? fixed_src : 0, blk_begin = 0;
+          for (int b = 0; b < nblk; ++b) {
+            if (fixed_src < 0) {
+              while (b >= p.src_blk_end[src]) {
+                blk_begin = p.src_blk_end[src];
+                ++src;
+              }
+            }
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+            tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
+            const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+            tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
+            if (++stage == STAGES) stage = 0, phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: accumulator i lives at TMEM columns [i*BLOCK_N, +BLOCK_N) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, kBlockM, BLOCK_N);
+      int stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, ++it) {
+        const uint32_t d_tmem = tmem_base + it * BLOCK_N;
+        for (int ks = 0; ks < num_k_steps; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (ks | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+        umma_commit(&tmem_full_bar[it]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue warps: phase 1, grid barrier, phase 2 =====================
+    const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int row = quarter * 32 + lane;
+    const int t = threadIdx.x - 64;  // 0..127
+    constexpr int kPitch = L::kPitch;
+    uint8_t* stg = smem + L::kStgOff;
+    uint8_t* ytile = smem + L::kYOff;                              // the producer layer's saved conv output, same tile
+    float* coef = reinterpret_cast<float*>(smem + L::kCoefOff);  // [ka | kb | kc | fshift][BLOCK_N]: dy = ka*g' + kb*y + kc
+    constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
+    const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+
+    for (int phase2 = 0; phase2 < 2; ++phase2) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, ++it) {
+        const int n_tile = tile % p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        const bool first_m_tile = m_tile == 0;
+        const int tw = m_tile % p.tiles_w;
+        m_tile /= p.tiles_w;
+        const int th = m_tile % p.tiles_h;
+        const int img = m_tile / p.tiles_h;
+        const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + it * BLOCK_N;
+        const int hh = h0 + (row >> p.bw_shift), ww = w0 + (row & (p.BW - 1));
+        const bool valid = (hh < p.H) && (ww < p.W);
+
+        if (phase2) {
+          // per-channel coefficients of this tile's channel block from the complete statistics
+          if (t < BLOCK_N) {
+            const int c = n0 + t;
+            float ka = 0.f, kb = 0.f, kc = 0.f, fb = -1.f;
+            if (c < p.cout) {
+              // totals of the whole layer: s1 = sum g', s2 = inv_std * (sum g'*y - mean * s1) = sum g'*xhat
+              const float s1 = __ldcg(p.bw_s1 + c), s2raw = __ldcg(p.bw_s2 + c);
+              const float mu = q.mean[c], inv = q.invstd[c], fs = p.bw_fscale[c];
+              const float s2 = inv * (s2raw - mu * s1);
+              const float inv_m = 1.f / q.count;
+              const float tt = fs * inv * s2 * inv_m;
+              ka = fs, kb = -tt, kc = tt * mu - fs * s1 * inv_m, fb = p.bw_fshift[c];
+              if (first_m_tile && q.dgamma_out != nullptr) q.dgamma_out[c] = s2;   // dbeta = s1 is already in place
+            }
+            coef[t] = ka, coef[BLOCK_N + t] = kb, coef[2 * BLOCK_N + t] = kc, coef[3 * BLOCK_N + t] = fb;
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          tc_fence_after();
+        } else {
+          mbar_wait(&tmem_full_bar[it], 0);
+          tc_fence_after();
+        }
+
+        const long pix_off_y = img * p.bw_img_stride + hh * p.bw_row_stride + static_cast<long>(ww) * p.bw_ld;
+#pragma unroll 1
+        for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+          uint32_t raw[32];
+          tmem_ld_32x32(d_tmem + (static_cast<uint32_t>(quarter * 32) << 16) + chunk * 32, raw);
+          tmem_ld_wait();
+          float v[32];
+          const int col0 = n0 + chunk * 32;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)  // y as stored: one bf16 rounding of the fp32 accumulator
+            v[j] = __bfloat162float(__float2bfloat16_rn(__uint_as_float(raw[j])));
+          if (phase2) {
+            // dy = ka*g' + kb*y + kc with g' = g * [y*fscale + fshift > 0]; y is read row-wise (this thread's pixel)
+            const float* kf = coef + chunk * 32;
+            float yv[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) yv[j] = 0.f;
+            if (valid) {
+              const __nv_bfloat16* yp = p.bw_y + pix_off_y + col0;
+#pragma unroll
+              for (int g8 = 0; g8 < 4; ++g8) {
+                if (col0 + g8 * 8 < p.cout) {
+                  const uint4 u = __ldg(reinterpret_cast<const uint4*>(yp + g8 * 8));
+                  const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+                  for (int e = 0; e < 4; ++e) {
+                    const float2 f = __bfloat1622float2(h2[e]);
+                    yv[g8 * 8 + 2 * e] = f.x, yv[g8 * 8 + 2 * e + 1] = f.y;
+                  }
+                }
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float gm = fmaf(yv[j], kf[j], kf[3 * BLOCK_N + j]) > 0.f ? v[j] : 0.f;
+              v[j] = fmaf(kf[j], gm, fmaf(kf[BLOCK_N + j], yv[j], kf[2 * BLOCK_N + j]));
+            }
+          }
+          uint8_t* sp = stg + row * kPitch + chunk * 64;
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);  // rows outside the image contribute zeros to the statistics
+            if (valid) {
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(v[g8 * 8 + 2 * e], v[g8 * 8 + 2 * e + 1]);
+            }
+            *reinterpret_cast<uint4*>(sp + g8 * 16) = u;
+          }
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the staged tile is complete
+
+        if (!phase2) {
+          // the producer's saved conv output y, same tile geometry, copied with coalesced 16-byte loads
+          {
+            constexpr int kPasses = 128 / kRowsPerPass;
+            uint4 u[kPasses];
+#pragma unroll
+            for (int pass = 0; pass < kPasses; ++pass) {
+              const int r = pass * kRowsPerPass + r0;
+              const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+              u[pass] = make_uint4(0u, 0u, 0u, 0u);
+              if (rh < p.H && rw < p.W && n0 + seg * 8 < p.cout)
+                u[pass] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
+                                                               static_cast<size_t>(rw) * p.bw_ld + n0 + seg * 8));
+            }
+#pragma unroll
+            for (int pass = 0; pass < kPasses; ++pass)
+              *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = u[pass];
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
+          const int cp = t % kPairs, slab = t / kPairs;
+          const int col = n0 + cp * 2;
+          if (col < p.cout) {
+            const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
+            const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+            const uint8_t* gbase = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+            const uint8_t* ybase = ytile + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll 8
+            for (int r = 0; r < kRowsPerSlab; ++r) {
+              const float2 gg = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
+              const float2 yy = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
+              const float g0 = fmaf(yy.x, fs0, fb0) > 0.f ? gg.x : 0.f;
+              const float g1 = fmaf(yy.y, fs1, fb1) > 0.f ? gg.y : 0.f;
+              a0 += g0, a1 += g1;
+              b0 = fmaf(g0, yy.x, b0), b1 = fmaf(g1, yy.y, b1);
+            }
+            atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
+            if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
+          }
+        }
+        // coalesced store of the staged tile: nothing in phase 1 (the gradient g itself never reaches HBM), dy in phase 2
+        __nv_bfloat16* dst = phase2 ? q.dy_out : nullptr;
+        if (dst != nullptr && n0 + seg * 8 < p.n_store) {
+          const long istr = q.dy_img_stride, rstr = q.dy_row_stride;
+          const long ld = q.ld_dy;
+#pragma unroll 4
+          for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
+            const int r = pass * kRowsPerPass + r0;
+            const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+            if (rh < p.H && rw < p.W) {
+              const uint4 u = *reinterpret_cast<const uint4*>(stg + r * kPitch + seg * 16);
+              *reinterpret_cast<uint4*>(dst + img * istr + rh * rstr + static_cast<long>(rw) * ld + n0 + seg * 8) = u;
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile (and coefficients) free for the next tile
+      }
+      if (!phase2) {
+        // ---- grid barrier: the layer's statistics are complete once every CTA has arrived
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (t == 0) {
+          atomicAdd(q.counter, 1u);
+          while (ld_acquire_gpu(q.counter) < gridDim.x) {
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int BLOCK_N, int STAGES>
+static int launch_dgrad_bn(const IgemmDgradBnParams& q, int grid, cudaStream_t stream) {
+  using L = IgemmDgradBnSmem<BLOCK_N, STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  SSEG_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    SSEG_CUDA(cudaFuncSetAttribute(igemm_dgrad_bn_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   L::kDynBytes));
+    configured[dev] = true;
+  }
+  count_launch(1);
+  return check_cuda(launch_coop(igemm_dgrad_bn_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream,
+                                q),
+                    "igemm_dgrad_bn_kernel launch");
+}
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
@@ -1312,6 +1641,54 @@ extern "C" int sseg_conv_bn_train(const sseg_conv_geom_t* g, const void* w_bf16,
 extern "C" int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
                                        const sseg_act_t* y, const sseg_act_t* a_out, const sseg_bn_fused_t* bn) {
   return conv_bn_train_impl(g, w_bf16, w_ld, cout, y, a_out, bn, 1, nullptr);
+}
+
+static int conv_dgrad_bn_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                              const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
+                              const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,
+                              unsigned int* counter, int query_only, sseg_stream_t stream_) {
+  SSEG_REQUIRE(y != nullptr && dy_out != nullptr && fscale && fshift && mean && invstd && s1 && s2_raw && counter &&
+                   count > 1.f,
+               "sseg_conv_dgrad_bn: null argument");
+  IgemmDgradBnParams q;
+  memset(&q, 0, sizeof(q));
+  int block_n = 0;
+  // geometry / operand / fused-reduction set-up is sseg_conv_igemm_bnbwd's, with dy_out standing in for the (never
+  // written) gradient tensor in the shape checks
+  const int tiles = conv_igemm_impl(g, w_bf16, w_ld, cout, dy_out, 0, nullptr, nullptr, nullptr, nullptr, y, fscale, fshift, s1,
+                                    s2_raw, stream_, nullptr, &q.g, &block_n);
+  if (tiles < 0) return tiles;
+  q.g.out = nullptr;
+  int sms = 0;
+  int rc = num_sms_of_current_device(&sms);
+  if (rc) return rc;
+  const int per_cta = ceil_div(tiles, sms);
+  if (query_only) return per_cta <= 512 / block_n ? 1 : 0;
+  SSEG_REQUIRE(per_cta <= 512 / block_n, "sseg_conv_dgrad_bn: %d tiles do not fit the tensor memory of %d SMs", tiles, sms);
+  q.dy_out = static_cast<__nv_bfloat16*>(dy_out->ptr);
+  q.ld_dy = dy_out->ld, q.dy_row_stride = dy_out->row_stride, q.dy_img_stride = dy_out->img_stride;
+  q.mean = mean, q.invstd = invstd, q.count = count, q.dgamma_out = dgamma_out, q.counter = counter;
+  q.num_tiles = tiles, q.tiles_per_cta = per_cta;
+  const int grid = ceil_div(tiles, per_cta);
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (block_n == 64) return launch_dgrad_bn<64, 6>(q, grid, stream);
+  return launch_dgrad_bn<128, 4>(q, grid, stream);
+}
+
+extern "C" int sseg_conv_dgrad_bn(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
+                                  const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
+                                  const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,
+                                  unsigned int* counter, sseg_stream_t stream) {
+  return conv_dgrad_bn_impl(g, w_bf16, w_ld, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2_raw, dgamma_out,
+                            counter, 0, stream);
+}
+
+extern "C" int sseg_conv_dgrad_bn_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                                       const sseg_act_t* y, const sseg_act_t* dy_out, const float* fscale,
+                                       const float* fshift, const float* mean, const float* invstd, float count, float* s1,
+                                       float* s2_raw, float* dgamma_out, unsigned int* counter) {
+  return conv_dgrad_bn_impl(g, w_bf16, w_ld, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2_raw, dgamma_out,
+                            counter, 1, nullptr);
 }
 
 // =====================================================================================================

@@ -113,6 +113,22 @@ def conv_bn_train_fits(geom, w_bf16, cout, y, a_out, bn):
     return rc == 1
 
 
+def conv_dgrad_bn(geom, w_bf16, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2_raw, dgamma_out, counter,
+                  query=False):
+    """Data gradient of the consumer conv + the producer layer's whole BN backward in one kernel: only dy_out is written.
+    query=True: returns whether the layer fits (no launch)."""
+    n_store = (cout + 7) // 8 * 8
+    args = (geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, act(y), act(dy_out[..., :n_store]), _C.ptr(fscale), _C.ptr(fshift),
+            _C.ptr(mean), _C.ptr(invstd), float(count), _C.ptr(s1), _C.ptr(s2_raw), _C.ptr(dgamma_out), _C.ptr(counter))
+    if query:
+        rc = _C.lib().sseg_conv_dgrad_bn_fits(*args)
+        if rc < 0:
+            _C.check(rc)
+        return rc == 1
+    _C.check(_C.lib().sseg_conv_dgrad_bn(*args, _stream()))
+    return dy_out
+
+
 def conv_igemm_bnbwd(geom, w_bf16, cout, out, y, fscale, fshift, s1, s2_raw, addend=None):
     """Data gradient into `out` + the producer layer's BN-backward partial sums (see sseg_conv_igemm_bnbwd)."""
     assert out.dtype == torch.bfloat16 and w_bf16.dim() == 2 and w_bf16.stride(1) == 1

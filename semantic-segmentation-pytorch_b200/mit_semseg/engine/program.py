@@ -38,6 +38,19 @@ def _dist():
     return None
 
 
+def _coop_fits_estimate(n, h, w, k, channels):
+    """CPU-side stand-in for sseg_conv_bn_train_fits / sseg_conv_dgrad_bn_fits (dry-run schedules only): tiles of 128 pixels
+    x 64|128 channels, one persistent CTA per SM (148), at most 512 tensor-memory columns per CTA."""
+    if k == 1:
+        m_tiles = math.ceil(n * h * w / 128)
+    else:
+        bw = min(128, 1 << max(3, (w - 1).bit_length()))
+        m_tiles = n * math.ceil(h / (128 // bw)) * math.ceil(w / bw)
+    cp = _pad(channels, 8)
+    cols = 64 if (channels <= 64 or m_tiles * math.ceil(cp / 128) <= 80) else 128
+    return math.ceil(m_tiles * math.ceil(cp / cols) / 148) * cols <= 512
+
+
 class Act:
     """An activation tensor (NHWC bf16) plus, during backward construction, its gradient buffer."""
     __slots__ = ("t", "tp", "g", "gw", "uses", "producer")
@@ -231,6 +244,7 @@ class SegProgram:
             # the padding slot behind [sum | sqsum | count] doubles as the grid-barrier counter of the fused conv+BN kernel
             # (an all-zero float is an all-zero uint32; the per-step copy from `sinit` re-zeroes it)
             b.counter = self.sflat[os_ + 2 * b.C + 1:os_ + 2 * b.C + 2] if (2 * b.C + 1) % 4 != 0 else None
+            b.counter_bwd = self.sflat[os_ + 2 * b.C + 2:os_ + 2 * b.C + 3] if (2 * b.C + 1) % 4 == 1 else None
             os_ += _pad(2 * b.C + 1, 4)
             b.s2y = self.sflat[os_:os_ + b.Cp]
             os_ += b.Cp
@@ -1008,6 +1022,7 @@ class ConvBNRec:
         self.count = n * ho * wo
         self.fused = False  # set by the (single) consumer when its dgrad epilogue does this layer's BN-backward reduce
         self.coop = False   # conv + train-mode BN as one persistent kernel (_try_coop)
+        self.dy_pre = None  # set when the consumer's data-gradient kernel already produced this layer's dy
         self.folded = (P.fold_bn_eval and self.mode == ops.BN_EVAL and not P.with_grad and chanmul is None and
                        (res is None or isinstance(res, Act) or res.folded))
         if self.folded:
@@ -1071,13 +1086,7 @@ class ConvBNRec:
                                res_after_relu=self.post_add is not None)
         geom, wf = self.geom, cw.wf
         if P.dry_run:
-            # no device: same rule as the library (tiles of 128 pixels x 64|128 channels, at most 512 TMEM columns per SM)
-            pix = n * ho * wo if cw.k == 1 else n * math.ceil(ho / max(1, 128 // min(128, 1 << (wo - 1).bit_length()))) * \
-                math.ceil(wo / min(128, 1 << max(3, (wo - 1).bit_length()))) * 128
-            tiles128 = math.ceil(pix / 128) * math.ceil(bns.Cp / 128)
-            bn_cols = 64 if (C <= 64 or tiles128 <= 80) else 128
-            tiles = math.ceil(pix / 128) * math.ceil(bns.Cp / bn_cols)
-            fits = math.ceil(tiles / 148) * bn_cols <= 512
+            fits = _coop_fits_estimate(n, ho, wo, cw.k, C)
         else:
             fits = ops.conv_bn_train_fits(geom, wf, C, y, a.tp, bn)
         if not fits:
@@ -1121,6 +1130,14 @@ class ConvBNRec:
             return  # projection shortcuts are driven by the record that consumed them
         g = g_override if g_override is not None else self.a.g
         if g is None:
+            return
+        if self.dy_pre is not None:
+            # sseg_conv_dgrad_bn (emitted by the consumer) did this layer's BN backward: dy, dgamma, dbeta are final
+            assert self.fused and self.res is None and self.post_add is None
+            dy = self.dy_pre
+            geom, gw, O = self.geom, cw.gw, cw.O
+            P.bwd.append(P.on_side(lambda: ops.conv_wgrad(geom, dy, O, gw)))
+            self._emit_dgrad(dy)
             return
         dy = torch.empty_like(self.y)
         dres = None
@@ -1182,7 +1199,20 @@ class ConvBNRec:
                 else:
                     s1, s2 = pb.dbeta, pb.s2y
                 py = prod.y
-                P.bwd.append(lambda: ops.conv_igemm_bnbwd(gd, wd, I, buf, py, pb.scale, pb.shift, s1, s2))
+                coop = (P.coop_bn and prod.mode == ops.BN_TRAIN and P.peer is None and pb.counter_bwd is not None and
+                        prod.cw.O == I)
+                if coop:
+                    # the producer's whole BN backward rides in this data-gradient kernel: dy is written, g never is
+                    dyp = torch.empty_like(py)
+                    n_, h_, w_, _ = py.shape
+                    args = (gd, wd, I, py, dyp, pb.scale, pb.shift, pb.mean, pb.invstd, prod.count, pb.dbeta, pb.s2y, pb.dgamma,
+                            pb.counter_bwd)
+                    coop = _coop_fits_estimate(n_, h_, w_, cw.k, I) if P.dry_run else ops.conv_dgrad_bn(*args, query=True)
+                if coop:
+                    prod.dy_pre = dyp
+                    P.bwd.append(lambda: ops.conv_dgrad_bn(*args))
+                else:
+                    P.bwd.append(lambda: ops.conv_igemm_bnbwd(gd, wd, I, buf, py, pb.scale, pb.shift, s1, s2))
             else:
                 P.bwd.append(lambda: ops.conv_igemm(gd, wd, I, buf, n_store=_pad(I, 8), addend=buf if acc else None))
         else:

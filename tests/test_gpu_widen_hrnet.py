@@ -249,3 +249,44 @@ def test_fused_conv_bn_train_schedule_matches_the_default_step(monkeypatch):
     assert abs(o0[0].item() - o1[0].item()) <= 2e-3 * abs(o0[0].item())
     assert _rel(f1, f0) <= 3e-2 and torch.allclose(r1, r0, atol=1e-5)
     assert torch.dot(g0, g1).item() / (g0.norm() * g1.norm()).item() >= 0.98
+
+
+@_EXPERIMENTAL
+@pytest.mark.parametrize("k,hw,cprod,cout_next", [(1, 64, 128, 256), (3, 64, 128, 256), (3, 38, 128, 256), (3, 32, 48, 48),
+                                                  (3, 128, 64, 64), (1, 64, 1024, 256)])
+def test_fused_conv_bn_dgrad_kernel_matches_the_two_kernel_sequence(k, hw, cprod, cout_next):
+    """sseg_conv_dgrad_bn (data gradient + the producer's whole BN backward, g resident in TMEM across the grid barrier)
+    against sseg_conv_igemm_bnbwd + sseg_bn_bwd_apply(s2_raw) on the same operands."""
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(23)
+    n = 2
+    y = torch.randn(n, hw, hw, cprod, device="cuda", generator=g).bfloat16()        # producer's saved conv output
+    fscale = torch.rand(cprod, device="cuda", generator=g) + 0.5                    # gamma * inv_std
+    fshift = torch.randn(cprod, device="cuda", generator=g) * 0.3
+    mean = torch.randn(cprod, device="cuda", generator=g) * 0.2
+    invstd = torch.rand(cprod, device="cuda", generator=g) + 0.5
+    dy_next = (torch.randn(n, hw, hw, cout_next, device="cuda", generator=g) * 0.1).bfloat16()
+    w = (torch.randn(cout_next, cprod, k, k, device="cuda", generator=g) * 0.05).bfloat16()
+    wd = torch.zeros(cprod, k * k * cout_next, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weight(w.float().contiguous(), None, wd, o_pad=cout_next)
+    dh, dw = ops.conv_taps(k, 1)
+    gd = ops.make_geom([dy_next], ([-v for v in dh], [-v for v in dw]), tap_koff=[t * cout_next for t in range(k * k)])
+    cnt = n * hw * hw
+    # reference: dgrad with the fused partial sums, then the apply kernel
+    gout = torch.empty(n, hw, hw, cprod, device="cuda", dtype=torch.bfloat16)
+    s1a, s2a, dga = (torch.zeros(cprod, device="cuda") for _ in range(3))
+    ops.conv_igemm_bnbwd(gd, wd, cprod, gout, y, fscale, fshift, s1a, s2a)
+    dya = torch.empty_like(y)
+    ops.bn_bwd_apply(gout, None, y, mean, invstd, fscale, s1a, s2a, cnt, dya, fshift=fshift, s2_raw=True, dgamma_out=dga)
+    # fused kernel
+    s1b, s2b, dgb = (torch.zeros(cprod, device="cuda") for _ in range(3))
+    counter = torch.zeros(4, device="cuda")
+    dyb = torch.full_like(y, float("nan"))
+    args = (gd, wd, cprod, y, dyb, fscale, fshift, mean, invstd, cnt, s1b, s2b, dgb, counter[:1])
+    assert ops.conv_dgrad_bn(*args, query=True)
+    ops.conv_dgrad_bn(*args)
+    torch.cuda.synchronize()
+    assert torch.allclose(s1b, s1a, rtol=1e-4, atol=1e-3) and torch.allclose(s2b, s2a, rtol=1e-4, atol=1e-3)
+    assert torch.allclose(dgb, dga, rtol=1e-3, atol=1e-3)
+    assert torch.isfinite(dyb.float()).all()
+    assert (dyb.float() - dya.float()).abs().max().item() <= 2 ** -7 * dya.float().abs().max().item()

@@ -176,7 +176,10 @@ def test_fused_conv_bn_schedule(monkeypatch):
     assert len(recs) == 60 and len(coop) == 52
     assert all(r.apply and r.y is not None for r in coop)           # y is kept: the backward pass reads it
     assert not any(r.coop for r in recs if r.cw.O == 2048)
-    assert len(Q.fwd) - len(P.fwd) == 2 * len(coop) and len(Q.bwd) == len(P.bwd)
+    assert len(Q.fwd) - len(P.fwd) == 2 * len(coop)
+    # backward: producers with a single consumer get their whole BN backward from the consumer's data-gradient kernel
+    pre = [r for r in recs if r.dy_pre is not None]
+    assert len(pre) >= 25 and all(r.fused for r in pre) and len(Q.bwd) - len(P.bwd) == len(pre)
     # every BN of a fused layer has a barrier counter slot that the per-step statistics reset zeroes
     assert all(r.bns.counter is not None and r.bns.counter.numel() == 1 for r in coop)
     # frozen BN (eval) and inference never take the fused training kernel
