@@ -890,6 +890,7 @@ class StemRec:
         self.a = Act(P._new(N, ho, wo, 64))
         self.a.producer = self
         self.relu, self.res, self.post_add, self.chanmul, self.apply, self.fused = True, None, None, None, True, False
+        self.dy_pre = None   # set when the consumer's data-gradient kernel already did this layer's BN backward
         self.mode = P._bn_mode(bns)
         self.count = N * ho * wo
         w = cw.mod.weight
@@ -903,9 +904,12 @@ class StemRec:
         P, bns = self.P, self.bns
         if self.a.g is None:
             return
-        dy = torch.empty_like(self.y)
-        _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, None, self.y, dy, None, None, mask_from_y=True,
-                          fused=self.fused)
+        if self.dy_pre is not None:
+            dy = self.dy_pre
+        else:
+            dy = torch.empty_like(self.y)
+            _emit_bn_backward(P, bns, self.mode, self.count, self.a.g, None, self.y, dy, None, None, mask_from_y=True,
+                              fused=self.fused)
         gw = self.cw.gw
         P.bwd.append(P.on_side(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3))))
 

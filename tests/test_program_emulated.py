@@ -1,0 +1,192 @@
+"""CPU: whole step programs EXECUTED against `tests/abi_emulator.py` (a Python restatement of the C ABI's documented
+semantics) and compared with the oracle — the schedules' arithmetic wiring without a GPU.
+
+ * default schedule vs the bf16-emulating oracle: frozen BN pins every gradient route; train-mode BN pins loss / features
+   (two bf16 pipelines decorrelate through ReLU-mask flips);
+ * every opt-in schedule (fused conv+BN kernels, folded eval BN, branch streams, overlapped re-layout, fused multi-scale
+   head) vs the default schedule on the same emulator: same loss, same gradients, same probabilities.
+The CUDA kernels themselves are covered by the `-m gpu` tests; this file covers which kernel gets which buffer and
+coefficient vector, in which order."""
+import statistics
+
+import pytest
+import torch
+import torch.nn as nn
+
+from abi_emulator import EmuLib
+from oracle import segnet_oracle as O
+from test_program_dry import _seg
+
+SWITCHES = ("SSEG_BRANCH_STREAMS", "SSEG_FOLD_BN_EVAL", "SSEG_OVERLAP_RELAYOUT", "SSEG_COOP_BN")
+
+
+@pytest.fixture
+def emu(monkeypatch):
+    from mit_semseg.engine import _C, ops
+    lib = EmuLib()
+    monkeypatch.setattr(_C, "lib", lambda: lib)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    for name in SWITCHES:
+        monkeypatch.delenv(name, raising=False)
+    return lib
+
+
+def _load(seg, enc_arch, dec_arch, fc, gain=0.25, bias_shift=0.0, calibrate_on=None):
+    esd = O.synth_state_dict(O.encoder_param_shapes(enc_arch), 304, gain)
+    dsd = O.synth_state_dict(O.decoder_param_shapes(dec_arch, fc), 305)
+    if bias_shift:
+        for sd in (esd, dsd):
+            for k in sd:
+                if k.endswith(".bias") and (k[:-5] + ".running_mean") in sd:
+                    sd[k] = sd[k] + bias_shift
+    if calibrate_on is not None:
+        with torch.no_grad():
+            st = O.BNState(True, update_running=True, momentum=1.0)
+            O.decoder_forward(O.encoder_forward(calibrate_on["img_data"], esd, enc_arch, st), dsd, dec_arch, st, dropout_p=0.0)
+    seg.encoder.load_state_dict(esd)
+    seg.decoder.load_state_dict(dsd)
+    return esd, dsd
+
+
+def _run_train(seg, feed):
+    from mit_semseg.engine import program as PR
+    P = PR.SegProgram(seg, tuple(feed["img_data"].shape), training=True, with_grad=True, dry_run=True)
+    P.dry_run, P.serial = False, True
+    P.load_inputs(feed["img_data"], feed["seg_label"])
+    P.run_eager()
+    return P
+
+
+def _rel(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def _freeze(seg):
+    for m in seg.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.eval()
+        if isinstance(m, nn.Dropout2d):
+            m.p = 0.0
+
+
+@pytest.mark.parametrize("enc,dec,fc,stride,hw", [("resnet18dilated", "ppm_deepsup", 512, 8, 64),
+                                                  ("resnet50", "upernet", 2048, 4, 64),
+                                                  ("hrnetv2", "c1", 720, 4, 64)])
+def test_default_schedule_frozen_bn_matches_the_oracle(enc, dec, fc, stride, hw, emu):
+    seg = _seg(enc, dec, fc)
+    feed = O.synth_batch(2, hw, hw, stride, 1)
+    esd, dsd = _load(seg, enc, dec, fc, bias_shift=2.0 if enc == "hrnetv2" else 0.0,
+                     calibrate_on=feed if enc == "hrnetv2" else None)
+    seg.train()
+    _freeze(seg)
+    P = _run_train(seg, feed)
+    e = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in esd.items()}
+    d = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in dsd.items()}
+    ds = seg.deep_sup_scale
+    l_ref, a_ref = O.segmentation_forward(feed, e, d, enc, dec, O.BNState(False, emulate="bf16"), ds, dropout_p=0.0)
+    l_ref.backward()
+    assert abs(P.out[0].item() - l_ref.item()) <= 2e-3 * abs(l_ref.item())
+    grads = P.param_grads()
+    rels = {}
+    for prefix, net, sd in (("enc.", seg.encoder, e), ("dec.", seg.decoder, d)):
+        for name, p in net.named_parameters():
+            rels[prefix + name] = _rel(grads[p], sd[name].grad)
+    worst = max(rels, key=rels.get)
+    print(enc, dec, "loss", P.out[0].item(), l_ref.item(), "grad rel median %.4f max %.4f (%s)" % (
+        statistics.median(rels.values()), rels[worst], worst))
+    # a mis-routed gradient is an O(1) error; bf16 rounding noise of these tiny (2x2-pixel layer4) runs stays below 10 %
+    assert statistics.median(rels.values()) <= 0.08 and rels[worst] <= 0.4, (worst, rels[worst])
+
+
+@pytest.mark.parametrize("enc,dec,fc,stride", [("resnet18dilated", "ppm_deepsup", 512, 8), ("hrnetv2", "c1", 720, 4)])
+def test_default_schedule_train_mode_bn_matches_the_oracle(enc, dec, fc, stride, emu):
+    seg = _seg(enc, dec, fc)
+    feed = O.synth_batch(2, 64, 64, stride, 1)
+    esd, dsd = _load(seg, enc, dec, fc)
+    seg.train()
+    for m in seg.modules():
+        if isinstance(m, nn.Dropout2d):
+            m.p = 0.0
+    rm0 = seg.encoder.bn1.running_mean.clone()
+    P = _run_train(seg, feed)
+    l_ref, a_ref, feats, out = O.segmentation_forward(feed, dict(esd), dict(dsd), enc, dec, O.BNState(True, emulate="bf16"),
+                                                      seg.deep_sup_scale, dropout_p=0.0, return_aux=True)
+    assert abs(P.out[0].item() - l_ref.item()) <= 5e-3 * abs(l_ref.item())
+    f = P.feats[-1]
+    got = torch.cat([q.t for q in f], 3) if isinstance(f, list) else f.t
+    assert _rel(got.float().permute(0, 3, 1, 2), feats[-1]) <= 0.1
+    assert not torch.equal(seg.encoder.bn1.running_mean, rm0)       # running statistics moved (F.batch_norm semantics)
+
+
+@pytest.mark.parametrize("enc,dec,fc,stride", [("resnet18dilated", "ppm_deepsup", 512, 8), ("resnet50", "upernet", 2048, 4),
+                                               ("hrnetv2", "c1", 720, 4)])
+@pytest.mark.parametrize("switch", ["SSEG_COOP_BN", "SSEG_BRANCH_STREAMS", "SSEG_OVERLAP_RELAYOUT"])
+def test_opt_in_training_schedules_equal_the_default_schedule(enc, dec, fc, stride, switch, emu, monkeypatch):
+    """Train-mode BN, same emulator, same weights: an opt-in schedule must reproduce the default schedule's loss, running
+    statistics and gradients (only the split of the arithmetic over kernels differs)."""
+    feed = O.synth_batch(2, 64, 64, stride, 2)
+    res = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv(switch, flag)
+        seg = _seg(enc, dec, fc)
+        _load(seg, enc, dec, fc)
+        seg.train()
+        for m in seg.modules():
+            if isinstance(m, nn.Dropout2d):
+                m.p = 0.0
+        P = _run_train(seg, feed)
+        res[flag] = (P.out.clone(), {n: g.clone() for n, g in zip([n for n, _ in seg.named_parameters()],
+                                                                    [P.param_grads()[p] for p in seg.parameters()])},
+                     {n: b.clone() for n, b in seg.named_buffers() if "running" in n})
+        if switch == "SSEG_COOP_BN" and flag == "1":
+            assert emu.calls.get("sseg_conv_bn_train", 0) > 0 and emu.calls.get("sseg_conv_dgrad_bn", 0) > 0
+    (o0, g0, b0), (o1, g1, b1) = res["0"], res["1"]
+    assert torch.allclose(o0, o1, rtol=1e-4, atol=1e-6), (o0, o1)
+    for n in b0:
+        assert torch.allclose(b0[n], b1[n], rtol=1e-4, atol=1e-6), n
+    rels = {n: _rel(g1[n], g0[n]) for n in g0}
+    worst = max(rels, key=rels.get)
+    print(switch, enc, "grad rel vs default schedule: median %.2e max %.2e (%s)" % (statistics.median(rels.values()), rels[worst], worst))
+    # identical arithmetic up to fp32 association; train-mode BN amplifies the resulting rounding flips
+    assert statistics.median(rels.values()) <= 1e-2 and rels[worst] <= 0.15, (worst, rels[worst])
+
+
+@pytest.mark.parametrize("enc,dec,fc", [("resnet18dilated", "ppm_deepsup", 512), ("resnet50", "upernet", 2048), ("hrnetv2", "c1", 720)])
+def test_inference_schedules_match_the_oracle_and_each_other(enc, dec, fc, emu, monkeypatch):
+    from mit_semseg.engine import program as PR
+    feed = O.synth_batch(1, 64, 96, 8, 5)
+    hr = enc == "hrnetv2"   # HRNet needs calibrated statistics (its synthetic ones explode); the ResNets run as they are
+    probs = {}
+    for fold in ("0", "1"):
+        monkeypatch.setenv("SSEG_FOLD_BN_EVAL", fold)
+        seg = _seg(enc, dec, fc)
+        esd, dsd = _load(seg, enc, dec, fc, bias_shift=1.0 if hr else 0.0, calibrate_on=feed if hr else None)
+        seg.eval()
+        P = PR.SegProgram(seg, (1, 3, 64, 96), training=False, with_grad=False, seg_size=(64, 96), dry_run=True)
+        P.dry_run, P.serial = False, True
+        P.load_inputs(feed["img_data"])
+        P.run_eager()
+        probs[fold] = P.probs.clone()
+    with torch.no_grad():
+        ref = O.segmentation_forward(feed, esd, dsd, enc, dec, O.BNState(False, emulate="bf16"), None, segSize=(64, 96))
+    for fold, p in probs.items():
+        assert (p.sum(1) - 1).abs().max().item() < 1e-3
+        agree = (p.argmax(1) == ref.argmax(1)).float().mean().item()
+        # (uncalibrated synthetic statistics saturate the softmax: a flipped pixel is a probability error of 1)
+        assert agree >= 0.9 and (not hr or (p - ref).abs().max().item() <= 5e-2), (fold, agree)
+    assert (probs["0"].argmax(1) == probs["1"].argmax(1)).float().mean().item() >= 0.9
+    # fused multi-scale head == the reference loop (eval.py:63-72), through the program interface
+    seg.eval()
+    imgs = [torch.randn(1, 3, 64, 96), torch.randn(1, 3, 96, 128)]
+    scores = torch.zeros(1, 150, 64, 96)
+    loop = torch.zeros(1, 150, 64, 96)
+    for im in imgs:
+        for head in (dict(), dict(head_out=scores, head_weight=0.5)):
+            P = PR.SegProgram(seg, tuple(im.shape), training=False, with_grad=False, seg_size=(64, 96), dry_run=True, **head)
+            P.dry_run, P.serial = False, True
+            P.load_inputs(im)
+            P.run_eager()
+            if not head:
+                loop += 0.5 * P.probs
+    assert torch.allclose(scores, loop, atol=1e-6)
