@@ -129,6 +129,50 @@ def _worker(rank, world, port, ret):
             nsmall = P.g_small
             assert torch.all(P.gflat[nsmall:] == 3.0), "conv gradient buckets must be summed over the ranks exactly once"
         os.environ.pop("SSEG_OVERLAP_RELAYOUT")
+
+        # ---- the same schedule COMPUTED (tests/abi_emulator.py restates the C ABI in torch): two ranks over gloo against
+        #      the oracle on the CONCATENATED batch with the synchronised BN formula and the mean of the per-rank losses -
+        #      the reference's DataParallel semantics (batchnorm.py:98-139, train.py:42); what tools/dist_check.py checks
+        #      on two GPUs.
+        import torch.nn.functional as F
+        from abi_emulator import EmuLib
+        from test_program_emulated import _load, _rel
+        emu = EmuLib()
+        _C.lib = lambda: emu
+        enc_arch, dec_arch, fc = "resnet18dilated", "c1_deepsup", 512
+        seg = _seg(enc_arch, dec_arch, fc)
+        esd, dsd = _load(seg, enc_arch, dec_arch, fc)
+        seg.train()
+        feeds = [O.synth_batch(2, 64, 64, 8, 100 + r) for r in range(world)]
+        P = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+        P.dry_run, P.serial = False, True
+        P.load_inputs(feeds[rank]["img_data"], feeds[rank]["seg_label"])
+        P.run_eager()
+        grads = {("enc." if net is seg.encoder else "dec.") + n: P.param_grads()[p].clone()
+                 for net in (seg.encoder, seg.decoder) for n, p in net.named_parameters()}
+        fl = torch.cat([g.flatten() for g in grads.values()])
+        other = fl.clone()
+        dist.broadcast(other, 0)
+        assert torch.equal(fl, other), "ranks disagree on the reduced gradients"
+        losses = [torch.zeros(1) for _ in range(world)]
+        dist.all_gather(losses, P.out[:1].clone())
+        e = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in esd.items()}
+        d = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in dsd.items()}
+        st = O.BNState(True, sync=True, update_running=True, emulate="bf16")
+        feats = O.encoder_forward(torch.cat([f["img_data"] for f in feeds]), e, enc_arch, st)
+        lg, lg_ds = O.decoder_forward(feats, d, dec_arch, st, dropout_p=0.0, return_logits=True)
+        per = []
+        for r in range(world):
+            sl, lab = slice(2 * r, 2 * r + 2), feeds[r]["seg_label"]
+            per.append(F.nll_loss(F.log_softmax(lg[sl], 1), lab, ignore_index=-1) +
+                       0.4 * F.nll_loss(F.log_softmax(lg_ds[sl], 1), lab, ignore_index=-1))
+        (sum(per) / world).backward()
+        for got, want in zip(losses, per):
+            assert abs(got.item() - want.item()) <= 5e-3 * abs(want.item()), (got.item(), want.item())
+        gr = torch.cat([(e if n.startswith("enc.") else d)[n[4:]].grad.flatten() for n in grads])
+        cos = torch.dot(fl, gr).item() / (fl.norm() * gr.norm()).item()
+        assert cos >= 0.97, cos
+        assert (seg.encoder.bn1.running_mean - e["bn1.running_mean"]).abs().max().item() < 1e-4   # accumulator formula
         ret[rank] = True
     finally:
         dist.destroy_process_group()

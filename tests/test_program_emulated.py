@@ -190,3 +190,48 @@ def test_inference_schedules_match_the_oracle_and_each_other(enc, dec, fc, emu, 
             if not head:
                 loop += 0.5 * P.probs
     assert torch.allclose(scores, loop, atol=1e-6)
+
+
+def test_training_loss_curve_follows_the_oracle(emu, monkeypatch):
+    """north_star: "the training loss curve overlays the reference". Six SGD steps (train.py's optimiser settings) through
+    the public API - SegmentationModule(feed) -> loss.backward() -> torch.optim.SGD.step() - on the emulated ABI, against
+    the oracle trained with autograd from the same weights on the same batches."""
+    from mit_semseg.engine import functional as EF
+    from mit_semseg.engine import program as PR
+    real = PR.SegProgram
+
+    def factory(*a, **k):
+        k["dry_run"] = True
+        prog = real(*a, **k)
+        prog.dry_run, prog.serial = False, True
+        return prog
+    monkeypatch.setattr(EF, "SegProgram", factory)
+    monkeypatch.setattr(real, "capture", lambda self: None)
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    enc, dec, fc = "resnet18dilated", "c1_deepsup", 512
+    seg = _seg(enc, dec, fc)
+    esd, dsd = _load(seg, enc, dec, fc)
+    seg.train()
+    opt = torch.optim.SGD(seg.parameters(), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    e = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in esd.items()}
+    d = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in dsd.items()}
+    params = [v for v in list(e.values()) + list(d.values()) if v.requires_grad]
+    opt_ref = torch.optim.SGD(params, lr=0.02, momentum=0.9, weight_decay=1e-4)
+    ours, ref = [], []
+    for step in range(6):
+        feed = O.synth_batch(2, 64, 64, 8, 100 + step % 2)          # two alternating batches: the loss must come down
+        opt.zero_grad()
+        loss, acc = seg(feed)
+        loss.backward()
+        opt.step()
+        ours.append(loss.item())
+        opt_ref.zero_grad()
+        l_ref, _ = O.segmentation_forward(feed, e, d, enc, dec, O.BNState(True, emulate="bf16", update_running=True), 0.4,
+                                          dropout_p=0.0)
+        l_ref.backward()
+        opt_ref.step()
+        ref.append(l_ref.item())
+    print("engine schedule:", ["%.4f" % v for v in ours])
+    print("oracle         :", ["%.4f" % v for v in ref])
+    assert ours[4] < ours[0] and ours[5] < ours[1]                  # it trains (same batch, two / three updates later)
+    assert all(abs(a - b) <= 2e-2 * abs(b) for a, b in zip(ours, ref)), (ours, ref)
