@@ -178,8 +178,9 @@ def test_fused_conv_bn_schedule(monkeypatch):
     assert not any(r.coop for r in recs if r.cw.O == 2048)
     assert len(Q.fwd) - len(P.fwd) == 2 * len(coop)
     # backward: producers with a single consumer get their whole BN backward from the consumer's data-gradient kernel
-    pre = [r for r in recs if r.dy_pre is not None]
+    pre = [r for r in P.records if isinstance(r, (PR.ConvBNRec, PR.StemRec)) and r.dy_pre is not None]
     assert len(pre) >= 25 and all(r.fused for r in pre) and len(Q.bwd) - len(P.bwd) == len(pre)
+    assert any(isinstance(r, PR.StemRec) for r in pre)   # the stem's BN backward rides in conv2's data-gradient kernel too
     # every BN of a fused layer has a barrier counter slot that the per-step statistics reset zeroes
     assert all(r.bns.counter is not None and r.bns.counter.numel() == 1 for r in coop)
     # frozen BN (eval) and inference never take the fused training kernel
