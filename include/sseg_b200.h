@@ -350,6 +350,27 @@ int sseg_sum_terms(const sseg_sum_term_t* terms, int nterms, int N, int Ho, int 
 int sseg_relu_mask_bwd(const void* g, long g_ld, const void* out, long out_ld, void* ds, long ds_ld, void* acc_out,
                        long acc_ld, int accumulate, long P, int C, sseg_stream_t stream);
 
+/* ---- fp32-accurate inference on bf16 tensor cores (BASELINE config 2: logits within 1e-3 of the fp32 reference) ------
+ * Every activation / weight is a PAIR of bf16 tensors (hi = bf16(x), lo = bf16(x - hi)); conv(x, w) ~= x_hi*w_hi +
+ * x_lo*w_hi + x_hi*w_lo is ONE sseg_conv_igemm launch (out_f32 = 1) over the virtual concat [x_hi | x_lo | x_hi] and the
+ * K-concatenated weight [w_hi | w_hi | w_lo] per tap (sseg_prep_conv_weight_split). The functions below surround it. */
+/* out pair = relu?( z*scale + shift (+ res pair) ); z: fp32 NHWC view (a strided view subsamples a stride-1 output, which
+ * is how stride-2 convolutions run in this mode); scale/shift NULL = identity; out/res: pixel-dense bf16 [N*H*W][ld]. */
+int sseg_split_affine(const sseg_act_t* z, const float* scale, const float* shift, const void* res_hi, const void* res_lo,
+                      long res_ld, void* out_hi, void* out_lo, long out_ld, int relu, int res_after_relu,
+                      sseg_stream_t stream);
+/* conv1 of the deep stem in fp32 (models/resnet.py:100): img fp32 NCHW -> out fp32 NHWC [N,Ho,Wo,64]. */
+int sseg_stem_conv_fwd_f32(const float* img, int N, int H, int W, const float* w, float* out, sseg_stream_t stream);
+/* nn.MaxPool2d(3,2,1), nn.AdaptiveAvgPool2d(S), F.interpolate(bilinear) on pairs (fp32 arithmetic on hi + lo). */
+int sseg_maxpool_pair_fwd(const void* x_hi, const void* x_lo, int N, int H, int W, int C, void* out_hi, void* out_lo,
+                          sseg_stream_t stream);
+int sseg_avgpool_pair_fwd(const void* x_hi, const void* x_lo, long x_ld, int N, int H, int W, int C, int S, void* out_hi,
+                          void* out_lo, sseg_stream_t stream);
+int sseg_bilinear_pair_fwd(const void* x_hi, const void* x_lo, long x_ld, int N, int Hi, int Wi, int C, void* out_hi,
+                           void* out_lo, long out_ld, int Ho, int Wo, sseg_stream_t stream);
+/* fp32 OIHW weight -> bf16 [O][ld], per tap t: out[o][t*3I + i] = out[o][t*3I + I + i] = w_hi, out[o][t*3I + 2I + i] = w_lo. */
+int sseg_prep_conv_weight_split(const float* w_oihw, int O, int I, int T, void* out, long ld, sseg_stream_t stream);
+
 /* ---- loss ------------------------------------------------------------------------------- */
 /* F.log_softmax + nn.NLLLoss(ignore_index=-1) + pixel_acc (models/models.py:12-18,37-42,492-493; train.py:154).
  * logits fp32 [P][ld]; label int64 [P]; lse float [P] out; accum float[3] (caller-zeroed):

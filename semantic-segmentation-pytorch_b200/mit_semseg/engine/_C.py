@@ -141,6 +141,12 @@ _SIGNATURES = {
     "sseg_bilinear_bwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, c_int, _p, _p],
     "sseg_sum_terms": [POINTER(SumTerm), c_int, c_int, c_int, c_int, c_int, _p, c_long, c_int, _p],
     "sseg_relu_mask_bwd": [_p, c_long, _p, c_long, _p, c_long, _p, c_long, c_int, c_long, c_int, _p],
+    "sseg_split_affine": [POINTER(Act), _p, _p, _p, _p, c_long, _p, _p, c_long, c_int, c_int, _p],
+    "sseg_stem_conv_fwd_f32": [_p, c_int, c_int, c_int, _p, _p, _p],
+    "sseg_maxpool_pair_fwd": [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p],
+    "sseg_avgpool_pair_fwd": [_p, _p, c_long, c_int, c_int, c_int, c_int, c_int, _p, _p, _p],
+    "sseg_bilinear_pair_fwd": [_p, _p, c_long, c_int, c_int, c_int, c_int, _p, _p, c_long, c_int, c_int, _p],
+    "sseg_prep_conv_weight_split": [_p, c_int, c_int, c_int, _p, c_long, _p],
     "sseg_softmax_nll_fwd": [_p, c_long, c_int, _p, c_long, _p, _p, _p],
     "sseg_nll_finalize": [_p, _p, c_float, _p, _p],
     "sseg_softmax_nll_bwd": [_p, c_long, c_int, _p, _p, _p, c_float, c_long, _p, c_long, c_int, _p],

@@ -1,6 +1,7 @@
 """Entry points the nn.Module classes call: they look up (or build) the step program for the input shape, run it, and
 connect its precomputed gradients to autograd.  See engine/program.py for what a program is."""
 import collections
+import os
 
 import torch
 
@@ -86,7 +87,13 @@ def segmentation_inference(seg, img, seg_size):
         raise RuntimeError("the B200 engine has no CPU path: move the module and the batch to a CUDA device")
     if not getattr(seg.decoder, "use_softmax", False):
         raise RuntimeError("inference (segSize=...) requires a decoder built with use_softmax=True")
-    prog = get_program(seg, img.shape, seg_size=tuple(seg_size), with_grad=False, capture=False)
+    if os.environ.get("SSEG_ACCURATE_INFERENCE", "0") == "1":
+        # fp32-accurate mode (bf16 pairs, three-term products; engine/accurate.py): logits within 1e-3 of the fp32 reference
+        from .accurate import AccurateInference
+        key = ("acc", tuple(img.shape), tuple(seg_size), _flags(seg))
+        prog = _cached(seg, key, lambda: AccurateInference(seg, tuple(img.shape), tuple(seg_size)))
+    else:
+        prog = get_program(seg, img.shape, seg_size=tuple(seg_size), with_grad=False, capture=False)
     prog.load_inputs(img)
     # image sizes vary during evaluation, so a program is only captured into a CUDA graph once its shape recurs
     prog.uses = getattr(prog, "uses", 0) + 1

@@ -360,6 +360,49 @@ def relu_mask_bwd(g, out, ds, acc_out=None, accumulate=False):
     return ds
 
 
+# ---------------------------------------------------------------------------------------------------------
+# fp32-accurate inference: activations / weights as (hi, lo) bf16 pairs (csrc/accurate.cu)
+def split_affine(z, out_hi, out_lo, scale=None, shift=None, res=None, relu=True, res_after_relu=False):
+    """(out_hi, out_lo) = split(relu?(z*scale + shift (+ res_hi + res_lo))); z: fp32 NHWC view, res: (hi, lo) or None."""
+    assert z.dtype == torch.float32
+    rh, rl = res if res is not None else (None, None)
+    _C.check(_C.lib().sseg_split_affine(act(z), _C.ptr(scale), _C.ptr(shift), _C.ptr(rh), _C.ptr(rl),
+                                        _pix(rh)[2] if rh is not None else 0, _C.ptr(out_hi), _C.ptr(out_lo), _pix(out_hi)[2],
+                                        int(relu), int(res_after_relu), _stream()))
+
+
+def stem_conv_fwd_f32(img, w, out):
+    n, c, h, w_ = img.shape
+    assert c == 3 and img.is_contiguous() and out.dtype == torch.float32 and out.is_contiguous()
+    _C.check(_C.lib().sseg_stem_conv_fwd_f32(_C.ptr(img), n, h, w_, _C.ptr(w), _C.ptr(out), _stream()))
+
+
+def maxpool_pair_fwd(x, out):
+    n, h, w, c = x[0].shape
+    assert all(t.is_contiguous() for t in x + out)
+    _C.check(_C.lib().sseg_maxpool_pair_fwd(_C.ptr(x[0]), _C.ptr(x[1]), n, h, w, c, _C.ptr(out[0]), _C.ptr(out[1]), _stream()))
+
+
+def avgpool_pair_fwd(x, S, out):
+    n, h, w, c = x[0].shape
+    assert out[0].is_contiguous() and out[1].is_contiguous() and out[0].shape == (n, S, S, c)
+    _C.check(_C.lib().sseg_avgpool_pair_fwd(_C.ptr(x[0]), _C.ptr(x[1]), _pix(x[0])[2], n, h, w, c, S, _C.ptr(out[0]),
+                                            _C.ptr(out[1]), _stream()))
+
+
+def bilinear_pair_fwd(x, out):
+    n, hi, wi, c = x[0].shape
+    _, ho, wo, _ = out[0].shape
+    _C.check(_C.lib().sseg_bilinear_pair_fwd(_C.ptr(x[0]), _C.ptr(x[1]), _pix(x[0])[2], n, hi, wi, c, _C.ptr(out[0]),
+                                             _C.ptr(out[1]), _pix(out[0])[2], ho, wo, _stream()))
+
+
+def prep_conv_weight_split(w, out):
+    O, I, kh, kw = w.shape
+    assert w.is_contiguous() and w.dtype == torch.float32 and out.dtype == torch.bfloat16
+    _C.check(_C.lib().sseg_prep_conv_weight_split(_C.ptr(w), O, I, kh * kw, _C.ptr(out), out.stride(0), _stream()))
+
+
 def softmax_nll_fwd(logits, num_class, label, lse, accum):
     P, _, ld = _pix(logits)
     assert label.dtype == torch.int64 and label.is_contiguous() and label.numel() == P

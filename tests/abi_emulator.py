@@ -510,3 +510,66 @@ class EmuLib:
         pix_view(out, ld, N * H * W, C).copy_(_bf(flat(x, N * C * H * W, torch.float32).view(N, C, H, W).permute(0, 2, 3, 1)
                                                   .reshape(-1, C)))
         return 0
+
+    # ---- fp32-accurate inference (pairs of bf16 tensors)
+    @staticmethod
+    def _pair_val(hi, lo, ld, P, C):
+        return pix_view(hi, ld, P, C).float() + pix_view(lo, ld, P, C).float()
+
+    @staticmethod
+    def _pair_store(hi, lo, ld, P, C, val):
+        h = _bf(val)
+        pix_view(hi, ld, P, C).copy_(h)
+        pix_view(lo, ld, P, C).copy_(_bf(val - h.float()))
+
+    def sseg_split_affine(self, z, scale, shift, res_hi, res_lo, res_ld, out_hi, out_lo, out_ld, relu, res_after_relu, stream):
+        v = act_view(z, torch.float32).clone()
+        n, h, w, c = v.shape
+        P = n * h * w
+        if _addr(scale):
+            v = v * vec(scale, c) + vec(shift, c)
+        v = v.reshape(P, c)
+        rr = self._pair_val(res_hi, res_lo, res_ld, P, c) if _addr(res_hi) else 0
+        if not res_after_relu:
+            v = v + rr
+        if relu:
+            v = torch.relu(v)
+        if res_after_relu:
+            v = v + rr
+        self._pair_store(out_hi, out_lo, out_ld, P, c, v)
+        return 0
+
+    def sseg_stem_conv_fwd_f32(self, img, N, H, W, w, out, stream):
+        x = flat(img, N * 3 * H * W, torch.float32).view(N, 3, H, W)
+        wt = flat(w, 64 * 27, torch.float32).view(64, 3, 3, 3)
+        y = F.conv2d(x, wt, stride=2, padding=1).permute(0, 2, 3, 1)
+        flat(out, y.numel(), torch.float32).view(y.shape).copy_(y)
+        return 0
+
+    def sseg_maxpool_pair_fwd(self, xh, xl, N, H, W, C, oh, ol, stream):
+        v = self._pair_val(xh, xl, C, N * H * W, C).view(N, H, W, C).permute(0, 3, 1, 2)
+        o = F.max_pool2d(v, 3, 2, 1).permute(0, 2, 3, 1)
+        self._pair_store(oh, ol, C, o.shape[0] * o.shape[1] * o.shape[2], C, o.reshape(-1, C))
+        return 0
+
+    def sseg_avgpool_pair_fwd(self, xh, xl, x_ld, N, H, W, C, S, oh, ol, stream):
+        v = self._pair_val(xh, xl, x_ld, N * H * W, C).view(N, H, W, C).permute(0, 3, 1, 2)
+        o = F.adaptive_avg_pool2d(v, S).permute(0, 2, 3, 1)
+        self._pair_store(oh, ol, C, N * S * S, C, o.reshape(-1, C))
+        return 0
+
+    def sseg_bilinear_pair_fwd(self, xh, xl, x_ld, N, Hi, Wi, C, oh, ol, out_ld, Ho, Wo, stream):
+        v = self._pair_val(xh, xl, x_ld, N * Hi * Wi, C).view(N, Hi, Wi, C).permute(0, 3, 1, 2)
+        o = F.interpolate(v, size=(Ho, Wo), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+        self._pair_store(oh, ol, out_ld, N * Ho * Wo, C, o.reshape(-1, C))
+        return 0
+
+    def sseg_prep_conv_weight_split(self, w, O, I, T, out, ld, stream):
+        wt = flat(w, O * I * T, torch.float32).view(O, I, T)
+        hi = _bf(wt)
+        lo = _bf(wt - hi.float())
+        o = flat(out, (O - 1) * ld + 3 * T * I, torch.bfloat16).as_strided((O, T, 3, I), (ld, 3 * I, I, 1))
+        o[:, :, 0, :] = hi.permute(0, 2, 1)
+        o[:, :, 1, :] = hi.permute(0, 2, 1)
+        o[:, :, 2, :] = lo.permute(0, 2, 1)
+        return 0

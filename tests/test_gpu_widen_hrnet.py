@@ -290,3 +290,76 @@ def test_fused_conv_bn_dgrad_kernel_matches_the_two_kernel_sequence(k, hw, cprod
     assert torch.allclose(dgb, dga, rtol=1e-3, atol=1e-3)
     assert torch.isfinite(dyb.float()).all()
     assert (dyb.float() - dya.float()).abs().max().item() <= 2 ** -7 * dya.float().abs().max().item()
+
+
+@_EXPERIMENTAL
+def test_pair_kernels_against_torch():
+    """csrc/accurate.cu: split_affine, pooling / resizing of (hi, lo) pairs, fp32 stem, weight split."""
+    import torch.nn.functional as F
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(4)
+    n, h, w, c = 2, 12, 20, 64
+
+    def pair(t):
+        hi = t.bfloat16()
+        return hi, (t - hi.float()).bfloat16()
+
+    def val(p):
+        return p[0].float() + p[1].float()
+    x = torch.randn(n, h, w, c, device="cuda", generator=g) * 3
+    xp = pair(x)
+    assert (val(xp) - x).abs().max().item() <= 2 ** -15 * x.abs().max().item()
+    # split_affine with a strided fp32 view (stride-2 subsampling), BN affine, shortcut pair, ReLU
+    z = torch.randn(n, 2 * h, 2 * w, c + 8, device="cuda", generator=g)
+    sc, sh = torch.rand(c, device="cuda", generator=g) + 0.5, torch.randn(c, device="cuda", generator=g)
+    oh, ol = torch.empty(n, h, w, c, device="cuda", dtype=torch.bfloat16), torch.empty(n, h, w, c, device="cuda", dtype=torch.bfloat16)
+    ops.split_affine(z[:, ::2, ::2, :c], oh, ol, scale=sc, shift=sh, res=xp, relu=True)
+    ref = torch.relu(z[:, ::2, ::2, :c] * sc + sh + val(xp))
+    assert (val((oh, ol)) - ref).abs().max().item() <= 2 ** -14 * ref.abs().max().item()
+    # pooling / resize on pairs
+    mo = (torch.empty(n, 6, 10, c, device="cuda", dtype=torch.bfloat16), torch.empty(n, 6, 10, c, device="cuda", dtype=torch.bfloat16))
+    ops.maxpool_pair_fwd(xp, mo)
+    ref = F.max_pool2d(val(xp).permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(val(mo), ref)
+    for S in (1, 2, 3, 6):
+        ao = (torch.empty(n, S, S, c, device="cuda", dtype=torch.bfloat16), torch.empty(n, S, S, c, device="cuda", dtype=torch.bfloat16))
+        ops.avgpool_pair_fwd(xp, S, ao)
+        ref = F.adaptive_avg_pool2d(val(xp).permute(0, 3, 1, 2), S).permute(0, 2, 3, 1)
+        assert (val(ao) - ref).abs().max().item() <= 2 ** -14 * ref.abs().max().item()
+        buf = (torch.empty(n, h, w, c + 16, device="cuda", dtype=torch.bfloat16), torch.empty(n, h, w, c + 16, device="cuda", dtype=torch.bfloat16))
+        ops.bilinear_pair_fwd(ao, (buf[0][..., 16:], buf[1][..., 16:]))
+        ref = F.interpolate(val(ao).permute(0, 3, 1, 2), size=(h, w), mode="bilinear", align_corners=False).permute(0, 2, 3, 1)
+        assert (val((buf[0][..., 16:], buf[1][..., 16:])) - ref).abs().max().item() <= 2 ** -14 * ref.abs().max().item() + 1e-6
+    # fp32 stem and weight split
+    img = torch.randn(2, 3, 32, 48, device="cuda", generator=g)
+    w1 = torch.randn(64, 3, 3, 3, device="cuda", generator=g) * 0.2
+    zo = torch.empty(2, 16, 24, 64, device="cuda")
+    ops.stem_conv_fwd_f32(img, w1, zo)
+    ref = F.conv2d(img, w1, stride=2, padding=1).permute(0, 2, 3, 1)
+    assert (zo - ref).abs().max().item() <= 1e-5 * ref.abs().max().item()
+    wt = torch.randn(40, 24, 3, 3, device="cuda", generator=g)
+    w3 = torch.zeros(40, 3 * 9 * 24, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weight_split(wt, w3)
+    v = w3.view(40, 9, 3, 24).float()
+    whi = wt.bfloat16().float().reshape(40, 24, 9).permute(0, 2, 1)
+    assert torch.equal(v[:, :, 0], whi) and torch.equal(v[:, :, 1], whi)
+    assert (v[:, :, 0] + v[:, :, 2] - wt.reshape(40, 24, 9).permute(0, 2, 1)).abs().max().item() <= 2 ** -15 * wt.abs().max().item()
+
+
+@_EXPERIMENTAL
+def test_accurate_inference_reaches_fp32_accuracy_on_the_gpu(monkeypatch):
+    """BASELINE config 2: ResNet18dilated + PPM_deepsup inference, logits / probabilities within 1e-3 of the fp32 oracle."""
+    from oracle import segnet_oracle as O
+    seg, esd, dsd, ds = _build("resnet18dilated", "ppm_deepsup", 512, use_softmax=True, residual_gain=0.25)
+    seg.cuda().eval()
+    feed = O.synth_batch(2, 128, 160, 8, 9)
+    with torch.no_grad():
+        ref = O.segmentation_forward(feed, esd, dsd, "resnet18dilated", "ppm_deepsup", O.BNState(False), None, segSize=(128, 160))
+        bf16 = seg({"img_data": feed["img_data"].cuda()}, segSize=(128, 160)).cpu()
+        monkeypatch.setenv("SSEG_ACCURATE_INFERENCE", "1")
+        for _ in range(3):     # the third call replays the captured graph
+            acc = seg({"img_data": feed["img_data"].cuda()}, segSize=(128, 160)).cpu()
+    e_acc, e_bf = (acc - ref).abs().max().item(), (bf16 - ref).abs().max().item()
+    agree = (acc.argmax(1) == ref.argmax(1)).float().mean().item()
+    print("accurate mode: max |dp| %.2e (bf16 path %.2e), arg-max agreement %.6f" % (e_acc, e_bf, agree))
+    assert e_acc <= 1e-3 and agree >= 0.9995

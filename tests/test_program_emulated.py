@@ -235,3 +235,37 @@ def test_training_loss_curve_follows_the_oracle(emu, monkeypatch):
     print("oracle         :", ["%.4f" % v for v in ref])
     assert ours[4] < ours[0] and ours[5] < ours[1]                  # it trains (same batch, two / three updates later)
     assert all(abs(a - b) <= 2e-2 * abs(b) for a, b in zip(ours, ref)), (ours, ref)
+
+
+@pytest.mark.parametrize("enc,dec,fc", [("resnet18dilated", "ppm_deepsup", 512), ("resnet18", "c1", 512)])
+def test_accurate_inference_schedule_reaches_fp32_accuracy(enc, dec, fc, emu):
+    """BASELINE config 2 (ResNet18dilated + PPM_deepsup inference): logits within 1e-3 of the fp32 reference and the same
+    arg-max map. The bf16-pair schedule (engine/accurate.py: three-term products as ONE virtual-concat GEMM launch per
+    convolution) against the plain fp32 oracle - and, for scale, the ordinary bf16 schedule on the same input."""
+    from mit_semseg.engine import accurate as ACC
+    from mit_semseg.engine import program as PR
+    seg = _seg(enc, dec, fc)
+    esd, dsd = _load(seg, enc, dec, fc)
+    seg.eval()
+    feed = O.synth_batch(2, 64, 96, 8, 9)
+    with torch.no_grad():
+        feats = O.encoder_forward(feed["img_data"], esd, enc, O.BNState(False))
+        lg = O.decoder_forward(feats, dsd, dec, O.BNState(False), return_logits=True)
+        lg = lg[0] if isinstance(lg, tuple) else lg
+        ref = O.segmentation_forward(feed, esd, dsd, enc, dec, O.BNState(False), None, segSize=(64, 96))
+    A = ACC.AccurateInference(seg, (2, 3, 64, 96), (64, 96), dry_run=True)
+    A.dry_run = False
+    A.load_inputs(feed["img_data"])
+    A.run_eager()
+    got = A.logits.permute(0, 3, 1, 2)
+    rel = _rel(got, lg)
+    agree = (A.probs.argmax(1) == ref.argmax(1)).float().mean().item()
+    B = PR.SegProgram(seg, (2, 3, 64, 96), training=False, with_grad=False, seg_size=(64, 96), dry_run=True)
+    B.dry_run, B.serial = False, True
+    B.load_inputs(feed["img_data"])
+    B.run_eager()
+    rel_bf16 = _rel(B.logits[..., :150].permute(0, 3, 1, 2), lg)
+    print("%s+%s logits rel-L2 vs fp32 oracle: accurate %.2e (bf16 schedule %.2e), arg-max agreement %.6f" % (enc, dec, rel, rel_bf16, agree))
+    assert rel <= 1e-3 and rel < rel_bf16 / 20
+    assert agree >= 0.9995    # two fp32-grade implementations differ only at exact ties of random-init logits
+    assert (A.probs - ref).abs().max().item() <= 1e-3 and (A.probs.sum(1) - 1).abs().max().item() < 1e-4

@@ -140,6 +140,15 @@ def null_engine(null_lib, monkeypatch):
     monkeypatch.setattr(EF, "SegProgram", factory)
     monkeypatch.setattr(real, "capture", lambda self: None)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    from mit_semseg.engine import accurate as ACC
+    real_acc = ACC.AccurateInference
+
+    def acc_factory(*a, **k):
+        prog = real_acc(*a, dry_run=True, **k)
+        prog.dry_run = False
+        return prog
+    monkeypatch.setattr(ACC, "AccurateInference", acc_factory)
+    monkeypatch.setattr(real_acc, "capture", lambda self: None)
     return null_lib
 
 
@@ -172,6 +181,15 @@ def test_public_entry_points_execute(null_engine):
         for _ in range(3):
             scores = EF.multiscale_inference(seg, imgs, (64, 96))
         assert scores.shape == (1, 150, 64, 96)
+        # fp32-accurate mode through the same entry point
+        import os
+        os.environ["SSEG_ACCURATE_INFERENCE"] = "1"
+        try:
+            for _ in range(3):
+                probs = seg({"img_data": torch.randn(1, 3, 64, 96)}, segSize=(64, 96))
+        finally:
+            os.environ.pop("SSEG_ACCURATE_INFERENCE")
+        assert probs.shape == (1, 150, 64, 96) and null_engine.calls["sseg_split_affine"] > 0
     seg.decoder.use_softmax = False
     with pytest.raises(RuntimeError, match="use_softmax"):
         seg({"img_data": torch.randn(1, 3, 64, 96)}, segSize=(64, 96))

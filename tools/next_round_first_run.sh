@@ -32,7 +32,7 @@ for sw in "" "SSEG_BRANCH_STREAMS=1"; do
   echo "[$sw]"; env $sw timeout 200 python tools/step_breakdown.py --net hrnet --replay-only 2>&1 | tail -1
 done
 echo "== inference (configs 2 and 5)"
-for sw in "SSEG_FOLD_BN_EVAL=0" "SSEG_FOLD_BN_EVAL=1"; do
+for sw in "SSEG_FOLD_BN_EVAL=0" "SSEG_FOLD_BN_EVAL=1" "SSEG_ACCURATE_INFERENCE=1"; do
   env $sw timeout 120 python tools/infer_bench.py --net r18ppm 2>&1 | tail -1
   env $sw timeout 200 python tools/infer_bench.py --net hrnet --multiscale 2>&1 | tail -1
 done
