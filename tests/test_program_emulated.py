@@ -269,3 +269,24 @@ def test_accurate_inference_schedule_reaches_fp32_accuracy(enc, dec, fc, emu):
     assert rel <= 1e-3 and rel < rel_bf16 / 20
     assert agree >= 0.9995    # two fp32-grade implementations differ only at exact ties of random-init logits
     assert (A.probs - ref).abs().max().item() <= 1e-3 and (A.probs.sum(1) - 1).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("coop", ["0", "1"])
+def test_dropout2d_masks_reach_the_oracle_loss(coop, emu, monkeypatch):
+    """nn.Dropout2d(0.1) active (models/models.py:460,464): injected keep-masks, default and fused conv+BN schedules."""
+    from mit_semseg.engine import program as PR
+    monkeypatch.setenv("SSEG_COOP_BN", coop)
+    enc, dec, fc = "resnet18dilated", "ppm_deepsup", 512
+    seg = _seg(enc, dec, fc)
+    esd, dsd = _load(seg, enc, dec, fc)
+    seg.train()
+    feed = O.synth_batch(2, 64, 64, 8, 9)
+    g = torch.Generator().manual_seed(5)
+    masks = {"main": (torch.rand(2, 512, generator=g) >= 0.3).float(), "deepsup": (torch.rand(2, 128, generator=g) >= 0.3).float()}
+    P = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True, dropout_masks=masks)
+    P.dry_run, P.serial = False, True
+    P.load_inputs(feed["img_data"], feed["seg_label"])
+    P.run_eager()
+    l_ref, _ = O.segmentation_forward(feed, dict(esd), dict(dsd), enc, dec, O.BNState(True, emulate="bf16"), 0.4,
+                                      dropout_p=0.1, masks=masks)
+    assert abs(P.out[0].item() - l_ref.item()) <= 5e-3 * abs(l_ref.item()), (P.out[0].item(), l_ref.item())
