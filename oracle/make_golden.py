@@ -26,7 +26,7 @@ import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 from mit_semseg.lib.nn import SynchronizedBatchNorm2d  # noqa: E402  (reference)
 from mit_semseg.models import ModelBuilder, SegmentationModule  # noqa: E402  (reference)
-from mit_semseg.models import models as rmodels, resnet as rresnet, hrnet as rhrnet  # noqa: E402
+from mit_semseg.models import models as rmodels, resnet as rresnet, hrnet as rhrnet, mobilenet as rmobilenet  # noqa: E402
 
 from oracle import segnet_oracle as O  # noqa: E402
 
@@ -39,6 +39,8 @@ def build_ref(enc_arch, dec_arch, fc_dim, use_softmax=False):
     base, dil = O.parse_encoder_arch(enc_arch)
     if base == "hrnetv2":
         enc = rhrnet.hrnetv2(pretrained=False)
+    elif base == "mobilenetv2":
+        enc = rmodels.MobileNetV2Dilated(rmobilenet.mobilenetv2(pretrained=False), dilate_scale=8)
     else:
         net = rresnet.__dict__[base](pretrained=False)
         enc = rmodels.ResnetDilated(net, 8) if dil else rmodels.Resnet(net)
@@ -196,6 +198,13 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "api":
         api_case()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "mobilenet":
+        # BASELINE configs[0]: MobileNetV2dilated + C1_deepsup, single-image forward at 384x384 (the reference's CPU case)
+        infer_case("infer_mobilenetv2dilated_c1_deepsup_384", "mobilenetv2dilated", "c1_deepsup", 320, 1, 384, 384)
+        train_case("train_mobilenetv2dilated_c1_deepsup_96", "mobilenetv2dilated", "c1_deepsup", 320, 2, 96, 8,
+                   ["enc.features.0.0.weight", "enc.features.7.conv.3.weight", "enc.features.17.conv.6.weight",
+                    "dec.cbr_deepsup.0.weight"])
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "hrnet":
         train_case("train_hrnetv2_c1_64", "hrnetv2", "c1", 720, 2, 64, 4,
                    ["enc.conv1.weight", "enc.stage2.0.fuse_layers.0.1.0.weight", "enc.stage4.2.fuse_layers.3.0.2.0.weight",
@@ -216,6 +225,10 @@ if __name__ == "__main__":
                 "enc.stage3.1.branches.2.3.conv2.weight", "enc.transition2.2.0.0.weight", "dec.cbr.0.weight",
                 "dec.conv_last.bias"])
     infer_case("infer_hrnetv2_c1_64x96", "hrnetv2", "c1", 720, 1, 64, 96)
+    infer_case("infer_mobilenetv2dilated_c1_deepsup_384", "mobilenetv2dilated", "c1_deepsup", 320, 1, 384, 384)
+    train_case("train_mobilenetv2dilated_c1_deepsup_96", "mobilenetv2dilated", "c1_deepsup", 320, 2, 96, 8,
+               ["enc.features.0.0.weight", "enc.features.7.conv.3.weight", "enc.features.17.conv.6.weight",
+                "dec.cbr_deepsup.0.weight"])
     syncbn_case()
     dropout_case()
     api_case()

@@ -1,7 +1,7 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  Not part of the product path.
 
 A CPU, fp32 restatement of the reference hot path (CSAILVision/semantic-segmentation-pytorch @ 8f27c9b):
-deep-stem (dilated) ResNet or HRNetV2-W48 -> PPM / PPM_deepsup / C1 / UPerNet decoder -> log-softmax / NLL / pixel accuracy, with both
+deep-stem (dilated) ResNet, HRNetV2-W48 or MobileNetV2dilated -> PPM / PPM_deepsup / C1 / UPerNet decoder -> log-softmax / NLL / pixel accuracy, with both
 batch-norm formulas of SynchronizedBatchNorm2d.  It is written functionally over a flat state dict that uses the
 reference's parameter names, so one weights file loads into the reference, this oracle and the B200 engine.
 
@@ -37,10 +37,17 @@ HRNET_BRANCH_BLOCKS = 4
 HRNET_LAYER1_BLOCKS = 4
 
 
+# MobileNetV2 (reference models/mobilenet.py:86-95): (expansion t, channels c, repeats n, stride s) per group
+MOBILENET_SETTING = ((1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1))
+MOBILENET_DOWN_IDX = (2, 4, 7, 14)   # models/models.py:280
+
+
 def parse_encoder_arch(arch):
     arch = arch.lower()
     if arch == "hrnetv2":
         return "hrnetv2", False
+    if arch == "mobilenetv2dilated":
+        return "mobilenetv2", True
     dilated = arch.endswith("dilated")
     base = arch[:-len("dilated")] if dilated else arch
     if base not in RESNET_LAYERS:
@@ -245,10 +252,67 @@ def hrnet_forward(x, sd, st, prefix=""):
     return [torch.cat(ups, 1)]
 
 
+def _mobilenet_blocks():
+    """[(index in `features`, inp, oup, stride, expand_ratio)] of the InvertedResidual blocks (mobilenet.py:104-112)."""
+    out, inp, idx = [], 32, 1
+    for t, c, n, s in MOBILENET_SETTING:
+        for i in range(n):
+            out.append((idx, inp, c, s if i == 0 else 1, t))
+            inp, idx = c, idx + 1
+    return out
+
+
+def _mobilenet_dilate(idx, stride, is3x3):
+    """MobileNetV2Dilated._nostride_dilate with dilate_scale 8 (models/models.py:282-310): features[7:14] dilate 2,
+    features[14:] dilate 4 -> (stride, dilation = padding) of a 3x3 conv, stride of a 1x1 conv."""
+    dilate = 2 if 7 <= idx < 14 else (4 if idx >= 14 else 0)
+    dil = 1
+    if dilate:
+        if stride == 2:
+            stride = 1
+            if is3x3:
+                dil = dilate // 2
+        elif is3x3:
+            dil = dilate
+    return stride, dil
+
+
+def mobilenet_forward(x, sd, st, prefix="", return_feature_maps=True):
+    """MobileNetV2Dilated.forward (reference models/models.py:312-323) over mobilenet.py's InvertedResidual blocks
+    (:38-76): ReLU6 activations, depthwise 3x3 convolutions (groups = channels). fp32 only (no engine path yet)."""
+    P = prefix
+
+    def cbr6(x, conv, bn, stride=1, dil=1, groups=1, k=3, act=True):
+        pad = dil if k == 3 else 0
+        y = F.conv2d(x, sd[conv + ".weight"], None, stride, pad, dil, groups)
+        y = batch_norm(y, sd, bn, st)
+        return F.relu6(y) if act else y
+    x = cbr6(x, P + "features.0.0", P + "features.0.1", stride=2)
+    outs = []
+    for idx, inp, oup, stride, t in _mobilenet_blocks():
+        p = "%sfeatures.%d.conv." % (P, idx)
+        hidden = round(inp * t)
+        s3, d3 = _mobilenet_dilate(idx, stride, True)
+        y = x
+        k = 0
+        if t != 1:
+            y = cbr6(y, p + "0", p + "1", k=1)
+            k = 3
+        y = cbr6(y, p + "%d" % k, p + "%d" % (k + 1), stride=s3, dil=d3, groups=hidden)
+        y = cbr6(y, p + "%d" % (k + 3), p + "%d" % (k + 4), k=1, act=False)
+        x = x + y if (stride == 1 and inp == oup) else y
+        if idx in MOBILENET_DOWN_IDX:
+            outs.append(x)
+    outs.append(x)
+    return outs if return_feature_maps else [x]
+
+
 def encoder_forward(x, sd, arch, st, prefix=""):
     base, dilated = parse_encoder_arch(arch)
     if base == "hrnetv2":
         return hrnet_forward(x, sd, st, prefix)
+    if base == "mobilenetv2":
+        return mobilenet_forward(x, sd, st, prefix)
     block, counts = RESNET_LAYERS[base]
     P = prefix
     x = _cbr(x, sd, P + "conv1", P + "bn1", st, stride=2, padding=1)
@@ -436,10 +500,25 @@ def hrnet_param_shapes():
     return shapes
 
 
+def mobilenet_param_shapes():
+    shapes = {"features.0.0": ("conv", (32, 3, 3, 3)), "features.0.1": ("bn", 32)}
+    for idx, inp, oup, stride, t in _mobilenet_blocks():
+        p = "features.%d.conv." % idx
+        hidden, k = round(inp * t), 0
+        if t != 1:
+            shapes[p + "0"], shapes[p + "1"] = ("conv", (hidden, inp, 1, 1)), ("bn", hidden)
+            k = 3
+        shapes[p + "%d" % k], shapes[p + "%d" % (k + 1)] = ("conv", (hidden, 1, 3, 3)), ("bn", hidden)   # depthwise
+        shapes[p + "%d" % (k + 3)], shapes[p + "%d" % (k + 4)] = ("conv", (oup, hidden, 1, 1)), ("bn", oup)
+    return shapes
+
+
 def encoder_param_shapes(arch):
     base, _ = parse_encoder_arch(arch)
     if base == "hrnetv2":
         return hrnet_param_shapes()
+    if base == "mobilenetv2":
+        return mobilenet_param_shapes()
     block, counts = RESNET_LAYERS[base]
     exp = 1 if block == "basic" else 4
     shapes = {}

@@ -38,6 +38,7 @@ def _oracle_train(enc_arch, dec_arch, fc, n, hw, stride):
     ("train_r18dilated_c1_deepsup_96", "resnet18dilated", "c1_deepsup", 512, 96, 8),
     ("train_r50_upernet_128", "resnet50", "upernet", 2048, 128, 4),
     ("train_hrnetv2_c1_64", "hrnetv2", "c1", 720, 64, 4),
+    ("train_mobilenetv2dilated_c1_deepsup_96", "mobilenetv2dilated", "c1_deepsup", 320, 96, 8),
 ])
 def test_oracle_training_matches_reference_golden(name, enc, dec, fc, hw, stride):
     g = _gold(name)
@@ -62,6 +63,7 @@ def test_oracle_training_matches_reference_golden(name, enc, dec, fc, hw, stride
 @pytest.mark.parametrize("name,enc,dec,fc,n,h,w", [
     ("infer_r18dilated_ppm_deepsup_96x128", "resnet18dilated", "ppm_deepsup", 512, 2, 96, 128),
     ("infer_hrnetv2_c1_64x96", "hrnetv2", "c1", 720, 1, 64, 96),
+    ("infer_mobilenetv2dilated_c1_deepsup_384", "mobilenetv2dilated", "c1_deepsup", 320, 1, 384, 384),   # BASELINE configs[0]
 ])
 def test_oracle_inference_matches_reference_golden(name, enc, dec, fc, n, h, w):
     g = _gold(name)
