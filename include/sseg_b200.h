@@ -168,7 +168,8 @@ int sseg_conv_dgrad_bn_fits(const sseg_conv_geom_t* g, const void* w_bf16, long 
  * BatchNorm with running statistics is a per-channel affine (F.batch_norm eval branch, lib/nn/modules/batchnorm.py:
  * 58-61), so conv -> BN -> (+shortcut) -> ReLU (models/resnet.py:37-53,72-92; models/models.py:160-167) is ONE kernel
  * and the raw convolution output never reaches HBM. relu: 0 none | 1 after the addend (residual blocks) | 2 before the
- * addend (FPN lateral + top-down add, models/models.py:561-563). bf16 output; scale/shift float[cout] or both NULL.
+ * addend (FPN lateral + top-down add, models/models.py:561-563); + 4: ReLU6 (nn.ReLU6, models/mobilenet.py:26,34).
+ * bf16 output; scale/shift float[cout] or both NULL.
  */
 int sseg_conv_igemm_affine(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
                            const float* scale, const float* shift, int relu, const sseg_act_t* addend,
@@ -370,6 +371,16 @@ int sseg_bilinear_pair_fwd(const void* x_hi, const void* x_lo, long x_ld, int N,
                            void* out_lo, long out_ld, int Ho, int Wo, sseg_stream_t stream);
 /* fp32 OIHW weight -> bf16 [O][ld], per tap t: out[o][t*3I + i] = out[o][t*3I + I + i] = w_hi, out[o][t*3I + 2I + i] = w_lo. */
 int sseg_prep_conv_weight_split(const float* w_oihw, int O, int I, int T, void* out, long ld, sseg_stream_t stream);
+
+/* First layer of MobileNetV2 (nn.Conv2d(3, cout, 3, 2, 1), cout <= 64, multiple of 8; models/mobilenet.py:102) from the
+ * fp32 NCHW image with the inference epilogue: out = relu6?(conv * scale + shift), bf16 NHWC [N,Ho,Wo,cout] dense. */
+int sseg_stem_conv_affine(const float* img, int N, int H, int W, const float* w, int cout, const float* scale,
+                          const float* shift, int relu6, void* out, sseg_stream_t stream);
+/* Depthwise 3x3 convolution (nn.Conv2d(C, C, 3, stride, dilation, groups=C), models/mobilenet.py:52,62) with the
+ * inference epilogue: out = relu6?( dwconv(x) * scale + shift ). x: bf16 NHWC [N,H,W,C] dense; w: fp32 [C][3][3] (the
+ * module's weight [C,1,3,3]); 'same' padding = dilation; out: bf16 [N,Ho,Wo,C] dense, Ho = ceil(H/stride). */
+int sseg_dwconv_affine(const void* x, int N, int H, int W, int C, const float* w, int stride, int dilation,
+                       const float* scale, const float* shift, int relu6, void* out, sseg_stream_t stream);
 
 /* ---- loss ------------------------------------------------------------------------------- */
 /* F.log_softmax + nn.NLLLoss(ignore_index=-1) + pixel_acc (models/models.py:12-18,37-42,492-493; train.py:154).

@@ -177,7 +177,7 @@ def api_case():
     for enc_arch, dec_arch, fc in (("resnet50dilated", "ppm_deepsup", 2048), ("resnet18dilated", "ppm_deepsup", 512),
                                    ("resnet101", "c1_deepsup", 2048), ("resnet50", "ppm", 2048), ("resnet18", "c1", 512),
                                    ("resnet50", "upernet", 2048), ("resnet18", "upernet_lite", 512),
-                                   ("hrnetv2", "c1", 720)):
+                                   ("hrnetv2", "c1", 720), ("mobilenetv2dilated", "c1_deepsup", 320)):
         torch.manual_seed(304)
         enc, dec = build_ref(enc_arch, dec_arch, fc)
         rec = {"enc_keys": {k: list(v.shape) for k, v in enc.state_dict().items()},
@@ -186,8 +186,8 @@ def api_case():
                             for k, v in list(enc.state_dict().items())[:: 37] if v.is_floating_point()},
                "dec_init": {k: [float(v.double().sum()), float(v.double().abs().sum())]
                             for k, v in dec.state_dict().items() if v.is_floating_point() and v.dim() > 1},
-               "conv_hparams": {k: [list(m.stride), list(m.dilation), list(m.padding)] for k, m in enc.named_modules()
-                                if isinstance(m, nn.Conv2d)}}
+               "conv_hparams": {k: [list(m.stride), list(m.dilation), list(m.padding)] + ([m.groups] if m.groups != 1 else [])
+                                for k, m in enc.named_modules() if isinstance(m, nn.Conv2d)}}
         out["%s+%s" % (enc_arch, dec_arch)] = rec
     json.dump(out, open(os.path.join(GOLD, "reference_api.json"), "w"), indent=0, sort_keys=True)
     print("api ok")

@@ -279,14 +279,21 @@ def _mobilenet_dilate(idx, stride, is3x3):
 
 def mobilenet_forward(x, sd, st, prefix="", return_feature_maps=True):
     """MobileNetV2Dilated.forward (reference models/models.py:312-323) over mobilenet.py's InvertedResidual blocks
-    (:38-76): ReLU6 activations, depthwise 3x3 convolutions (groups = channels). fp32 only (no engine path yet)."""
+    (:38-76): ReLU6 activations, depthwise 3x3 convolutions (groups = channels)."""
     P = prefix
 
-    def cbr6(x, conv, bn, stride=1, dil=1, groups=1, k=3, act=True):
+    def cbr6(x, conv, bn, stride=1, dil=1, groups=1, k=3, act=True, add=None):
+        # storage-precision emulation follows the engine's inference kernels: GEMM weights in bf16 (the depthwise / first
+        # layer kernels read fp32 weights), ONE rounding per layer - after BN, shortcut and ReLU6, which ride in the epilogue
         pad = dil if k == 3 else 0
-        y = F.conv2d(x, sd[conv + ".weight"], None, stride, pad, dil, groups)
+        w = sd[conv + ".weight"]
+        if groups == 1 and x.shape[1] != 3:
+            w = _qw(w, st)
+        y = F.conv2d(x, w, None, stride, pad, dil, groups)
         y = batch_norm(y, sd, bn, st)
-        return F.relu6(y) if act else y
+        if add is not None:
+            y = y + add
+        return _q(F.relu6(y) if act else y, st)
     x = cbr6(x, P + "features.0.0", P + "features.0.1", stride=2)
     outs = []
     for idx, inp, oup, stride, t in _mobilenet_blocks():
@@ -299,8 +306,7 @@ def mobilenet_forward(x, sd, st, prefix="", return_feature_maps=True):
             y = cbr6(y, p + "0", p + "1", k=1)
             k = 3
         y = cbr6(y, p + "%d" % k, p + "%d" % (k + 1), stride=s3, dil=d3, groups=hidden)
-        y = cbr6(y, p + "%d" % (k + 3), p + "%d" % (k + 4), k=1, act=False)
-        x = x + y if (stride == 1 and inp == oup) else y
+        x = cbr6(y, p + "%d" % (k + 3), p + "%d" % (k + 4), k=1, act=False, add=x if (stride == 1 and inp == oup) else None)
         if idx in MOBILENET_DOWN_IDX:
             outs.append(x)
     outs.append(x)

@@ -47,7 +47,7 @@ struct IgemmParams {
   float* stat_sum;
   float* stat_sqsum;
   // fused inference epilogue (BatchNorm with running statistics is a per-channel affine): v = v*ep_scale + ep_shift,
-  // ReLU before (ep_relu == 2) or after (ep_relu == 1) the addend (= shortcut / top-down tensor) is added
+  // ReLU before ((ep_relu & 3) == 2) or after (== 1) the addend (= shortcut / top-down tensor) is added; bit 2: clip at 6
   const float* ep_scale;
   const float* ep_shift;
   int ep_relu;
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.cout) v[j] = fmaf(v[j], __ldg(p.ep_scale + col0 + j), __ldg(p.ep_shift + col0 + j));
       }
-      if (p.ep_relu == 2) {
+      if ((p.ep_relu & 3) == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
@@ -220,9 +220,13 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
           }
         }
       }
-      if (p.ep_relu == 1) {
+      if ((p.ep_relu & 3) == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.ep_relu & 4) {  // ReLU6 (MobileNetV2): the ReLU above, clipped at 6
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fminf(v[j], 6.f);
       }
       if (p.out_f32) {
         if (valid) {
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
         for (int j = 0; j < 32; ++j)
           if (col0 + j < p.cout) v[j] = fmaf(v[j], __ldg(p.ep_scale + col0 + j), __ldg(p.ep_shift + col0 + j));
       }
-      if (p.ep_relu == 2) {
+      if ((p.ep_relu & 3) == 2) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
       }
@@ -527,9 +531,13 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
           }
         }
       }
-      if (p.ep_relu == 1) {
+      if ((p.ep_relu & 3) == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      }
+      if (p.ep_relu & 4) {  // ReLU6 (MobileNetV2): the ReLU above, clipped at 6
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fminf(v[j], 6.f);
       }
       if (p.out_f32) {
         if (valid) {
@@ -1497,7 +1505,7 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   p.stat_sum = stat_sum, p.stat_sqsum = stat_sqsum;
   if (ep != nullptr) {
     SSEG_REQUIRE((ep->scale == nullptr) == (ep->shift == nullptr), "sseg_conv_igemm_affine: scale/shift must pair");
-    SSEG_REQUIRE(ep->relu >= 0 && ep->relu <= 2, "sseg_conv_igemm_affine: relu mode %d", ep->relu);
+    SSEG_REQUIRE(ep->relu >= 0 && (ep->relu & 3) <= 2 && ep->relu <= 6, "sseg_conv_igemm_affine: relu mode %d", ep->relu);
     p.ep_scale = ep->scale, p.ep_shift = ep->shift, p.ep_relu = ep->relu;
   }
   if (bw_y != nullptr) {

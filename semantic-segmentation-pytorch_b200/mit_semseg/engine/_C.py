@@ -141,6 +141,8 @@ _SIGNATURES = {
     "sseg_bilinear_bwd": [_p, c_long, c_int, c_int, c_int, c_int, _p, c_long, c_int, c_int, c_int, _p, _p],
     "sseg_sum_terms": [POINTER(SumTerm), c_int, c_int, c_int, c_int, c_int, _p, c_long, c_int, _p],
     "sseg_relu_mask_bwd": [_p, c_long, _p, c_long, _p, c_long, _p, c_long, c_int, c_long, c_int, _p],
+    "sseg_stem_conv_affine": [_p, c_int, c_int, c_int, _p, c_int, _p, _p, c_int, _p, _p],
+    "sseg_dwconv_affine": [_p, c_int, c_int, c_int, c_int, _p, c_int, c_int, _p, _p, c_int, _p, _p],
     "sseg_split_affine": [POINTER(Act), _p, _p, _p, _p, c_long, _p, _p, c_long, c_int, c_int, _p],
     "sseg_stem_conv_fwd_f32": [_p, c_int, c_int, c_int, _p, _p, _p],
     "sseg_maxpool_pair_fwd": [_p, _p, c_int, c_int, c_int, c_int, _p, _p, _p],

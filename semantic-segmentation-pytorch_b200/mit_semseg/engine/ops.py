@@ -64,6 +64,7 @@ def conv_igemm(geom, w_bf16, cout, out, n_store=None, bias=None, addend=None, st
 
 
 RELU_NONE, RELU_AFTER_ADD, RELU_BEFORE_ADD = 0, 1, 2
+RELU6 = 4   # or-ed to one of the above: clip at 6 (nn.ReLU6)
 
 
 def conv_igemm_affine(geom, w_bf16, cout, out, scale, shift, relu=RELU_AFTER_ADD, addend=None):
@@ -127,6 +128,26 @@ def conv_dgrad_bn(geom, w_bf16, cout, y, dy_out, fscale, fshift, mean, invstd, c
         return rc == 1
     _C.check(_C.lib().sseg_conv_dgrad_bn(*args, _stream()))
     return dy_out
+
+
+def stem_conv_affine(img, w, out, scale=None, shift=None, relu6=True):
+    """3x3 stride-2 conv from the fp32 NCHW image (3 -> cout <= 64) + eval-BN affine + ReLU6 -> bf16 NHWC."""
+    n, c, h, w_ = img.shape
+    cout = w.shape[0]
+    assert c == 3 and img.is_contiguous() and w.is_contiguous() and out.is_contiguous() and out.shape[3] == cout
+    _C.check(_C.lib().sseg_stem_conv_affine(_C.ptr(img), n, h, w_, _C.ptr(w), cout, _C.ptr(scale), _C.ptr(shift), int(relu6),
+                                            _C.ptr(out), _stream()))
+    return out
+
+
+def dwconv_affine(x, w, out, stride=1, dilation=1, scale=None, shift=None, relu6=True):
+    """Depthwise 3x3 conv ('same' padding = dilation) + eval-BN affine + ReLU6; x/out dense NHWC bf16, w fp32 [C,1,3,3]."""
+    n, h, w_, c = x.shape
+    assert x.is_contiguous() and out.is_contiguous() and w.is_contiguous() and w.dtype == torch.float32 and w.shape[0] == c
+    assert out.shape == (n, (h - 1) // stride + 1, (w_ - 1) // stride + 1, c)
+    _C.check(_C.lib().sseg_dwconv_affine(_C.ptr(x), n, h, w_, c, _C.ptr(w), stride, dilation, _C.ptr(scale), _C.ptr(shift),
+                                         int(relu6), _C.ptr(out), _stream()))
+    return out
 
 
 def conv_igemm_bnbwd(geom, w_bf16, cout, out, y, fscale, fshift, s1, s2_raw, addend=None):

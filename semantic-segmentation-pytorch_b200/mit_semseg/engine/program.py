@@ -162,6 +162,8 @@ class SegProgram:
         self.convs, self.bns = {}, {}
         for m in self._modules():
             if isinstance(m, nn.Conv2d):
+                if m.groups != 1:
+                    continue   # depthwise convolutions (MobileNetV2) read their fp32 weight directly (csrc/depthwise.cu)
                 self.convs[id(m)] = ConvW(m)
             elif isinstance(m, _BatchNorm):
                 self.bns[id(m)] = BNS(m)
@@ -596,11 +598,71 @@ class SegProgram:
         self.join_branches()
         return outs
 
+    def _build_mobilenet(self):
+        """MobileNetV2Dilated.forward (reference models/models.py:312-323) over InvertedResidual blocks
+        (models/mobilenet.py:38-76), inference only: every BatchNorm (running statistics) and ReLU6 is folded into the
+        kernel that produces the tensor — 1x1 convolutions on the implicit-GEMM kernel (sseg_conv_igemm_affine, shortcut as
+        addend), depthwise 3x3 convolutions and the 3-channel first layer on their own kernels (csrc/depthwise.cu)."""
+        enc = self.enc
+        if self.with_grad or self.training:
+            raise NotImplementedError("MobileNetV2 runs on the B200 engine in eval mode only (no ReLU6 / depthwise backward)")
+
+        def affine(bn_mod):
+            bns = self.bns[id(bn_mod)]
+            if self._bn_mode(bns) != ops.BN_EVAL:
+                raise NotImplementedError("MobileNetV2 runs on the B200 engine in eval mode only")
+            _emit_bn_forward(self, bns, ops.BN_EVAL, 1, None, None, False, None, None, None, None)
+            return bns.scale, bns.shift
+        first = enc.features[0]
+        conv0, bn0 = first[0], first[1]
+        assert conv0.in_channels == 3 and conv0.stride == (2, 2) and conv0.kernel_size == (3, 3)
+        sc, sh = affine(bn0)
+        ho, wo = (self.H - 1) // 2 + 1, (self.W - 1) // 2 + 1
+        x = Act(self._new(self.N, ho, wo, conv0.out_channels))
+        w0 = conv0.weight.detach()
+        self.fwd.append(lambda x=x, sc=sc, sh=sh: ops.stem_conv_affine(self.img, w0, x.t, scale=sc, shift=sh, relu6=True))
+        feats = []
+        self.block_outs = [x]   # per-block outputs (tools / tests compare them with the oracle's)
+        for idx in range(1, enc.total_idx):
+            block = enc.features[idx]
+            inp = x
+            stages = block.stages()
+            for si, (cv, bn, act) in enumerate(stages):
+                last = si == len(stages) - 1
+                sc, sh = affine(bn)
+                n, h, w, c = x.t.shape
+                if cv.groups != 1:
+                    assert cv.groups == c == cv.out_channels and cv.kernel_size == (3, 3) and cv.padding[0] == cv.dilation[0]
+                    s_, d_ = cv.stride[0], cv.dilation[0]
+                    y = Act(self._new(n, (h - 1) // s_ + 1, (w - 1) // s_ + 1, c))
+                    wdw = cv.weight.detach()
+                    self.fwd.append(lambda x=x, y=y, wdw=wdw, s_=s_, d_=d_, sc=sc, sh=sh, act=act:
+                                    ops.dwconv_affine(x.t, wdw, y.t, stride=s_, dilation=d_, scale=sc, shift=sh, relu6=act))
+                else:
+                    cw = self.convs[id(cv)]
+                    assert cw.k == 1 and cw.stride == 1
+                    geom, _, _ = self._conv_geom([x.t], cw)
+                    y = self._new_act(n, h, w, cw.O)
+                    relu = (ops.RELU_AFTER_ADD | ops.RELU6) if act else ops.RELU_NONE
+                    add = inp.tp if (last and block.use_res_connect) else None   # x + conv(x), no activation after the add
+                    self._need_weights(cw)
+                    self.fwd.append(lambda geom=geom, cw=cw, y=y, sc=sc, sh=sh, relu=relu, add=add:
+                                    ops.conv_igemm_affine(geom, cw.wf, cw.O, y.tp, sc, sh, relu=relu, addend=add))
+                x = y
+            self.block_outs.append(x)
+            if idx in enc.down_idx:
+                feats.append(x)
+        feats.append(x)
+        return feats
+
     def _build_encoder(self, R):
         enc = self.enc
         from ..models import hrnet as HR
+        from ..models import models as M_
         if isinstance(enc, HR.HRNetV2):
             return self._build_hrnet()
+        if isinstance(enc, M_.MobileNetV2Dilated):
+            return self._build_mobilenet()
         # ---- stem (reference models/resnet.py:100-109, models/models.py:256-259)
         stem = StemRec(self, self.convs[id(enc.conv1)], self.bns[id(enc.bn1)])
         self.records.append(stem)

@@ -7,7 +7,7 @@ and, for `SegmentationModule`, the backward as well — is a schedule of sm_100a
 `mit_semseg.engine.program` (implicit-GEMM convolutions on tcgen05, fused BN/ReLU/residual, PPM cascade with a
 virtual concat, fused log-softmax/NLL/accuracy).  There is no PyTorch-operator fallback.
 
-Supported on the engine in this build: resnet18/50/101 (+dilated) and hrnetv2 encoders; ppm, ppm_deepsup, c1, c1_deepsup,
+Supported on the engine in this build: resnet18/50/101 (+dilated), hrnetv2 and (inference only) mobilenetv2dilated encoders; ppm, ppm_deepsup, c1, c1_deepsup,
 upernet, upernet_lite decoders.  Other reference arch names are recognised and raise NotImplementedError with an explanation
 (unknown names raise the reference's Exception('Architecture undefined!')).
 """
@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from ..lib.nn import SynchronizedBatchNorm2d
-from . import hrnet, resnet
+from . import hrnet, mobilenet, resnet
 
 BatchNorm2d = SynchronizedBatchNorm2d
 
@@ -79,10 +79,13 @@ class ModelBuilder:
             raise NotImplementedError
         elif arch == 'hrnetv2':
             net_encoder = hrnet.__dict__['hrnetv2'](pretrained=pretrained)
-        elif arch in ('mobilenetv2dilated', 'resnext101'):
+        elif arch == 'mobilenetv2dilated':
+            orig_mobilenet = mobilenet.__dict__['mobilenetv2'](pretrained=pretrained)
+            net_encoder = MobileNetV2Dilated(orig_mobilenet, dilate_scale=8)
+        elif arch == 'resnext101':
             raise NotImplementedError(
                 "encoder '%s' is part of the reference API but not built on the B200 engine "
-                "(grouped / depthwise convolutions; see DESIGN.md 'out of scope')" % arch)
+                "(grouped convolutions; see DESIGN.md 'out of scope')" % arch)
         else:
             raise Exception('Architecture undefined!')
         if len(weights) > 0:
@@ -165,6 +168,33 @@ class ResnetDilated(_ResnetTrunk):
         elif m.kernel_size == (3, 3):
             m.dilation = (dilate, dilate)
             m.padding = (dilate, dilate)
+
+
+class MobileNetV2Dilated(nn.Module):
+    """Reference models.py:271-323: MobileNetV2 features without the last 1x1 conv, features[7:14] dilated by 2 and
+    features[14:] by 4 (stride-2 convs lose their stride). Feature maps are returned after features[2, 4, 7, 14] and at
+    the end (5 maps). Inference only on the engine (see models/mobilenet.py)."""
+
+    def __init__(self, orig_net, dilate_scale=8):
+        super().__init__()
+        self.features = orig_net.features[:-1]
+        self.total_idx = len(self.features)
+        self.down_idx = [2, 4, 7, 14]
+        if dilate_scale == 8:
+            for i in range(self.down_idx[-2], self.down_idx[-1]):
+                self.features[i].apply(partial(self._nostride_dilate, dilate=2))
+            for i in range(self.down_idx[-1], self.total_idx):
+                self.features[i].apply(partial(self._nostride_dilate, dilate=4))
+        elif dilate_scale == 16:
+            for i in range(self.down_idx[-1], self.total_idx):
+                self.features[i].apply(partial(self._nostride_dilate, dilate=2))
+
+    _nostride_dilate = ResnetDilated._nostride_dilate
+
+    def forward(self, x, return_feature_maps=False):
+        from ..engine import functional as EF
+        conv_out = EF.encoder_forward(self, x)
+        return conv_out if return_feature_maps else [conv_out[-1]]
 
 
 # ------------------------------------------------------------------------------------------------ decoders

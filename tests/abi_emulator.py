@@ -127,14 +127,16 @@ class EmuLib:
             scale, shift, relu = ep
             if _addr(scale):
                 v = v * vec(scale, cout) + vec(shift, cout)
-            if relu == 2:
+            if relu & 3 == 2:
                 v = torch.relu(v)
         else:
             relu = 0
         if addend is not None:
             v = v + act_view(addend).float()[..., :cout]
-        if relu == 1:
+        if relu & 3 == 1:
             v = torch.relu(v)
+        if relu & 4:
+            v = v.clamp(max=6.0)
         dtype = torch.float32 if out_f32 else torch.bfloat16
         _store(out, v, cout, dtype)
         if _addr(ssum):
@@ -572,4 +574,26 @@ class EmuLib:
         o[:, :, 0, :] = hi.permute(0, 2, 1)
         o[:, :, 1, :] = hi.permute(0, 2, 1)
         o[:, :, 2, :] = lo.permute(0, 2, 1)
+        return 0
+
+    def sseg_dwconv_affine(self, x, N, H, W, C, w, stride, dilation, scale, shift, relu6, out, stream):
+        xv = flat(x, N * H * W * C, torch.bfloat16).view(N, H, W, C).float().permute(0, 3, 1, 2)
+        wt = flat(w, C * 9, torch.float32).view(C, 1, 3, 3)
+        y = F.conv2d(xv, wt, None, stride, dilation, dilation, C).permute(0, 2, 3, 1)
+        if _addr(scale):
+            y = y * vec(scale, C) + vec(shift, C)
+        if relu6:
+            y = y.clamp(0.0, 6.0)
+        flat(out, y.numel(), torch.bfloat16).view(y.shape).copy_(_bf(y))
+        return 0
+
+    def sseg_stem_conv_affine(self, img, N, H, W, w, cout, scale, shift, relu6, out, stream):
+        x = flat(img, N * 3 * H * W, torch.float32).view(N, 3, H, W)
+        wt = flat(w, cout * 27, torch.float32).view(cout, 3, 3, 3)
+        y = F.conv2d(x, wt, stride=2, padding=1).permute(0, 2, 3, 1)
+        if _addr(scale):
+            y = y * vec(scale, cout) + vec(shift, cout)
+        if relu6:
+            y = y.clamp(0.0, 6.0)
+        flat(out, y.numel(), torch.bfloat16).view(y.shape).copy_(_bf(y))
         return 0

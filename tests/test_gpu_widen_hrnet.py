@@ -363,3 +363,53 @@ def test_accurate_inference_reaches_fp32_accuracy_on_the_gpu(monkeypatch):
     agree = (acc.argmax(1) == ref.argmax(1)).float().mean().item()
     print("accurate mode: max |dp| %.2e (bf16 path %.2e), arg-max agreement %.6f" % (e_acc, e_bf, agree))
     assert e_acc <= 1e-3 and agree >= 0.9995
+
+
+@_EXPERIMENTAL
+def test_mobilenet_kernels_and_inference():
+    """csrc/depthwise.cu against torch, then BASELINE configs[0] (MobileNetV2dilated + C1_deepsup forward) end to end."""
+    import torch.nn.functional as F
+    from mit_semseg.engine import ops
+    from mit_semseg.models import ModelBuilder, SegmentationModule
+    from mit_semseg.models import mobilenet as MB, models as M
+    from oracle import segnet_oracle as O
+    g = torch.Generator(device="cuda").manual_seed(8)
+    for c, stride, dil, hw in ((32, 1, 1, 40), (96, 2, 1, 24), (192, 1, 2, 16), (960, 1, 4, 12)):
+        x = torch.randn(2, hw, hw + 8, c, device="cuda", generator=g).bfloat16()
+        w = torch.randn(c, 1, 3, 3, device="cuda", generator=g) * 0.3
+        sc, sh = torch.rand(c, device="cuda", generator=g) + 0.5, torch.randn(c, device="cuda", generator=g)
+        out = torch.empty(2, (hw - 1) // stride + 1, (hw + 7) // stride + 1, c, device="cuda", dtype=torch.bfloat16)
+        ops.dwconv_affine(x, w, out, stride=stride, dilation=dil, scale=sc, shift=sh, relu6=True)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), w, None, stride, dil, dil, c).permute(0, 2, 3, 1) * sc + sh
+        ref = ref.clamp(0, 6)
+        assert (out.float() - ref).abs().max().item() <= 2 ** -8 * 6.0
+    img = torch.randn(2, 3, 64, 96, device="cuda", generator=g)
+    w0 = torch.randn(32, 3, 3, 3, device="cuda", generator=g) * 0.3
+    sc, sh = torch.rand(32, device="cuda", generator=g) + 0.5, torch.randn(32, device="cuda", generator=g)
+    o0 = torch.empty(2, 32, 48, 32, device="cuda", dtype=torch.bfloat16)
+    ops.stem_conv_affine(img, w0, o0, scale=sc, shift=sh, relu6=True)
+    ref = (F.conv2d(img, w0, stride=2, padding=1).permute(0, 2, 3, 1) * sc + sh).clamp(0, 6)
+    assert (o0.float() - ref).abs().max().item() <= 2 ** -8 * 6.0
+    # whole network
+    enc_arch, dec_arch, fc = "mobilenetv2dilated", "c1_deepsup", 320
+    enc = M.MobileNetV2Dilated(MB.mobilenetv2(pretrained=False), dilate_scale=8)
+    dec = ModelBuilder.build_decoder(dec_arch, fc_dim=fc, num_class=150, use_softmax=True)
+    seg = SegmentationModule(enc, dec, torch.nn.NLLLoss(ignore_index=-1), 0.4)
+    esd = O.synth_state_dict(O.encoder_param_shapes(enc_arch), 304)
+    dsd = O.synth_state_dict(O.decoder_param_shapes(dec_arch, fc), 305)
+    with torch.no_grad():
+        st = O.BNState(True, update_running=True, momentum=1.0)
+        O.decoder_forward(O.encoder_forward(O.synth_batch(2, 96, 128, 8, 6)["img_data"], esd, enc_arch, st), dsd, dec_arch, st, dropout_p=0.0)
+    enc.load_state_dict(esd)
+    dec.load_state_dict(dsd)
+    seg.cuda().eval()
+    feed = O.synth_batch(1, 96, 128, 8, 5)
+    with torch.no_grad():
+        probs = seg({"img_data": feed["img_data"].cuda()}, segSize=(96, 128)).cpu()
+        feats = seg.encoder(feed["img_data"].cuda(), return_feature_maps=True)
+        rfeats = O.encoder_forward(feed["img_data"], esd, enc_arch, O.BNState(False, emulate="bf16"))
+        ref = O.segmentation_forward(feed, esd, dsd, enc_arch, dec_arch, O.BNState(False, emulate="bf16"), None, segSize=(96, 128))
+    frel = [_rel(f.cpu(), r) for f, r in zip(feats, rfeats)]
+    agree = (probs.argmax(1) == ref.argmax(1)).float().mean().item()
+    print("mobilenet features rel", frel, "arg-max agreement %.4f" % agree)
+    assert len(feats) == 5 and max(frel[:3]) <= 2e-2 and max(frel) <= 0.2 and agree >= 0.8

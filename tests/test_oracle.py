@@ -190,6 +190,9 @@ def _build_mine(enc_arch, dec_arch, fc):
     if base == "hrnetv2":
         from mit_semseg.models import hrnet as HR
         enc = HR.hrnetv2(pretrained=False)
+    elif base == "mobilenetv2":
+        from mit_semseg.models import mobilenet as MB
+        enc = M.MobileNetV2Dilated(MB.mobilenetv2(pretrained=False), dilate_scale=8)
     else:
         net = R.__dict__[base](pretrained=False)
         enc = M.ResnetDilated(net, 8) if dil else M.Resnet(net)
@@ -200,7 +203,7 @@ def _build_mine(enc_arch, dec_arch, fc):
 @pytest.mark.parametrize("combo,fc", [("resnet50dilated+ppm_deepsup", 2048), ("resnet18dilated+ppm_deepsup", 512),
                                       ("resnet101+c1_deepsup", 2048), ("resnet50+ppm", 2048), ("resnet18+c1", 512),
                                       ("resnet50+upernet", 2048), ("resnet18+upernet_lite", 512),
-                                      ("hrnetv2+c1", 720)])
+                                      ("hrnetv2+c1", 720), ("mobilenetv2dilated+c1_deepsup", 320)])
 def test_module_tree_matches_reference_state_dict_init_and_hparams(combo, fc):
     enc_arch, dec_arch = combo.split("+")
     ref = API[combo]
@@ -215,14 +218,15 @@ def test_module_tree_matches_reference_state_dict_init_and_hparams(combo, fc):
     for k, (s, a) in ref["dec_init"].items():
         v = dec.state_dict()[k].double()
         assert abs(v.abs().sum().item() - a) <= 1e-6 * max(1.0, a), k
-    hp = {k: [list(m.stride), list(m.dilation), list(m.padding)] for k, m in enc.named_modules() if isinstance(m, nn.Conv2d)}
+    hp = {k: [list(m.stride), list(m.dilation), list(m.padding)] + ([m.groups] if m.groups != 1 else [])
+          for k, m in enc.named_modules() if isinstance(m, nn.Conv2d)}
     assert hp == ref["conv_hparams"]
     # oracle's own table of hyper-parameters (used by encoder_forward) agrees as well
     base, dil = O.parse_encoder_arch(enc_arch)
     # the oracle's parameter table names exactly the reference's parameters
     shapes = O.synth_state_dict(O.encoder_param_shapes(enc_arch), 1)
     assert {k: list(v.shape) for k, v in shapes.items()} == ref["enc_keys"]
-    if base == "hrnetv2":
+    if base in ("hrnetv2", "mobilenetv2"):
         return
     block, counts = O.RESNET_LAYERS[base]
     for li, nb in enumerate(counts, start=1):

@@ -18,6 +18,9 @@ def _seg(enc_arch, dec_arch, fc):
     from mit_semseg.models import hrnet as HR, models as M, resnet as R
     if enc_arch == "hrnetv2":
         enc = HR.hrnetv2(pretrained=False)
+    elif enc_arch == "mobilenetv2dilated":
+        from mit_semseg.models import mobilenet as MB
+        enc = M.MobileNetV2Dilated(MB.mobilenetv2(pretrained=False), dilate_scale=8)
     else:
         dil = enc_arch.endswith("dilated")
         net = R.__dict__[enc_arch.replace("dilated", "")](pretrained=False)
