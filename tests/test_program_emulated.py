@@ -70,7 +70,8 @@ def _freeze(seg):
             m.p = 0.0
 
 
-@pytest.mark.parametrize("enc,dec,fc,stride,hw", [("resnet18dilated", "ppm_deepsup", 512, 8, 64),
+@pytest.mark.parametrize("enc,dec,fc,stride,hw", [("resnet50dilated", "ppm_deepsup", 2048, 8, 64),   # the bench network
+                                                  ("resnet18dilated", "ppm_deepsup", 512, 8, 64),
                                                   ("resnet50", "upernet", 2048, 4, 64),
                                                   ("hrnetv2", "c1", 720, 4, 64)])
 def test_default_schedule_frozen_bn_matches_the_oracle(enc, dec, fc, stride, hw, emu):
