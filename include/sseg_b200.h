@@ -118,6 +118,17 @@ int sseg_conv_igemm(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld,
  *   res (+ rscale/rshift) : shortcut tensor (and, for projection shortcuts, its own BN affine); res_after_relu as in
  *                           sseg_bn_apply; chanmul: float[N][cout] Dropout2d keep-mask/(1-p) or NULL
  */
+/* world > 1 (SynchronizedBatchNorm's data-parallel branch, batchnorm.py:63-81,123-139): the cooperative kernels pool the
+ * per-rank partial sums over NVLink peer memory themselves. bases: every rank's arena (sseg_peer_alloc / sseg_peer_open);
+ * data_off: [sum C | sqsum C | count] (forward, data_stride = C) or [s1 | s2raw] (backward) inside each arena; flag_off:
+ * `world` int slots of the step-number handshake (never reset); step: device counter advanced by sseg_peer_step. */
+typedef struct {
+  void* const* bases;
+  int world, rank;
+  long data_off, data_stride, flag_off;
+  const int* step;
+} sseg_coop_peer_t;
+
 typedef struct {
   const float* gamma;
   const float* beta;
@@ -136,7 +147,18 @@ typedef struct {
   const float* rshift;
   const float* chanmul;
   int relu, res_after_relu;
+  /* synchronised branch (all NULL / 0 on a single GPU): stat_sum / stat_sqsum must then point at data_off inside this rank's
+   * arena; clamp(var, eps)^-1/2; tmp_running_* accumulators + running_iter are advanced here, running_mean / running_var
+   * are refreshed from them by sseg_bn_running_from_tmp; count_out receives the pooled pixel count. */
+  const sseg_coop_peer_t* peer;
+  float* tmp_running_mean;
+  float* tmp_running_var;
+  float* running_iter;
+  float* count_out;
 } sseg_bn_fused_t;
+/* running_mean = tmp_running_mean / running_iter, running_var likewise (batchnorm.py:136-137). */
+int sseg_bn_running_from_tmp(const float* tmp_running_mean, const float* tmp_running_var, const float* running_iter,
+                             float* running_mean, float* running_var, int C, sseg_stream_t stream);
 int sseg_conv_bn_train(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                        const sseg_act_t* a_out, const sseg_bn_fused_t* bn, sseg_stream_t stream);
 int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
@@ -153,11 +175,14 @@ int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_bf16, long 
  *   y        : the producer's saved convolution output; fscale / fshift its forward scale / shift (ReLU mask)
  *   mean, invstd, count : the producer's batch statistics;  s1 (= dbeta), s2_raw : float[cout], zeroed by the caller
  *   dgamma_out : float[cout] or NULL;  counter : one zeroed uint32;  dy_out : bf16, shape of y
+ *   peer (NULL on a single GPU): s1 / s2_raw then are this rank's partial-sum slots at peer->data_off inside its arena,
+ *   count_dev the pooled pixel count, and dbeta_out / dgamma_out receive the pooled sums divided by world.
  */
 int sseg_conv_dgrad_bn(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                        const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
                        const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,
-                       unsigned int* counter, sseg_stream_t stream);
+                       unsigned int* counter, const sseg_coop_peer_t* peer, const float* count_dev, float* dbeta_out,
+                       sseg_stream_t stream);
 int sseg_conv_dgrad_bn_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                             const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
                             const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,

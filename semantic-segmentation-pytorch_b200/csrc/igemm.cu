@@ -705,6 +705,41 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
 // of y per layer (reference: conv -> F.batch_norm(training) -> (+residual) -> ReLU, models/resnet.py:37-53,72-92;
 // lib/nn/modules/batchnorm.py:58-61).
 // =====================================================================================================
+// Cross-GPU half of SynchronizedBatchNorm inside the cooperative kernels (world > 1): after the local grid barrier CTA 0
+// publishes "this rank's partial sums of the layer are complete" into every peer's arena, every CTA waits for all peers'
+// flags, and phase 2 pools the partial sums straight out of peer memory over NVLink - the protocol of csrc/peer.cu
+// (step-number flags, never reset), without a kernel boundary.
+struct CoopPeer {
+  float* base[SSEG_MAX_PEERS];
+  int world, rank;       // world <= 1: single-GPU behaviour
+  long data_off;         // [sum C | sqsum C | count] (forward) or [s1 | s2raw] (backward) inside every rank's arena
+  long data_stride;      // distance between the two vectors (C forward, the 8-padded C backward)
+  long flag_off;
+  const int* step;
+};
+__device__ __forceinline__ void coop_st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int coop_ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// called by the 128 epilogue threads of every CTA right after the local grid barrier; t = epilogue thread index
+__device__ __forceinline__ void coop_peer_handshake(const CoopPeer& pr, int t) {
+  if (pr.world <= 1) return;
+  const int step = *pr.step;
+  if (blockIdx.x == 0 && t < pr.world) {
+    __threadfence_system();
+    coop_st_release_sys(reinterpret_cast<int*>(pr.base[t]) + pr.flag_off + pr.rank, step);
+  }
+  if (t < pr.world) {
+    const int* mine = reinterpret_cast<const int*>(pr.base[pr.rank]) + pr.flag_off + t;
+    while (coop_ld_acquire_sys(mine) < step) __nanosleep(32);
+  }
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
 struct IgemmBnParams {
   IgemmParams g;  // operands / geometry; g.out = y (bf16) or null; g.stat_sum / g.stat_sqsum = the layer's statistics
   __nv_bfloat16* a_out;  // activation, same geometry as y
@@ -724,6 +759,10 @@ struct IgemmBnParams {
   long pix_per_img;  // to find the image of a pixel when the batch is viewed as one row of pixels (1x1 convs)
   unsigned int* counter;  // zeroed by the caller before every launch
   int num_tiles, tiles_per_cta;
+  // synchronised branch (lib/nn/modules/batchnorm.py:63-81,123-139): pooled statistics, clamp(var, eps), accumulator
+  // running statistics (tmp_*; running_iter and running = tmp / iter are finished by sseg_bn_running_from_tmp)
+  CoopPeer peer;
+  float *tmp_mean, *tmp_var, *running_iter, *count_out;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -871,18 +910,36 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
             const int c = n0 + t;
             float sc = 0.f, sh = 0.f, rs = 1.f, rb = 0.f;
             if (c < p.cout) {
-              const float sum = __ldcg(p.stat_sum + c), sq = __ldcg(p.stat_sqsum + c);
-              const float mean = sum / q.count;
+              float sum, sq, cnt, inv_std;
+              if (q.peer.world > 1) {  // pooled over the ranks, in rank order (bit-identical on every rank)
+                sum = 0.f, sq = 0.f, cnt = 0.f;
+                for (int r = 0; r < q.peer.world; ++r) {
+                  const float* st = q.peer.base[r] + q.peer.data_off;
+                  sum += __ldcv(st + c), sq += __ldcv(st + q.peer.data_stride + c), cnt += __ldcv(st + 2 * q.peer.data_stride);
+                }
+              } else {
+                sum = __ldcg(p.stat_sum + c), sq = __ldcg(p.stat_sqsum + c), cnt = q.count;
+              }
+              const float mean = sum / cnt;
               const float sumvar = sq - sum * mean;
-              const float inv_std = rsqrtf(fmaxf(sumvar / q.count, 0.f) + q.eps);
+              if (q.peer.world > 1) inv_std = rsqrtf(fmaxf(sumvar / cnt, q.eps));   // clamp(var, eps)^-1/2, batchnorm.py:139
+              else inv_std = rsqrtf(fmaxf(sumvar / cnt, 0.f) + q.eps);
               const float gm = q.gamma ? q.gamma[c] : 1.f, bt = q.beta ? q.beta[c] : 0.f;
               sc = gm * inv_std, sh = bt - mean * gm * inv_std;
               if (q.rscale != nullptr) rs = q.rscale[c], rb = q.rshift[c];
               if (first_m_tile) {  // exactly one tile per channel block publishes (the backward pass reads these)
                 q.mean_out[c] = mean, q.invstd_out[c] = inv_std, q.scale_out[c] = sc, q.shift_out[c] = sh;
-                if (q.running_mean != nullptr) {
+                if (q.peer.world > 1) {
+                  if (c == 0 && q.count_out != nullptr) *q.count_out = cnt;
+                  if (q.tmp_mean != nullptr) {  // accumulator running statistics (batchnorm.py:131-137)
+                    const float frac = 1.f - q.momentum;
+                    q.tmp_mean[c] = q.tmp_mean[c] * frac + mean;
+                    q.tmp_var[c] = q.tmp_var[c] * frac + sumvar / (cnt - 1.f);
+                    if (c == 0) q.running_iter[0] = q.running_iter[0] * frac + 1.f;
+                  }
+                } else if (q.running_mean != nullptr) {
                   q.running_mean[c] = (1.f - q.momentum) * q.running_mean[c] + q.momentum * mean;
-                  q.running_var[c] = (1.f - q.momentum) * q.running_var[c] + q.momentum * sumvar / (q.count - 1.f);
+                  q.running_var[c] = (1.f - q.momentum) * q.running_var[c] + q.momentum * sumvar / (cnt - 1.f);
                 }
               }
             }
@@ -1007,6 +1064,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        coop_peer_handshake(q.peer, t);  // world > 1: every rank's partial sums are complete and visible
       }
     }
   }
@@ -1052,6 +1110,11 @@ struct IgemmDgradBnParams {
   float* dgamma_out;
   unsigned int* counter;
   int num_tiles, tiles_per_cta;
+  // synchronised branch: s1 / s2raw partial sums live in the rank's arena, totals are pooled over the ranks in phase 2;
+  // dbeta / dgamma are stored divided by world (the gradient-bucket all-reduce sums them over the ranks again)
+  CoopPeer peer;
+  const float* count_dev;  // pooled pixel count written by the forward kernel
+  float* dbeta_out;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -1197,13 +1260,26 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
             float ka = 0.f, kb = 0.f, kc = 0.f, fb = -1.f;
             if (c < p.cout) {
               // totals of the whole layer: s1 = sum g', s2 = inv_std * (sum g'*y - mean * s1) = sum g'*xhat
-              const float s1 = __ldcg(p.bw_s1 + c), s2raw = __ldcg(p.bw_s2 + c);
+              float s1, s2raw, cnt = q.count, inv_w = 1.f;
+              if (q.peer.world > 1) {
+                s1 = 0.f, s2raw = 0.f;
+                for (int r = 0; r < q.peer.world; ++r) {
+                  const float* pt = q.peer.base[r] + q.peer.data_off;
+                  s1 += __ldcv(pt + c), s2raw += __ldcv(pt + q.peer.data_stride + c);
+                }
+                cnt = *q.count_dev, inv_w = 1.f / (float)q.peer.world;
+              } else {
+                s1 = __ldcg(p.bw_s1 + c), s2raw = __ldcg(p.bw_s2 + c);
+              }
               const float mu = q.mean[c], inv = q.invstd[c], fs = p.bw_fscale[c];
               const float s2 = inv * (s2raw - mu * s1);
-              const float inv_m = 1.f / q.count;
+              const float inv_m = 1.f / cnt;
               const float tt = fs * inv * s2 * inv_m;
               ka = fs, kb = -tt, kc = tt * mu - fs * s1 * inv_m, fb = p.bw_fshift[c];
-              if (first_m_tile && q.dgamma_out != nullptr) q.dgamma_out[c] = s2;   // dbeta = s1 is already in place
+              if (first_m_tile) {   // single GPU: dbeta = s1 is already in place (the partial sums went straight into it)
+                if (q.dgamma_out != nullptr) q.dgamma_out[c] = s2 * inv_w;
+                if (q.dbeta_out != nullptr) q.dbeta_out[c] = s1 * inv_w;
+              }
             }
             coef[t] = ka, coef[BLOCK_N + t] = kb, coef[2 * BLOCK_N + t] = kc, coef[3 * BLOCK_N + t] = fb;
           }
@@ -1335,6 +1411,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
           }
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
+        coop_peer_handshake(q.peer, t);  // world > 1: every rank's partial sums are complete and visible
       }
     }
   }
@@ -1582,6 +1659,20 @@ static int num_sms_of_current_device(int* out) {
   return 0;
 }
 
+static int fill_coop_peer(CoopPeer* out, const sseg_coop_peer_t* in, const char* who) {
+  memset(out, 0, sizeof(*out));
+  if (in == nullptr || in->world <= 1) return 0;
+  SSEG_REQUIRE(in->bases != nullptr && in->world <= SSEG_MAX_PEERS && in->rank >= 0 && in->rank < in->world && in->step != nullptr,
+               "%s: bad peer table (world %d rank %d)", who, in->world, in->rank);
+  for (int r = 0; r < in->world; ++r) {
+    SSEG_REQUIRE(in->bases[r] != nullptr, "%s: peer %d not mapped", who, r);
+    out->base[r] = static_cast<float*>(in->bases[r]);
+  }
+  out->world = in->world, out->rank = in->rank;
+  out->data_off = in->data_off, out->data_stride = in->data_stride, out->flag_off = in->flag_off, out->step = in->step;
+  return 0;
+}
+
 static int conv_bn_train_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                               const sseg_act_t* a_out, const sseg_bn_fused_t* bn, int query_only, sseg_stream_t stream_) {
   SSEG_REQUIRE(a_out != nullptr && bn != nullptr, "sseg_conv_bn_train: null argument");
@@ -1635,6 +1726,16 @@ static int conv_bn_train_impl(const sseg_conv_geom_t* g, const void* w_bf16, lon
   q.counter = bn->counter;
   q.num_tiles = tiles;
   q.tiles_per_cta = per_cta;
+  rc = fill_coop_peer(&q.peer, bn->peer, "sseg_conv_bn_train");
+  if (rc) return rc;
+  if (q.peer.world > 1) {
+    SSEG_REQUIRE(bn->count_out != nullptr, "sseg_conv_bn_train: count_out required with peers");
+    SSEG_REQUIRE((bn->tmp_running_mean == nullptr) == (bn->tmp_running_var == nullptr) &&
+                     (bn->tmp_running_mean == nullptr) == (bn->running_iter == nullptr),
+                 "sseg_conv_bn_train: tmp_running_mean / tmp_running_var / running_iter must come together");
+    q.tmp_mean = bn->tmp_running_mean, q.tmp_var = bn->tmp_running_var, q.running_iter = bn->running_iter;
+    q.count_out = bn->count_out;
+  }
   const int grid = ceil_div(tiles, per_cta);  // <= number of SMs: every CTA is resident, the in-kernel barrier is safe
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (block_n == 64) return launch_bn<64, 6>(q, grid, stream);
@@ -1654,7 +1755,8 @@ extern "C" int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_
 static int conv_dgrad_bn_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                               const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
                               const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,
-                              unsigned int* counter, int query_only, sseg_stream_t stream_) {
+                              unsigned int* counter, const sseg_coop_peer_t* peer, const float* count_dev, float* dbeta_out,
+                              int query_only, sseg_stream_t stream_) {
   SSEG_REQUIRE(y != nullptr && dy_out != nullptr && fscale && fshift && mean && invstd && s1 && s2_raw && counter &&
                    count > 1.f,
                "sseg_conv_dgrad_bn: null argument");
@@ -1677,6 +1779,13 @@ static int conv_dgrad_bn_impl(const sseg_conv_geom_t* g, const void* w_bf16, lon
   q.ld_dy = dy_out->ld, q.dy_row_stride = dy_out->row_stride, q.dy_img_stride = dy_out->img_stride;
   q.mean = mean, q.invstd = invstd, q.count = count, q.dgamma_out = dgamma_out, q.counter = counter;
   q.num_tiles = tiles, q.tiles_per_cta = per_cta;
+  rc = fill_coop_peer(&q.peer, peer, "sseg_conv_dgrad_bn");
+  if (rc) return rc;
+  if (q.peer.world > 1) {
+    SSEG_REQUIRE(count_dev != nullptr && dbeta_out != nullptr && dgamma_out != nullptr,
+                 "sseg_conv_dgrad_bn: count_dev / dbeta_out / dgamma_out required with peers");
+    q.count_dev = count_dev, q.dbeta_out = dbeta_out;
+  }
   const int grid = ceil_div(tiles, per_cta);
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   if (block_n == 64) return launch_dgrad_bn<64, 6>(q, grid, stream);
@@ -1686,9 +1795,10 @@ static int conv_dgrad_bn_impl(const sseg_conv_geom_t* g, const void* w_bf16, lon
 extern "C" int sseg_conv_dgrad_bn(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                                   const sseg_act_t* dy_out, const float* fscale, const float* fshift, const float* mean,
                                   const float* invstd, float count, float* s1, float* s2_raw, float* dgamma_out,
-                                  unsigned int* counter, sseg_stream_t stream) {
+                                  unsigned int* counter, const sseg_coop_peer_t* peer, const float* count_dev,
+                                  float* dbeta_out, sseg_stream_t stream) {
   return conv_dgrad_bn_impl(g, w_bf16, w_ld, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2_raw, dgamma_out,
-                            counter, 0, stream);
+                            counter, peer, count_dev, dbeta_out, 0, stream);
 }
 
 extern "C" int sseg_conv_dgrad_bn_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
@@ -1696,7 +1806,7 @@ extern "C" int sseg_conv_dgrad_bn_fits(const sseg_conv_geom_t* g, const void* w_
                                        const float* fshift, const float* mean, const float* invstd, float count, float* s1,
                                        float* s2_raw, float* dgamma_out, unsigned int* counter) {
   return conv_dgrad_bn_impl(g, w_bf16, w_ld, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2_raw, dgamma_out,
-                            counter, 1, nullptr);
+                            counter, nullptr, nullptr, nullptr, 1, nullptr);
 }
 
 // =====================================================================================================

@@ -201,6 +201,15 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
   return rc;
 }
 
+int sseg_bn_running_from_tmp(const float* tmp_mean, const float* tmp_var, const float* running_iter, float* running_mean,
+                             float* running_var, int C, sseg_stream_t st) {
+  SSEG_REQUIRE(tmp_mean && tmp_var && running_iter && running_mean && running_var && C > 0, "sseg_bn_running_from_tmp: null");
+  count_launch(1);
+  return check_cuda(launch_k(bn_running_from_tmp_kernel, dim3((C + 255) / 256), dim3(256), 0, (cudaStream_t)st, tmp_mean,
+                             tmp_var, running_iter, running_mean, running_var, C),
+                    "bn_running_from_tmp_kernel");
+}
+
 int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
                          float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
                          int s2_raw, int C, sseg_stream_t st) {

@@ -43,13 +43,21 @@ class SumTerm(Structure):
     _fields_ = [("x", c_void_p), ("h", c_int), ("w", c_int), ("ld", c_long), ("scale", c_void_p), ("shift", c_void_p)]
 
 
+class CoopPeer(Structure):
+    """sseg_coop_peer_t: the peer arenas the cooperative conv+BN kernels pool their partial sums from (world > 1)."""
+    _fields_ = [("bases", POINTER(c_void_p)), ("world", c_int), ("rank", c_int), ("data_off", c_long), ("data_stride", c_long),
+                ("flag_off", c_long), ("step", c_void_p)]
+
+
 class BnFused(Structure):
     """sseg_bn_fused_t: the BatchNorm half of sseg_conv_bn_train."""
     _fields_ = [("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float), ("momentum", c_float), ("count", c_float),
                 ("stat_sum", c_void_p), ("stat_sqsum", c_void_p), ("counter", c_void_p), ("mean_out", c_void_p),
                 ("invstd_out", c_void_p), ("scale_out", c_void_p), ("shift_out", c_void_p), ("running_mean", c_void_p),
                 ("running_var", c_void_p), ("res", POINTER(Act)), ("rscale", c_void_p), ("rshift", c_void_p),
-                ("chanmul", c_void_p), ("relu", c_int), ("res_after_relu", c_int)]
+                ("chanmul", c_void_p), ("relu", c_int), ("res_after_relu", c_int), ("peer", POINTER(CoopPeer)),
+                ("tmp_running_mean", c_void_p), ("tmp_running_var", c_void_p), ("running_iter", c_void_p),
+                ("count_out", c_void_p)]
 
 
 class SgdChunk(Structure):
@@ -105,7 +113,8 @@ _SIGNATURES = {
     "sseg_conv_bn_train": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(BnFused), _p],
     "sseg_conv_bn_train_fits": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(BnFused)],
     "sseg_conv_dgrad_bn": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), _p, _p, _p, _p, c_float, _p, _p, _p,
-                           _p, _p],
+                           _p, POINTER(CoopPeer), _p, _p, _p],
+    "sseg_bn_running_from_tmp": [_p, _p, _p, _p, _p, c_int, _p],
     "sseg_conv_dgrad_bn_fits": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), _p, _p, _p, _p, c_float, _p, _p,
                                 _p, _p],
     "sseg_conv_igemm_bnbwd": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(Act), _p, _p, _p, _p, _p],

@@ -78,9 +78,26 @@ def conv_igemm_affine(geom, w_bf16, cout, out, scale, shift, relu=RELU_AFTER_ADD
     return out
 
 
+def make_coop_peer(arena, data_off, data_stride, flag_off, step):
+    """sseg_coop_peer_t over a PeerArena (engine/peer.py); keep the returned object alive while it is in use."""
+    p = _C.CoopPeer()
+    p.bases = _C.ctypes.cast(arena.bases, _C.POINTER(_C.c_void_p))
+    p.world, p.rank = arena.world, arena.rank
+    p.data_off, p.data_stride, p.flag_off = int(data_off), int(data_stride), int(flag_off)
+    p.step = _C.ptr(step)
+    p._keep = (arena, step)
+    return p
+
+
+def bn_running_from_tmp(tmp_mean, tmp_var, running_iter, running_mean, running_var):
+    _C.check(_C.lib().sseg_bn_running_from_tmp(_C.ptr(tmp_mean), _C.ptr(tmp_var), _C.ptr(running_iter), _C.ptr(running_mean),
+                                               _C.ptr(running_var), running_mean.numel(), _stream()))
+
+
 def make_bn_fused(gamma, beta, eps, momentum, count, stat_sum, stat_sqsum, counter, mean, invstd, scale, shift,
                   running_mean=None, running_var=None, res=None, rscale=None, rshift=None, chanmul=None, relu=True,
-                  res_after_relu=False):
+                  res_after_relu=False, peer=None, tmp_running_mean=None, tmp_running_var=None, running_iter=None,
+                  count_out=None):
     """sseg_bn_fused_t for conv_bn_train (keep the returned object and the tensors alive while it is in use)."""
     b = _C.BnFused()
     b.gamma, b.beta = _C.ptr(gamma), _C.ptr(beta)
@@ -92,6 +109,10 @@ def make_bn_fused(gamma, beta, eps, momentum, count, stat_sum, stat_sqsum, count
     b.res = _C.ctypes.pointer(b._res_act) if res is not None else None
     b.rscale, b.rshift, b.chanmul = _C.ptr(rscale), _C.ptr(rshift), _C.ptr(chanmul)
     b.relu, b.res_after_relu = int(relu), int(res_after_relu)
+    b._peer = peer
+    b.peer = _C.ctypes.pointer(peer) if peer is not None else None
+    b.tmp_running_mean, b.tmp_running_var = _C.ptr(tmp_running_mean), _C.ptr(tmp_running_var)
+    b.running_iter, b.count_out = _C.ptr(running_iter), _C.ptr(count_out)
     return b
 
 
@@ -115,7 +136,7 @@ def conv_bn_train_fits(geom, w_bf16, cout, y, a_out, bn):
 
 
 def conv_dgrad_bn(geom, w_bf16, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2_raw, dgamma_out, counter,
-                  query=False):
+                  query=False, peer=None, count_dev=None, dbeta_out=None):
     """Data gradient of the consumer conv + the producer layer's whole BN backward in one kernel: only dy_out is written.
     query=True: returns whether the layer fits (no launch)."""
     n_store = (cout + 7) // 8 * 8
@@ -126,7 +147,7 @@ def conv_dgrad_bn(geom, w_bf16, cout, y, dy_out, fscale, fshift, mean, invstd, c
         if rc < 0:
             _C.check(rc)
         return rc == 1
-    _C.check(_C.lib().sseg_conv_dgrad_bn(*args, _stream()))
+    _C.check(_C.lib().sseg_conv_dgrad_bn(*args, peer, _C.ptr(count_dev), _C.ptr(dbeta_out), _stream()))
     return dy_out
 
 

@@ -1126,7 +1126,10 @@ class ConvBNRec:
         layer fits (sseg_conv_bn_train). Returns False to fall back to conv / finalize / apply."""
         P, cw, bns = self.P, self.cw, self.bns
         self.coop = False
-        if not (P.coop_bn and self.mode == ops.BN_TRAIN and self.apply and bns.counter is not None and P.peer is None):
+        sync = self.mode == ops.BN_TRAIN_SYNC and P.peer is not None   # statistics pooled over NVLink inside the kernel
+        if not (P.coop_bn and (self.mode == ops.BN_TRAIN or sync) and self.apply and bns.counter is not None):
+            return False
+        if self.mode == ops.BN_TRAIN and P.peer is not None:
             return False
         if isinstance(self.res, ConvBNRec) and getattr(self.res, "coop", False):
             return False
@@ -1143,13 +1146,23 @@ class ConvBNRec:
             r = self.post_add.tp
         upd = m.track_running_stats and m.running_mean is not None
         st = bns.stats
+        extra = {}
+        if sync:
+            # [sum | sqsum | count] of this layer sit at stats_off in EVERY rank's arena; flags [flag_off, +world)
+            P.sinit[bns.stats_off + 2 * C] = float(self.count)
+            peer = ops.make_coop_peer(P.peer, bns.stats_off, C, bns.flag_off, P.peer_step)
+            extra = dict(peer=peer, count_out=bns.tot[2 * bns.Cp:2 * bns.Cp + 1])
+            if upd:
+                extra.update(tmp_running_mean=m._tmp_running_mean, tmp_running_var=m._tmp_running_var,
+                             running_iter=m._running_iter)
         bn = ops.make_bn_fused(m.weight.detach() if m.weight is not None else None,
                                m.bias.detach() if m.bias is not None else None, m.eps,
                                m.momentum if m.momentum is not None else 0.1, self.count, st[:C], st[C:2 * C], bns.counter,
                                bns.mean[:C], bns.invstd[:C], bns.scale[:C], bns.shift[:C],
-                               running_mean=m.running_mean if upd else None, running_var=m.running_var if upd else None,
+                               running_mean=m.running_mean if (upd and not sync) else None,
+                               running_var=m.running_var if (upd and not sync) else None,
                                res=r, rscale=rs, rshift=rb, chanmul=self.chanmul, relu=self.relu,
-                               res_after_relu=self.post_add is not None)
+                               res_after_relu=self.post_add is not None, **extra)
         geom, wf = self.geom, cw.wf
         if P.dry_run:
             fits = _coop_fits_estimate(n, ho, wo, cw.k, C)
@@ -1162,6 +1175,9 @@ class ConvBNRec:
         P.keep.append(bn)
         P._need_weights(cw)
         P.fwd.append(lambda: ops.conv_bn_train(geom, wf, C, y, a.tp, bn))
+        if sync and upd:   # running_mean / running_var = accumulators / running_iter (batchnorm.py:136-137)
+            P.fwd.append(lambda: ops.bn_running_from_tmp(m._tmp_running_mean, m._tmp_running_var, m._running_iter,
+                                                         m.running_mean, m.running_var))
         return True
 
     def _init_folded(self, n, ho, wo):
@@ -1261,22 +1277,30 @@ class ConvBNRec:
                 prod.fused = True
                 pb = prod.bns
                 if prod.mode == ops.BN_TRAIN_SYNC and P.peer is not None:
-                    s1, s2 = pb.part[:pb.C], pb.part[pb.C:2 * pb.C]
+                    s1, s2 = pb.part[:pb.Cp], pb.part[pb.Cp:2 * pb.Cp]
                 else:
                     s1, s2 = pb.dbeta, pb.s2y
                 py = prod.y
-                coop = (P.coop_bn and prod.mode == ops.BN_TRAIN and P.peer is None and pb.counter_bwd is not None and
-                        prod.cw.O == I)
+                sync = prod.mode == ops.BN_TRAIN_SYNC and P.peer is not None
+                coop = (P.coop_bn and (sync or (prod.mode == ops.BN_TRAIN and P.peer is None)) and
+                        pb.counter_bwd is not None and prod.cw.O == I)
+                kw = {}
                 if coop:
                     # the producer's whole BN backward rides in this data-gradient kernel: dy is written, g never is
                     dyp = torch.empty_like(py)
                     n_, h_, w_, _ = py.shape
-                    args = (gd, wd, I, py, dyp, pb.scale, pb.shift, pb.mean, pb.invstd, prod.count, pb.dbeta, pb.s2y, pb.dgamma,
+                    args = (gd, wd, I, py, dyp, pb.scale, pb.shift, pb.mean, pb.invstd, prod.count, s1, s2, pb.dgamma,
                             pb.counter_bwd)
                     coop = _coop_fits_estimate(n_, h_, w_, cw.k, I) if P.dry_run else ops.conv_dgrad_bn(*args, query=True)
+                if coop and sync:
+                    # partial sums [s1 | s2raw] in this rank's arena, pooled over the ranks inside the kernel; the pooled
+                    # pixel count was left in tot[2*Cp] by the forward kernel; dbeta / dgamma come out divided by world
+                    kw = dict(peer=ops.make_coop_peer(P.peer, pb.part_off, pb.Cp, pb.flag_off + 8, P.peer_step),
+                              count_dev=pb.tot[2 * pb.Cp:2 * pb.Cp + 1], dbeta_out=pb.dbeta)
+                    P.keep.append(kw["peer"])
                 if coop:
                     prod.dy_pre = dyp
-                    P.bwd.append(lambda: ops.conv_dgrad_bn(*args))
+                    P.bwd.append(lambda: ops.conv_dgrad_bn(*args, **kw))
                 else:
                     P.bwd.append(lambda: ops.conv_igemm_bnbwd(gd, wd, I, buf, py, pb.scale, pb.shift, s1, s2))
             else:

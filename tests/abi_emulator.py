@@ -178,6 +178,7 @@ class EmuLib:
         return 1
 
     def sseg_conv_bn_train(self, g, w, w_ld, cout, y, a_out, bn, stream):
+        assert not bool(bn.peer), "peer-memory pooling is not emulated (CUDA IPC)"
         v = _bf(_conv(g, w, w_ld, cout)).float()                      # y as stored
         if y is not None:
             _store(y, v, cout)
@@ -215,8 +216,15 @@ class EmuLib:
         _store(a_out, t, cout)
         return 0
 
+    def sseg_bn_running_from_tmp(self, tm, tv, it, rm, rv, C, stream):
+        i = flat(it, 1, torch.float32)
+        vec(rm, C).copy_(vec(tm, C) / i)
+        vec(rv, C).copy_(vec(tv, C) / i)
+        return 0
+
     def sseg_conv_dgrad_bn(self, g, w, w_ld, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2raw, dgamma,
-                           counter, stream):
+                           counter, peer, count_dev, dbeta_out, stream):
+        assert peer is None, "peer-memory pooling is not emulated (CUDA IPC)"
         gr = _bf(_conv(g, w, w_ld, cout)).float()
         yv = act_view(y).float()[..., :cout]
         fs, fb = vec(fscale, cout), vec(fshift, cout)
