@@ -177,8 +177,12 @@ class EmuLib:
     def sseg_conv_dgrad_bn_fits(self, *a):
         return 1
 
+    @staticmethod
+    def _pool(peer, off, n):
+        """sum over the ranks of the n floats at `off` (4-byte units) inside every rank's arena"""
+        return sum(flat(peer.bases[r] + 4 * off, n, torch.float32).clone() for r in range(peer.world))
+
     def sseg_conv_bn_train(self, g, w, w_ld, cout, y, a_out, bn, stream):
-        assert not bool(bn.peer), "peer-memory pooling is not emulated (CUDA IPC)"
         v = _bf(_conv(g, w, w_ld, cout)).float()                      # y as stored
         if y is not None:
             _store(y, v, cout)
@@ -186,15 +190,30 @@ class EmuLib:
         ssum.add_(v.sum((0, 1, 2)))
         ssq.add_((v * v).sum((0, 1, 2)))
         flat(bn.counter, 1, torch.int32).add_(1)                      # the grid barrier leaves a non-zero counter
-        mean = ssum / bn.count
-        sumvar = ssq - ssum * mean
-        inv = torch.rsqrt((sumvar / bn.count).clamp(min=0) + bn.eps)
+        if bool(bn.peer):   # synchronised branch: pooled over the ranks' arenas, clamp(var, eps), accumulator running stats
+            pr = bn.peer.contents
+            ssum = self._pool(pr, pr.data_off, cout)
+            ssq = self._pool(pr, pr.data_off + pr.data_stride, cout)
+            cnt = self._pool(pr, pr.data_off + 2 * pr.data_stride, 1).item()
+            mean = ssum / cnt
+            sumvar = ssq - ssum * mean
+            inv = torch.rsqrt((sumvar / cnt).clamp(min=bn.eps))
+            flat(bn.count_out, 1, torch.float32).fill_(cnt)
+            if _addr(bn.tmp_running_mean):
+                frac = 1 - bn.momentum
+                vec(bn.tmp_running_mean, cout).mul_(frac).add_(mean)
+                vec(bn.tmp_running_var, cout).mul_(frac).add_(sumvar / (cnt - 1))
+                flat(bn.running_iter, 1, torch.float32).mul_(frac).add_(1)
+        else:
+            mean = ssum / bn.count
+            sumvar = ssq - ssum * mean
+            inv = torch.rsqrt((sumvar / bn.count).clamp(min=0) + bn.eps)
         gm = vec(bn.gamma, cout) if _addr(bn.gamma) else torch.ones(cout)
         bt = vec(bn.beta, cout) if _addr(bn.beta) else torch.zeros(cout)
         sc, sh = gm * inv, bt - mean * gm * inv
         for ptr, val in ((bn.mean_out, mean), (bn.invstd_out, inv), (bn.scale_out, sc), (bn.shift_out, sh)):
             vec(ptr, cout).copy_(val)
-        if _addr(bn.running_mean):
+        if _addr(bn.running_mean) and not bool(bn.peer):
             rm, rv = vec(bn.running_mean, cout), vec(bn.running_var, cout)
             rm.mul_(1 - bn.momentum).add_(bn.momentum * mean)
             rv.mul_(1 - bn.momentum).add_(bn.momentum * sumvar / (bn.count - 1))
@@ -224,7 +243,6 @@ class EmuLib:
 
     def sseg_conv_dgrad_bn(self, g, w, w_ld, cout, y, dy_out, fscale, fshift, mean, invstd, count, s1, s2raw, dgamma,
                            counter, peer, count_dev, dbeta_out, stream):
-        assert peer is None, "peer-memory pooling is not emulated (CUDA IPC)"
         gr = _bf(_conv(g, w, w_ld, cout)).float()
         yv = act_view(y).float()[..., :cout]
         fs, fb = vec(fscale, cout), vec(fshift, cout)
@@ -234,9 +252,16 @@ class EmuLib:
         b.add_((gp * yv).sum((0, 1, 2)))
         flat(counter, 1, torch.int32).add_(1)
         mu, inv = vec(mean, cout), vec(invstd, cout)
+        inv_w = 1.0
+        if peer is not None:   # totals over the ranks; dbeta / dgamma leave divided by world
+            a = self._pool(peer, peer.data_off, cout)
+            b = self._pool(peer, peer.data_off + peer.data_stride, cout)
+            count = flat(count_dev, 1, torch.float32).item()
+            inv_w = 1.0 / peer.world
+            vec(dbeta_out, cout).copy_(a * inv_w)
         s2 = inv * (b - mu * a)
         if _addr(dgamma):
-            vec(dgamma, cout).copy_(s2)
+            vec(dgamma, cout).copy_(s2 * inv_w)
         tt = fs * inv * s2 / count
         _store(dy_out, fs * gp - tt * yv + (tt * mu - fs * a / count), cout)
         return 0
@@ -604,4 +629,48 @@ class EmuLib:
         if relu6:
             y = y.clamp(0.0, 6.0)
         flat(out, y.numel(), torch.bfloat16).view(y.shape).copy_(_bf(y))
+        return 0
+
+    # ---- SyncBN over peer arenas (csrc/peer.cu); the handshake itself (flags over NVLink) has no CPU counterpart
+    class _Peers:
+        def __init__(self, bases, world):
+            self.bases, self.world = [_addr(bases[r]) for r in range(world)], world
+
+    def sseg_peer_step(self, step, stream):
+        flat(step, 1, torch.int32).add_(1)
+        return 0
+
+    def sseg_bn_finalize_peer(self, bases, world, rank, stats_off, flag_off, step, gamma, beta, eps, momentum, update, rm, rv,
+                              tm, tv, it, mean_out, invstd_out, scale, shift, count_out, C, stream):
+        pr = self._Peers(bases, world)
+        s, q = self._pool(pr, stats_off, C), self._pool(pr, stats_off + C, C)
+        cnt = self._pool(pr, stats_off + 2 * C, 1).item()
+        flat(count_out, 1, torch.float32).fill_(cnt)
+        mean = s / cnt
+        sumvar = q - s * mean
+        inv = torch.rsqrt((sumvar / cnt).clamp(min=eps))
+        if update:
+            frac = 1 - momentum
+            i = flat(it, 1, torch.float32)
+            i.mul_(frac).add_(1)
+            vec(tm, C).mul_(frac).add_(mean)
+            vec(tv, C).mul_(frac).add_(sumvar / (cnt - 1))
+            vec(rm, C).copy_(vec(tm, C) / i)
+            vec(rv, C).copy_(vec(tv, C) / i)
+        g = vec(gamma, C) if _addr(gamma) else torch.ones(C)
+        b = vec(beta, C) if _addr(beta) else torch.zeros(C)
+        for ptr, val in ((mean_out, mean), (invstd_out, inv), (scale, g * inv), (shift, b - mean * g * inv)):
+            vec(ptr, C).copy_(val)
+        return 0
+
+    def sseg_bn_bwd_peer_sum(self, bases, world, rank, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean, invstd,
+                             s2_raw, C, stream):
+        pr = self._Peers(bases, world)
+        a, b = self._pool(pr, part_off, C), self._pool(pr, part_off + C, C)
+        if s2_raw:
+            b = vec(invstd, C) * (b - vec(mean, C) * a)
+        vec(s1_tot, C).copy_(a)
+        vec(s2_tot, C).copy_(b)
+        vec(dbeta, C).copy_(a / world)
+        vec(dgamma, C).copy_(b / world)
         return 0

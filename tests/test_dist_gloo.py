@@ -173,6 +173,54 @@ def _worker(rank, world, port, ret):
         cos = torch.dot(fl, gr).item() / (fl.norm() * gr.norm()).item()
         assert cos >= 0.97, cos
         assert (seg.encoder.bn1.running_mean - e["bn1.running_mean"]).abs().max().item() < 1e-4   # accumulator formula
+
+        # ---- the PEER-MEMORY schedule (the default on GPUs: SyncBN statistics pooled out of the ranks' arenas, no
+        #      collective per layer), plain and with the fused conv+BN kernels doing the pooling themselves.  CUDA IPC has
+        #      no CPU counterpart, so every "peer" pointer of the stand-in arena maps this rank's own memory: with the SAME
+        #      batch on both ranks the pooled sums are exactly world x local, i.e. the oracle on the batch concatenated
+        #      with itself.  (The NVLink handshake itself is exercised by tools/dist_check.py on GPUs.)
+        import ctypes
+        from mit_semseg.engine import peer as PEER
+
+        class LocalArena:
+            def __init__(self, nfloats, dist_, device):
+                self.world, self.rank = dist_.get_world_size(), dist_.get_rank()
+                self.floats = torch.zeros(nfloats)
+                self.ints = self.floats.view(torch.int32)
+                self.bases = (ctypes.c_void_p * self.world)(*([self.floats.data_ptr()] * self.world))
+        PEER.PeerArena = LocalArena
+        os.environ["SSEG_PEER_SYNC"] = "1"
+        same = O.synth_batch(2, 64, 64, 8, 300)
+        ref_grads = None
+        for coop in ("0", "1"):
+            os.environ["SSEG_COOP_BN"] = coop
+            seg = _seg(enc_arch, dec_arch, fc)
+            esd, dsd = _load(seg, enc_arch, dec_arch, fc)
+            seg.train()
+            P = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+            assert P.peer is not None and P.world == 2
+            P.dry_run, P.serial = False, True
+            P.load_inputs(same["img_data"], same["seg_label"])
+            P.run_eager()
+            if coop == "1":
+                assert emu.calls.get("sseg_conv_bn_train", 0) > 0 and emu.calls.get("sseg_conv_dgrad_bn", 0) > 0
+            e = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in esd.items()}
+            d = {k: v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k, v in dsd.items()}
+            st = O.BNState(True, sync=True, update_running=True, emulate="bf16")
+            feats = O.encoder_forward(torch.cat([same["img_data"], same["img_data"]]), e, enc_arch, st)
+            lg, lg_ds = O.decoder_forward(feats, d, dec_arch, st, dropout_p=0.0, return_logits=True)
+            lab = same["seg_label"]
+            per = [F.nll_loss(F.log_softmax(lg[sl], 1), lab, ignore_index=-1) + 0.4 * F.nll_loss(F.log_softmax(lg_ds[sl], 1), lab, ignore_index=-1)
+                   for sl in (slice(0, 2), slice(2, 4))]
+            (sum(per) / world).backward()
+            assert abs(P.out[0].item() - per[rank].item()) <= 5e-3 * abs(per[rank].item()), (coop, P.out[0].item(), per[rank].item())
+            names = [("enc." if net is seg.encoder else "dec.") + n for net in (seg.encoder, seg.decoder) for n, _ in net.named_parameters()]
+            fl = torch.cat([P.param_grads()[p].flatten() for net in (seg.encoder, seg.decoder) for p in net.parameters()])
+            gr = torch.cat([(e if n.startswith("enc.") else d)[n[4:]].grad.flatten() for n in names])
+            cos = torch.dot(fl, gr).item() / (fl.norm() * gr.norm()).item()
+            assert cos >= 0.97, (coop, cos)
+            assert (seg.encoder.bn1.running_mean - e["bn1.running_mean"]).abs().max().item() < 1e-4, coop
+        os.environ.pop("SSEG_COOP_BN")
         ret[rank] = True
     finally:
         dist.destroy_process_group()
