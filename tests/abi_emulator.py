@@ -674,3 +674,13 @@ class EmuLib:
         vec(dbeta, C).copy_(a / world)
         vec(dgamma, C).copy_(b / world)
         return 0
+
+    # ---- optimiser
+    def sseg_sgd_step(self, chunks, nchunks, lr, momentum, first_step, stream):
+        from mit_semseg.engine import _C
+        for c in (_C.SgdChunk * nchunks).from_address(_addr(chunks)):
+            p, g, b = flat(c.param, c.n, torch.float32), flat(c.grad, c.n, torch.float32), flat(c.momentum_buf, c.n, torch.float32)
+            d = g + c.weight_decay * p
+            b.copy_(d if first_step else momentum * b + d)
+            p.sub_(lr * b)
+        return 0

@@ -329,3 +329,38 @@ def test_mobilenetv2dilated_inference_matches_the_oracle(emu):
     seg.train()
     with pytest.raises(NotImplementedError, match="eval mode only"):
         PR.SegProgram(seg, (1, 3, 96, 128), training=True, with_grad=True, dry_run=True)
+
+
+def test_fused_sgd_equals_torch_sgd(emu, monkeypatch):
+    """engine/optim.py::FusedSGD (one multi-tensor launch over a chunk table) against torch.optim.SGD - train.py's optimiser
+    (train.py:115-127: two parameter groups, weight decay only on conv weights) - over three steps with changing
+    gradients, including train.py's adjust_learning_rate rewriting group['lr']."""
+    import types
+    from mit_semseg.engine.optim import FusedSGD
+    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 3, 3, 3), (64,), (64,), (150, 512, 1, 1), (150,), (70001,)]     # the last one spans two chunks, not x4
+    pa = [nn.Parameter(torch.randn(s, generator=g)) for s in shapes]
+    pb = [nn.Parameter(p.detach().clone()) for p in pa]
+
+    def groups(ps):
+        return [{"params": [p for p in ps if p.dim() > 1]}, {"params": [p for p in ps if p.dim() <= 1], "weight_decay": 0.0}]
+    oa = FusedSGD(groups(pa), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    ob = torch.optim.SGD(groups(pb), lr=0.02, momentum=0.9, weight_decay=1e-4)
+    grads = [torch.empty_like(p) for p in pa]          # static gradient buffers, like the engine's
+    for p, gr in zip(pa, grads):
+        p.grad = gr
+    for step in range(3):
+        for p, q, gr in zip(pa, pb, grads):
+            gr.copy_(torch.randn(p.shape, generator=g))
+            q.grad = gr.clone()
+        if step == 2:
+            for o in (oa, ob):
+                for grp in o.param_groups:
+                    grp["lr"] = 0.01
+        oa.step()
+        ob.step()
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=1e-6, atol=1e-7)
+    assert emu.calls["sseg_sgd_step"] == 6             # one launch per parameter group and step
