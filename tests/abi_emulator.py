@@ -271,6 +271,21 @@ class EmuLib:
         from mit_semseg.engine import _C
         return (_C.WeightDesc * n).from_address(_addr(table))
 
+    def sseg_prep_conv_weight(self, w, O, I, T, wf, fwd_ld, wd, dgrad_ld, o_pad, stream):
+        wt = flat(w, O * I * T, torch.float32).view(O, I, T)
+        if _addr(wf):
+            flat(wf, (O - 1) * fwd_ld + T * I, torch.bfloat16).as_strided((O, T, I), (fwd_ld, I, 1)).copy_(wt.permute(0, 2, 1))
+        if _addr(wd):
+            flat(wd, (I - 1) * dgrad_ld + (T - 1) * o_pad + O, torch.bfloat16).as_strided((I, T, O), (dgrad_ld, o_pad, 1)).copy_(
+                wt.permute(1, 2, 0))
+        return 0
+
+    def sseg_grad_to_oihw(self, g, g_ld, O, I, T, out, scale, accumulate, stream):
+        gs = flat(g, (O - 1) * g_ld + T * I, torch.float32).as_strided((O, T, I), (g_ld, I, 1)).permute(0, 2, 1) * scale
+        o = flat(out, O * I * T, torch.float32).view(O, I, T)
+        o.copy_(o + gs if accumulate else gs)
+        return 0
+
     def sseg_prep_conv_weights_batched(self, table, n, tiles, stream):
         for d in self._descs(table, n):
             w = flat(d.w, d.O * d.I * d.T, torch.float32).view(d.O, d.I, d.T)
