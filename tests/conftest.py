@@ -61,6 +61,8 @@ def _gpu_tests_on_the_emulator(request, monkeypatch):
     monkeypatch.setattr(torch, "Generator", _CpuGenerator)
     import types
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
     monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
     monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))

@@ -312,3 +312,9 @@ def test_upernet_resnet50_backward_wiring_and_train_loss():
     assert max(rels.values()) <= 0.12 and statistics.median(rels.values()) <= 0.05, max(rels, key=rels.get)
     loss, ref, rels = run(bn_eval=False)
     assert abs(loss - ref) <= 5e-3 * abs(ref)
+
+
+def test_graft_entry_smoke():
+    """The driver's smoke entry point (one small training step checked against the oracle) as part of the suite."""
+    import __graft_entry__ as ge
+    ge.smoke()
