@@ -47,6 +47,17 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // Kernel launch with the programmatic-stream-serialization attribute (PDL) unless disabled (SSEG_PDL=0 in the
 // environment or sseg_set_pdl(0)); then a plain launch.
 bool pdl_enabled();
+#ifdef __CUSIM__
+// CPU simulator build (tests/cusim): the same kernels run as OS threads; a cooperative launch runs all CTAs concurrently.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
+  return static_cast<cudaError_t>(::cusim::launch(grid, block, smem, false, [=]() { kernel(args...); }));
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
+  return static_cast<cudaError_t>(::cusim::launch(grid, block, smem, true, [=]() { kernel(args...); }));
+}
+#else
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
                             Args&&... args) {
@@ -75,5 +86,6 @@ inline cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, 
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+#endif  // __CUSIM__
 
 }  // namespace sseg

@@ -75,7 +75,7 @@ struct IgemmSmem {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constant__ IgemmParams p) {
   using L = IgemmSmem<BLOCK_N, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
+  SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
       }
     }
     if (!p.out_f32) {
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps only: the staged tile is complete
+      bar_sync_epilogue();  // the 4 epilogue warps only: the staged tile is complete
       const int t = threadIdx.x - 64;
       if (do_stats) {
         // thread = one pair of adjacent columns x one slab of rows; fp32 sums of the bf16 values as stored
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
           for (int pass = 0; pass < kPasses; ++pass)
             *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = q[pass];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bar_sync_epilogue();
         constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
         const int cp = t % kPairs, slab = t / kPairs;
         const int col = n0 + cp * 2;
@@ -360,7 +360,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const __grid_constant__ IgemmParams p,
                                                                           const int num_tiles) {
   using L = IgemmPersistSmem<BLOCK_N, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
+  SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
       }
     }
     tc_fence_before();
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // the 4 epilogue warps: all tcgen05.ld of this tile are done
+    bar_sync_epilogue();  // the 4 epilogue warps: all tcgen05.ld of this tile are done
     if (threadIdx.x == 64) mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may refill this accumulator buffer
     if (!p.out_f32) {
       const int t = threadIdx.x - 64;
@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
           for (int pass = 0; pass < kPasses; ++pass)
             *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = q[pass];
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bar_sync_epilogue();
         constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
         const int cp = t % kPairs, slab = t / kPairs;
         const int col = n0 + cp * 2;
@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
         }
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile fully consumed before the next tile overwrites it
+    bar_sync_epilogue();  // staging tile fully consumed before the next tile overwrites it
     }  // tile loop
   }
 
@@ -717,27 +717,19 @@ struct CoopPeer {
   long flag_off;
   const int* step;
 };
-__device__ __forceinline__ void coop_st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int coop_ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // called by the 128 epilogue threads of every CTA right after the local grid barrier; t = epilogue thread index
 __device__ __forceinline__ void coop_peer_handshake(const CoopPeer& pr, int t) {
   if (pr.world <= 1) return;
   const int step = *pr.step;
   if (blockIdx.x == 0 && t < pr.world) {
     __threadfence_system();
-    coop_st_release_sys(reinterpret_cast<int*>(pr.base[t]) + pr.flag_off + pr.rank, step);
+    st_release_sys(reinterpret_cast<int*>(pr.base[t]) + pr.flag_off + pr.rank, step);
   }
   if (t < pr.world) {
     const int* mine = reinterpret_cast<const int*>(pr.base[pr.rank]) + pr.flag_off + t;
-    while (coop_ld_acquire_sys(mine) < step) __nanosleep(32);
+    while (ld_acquire_sys(mine) < step) __nanosleep(32);
   }
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+  bar_sync_epilogue();
 }
 
 struct IgemmBnParams {
@@ -778,17 +770,11 @@ struct IgemmBnSmem {
   static constexpr int kMaxTiles = 512 / BLOCK_N;  // accumulators that fit the SM's tensor memory
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_constant__ IgemmBnParams q) {
   using L = IgemmBnSmem<BLOCK_N, STAGES>;
   const IgemmParams& p = q.g;
-  extern __shared__ uint8_t smem_raw[];
+  SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -945,7 +931,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
             }
             coef[t] = sc, coef[BLOCK_N + t] = sh, coef[2 * BLOCK_N + t] = rs, coef[3 * BLOCK_N + t] = rb;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          bar_sync_epilogue();
           tc_fence_after();
         } else {
           mbar_wait(&tmem_full_bar[it], 0);
@@ -1019,7 +1005,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
           }
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the staged tile is complete
+        bar_sync_epilogue();  // the staged tile is complete
 
         if (!phase2) {
           // statistics of the values as stored: thread = one pair of adjacent columns x one slab of rows
@@ -1052,18 +1038,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile (and coefficients) free for the next tile
+        bar_sync_epilogue();  // staging tile (and coefficients) free for the next tile
       }
       if (!phase2) {
         // ---- grid barrier: the layer's statistics are complete once every CTA has arrived
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bar_sync_epilogue();
         if (t == 0) {
           atomicAdd(q.counter, 1u);
           while (ld_acquire_gpu(q.counter) < gridDim.x) {
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bar_sync_epilogue();
         coop_peer_handshake(q.peer, t);  // world > 1: every rank's partial sums are complete and visible
       }
     }
@@ -1136,7 +1122,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __grid_constant__ IgemmDgradBnParams q) {
   using L = IgemmDgradBnSmem<BLOCK_N, STAGES>;
   const IgemmParams& p = q.g;
-  extern __shared__ uint8_t smem_raw[];
+  SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -1283,7 +1269,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
             }
             coef[t] = ka, coef[BLOCK_N + t] = kb, coef[2 * BLOCK_N + t] = kc, coef[3 * BLOCK_N + t] = fb;
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          bar_sync_epilogue();
           tc_fence_after();
         } else {
           mbar_wait(&tmem_full_bar[it], 0);
@@ -1341,7 +1327,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
           }
         }
         tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the staged tile is complete
+        bar_sync_epilogue();  // the staged tile is complete
 
         if (!phase2) {
           // the producer's saved conv output y, same tile geometry, copied with coalesced 16-byte loads
@@ -1361,7 +1347,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
             for (int pass = 0; pass < kPasses; ++pass)
               *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = u[pass];
           }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          bar_sync_epilogue();
           constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
           const int cp = t % kPairs, slab = t / kPairs;
           const int col = n0 + cp * 2;
@@ -1399,18 +1385,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
             }
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // staging tile (and coefficients) free for the next tile
+        bar_sync_epilogue();  // staging tile (and coefficients) free for the next tile
       }
       if (!phase2) {
         // ---- grid barrier: the layer's statistics are complete once every CTA has arrived
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bar_sync_epilogue();
         if (t == 0) {
           atomicAdd(q.counter, 1u);
           while (ld_acquire_gpu(q.counter) < gridDim.x) {
           }
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        bar_sync_epilogue();
         coop_peer_handshake(q.peer, t);  // world > 1: every rank's partial sums are complete and visible
       }
     }
@@ -1857,7 +1843,7 @@ struct WgradSmem {
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constant__ WgradParams p) {
   using L = WgradSmem<BLOCK_N, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
+  SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;

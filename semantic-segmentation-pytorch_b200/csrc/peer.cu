@@ -21,15 +21,6 @@ struct PeerTable {
   int world, rank;
 };
 
-__device__ __forceinline__ void st_release_sys(int* p, int v) {
-  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ int ld_acquire_sys(const int* p) {
-  int v;
-  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
 // All threads of every block call this. Block 0 publishes; every block waits for all peers.
 __device__ __forceinline__ void peer_handshake(const PeerTable& pt, long flag_off, int step) {
   if (blockIdx.x == 0 && threadIdx.x < pt.world) {

@@ -6,6 +6,12 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 
+#ifdef __CUSIM__
+// CPU functional model of the instruction wrappers (tests/cusim: the same kernel sources run as OS threads in the CPU
+// test suite); the descriptor encoders at the end of this file are shared, the model decodes what they produce.
+#include "cusim_ptx.h"
+namespace sseg {
+#else
 namespace sseg {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -36,6 +42,27 @@ __device__ __forceinline__ void pdl_sync() {
   pdl_wait();
   pdl_launch_dependents();
 #endif
+}
+
+// Dynamic shared memory of the CTA (a macro so that the CPU simulator can substitute its own per-CTA block)
+#define SSEG_DYN_SMEM(name) extern __shared__ uint8_t name[]
+
+// Named barrier 1 over the 4 epilogue warps (128 threads) of the GEMM kernels
+__device__ __forceinline__ void bar_sync_epilogue() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// ---------------------------------------------------------------- cross-CTA / cross-GPU flags
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // ---------------------------------------------------------------- mbarrier
@@ -147,6 +174,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+#endif  // __CUSIM__
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout, version 1 = Blackwell):

@@ -14,7 +14,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
-EMULATE = os.environ.get("SSEG_GPU_TESTS_ON_EMULATOR", "0") == "1"
+# "1": the Python restatement of the C ABI (tests/abi_emulator.py); "sim": the REAL kernel sources compiled for the CPU
+# simulator (tests/cusim: OS thread per CUDA thread, functional TMA / mbarrier / tcgen05 models)
+EMULATE_MODE = os.environ.get("SSEG_GPU_TESTS_ON_EMULATOR", "0")
+EMULATE = EMULATE_MODE in ("1", "sim")
+_SIM_LIB = None
+
+
+def sim_lib():
+    """libsseg_sim.so (built on first use by tests/cusim/build_sim.sh) behind the same ctypes declarations as the product."""
+    global _SIM_LIB
+    if _SIM_LIB is None:
+        import ctypes
+        import subprocess
+        from mit_semseg.engine import _C
+        out = subprocess.run([os.path.join(ROOT, "tests", "cusim", "build_sim.sh")], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr[-3000:]
+        L = ctypes.CDLL(out.stdout.strip().splitlines()[-1])
+        _C._declare(L)
+        _SIM_LIB = L
+    return _SIM_LIB
 
 
 def pytest_collection_modifyitems(config, items):
@@ -40,7 +59,7 @@ def _gpu_tests_on_the_emulator(request, monkeypatch):
     import torch.nn as nn
     from abi_emulator import EmuLib
     from mit_semseg.engine import _C, ops
-    lib = EmuLib()
+    lib = sim_lib() if EMULATE_MODE == "sim" else EmuLib()
     monkeypatch.setattr(_C, "lib", lambda: lib)
     monkeypatch.setattr(ops, "_stream", lambda: None)
 

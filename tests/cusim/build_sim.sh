@@ -1,0 +1,25 @@
+#!/bin/bash
+# Builds tests/cusim/_build/libsseg_sim.so: the product's .cu sources compiled by g++ against the cusim model (no nvcc, no GPU).
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+CSRC="$HERE/../../semantic-segmentation-pytorch_b200/csrc"
+OUT="$HERE/_build"
+CUDA_INC="${CUDA_HOME:-/usr/local/cuda}/include"
+mkdir -p "$OUT"
+FLAGS="-O2 -g -fno-strict-aliasing -std=c++17 -fPIC -pthread -w -I$HERE -I$CUDA_INC -include $HERE/cusim.h"
+pids=()
+for f in "$CSRC"/*.cu; do
+  o="$OUT/$(basename "${f%.cu}").o"
+  if [ ! -f "$o" ] || [ "$f" -nt "$o" ] || [ -n "$(find "$CSRC" "$HERE" -maxdepth 1 \( -name '*.h' -o -name '*.cuh' \) -newer "$o")" ]; then
+    g++ $FLAGS -x c++ -c "$f" -o "$o" &
+    pids+=($!)
+  fi
+done
+o="$OUT/cusim_runtime.o"
+if [ ! -f "$o" ] || [ "$HERE/cusim_runtime.cpp" -nt "$o" ] || [ "$HERE/cusim.h" -nt "$o" ] || [ "$HERE/cusim_ptx.h" -nt "$o" ]; then
+  g++ $FLAGS -c "$HERE/cusim_runtime.cpp" -o "$o" &
+  pids+=($!)
+fi
+for p in "${pids[@]}"; do wait "$p"; done
+g++ -shared -pthread -Wl,-Bsymbolic -o "$OUT/libsseg_sim.so" "$OUT"/*.o
+echo "$OUT/libsseg_sim.so"

@@ -1,0 +1,565 @@
+// cusim runtime: the executor (OS thread per CUDA thread), barriers, mbarrier / TMA / tensor-memory / tcgen05 models and
+// the handful of CUDA runtime entry points the library's host code calls. TEST INFRASTRUCTURE ONLY (see cusim.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <array>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "cusim.h"
+#include "cusim_ptx.h"
+
+namespace cusim {
+
+thread_local ThreadCtx tl;
+
+struct Abort {};
+
+struct Bar {
+  int count = 0;
+  unsigned gen = 0;
+};
+
+struct PendingMma {
+  uint32_t d;
+  uint64_t da, db;
+  uint32_t idesc, acc;
+  int kind;
+};
+
+struct Cta {
+  std::mutex mu;
+  std::condition_variable cv;
+  int nthreads = 0, alive = 0;
+  Bar sync;
+  Bar named[16];
+  std::vector<Bar> warp_bar;
+  std::vector<std::array<uint64_t, 32>> warp_slot;
+  uint8_t* smem = nullptr;
+  size_t smem_bytes = 0;
+  float* tmem = nullptr;  // [128][512]
+  uint32_t tmem_next = 0;
+  std::vector<PendingMma> pending;
+  int index = 0;
+};
+
+static std::atomic<bool> g_abort{false};
+static std::mutex g_msg_mu;
+static std::string g_abort_msg;
+static std::mutex g_atomic_mu;
+static cudaError_t g_last_error = cudaSuccess;
+
+static double timeout_seconds() {
+  const char* e = getenv("CUSIM_TIMEOUT");
+  return e ? atof(e) : 60.0;
+}
+
+static void raise_abort(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  {
+    std::lock_guard<std::mutex> lk(g_msg_mu);
+    if (!g_abort.load()) g_abort_msg = buf;
+  }
+  g_abort.store(true);
+  throw Abort();
+}
+
+#define CUSIM_CHECK(cond, ...)                 \
+  do {                                         \
+    if (!(cond)) raise_abort(__VA_ARGS__);     \
+  } while (0)
+
+template <typename Pred>
+static void wait_until(Cta* c, std::unique_lock<std::mutex>& lk, Pred pred, const char* what, long detail) {
+  const auto t0 = std::chrono::steady_clock::now();
+  const double limit = timeout_seconds();
+  while (!pred()) {
+    if (g_abort.load()) throw Abort();
+    c->cv.wait_for(lk, std::chrono::milliseconds(20));
+    if (pred()) break;
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (dt > limit) {
+      lk.unlock();
+      raise_abort("deadlock: CTA %d thread %d waited %.0f s on %s (%ld)", c->index, tl.linear_tid, dt, what, detail);
+    }
+  }
+}
+
+static void bar_arrive_wait(Cta* c, Bar& b, int expected, const char* what, long detail) {
+  std::unique_lock<std::mutex> lk(c->mu);
+  const unsigned g = b.gen;
+  if (++b.count >= expected) {
+    b.count = 0;
+    b.gen++;
+    c->cv.notify_all();
+    return;
+  }
+  wait_until(c, lk, [&] { return b.gen != g; }, what, detail);
+}
+
+void syncthreads() {
+  Cta* c = tl.cta;
+  std::unique_lock<std::mutex> lk(c->mu);
+  Bar& b = c->sync;
+  const unsigned g = b.gen;
+  if (++b.count >= c->alive) {
+    b.count = 0;
+    b.gen++;
+    c->cv.notify_all();
+    return;
+  }
+  wait_until(c, lk, [&] { return b.gen != g; }, "__syncthreads", b.count);
+}
+
+void named_barrier(int id, int count) { bar_arrive_wait(tl.cta, tl.cta->named[id & 15], count, "bar.sync id", id); }
+
+void syncwarp() {
+  Cta* c = tl.cta;
+  const int w = tl.linear_tid >> 5;
+  const int in_warp = std::min(32, c->nthreads - w * 32);
+  bar_arrive_wait(c, c->warp_bar[w], in_warp, "__syncwarp / shuffle of warp", w);
+}
+
+uint64_t warp_exchange(uint64_t v, int src_lane) {
+  Cta* c = tl.cta;
+  const int w = tl.linear_tid >> 5, lane = tl.linear_tid & 31;
+  c->warp_slot[w][lane] = v;
+  syncwarp();
+  const uint64_t r = c->warp_slot[w][src_lane];
+  syncwarp();
+  return r;
+}
+
+uint8_t* dyn_smem() { return tl.cta->smem; }
+void atomic_lock() { g_atomic_mu.lock(); }
+void atomic_unlock() { g_atomic_mu.unlock(); }
+
+void spin_pause() {
+  if (g_abort.load()) throw Abort();
+  static thread_local std::chrono::steady_clock::time_point t0;
+  static thread_local long spins = 0;
+  if (spins++ == 0) t0 = std::chrono::steady_clock::now();
+  if ((spins & 1023) == 0) {
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (dt > timeout_seconds()) {
+      spins = 0;
+      raise_abort("deadlock: CTA %d thread %d polled a global flag for %.0f s", tl.cta ? tl.cta->index : -1, tl.linear_tid, dt);
+    }
+  }
+  sched_yield();
+}
+
+uint32_t smem_handle(const void* p) {
+  Cta* c = tl.cta;
+  const uint8_t* q = static_cast<const uint8_t*>(p);
+  if (q >= c->smem && q < c->smem + c->smem_bytes) return static_cast<uint32_t>(q - c->smem);
+  return 0x40000u | (static_cast<uint32_t>(reinterpret_cast<uintptr_t>(p)) & 0xFFF0u);  // static shared: not addressable by descriptors
+}
+
+static uint8_t* smem_ptr(Cta* c, uint32_t handle, uint32_t bytes, const char* who) {
+  CUSIM_CHECK((size_t)handle + bytes <= c->smem_bytes, "%s: shared-memory address 0x%x (+%u) outside the CTA's %zu bytes", who, handle,
+              bytes, c->smem_bytes);
+  return c->smem + handle;
+}
+
+// ---------------------------------------------------------------------------------------------------------- mbarrier
+struct MBar {
+  int32_t tx;
+  int16_t pending;
+  uint8_t expected;
+  uint8_t phase;
+};
+static_assert(sizeof(MBar) == 8, "mbarrier word");
+
+static void mbar_settle(Cta* c, MBar* b) {
+  if (b->pending <= 0 && b->tx == 0) {
+    b->phase ^= 1;
+    b->pending = b->expected;
+    c->cv.notify_all();
+  }
+}
+
+void mbar_init(uint64_t* bar, uint32_t count) {
+  Cta* c = tl.cta;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MBar* b = reinterpret_cast<MBar*>(bar);
+  b->tx = 0, b->pending = (int16_t)count, b->expected = (uint8_t)count, b->phase = 0;
+}
+
+static void mbar_arrive_on(Cta* c, uint64_t* bar, uint32_t tx_expect) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  MBar* b = reinterpret_cast<MBar*>(bar);
+  b->tx += (int32_t)tx_expect;
+  b->pending -= 1;
+  mbar_settle(c, b);
+}
+void mbar_arrive(uint64_t* bar, uint32_t tx_expect) { mbar_arrive_on(tl.cta, bar, tx_expect); }
+
+void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
+  Cta* c = tl.cta;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MBar* b = reinterpret_cast<MBar*>(bar);
+  b->tx -= (int32_t)bytes;
+  mbar_settle(c, b);
+}
+
+bool mbar_test(uint64_t* bar, uint32_t parity) {
+  Cta* c = tl.cta;
+  std::lock_guard<std::mutex> lk(c->mu);
+  return reinterpret_cast<MBar*>(bar)->phase != (parity & 1);
+}
+
+void mbar_wait(uint64_t* bar, uint32_t parity) {
+  Cta* c = tl.cta;
+  std::unique_lock<std::mutex> lk(c->mu);
+  MBar* b = reinterpret_cast<MBar*>(bar);
+  wait_until(c, lk, [&] { return b->phase != (parity & 1); }, "mbarrier (smem offset) parity",
+             (long)(reinterpret_cast<uint8_t*>(bar) - c->smem) * 10 + (parity & 1));
+}
+
+// ---------------------------------------------------------------------------------------------------------- TMA
+struct SimTmap {
+  uint64_t magic;
+  uint8_t* ptr;
+  uint32_t elem, rank;
+  uint64_t dims[4];
+  uint64_t strides[3];  // bytes, dims 1..3
+  uint32_t box[4];
+  uint32_t swizzle;
+};
+static_assert(sizeof(SimTmap) <= sizeof(CUtensorMap), "SimTmap must fit the opaque tensor map");
+static const uint64_t kTmapMagic = 0x50414D5453554Cull;
+
+static inline uintptr_t swz128(uintptr_t a) { return a ^ (((a >> 7) & 7) << 4); }
+
+void tma_load(void* smem_dst, const void* tmap, uint64_t* bar, int rank, const int* coords) {
+  Cta* c = tl.cta;
+  SimTmap m;
+  memcpy(&m, tmap, sizeof(m));
+  CUSIM_CHECK(m.magic == kTmapMagic, "TMA: tensor map was not produced by cuTensorMapEncodeTiled");
+  CUSIM_CHECK((int)m.rank == rank, "TMA: %dd load through a rank-%u tensor map", rank, m.rank);
+  uint8_t* dst = static_cast<uint8_t*>(smem_dst);
+  CUSIM_CHECK(dst >= c->smem && dst < c->smem + c->smem_bytes, "TMA: destination is not in dynamic shared memory");
+  CUSIM_CHECK(((dst - c->smem) & 1023) == 0, "TMA: SWIZZLE_128B destination offset 0x%lx is not 1024-byte aligned", (long)(dst - c->smem));
+  uint32_t box[4] = {1, 1, 1, 1};
+  for (int d = 0; d < rank; ++d) box[d] = m.box[d];
+  const size_t bytes = (size_t)box[0] * box[1] * box[2] * box[3] * m.elem;
+  CUSIM_CHECK((size_t)(dst - c->smem) + bytes <= c->smem_bytes, "TMA: box of %zu bytes overruns shared memory", bytes);
+  const size_t row_bytes = (size_t)box[0] * m.elem;
+  size_t off = 0;
+  for (uint32_t i3 = 0; i3 < box[3]; ++i3)
+    for (uint32_t i2 = 0; i2 < box[2]; ++i2)
+      for (uint32_t i1 = 0; i1 < box[1]; ++i1) {
+        long g[4] = {0, 0, 0, 0};
+        const uint32_t idx[4] = {0, i1, i2, i3};
+        bool outer_ok = true;
+        for (int d = 1; d < rank; ++d) {
+          g[d] = (long)coords[d] + idx[d];
+          if (g[d] < 0 || g[d] >= (long)m.dims[d]) outer_ok = false;
+        }
+        const uint8_t* src = m.ptr;
+        if (outer_ok)
+          for (int d = 1; d < rank; ++d) src += (size_t)g[d] * m.strides[d - 1];
+        for (uint32_t i0 = 0; i0 < box[0]; ++i0, off += m.elem) {
+          const long g0 = (long)coords[0] + i0;
+          uint8_t* out = c->smem + swz128((uintptr_t)(dst - c->smem) + off);
+          if (outer_ok && g0 >= 0 && g0 < (long)m.dims[0]) memcpy(out, src + (size_t)g0 * m.elem, m.elem);
+          else memset(out, 0, m.elem);
+        }
+        (void)row_bytes;
+      }
+  mbar_complete_tx(bar, (uint32_t)bytes);
+}
+
+// ---------------------------------------------------------------------------------------------------------- tensor memory
+void tmem_alloc(uint32_t* smem_result, uint32_t ncols) {
+  Cta* c = tl.cta;
+  if ((tl.linear_tid & 31) != 0) return;  // .sync.aligned: the whole warp executes it, one lane does the bookkeeping
+  std::unique_lock<std::mutex> lk(c->mu);
+  if (c->tmem_next + ncols > 512) {
+    lk.unlock();
+    raise_abort("tcgen05.alloc: %u columns requested with %u already allocated (512 per SM)", ncols, c->tmem_next);
+  }
+  *smem_result = c->tmem_next;  // lane 0, column offset
+  c->tmem_next += ncols;
+}
+void tmem_dealloc(uint32_t, uint32_t) {}
+
+static inline float bf16_bits_to_float(uint16_t h) {
+  uint32_t u = (uint32_t)h << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+static inline float tf32_of(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u &= 0xFFFFE000u;  // 10-bit mantissa (truncation)
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// Gather one operand into a dense [rows][K] float matrix.
+static void gather_operand(Cta* c, uint64_t desc, int rows, int kelems, int esize, int mn_major, int kind, std::vector<float>& out) {
+  const uint32_t start = (uint32_t)(desc & 0x3FFF) << 4;
+  const uint32_t lbo = (uint32_t)((desc >> 16) & 0x3FFF) << 4;
+  const uint32_t sbo = (uint32_t)((desc >> 32) & 0x3FFF) << 4;
+  CUSIM_CHECK(((desc >> 61) & 7) == 2, "tcgen05.mma: smem descriptor layout %d, only SWIZZLE_128B (2) is modelled", (int)((desc >> 61) & 7));
+  CUSIM_CHECK(((desc >> 46) & 3) == 1, "tcgen05.mma: smem descriptor version %d, Blackwell needs 1", (int)((desc >> 46) & 3));
+  out.resize((size_t)rows * kelems);
+  for (int r = 0; r < rows; ++r)
+    for (int k = 0; k < kelems; ++k) {
+      uint32_t addr;
+      if (!mn_major) {
+        // K-major: 8-row x 128-byte atoms, SBO between 8-row groups (LBO unused for a 32-byte K extent)
+        addr = start + (uint32_t)(r & 7) * 128 + (uint32_t)(r >> 3) * sbo + (uint32_t)k * esize;
+      } else {
+        // MN-major: (64 MN elements = 128 B) x 8 K atoms; LBO between 64-element MN groups, SBO between 8-K groups
+        CUSIM_CHECK(esize == 2, "tcgen05.mma: MN-major operands are modelled for 16-bit types only");
+        addr = start + (uint32_t)(r >> 6) * lbo + (uint32_t)(k >> 3) * sbo + (uint32_t)(k & 7) * 128 + (uint32_t)(r & 63) * 2;
+      }
+      const uint8_t* p = smem_ptr(c, (uint32_t)swz128(addr), esize, "tcgen05.mma operand");
+      float v;
+      if (esize == 2) {
+        uint16_t h;
+        memcpy(&h, p, 2);
+        v = bf16_bits_to_float(h);
+      } else {
+        memcpy(&v, p, 4);
+        if (kind == 1) v = tf32_of(v);
+      }
+      out[(size_t)r * kelems + k] = v;
+    }
+}
+
+static void execute_mma(Cta* c, const PendingMma& q) {
+  const uint32_t i = q.idesc;
+  const int c_fmt = (i >> 4) & 3, a_fmt = (i >> 7) & 7, b_fmt = (i >> 10) & 7;
+  const int a_mn = (i >> 15) & 1, b_mn = (i >> 16) & 1;
+  const int N = (int)((i >> 17) & 0x3F) << 3, M = (int)((i >> 24) & 0x1F) << 4;
+  CUSIM_CHECK(c_fmt == 1, "tcgen05.mma: accumulator format %d, expected F32 (1)", c_fmt);
+  CUSIM_CHECK(a_fmt == b_fmt, "tcgen05.mma: A format %d != B format %d", a_fmt, b_fmt);
+  CUSIM_CHECK(q.kind == 0 ? a_fmt == 1 : a_fmt == 2, "tcgen05.mma kind %d with operand format %d", q.kind, a_fmt);
+  CUSIM_CHECK(M == 128, "tcgen05.mma: M = %d, only the M = 128 cta_group::1 layout is modelled", M);
+  CUSIM_CHECK(N >= 16 && N <= 256 && N % 16 == 0, "tcgen05.mma: N = %d is not legal for M = 128", N);
+  const int esize = q.kind == 0 ? 2 : 4, K = 32 / esize;
+  const uint32_t lane = q.d >> 16, col = q.d & 0xFFFF;
+  CUSIM_CHECK(lane == 0, "tcgen05.mma: accumulator lane base %u (M = 128 uses all lanes, base 0)", lane);
+  CUSIM_CHECK(col + N <= 512 && col + N <= c->tmem_next, "tcgen05.mma: accumulator columns [%u, %u) outside the allocation (%u columns)",
+              col, col + N, c->tmem_next);
+  static thread_local std::vector<float> A, B;
+  gather_operand(c, q.da, M, K, esize, a_mn, q.kind, A);
+  gather_operand(c, q.db, N, K, esize, b_mn, q.kind, B);
+  for (int m = 0; m < M; ++m) {
+    float* drow = c->tmem + (size_t)m * 512 + col;
+    const float* a = &A[(size_t)m * K];
+    for (int n = 0; n < N; ++n) {
+      const float* b = &B[(size_t)n * K];
+      float acc = 0.f;
+      for (int k = 0; k < K; ++k) acc += a[k] * b[k];
+      drow[n] = q.acc ? drow[n] + acc : acc;
+    }
+  }
+}
+
+void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate, int kind) {
+  tl.cta->pending.push_back(PendingMma{tmem_d, da, db, idesc, accumulate, kind});  // only the single MMA thread issues
+}
+
+void umma_commit(uint64_t* bar) {
+  Cta* c = tl.cta;
+  for (const PendingMma& q : c->pending) execute_mma(c, q);
+  c->pending.clear();
+  mbar_arrive_on(c, bar, 0);
+}
+
+void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
+  Cta* c = tl.cta;
+  const uint32_t lane_base = taddr >> 16, col = taddr & 0xFFFF;
+  const int warp = tl.linear_tid >> 5, lane = tl.linear_tid & 31;
+  CUSIM_CHECK(lane_base == (uint32_t)(warp & 3) * 32, "tcgen05.ld: warp %d may only read lanes [%d, +32), address names lane %u", warp,
+              (warp & 3) * 32, lane_base);
+  CUSIM_CHECK(col + 32 <= c->tmem_next, "tcgen05.ld: columns [%u, %u) outside the allocation (%u columns)", col, col + 32, c->tmem_next);
+  memcpy(v, c->tmem + (size_t)(lane_base + lane) * 512 + col, 32 * sizeof(float));
+}
+
+// ---------------------------------------------------------------------------------------------------------- executor
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static void cta_thread_exit(Cta* c) {
+  std::lock_guard<std::mutex> lk(c->mu);
+  c->alive -= 1;
+  Bar& b = c->sync;
+  if (b.count > 0 && b.count >= c->alive) {  // exited threads no longer take part in __syncthreads
+    b.count = 0;
+    b.gen++;
+  }
+  c->cv.notify_all();
+}
+
+int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& body) {
+  const int nthreads = (int)(block.x * block.y * block.z);
+  const long nctas = (long)grid.x * grid.y * grid.z;
+  if (nthreads <= 0 || nthreads > 1024 || nctas <= 0 || smem > 232448) {
+    g_last_error = cudaErrorInvalidConfiguration;
+    return (int)g_last_error;
+  }
+  if (cooperative && nctas > env_int("CUSIM_SMS", 4)) {
+    g_last_error = cudaErrorCooperativeLaunchTooLarge;
+    return (int)g_last_error;
+  }
+  g_abort.store(false);
+  const long group = cooperative ? nctas : 1;
+  for (long first = 0; first < nctas && !g_abort.load(); first += group) {
+    std::vector<Cta*> ctas;
+    for (long j = first; j < std::min(nctas, first + group); ++j) {
+      Cta* c = new Cta();
+      c->index = (int)j;
+      c->nthreads = c->alive = nthreads;
+      c->warp_bar.resize((nthreads + 31) / 32);
+      c->warp_slot.resize((nthreads + 31) / 32);
+      c->smem_bytes = smem;
+      if (posix_memalign(reinterpret_cast<void**>(&c->smem), 1024, smem + 1024) != 0) abort();
+      memset(c->smem, 0xCD, smem + 1024);  // shared memory starts out as garbage
+      c->tmem = static_cast<float*>(malloc(128 * 512 * sizeof(float)));
+      for (int i = 0; i < 128 * 512; ++i) c->tmem[i] = NAN;
+      ctas.push_back(c);
+    }
+    std::vector<std::thread> threads;
+    threads.reserve(ctas.size() * nthreads);
+    for (Cta* c : ctas)
+      for (int t = 0; t < nthreads; ++t)
+        threads.emplace_back([=, &body] {
+          tl.cta = c;
+          tl.linear_tid = t;
+          tl.bdim = block, tl.gdim = grid;
+          tl.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+          const long j = c->index;
+          tl.bid = make_uint3((unsigned)(j % grid.x), (unsigned)((j / grid.x) % grid.y), (unsigned)(j / ((long)grid.x * grid.y)));
+          try {
+            body();
+          } catch (const Abort&) {
+          }
+          cta_thread_exit(c);
+          tl.cta = nullptr;
+        });
+    for (auto& th : threads) th.join();
+    for (Cta* c : ctas) {
+      free(c->smem);
+      free(c->tmem);
+      delete c;
+    }
+  }
+  if (g_abort.load()) {
+    fprintf(stderr, "[cusim] launch aborted: %s\n", g_abort_msg.c_str());
+    g_last_error = cudaErrorLaunchFailure;
+    return (int)g_last_error;
+  }
+  return (int)cudaSuccess;
+}
+
+const char* abort_message() { return g_abort_msg.c_str(); }
+
+}  // namespace cusim
+
+// ============================================================================================================ CUDA API stubs
+static CUresult sim_encode_tiled(CUtensorMap* out, CUtensorMapDataType dt, cuuint32_t rank, void* ptr, const cuuint64_t* gdim,
+                                 const cuuint64_t* gstr, const cuuint32_t* box, const cuuint32_t* estr, CUtensorMapInterleave il,
+                                 CUtensorMapSwizzle sw, CUtensorMapL2promotion, CUtensorMapFloatOOBfill) {
+  using namespace cusim;
+  const uint32_t elem = dt == CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 ? 2 : (dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4 : 0);
+  if (elem == 0 || rank < 1 || rank > 4 || il != CU_TENSOR_MAP_INTERLEAVE_NONE || sw != CU_TENSOR_MAP_SWIZZLE_128B)
+    return CUDA_ERROR_INVALID_VALUE;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return CUDA_ERROR_INVALID_VALUE;
+  SimTmap m;
+  memset(&m, 0, sizeof(m));
+  m.magic = kTmapMagic, m.ptr = static_cast<uint8_t*>(ptr), m.elem = elem, m.rank = rank, m.swizzle = 128;
+  for (uint32_t d = 0; d < rank; ++d) {
+    if (gdim[d] == 0 || gdim[d] > (1ull << 32) || box[d] == 0 || box[d] > 256 || estr[d] != 1) return CUDA_ERROR_INVALID_VALUE;
+    m.dims[d] = gdim[d], m.box[d] = box[d];
+  }
+  for (uint32_t d = 0; d + 1 < rank; ++d) {
+    if (gstr[d] % 16 != 0 || gstr[d] >= (1ull << 40)) return CUDA_ERROR_INVALID_VALUE;
+    m.strides[d] = gstr[d];
+  }
+  if ((uint64_t)box[0] * elem > 128) return CUDA_ERROR_INVALID_VALUE;  // SWIZZLE_128B: inner box extent <= 128 bytes
+  memset(out, 0, sizeof(*out));
+  memcpy(out, &m, sizeof(m));
+  return CUDA_SUCCESS;
+}
+
+extern "C" {
+
+cudaError_t cudaGetLastError(void) {
+  const cudaError_t e = cusim::g_last_error;
+  cusim::g_last_error = cudaSuccess;
+  return e;
+}
+cudaError_t cudaPeekAtLastError(void) { return cusim::g_last_error; }
+const char* cudaGetErrorString(cudaError_t e) {
+  if (e == cudaSuccess) return "no error";
+  if (e == cudaErrorLaunchFailure) return cusim::g_abort_msg.c_str();
+  if (e == cudaErrorCooperativeLaunchTooLarge) return "too many blocks in cooperative launch";
+  return "cusim error";
+}
+cudaError_t cudaGetDevice(int* dev) {
+  *dev = 0;
+  return cudaSuccess;
+}
+cudaError_t cudaDeviceGetAttribute(int* value, enum cudaDeviceAttr attr, int) {
+  if (attr == cudaDevAttrMultiProcessorCount) *value = cusim::env_int("CUSIM_SMS", 4);
+  else *value = 0;
+  return cudaSuccess;
+}
+cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
+cudaError_t cudaMalloc(void** p, size_t bytes) {
+  return posix_memalign(p, 256, bytes ? bytes : 256) == 0 ? cudaSuccess : cudaErrorMemoryAllocation;
+}
+cudaError_t cudaFree(void* p) {
+  free(p);
+  return cudaSuccess;
+}
+cudaError_t cudaMemset(void* p, int v, size_t n) {
+  memset(p, v, n);
+  return cudaSuccess;
+}
+cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
+  memset(p, v, n);
+  return cudaSuccess;
+}
+cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
+  memset(h, 0, sizeof(*h));
+  memcpy(h, &p, sizeof(p));
+  return cudaSuccess;
+}
+cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned int) {
+  memcpy(p, &h, sizeof(*p));
+  return cudaSuccess;
+}
+cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+
+cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, enum cudaDriverEntryPointQueryResult* status) {
+  *fn = nullptr;
+  if (strcmp(symbol, "cuTensorMapEncodeTiled") == 0) *fn = reinterpret_cast<void*>(&sim_encode_tiled);
+  if (status) *status = *fn ? cudaDriverEntryPointSuccess : cudaDriverEntryPointSymbolNotFound;
+  return cudaSuccess;
+}
+
+const char* cusim_abort_message(void) { return cusim::abort_message(); }
+
+}  // extern "C"

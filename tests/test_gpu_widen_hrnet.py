@@ -187,7 +187,10 @@ def test_folded_eval_bn_inference_matches_the_unfolded_schedule(enc, dec, fc, mo
 @pytest.mark.parametrize("k,cin,cout,hw,res,relu", [(1, 256, 128, 64, False, True), (3, 128, 256, 64, True, True),
                                                      (3, 64, 64, 128, False, True), (1, 512, 2048, 16, True, False),
                                                      (3, 96, 48, 32, False, True),
-                                                     (3, 64, 64, 256, True, True)])   # 1024 tiles: 7 accumulators per CTA
+                                                     (3, 64, 64, 256, True, True),    # 1024 tiles: 7 accumulators per CTA
+                                                     # small grids (fewer tiles than SMs; also the sizes tests/cusim runs)
+                                                     (1, 64, 128, 32, False, True), (3, 64, 64, 32, True, True),
+                                                     (3, 96, 48, 16, False, True), (1, 128, 256, 16, True, False)])
 def test_fused_conv_bn_train_kernel_matches_the_three_kernel_sequence(k, cin, cout, hw, res, relu):
     """sseg_conv_bn_train (persistent CTAs, accumulators resident in TMEM across an in-kernel grid barrier) against
     sseg_conv_igemm(stats) + sseg_bn_finalize(train) + sseg_bn_apply on the same operands."""
@@ -257,7 +260,8 @@ def test_fused_conv_bn_train_schedule_matches_the_default_step(monkeypatch):
 
 @_EXPERIMENTAL
 @pytest.mark.parametrize("k,hw,cprod,cout_next", [(1, 64, 128, 256), (3, 64, 128, 256), (3, 38, 128, 256), (3, 32, 48, 48),
-                                                  (3, 128, 64, 64), (1, 64, 1024, 256)])
+                                                  (3, 128, 64, 64), (1, 64, 1024, 256),
+                                                  (1, 32, 64, 128), (3, 32, 128, 64), (3, 14, 48, 96), (1, 16, 256, 64)])
 def test_fused_conv_bn_dgrad_kernel_matches_the_two_kernel_sequence(k, hw, cprod, cout_next):
     """sseg_conv_dgrad_bn (data gradient + the producer's whole BN backward, g resident in TMEM across the grid barrier)
     against sseg_conv_igemm_bnbwd + sseg_bn_bwd_apply(s2_raw) on the same operands."""
