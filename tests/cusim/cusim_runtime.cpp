@@ -40,8 +40,13 @@ struct Cta {
   int nthreads = 0, alive = 0;
   Bar sync;
   Bar named[16];
-  std::vector<Bar> warp_bar;
-  std::vector<std::array<uint64_t, 32>> warp_slot;
+  struct WarpSync {
+    std::mutex mu;
+    std::condition_variable cv;
+    Bar bar;
+    uint64_t slot[32];
+  };
+  std::vector<WarpSync> warps;
   uint8_t* smem = nullptr;
   size_t smem_bytes = 0;
   float* tmem = nullptr;  // [128][512]
@@ -81,12 +86,14 @@ static void raise_abort(const char* fmt, ...) {
   } while (0)
 
 template <typename Pred>
-static void wait_until(Cta* c, std::unique_lock<std::mutex>& lk, Pred pred, const char* what, long detail) {
+static void wait_until(Cta* c, std::unique_lock<std::mutex>& lk, Pred pred, const char* what, long detail,
+                       std::condition_variable* cv = nullptr) {
   const auto t0 = std::chrono::steady_clock::now();
   const double limit = timeout_seconds();
+  if (cv == nullptr) cv = &c->cv;
   while (!pred()) {
     if (g_abort.load()) throw Abort();
-    c->cv.wait_for(lk, std::chrono::milliseconds(20));
+    cv->wait_for(lk, std::chrono::milliseconds(20));
     if (pred()) break;
     const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (dt > limit) {
@@ -124,19 +131,28 @@ void syncthreads() {
 
 void named_barrier(int id, int count) { bar_arrive_wait(tl.cta, tl.cta->named[id & 15], count, "bar.sync id", id); }
 
-void syncwarp() {
+void syncwarp() {  // own mutex / condition variable per warp: a shuffle wakes 31 threads, not the whole CTA
   Cta* c = tl.cta;
   const int w = tl.linear_tid >> 5;
   const int in_warp = std::min(32, c->nthreads - w * 32);
-  bar_arrive_wait(c, c->warp_bar[w], in_warp, "__syncwarp / shuffle of warp", w);
+  Cta::WarpSync& ws = c->warps[w];
+  std::unique_lock<std::mutex> lk(ws.mu);
+  const unsigned g = ws.bar.gen;
+  if (++ws.bar.count >= in_warp) {
+    ws.bar.count = 0;
+    ws.bar.gen++;
+    ws.cv.notify_all();
+    return;
+  }
+  wait_until(c, lk, [&] { return ws.bar.gen != g; }, "__syncwarp / shuffle of warp", w, &ws.cv);
 }
 
 uint64_t warp_exchange(uint64_t v, int src_lane) {
   Cta* c = tl.cta;
   const int w = tl.linear_tid >> 5, lane = tl.linear_tid & 31;
-  c->warp_slot[w][lane] = v;
+  c->warps[w].slot[lane] = v;
   syncwarp();
-  const uint64_t r = c->warp_slot[w][src_lane];
+  const uint64_t r = c->warps[w].slot[src_lane];
   syncwarp();
   return r;
 }
@@ -412,6 +428,56 @@ static void cta_thread_exit(Cta* c) {
   c->cv.notify_all();
 }
 
+static Cta* new_cta(int nthreads, size_t smem) {
+  Cta* c = new Cta();
+  c->nthreads = nthreads;
+  c->warps = std::vector<Cta::WarpSync>((nthreads + 31) / 32);
+  c->smem_bytes = smem;
+  if (posix_memalign(reinterpret_cast<void**>(&c->smem), 1024, smem + 1024) != 0) abort();
+  c->tmem = static_cast<float*>(malloc(128 * 512 * sizeof(float)));
+  return c;
+}
+
+static void reset_cta(Cta* c, long index) {  // a fresh CTA: garbage in shared and tensor memory, no barrier state
+  c->index = (int)index;
+  c->alive = c->nthreads;
+  c->sync = Bar();
+  for (Bar& b : c->named) b = Bar();
+  for (auto& w : c->warps) w.bar = Bar();
+  memset(c->smem, 0xCD, c->smem_bytes + 1024);
+  if (c->tmem_next != 0 || index == 0)
+    for (int i = 0; i < 128 * 512; ++i) c->tmem[i] = NAN;
+  c->tmem_next = 0;
+  c->pending.clear();
+}
+
+static void free_cta(Cta* c) {
+  free(c->smem);
+  free(c->tmem);
+  delete c;
+}
+
+// A reusable rendezvous of the worker threads of one CTA slot (between consecutive CTAs of an ordinary launch).
+struct PoolBarrier {
+  std::mutex mu;
+  std::condition_variable cv;
+  int count = 0, n = 0;
+  unsigned gen = 0;
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    const unsigned g = gen;
+    if (++count == n) {
+      count = 0;
+      gen++;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return gen != g; });
+    }
+  }
+};
+
+// Ordinary launch: CTAs run one after another (static __shared__ variables are process-wide statics here), each by the
+// same `nthreads` worker threads. Cooperative launch: every CTA gets its own threads, all run concurrently.
 int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& body) {
   const int nthreads = (int)(block.x * block.y * block.z);
   const long nctas = (long)grid.x * grid.y * grid.z;
@@ -424,47 +490,40 @@ int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::func
     return (int)g_last_error;
   }
   g_abort.store(false);
-  const long group = cooperative ? nctas : 1;
-  for (long first = 0; first < nctas && !g_abort.load(); first += group) {
-    std::vector<Cta*> ctas;
-    for (long j = first; j < std::min(nctas, first + group); ++j) {
-      Cta* c = new Cta();
-      c->index = (int)j;
-      c->nthreads = c->alive = nthreads;
-      c->warp_bar.resize((nthreads + 31) / 32);
-      c->warp_slot.resize((nthreads + 31) / 32);
-      c->smem_bytes = smem;
-      if (posix_memalign(reinterpret_cast<void**>(&c->smem), 1024, smem + 1024) != 0) abort();
-      memset(c->smem, 0xCD, smem + 1024);  // shared memory starts out as garbage
-      c->tmem = static_cast<float*>(malloc(128 * 512 * sizeof(float)));
-      for (int i = 0; i < 128 * 512; ++i) c->tmem[i] = NAN;
-      ctas.push_back(c);
-    }
-    std::vector<std::thread> threads;
-    threads.reserve(ctas.size() * nthreads);
-    for (Cta* c : ctas)
-      for (int t = 0; t < nthreads; ++t)
-        threads.emplace_back([=, &body] {
-          tl.cta = c;
-          tl.linear_tid = t;
-          tl.bdim = block, tl.gdim = grid;
-          tl.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
-          const long j = c->index;
-          tl.bid = make_uint3((unsigned)(j % grid.x), (unsigned)((j / grid.x) % grid.y), (unsigned)(j / ((long)grid.x * grid.y)));
-          try {
-            body();
-          } catch (const Abort&) {
-          }
-          cta_thread_exit(c);
-          tl.cta = nullptr;
-        });
-    for (auto& th : threads) th.join();
-    for (Cta* c : ctas) {
-      free(c->smem);
-      free(c->tmem);
-      delete c;
-    }
+  const long slots = cooperative ? nctas : 1;  // CTAs resident at the same time
+  std::vector<Cta*> ctas;
+  std::vector<PoolBarrier> gates(slots);
+  for (long s = 0; s < slots; ++s) {
+    ctas.push_back(new_cta(nthreads, smem));
+    gates[s].n = nthreads;
   }
+  std::vector<std::thread> threads;
+  threads.reserve(slots * nthreads);
+  for (long s = 0; s < slots; ++s)
+    for (int t = 0; t < nthreads; ++t)
+      threads.emplace_back([=, &body, &ctas, &gates] {
+        Cta* c = ctas[s];
+        tl.linear_tid = t;
+        tl.bdim = block, tl.gdim = grid;
+        tl.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+        for (long j = s; j < nctas; j += slots) {
+          if (t == 0) reset_cta(c, j);
+          gates[s].wait();
+          if (!g_abort.load()) {
+            tl.cta = c;
+            tl.bid = make_uint3((unsigned)(j % grid.x), (unsigned)((j / grid.x) % grid.y), (unsigned)(j / ((long)grid.x * grid.y)));
+            try {
+              body();
+            } catch (const Abort&) {
+            }
+            cta_thread_exit(c);
+            tl.cta = nullptr;
+          }
+          gates[s].wait();
+        }
+      });
+  for (auto& th : threads) th.join();
+  for (Cta* c : ctas) free_cta(c);
   if (g_abort.load()) {
     fprintf(stderr, "[cusim] launch aborted: %s\n", g_abort_msg.c_str());
     g_last_error = cudaErrorLaunchFailure;

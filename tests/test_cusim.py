@@ -1,0 +1,246 @@
+"""The REAL kernel sources on the CPU simulator (tests/cusim): csrc/*.cu compiled by g++ against a functional model of the
+CUDA execution model and of the sm_100a instructions the kernels use (TMA with 128B swizzle + out-of-bounds fill,
+mbarrier, tensor memory, tcgen05.mma / .commit / .ld, named barriers, warp shuffles), one OS thread per CUDA thread.
+
+What this pins (and what it cannot):
+  * control flow, indexing, pipeline phases, tile loops, the grid barrier and the peer handshake of every kernel -- a
+    deadlock is reported by the simulator's watchdog instead of hanging a B200 box;
+  * arithmetic against the same references the `-m gpu` tests use (the gpu tests themselves are re-run on the simulator);
+  * NOT performance, NOT the hardware memory model, NOT descriptor bits the model does not decode. The model itself is
+    pinned by the kernels that were validated on B200 in round 1 (forward / dgrad / wgrad GEMMs incl. MN-major operands).
+"""
+import os
+import subprocess
+import sys
+import threading
+import types
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# `-m gpu` tests re-run on the simulator inside the CPU suite (a few seconds each; the full gpu suite also passes on it
+# but takes ~25 minutes: SSEG_GPU_TESTS_ON_EMULATOR=sim SSEG_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -n 6)
+_CURATED = " or ".join([
+    # tcgen05 GEMM family: validated on B200 -> pins the simulator's TMA / UMMA-descriptor / tensor-memory model
+    "test_pointwise_basic", "test_3x3_dilated", "test_virtual_concat_3x3", "test_classifier_f32_bias", "test_addend",
+    "test_wgrad_3x3", "test_wgrad_ragged", "(test_dgrad_with_fused_bn_backward_reduce and 3-38)",
+    # never run on a GPU yet: cooperative conv+BN kernels (small grids), folded epilogue, fp32-pair kernels
+    "(test_fused_conv_bn_train_kernel and (1-64-128-32 or 3-64-64-32 or 3-96-48-16 or 1-128-256-16))",
+    "(test_fused_conv_bn_dgrad_kernel and (1-32-64-128 or 3-32-128-64 or 3-14-48-96 or 1-16-256-64))",
+    "test_conv_with_folded_affine_epilogue", "test_pair_kernels_against_torch",
+    # streaming kernels with warp shuffles / shared-memory reductions
+    "(test_bn_forward_backward and 64-40)", "test_maxpool", "(test_bilinear and 3-64)",
+])
+
+
+def _run_gpu_tests_on_sim(kexpr, sms, extra_env=None, timeout=1500):
+    env = dict(os.environ, SSEG_GPU_TESTS_ON_EMULATOR="sim", SSEG_TEST_EXPERIMENTAL="1", CUSIM_SMS=str(sms), CUSIM_TIMEOUT="60")
+    env.update(extra_env or {})
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-n", "4", "-p", "no:cacheprovider", "-k", kexpr,
+           os.path.join(ROOT, "tests", "test_gpu_igemm.py"), os.path.join(ROOT, "tests", "test_gpu_elementwise.py"),
+           os.path.join(ROOT, "tests", "test_gpu_widen_hrnet.py")]
+    out = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    tail = (out.stdout + out.stderr)[-4000:]
+    assert out.returncode == 0, tail
+    return out.stdout
+
+
+def test_kernel_sources_pass_their_gpu_tests_on_the_simulator():
+    out = _run_gpu_tests_on_sim(_CURATED, sms=8)
+    assert " passed" in out and "failed" not in out
+    n = int(out.strip().splitlines()[-1].split(" passed")[0].split()[-1])
+    assert n >= 29, out[-500:]
+
+
+def test_cooperative_kernels_with_uneven_tile_distribution_and_the_persistent_gemm():
+    """5 'SMs' -> CTAs hold different numbers of resident accumulators; the persistent GEMM variant walks 5 CTAs through
+    many tiles and both tensor-memory buffers (passes on B200 with the same switches: profiles/r1_summary.md)."""
+    _run_gpu_tests_on_sim("(test_fused_conv_bn_train_kernel and (1-64-128-32 or 3-64-64-32)) or "
+                          "(test_fused_conv_bn_dgrad_kernel and (3-32-128-64 or 1-16-256-64))", sms=5)
+    _run_gpu_tests_on_sim("test_pointwise_wide_k_and_stats or test_3x3_cout256_cin512 or test_ragged_spatial", sms=8,
+                          extra_env={"SSEG_IGEMM_PERSISTENT": "2", "SSEG_IGEMM_PERSISTENT_CTAS": "5"})
+
+
+# ------------------------------------------------------------------------------------------------ two ranks, one process
+@pytest.fixture()
+def sim(monkeypatch):
+    import conftest
+    from mit_semseg.engine import _C, ops
+    os.environ.setdefault("CUSIM_SMS", "8")
+    lib = conftest.sim_lib()
+    monkeypatch.setattr(_C, "lib", lambda: lib)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    return lib
+
+
+def _arena_ns(arenas, rank):
+    from mit_semseg.engine import _C
+    bases = (_C.c_void_p * 8)()
+    for r, a in enumerate(arenas):
+        bases[r] = a.data_ptr()
+    return types.SimpleNamespace(bases=bases, world=len(arenas), rank=rank)
+
+
+def _both_ranks(fn):
+    """fn(rank) on two host threads at once: the kernels of the two 'GPUs' must overlap in time, they poll each other's
+    flags (ctypes releases the GIL for the duration of a call)."""
+    errs = []
+
+    def run(r):
+        try:
+            fn(r)
+        except Exception as e:   # noqa: BLE001
+            errs.append((r, e))
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    assert not errs, errs
+
+
+@pytest.mark.parametrize("k,cin,cout,hw", [(1, 64, 128, 32), (3, 64, 64, 16)])
+def test_synchronised_conv_bn_kernels_two_ranks_over_shared_arenas(sim, k, cin, cout, hw):
+    """world = 2: sseg_conv_bn_train and sseg_conv_dgrad_bn pool their partial sums through the peers' arenas inside the
+    kernel (flag handshake after the grid barrier). Two host threads stand in for the two GPUs; the reference is the
+    Python restatement of the ABI (tests/abi_emulator.py) run rank by rank over the same arenas."""
+    from abi_emulator import EmuLib
+    from mit_semseg.engine import _C, ops
+    g = torch.Generator().manual_seed(11)
+    n, world = 1, 2
+    cp = (cout + 7) // 8 * 8
+    wt = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).bfloat16()
+    w2 = wt.permute(0, 2, 3, 1).reshape(cout, -1).contiguous()
+    gamma, beta = torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.2
+    xs = [torch.randn(n, hw, hw, cin, generator=g).bfloat16() for _ in range(world)]
+    count = float(n * hw * hw)
+    DATA_F, DATA_B, FLAGS = 0, 1024, 3000
+
+    def fresh():
+        st = types.SimpleNamespace()
+        st.arenas = [torch.zeros(4096) for _ in range(world)]
+        for a in st.arenas:
+            a[DATA_F + 2 * cout] = count
+        st.y = [torch.full((n, hw, hw, cp), float("nan"), dtype=torch.bfloat16) for _ in range(world)]
+        st.a = [torch.full((n, hw, hw, cp), float("nan"), dtype=torch.bfloat16) for _ in range(world)]
+        st.vec = [torch.zeros(4, cout) for _ in range(world)]
+        st.tmp = [torch.zeros(3, cout) for _ in range(world)]       # tmp mean | tmp var | running_iter[0]
+        st.cnt = [torch.zeros(1) for _ in range(world)]
+        st.counter = [torch.zeros(4, dtype=torch.int32) for _ in range(world)]
+        st.step = [torch.ones(1, dtype=torch.int32) for _ in range(world)]
+        st.keep = []
+        return st
+
+    def forward(st, r):
+        ar = st.arenas[r]
+        peer = ops.make_coop_peer(_arena_ns(st.arenas, r), DATA_F, cout, FLAGS, st.step[r])
+        bn = ops.make_bn_fused(gamma, beta, 1e-5, 0.1, count, ar[DATA_F:DATA_F + cout], ar[DATA_F + cout:DATA_F + 2 * cout],
+                               st.counter[r][:1], st.vec[r][0], st.vec[r][1], st.vec[r][2], st.vec[r][3], peer=peer,
+                               tmp_running_mean=st.tmp[r][0], tmp_running_var=st.tmp[r][1], running_iter=st.tmp[r][2][:1],
+                               count_out=st.cnt[r])
+        st.keep.append((peer, bn))
+        geom = ops.make_geom([xs[r]], ops.conv_taps(k, 1))
+        ops.conv_bn_train(geom, w2, cout, st.y[r], st.a[r], bn)
+
+    # ---- simulator: both ranks concurrently
+    S = fresh()
+    _both_ranks(lambda r: forward(S, r))
+    # ---- reference: emulator, rank after rank; a second pass after clearing each rank's own sums sees complete arenas
+    E = fresh()
+    emu = EmuLib()
+    import pytest as _pt
+    mp = _pt.MonkeyPatch()
+    mp.setattr(_C, "lib", lambda: emu)
+    try:
+        for r in range(world):
+            forward(E, r)
+        for r in range(world):
+            E.arenas[r][DATA_F:DATA_F + 2 * cout] = 0
+            E.tmp[r].zero_()
+            forward(E, r)
+    finally:
+        mp.undo()
+    for r in range(world):
+        # fp32 accumulation order differs between the two restatements: single bf16 roundings may flip
+        ys, ye = S.y[r][..., :cout].float(), E.y[r][..., :cout].float()
+        assert (ys - ye).abs().max().item() <= 2 ** -7 * ye.abs().max().item() and (ys != ye).float().mean().item() < 0.02
+        assert torch.allclose(S.arenas[r][:2 * cout], E.arenas[r][:2 * cout], rtol=2e-3, atol=5e-2)
+        assert torch.allclose(S.vec[r], E.vec[r], rtol=2e-3, atol=2e-4)
+        assert torch.allclose(S.tmp[r], E.tmp[r], rtol=2e-3, atol=2e-4) and S.cnt[r].item() == world * count
+        assert (S.a[r][..., :cout].float() - E.a[r][..., :cout].float()).abs().max().item() <= 2 ** -6 * E.a[r].float()[..., :cout].abs().max().item()
+    assert torch.equal(S.vec[0], S.vec[1])                 # pooled in rank order: bit-identical coefficients on both ranks
+
+    # ---- backward twin: dgrad of a consumer conv + this layer's BN backward, sums pooled over the ranks
+    cnext = 64
+    wn = (torch.randn(cnext, cout, k, k, generator=g) * 0.05).bfloat16()
+    wd = torch.zeros(cout, k * k * cnext, dtype=torch.bfloat16)
+    dys = [(torch.randn(n, hw, hw, cnext, generator=g) * 0.1).bfloat16() for _ in range(world)]
+    dh, dw = ops.conv_taps(k, 1)
+
+    def backward(st, r, lib_is_emu):
+        ar = st.arenas[r]
+        if not hasattr(st, "wd_ready"):
+            ops.prep_conv_weight(wn.float().contiguous(), None, wd, o_pad=cnext)
+            st.wd_ready = True
+        st.step[r].fill_(2)
+        peer = ops.make_coop_peer(_arena_ns(st.arenas, r), DATA_B, cp, FLAGS, st.step[r])
+        gd = ops.make_geom([dys[r]], ([-v for v in dh], [-v for v in dw]), tap_koff=[t * cnext for t in range(k * k)])
+        st.dx = getattr(st, "dx", [None] * world)
+        st.dgb = getattr(st, "dgb", [None] * world)
+        st.dx[r] = torch.full((n, hw, hw, cp), float("nan"), dtype=torch.bfloat16)
+        st.dgb[r] = torch.zeros(2, cout)
+        st.counter[r].zero_()
+        st.keep.append((peer, gd))
+        ops.conv_dgrad_bn(gd, wd, cout, st.y[r], st.dx[r], st.vec[r][2], st.vec[r][3], st.vec[r][0], st.vec[r][1], count,
+                          ar[DATA_B:DATA_B + cout], ar[DATA_B + cp:DATA_B + cp + cout], st.dgb[r][0], st.counter[r][:1],
+                          peer=peer, count_dev=st.cnt[r], dbeta_out=st.dgb[r][1])
+
+    emu_prep = EmuLib()
+    mp = _pt.MonkeyPatch()
+    mp.setattr(_C, "lib", lambda: emu_prep)
+    try:
+        ops.prep_conv_weight(wn.float().contiguous(), None, wd, o_pad=cnext)
+        S.wd_ready = E.wd_ready = True
+        # the emulated reference consumes the SIMULATOR's forward results, so only the backward kernels are compared
+        for r in range(world):
+            E.y[r], E.vec[r], E.cnt[r] = S.y[r].clone(), S.vec[r].clone(), S.cnt[r].clone()
+        for r in range(world):
+            backward(E, r, True)
+        for r in range(world):
+            E.arenas[r][DATA_B:DATA_B + 2 * cp] = 0
+            backward(E, r, True)
+    finally:
+        mp.undo()
+    _both_ranks(lambda r: backward(S, r, False))
+    for r in range(world):
+        assert torch.allclose(S.arenas[r][DATA_B:DATA_B + 2 * cp], E.arenas[r][DATA_B:DATA_B + 2 * cp], rtol=1e-4, atol=1e-3)
+        assert torch.allclose(S.dgb[r], E.dgb[r], rtol=1e-3, atol=1e-3)
+        ref = E.dx[r][..., :cout].float()
+        assert torch.isfinite(S.dx[r][..., :cout].float()).all()
+        assert (S.dx[r][..., :cout].float() - ref).abs().max().item() <= 2 ** -6 * ref.abs().max().item()
+    assert torch.equal(S.dgb[0], S.dgb[1])
+
+
+def test_watchdog_reports_a_rank_that_waits_for_a_peer_that_never_arrives(sim, monkeypatch):
+    """The failure mode that would hang a GPU box: one rank enters the synchronised kernel alone. The simulator aborts the
+    launch after CUSIM_TIMEOUT seconds and the C ABI returns an error naming the wait."""
+    from mit_semseg.engine import _C, ops
+    monkeypatch.setenv("CUSIM_TIMEOUT", "2")
+    g = torch.Generator().manual_seed(3)
+    cin, cout, hw = 64, 64, 16
+    x = torch.randn(1, hw, hw, cin, generator=g).bfloat16()
+    w2 = (torch.randn(cout, cin, generator=g) * 0.1).bfloat16()
+    arenas = [torch.zeros(1024) for _ in range(2)]
+    arenas[0][2 * cout] = hw * hw
+    step = torch.ones(1, dtype=torch.int32)
+    peer = ops.make_coop_peer(_arena_ns(arenas, 0), 0, cout, 512, step)
+    vec, tmp, cnt = torch.zeros(4, cout), torch.zeros(3, cout), torch.zeros(1)
+    counter = torch.zeros(4, dtype=torch.int32)
+    bn = ops.make_bn_fused(torch.ones(cout), torch.zeros(cout), 1e-5, 0.1, hw * hw, arenas[0][:cout], arenas[0][cout:2 * cout],
+                           counter[:1], vec[0], vec[1], vec[2], vec[3], peer=peer, tmp_running_mean=tmp[0],
+                           tmp_running_var=tmp[1], running_iter=tmp[2][:1], count_out=cnt)
+    y, a = torch.zeros(1, hw, hw, cout, dtype=torch.bfloat16), torch.zeros(1, hw, hw, cout, dtype=torch.bfloat16)
+    with pytest.raises(_C.SsegError, match="deadlock"):
+        ops.conv_bn_train(ops.make_geom([x], ops.conv_taps(1, 1)), w2, cout, y, a, bn)
