@@ -28,7 +28,8 @@ def sim_lib():
         import ctypes
         import subprocess
         from mit_semseg.engine import _C
-        out = subprocess.run([os.path.join(ROOT, "tests", "cusim", "build_sim.sh")], capture_output=True, text=True)
+        env = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}   # a preloaded sanitizer runtime is for us, not for g++
+        out = subprocess.run([os.path.join(ROOT, "tests", "cusim", "build_sim.sh")], capture_output=True, text=True, env=env)
         assert out.returncode == 0, out.stderr[-3000:]
         L = ctypes.CDLL(out.stdout.strip().splitlines()[-1])
         _C._declare(L)

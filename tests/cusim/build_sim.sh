@@ -3,10 +3,18 @@
 set -e
 HERE="$(cd "$(dirname "$0")" && pwd)"
 CSRC="$HERE/../../semantic-segmentation-pytorch_b200/csrc"
+# CUSIM_SANITIZE=address|thread: instrumented build in its own directory (run the tests with the matching runtime preloaded:
+#   LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0  /  LD_PRELOAD=$(gcc -print-file-name=libtsan.so))
+# = out-of-bounds checking of every global / shared memory access of the kernels, resp. data-race detection between CUDA threads
+SAN=""
 OUT="$HERE/_build"
+if [ -n "$CUSIM_SANITIZE" ]; then
+  SAN="-fsanitize=$CUSIM_SANITIZE -fno-omit-frame-pointer"
+  OUT="$HERE/_build/$CUSIM_SANITIZE"
+fi
 CUDA_INC="${CUDA_HOME:-/usr/local/cuda}/include"
 mkdir -p "$OUT"
-FLAGS="-O2 -g -fno-strict-aliasing -std=c++17 -fPIC -pthread -w -I$HERE -I$CUDA_INC -include $HERE/cusim.h"
+FLAGS="$SAN -O2 -g -fno-strict-aliasing -std=c++17 -fPIC -pthread -w -I$HERE -I$CUDA_INC -include $HERE/cusim.h"
 pids=()
 for f in "$CSRC"/*.cu; do
   o="$OUT/$(basename "${f%.cu}").o"
@@ -15,11 +23,16 @@ for f in "$CSRC"/*.cu; do
     pids+=($!)
   fi
 done
+o="$OUT/selftest.o"
+if [ ! -f "$o" ] || [ "$HERE/selftest.cu" -nt "$o" ] || [ "$HERE/cusim.h" -nt "$o" ]; then
+  g++ $FLAGS -x c++ -c "$HERE/selftest.cu" -o "$o" &
+  pids+=($!)
+fi
 o="$OUT/cusim_runtime.o"
 if [ ! -f "$o" ] || [ "$HERE/cusim_runtime.cpp" -nt "$o" ] || [ "$HERE/cusim.h" -nt "$o" ] || [ "$HERE/cusim_ptx.h" -nt "$o" ]; then
   g++ $FLAGS -c "$HERE/cusim_runtime.cpp" -o "$o" &
   pids+=($!)
 fi
 for p in "${pids[@]}"; do wait "$p"; done
-g++ -shared -pthread -Wl,-Bsymbolic -o "$OUT/libsseg_sim.so" "$OUT"/*.o
+g++ $SAN -shared -pthread -Wl,-Bsymbolic -o "$OUT/libsseg_sim.so" "$OUT"/*.o
 echo "$OUT/libsseg_sim.so"

@@ -244,3 +244,68 @@ def test_watchdog_reports_a_rank_that_waits_for_a_peer_that_never_arrives(sim, m
     y, a = torch.zeros(1, hw, hw, cout, dtype=torch.bfloat16), torch.zeros(1, hw, hw, cout, dtype=torch.bfloat16)
     with pytest.raises(_C.SsegError, match="deadlock"):
         ops.conv_bn_train(ops.make_geom([x], ops.conv_taps(1, 1)), w2, cout, y, a, bn)
+
+
+# ------------------------------------------------------------------------------------------------ detectors
+def _san_env(kind):
+    rt = subprocess.run(["gcc", "-print-file-name=lib%s.so" % {"address": "asan", "thread": "tsan"}[kind]], capture_output=True,
+                        text=True).stdout.strip()
+    if not os.path.isabs(rt) or not os.path.exists(rt):
+        pytest.skip("no %s sanitizer runtime" % kind)
+    env = dict(os.environ, CUSIM_SANITIZE=kind, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0", TSAN_OPTIONS="exitcode=66 report_signal_unsafe=0")
+    build = subprocess.run([os.path.join(ROOT, "tests", "cusim", "build_sim.sh")], capture_output=True, text=True,
+                           env={k: v for k, v in env.items() if k != "LD_PRELOAD"})
+    assert build.returncode == 0, build.stderr[-2000:]
+    return env, build.stdout.strip().splitlines()[-1]
+
+
+def _selftest(lib, which, env):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "tests", "cusim", "selftest_run.py"), lib, which], env=env,
+                          capture_output=True, text=True, timeout=300)
+
+
+def test_detectors_catch_planted_defects():
+    """The three failure classes the simulator exists for, each planted in a tiny kernel (tests/cusim/selftest.cu): a
+    missing __syncthreads (ThreadSanitizer names both source lines), a wait on an mbarrier phase that never completes
+    (watchdog), a store one element past a buffer (AddressSanitizer)."""
+    env, lib = _san_env("thread")
+    out = _selftest(lib, "race", env)
+    assert "ThreadSanitizer: data race" in out.stderr and "selftest.cu:12" in out.stderr and "selftest.cu:14" in out.stderr
+    out = _selftest(lib, "norace", env)
+    assert "ThreadSanitizer" not in out.stderr and "rc 0 [63.0, 62.0, 61.0]" in out.stdout
+    import conftest
+    conftest.sim_lib()
+    plain = os.path.join(ROOT, "tests", "cusim", "_build", "libsseg_sim.so")
+    out = _selftest(plain, "stuck", dict(os.environ, CUSIM_TIMEOUT="2"))
+    assert "deadlock: CTA 0 thread 32 waited" in out.stdout + out.stderr and "rc 719" in out.stdout
+    assert "rc 0" in _selftest(plain, "notstuck", dict(os.environ, CUSIM_TIMEOUT="2")).stdout
+    env, lib = _san_env("address")
+    out = _selftest(lib, "oob", env)
+    assert "heap-buffer-overflow" in out.stderr and "oob_kernel" in out.stderr
+
+
+_SANITIZED = ("test_pointwise_basic or test_ragged_spatial or test_channel_counts_not_multiple_of_64 or test_wgrad_ragged or "
+              "(test_dgrad_with_fused_bn_backward_reduce and 3-38) or "
+              "(test_fused_conv_bn_train_kernel and (3-64-64-32 or 3-96-48-16)) or "
+              "(test_fused_conv_bn_dgrad_kernel and (3-14-48-96 or 1-16-256-64)) or test_pair_kernels_against_torch or "
+              "(test_bn_forward_backward and 64-40) or (test_bilinear and 3-64)")
+
+
+@pytest.mark.parametrize("kind", ["address", "thread"])
+def test_kernels_are_clean_under_the_sanitizers(kind):
+    """compute-sanitizer's memcheck / racecheck, CPU edition: every global and shared memory access of the kernels is
+    bounds-checked (torch's CPU allocations get red zones), resp. checked for unordered conflicting accesses between CUDA
+    threads (barriers, mbarriers and flags are real synchronisation in the simulator, so ordered accesses are silent)."""
+    env, _ = _san_env(kind)
+    log = "/tmp/cusim_%s_%d" % (kind, os.getpid())
+    if kind == "thread":
+        env["TSAN_OPTIONS"] += " log_path=" + log
+    else:
+        env["ASAN_OPTIONS"] += " log_path=" + log
+    _run_gpu_tests_on_sim(_SANITIZED, sms=5, extra_env=env, timeout=3000)
+    import glob
+    reports = [open(f).read() for f in glob.glob(log + ".*")]
+    mine = [r for r in reports if "libsseg_sim" in r]
+    for f in glob.glob(log + ".*"):
+        os.remove(f)
+    assert not mine, mine[0][:3000]
