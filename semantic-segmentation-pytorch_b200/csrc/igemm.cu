@@ -717,6 +717,9 @@ struct CoopPeer {
   long flag_off;
   const int* step;
 };
+// Bound on every cross-CTA / cross-GPU poll of the cooperative kernels (~10-30 s of polling; a legitimate wait is
+// micro- to milliseconds): a protocol bug then aborts the grid with a launch failure instead of spinning forever.
+constexpr unsigned int kCoopSpinLimit = 1u << 24;
 // called by the 128 epilogue threads of every CTA right after the local grid barrier; t = epilogue thread index
 __device__ __forceinline__ void coop_peer_handshake(const CoopPeer& pr, int t) {
   if (pr.world <= 1) return;
@@ -727,7 +730,11 @@ __device__ __forceinline__ void coop_peer_handshake(const CoopPeer& pr, int t) {
   }
   if (t < pr.world) {
     const int* mine = reinterpret_cast<const int*>(pr.base[pr.rank]) + pr.flag_off + t;
-    while (ld_acquire_sys(mine) < step) __nanosleep(32);
+    unsigned int polls = 0;
+    while (ld_acquire_sys(mine) < step) {
+      __nanosleep(32);
+      if (++polls > kCoopSpinLimit) __trap();  // a peer that never arrives ends in a launch failure, not in a hung GPU
+    }
   }
   bar_sync_epilogue();
 }
@@ -1046,7 +1053,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
         bar_sync_epilogue();
         if (t == 0) {
           atomicAdd(q.counter, 1u);
+          unsigned int polls = 0;
           while (ld_acquire_gpu(q.counter) < gridDim.x) {
+            if (++polls > kCoopSpinLimit) __trap();  // see kCoopSpinLimit
           }
         }
         bar_sync_epilogue();
@@ -1393,7 +1402,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
         bar_sync_epilogue();
         if (t == 0) {
           atomicAdd(q.counter, 1u);
+          unsigned int polls = 0;
           while (ld_acquire_gpu(q.counter) < gridDim.x) {
+            if (++polls > kCoopSpinLimit) __trap();  // see kCoopSpinLimit
           }
         }
         bar_sync_epilogue();

@@ -49,6 +49,7 @@ uint64_t warp_exchange(uint64_t v, int src_lane);  // every lane of the warp cal
 uint8_t* dyn_smem();
 void atomic_lock();
 void atomic_unlock();
+void trap();
 void spin_pause();  // called from polling loops: yields and throws when the launch has been aborted
 int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& body);
 
@@ -66,6 +67,7 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { ::cusim::syncwarp(); }
 static inline void __threadfence() { __sync_synchronize(); }
 static inline void __threadfence_system() { __sync_synchronize(); }
 static inline void __nanosleep(unsigned) { ::cusim::spin_pause(); }
+static inline void __trap() { ::cusim::trap(); }
 
 template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src, int = 32) {

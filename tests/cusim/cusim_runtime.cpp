@@ -161,6 +161,8 @@ uint8_t* dyn_smem() { return tl.cta->smem; }
 void atomic_lock() { g_atomic_mu.lock(); }
 void atomic_unlock() { g_atomic_mu.unlock(); }
 
+void trap() { raise_abort("__trap() executed by CTA %d thread %d", tl.cta ? tl.cta->index : -1, tl.linear_tid); }
+
 void spin_pause() {
   if (g_abort.load()) throw Abort();
   static thread_local std::chrono::steady_clock::time_point t0;
