@@ -284,6 +284,8 @@ def test_detectors_catch_planted_defects():
     assert "heap-buffer-overflow" in out.stderr and "oob_kernel" in out.stderr
 
 
+_SANITIZED_QUICK = ("test_pointwise_basic or (test_fused_conv_bn_train_kernel and 3-96-48-16) or "
+                    "(test_fused_conv_bn_dgrad_kernel and 3-14-48-96) or test_pair_kernels_against_torch")
 _SANITIZED = ("test_pointwise_basic or test_ragged_spatial or test_channel_counts_not_multiple_of_64 or test_wgrad_ragged or "
               "(test_dgrad_with_fused_bn_backward_reduce and 3-38) or "
               "(test_fused_conv_bn_train_kernel and (3-64-64-32 or 3-96-48-16)) or "
@@ -295,17 +297,28 @@ _SANITIZED = ("test_pointwise_basic or test_ragged_spatial or test_channel_count
 def test_kernels_are_clean_under_the_sanitizers(kind):
     """compute-sanitizer's memcheck / racecheck, CPU edition: every global and shared memory access of the kernels is
     bounds-checked (torch's CPU allocations get red zones), resp. checked for unordered conflicting accesses between CUDA
-    threads (barriers, mbarriers and flags are real synchronisation in the simulator, so ordered accesses are silent)."""
+    threads (barriers, mbarriers and flags are real synchronisation in the simulator, so ordered accesses are silent).
+    Default: the kernels that have not run on hardware yet; SSEG_TEST_SANITIZERS_FULL=1: the wider list (2 min each)."""
     env, _ = _san_env(kind)
     log = "/tmp/cusim_%s_%d" % (kind, os.getpid())
     if kind == "thread":
         env["TSAN_OPTIONS"] += " log_path=" + log
     else:
         env["ASAN_OPTIONS"] += " log_path=" + log
-    _run_gpu_tests_on_sim(_SANITIZED, sms=5, extra_env=env, timeout=3000)
+    full = os.environ.get("SSEG_TEST_SANITIZERS_FULL", "0") == "1"
+    _run_gpu_tests_on_sim(_SANITIZED if full else _SANITIZED_QUICK, sms=5, extra_env=env, timeout=3000)
     import glob
-    reports = [open(f).read() for f in glob.glob(log + ".*")]
-    mine = [r for r in reports if "libsseg_sim" in r]
+    # one file per process, several reports per file; torch's own OpenMP pool (libgomp is not TSan-aware) shows up too
+    reports = [r for f in glob.glob(log + ".*") for r in open(f).read().split("==================")]
+    def between_cuda_threads(r):
+        """both conflicting accesses come from simulated CUDA threads (a kernel's store followed by torch's own OpenMP
+        workers reading the result is reported too: libgomp's hand-over is invisible to the sanitizer)"""
+        if kind == "address":
+            return "libsseg_sim" in r
+        head, _, rest = r.partition("Previous ")
+        prev = rest.split("\n\n")[0]
+        return "libsseg_sim" in head and "libsseg_sim" in prev
+    mine = [r for r in reports if between_cuda_threads(r)]
     for f in glob.glob(log + ".*"):
         os.remove(f)
     assert not mine, mine[0][:3000]
