@@ -49,9 +49,13 @@ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 bool pdl_enabled();
 #ifdef __CUSIM__
 // CPU simulator build (tests/cusim): the same kernels run as OS threads; a cooperative launch runs all CTAs concurrently.
+// A translation unit without static __shared__ variables may let ordinary launches run several CTAs at a time.
+#ifndef SSEG_SIM_PARALLEL_CTAS
+#define SSEG_SIM_PARALLEL_CTAS 1
+#endif
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {
-  return static_cast<cudaError_t>(::cusim::launch(grid, block, smem, false, [=]() { kernel(args...); }));
+  return static_cast<cudaError_t>(::cusim::launch(grid, block, smem, false, [=]() { kernel(args...); }, SSEG_SIM_PARALLEL_CTAS));
 }
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_coop(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t, Args&&... args) {

@@ -14,6 +14,7 @@
 //   (batch-norm statistics, lib/nn/modules/batchnorm.py:68-70 of the reference) and bf16 / fp32 store.
 #include <stdlib.h>
 
+#define SSEG_SIM_PARALLEL_CTAS 6  // CPU simulator only: no static __shared__ variables in this file
 #include "common.h"
 #include "ptx.cuh"
 

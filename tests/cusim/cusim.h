@@ -51,7 +51,7 @@ void atomic_lock();
 void atomic_unlock();
 void trap();
 void spin_pause();  // called from polling loops: yields and throws when the launch has been aborted
-int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& body);
+int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& body, int parallel_ctas = 1);
 
 }  // namespace cusim
 

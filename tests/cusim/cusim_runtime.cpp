@@ -53,6 +53,7 @@ struct Cta {
   uint32_t tmem_next = 0;
   std::vector<PendingMma> pending;
   int index = 0;
+  bool fresh = true;
 };
 
 static std::atomic<bool> g_abort{false};
@@ -447,8 +448,9 @@ static void reset_cta(Cta* c, long index) {  // a fresh CTA: garbage in shared a
   for (Bar& b : c->named) b = Bar();
   for (auto& w : c->warps) w.bar = Bar();
   memset(c->smem, 0xCD, c->smem_bytes + 1024);
-  if (c->tmem_next != 0 || index == 0)
+  if (c->tmem_next != 0 || c->fresh)
     for (int i = 0; i < 128 * 512; ++i) c->tmem[i] = NAN;
+  c->fresh = false;
   c->tmem_next = 0;
   c->pending.clear();
 }
@@ -478,9 +480,10 @@ struct PoolBarrier {
   }
 };
 
-// Ordinary launch: CTAs run one after another (static __shared__ variables are process-wide statics here), each by the
-// same `nthreads` worker threads. Cooperative launch: every CTA gets its own threads, all run concurrently.
-int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& body) {
+// Ordinary launch: `parallel_ctas` CTA slots (1 for translation units with static __shared__ variables, which are
+// process-wide statics here), each slot = `nthreads` worker threads walking its share of the CTAs. Cooperative launch:
+// every CTA gets its own slot, all run concurrently.
+int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::function<void()>& body, int parallel_ctas) {
   const int nthreads = (int)(block.x * block.y * block.z);
   const long nctas = (long)grid.x * grid.y * grid.z;
   if (nthreads <= 0 || nthreads > 1024 || nctas <= 0 || smem > 232448) {
@@ -492,7 +495,7 @@ int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::func
     return (int)g_last_error;
   }
   g_abort.store(false);
-  const long slots = cooperative ? nctas : 1;  // CTAs resident at the same time
+  const long slots = cooperative ? nctas : std::max(1L, std::min<long>(nctas, parallel_ctas));  // CTAs resident at the same time
   std::vector<Cta*> ctas;
   std::vector<PoolBarrier> gates(slots);
   for (long s = 0; s < slots; ++s) {

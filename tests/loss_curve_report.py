@@ -1,6 +1,8 @@
 """Report (not a test): 24 SGD steps through the public API on the emulated ABI next to the oracle with bf16 storage
 emulation and the plain fp32 oracle (= the reference's arithmetic); the table in profiles/r1_summary.md comes from here.
-    python tests/loss_curve_report.py
+    python tests/loss_curve_report.py [--sim] [--steps N]
+--sim: the library is libsseg_sim.so, i.e. the REAL csrc/*.cu kernel sources on the CPU simulator (tests/cusim), not the
+Python restatement of the ABI (minutes per step).
 """
 import sys, os, torch, torch.nn as nn
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -11,7 +13,15 @@ from oracle import segnet_oracle as O
 from test_program_dry import _seg
 from test_program_emulated import _load
 from mit_semseg.engine import _C, ops, functional as EF, program as PR
-lib=EmuLib(); _C.lib=lambda: lib; ops._stream=lambda: None
+SIM="--sim" in sys.argv
+STEPS=int(sys.argv[sys.argv.index("--steps")+1]) if "--steps" in sys.argv else 24
+if SIM:
+    os.environ.setdefault("CUSIM_SMS","16")
+    import conftest
+    lib=conftest.sim_lib()
+else:
+    lib=EmuLib()
+_C.lib=lambda: lib; ops._stream=lambda: None
 real=PR.SegProgram
 def factory(*a,**k):
     k["dry_run"]=True; p=real(*a,**k); p.dry_run=False; p.serial=True; return p
@@ -31,7 +41,7 @@ e32={k:v.clone().requires_grad_(v.is_floating_point() and "running" not in k) fo
 d32={k:v.clone().requires_grad_(v.is_floating_point() and "running" not in k) for k,v in dsd.items()}
 opt32=torch.optim.SGD([v for v in list(e32.values())+list(d32.values()) if v.requires_grad],lr=0.02,momentum=0.9,weight_decay=1e-4)
 rows=[]
-for step in range(24):
+for step in range(STEPS):
     feed=O.synth_batch(2,64,64,8,200+step%4)
     opt.zero_grad(); loss,acc=seg(feed); loss.backward(); opt.step()
     optr.zero_grad(); lr_,_=O.segmentation_forward(feed,e,d,enc,dec,O.BNState(True,emulate="bf16",update_running=True),0.4,dropout_p=0.0); lr_.backward(); optr.step()

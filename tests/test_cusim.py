@@ -322,3 +322,22 @@ def test_kernels_are_clean_under_the_sanitizers(kind):
     for f in glob.glob(log + ".*"):
         os.remove(f)
     assert not mine, mine[0][:3000]
+
+
+def test_every_kernel_waits_for_its_predecessor_grid():
+    """Every kernel is launched with programmatic stream serialization (common.h::launch_k), i.e. it may start while its
+    predecessor is still running: each __global__ body must execute griddepcontrol.wait (pdl_sync / pdl_wait) before it
+    touches global memory. The simulator ignores PDL, so the presence of the wait is checked on the source."""
+    import glob
+    import re
+    csrc = os.path.join(ROOT, "semantic-segmentation-pytorch_b200", "csrc")
+    kernels = 0
+    for path in sorted(glob.glob(os.path.join(csrc, "*.cu"))):
+        src = open(path).read()
+        parts = re.split(r"__global__\s+void", src)
+        for body in parts[1:]:
+            body = body[:body.find("\n}\n")]
+            name = re.search(r"(\w+)\s*\(", re.sub(r"__launch_bounds__\([^)]*\)", "", body, count=1)).group(1)
+            kernels += 1
+            assert "pdl_sync()" in body or "pdl_wait()" in body, "%s::%s has no griddepcontrol.wait" % (os.path.basename(path), name)
+    assert kernels >= 40
