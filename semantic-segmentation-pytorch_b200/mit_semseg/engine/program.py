@@ -19,6 +19,7 @@ Activations are NHWC bf16, accumulation is fp32 (TMEM), BN statistics / loss / a
 Reference call sites are cited on each record class.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -40,7 +41,9 @@ def _dist():
 
 def _coop_fits_estimate(n, h, w, k, channels):
     """CPU-side stand-in for sseg_conv_bn_train_fits / sseg_conv_dgrad_bn_fits (dry-run schedules only): tiles of 128 pixels
-    x 64|128 channels, one persistent CTA per SM (148), at most 512 tensor-memory columns per CTA."""
+    x 64|128 channels, one persistent CTA per SM (148; SSEG_DRY_RUN_SMS overrides it for schedules built for the CPU
+    simulator's smaller "device"), at most 512 tensor-memory columns per CTA."""
+    sms = int(os.environ.get("SSEG_DRY_RUN_SMS", "148"))
     if k == 1:
         m_tiles = math.ceil(n * h * w / 128)
     else:
@@ -48,7 +51,7 @@ def _coop_fits_estimate(n, h, w, k, channels):
         m_tiles = n * math.ceil(h / (128 // bw)) * math.ceil(w / bw)
     cp = _pad(channels, 8)
     cols = 64 if (channels <= 64 or m_tiles * math.ceil(cp / 128) <= 80) else 128
-    return math.ceil(m_tiles * math.ceil(cp / cols) / 148) * cols <= 512
+    return math.ceil(m_tiles * math.ceil(cp / cols) / sms) * cols <= 512
 
 
 class Act:

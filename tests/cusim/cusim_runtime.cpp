@@ -3,11 +3,14 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <sys/mman.h>
+#include <ucontext.h>
 
 #include <array>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -54,6 +57,7 @@ struct Cta {
   std::vector<PendingMma> pending;
   int index = 0;
   bool fresh = true;
+  std::chrono::steady_clock::time_point launch_t0;
 };
 
 static std::atomic<bool> g_abort{false};
@@ -86,9 +90,53 @@ static void raise_abort(const char* fmt, ...) {
     if (!(cond)) raise_abort(__VA_ARGS__);     \
   } while (0)
 
+// ---------------------------------------------------------------------------------------------------------- fibers
+// Default executor: the CUDA threads of a CTA are ucontext fibers on ONE OS thread (one OS thread per resident CTA). A
+// blocked fiber parks a predicate with the scheduler, which re-evaluates it without switching; when every fiber of a CTA is
+// parked on a false predicate the CTA is deadlocked, which is reported at once (no timeout involved). Polling loops on
+// global memory (grid barrier, peer flags) yield on every poll. CUSIM_EXECUTOR=threads selects the OS-thread-per-CUDA-thread
+// executor below instead (needed under ThreadSanitizer / AddressSanitizer, which do not follow ucontext switches).
+struct Fiber {
+  ucontext_t ctx;
+  char* stack = nullptr;
+  ThreadCtx tctx;
+  bool done = false;
+  const std::function<bool()>* pred = nullptr;
+  const char* what = nullptr;
+  long detail = 0;
+};
+static thread_local Fiber* t_fiber = nullptr;       // the running fiber (null on plain OS threads)
+static thread_local ucontext_t t_sched;             // the scheduler of this OS thread
+static const size_t kFiberStack = 512 * 1024;
+
+static bool use_fibers() {
+  const char* e = getenv("CUSIM_EXECUTOR");
+  return !(e != nullptr && strcmp(e, "threads") == 0);
+}
+
+static void fiber_switch_out() {
+  Fiber* f = t_fiber;
+  swapcontext(&f->ctx, &t_sched);
+  if (g_abort.load()) throw Abort();
+}
+
+static void fiber_block(const std::function<bool()>& pred, const char* what, long detail) {
+  Fiber* f = t_fiber;
+  f->pred = &pred, f->what = what, f->detail = detail;
+  fiber_switch_out();
+}
+
 template <typename Pred>
 static void wait_until(Cta* c, std::unique_lock<std::mutex>& lk, Pred pred, const char* what, long detail,
                        std::condition_variable* cv = nullptr) {
+  if (t_fiber != nullptr) {
+    if (pred()) return;
+    lk.unlock();  // never switch away with a lock held
+    const std::function<bool()> fn = [&] { return pred(); };
+    fiber_block(fn, what, detail);
+    lk.lock();
+    return;
+  }
   const auto t0 = std::chrono::steady_clock::now();
   const double limit = timeout_seconds();
   if (cv == nullptr) cv = &c->cv;
@@ -166,17 +214,14 @@ void trap() { raise_abort("__trap() executed by CTA %d thread %d", tl.cta ? tl.c
 
 void spin_pause() {
   if (g_abort.load()) throw Abort();
-  static thread_local std::chrono::steady_clock::time_point t0;
   static thread_local long spins = 0;
-  if (spins++ == 0) t0 = std::chrono::steady_clock::now();
-  if ((spins & 1023) == 0) {
-    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    if (dt > timeout_seconds()) {
-      spins = 0;
-      raise_abort("deadlock: CTA %d thread %d polled a global flag for %.0f s", tl.cta ? tl.cta->index : -1, tl.linear_tid, dt);
-    }
+  if ((++spins & 1023) == 0 && tl.cta != nullptr) {  // watchdog of polling loops: measured from the start of the launch
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - tl.cta->launch_t0).count();
+    if (dt > timeout_seconds())
+      raise_abort("deadlock: CTA %d thread %d still polls a global flag %.0f s after the launch started", tl.cta->index, tl.linear_tid, dt);
   }
-  sched_yield();
+  if (t_fiber != nullptr) fiber_switch_out();  // let the other fibers of this CTA run, then poll again
+  else sched_yield();
 }
 
 uint32_t smem_handle(const void* p) {
@@ -235,8 +280,13 @@ void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
 
 bool mbar_test(uint64_t* bar, uint32_t parity) {
   Cta* c = tl.cta;
-  std::lock_guard<std::mutex> lk(c->mu);
-  return reinterpret_cast<MBar*>(bar)->phase != (parity & 1);
+  bool ok;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    ok = reinterpret_cast<MBar*>(bar)->phase != (parity & 1);
+  }
+  if (!ok) spin_pause();  // a try_wait loop in kernel code must let the other threads run
+  return ok;
 }
 
 void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -480,6 +530,78 @@ struct PoolBarrier {
   }
 };
 
+static void fiber_entry() {
+  Fiber* f = t_fiber;
+  const std::function<void()>* body = reinterpret_cast<const std::function<void()>*>(f->detail);
+  try {
+    (*body)();
+  } catch (const Abort&) {
+  }
+  f->done = true;
+  swapcontext(&f->ctx, &t_sched);
+}
+
+// All CTAs j = first, first + stride, ... of one launch, on the calling OS thread.
+static void run_ctas_as_fibers(Cta* c, long first, long stride, long nctas, dim3 grid, dim3 block, const std::function<void()>& body) {
+  const int n = c->nthreads;
+  std::vector<Fiber> fibers(n);
+  for (Fiber& f : fibers) {
+    f.stack = static_cast<char*>(mmap(nullptr, kFiberStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE, -1, 0));
+    if (f.stack == MAP_FAILED) abort();
+  }
+  for (long j = first; j < nctas && !g_abort.load(); j += stride) {
+    reset_cta(c, j);
+    for (int t = 0; t < n; ++t) {
+      Fiber& f = fibers[t];
+      getcontext(&f.ctx);
+      f.ctx.uc_stack.ss_sp = f.stack, f.ctx.uc_stack.ss_size = kFiberStack, f.ctx.uc_link = nullptr;
+      makecontext(&f.ctx, fiber_entry, 0);
+      f.done = false, f.pred = nullptr;
+      f.detail = reinterpret_cast<long>(&body);  // read once by fiber_entry
+      f.tctx.cta = c, f.tctx.linear_tid = t, f.tctx.bdim = block, f.tctx.gdim = grid;
+      f.tctx.tid = make_uint3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      f.tctx.bid = make_uint3((unsigned)(j % grid.x), (unsigned)((j / grid.x) % grid.y), (unsigned)(j / ((long)grid.x * grid.y)));
+    }
+    int remaining = n;
+    while (remaining > 0) {
+      bool ran = false;
+      for (int t = 0; t < n; ++t) {
+        Fiber& f = fibers[t];
+        if (f.done) continue;
+        if (f.pred != nullptr) {
+          if (!g_abort.load() && !(*f.pred)()) continue;
+          f.pred = nullptr;
+        }
+        ran = true;
+        tl = f.tctx;
+        t_fiber = &f;
+        swapcontext(&t_sched, &f.ctx);
+        t_fiber = nullptr;
+        if (f.done) {
+          cta_thread_exit(c);
+          --remaining;
+        }
+      }
+      if (!ran) {  // every live fiber is parked on a false predicate: nothing inside this CTA can ever release them
+        std::string msg = "deadlock in CTA " + std::to_string(c->index) + ": every live thread is blocked;";
+        int shown = 0;
+        for (int t = 0; t < n && shown < 6; ++t)
+          if (!fibers[t].done && (t == 0 || fibers[t].what != fibers[t - 1].what || fibers[t].detail != fibers[t - 1].detail)) {
+            msg += " thread " + std::to_string(t) + " waits on " + fibers[t].what + " (" + std::to_string(fibers[t].detail) + ");";
+            ++shown;
+          }
+        {
+          std::lock_guard<std::mutex> lk(g_msg_mu);
+          if (!g_abort.load()) g_abort_msg = msg;
+        }
+        g_abort.store(true);  // the parked fibers are resumed once more and unwind with Abort
+      }
+    }
+    tl.cta = nullptr;
+  }
+  for (Fiber& f : fibers) munmap(f.stack, kFiberStack);
+}
+
 // Ordinary launch: `parallel_ctas` CTA slots (1 for translation units with static __shared__ variables, which are
 // process-wide statics here), each slot = `nthreads` worker threads walking its share of the CTAs. Cooperative launch:
 // every CTA gets its own slot, all run concurrently.
@@ -500,9 +622,18 @@ int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::func
   std::vector<PoolBarrier> gates(slots);
   for (long s = 0; s < slots; ++s) {
     ctas.push_back(new_cta(nthreads, smem));
+    ctas.back()->launch_t0 = std::chrono::steady_clock::now();
     gates[s].n = nthreads;
   }
   std::vector<std::thread> threads;
+  if (use_fibers()) {
+    if (slots == 1) {
+      run_ctas_as_fibers(ctas[0], 0, 1, nctas, grid, block, body);
+    } else {
+      for (long s = 0; s < slots; ++s)
+        threads.emplace_back([=, &body, &ctas] { run_ctas_as_fibers(ctas[s], s, slots, nctas, grid, block, body); });
+    }
+  } else {
   threads.reserve(slots * nthreads);
   for (long s = 0; s < slots; ++s)
     for (int t = 0; t < nthreads; ++t)
@@ -527,6 +658,7 @@ int launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const std::func
           gates[s].wait();
         }
       });
+  }
   for (auto& th : threads) th.join();
   for (Cta* c : ctas) free_cta(c);
   if (g_abort.load()) {

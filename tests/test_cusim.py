@@ -252,7 +252,9 @@ def _san_env(kind):
                         text=True).stdout.strip()
     if not os.path.isabs(rt) or not os.path.exists(rt):
         pytest.skip("no %s sanitizer runtime" % kind)
-    env = dict(os.environ, CUSIM_SANITIZE=kind, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0", TSAN_OPTIONS="exitcode=66 report_signal_unsafe=0")
+    # the sanitizers do not follow ucontext switches: OS thread per CUDA thread instead of the default fiber executor
+    env = dict(os.environ, CUSIM_SANITIZE=kind, CUSIM_EXECUTOR="threads", LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0",
+               TSAN_OPTIONS="exitcode=66 report_signal_unsafe=0")
     build = subprocess.run([os.path.join(ROOT, "tests", "cusim", "build_sim.sh")], capture_output=True, text=True,
                            env={k: v for k, v in env.items() if k != "LD_PRELOAD"})
     assert build.returncode == 0, build.stderr[-2000:]
@@ -276,9 +278,12 @@ def test_detectors_catch_planted_defects():
     import conftest
     conftest.sim_lib()
     plain = os.path.join(ROOT, "tests", "cusim", "_build", "libsseg_sim.so")
-    out = _selftest(plain, "stuck", dict(os.environ, CUSIM_TIMEOUT="2"))
+    out = _selftest(plain, "stuck", dict(os.environ, CUSIM_TIMEOUT="2", CUSIM_EXECUTOR="threads"))      # time-out watchdog
     assert "deadlock: CTA 0 thread 32 waited" in out.stdout + out.stderr and "rc 719" in out.stdout
-    assert "rc 0" in _selftest(plain, "notstuck", dict(os.environ, CUSIM_TIMEOUT="2")).stdout
+    out = _selftest(plain, "stuck", dict(os.environ, CUSIM_EXECUTOR="fibers"))     # fiber scheduler: found at once
+    assert "deadlock in CTA 0: every live thread is blocked; thread 32 waits on mbarrier" in out.stdout + out.stderr
+    for ex in ("threads", "fibers"):
+        assert "rc 0" in _selftest(plain, "notstuck", dict(os.environ, CUSIM_TIMEOUT="2", CUSIM_EXECUTOR=ex)).stdout
     env, lib = _san_env("address")
     out = _selftest(lib, "oob", env)
     assert "heap-buffer-overflow" in out.stderr and "oob_kernel" in out.stderr
