@@ -20,38 +20,32 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# `-m gpu` tests re-run on the simulator inside the CPU suite (a few seconds each; the full gpu suite also passes on it
-# but takes ~25 minutes: SSEG_GPU_TESTS_ON_EMULATOR=sim SSEG_TEST_EXPERIMENTAL=1 python -m pytest tests -m gpu -n 6)
-_CURATED = " or ".join([
-    # tcgen05 GEMM family: validated on B200 -> pins the simulator's TMA / UMMA-descriptor / tensor-memory model
-    "test_pointwise_basic", "test_3x3_dilated", "test_virtual_concat_3x3", "test_classifier_f32_bias", "test_addend",
-    "test_wgrad_3x3", "test_wgrad_ragged", "(test_dgrad_with_fused_bn_backward_reduce and 3-38)",
-    # never run on a GPU yet: cooperative conv+BN kernels (small grids), folded epilogue, fp32-pair kernels
-    "(test_fused_conv_bn_train_kernel and (1-64-128-32 or 3-64-64-32 or 3-96-48-16 or 1-128-256-16))",
-    "(test_fused_conv_bn_dgrad_kernel and (1-32-64-128 or 3-32-128-64 or 3-14-48-96 or 1-16-256-64))",
-    "test_conv_with_folded_affine_epilogue", "test_pair_kernels_against_torch",
-    # streaming kernels with warp shuffles / shared-memory reductions
-    "(test_bn_forward_backward and 64-40)", "test_maxpool", "(test_bilinear and 3-64)",
-])
+# Every kernel-level `-m gpu` test (the whole-step tests pass too - profiles/r1_gpu_suite_on_simulator.log - but take
+# 1-15 minutes each:  SSEG_GPU_TESTS_ON_EMULATOR=sim SSEG_TEST_EXPERIMENTAL=1 SSEG_DRY_RUN_SMS=16 CUSIM_SMS=16 python -m
+# pytest tests/test_gpu_e2e.py tests/test_gpu_widen_hrnet.py -m gpu -n 7)
+_KERNEL_LEVEL = ("test_gpu_igemm or test_gpu_elementwise or test_fused_conv_bn_train_kernel or test_fused_conv_bn_dgrad_kernel or "
+                 "test_conv_with_folded_affine_epilogue or test_pair_kernels_against_torch or test_mobilenet_kernels")
 
 
-def _run_gpu_tests_on_sim(kexpr, sms, extra_env=None, timeout=1500):
-    env = dict(os.environ, SSEG_GPU_TESTS_ON_EMULATOR="sim", SSEG_TEST_EXPERIMENTAL="1", CUSIM_SMS=str(sms), CUSIM_TIMEOUT="60")
+def _run_gpu_tests_on_sim(kexpr, sms, extra_env=None, timeout=1500, workers=4):
+    env = dict(os.environ, SSEG_GPU_TESTS_ON_EMULATOR="sim", SSEG_TEST_EXPERIMENTAL="1", CUSIM_SMS=str(sms),
+               SSEG_DRY_RUN_SMS=str(sms), CUSIM_TIMEOUT="120")
     env.update(extra_env or {})
-    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-n", "4", "-p", "no:cacheprovider", "-k", kexpr,
+    cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-n", str(workers), "-p", "no:cacheprovider", "-k", kexpr,
            os.path.join(ROOT, "tests", "test_gpu_igemm.py"), os.path.join(ROOT, "tests", "test_gpu_elementwise.py"),
-           os.path.join(ROOT, "tests", "test_gpu_widen_hrnet.py")]
+           os.path.join(ROOT, "tests", "test_gpu_widen_hrnet.py"), os.path.join(ROOT, "tests", "test_gpu_e2e.py")]
     out = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
     tail = (out.stdout + out.stderr)[-4000:]
     assert out.returncode == 0, tail
-    return out.stdout
+    return int(out.stdout.strip().splitlines()[-1].split(" passed")[0].split()[-1])
 
 
-def test_kernel_sources_pass_their_gpu_tests_on_the_simulator():
-    out = _run_gpu_tests_on_sim(_CURATED, sms=8)
-    assert " passed" in out and "failed" not in out
-    n = int(out.strip().splitlines()[-1].split(" passed")[0].split()[-1])
-    assert n >= 29, out[-500:]
+def test_every_kernel_level_gpu_test_passes_on_the_simulator():
+    """All of test_gpu_igemm.py and test_gpu_elementwise.py (the 57 tests that pass on B200: they pin the simulator's
+    model of TMA / UMMA descriptors / tensor memory) plus the kernel-level tests of the code that has not run on hardware
+    yet - both cooperative conv+BN kernels at every size (148 simulated SMs, up to 7 resident accumulators per CTA), the
+    folded-affine epilogue, the fp32-pair kernels, the depthwise / stem kernels with the MobileNetV2 inference schedule."""
+    assert _run_gpu_tests_on_sim(_KERNEL_LEVEL, sms=148) >= 83
 
 
 def test_cooperative_kernels_with_uneven_tile_distribution_and_the_persistent_gemm():
@@ -59,8 +53,15 @@ def test_cooperative_kernels_with_uneven_tile_distribution_and_the_persistent_ge
     many tiles and both tensor-memory buffers (passes on B200 with the same switches: profiles/r1_summary.md)."""
     _run_gpu_tests_on_sim("(test_fused_conv_bn_train_kernel and (1-64-128-32 or 3-64-64-32)) or "
                           "(test_fused_conv_bn_dgrad_kernel and (3-32-128-64 or 1-16-256-64))", sms=5)
-    _run_gpu_tests_on_sim("test_pointwise_wide_k_and_stats or test_3x3_cout256_cin512 or test_ragged_spatial", sms=8,
+    _run_gpu_tests_on_sim("test_gpu_igemm and not wgrad", sms=8,
                           extra_env={"SSEG_IGEMM_PERSISTENT": "2", "SSEG_IGEMM_PERSISTENT_CTAS": "5"})
+
+
+def test_whole_training_steps_on_the_simulator():
+    """Two whole programs through the real kernel sources: the default step captured/replayed vs the autograd path, and the
+    SSEG_COOP_BN=1 step (fused conv+BN kernels in both directions) against the default schedule."""
+    assert _run_gpu_tests_on_sim("test_fused_conv_bn_train_schedule_matches_the_default_step or "
+                                 "test_graph_replay_matches_eager_and_autograd_path", sms=16, workers=2, timeout=2400) == 2
 
 
 # ------------------------------------------------------------------------------------------------ two ranks, one process
