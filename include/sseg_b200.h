@@ -430,6 +430,21 @@ int sseg_upsample_softmax(const float* logits, long ld, int N, int Hi, int Wi, i
 int sseg_nhwc_bf16_to_nchw_f32(const void* x, long ld, int N, int H, int W, int C, float* out, sseg_stream_t stream);
 int sseg_nchw_f32_to_nhwc_bf16(const float* x, int N, int H, int W, int C, void* out, long ld, sseg_stream_t stream);
 
+/* ---- input pipeline --------------------------------------------------- */
+/* The reference's img_transform (mit_semseg/dataset.py:53-58: float32(x)/255, then (x - mean)/std per channel, HWC -> CHW)
+ * on the device, so that the bytes - a quarter of the fp32 tensor - are what crosses PCIe.
+ * img_u8 uint8 [N][H][W][3] (W % 4 == 0); valid_hw DEVICE int32 [N][2] = rows, columns of image n that are real: outside
+ * them the output is 0.0f, which is what the reference's pre-zeroed batch tensor holds there (dataset.py:150-151,179);
+ * mean_std HOST float[6] = mean r,g,b then std r,g,b; out fp32 [N][3][H][W]. Same fp32 operations in the same order as
+ * the reference (IEEE division): bit-identical. */
+int sseg_image_transform(const void* img_u8, int N, int H, int W, const int* valid_hw, const float* mean_std, float* out,
+                         sseg_stream_t stream);
+/* The reference's segm_transform (dataset.py:60-63: stored id - 1 as int64) on the device. seg_u8 uint8 [N][Hs][Ws] = the
+ * label map already strided by the segm_downsampling_rate `rate`; rows / columns beyond ceil(valid_hw / rate) are padding
+ * and come out as 0 (NOT -1: the reference pads its batch label tensor with zeros, dataset.py:152-155,180). */
+int sseg_label_transform(const void* seg_u8, int N, int Hs, int Ws, const int* valid_hw, int rate, long long* out,
+                         sseg_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -134,6 +134,8 @@ _SIGNATURES = {
     "sseg_bn_bwd_reduce": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, c_long, c_long, c_int, _p],
     "sseg_bn_bwd_apply": [_p, c_long, _p, c_long, _p, c_long, _p, _p, _p, _p, _p, _p, _p, _p, c_float, _p, c_long, _p,
                           c_long, c_long, c_long, c_int, c_int, c_int, _p, _p],
+    "sseg_image_transform": [_p, c_int, c_int, c_int, _p, POINTER(c_float), _p, _p],
+    "sseg_label_transform": [_p, c_int, c_int, c_int, _p, c_int, _p, _p],
     "sseg_peer_alloc": [ctypes.c_size_t, POINTER(c_void_p), _p],
     "sseg_peer_open": [_p, POINTER(c_void_p)],
     "sseg_peer_close": [_p],

@@ -487,6 +487,26 @@ def nchw_f32_to_nhwc_bf16(x, out):
     _C.check(_C.lib().sseg_nchw_f32_to_nhwc_bf16(_C.ptr(x), n, h, w, c, _C.ptr(out), _pix(out)[2], _stream()))
 
 
+def image_transform(img_u8, valid_hw, out, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """uint8 [N,H,W,3] -> normalised fp32 [N,3,H,W] (the reference's img_transform, dataset.py:53-58), zeros outside each
+    image's valid rows / columns (valid_hw: device int32 [N,2])."""
+    n, h, w, c = img_u8.shape
+    assert c == 3 and img_u8.dtype == torch.uint8 and img_u8.is_contiguous() and out.is_contiguous()
+    assert tuple(out.shape) == (n, 3, h, w) and out.dtype == torch.float32 and valid_hw.dtype == torch.int32
+    ms = (_C.c_float * 6)(*[float(torch.tensor(v, dtype=torch.float32)) for v in tuple(mean) + tuple(std)])
+    _C.check(_C.lib().sseg_image_transform(_C.ptr(img_u8), n, h, w, _C.ptr(valid_hw), ms, _C.ptr(out), _stream()))
+    return out
+
+
+def label_transform(seg_u8, valid_hw, rate, out):
+    """uint8 [N,Hs,Ws] stored ids -> int64 labels id - 1 (the reference's segm_transform, dataset.py:60-63); 0 in the padding."""
+    n, hs, ws = seg_u8.shape
+    assert seg_u8.dtype == torch.uint8 and seg_u8.is_contiguous() and out.is_contiguous() and out.dtype == torch.int64
+    assert tuple(out.shape) == (n, hs, ws) and valid_hw.dtype == torch.int32
+    _C.check(_C.lib().sseg_label_transform(_C.ptr(seg_u8), n, hs, ws, _C.ptr(valid_hw), int(rate), _C.ptr(out), _stream()))
+    return out
+
+
 class WeightTable:
     """Device table of sseg_weight_desc_t for the batched weight re-layout / gradient re-layout kernels.
     entries: list of dicts with keys w, wf, wd, g_src, g_dst (tensors or None), O, I, T, o_pad."""

@@ -561,6 +561,31 @@ class EmuLib:
                                                   .reshape(-1, C)))
         return 0
 
+    # ---- input pipeline
+    def sseg_image_transform(self, img, N, H, W, valid, mean_std, out, stream):
+        if W % 4:
+            self._err = b"sseg_image_transform: W must be a multiple of 4"
+            return -1
+        x = flat(img, N * H * W * 3, torch.uint8).view(N, H, W, 3)
+        v = flat(valid, 2 * N, torch.int32).view(N, 2)
+        ms = torch.tensor([mean_std[i] for i in range(6)], dtype=torch.float32)
+        o = flat(out, N * 3 * H * W, torch.float32).view(N, 3, H, W)
+        o.zero_()
+        for n in range(N):
+            h, w = int(v[n, 0]), int(v[n, 1])
+            o[n, :, :h, :w] = ((x[n, :h, :w].float() / 255.).permute(2, 0, 1) - ms[:3].view(3, 1, 1)) / ms[3:].view(3, 1, 1)
+        return 0
+
+    def sseg_label_transform(self, seg, N, Hs, Ws, valid, rate, out, stream):
+        x = flat(seg, N * Hs * Ws, torch.uint8).view(N, Hs, Ws)
+        v = flat(valid, 2 * N, torch.int32).view(N, 2)
+        o = flat(out, N * Hs * Ws, torch.int64).view(N, Hs, Ws)
+        o.zero_()
+        for n in range(N):
+            h, w = -(-int(v[n, 0]) // rate), -(-int(v[n, 1]) // rate)
+            o[n, :h, :w] = x[n, :h, :w].long() - 1
+        return 0
+
     # ---- fp32-accurate inference (pairs of bf16 tensors)
     @staticmethod
     def _pair_val(hi, lo, ld, P, C):

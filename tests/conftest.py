@@ -95,6 +95,8 @@ def _gpu_tests_on_the_emulator(request, monkeypatch):
             k["device"] = "cpu"
         return real_to(self, *a, **k)
     monkeypatch.setattr(torch.Tensor, "to", to)
+    from mit_semseg.engine import prefetch as PF
+    monkeypatch.setattr(PF.DevicePrefetcher, "_use_streams", False)
     # step programs: built as schedules on CPU tensors, executed against the emulator, no CUDA graphs / streams
     from mit_semseg.engine import accurate as ACC
     from mit_semseg.engine import program as PR

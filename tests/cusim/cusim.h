@@ -161,6 +161,10 @@ static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
 #define __expf(x) expf(x)
 #define __logf(x) logf(x)
 static inline float __fdividef(float a, float b) { return a / b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fmul_rn(float a, float b) { return a * b; }
 static inline float __frcp_rn(float a) { return 1.0f / a; }
 static inline float __saturatef(float a) { return a < 0.f ? 0.f : (a > 1.f ? 1.f : a); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
