@@ -1053,6 +1053,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
         __threadfence();
         bar_sync_epilogue();
         if (t == 0) {
+          __threadfence();  // release: everything this CTA's threads published before the barrier above, then the arrival
           atomicAdd(q.counter, 1u);
           unsigned int polls = 0;
           while (ld_acquire_gpu(q.counter) < gridDim.x) {
@@ -1402,6 +1403,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
         __threadfence();
         bar_sync_epilogue();
         if (t == 0) {
+          __threadfence();  // release: everything this CTA's threads published before the barrier above, then the arrival
           atomicAdd(q.counter, 1u);
           unsigned int polls = 0;
           while (ld_acquire_gpu(q.counter) < gridDim.x) {

@@ -12,6 +12,11 @@ if [ -n "$CUSIM_SANITIZE" ]; then
   SAN="-fsanitize=$CUSIM_SANITIZE -fno-omit-frame-pointer"
   OUT="$HERE/_build/$CUSIM_SANITIZE"
 fi
+# CUSIM_COVERAGE=1: gcov-instrumented build (which lines of csrc/*.cu do the tests execute?) in _build/coverage
+if [ -n "$CUSIM_COVERAGE" ]; then
+  SAN="--coverage -O0"
+  OUT="$HERE/_build/coverage"
+fi
 CUDA_INC="${CUDA_HOME:-/usr/local/cuda}/include"
 mkdir -p "$OUT"
 FLAGS="$SAN -O2 -g -fno-strict-aliasing -std=c++17 -fPIC -pthread -w -I$HERE -I$CUDA_INC -include $HERE/cusim.h"
