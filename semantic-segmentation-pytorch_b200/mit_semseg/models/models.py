@@ -49,6 +49,11 @@ class SegmentationModule(SegmentationModuleBase):
 
     def forward(self, feed_dict, *, segSize=None):
         from ..engine import functional as EF
+        if isinstance(feed_dict, (list, tuple)):
+            # `user_scattered_collate` hands the loader's list through; with one GPU train.py passes it on as it is
+            # (train.py:176-183 only wraps the module for len(gpus) > 1). Later upstream revisions unwrap it here too.
+            assert len(feed_dict) == 1, "one process drives one GPU: expected this GPU's batch only"
+            feed_dict = feed_dict[0]
         if segSize is None:
             return EF.segmentation_train_step(self, feed_dict['img_data'], feed_dict['seg_label'])
         return EF.segmentation_inference(self, feed_dict['img_data'], segSize)

@@ -47,22 +47,19 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
-@pytest.fixture(autouse=True)
-def _gpu_tests_on_the_emulator(request, monkeypatch):
-    """SSEG_GPU_TESTS_ON_EMULATOR=1 (development aid, no GPU needed): run the `gpu`-marked KERNEL tests against
-    tests/abi_emulator.py with every device="cuda" request mapped to the CPU. A test that passes on the B200 and here
-    pins the emulator to the kernels' validated behaviour; a gated test that passes here has sound test code."""
-    if not (EMULATE and "gpu" in request.keywords):
-        yield
-        return
+def install_cuda_stand_in(setattr_, mode):
+    """Map every device="cuda" request to the CPU and the library to the emulated ABI (mode "1") or to the simulated kernel
+    sources (mode "sim"). `setattr_(obj, name, value)`: monkeypatch.setattr inside tests, plain setattr for a whole process
+    (tests/run_reference_script.py runs the reference's unmodified train.py that way)."""
     import functools
+    import types
     import torch
     import torch.nn as nn
     from abi_emulator import EmuLib
     from mit_semseg.engine import _C, ops
-    lib = sim_lib() if EMULATE_MODE == "sim" else EmuLib()
-    monkeypatch.setattr(_C, "lib", lambda: lib)
-    monkeypatch.setattr(ops, "_stream", lambda: None)
+    lib = sim_lib() if mode == "sim" else EmuLib()
+    setattr_(_C, "lib", lambda: lib)
+    setattr_(ops, "_stream", lambda: None)
 
     def remap(fn):
         @functools.wraps(fn)
@@ -72,21 +69,20 @@ def _gpu_tests_on_the_emulator(request, monkeypatch):
             return fn(*a, **k)
         return wrapped
     for name in ("randn", "rand", "zeros", "ones", "empty", "full", "tensor", "arange", "randint"):
-        monkeypatch.setattr(torch, name, remap(getattr(torch, name)))
+        setattr_(torch, name, remap(getattr(torch, name)))
     real_gen = torch.Generator
 
     class _CpuGenerator(real_gen):
         def __new__(cls, device="cpu"):
             return real_gen(device="cpu")
-    monkeypatch.setattr(torch, "Generator", _CpuGenerator)
-    import types
-    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
-    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
-    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
-    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
-    monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
-    monkeypatch.setattr(nn.Module, "cuda", lambda self, *a, **k: self)
+    setattr_(torch, "Generator", _CpuGenerator)
+    setattr_(torch.cuda, "synchronize", lambda *a, **k: None)
+    setattr_(torch.cuda, "is_available", lambda: True)
+    setattr_(torch.cuda, "set_device", lambda *a, **k: None)
+    setattr_(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+    setattr_(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    setattr_(torch.Tensor, "is_cuda", property(lambda self: True))
+    setattr_(nn.Module, "cuda", lambda self, *a, **k: self)
     real_to = torch.Tensor.to
 
     def to(self, *a, **k):
@@ -94,9 +90,9 @@ def _gpu_tests_on_the_emulator(request, monkeypatch):
         if str(k.get("device", "")).startswith("cuda"):
             k["device"] = "cpu"
         return real_to(self, *a, **k)
-    monkeypatch.setattr(torch.Tensor, "to", to)
+    setattr_(torch.Tensor, "to", to)
     from mit_semseg.engine import prefetch as PF
-    monkeypatch.setattr(PF.DevicePrefetcher, "_use_streams", False)
+    setattr_(PF.DevicePrefetcher, "_use_streams", False)
     # step programs: built as schedules on CPU tensors, executed against the emulator, no CUDA graphs / streams
     from mit_semseg.engine import accurate as ACC
     from mit_semseg.engine import program as PR
@@ -107,6 +103,17 @@ def _gpu_tests_on_the_emulator(request, monkeypatch):
             k["dry_run"] = True
             _real(self, *a, **k)
             self.dry_run, self.serial = False, True
-        monkeypatch.setattr(cls, "__init__", init)
-        monkeypatch.setattr(cls, "capture", lambda self: None)
+        setattr_(cls, "__init__", init)
+        setattr_(cls, "capture", lambda self: None)
+
+
+@pytest.fixture(autouse=True)
+def _gpu_tests_on_the_emulator(request, monkeypatch):
+    """SSEG_GPU_TESTS_ON_EMULATOR=1 (development aid, no GPU needed): run the `gpu`-marked KERNEL tests against
+    tests/abi_emulator.py with every device="cuda" request mapped to the CPU. A test that passes on the B200 and here
+    pins the emulator to the kernels' validated behaviour; a gated test that passes here has sound test code."""
+    if not (EMULATE and "gpu" in request.keywords):
+        yield
+        return
+    install_cuda_stand_in(monkeypatch.setattr, EMULATE_MODE)
     yield
