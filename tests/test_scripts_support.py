@@ -2,7 +2,8 @@
 (yacs work-alike + the default tree), `mit_semseg.utils`, `mit_semseg.lib.utils.as_numpy`, `mit_semseg.dataset` - and the
 proof: the reference's own train.py, read from /root/reference, trains ResNet18dilated+PPM_deepsup on synthetic images for
 two epochs through this engine (kernels replaced by the emulated ABI; there is no GPU in the build container), writes the
-reference's checkpoint files and resumes from them."""
+reference's checkpoint files and resumes from them; the reference's own eval.py then evaluates the checkpoint (multi-scale)
+and reports the accuracy / mean IoU the fp32 oracle computes for it."""
 import glob
 import importlib.util
 import json
@@ -159,3 +160,34 @@ def test_the_reference_train_script_runs_unmodified_on_this_engine(tmp_path):
     log = out.stdout + out.stderr
     assert out.returncode == 0, log[-3000:]
     assert "Loading weights for net_encoder" in log and "Epoch: [3][0/3]" in log and (ckpt / "encoder_epoch_3.pth").exists()
+
+    # ---- the reference's eval.py, unmodified, on the epoch-2 checkpoint (multi-scale, one image at a time); it reads
+    # data/color150.mat relative to the working directory, hence cwd = the reference tree (nothing is written there)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_script.py"), "1", os.path.join(REF, "eval.py"),
+                          "--cfg", str(y), "--gpu", "0", "DATASET.list_val", str(odgt), "VAL.checkpoint", "epoch_2.pth"],
+                         capture_output=True, text=True, cwd=REF, timeout=900)
+    log = out.stdout + out.stderr
+    assert out.returncode == 0 and "Evaluation Done!" in log, log[-3000:]
+    summary = [line for line in log.splitlines() if line.startswith("Mean IoU")][0]
+    miou, acc = float(summary.split("Mean IoU: ")[1].split(",")[0]), float(summary.split("Accuracy: ")[1].split("%")[0])
+    # the same evaluation with the oracle (the reference's fp32 arithmetic) on the same checkpoint and images
+    import copy
+    from mit_semseg import dataset as D, utils as U
+    from oracle import segnet_oracle as O
+    val = D.ValDataset(str(data), copy.deepcopy(recs), S.dataset_options(imgSizes=(64, 80), imgMaxSize=128))
+    esd, dsd = torch.load(str(ckpt / "encoder_epoch_2.pth")), torch.load(str(ckpt / "decoder_epoch_2.pth"))
+    accm, im, um = U.AverageMeter(), U.AverageMeter(), U.AverageMeter()
+    for i in range(len(val)):
+        item = val[i]
+        lab = item["seg_label"][0].numpy()
+        scores = torch.zeros(1, 150, *lab.shape)
+        for img in item["img_data"]:
+            with torch.no_grad():
+                scores = scores + O.segmentation_forward({"img_data": img}, esd, dsd, "resnet18dilated", "ppm_deepsup",
+                                                         O.BNState(False), None, segSize=lab.shape) / len(item["img_data"])
+        pred = scores.argmax(1)[0].numpy()
+        a, pix = U.accuracy(pred, lab)
+        inter, union = U.intersectionAndUnion(pred, lab, 150)
+        accm.update(a, pix), im.update(inter), um.update(union)
+    want_miou, want_acc = float((im.sum / (um.sum + 1e-10)).mean()), accm.average() * 100
+    assert abs(acc - want_acc) <= 0.5 and abs(miou - want_miou) <= 1e-3, (summary, want_miou, want_acc)
