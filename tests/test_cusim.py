@@ -41,20 +41,12 @@ def _run_gpu_tests_on_sim(kexpr, sms, extra_env=None, timeout=1500, workers=4):
 
 
 def test_every_kernel_level_gpu_test_passes_on_the_simulator():
-    """All of test_gpu_igemm.py and test_gpu_elementwise.py (the 57 tests that pass on B200: they pin the simulator's
-    model of TMA / UMMA descriptors / tensor memory) plus the kernel-level tests of the code that has not run on hardware
-    yet - both cooperative conv+BN kernels at every size (148 simulated SMs, up to 7 resident accumulators per CTA), the
-    folded-affine epilogue, the fp32-pair kernels, the depthwise / stem kernels with the MobileNetV2 inference schedule."""
-    assert _run_gpu_tests_on_sim(_KERNEL_LEVEL, sms=148) >= 83
-
-
-def test_cooperative_kernels_with_uneven_tile_distribution_and_the_persistent_gemm():
-    """5 'SMs' -> CTAs hold different numbers of resident accumulators; the persistent GEMM variant walks 5 CTAs through
-    many tiles and both tensor-memory buffers (passes on B200 with the same switches: profiles/r1_summary.md)."""
-    _run_gpu_tests_on_sim("(test_fused_conv_bn_train_kernel and (1-64-128-32 or 3-64-64-32)) or "
-                          "(test_fused_conv_bn_dgrad_kernel and (3-32-128-64 or 1-16-256-64))", sms=5)
-    _run_gpu_tests_on_sim("test_gpu_igemm and not wgrad", sms=8,
-                          extra_env={"SSEG_IGEMM_PERSISTENT": "2", "SSEG_IGEMM_PERSISTENT_CTAS": "5"})
+    """All of test_gpu_igemm.py and test_gpu_elementwise.py (the tests that pass on B200: they pin the simulator's model of
+    TMA / UMMA descriptors / tensor memory) plus the kernel-level tests of the code that has not run on hardware yet - both
+    cooperative conv+BN kernels at every size (148 simulated SMs, up to 7 resident accumulators per CTA), the folded-affine
+    epilogue, the fp32-pair kernels, the depthwise / stem kernels with the MobileNetV2 inference schedule, the input
+    transforms and the prefetcher."""
+    assert _run_gpu_tests_on_sim(_KERNEL_LEVEL + " or device_prefetcher", sms=148, workers=6) >= 85
 
 
 def test_whole_training_steps_on_the_simulator():
@@ -62,6 +54,16 @@ def test_whole_training_steps_on_the_simulator():
     SSEG_COOP_BN=1 step (fused conv+BN kernels in both directions) against the default schedule."""
     assert _run_gpu_tests_on_sim("test_fused_conv_bn_train_schedule_matches_the_default_step or "
                                  "test_graph_replay_matches_eager_and_autograd_path", sms=16, workers=2, timeout=2400) == 2
+
+
+def test_cooperative_kernels_with_uneven_tile_distribution_and_the_persistent_gemm():
+    """5 'SMs' -> CTAs hold different numbers of resident accumulators; the persistent GEMM variant walks 5 CTAs through
+    many tiles and both tensor-memory buffers (passes on B200 with the same switches: profiles/r1_summary.md)."""
+    _run_gpu_tests_on_sim("(test_fused_conv_bn_train_kernel and (1-64-128-32 or 3-64-64-32)) or "
+                          "(test_fused_conv_bn_dgrad_kernel and (3-32-128-64 or 1-16-256-64))", sms=5)
+    _run_gpu_tests_on_sim("test_pointwise_wide_k_and_stats or test_3x3_cout256_cin512 or test_ragged_spatial or test_virtual_concat_3x3 "
+                          "or test_dgrad_with_fused_bn_backward_reduce", sms=8,
+                          extra_env={"SSEG_IGEMM_PERSISTENT": "2", "SSEG_IGEMM_PERSISTENT_CTAS": "5"})
 
 
 # ------------------------------------------------------------------------------------------------ two ranks, one process

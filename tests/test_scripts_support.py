@@ -191,3 +191,16 @@ def test_the_reference_train_script_runs_unmodified_on_this_engine(tmp_path):
         accm.update(a, pix), im.update(inter), um.update(union)
     want_miou, want_acc = float((im.sum / (um.sum + 1e-10)).mean()), accm.average() * 100
     assert abs(acc - want_acc) <= 0.5 and abs(miou - want_miou) <= 1e-3, (summary, want_miou, want_acc)
+
+    # ---- the reference's test.py, unmodified: one image in, class percentages on stdout, a colour rendering on disk
+    res = tmp_path / "result"
+    res.mkdir()
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_script.py"), "1", os.path.join(REF, "test.py"),
+                          "--imgs", str(data / "images" / "im_02.png"), "--cfg", str(y), "--gpu", "0",
+                          "TEST.checkpoint", "epoch_2.pth", "TEST.result", str(res)],
+                         capture_output=True, text=True, cwd=REF, timeout=900)
+    log = out.stdout + out.stderr
+    assert out.returncode == 0 and "Inference done!" in log and "Predictions in [" in log, log[-3000:]
+    from PIL import Image
+    vis = Image.open(str(res / "im_02.png"))
+    assert vis.size == (2 * 64, 64)          # input image next to the colour-coded prediction
