@@ -36,3 +36,5 @@ for sw in "SSEG_FOLD_BN_EVAL=0" "SSEG_FOLD_BN_EVAL=1" "SSEG_ACCURATE_INFERENCE=1
   env $sw timeout 120 python tools/infer_bench.py --net r18ppm 2>&1 | tail -1
   env $sw timeout 200 python tools/infer_bench.py --net hrnet --multiscale 2>&1 | tail -1
 done
+echo "== input pipeline (SURVEY 8(f) row 4): sync fp32 copy vs prefetched fp32 vs prefetched uint8 + device-side transform"
+timeout 300 python tools/input_pipeline_bench.py --steps 30 2>&1 | tail -3
