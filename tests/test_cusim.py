@@ -15,6 +15,7 @@ import sys
 import threading
 import types
 
+import numpy as np
 import pytest
 import torch
 
@@ -349,3 +350,70 @@ def test_every_kernel_waits_for_its_predecessor_grid():
             kernels += 1
             assert "pdl_sync()" in body or "pdl_wait()" in body, "%s::%s has no griddepcontrol.wait" % (os.path.basename(path), name)
     assert kernels >= 40
+
+
+def test_peer_memory_syncbn_kernels_two_ranks(sim):
+    """csrc/peer.cu (the default multi-GPU schedule's SyncBN exchange; ran on 2 and 4 B200s): arenas allocated / opened
+    through the library's own IPC entry points, two host threads as the two GPUs, three consecutive 'steps' (the flags carry
+    step numbers and are never reset). Reference: the Python restatement of the ABI on the complete arenas."""
+    import ctypes
+    from abi_emulator import EmuLib
+    from mit_semseg.engine import _C, ops
+    lib = _C.lib()
+    C, world = 96, 2
+    g = torch.Generator().manual_seed(4)
+    ptrs, handles = [], []
+    for r in range(world):        # every rank allocates its arena and exports a handle; the peers open it
+        p, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
+        _C.check(lib.sseg_peer_alloc(4 * 4096, ctypes.byref(p), h))
+        ptrs.append(p), handles.append(h)
+    opened = []
+    for r in range(world):
+        q = ctypes.c_void_p()
+        _C.check(lib.sseg_peer_open(handles[r], ctypes.byref(q)))
+        assert q.value == ptrs[r].value        # one process here: the mapping is the allocation itself
+        opened.append(q)
+    arenas = [torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * 4096).from_address(p.value))) for p in ptrs]
+    assert all(float(a.abs().sum()) == 0.0 for a in arenas)        # zero-initialised
+    STATS, PART, FLAGS = 0, 1024, 3000
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    steps = [torch.zeros(1, dtype=torch.int32) for _ in range(world)]
+    state = [dict(rm=torch.zeros(C), rv=torch.ones(C), tm=torch.zeros(C), tv=torch.zeros(C), it=torch.zeros(1)) for _ in range(world)]
+    ref_state = [dict((k, v.clone()) for k, v in s.items()) for s in state]
+    emu = EmuLib()
+    for step_no in range(1, 4):
+        for r in range(world):     # this step's partial sums [sum | sqsum | count] and backward partials [s1 | s2raw]
+            x = torch.randn(500 + 100 * r, C, generator=g) + 0.3 * r
+            arenas[r][STATS:STATS + C], arenas[r][STATS + C:STATS + 2 * C] = x.sum(0), (x * x).sum(0)
+            arenas[r][STATS + 2 * C] = x.shape[0]
+            arenas[r][PART:PART + 2 * C] = torch.randn(2 * C, generator=g)
+        out = [dict(v=torch.zeros(4, C), cnt=torch.zeros(1), tot=torch.zeros(4, C)) for _ in range(world)]
+
+        def rank_step(r):
+            ns = _arena_ns(arenas, r)
+            ops.peer_step(steps[r])
+            s = state[r]
+            ops.bn_finalize_peer(ns, STATS, FLAGS, steps[r], gamma, beta, 1e-5, 0.1, out[r]["v"][0], out[r]["v"][1], out[r]["v"][2],
+                                 out[r]["v"][3], out[r]["cnt"], running=(s["rm"], s["rv"], s["tm"], s["tv"], s["it"]), update_running=True)
+            ops.bn_bwd_peer_sum(ns, PART, FLAGS + 8, steps[r], out[r]["tot"][0], out[r]["tot"][1], out[r]["tot"][2], out[r]["tot"][3],
+                                mean=out[r]["v"][0], invstd=out[r]["v"][1], s2_raw=True)
+        _both_ranks(rank_step)
+        assert all(int(s) == step_no for s in steps)
+        for r in range(world):
+            ns = _arena_ns(arenas, r)
+            v, cnt, tot, s = torch.zeros(4, C), torch.zeros(1), torch.zeros(4, C), ref_state[r]
+            emu.sseg_bn_finalize_peer(ns.bases, world, r, STATS, FLAGS, _C.ptr(steps[r]), _C.ptr(gamma), _C.ptr(beta), 1e-5, 0.1, 1,
+                                      _C.ptr(s["rm"]), _C.ptr(s["rv"]), _C.ptr(s["tm"]), _C.ptr(s["tv"]), _C.ptr(s["it"]), _C.ptr(v[0]),
+                                      _C.ptr(v[1]), _C.ptr(v[2]), _C.ptr(v[3]), _C.ptr(cnt), C, None)
+            emu.sseg_bn_bwd_peer_sum(ns.bases, world, r, PART, FLAGS + 8, _C.ptr(steps[r]), _C.ptr(tot[0]), _C.ptr(tot[1]),
+                                     _C.ptr(tot[2]), _C.ptr(tot[3]), _C.ptr(v[0]), _C.ptr(v[1]), 1, C, None)
+            assert torch.allclose(out[r]["v"], v, rtol=1e-5, atol=1e-6) and out[r]["cnt"].item() == cnt.item() == 1100
+            assert torch.allclose(out[r]["tot"], tot, rtol=1e-4, atol=1e-5)
+            for k in ("rm", "rv", "tm", "tv", "it"):
+                assert torch.allclose(state[r][k], s[k], rtol=1e-5, atol=1e-6), k
+        assert torch.equal(out[0]["v"], out[1]["v"]) and torch.equal(out[0]["tot"], out[1]["tot"])   # pooled in rank order
+    for r in range(world):
+        _C.check(lib.sseg_peer_close(opened[r]))
+    del arenas
+    for r in range(world):
+        _C.check(lib.sseg_peer_free(ptrs[r]))
