@@ -47,7 +47,7 @@ def test_every_kernel_level_gpu_test_passes_on_the_simulator():
     cooperative conv+BN kernels at every size (148 simulated SMs, up to 7 resident accumulators per CTA), the folded-affine
     epilogue, the fp32-pair kernels, the depthwise / stem kernels with the MobileNetV2 inference schedule, the input
     transforms and the prefetcher."""
-    assert _run_gpu_tests_on_sim(_KERNEL_LEVEL + " or device_prefetcher", sms=148, workers=6) >= 85
+    assert _run_gpu_tests_on_sim(_KERNEL_LEVEL + " or input_transforms or device_prefetcher", sms=148, workers=6) >= 85
 
 
 def test_whole_training_steps_on_the_simulator():

@@ -318,43 +318,3 @@ def test_graft_entry_smoke():
     """The driver's smoke entry point (one small training step checked against the oracle) as part of the suite."""
     import __graft_entry__ as ge
     ge.smoke()
-
-
-def test_device_prefetcher_delivers_the_reference_batches(tmp_path):
-    """TrainDataset(raw=True) -> DevicePrefetcher (pinned staging, copy stream, device-side
-    img_transform / segm_transform) hands out, batch after batch and shape after shape, exactly the tensors the reference's
-    loader computes on the CPU; reference-format batches pass through unchanged."""
-    import copy
-    import numpy as np
-    from mit_semseg import dataset as D
-    from mit_semseg.engine.prefetch import DevicePrefetcher
-    from torch.utils.data import DataLoader
-    from mit_semseg.lib.nn import user_scattered_collate
-    from oracle import synth_images as S
-    recs = S.write_dataset(str(tmp_path))
-    opt = S.dataset_options()
-    host = D.TrainDataset(str(tmp_path), copy.deepcopy(recs), opt, batch_per_gpu=2)
-    raw = D.TrainDataset(str(tmp_path), copy.deepcopy(recs), opt, batch_per_gpu=2, raw=True)
-    np.random.seed(5)
-    want = [host[i] for i in range(5)]
-    np.random.seed(5)
-    got_raw = [raw[i] for i in range(5)]
-    shapes = set()
-    pf = DevicePrefetcher(got_raw, device="cuda")
-    n = 0
-    for feed, ref in zip(pf, want):
-        torch.cuda.synchronize()
-        assert feed["img_data"].is_cuda and feed["img_data"].dtype == torch.float32 and feed["seg_label"].dtype == torch.int64
-        assert torch.equal(feed["img_data"].cpu(), ref["img_data"]) and torch.equal(feed["seg_label"].cpu(), ref["seg_label"])
-        assert pf.h2d_bytes == sum(got_raw[n][k].numel() * got_raw[n][k].element_size() for k in ("img_u8", "seg_u8", "valid_hw"))
-        assert pf.h2d_bytes * 3.5 < ref["img_data"].numel() * 4           # a quarter of the fp32 bytes over PCIe
-        shapes.add(tuple(ref["img_data"].shape))
-        n += 1
-    assert n == 5 and len(shapes) >= 2           # the batches really change shape
-    # the reference's own loader output (list with one dict per GPU, float tensors) is staged and copied as it is
-    loader = DataLoader(host, batch_size=1, shuffle=False, collate_fn=user_scattered_collate, num_workers=0)
-    np.random.seed(11)
-    it = iter(DevicePrefetcher(loader, device="cuda"))
-    feed = next(it)
-    torch.cuda.synchronize()
-    assert feed["img_data"].dim() == 4 and feed["img_data"].is_cuda and feed["seg_label"].dtype == torch.int64

@@ -11,6 +11,7 @@ shift of +2 (most units active: the network is near-linear, rounding noise no lo
 gradient route shows up as an O(1) error against a ~1 % noise floor; the zero-shift runs pin loss / features / gradient
 direction at the noise floor.
 """
+import numpy as np
 import pytest
 import torch
 
@@ -421,3 +422,73 @@ def test_mobilenet_kernels_and_inference():
     agree = (probs.argmax(1) == ref.argmax(1)).float().mean().item()
     print("mobilenet features rel", frel, "arg-max agreement %.4f" % agree)
     assert len(feats) == 5 and max(frel[:3]) <= 2e-2 and max(frel) <= 0.2 and agree >= 0.8
+
+
+# ------------------------------------------------------------------ input pipeline (first hardware run pending)
+def test_input_transforms_are_bit_identical_to_the_reference_transforms():
+    """sseg_image_transform / sseg_label_transform = the reference's img_transform / segm_transform (dataset.py:53-63) on
+    the bytes a raw-mode batch carries, zeros in the padding like the reference's pre-zeroed batch tensors. Bit-exact."""
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(77)
+    n, h, w, rate = 3, 40, 56, 8
+    u8 = torch.randint(0, 256, (n, h, w, 3), device="cuda", generator=g).to(torch.uint8)
+    seg = torch.randint(0, 151, (n, h // rate, w // rate), device="cuda", generator=g).to(torch.uint8)
+    valid = torch.tensor([[40, 56], [33, 41], [8, 17]], device="cuda", dtype=torch.int32)
+    out = torch.full((n, 3, h, w), float("nan"), device="cuda")
+    lab = torch.full((n, h // rate, w // rate), 99, device="cuda", dtype=torch.int64)
+    ops.image_transform(u8, valid, out)
+    ops.label_transform(seg, valid, rate, lab)
+    torch.cuda.synchronize()
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    ref, rlab = torch.zeros(n, 3, h, w), torch.zeros(n, h // rate, w // rate, dtype=torch.int64)
+    for i in range(n):
+        vh, vw = int(valid[i, 0]), int(valid[i, 1])
+        x = torch.from_numpy((np.float32(u8[i, :vh, :vw].cpu().numpy()) / 255.).transpose((2, 0, 1)).copy())
+        ref[i, :, :vh, :vw] = (x - mean) / std
+        hs, ws = -(-vh // rate), -(-vw // rate)
+        rlab[i, :hs, :ws] = seg[i, :hs, :ws].cpu().long() - 1
+    assert torch.equal(out.cpu(), ref)
+    assert torch.equal(lab.cpu(), rlab)
+    with pytest.raises(Exception):
+        ops.image_transform(torch.zeros(1, 8, 6, 3, device="cuda", dtype=torch.uint8), valid[:1], torch.zeros(1, 3, 8, 6, device="cuda"))
+
+
+def test_device_prefetcher_delivers_the_reference_batches(tmp_path):
+    """TrainDataset(raw=True) -> DevicePrefetcher (pinned staging, copy stream, device-side
+    img_transform / segm_transform) hands out, batch after batch and shape after shape, exactly the tensors the reference's
+    loader computes on the CPU; reference-format batches pass through unchanged."""
+    import copy
+    import numpy as np
+    from mit_semseg import dataset as D
+    from mit_semseg.engine.prefetch import DevicePrefetcher
+    from torch.utils.data import DataLoader
+    from mit_semseg.lib.nn import user_scattered_collate
+    from oracle import synth_images as S
+    recs = S.write_dataset(str(tmp_path))
+    opt = S.dataset_options()
+    host = D.TrainDataset(str(tmp_path), copy.deepcopy(recs), opt, batch_per_gpu=2)
+    raw = D.TrainDataset(str(tmp_path), copy.deepcopy(recs), opt, batch_per_gpu=2, raw=True)
+    np.random.seed(5)
+    want = [host[i] for i in range(5)]
+    np.random.seed(5)
+    got_raw = [raw[i] for i in range(5)]
+    shapes = set()
+    pf = DevicePrefetcher(got_raw, device="cuda")
+    n = 0
+    for feed, ref in zip(pf, want):
+        torch.cuda.synchronize()
+        assert feed["img_data"].is_cuda and feed["img_data"].dtype == torch.float32 and feed["seg_label"].dtype == torch.int64
+        assert torch.equal(feed["img_data"].cpu(), ref["img_data"]) and torch.equal(feed["seg_label"].cpu(), ref["seg_label"])
+        assert pf.h2d_bytes == sum(got_raw[n][k].numel() * got_raw[n][k].element_size() for k in ("img_u8", "seg_u8", "valid_hw"))
+        assert pf.h2d_bytes * 3.5 < ref["img_data"].numel() * 4           # a quarter of the fp32 bytes over PCIe
+        shapes.add(tuple(ref["img_data"].shape))
+        n += 1
+    assert n == 5 and len(shapes) >= 2           # the batches really change shape
+    # the reference's own loader output (list with one dict per GPU, float tensors) is staged and copied as it is
+    loader = DataLoader(host, batch_size=1, shuffle=False, collate_fn=user_scattered_collate, num_workers=0)
+    np.random.seed(11)
+    it = iter(DevicePrefetcher(loader, device="cuda"))
+    feed = next(it)
+    torch.cuda.synchronize()
+    assert feed["img_data"].dim() == 4 and feed["img_data"].is_cuda and feed["seg_label"].dtype == torch.int64
