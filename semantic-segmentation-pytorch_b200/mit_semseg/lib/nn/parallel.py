@@ -21,7 +21,7 @@ import torch.nn as nn
 from torch.nn.parallel import DataParallel
 
 __all__ = ['UserScatteredDataParallel', 'user_scattered_collate', 'async_copy_to', 'DataParallelWithCallback',
-           'patch_replication_callback']
+           'patch_replication_callback', 'ensure_process_group']
 
 
 def async_copy_to(obj, dev, main_stream=None):
@@ -47,6 +47,30 @@ def _rank_world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
     return 0, 1
+
+
+def ensure_process_group():
+    """The reference's scripts know nothing about torch.distributed (they replicate inside one process). Launched as one
+    process per GPU - `python -m torch.distributed.run --nproc-per-node N train.py --gpus 0-(N-1)` - the launcher's
+    environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*) is all there is, so the first multi-GPU call the script makes
+    (wrapping the model in UserScatteredDataParallel, train.py:184-186) joins the job: this process takes GPU LOCAL_RANK
+    and the default process group is created (NCCL; gloo when there is no CUDA device, i.e. in the CPU tests).
+    Returns (rank, world). A no-op without the launcher's variables or when a group already exists."""
+    import os
+    import torch.distributed as dist
+    if not dist.is_available():
+        return 0, 1
+    if not dist.is_initialized():
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world <= 1 or "RANK" not in os.environ:
+            return 0, 1
+        use_cuda = torch.cuda.is_available() and torch.cuda.device_count() > 0
+        if use_cuda:
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", os.environ["RANK"])) % torch.cuda.device_count())
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        dist.init_process_group(backend="nccl" if use_cuda else "gloo")
+    return dist.get_rank(), dist.get_world_size()
 
 
 def _lift(out):
@@ -79,6 +103,12 @@ class DictGatherDataParallel(DataParallel):
 class UserScatteredDataParallel(DictGatherDataParallel):
     def __init__(self, module, device_ids=None, output_device=None, dim=0):
         # One process drives one GPU: keep only this process's device so nn.DataParallel never replicates.
+        _, world = ensure_process_group()    # under torchrun: take GPU LOCAL_RANK and join the job (before the script's .cuda())
+        if world == 1 and device_ids is not None and len(device_ids) > 1:
+            import warnings
+            warnings.warn("UserScatteredDataParallel(device_ids=%s) in a single process: this engine runs one process per GPU "
+                          "- launch the script with `python -m torch.distributed.run --nproc-per-node %d ...`; continuing on "
+                          "one GPU with the first entry of every per-GPU batch list" % (list(device_ids), len(device_ids)))
         if torch.cuda.is_available():
             dev = torch.cuda.current_device()
             super().__init__(module, device_ids=[dev], output_device=dev, dim=dim)

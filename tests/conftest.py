@@ -79,7 +79,30 @@ def install_cuda_stand_in(setattr_, mode):
     setattr_(torch.cuda, "synchronize", lambda *a, **k: None)
     setattr_(torch.cuda, "is_available", lambda: True)
     setattr_(torch.cuda, "set_device", lambda *a, **k: None)
-    setattr_(torch.cuda, "current_stream", lambda *a, **k: types.SimpleNamespace(cuda_stream=0))
+    import contextlib
+
+    class _Stream:
+        cuda_stream = 0
+
+        def __init__(self, *a, **k):
+            pass
+
+        def wait_stream(self, other):
+            pass
+
+        def wait_event(self, ev):
+            pass
+
+        def synchronize(self):
+            pass
+    setattr_(torch.cuda, "current_stream", lambda *a, **k: _Stream())
+    setattr_(torch.cuda, "Stream", _Stream)
+    setattr_(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    setattr_(torch.cuda, "device", lambda d: contextlib.nullcontext())
+    setattr_(torch.cuda, "current_device", lambda: 0)
+    setattr_(torch.cuda, "get_device_properties", lambda d=None: types.SimpleNamespace(
+        name="stand-in", total_memory=180 << 30, multi_processor_count=148, major=10, minor=0))
+    setattr_(torch.Tensor, "record_stream", lambda self, s: None)
     setattr_(torch.Tensor, "cuda", lambda self, *a, **k: self)
     setattr_(torch.Tensor, "is_cuda", property(lambda self: True))
     setattr_(nn.Module, "cuda", lambda self, *a, **k: self)

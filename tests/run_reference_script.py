@@ -31,6 +31,11 @@ def main():
             k["pin_memory"] = False
             super().__init__(*a, **k)
     torch.utils.data.DataLoader = Loader
+    if os.environ.get("SSEG_TEST_RANK_CWD") == "1" and "RANK" in os.environ:
+        # every rank in its own working directory: a relative cfg.DIR then gives per-rank checkpoint files to compare
+        d = os.path.join(os.getcwd(), "rank%s" % os.environ["RANK"])
+        os.makedirs(d, exist_ok=True)
+        os.chdir(d)
     sys.argv = [script] + sys.argv[3:]
     runpy.run_path(script, run_name="__main__")
 

@@ -213,3 +213,42 @@ def test_the_reference_train_script_runs_unmodified_on_this_engine(tmp_path):
     from PIL import Image
     vis = Image.open(str(res / "im_02.png"))
     assert vis.size == (2 * 64, 64)          # input image next to the colour-coded prediction
+
+
+@needs_reference
+def test_the_reference_train_script_as_one_process_per_gpu(tmp_path):
+    """`python -m torch.distributed.run --nproc-per-node 2 train.py --gpus 0-1`: the unmodified script knows
+    nothing about torch.distributed; wrapping the model in UserScatteredDataParallel joins the job (ensure_process_group),
+    every rank consumes its own entry of the loader's per-GPU list, SyncBN statistics and gradients are all-reduced by the
+    engine (gloo here, through the NCCL-mode schedule). Proof of synchronisation: the ranks see different data, each writes
+    its checkpoint into its own directory, and the files are identical."""
+    import random
+    from oracle import synth_images as S
+    data = tmp_path / "data"
+    recs = S.write_dataset(str(data))
+    odgt = tmp_path / "train.odgt"
+    odgt.write_text("".join(json.dumps(r) + "\n" for r in recs))
+    pe, pd = _initial_weights(tmp_path)
+    y = tmp_path / "tiny.yaml"
+    y.write_text('DATASET:\n  root_dataset: "%s"\n  list_train: "%s"\n  imgSizes: (64, 80)\n  imgMaxSize: 128\n'
+                 'MODEL:\n  arch_encoder: "resnet18dilated"\n  arch_decoder: "ppm_deepsup"\n  fc_dim: 512\n'
+                 'TRAIN:\n  batch_size_per_gpu: 2\n  num_epoch: 1\n  epoch_iters: 3\n  workers: 0\n  disp_iter: 1\n'
+                 'DIR: "ckpt"\n' % (data, odgt))
+    env = dict(os.environ, SSEG_PEER_SYNC="0", SSEG_TEST_RANK_CWD="1")
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", str(29600 + random.randint(0, 300)), os.path.join(ROOT, "tests", "run_reference_script.py"), "1",
+                          os.path.join(REF, "train.py"), "--cfg", str(y), "--gpus", "0-1", "MODEL.weights_encoder", pe,
+                          "MODEL.weights_decoder", pd], capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
+    log = out.stdout + out.stderr
+    assert out.returncode == 0 and log.count("Training Done!") == 2, log[-3000:]
+    first = [float(line.split("Loss: ")[1]) for line in log.splitlines() if "Epoch: [1][0/3]" in line]
+    assert len(first) == 2 and first[0] != first[1]                  # the ranks really trained on different entries
+    for name in ("encoder_epoch_1.pth", "decoder_epoch_1.pth"):
+        a, b = torch.load(str(tmp_path / "rank0" / "ckpt" / name)), torch.load(str(tmp_path / "rank1" / "ckpt" / name))
+        assert list(a) == list(b)
+        for k in a:
+            assert torch.equal(a[k], b[k]), (name, k)                 # weights AND BatchNorm running statistics
+    start = torch.load(pe)
+    assert not torch.equal(start["conv1.weight"], torch.load(str(tmp_path / "rank0" / "ckpt" / "encoder_epoch_1.pth"))["conv1.weight"])
