@@ -15,6 +15,14 @@ class _RawCuda:
 
 
 class PeerArena:
+    @staticmethod
+    def _view(ptr, count, typestr, device):
+        """torch tensor over the arena (the CPU simulator's test harness substitutes a host view)"""
+        raw = _RawCuda(ptr, count, typestr)
+        t = torch.as_tensor(raw, device=device)
+        t._keep_raw = raw
+        return t
+
     def __init__(self, nfloats, dist, device):
         self.world, self.rank = dist.get_world_size(), dist.get_rank()
         assert self.world <= 8
@@ -39,10 +47,8 @@ class PeerArena:
                     self.bases[r] = p.value
                 except _C.SsegError as exc:  # keep going: every rank must reach the barrier below
                     err = exc
-        self._raw_f = _RawCuda(self.local_ptr, self.nbytes // 4, "<f4")
-        self._raw_i = _RawCuda(self.local_ptr, self.nbytes // 4, "<i4")
-        self.floats = torch.as_tensor(self._raw_f, device=device)
-        self.ints = torch.as_tensor(self._raw_i, device=device)
+        self.floats = self._view(self.local_ptr, self.nbytes // 4, "<f4", device)
+        self.ints = self._view(self.local_ptr, self.nbytes // 4, "<i4", device)
         dist.barrier()  # every rank has mapped every arena before anyone starts signalling
         if err is not None:
             raise err

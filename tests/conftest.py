@@ -116,6 +116,15 @@ def install_cuda_stand_in(setattr_, mode):
     setattr_(torch.Tensor, "to", to)
     from mit_semseg.engine import prefetch as PF
     setattr_(PF.DevicePrefetcher, "_use_streams", False)
+    # peer arenas (simulator: POSIX shared memory behind the library's IPC entry points) as host tensors
+    import ctypes
+    import numpy as np
+    from mit_semseg.engine import peer as PEER
+
+    def host_view(ptr, count, typestr, device):
+        ct = ctypes.c_float if typestr == "<f4" else ctypes.c_int32
+        return torch.from_numpy(np.ctypeslib.as_array((ct * count).from_address(ptr)))
+    setattr_(PEER.PeerArena, "_view", staticmethod(host_view))
     # step programs: built as schedules on CPU tensors, executed against the emulator, no CUDA graphs / streams
     from mit_semseg.engine import accurate as ACC
     from mit_semseg.engine import program as PR

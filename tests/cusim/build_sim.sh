@@ -19,6 +19,8 @@ if [ -n "$CUSIM_COVERAGE" ]; then
 fi
 CUDA_INC="${CUDA_HOME:-/usr/local/cuda}/include"
 mkdir -p "$OUT"
+exec 9>"$OUT/.lock"   # several test processes (xdist workers, torchrun ranks) may ask for the library at once: one builds
+flock 9
 FLAGS="$SAN -O2 -g -fno-strict-aliasing -std=c++17 -fPIC -pthread -w -I$HERE -I$CUDA_INC -include $HERE/cusim.h"
 pids=()
 for f in "$CSRC"/*.cu; do
@@ -39,5 +41,5 @@ if [ ! -f "$o" ] || [ "$HERE/cusim_runtime.cpp" -nt "$o" ] || [ "$HERE/cusim.h" 
   pids+=($!)
 fi
 for p in "${pids[@]}"; do wait "$p"; done
-g++ $SAN -shared -pthread -Wl,-Bsymbolic -o "$OUT/libsseg_sim.so" "$OUT"/*.o
+g++ $SAN -shared -pthread -Wl,-Bsymbolic -o "$OUT/libsseg_sim.so" "$OUT"/*.o -lrt
 echo "$OUT/libsseg_sim.so"

@@ -3,7 +3,10 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <ucontext.h>
 
 #include <array>
@@ -723,12 +726,58 @@ cudaError_t cudaDeviceGetAttribute(int* value, enum cudaDeviceAttr attr, int) {
   return cudaSuccess;
 }
 cudaError_t cudaFuncSetAttribute(const void*, enum cudaFuncAttribute, int) { return cudaSuccess; }
+// "Device" allocations made through cudaMalloc (only the peer arenas of csrc/peer.cu) live in POSIX shared memory, so that
+// cudaIpcGetMemHandle / cudaIpcOpenMemHandle really map one rank's arena into another PROCESS (two-rank runs under
+// torch.distributed.run poll each other's flags through it). The 64-byte handle carries the object's name.
+struct ShmAlloc {
+  void* ptr;
+  size_t bytes;
+  std::string name;
+  bool owner;
+};
+static std::mutex g_shm_mu;
+static std::vector<ShmAlloc> g_shm;
+
+static void shm_cleanup_at_exit() {
+  for (const ShmAlloc& a : g_shm)
+    if (a.owner) shm_unlink(a.name.c_str());
+}
+
 cudaError_t cudaMalloc(void** p, size_t bytes) {
-  return posix_memalign(p, 256, bytes ? bytes : 256) == 0 ? cudaSuccess : cudaErrorMemoryAllocation;
+  static std::atomic<int> counter{0};
+  static std::once_flag once;
+  std::call_once(once, [] { atexit(shm_cleanup_at_exit); });
+  if (bytes == 0) bytes = 256;
+  char name[64];
+  snprintf(name, sizeof(name), "/cusim_%d_%d", (int)getpid(), counter.fetch_add(1));
+  const int fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+  if (fd < 0) return cudaErrorMemoryAllocation;
+  if (ftruncate(fd, (off_t)bytes) != 0) {
+    close(fd);
+    shm_unlink(name);
+    return cudaErrorMemoryAllocation;
+  }
+  void* q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) {
+    shm_unlink(name);
+    return cudaErrorMemoryAllocation;
+  }
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  g_shm.push_back(ShmAlloc{q, bytes, name, true});
+  *p = q;
+  return cudaSuccess;
 }
 cudaError_t cudaFree(void* p) {
-  free(p);
-  return cudaSuccess;
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  for (size_t i = 0; i < g_shm.size(); ++i)
+    if (g_shm[i].ptr == p && g_shm[i].owner) {
+      munmap(p, g_shm[i].bytes);
+      shm_unlink(g_shm[i].name.c_str());
+      g_shm.erase(g_shm.begin() + i);
+      return cudaSuccess;
+    }
+  return cudaErrorInvalidValue;
 }
 cudaError_t cudaMemset(void* p, int v, size_t n) {
   memset(p, v, n);
@@ -739,15 +788,49 @@ cudaError_t cudaMemsetAsync(void* p, int v, size_t n, cudaStream_t) {
   return cudaSuccess;
 }
 cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) {
-  memset(h, 0, sizeof(*h));
-  memcpy(h, &p, sizeof(p));
-  return cudaSuccess;
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  for (const ShmAlloc& a : g_shm)
+    if (a.ptr == p && a.owner) {
+      memset(h, 0, sizeof(*h));
+      memcpy(h, a.name.c_str(), a.name.size() + 1);
+      return cudaSuccess;
+    }
+  return cudaErrorInvalidValue;
 }
 cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned int) {
-  memcpy(p, &h, sizeof(*p));
+  char name[64];
+  memcpy(name, &h, sizeof(name));
+  name[63] = 0;
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  for (const ShmAlloc& a : g_shm)
+    if (a.name == name) {  // same process (or opened before): the existing mapping
+      *p = a.ptr;
+      return cudaSuccess;
+    }
+  const int fd = shm_open(name, O_RDWR, 0600);
+  if (fd < 0) return cudaErrorInvalidValue;
+  struct stat st;
+  if (fstat(fd, &st) != 0) {
+    close(fd);
+    return cudaErrorInvalidValue;
+  }
+  void* q = mmap(nullptr, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  close(fd);
+  if (q == MAP_FAILED) return cudaErrorInvalidValue;
+  g_shm.push_back(ShmAlloc{q, (size_t)st.st_size, name, false});
+  *p = q;
   return cudaSuccess;
 }
-cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }
+cudaError_t cudaIpcCloseMemHandle(void* p) {
+  std::lock_guard<std::mutex> lk(g_shm_mu);
+  for (size_t i = 0; i < g_shm.size(); ++i)
+    if (g_shm[i].ptr == p && !g_shm[i].owner) {
+      munmap(p, g_shm[i].bytes);
+      g_shm.erase(g_shm.begin() + i);
+      break;
+    }
+  return cudaSuccess;
+}
 
 cudaError_t cudaGetDriverEntryPoint(const char* symbol, void** fn, unsigned long long, enum cudaDriverEntryPointQueryResult* status) {
   *fn = nullptr;

@@ -215,13 +215,21 @@ def test_the_reference_train_script_runs_unmodified_on_this_engine(tmp_path):
     assert vis.size == (2 * 64, 64)          # input image next to the colour-coded prediction
 
 
+_SIM_TWO_PROCESS = pytest.param("sim", marks=pytest.mark.skipif(os.environ.get("SSEG_TEST_SIM_TWO_PROCESS", "0") != "1",
+                                                                reason="1 minute; set SSEG_TEST_SIM_TWO_PROCESS=1 "
+                                                                       "(profiles/r1_reference_train_py_two_ranks_on_simulator.log)"))
+
+
 @needs_reference
-def test_the_reference_train_script_as_one_process_per_gpu(tmp_path):
+@pytest.mark.parametrize("mode", ["1", _SIM_TWO_PROCESS])
+def test_the_reference_train_script_as_one_process_per_gpu(tmp_path, mode):
     """`python -m torch.distributed.run --nproc-per-node 2 train.py --gpus 0-1`: the unmodified script knows
     nothing about torch.distributed; wrapping the model in UserScatteredDataParallel joins the job (ensure_process_group),
     every rank consumes its own entry of the loader's per-GPU list, SyncBN statistics and gradients are all-reduced by the
-    engine (gloo here, through the NCCL-mode schedule). Proof of synchronisation: the ranks see different data, each writes
-    its checkpoint into its own directory, and the files are identical."""
+    engine. mode "1": emulated ABI, collectives through the NCCL-mode schedule (gloo). mode "sim": the kernel sources on the
+    CPU simulator with the DEFAULT schedule - SyncBN statistics pooled by the csrc/peer.cu kernels through peer arenas that
+    the simulator backs with POSIX shared memory, so the two PROCESSES really poll each other's flags. Proof of
+    synchronisation: the ranks see different data, each writes its checkpoint into its own directory, the files are identical."""
     import random
     from oracle import synth_images as S
     data = tmp_path / "data"
@@ -234,11 +242,15 @@ def test_the_reference_train_script_as_one_process_per_gpu(tmp_path):
                  'MODEL:\n  arch_encoder: "resnet18dilated"\n  arch_decoder: "ppm_deepsup"\n  fc_dim: 512\n'
                  'TRAIN:\n  batch_size_per_gpu: 2\n  num_epoch: 1\n  epoch_iters: 3\n  workers: 0\n  disp_iter: 1\n'
                  'DIR: "ckpt"\n' % (data, odgt))
-    env = dict(os.environ, SSEG_PEER_SYNC="0", SSEG_TEST_RANK_CWD="1")
+    env = dict(os.environ, SSEG_TEST_RANK_CWD="1")
+    if mode == "1":
+        env["SSEG_PEER_SYNC"] = "0"
+    else:
+        env.update(SSEG_DRY_RUN_SMS="16", CUSIM_SMS="16")
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
         env.pop(k, None)
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                          "--master-port", str(29600 + random.randint(0, 300)), os.path.join(ROOT, "tests", "run_reference_script.py"), "1",
+                          "--master-port", str(29600 + random.randint(0, 300)), os.path.join(ROOT, "tests", "run_reference_script.py"), mode,
                           os.path.join(REF, "train.py"), "--cfg", str(y), "--gpus", "0-1", "MODEL.weights_encoder", pe,
                           "MODEL.weights_decoder", pd], capture_output=True, text=True, cwd=str(tmp_path), env=env, timeout=900)
     log = out.stdout + out.stderr
