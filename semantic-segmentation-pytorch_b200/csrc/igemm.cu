@@ -836,7 +836,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
                 ++src;
               }
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::kStageBytes;
             mbar_expect_tx(&full_bar[stage], L::kStageBytes);
             tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
@@ -855,7 +855,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
       for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t d_tmem = tmem_base + it * BLOCK_N;
         for (int ks = 0; ks < num_k_steps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_bounded(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
@@ -942,7 +942,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_bn_kernel(const __grid_c
           bar_sync_epilogue();
           tc_fence_after();
         } else {
-          mbar_wait(&tmem_full_bar[it], 0);
+          mbar_wait_bounded(&tmem_full_bar[it], 0);
           tc_fence_after();
         }
 
@@ -1187,7 +1187,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
                 ++src;
               }
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait_bounded(&empty_bar[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::kStageBytes;
             mbar_expect_tx(&full_bar[stage], L::kStageBytes);
             tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
@@ -1206,7 +1206,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
       for (int tile = blockIdx.x; tile < q.num_tiles; tile += gridDim.x, ++it) {
         const uint32_t d_tmem = tmem_base + it * BLOCK_N;
         for (int ks = 0; ks < num_k_steps; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
+          mbar_wait_bounded(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
@@ -1283,7 +1283,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_dgrad_bn_kernel(const __
           bar_sync_epilogue();
           tc_fence_after();
         } else {
-          mbar_wait(&tmem_full_bar[it], 0);
+          mbar_wait_bounded(&tmem_full_bar[it], 0);
           tc_fence_after();
         }
 

@@ -61,6 +61,7 @@ inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { ::cusim::mbar_arrive
 inline void mbar_arrive(uint64_t* bar) { ::cusim::mbar_arrive(bar, 0); }
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return ::cusim::mbar_test(bar, parity); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) { ::cusim::mbar_wait(bar, parity); }
+inline void mbar_wait_bounded(uint64_t* bar, uint32_t parity) { ::cusim::mbar_wait(bar, parity); }
 
 inline void tma_prefetch_desc(const CUtensorMap*) {}
 inline void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
