@@ -6,9 +6,11 @@
 //                   zeros, CU_TENSOR_MAP_SWIZZLE_128B applied to the shared-memory address (16-byte chunk index XOR
 //                   128-byte row index mod 8), then complete_tx(box bytes) on the mbarrier. Executed at issue.
 //   tensor memory   128 lanes x 512 fp32 columns per CTA, bump-allocated by tcgen05.alloc.
-//   tcgen05.mma     kind::f16 (bf16 x bf16 -> fp32) and kind::tf32, M = 128, cta_group::1, both operands K-major with
-//                   SWIZZLE_128B descriptors: row r, byte k of an operand is read from
-//                   swz(start + (r % 8) * 128 + (r / 8) * SBO + k). Issued MMAs are QUEUED and only executed by the
+//   tcgen05.mma     kind::f16 (bf16 x bf16 -> fp32) and kind::tf32, M = 128, cta_group::1, SWIZZLE_128B descriptors.
+//                   K-major operand: row r, byte k is read from swz(start + (r % 8) * 128 + (r / 8) * SBO + k);
+//                   MN-major operand (weight gradient): element (mn, k) from
+//                   swz(start + (mn / 64) * LBO + (k / 8) * SBO + (k % 8) * 128 + (mn % 64) * 2).
+//                   Issued MMAs are QUEUED and only executed by the
 //                   tcgen05.commit that covers them (as on the device, results are not visible before the commit's
 //                   mbarrier completes) -- a missing commit / wait shows up as a wrong result.
 //   tcgen05.ld      32x32b.x32: thread i of warp w reads lane 32*(w%4)+i; the lane field of the address must name the
