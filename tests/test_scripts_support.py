@@ -192,6 +192,16 @@ def test_the_reference_train_script_runs_unmodified_on_this_engine(tmp_path):
     want_miou, want_acc = float((im.sum / (um.sum + 1e-10)).mean()), accm.average() * 100
     assert abs(acc - want_acc) <= 0.5 and abs(miou - want_miou) <= 1e-3, (summary, want_miou, want_acc)
 
+    # ---- the same eval.py with SSEG_ACCURATE_INFERENCE=1 (fp32-grade inference on bf16 pairs, BASELINE config 2): the printed
+    # summary is the fp32 oracle's to the last digit
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_script.py"), "1", os.path.join(REF, "eval.py"),
+                          "--cfg", str(y), "--gpu", "0", "DATASET.list_val", str(odgt), "VAL.checkpoint", "epoch_2.pth"],
+                         capture_output=True, text=True, cwd=REF, timeout=900, env=dict(os.environ, SSEG_ACCURATE_INFERENCE="1"))
+    log = out.stdout + out.stderr
+    assert out.returncode == 0, log[-3000:]
+    exact = [line for line in log.splitlines() if line.startswith("Mean IoU")][0]
+    assert exact.startswith("Mean IoU: {:.4f}, Accuracy: {:.2f}%".format(want_miou, want_acc)), (exact, want_miou, want_acc)
+
     # ---- eval_multipro.py (one worker process per GPU, results through a queue): same numbers
     out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "run_reference_script.py"), "1", os.path.join(REF, "eval_multipro.py"),
                           "--cfg", str(y), "--gpus", "0", "DATASET.list_val", str(odgt), "VAL.checkpoint", "epoch_2.pth"],
