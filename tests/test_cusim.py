@@ -28,33 +28,41 @@ _KERNEL_LEVEL = ("test_gpu_igemm or test_gpu_elementwise or test_fused_conv_bn_t
                  "test_conv_with_folded_affine_epilogue or test_pair_kernels_against_torch or test_mobilenet_kernels")
 
 
-def _run_gpu_tests_on_sim(kexpr, sms, extra_env=None, timeout=1500, workers=4):
+def _start_gpu_tests_on_sim(kexpr, sms, extra_env=None, workers=4):
     env = dict(os.environ, SSEG_GPU_TESTS_ON_EMULATOR="sim", SSEG_TEST_EXPERIMENTAL="1", CUSIM_SMS=str(sms),
                SSEG_DRY_RUN_SMS=str(sms), CUSIM_TIMEOUT="120")
     env.update(extra_env or {})
     cmd = [sys.executable, "-m", "pytest", "-q", "-m", "gpu", "-x", "-n", str(workers), "-p", "no:cacheprovider", "-k", kexpr,
            os.path.join(ROOT, "tests", "test_gpu_igemm.py"), os.path.join(ROOT, "tests", "test_gpu_elementwise.py"),
            os.path.join(ROOT, "tests", "test_gpu_widen_hrnet.py"), os.path.join(ROOT, "tests", "test_gpu_e2e.py")]
-    out = subprocess.run(cmd, env=env, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
-    tail = (out.stdout + out.stderr)[-4000:]
-    assert out.returncode == 0, tail
-    return int(out.stdout.strip().splitlines()[-1].split(" passed")[0].split()[-1])
+    return subprocess.Popen(cmd, env=env, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
 
 
-def test_every_kernel_level_gpu_test_passes_on_the_simulator():
-    """All of test_gpu_igemm.py and test_gpu_elementwise.py (the tests that pass on B200: they pin the simulator's model of
-    TMA / UMMA descriptors / tensor memory) plus the kernel-level tests of the code that has not run on hardware yet - both
-    cooperative conv+BN kernels at every size (148 simulated SMs, up to 7 resident accumulators per CTA), the folded-affine
-    epilogue, the fp32-pair kernels, the depthwise / stem kernels with the MobileNetV2 inference schedule, the input
-    transforms and the prefetcher."""
-    assert _run_gpu_tests_on_sim(_KERNEL_LEVEL + " or input_transforms or device_prefetcher", sms=148, workers=6) >= 85
+def _finish(proc, timeout=1500):
+    out, _ = proc.communicate(timeout=timeout)
+    assert proc.returncode == 0, out[-4000:]
+    return int(out.strip().splitlines()[-1].split(" passed")[0].split()[-1])
 
 
-def test_whole_training_steps_on_the_simulator():
-    """Two whole programs through the real kernel sources: the default step captured/replayed vs the autograd path, and the
-    SSEG_COOP_BN=1 step (fused conv+BN kernels in both directions) against the default schedule."""
-    assert _run_gpu_tests_on_sim("test_fused_conv_bn_train_schedule_matches_the_default_step or "
-                                 "test_graph_replay_matches_eager_and_autograd_path", sms=16, workers=2, timeout=2400) == 2
+def _run_gpu_tests_on_sim(kexpr, sms, extra_env=None, timeout=1500, workers=4):
+    return _finish(_start_gpu_tests_on_sim(kexpr, sms, extra_env, workers), timeout)
+
+
+def test_gpu_tests_pass_on_the_simulator():
+    """Two runs side by side. (1) All of test_gpu_igemm.py and test_gpu_elementwise.py (the tests that pass on B200: they pin
+    the simulator's model of TMA / UMMA descriptors / tensor memory) plus the kernel-level tests of the code that has not run
+    on hardware yet - both cooperative conv+BN kernels at every size (148 simulated SMs, up to 7 resident accumulators per
+    CTA), the folded-affine epilogue, the fp32-pair kernels, the depthwise / stem kernels with the MobileNetV2 inference
+    schedule, the input transforms and the prefetcher. (2) Two whole training steps through the real kernel sources: the
+    default step captured / replayed vs the autograd path, and the SSEG_COOP_BN=1 step (fused conv+BN kernels in both
+    directions) against the default schedule."""
+    import conftest
+    conftest.sim_lib()          # build once, before the two pools ask for it
+    whole = _start_gpu_tests_on_sim("test_fused_conv_bn_train_schedule_matches_the_default_step or "
+                                    "test_graph_replay_matches_eager_and_autograd_path", sms=16, workers=2)
+    kernels = _start_gpu_tests_on_sim(_KERNEL_LEVEL + " or input_transforms or device_prefetcher", sms=148, workers=5)
+    assert _finish(kernels) >= 85
+    assert _finish(whole, timeout=2400) == 2
 
 
 def test_cooperative_kernels_with_uneven_tile_distribution_and_the_persistent_gemm():
