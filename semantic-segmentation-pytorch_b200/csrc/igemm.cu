@@ -346,13 +346,17 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
 // Persistent variant: one CTA per SM walks tiles (tile = blockIdx.x + i * gridDim.x). Two TMEM accumulator buffers let the
 // MMA warp start tile i+1 while the epilogue warps still drain / reduce / store tile i, and the TMA producer runs ahead
 // across tile boundaries, so the pipeline-fill and epilogue latencies are paid once per CTA instead of once per tile.
+// The main loop is bound by TMA round trips (~1.5 us per box pair: throughput = bytes in flight / latency), so shared
+// memory goes to pipeline stages (192 KB) and the epilogue works on 32-column slices of the accumulator through a small
+// staging buffer (20 KB) instead of staging the whole output tile.
+constexpr int kEpiN = 32;                      // accumulator columns per epilogue slice
+constexpr int kEpiPitch = kEpiN * 2 + 16;      // bytes per staged row (+16: rows start in different 16-byte bank groups)
 template <int BLOCK_N, int STAGES>
 struct IgemmPersistSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kPitch = BLOCK_N * 2 + 16;
-  static constexpr int kStgOff = STAGES * kStageBytes;                    // staged output tile + staged y tile
-  static constexpr int kBarOff = kStgOff + ((2 * 128 * kPitch + 1023) / 1024) * 1024;
+  static constexpr int kStgOff = STAGES * kStageBytes;                    // staged output slice + staged y slice
+  static constexpr int kBarOff = kStgOff + ((2 * 128 * kEpiPitch + 1023) / 1024) * 1024;
   static constexpr int kTotal = kBarOff + 256;
   static constexpr int kDynBytes = kTotal + 1024;
 };
@@ -361,6 +365,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const __grid_constant__ IgemmParams p,
                                                                           const int num_tiles) {
   using L = IgemmPersistSmem<BLOCK_N, STAGES>;
+  static_assert(L::kDynBytes <= 232448, "shared memory budget");
   SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -464,10 +469,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
     }
     __syncwarp();
   } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+    // ===================== epilogue: TMEM -> registers -> (staging slice) -> global =====================
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int row = quarter * 32 + lane;
+    const int t = threadIdx.x - 64;
     const bool do_stats = p.stat_sum != nullptr;
+    uint8_t* stg = smem + L::kStgOff;  // dedicated staging: the pipeline stages already carry the next tile
+    uint8_t* ytile = stg + 128 * kEpiPitch;
+    // thread mappings of the slice passes: column sums (thread = one pair of adjacent columns x one slab of rows) and
+    // row copies (kLanesPerRow lanes cover the 64 bytes of one row, several rows per pass)
+    constexpr int kPairs = kEpiN / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
+    constexpr int kLanesPerRow = kEpiN / 8, kRowsPerPass = 128 / kLanesPerRow, kPasses = 128 / kRowsPerPass;
+    const int cp = t % kPairs, slab = t / kPairs;
+    const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
     // tile decode: N-tile fastest so CTAs sharing an activation tile run together (L2 reuse)
@@ -486,18 +500,32 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
     const size_t add_off = img * p.add_img_stride + hh * p.add_row_stride + static_cast<size_t>(ww) * p.ld_addend;
     (void)out_off;
 
+    uint4 yq[kPasses];
+    auto load_y = [&](int c0) {
+#pragma unroll
+      for (int pass = 0; pass < kPasses; ++pass) {
+        const int r = pass * kRowsPerPass + r0;
+        const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+        yq[pass] = make_uint4(0u, 0u, 0u, 0u);
+        if (rh < p.H && rw < p.W && c0 + seg * 8 < p.cout)
+          yq[pass] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
+                                                          static_cast<size_t>(rw) * p.bw_ld + c0 + seg * 8));
+      }
+    };
+    if (p.bw_s1 != nullptr) load_y(n0);  // independent of the accumulator: in flight while the main loop finishes
+
     mbar_wait(&tmem_full_bar[buf], use & 1);
     tc_fence_after();
-    // bf16 outputs are staged through shared memory (the pipeline stages are idle once the accumulator is complete):
-    // rows are then stored with full 16-byte-per-lane coalescing and the per-channel statistics are column sums of the
-    // staged (bf16-rounded = as stored) tile. fp32 outputs (classifier logits) are written straight from registers.
-    constexpr int kPitch = BLOCK_N * 2 + 16;  // +16 B: consecutive rows start in different 16-byte bank groups
-    uint8_t* stg = smem + L::kStgOff;  // dedicated staging: the pipeline stages already carry the next tile
 #pragma unroll 1
-    for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+    for (int chunk = 0; chunk < BLOCK_N / kEpiN; ++chunk) {
       uint32_t raw[32];
       tmem_ld_32x32(d_tmem + (static_cast<uint32_t>(quarter * 32) << 16) + chunk * 32, raw);
       tmem_ld_wait();
+      if (chunk == BLOCK_N / kEpiN - 1) {
+        // every tcgen05.ld of this tile has completed in this thread; once all four warps are here (the barrier below)
+        // the MMA warp may refill this accumulator buffer
+        tc_fence_before();
+      }
       float v[32];
       const int col0 = n0 + chunk * 32;
 #pragma unroll
@@ -541,6 +569,7 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
         for (int j = 0; j < 32; ++j) v[j] = fminf(v[j], 6.f);
       }
       if (p.out_f32) {
+        // fp32 outputs (classifier logits) are written straight from registers
         if (valid) {
           float* op = reinterpret_cast<float*>(p.out) + out_off + col0;
 #pragma unroll
@@ -548,8 +577,16 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
             if (col0 + g * 4 < p.n_store)
               *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
         }
-      } else {
-        uint8_t* sp = stg + row * kPitch + chunk * 64;
+        if (chunk == BLOCK_N / kEpiN - 1) {
+          bar_sync_epilogue();
+          if (threadIdx.x == 64) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        continue;
+      }
+      // bf16 outputs: the 128 x 32 slice is staged in shared memory, so that rows are stored with 16 bytes per lane over
+      // whole 64-byte runs and the per-channel statistics are column sums of the staged (bf16-rounded = as stored) values
+      {
+        uint8_t* sp = stg + row * kEpiPitch;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 q = make_uint4(0u, 0u, 0u, 0u);  // rows outside the image contribute zeros to the statistics
@@ -561,92 +598,65 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_persistent_kernel(const 
           *reinterpret_cast<uint4*>(sp + g * 16) = q;
         }
       }
-    }
-    tc_fence_before();
-    bar_sync_epilogue();  // the 4 epilogue warps: all tcgen05.ld of this tile are done
-    if (threadIdx.x == 64) mbar_arrive(&tmem_empty_bar[buf]);  // the MMA warp may refill this accumulator buffer
-    if (!p.out_f32) {
-      const int t = threadIdx.x - 64;
+      if (p.bw_s1 != nullptr) {
+        // BN-backward partial sums of the producer layer: the matching slice of its saved conv output y goes to shared
+        // memory next to the staged gradient slice; the loads of the NEXT slice are issued right away, so their latency
+        // is covered by this slice's reductions and stores
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass)
+          *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kEpiPitch + seg * 16) = yq[pass];
+        if (chunk + 1 < BLOCK_N / kEpiN) load_y(col0 + kEpiN);
+      }
+      bar_sync_epilogue();  // the staged slice (and y slice) is complete
+      if (chunk == BLOCK_N / kEpiN - 1 && threadIdx.x == 64) mbar_arrive(&tmem_empty_bar[buf]);
+      const int col = col0 + cp * 2;
       if (do_stats) {
-        // thread = one pair of adjacent columns x one slab of rows; fp32 sums of the bf16 values as stored
-        constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
-        const int cp = t % kPairs, slab = t / kPairs;
         float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-        const uint8_t* base = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
-#pragma unroll 8
+        const uint8_t* base = stg + (slab * kRowsPerSlab) * kEpiPitch + cp * 4;
+#pragma unroll
         for (int r = 0; r < kRowsPerSlab; ++r) {
-          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + r * kPitch));
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + r * kEpiPitch));
           s0 += f.x, s1 += f.y;
           q0 = fmaf(f.x, f.x, q0), q1 = fmaf(f.y, f.y, q1);
         }
-        const int col = n0 + cp * 2;
         if (col < p.cout) atomicAdd(p.stat_sum + col, s0), atomicAdd(p.stat_sqsum + col, q0);
         if (col + 1 < p.cout) atomicAdd(p.stat_sum + col + 1, s1), atomicAdd(p.stat_sqsum + col + 1, q1);
       }
-      if (p.bw_s1 != nullptr) {
-        // BN-backward partial sums of the producer layer. Its saved conv output y (same tile geometry) is first copied
-        // into shared memory with fully coalesced 16-byte loads (all loads of a thread in flight together), then the
-        // per-channel sums run from shared memory next to the staged gradient tile.
-        uint8_t* ytile = stg + 128 * kPitch;
-        {
-          constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow, kPasses = 128 / kRowsPerPass;
-          const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
-          uint4 q[kPasses];
+      if (p.bw_s1 != nullptr && col < p.cout) {
+        const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
+        const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        const uint8_t* gbase = stg + (slab * kRowsPerSlab) * kEpiPitch + cp * 4;
+        const uint8_t* ybase = ytile + (slab * kRowsPerSlab) * kEpiPitch + cp * 4;
 #pragma unroll
-          for (int pass = 0; pass < kPasses; ++pass) {
-            const int r = pass * kRowsPerPass + r0;
-            const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
-            q[pass] = make_uint4(0u, 0u, 0u, 0u);
-            if (rh < p.H && rw < p.W && n0 + seg * 8 < p.cout)
-              q[pass] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
-                                                             static_cast<size_t>(rw) * p.bw_ld + n0 + seg * 8));
-          }
-#pragma unroll
-          for (int pass = 0; pass < kPasses; ++pass)
-            *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = q[pass];
+        for (int r = 0; r < kRowsPerSlab; ++r) {
+          // rows outside the image hold zeros in the staged gradient slice: they contribute nothing
+          const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kEpiPitch));
+          const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kEpiPitch));
+          const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
+          const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
+          a0 += g0, a1 += g1;
+          b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
         }
-        bar_sync_epilogue();
-        constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
-        const int cp = t % kPairs, slab = t / kPairs;
-        const int col = n0 + cp * 2;
-        if (col < p.cout) {
-          const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
-          const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
-          float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-          const uint8_t* gbase = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
-          const uint8_t* ybase = ytile + (slab * kRowsPerSlab) * kPitch + cp * 4;
-#pragma unroll 8
-          for (int r = 0; r < kRowsPerSlab; ++r) {
-            // rows outside the image hold zeros in the staged gradient tile: they contribute nothing
-            const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
-            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
-            const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
-            const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
-            a0 += g0, a1 += g1;
-            b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
-          }
-          atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
-          if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
-        }
+        atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
+        if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
       }
-      // coalesced store: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass
-      constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
-      const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
-      if (n0 + seg * 8 < p.n_store) {
-#pragma unroll 4
-        for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
+      // coalesced store of the slice
+      if (col0 + seg * 8 < p.n_store) {
+#pragma unroll
+        for (int pass = 0; pass < kPasses; ++pass) {
           const int r = pass * kRowsPerPass + r0;
           const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
           if (rh < p.H && rw < p.W) {
-            const uint4 q = *reinterpret_cast<const uint4*>(stg + r * kPitch + seg * 16);
+            const uint4 q = *reinterpret_cast<const uint4*>(stg + r * kEpiPitch + seg * 16);
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride + rh * p.out_row_stride +
-                                static_cast<size_t>(rw) * p.ld_out + n0 + seg * 8;
+                                static_cast<size_t>(rw) * p.ld_out + col0 + seg * 8;
             *reinterpret_cast<uint4*>(op) = q;
           }
         }
       }
+      bar_sync_epilogue();  // staging slice fully consumed before the next slice overwrites it
     }
-    bar_sync_epilogue();  // staging tile fully consumed before the next tile overwrites it
     }  // tile loop
   }
 
@@ -1441,6 +1451,17 @@ static int launch_dgrad_bn(const IgemmDgradBnParams& q, int grid, cudaStream_t s
                     "igemm_dgrad_bn_kernel launch");
 }
 
+static int sm_count() {
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0)
+      num_sms = 148;
+  }
+  return num_sms;
+}
+
 static int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return (e != nullptr && e[0] != 0) ? atoi(e) : dflt;
@@ -1613,8 +1634,15 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     static const int max_ctas = env_int("SSEG_IGEMM_PERSISTENT_CTAS", 0);  // test knob: force many tiles per CTA
     const int cap = max_ctas > 0 ? max_ctas : num_sms;
     const int pgrid = grid < cap ? grid : cap;
-    if (block_n == 64) return launch_persistent<64, 6>(p, grid, pgrid, stream);
-    return launch_persistent<128, 4>(p, grid, pgrid, stream);
+    if (block_n == 64) return launch_persistent<64, 8>(p, grid, pgrid, stream);
+    return launch_persistent<128, 6>(p, grid, pgrid, stream);
+  }
+  // At most one CTA per SM (grid <= #SMs): the kernel is bound by TMA round trips (measured: ~35 B/cycle/SM with 96 KB in
+  // flight, profiles/r2_summary.md), so the whole shared memory of the SM goes to pipeline stages (192 KB in flight).
+  static const int deep = env_int("SSEG_IGEMM_DEEP", 1);
+  if (deep && grid <= sm_count()) {
+    if (block_n == 64) return launch<64, 8>(p, grid, stream);
+    return launch<128, 6>(p, grid, stream);
   }
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);

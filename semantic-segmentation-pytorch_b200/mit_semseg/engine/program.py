@@ -146,8 +146,9 @@ class SegProgram:
         # Independent sub-chains of small kernels (the four PPM pyramid branches; the parallel branches of an HRNet
         # module) can run on streams of their own inside the step graph instead of back to back: each chain is a
         # handful of latency-bound launches (8..200 CTAs) that leave most of the 148 SMs idle.
-        # Opt-in until measured on B200: SSEG_BRANCH_STREAMS=1.
-        self.use_branches = _os.environ.get("SSEG_BRANCH_STREAMS", "0") == "1"
+        # Measured on B200 (profiles/r2_first_run.log): 6.51 -> 6.21 ms/step (R50+PPM), 15.8 -> 10.4 ms (HRNetV2+C1): default on;
+        # SSEG_BRANCH_STREAMS=0 turns it off.
+        self.use_branches = _os.environ.get("SSEG_BRANCH_STREAMS", "1") == "1"
         # Inference programs: BatchNorm with running statistics is a per-channel affine, so conv -> BN -> (+shortcut) ->
         # ReLU runs as ONE kernel (sseg_conv_igemm_affine) and the raw conv output never exists. Opt-in until measured.
         self.fold_bn_eval = _os.environ.get("SSEG_FOLD_BN_EVAL", "0") == "1"

@@ -19,9 +19,7 @@ from test_gpu_e2e import _build, _rel, _step_metrics
 
 pytestmark = pytest.mark.gpu
 
-# code paths written after the round's GPU budget was spent: they run with SSEG_TEST_EXPERIMENTAL=1 (first thing next round)
-_EXPERIMENTAL = pytest.mark.skipif(__import__("os").environ.get("SSEG_TEST_EXPERIMENTAL", "0") != "1",
-                                   reason="not yet run on B200 (set SSEG_TEST_EXPERIMENTAL=1)")
+# (round 2: every test below had its first B200 run - 42 passed, profiles/r2_first_run.log - and is ungated)
 
 def test_hrnetv2_c1_backward_wiring_bn_eval():
     """305 encoder convolutions on 48/96/192/384-channel branches (partial 64-channel K blocks),
@@ -72,7 +70,6 @@ def test_hrnetv2_c1_inference_and_module_level_encoder():
     assert _rel(feats[0].cpu(), ref_feats[0]) <= 1e-2
 
 
-@_EXPERIMENTAL
 def test_multiscale_inference_equals_the_reference_loop():
     """eval.py:63-72: scores = sum_k module({img_k}, segSize) / len(scales) — here accumulated inside the head kernel."""
     import torch.nn.functional as F
@@ -90,7 +87,6 @@ def test_multiscale_inference_equals_the_reference_loop():
     assert (fused.sum(1) - 1).abs().max().item() < 1e-3
 
 
-@_EXPERIMENTAL
 @pytest.mark.parametrize("switch", ["SSEG_BRANCH_STREAMS", "SSEG_OVERLAP_RELAYOUT"])
 @pytest.mark.parametrize("enc,dec,fc,stride", [("resnet18dilated", "ppm_deepsup", 512, 8), ("hrnetv2", "c1", 720, 4)])
 def test_opt_in_schedules_match_the_default_schedule(enc, dec, fc, stride, switch, monkeypatch):
@@ -127,7 +123,6 @@ def test_opt_in_schedules_match_the_default_schedule(enc, dec, fc, stride, switc
 
 
 
-@_EXPERIMENTAL
 @pytest.mark.parametrize("relu,with_add,cout", [(1, True, 128), (2, True, 256), (1, False, 48), (0, False, 180)])
 def test_conv_with_folded_affine_epilogue(relu, with_add, cout):
     """sseg_conv_igemm_affine vs torch: relu?(conv * scale + shift (+ addend)), ReLU before / after the addend."""
@@ -157,7 +152,6 @@ def test_conv_with_folded_affine_epilogue(relu, with_add, cout):
     assert (got - ref).abs().max().item() <= 2 ** -8 * ref.abs().max().item()
 
 
-@_EXPERIMENTAL
 @pytest.mark.parametrize("enc,dec,fc", [("resnet18dilated", "ppm_deepsup", 512), ("resnet50", "upernet", 2048), ("hrnetv2", "c1", 720)])
 def test_folded_eval_bn_inference_matches_the_unfolded_schedule(enc, dec, fc, monkeypatch):
     from mit_semseg.engine.program import SegProgram
@@ -184,7 +178,6 @@ def test_folded_eval_bn_inference_matches_the_unfolded_schedule(enc, dec, fc, mo
     assert agree >= 0.9 and (not hr or err <= 5e-2)
 
 
-@_EXPERIMENTAL
 @pytest.mark.parametrize("k,cin,cout,hw,res,relu", [(1, 256, 128, 64, False, True), (3, 128, 256, 64, True, True),
                                                      (3, 64, 64, 128, False, True), (1, 512, 2048, 16, True, False),
                                                      (3, 96, 48, 32, False, True),
@@ -233,7 +226,6 @@ def test_fused_conv_bn_train_kernel_matches_the_three_kernel_sequence(k, cin, co
     assert (a1 != a0).float().mean().item() < 1e-2               # differences only where a last-bit scale difference flips a rounding
 
 
-@_EXPERIMENTAL
 def test_fused_conv_bn_train_schedule_matches_the_default_step(monkeypatch):
     """SSEG_COOP_BN=1 on a train-mode step (ResNet18dilated + C1_deepsup: no tiny-batch BN): same loss, features, running
     statistics and gradient direction as the three-kernel BN forward."""
@@ -259,7 +251,6 @@ def test_fused_conv_bn_train_schedule_matches_the_default_step(monkeypatch):
     assert torch.dot(g0, g1).item() / (g0.norm() * g1.norm()).item() >= 0.98
 
 
-@_EXPERIMENTAL
 @pytest.mark.parametrize("k,hw,cprod,cout_next", [(1, 64, 128, 256), (3, 64, 128, 256), (3, 38, 128, 256), (3, 32, 48, 48),
                                                   (3, 128, 64, 64), (1, 64, 1024, 256),
                                                   (1, 32, 64, 128), (3, 32, 128, 64), (3, 14, 48, 96), (1, 16, 256, 64)])
@@ -301,7 +292,6 @@ def test_fused_conv_bn_dgrad_kernel_matches_the_two_kernel_sequence(k, hw, cprod
     assert (dyb.float() - dya.float()).abs().max().item() <= 2 ** -7 * dya.float().abs().max().item()
 
 
-@_EXPERIMENTAL
 def test_pair_kernels_against_torch():
     """csrc/accurate.cu: split_affine, pooling / resizing of (hi, lo) pairs, fp32 stem, weight split."""
     import torch.nn.functional as F
@@ -355,7 +345,6 @@ def test_pair_kernels_against_torch():
     assert (v[:, :, 0] + v[:, :, 2] - wt.reshape(40, 24, 9).permute(0, 2, 1)).abs().max().item() <= 2 ** -15 * wt.abs().max().item()
 
 
-@_EXPERIMENTAL
 def test_accurate_inference_reaches_fp32_accuracy_on_the_gpu(monkeypatch):
     """BASELINE config 2: ResNet18dilated + PPM_deepsup inference, logits / probabilities within 1e-3 of the fp32 oracle."""
     from oracle import segnet_oracle as O
@@ -374,7 +363,6 @@ def test_accurate_inference_reaches_fp32_accuracy_on_the_gpu(monkeypatch):
     assert e_acc <= 1e-3 and agree >= 0.9995
 
 
-@_EXPERIMENTAL
 def test_mobilenet_kernels_and_inference():
     """csrc/depthwise.cu against torch, then BASELINE configs[0] (MobileNetV2dilated + C1_deepsup forward) end to end."""
     import torch.nn.functional as F
