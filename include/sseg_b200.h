@@ -268,6 +268,10 @@ typedef struct {
 } sseg_sgd_chunk_t;
 int sseg_sgd_step(const sseg_sgd_chunk_t* chunks_dev, int nchunks, float lr, float momentum, int first_step,
                   sseg_stream_t stream);
+/* x[0..n) *= *scalar_dev (a DEVICE scalar); nothing is read or written when the scalar is exactly 1. Replaces the
+ * multiplication by grad_output that autograd's chain rule applies to the step's parameter gradients when
+ * `loss.backward()` is called (train.py:43): the seed gradient is 1 there, so the pass is free. x 16-byte aligned. */
+int sseg_scale_by_scalar(float* x, long n, const float* scalar_dev, sseg_stream_t stream);
 
 /* ---- stem convolution (Cin = 3, 3x3, stride 2, pad 1, Cout = 64): models/resnet.py:100 -------------- */
 /* img: fp32 NCHW [N,3,H,W]; w: fp32 OIHW [64,3,3,3]; out: bf16 NHWC [N,Ho,Wo,64] dense; optional BN statistics. */

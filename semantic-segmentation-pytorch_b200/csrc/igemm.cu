@@ -20,9 +20,27 @@
 
 namespace sseg {
 
+// Cycle stamps of the plain kernel's phases (development builds only: `make trace` -> libsseg_b200_trace.so, read back with
+// sseg_debug_read_trace; tools/trace_igemm.py). One row of 16 clock64() values per CTA.
+#ifdef SSEG_TRACE
+__device__ long long g_trace[4096 * 16];
+#define SSEG_STAMP(k)                                                        \
+  do {                                                                       \
+    if (blockIdx.x < 4096) g_trace[blockIdx.x * 16 + (k)] = clock64();       \
+  } while (0)
+#else
+#define SSEG_STAMP(k) \
+  do {                \
+  } while (0)
+#endif
+
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle span
 constexpr int kNumThreads = 192;
+// the plain conv / weight-gradient kernels carry a SECOND producer warp: one thread issuing both operands' TMA boxes
+// back to back is the bottleneck of the main loop (measured with cycle stamps, profiles/r2_summary.md: ~230 cycles per
+// box issue = 470-550 cycles per k-step against 256 cycles of MMA), so the A and the B boxes are issued by different warps
+constexpr int kNumThreads2 = 224;
 constexpr int kABytes = kBlockM * kBlockK * 2;
 
 struct IgemmParams {
@@ -74,8 +92,10 @@ struct IgemmSmem {
 };
 
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_constant__ IgemmParams p) {
   using L = IgemmSmem<BLOCK_N, STAGES>;
+  static_assert(L::kDynBytes <= 232448, "shared memory budget");
+  static_assert(2 * 128 * (BLOCK_N * 2 + 16) <= STAGES * L::kStageBytes, "the epilogue stages two tiles in the pipeline buffers");
   SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
@@ -85,6 +105,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SSEG_STAMP(0);
 
   // tile decode: N-tile fastest so CTAs sharing an activation tile run together (L2 reuse)
   const int n_tile = blockIdx.x % p.n_tiles;
@@ -98,7 +119,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // one arrive.expect_tx per producer warp (A boxes, B boxes)
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -113,11 +134,14 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) SSEG_STAMP(1);
   pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) SSEG_STAMP(2);
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 0 || warp == 6) {
+    // ===================== TMA producers: warp 0 the activation boxes (A), warp 6 the weight boxes (B) =====================
     if (lane == 0) {
+      const bool is_a = warp == 0;
       int stage = 0, phase = 0;
       for (int t = 0; t < p.ntaps; ++t) {
         const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
@@ -133,15 +157,21 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
-          mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-          tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
-          // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
-          // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
-          const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
-          tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
+          if (is_a) {
+            mbar_expect_tx(&full_bar[stage], kABytes);
+            tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
+            if (t == 0 && b == 0) SSEG_STAMP(3);
+          } else {
+            // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
+            // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
+            const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+            mbar_expect_tx(&full_bar[stage], L::kBBytes);
+            tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
+          }
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
+      if (is_a) SSEG_STAMP(4);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (single thread) =====================
@@ -150,6 +180,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
       int stage = 0, phase = 0;
       for (int ks = 0; ks < num_k_steps; ++ks) {
         mbar_wait(&full_bar[stage], phase);
+        if (ks == 0) SSEG_STAMP(5);
         tc_fence_after();
         const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
         const uint32_t b_addr = a_addr + kABytes;
@@ -163,6 +194,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         if (++stage == STAGES) stage = 0, phase ^= 1;
       }
       umma_commit(tmem_full_bar);  // accumulator complete
+      SSEG_STAMP(6);
     }
     __syncwarp();
   } else {
@@ -176,6 +208,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
     const bool do_stats = p.stat_sum != nullptr;
 
     mbar_wait(tmem_full_bar, 0);
+    if (threadIdx.x == 64) SSEG_STAMP(7);
     tc_fence_after();
     // bf16 outputs are staged through shared memory (the pipeline stages are idle once the accumulator is complete):
     // rows are then stored with full 16-byte-per-lane coalescing and the per-channel statistics are column sums of the
@@ -251,9 +284,11 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         }
       }
     }
+    if (threadIdx.x == 64) SSEG_STAMP(8);
     if (!p.out_f32) {
       bar_sync_epilogue();  // the 4 epilogue warps only: the staged tile is complete
       const int t = threadIdx.x - 64;
+      if (threadIdx.x == 64) SSEG_STAMP(9);
       if (do_stats) {
         // thread = one pair of adjacent columns x one slab of rows; fp32 sums of the bf16 values as stored
         constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
@@ -270,6 +305,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         if (col < p.cout) atomicAdd(p.stat_sum + col, s0), atomicAdd(p.stat_sqsum + col, q0);
         if (col + 1 < p.cout) atomicAdd(p.stat_sum + col + 1, s1), atomicAdd(p.stat_sqsum + col + 1, q1);
       }
+      if (threadIdx.x == 64) SSEG_STAMP(10);
       if (p.bw_s1 != nullptr) {
         // BN-backward partial sums of the producer layer. Its saved conv output y (same tile geometry) is first copied
         // into shared memory with fully coalesced 16-byte loads (all loads of a thread in flight together), then the
@@ -277,20 +313,24 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
         uint8_t* ytile = stg + 128 * kPitch;
         {
           constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow, kPasses = 128 / kRowsPerPass;
+          constexpr int kBatch = kPasses < 16 ? kPasses : 16;   // loads in flight per thread (registers: 4 per load)
           const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
-          uint4 q[kPasses];
+#pragma unroll 1
+          for (int pb = 0; pb < kPasses; pb += kBatch) {
+            uint4 q[kBatch];
 #pragma unroll
-          for (int pass = 0; pass < kPasses; ++pass) {
-            const int r = pass * kRowsPerPass + r0;
-            const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
-            q[pass] = make_uint4(0u, 0u, 0u, 0u);
-            if (rh < p.H && rw < p.W && n0 + seg * 8 < p.cout)
-              q[pass] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
-                                                             static_cast<size_t>(rw) * p.bw_ld + n0 + seg * 8));
+            for (int j = 0; j < kBatch; ++j) {
+              const int r = (pb + j) * kRowsPerPass + r0;
+              const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+              q[j] = make_uint4(0u, 0u, 0u, 0u);
+              if (rh < p.H && rw < p.W && n0 + seg * 8 < p.cout)
+                q[j] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
+                                                            static_cast<size_t>(rw) * p.bw_ld + n0 + seg * 8));
+            }
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j)
+              *reinterpret_cast<uint4*>(ytile + ((pb + j) * kRowsPerPass + r0) * kPitch + seg * 16) = q[j];
           }
-#pragma unroll
-          for (int pass = 0; pass < kPasses; ++pass)
-            *reinterpret_cast<uint4*>(ytile + (pass * kRowsPerPass + r0) * kPitch + seg * 16) = q[pass];
         }
         bar_sync_epilogue();
         constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
@@ -319,6 +359,7 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
       // coalesced store: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass
       constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
       const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+      if (threadIdx.x == 64) SSEG_STAMP(11);
       if (n0 + seg * 8 < p.n_store) {
 #pragma unroll 4
         for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
@@ -335,12 +376,15 @@ __global__ void __launch_bounds__(kNumThreads) igemm_kernel(const __grid_constan
     }
   }
 
+  if (threadIdx.x == 64) SSEG_STAMP(12);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) SSEG_STAMP(13);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<BLOCK_N>(tmem_base);
   }
+  if (threadIdx.x == 32) SSEG_STAMP(14);
 }
 
 // Persistent variant: one CTA per SM walks tiles (tile = blockIdx.x + i * gridDim.x). Two TMEM accumulator buffers let the
@@ -697,7 +741,7 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
     configured[dev] = true;
   }
   count_launch(1);
-  return check_cuda(launch_k(igemm_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, p),
+  return check_cuda(launch_k(igemm_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads2), L::kDynBytes, stream, p),
                     "igemm_kernel launch");
 }
 
@@ -1581,6 +1625,16 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   int block_n = cout <= 64 ? 64 : 128;
   static const int ntile_thresh = env_int("SSEG_NTILE_THRESH", 80);
   if (block_n == 128 && m_tiles * ceil_div(n_store, 128) <= ntile_thresh) block_n = 64;
+  // N tile 256 for long-K layers with enough tiles (conv_last, cbr_deepsup, layer4's 3x3 convs and their data gradients):
+  // the main loop is bound by what one SM can take in through TMA (~100 B/cycle measured); a 128 x 256 tile needs
+  // 48 KB per 512 MMA cycles = 96 B/cycle where 128 x 128 needs 128 B/cycle. One CTA per SM then (192 KB of stages), so
+  // only where the un-overlapped epilogue is small against the main loop.
+  static const int n256 = env_int("SSEG_IGEMM_N256", 1);
+  static const int n256_min_ksteps = env_int("SSEG_IGEMM_N256_KSTEPS", 48);
+  static const int n256_min_tiles = env_int("SSEG_IGEMM_N256_TILES", 96);   // (both knobs: test hooks for small shapes)
+  if (n256 && block_n == 128 && n_store >= 256 && p.num_k_steps >= n256_min_ksteps && params_out == nullptr &&
+      m_tiles * ceil_div(n_store, 256) >= n256_min_tiles)
+    block_n = 256;
   p.n_tiles = ceil_div(n_store, block_n);
   rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, block_n);
   if (rc) return rc;
@@ -1624,7 +1678,7 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   }
   // persistent CTAs (one per SM, double-buffered accumulators) once there are clearly more tiles than SMs
   static const int persistent_min_tiles = env_int("SSEG_IGEMM_PERSISTENT", 0);  // 0 = off; e.g. 200 = on for >= 200 tiles
-  if (persistent_min_tiles > 0 && grid >= persistent_min_tiles) {
+  if (persistent_min_tiles > 0 && grid >= persistent_min_tiles && block_n != 256) {
     static int num_sms = 0;
     if (num_sms == 0) {
       int dev = 0;
@@ -1640,10 +1694,11 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   // At most one CTA per SM (grid <= #SMs): the kernel is bound by TMA round trips (measured: ~35 B/cycle/SM with 96 KB in
   // flight, profiles/r2_summary.md), so the whole shared memory of the SM goes to pipeline stages (192 KB in flight).
   static const int deep = env_int("SSEG_IGEMM_DEEP", 1);
-  if (deep && grid <= sm_count()) {
+  if (deep && grid <= sm_count() && block_n != 256) {
     if (block_n == 64) return launch<64, 8>(p, grid, stream);
     return launch<128, 6>(p, grid, stream);
   }
+  if (block_n == 256) return launch<256, 4>(p, grid, stream);
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);
 }
@@ -1883,7 +1938,7 @@ struct WgradSmem {
 };
 
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constant__ WgradParams p) {
+__global__ void __launch_bounds__(kNumThreads2) wgrad_kernel(const __grid_constant__ WgradParams p) {
   using L = WgradSmem<BLOCK_N, STAGES>;
   SSEG_DYN_SMEM(smem_raw);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1908,7 +1963,7 @@ __global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constan
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);  // one arrive.expect_tx per producer warp (dy boxes, x boxes)
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -1925,8 +1980,10 @@ __global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_sync();
 
-  if (warp == 0) {
+  if (warp == 0 || warp == 6) {
+    // warp 0 issues the two dy boxes (A, 128 output channels), warp 6 the x boxes (B, BLOCK_N input channels) of every k-step
     if (lane == 0) {
+      const bool is_a = warp == 0;
       // resolve, once, which source / channel offset each 64-channel B box comes from
       int bsrc[BLOCK_N / 64], bchan[BLOCK_N / 64];
 #pragma unroll
@@ -1954,12 +2011,16 @@ __global__ void __launch_bounds__(kNumThreads) wgrad_kernel(const __grid_constan
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes_;
-        mbar_expect_tx(&full_bar[stage], L::kStageBytes);
-        tma_load_4d(sa, &p.tmDY, &full_bar[stage], co0, w0, h0, img);
-        tma_load_4d(sa + kWgBoxBytes, &p.tmDY, &full_bar[stage], co0 + 64, w0, h0, img);
+        if (is_a) {
+          mbar_expect_tx(&full_bar[stage], L::kABytes_);
+          tma_load_4d(sa, &p.tmDY, &full_bar[stage], co0, w0, h0, img);
+          tma_load_4d(sa + kWgBoxBytes, &p.tmDY, &full_bar[stage], co0 + 64, w0, h0, img);
+        } else {
+          mbar_expect_tx(&full_bar[stage], L::kBBytes_);
 #pragma unroll
-        for (int j = 0; j < BLOCK_N / 64; ++j)
-          tma_load_4d(sb + j * kWgBoxBytes, &p.tmX[bsrc[j]], &full_bar[stage], bchan[j], w0 + dw, h0 + dh, img);
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_4d(sb + j * kWgBoxBytes, &p.tmX[bsrc[j]], &full_bar[stage], bchan[j], w0 + dw, h0 + dh, img);
+        }
         if (++stage == STAGES) stage = 0, phase ^= 1;
       }
     }
@@ -2039,7 +2100,7 @@ static int launch_wgrad(const WgradParams& p, int grid, cudaStream_t stream) {
     configured[dev] = true;
   }
   count_launch(1);
-  return check_cuda(launch_k(wgrad_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, p),
+  return check_cuda(launch_k(wgrad_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads2), L::kDynBytes, stream, p),
                     "wgrad_kernel launch");
 }
 
@@ -2096,3 +2157,14 @@ extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, 
   if (block_n == 64) return launch_wgrad<64, 4>(p, grid, stream);
   return launch_wgrad<128, 3>(p, grid, stream);
 }
+
+#ifdef SSEG_TRACE
+extern "C" int sseg_debug_read_trace(long long* host_out, long count) {
+  return sseg::check_cuda(cudaMemcpyFromSymbol(host_out, sseg::g_trace, count * sizeof(long long)), "read trace");
+}
+extern "C" int sseg_debug_clear_trace() {
+  void* p = nullptr;
+  if (cudaGetSymbolAddress(&p, sseg::g_trace) != cudaSuccess) return -1;
+  return sseg::check_cuda(cudaMemset(p, 0, sizeof(long long) * 4096 * 16), "clear trace");
+}
+#endif

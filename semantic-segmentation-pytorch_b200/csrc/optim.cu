@@ -17,16 +17,33 @@ __global__ void __launch_bounds__(256) sgd_chunks_kernel(const sseg_sgd_chunk_t*
   const float wd = c.weight_decay;
   const int n = c.n;
   if (c.vec4) {
+    // 4 independent float4 triples per thread in flight (all loads of an iteration are issued before the first use)
     const int n4 = n >> 2;
-    for (int i = threadIdx.x; i < n4; i += 256) {
-      float4 pv = reinterpret_cast<float4*>(p)[i];
-      const float4 gv = reinterpret_cast<const float4*>(g)[i];
-      float4 bv = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(b)[i];
-      bv.x = momentum * bv.x + fmaf(wd, pv.x, gv.x), bv.y = momentum * bv.y + fmaf(wd, pv.y, gv.y);
-      bv.z = momentum * bv.z + fmaf(wd, pv.z, gv.z), bv.w = momentum * bv.w + fmaf(wd, pv.w, gv.w);
-      pv.x -= lr * bv.x, pv.y -= lr * bv.y, pv.z -= lr * bv.z, pv.w -= lr * bv.w;
-      reinterpret_cast<float4*>(b)[i] = bv;
-      reinterpret_cast<float4*>(p)[i] = pv;
+    constexpr int U = 4;
+    for (int i0 = threadIdx.x; i0 < n4; i0 += 256 * U) {
+      float4 pv[U], gv[U], bv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        if (i < n4) {
+          pv[u] = reinterpret_cast<float4*>(p)[i];
+          gv[u] = reinterpret_cast<const float4*>(g)[i];
+          bv[u] = first_step ? make_float4(0.f, 0.f, 0.f, 0.f) : reinterpret_cast<float4*>(b)[i];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + u * 256;
+        if (i < n4) {
+          float4 q = pv[u], m = bv[u];
+          const float4 d = gv[u];
+          m.x = momentum * m.x + fmaf(wd, q.x, d.x), m.y = momentum * m.y + fmaf(wd, q.y, d.y);
+          m.z = momentum * m.z + fmaf(wd, q.z, d.z), m.w = momentum * m.w + fmaf(wd, q.w, d.w);
+          q.x -= lr * m.x, q.y -= lr * m.y, q.z -= lr * m.z, q.w -= lr * m.w;
+          reinterpret_cast<float4*>(b)[i] = m;
+          reinterpret_cast<float4*>(p)[i] = q;
+        }
+      }
     }
   } else {
     for (int i = threadIdx.x; i < n; i += 256) {
@@ -38,9 +55,35 @@ __global__ void __launch_bounds__(256) sgd_chunks_kernel(const sseg_sgd_chunk_t*
   }
 }
 
+// x *= *scalar, skipped altogether when the scalar is exactly 1 (the gradient `loss.backward()` seeds): the engine's
+// gradients are d loss / d param already, autograd's incoming grad_output only rescales them (engine/functional.py).
+__global__ void __launch_bounds__(256) scale_by_scalar_kernel(float* __restrict__ x, long n, const float* __restrict__ s) {
+  pdl_sync();
+  const float v = *s;
+  if (v == 1.f) return;
+  const long n4 = n >> 2;
+  for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long)gridDim.x * 256) {
+    float4 q = reinterpret_cast<float4*>(x)[i];
+    q.x *= v, q.y *= v, q.z *= v, q.w *= v;
+    reinterpret_cast<float4*>(x)[i] = q;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) x[(n4 << 2) + threadIdx.x] *= v;
+}
+
 }  // namespace sseg
 
 using namespace sseg;
+
+extern "C" int sseg_scale_by_scalar(float* x, long n, const float* scalar_dev, sseg_stream_t st) {
+  SSEG_REQUIRE(x != nullptr && scalar_dev != nullptr && n >= 0, "sseg_scale_by_scalar: bad argument");
+  SSEG_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "sseg_scale_by_scalar: x must be 16-byte aligned");
+  if (n == 0) return 0;
+  count_launch(1);
+  const long blocks = (n / 4 + 255) / 256;
+  return check_cuda(launch_k(scale_by_scalar_kernel, dim3((unsigned)(blocks < 1 ? 1 : (blocks > 148 * 8 ? 148 * 8 : blocks))),
+                             dim3(256), 0, (cudaStream_t)st, x, n, scalar_dev),
+                    "scale_by_scalar_kernel");
+}
 
 extern "C" int sseg_sgd_step(const sseg_sgd_chunk_t* chunks_dev, int nchunks, float lr, float momentum, int first_step,
                              sseg_stream_t st) {

@@ -21,7 +21,9 @@ struct PeerTable {
   int world, rank;
 };
 
-// All threads of every block call this. Block 0 publishes; every block waits for all peers.
+// All threads of every block call this. Block 0 publishes; every block waits for all peers. The wait is bounded: a peer
+// that never publishes (a dead or diverged rank) ends the launch with a trap after ~10 s of SM clocks instead of hanging
+// the job for ever (the reference's host-side rendezvous, comm.py:113, blocks without a timeout).
 __device__ __forceinline__ void peer_handshake(const PeerTable& pt, long flag_off, int step) {
   if (blockIdx.x == 0 && threadIdx.x < pt.world) {
     __threadfence_system();
@@ -29,9 +31,38 @@ __device__ __forceinline__ void peer_handshake(const PeerTable& pt, long flag_of
   }
   if (threadIdx.x < pt.world) {
     const int* mine = reinterpret_cast<const int*>(pt.base[pt.rank]) + flag_off + threadIdx.x;
-    while (ld_acquire_sys(mine) < step) __nanosleep(32);
+    const long long t0 = clock64();
+    while (ld_acquire_sys(mine) < step) {
+      __nanosleep(32);
+      if (clock64() - t0 > 20000000000ll) __trap();
+    }
   }
   __syncthreads();
+}
+
+// Sum of one value per rank, read straight out of the peers' arenas. All loads are issued before the first use (one NVLink
+// round trip, not `world` of them: with a data-dependent loop the eight loads of an 8-GPU job serialise, ~1 us each) and
+// added in rank order, so every rank computes bit-identical totals.
+__device__ __forceinline__ float peer_sum(const PeerTable& pt, long off) {
+  float v[SSEG_MAX_PEERS];
+#pragma unroll
+  for (int r = 0; r < SSEG_MAX_PEERS; ++r) v[r] = r < pt.world ? __ldcv(pt.base[r] + off) : 0.f;
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < SSEG_MAX_PEERS; ++r) s += v[r];
+  return s;
+}
+__device__ __forceinline__ void peer_sum2(const PeerTable& pt, long off_a, long off_b, float* a, float* b) {
+  float va[SSEG_MAX_PEERS], vb[SSEG_MAX_PEERS];
+#pragma unroll
+  for (int r = 0; r < SSEG_MAX_PEERS; ++r) {
+    va[r] = r < pt.world ? __ldcv(pt.base[r] + off_a) : 0.f;
+    vb[r] = r < pt.world ? __ldcv(pt.base[r] + off_b) : 0.f;
+  }
+  float sa = 0.f, sb = 0.f;
+#pragma unroll
+  for (int r = 0; r < SSEG_MAX_PEERS; ++r) sa += va[r], sb += vb[r];
+  *a = sa, *b = sb;
 }
 
 __global__ void peer_step_kernel(int* step) {
@@ -52,18 +83,15 @@ __global__ void __launch_bounds__(256) bn_finalize_peer_kernel(const PeerTable p
   pdl_sync();
   peer_handshake(pt, flag_off, *step_ptr);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  float cnt = 0.f;
-  for (int r = 0; r < pt.world; ++r) cnt += __ldcv(pt.base[r] + stats_off + 2 * C);
+  const int cc = c < C ? c : 0;
+  float s, q;
+  peer_sum2(pt, stats_off + cc, stats_off + C + cc, &s, &q);   // in flight together with the count loads below
+  const float cnt = peer_sum(pt, stats_off + 2 * C);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *count_out = cnt;
     if (update_running) running_iter[0] = running_iter[0] * (1.f - momentum) + 1.f;
   }
   if (c >= C) return;
-  float s = 0.f, q = 0.f;
-  for (int r = 0; r < pt.world; ++r) {
-    s += __ldcv(pt.base[r] + stats_off + c);
-    q += __ldcv(pt.base[r] + stats_off + C + c);
-  }
   const float mean = s / cnt;
   const float sumvar = q - s * mean;
   const float bias_var = sumvar / cnt, unbias_var = sumvar / (cnt - 1.f);
@@ -101,11 +129,8 @@ __global__ void __launch_bounds__(256) bn_bwd_peer_sum_kernel(const PeerTable pt
   peer_handshake(pt, flag_off, *step_ptr);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  float a = 0.f, b = 0.f;
-  for (int r = 0; r < pt.world; ++r) {
-    a += __ldcv(pt.base[r] + part_off + c);
-    b += __ldcv(pt.base[r] + part_off + C + c);
-  }
+  float a, b;
+  peer_sum2(pt, part_off + c, part_off + C + c, &a, &b);
   if (s2_raw) b = invstd[c] * (b - mean[c] * a);  // partials were sum g'*y (fused dgrad epilogue): convert to sum g'*xhat
   s1_tot[c] = a, s2_tot[c] = b;
   const float inv_w = 1.f / (float)pt.world;

@@ -464,6 +464,12 @@ def softmax_nll_bwd(logits, num_class, label, lse, accum, weight, dlogits):
                                            _stream()))
 
 
+def scale_by_scalar(x, scalar_dev):
+    """x (fp32, contiguous, 16-byte aligned) *= the device scalar; free when the scalar is exactly 1."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and scalar_dev.dtype == torch.float32
+    _C.check(_C.lib().sseg_scale_by_scalar(_C.ptr(x), x.numel(), _C.ptr(scalar_dev), _stream()))
+
+
 def colsum(x, C, out):
     P, _, ld = _pix(x)
     _C.check(_C.lib().sseg_colsum(_C.ptr(x), ld, P, C, _C.ptr(out), _stream()))

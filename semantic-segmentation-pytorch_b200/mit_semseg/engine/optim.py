@@ -9,7 +9,7 @@ import torch
 
 from . import _C
 
-_CHUNK = 65536
+_CHUNK = 16384   # elements per block: 4 iterations of 4 float4 triples in flight per thread
 
 
 class FusedSGD(torch.optim.Optimizer):

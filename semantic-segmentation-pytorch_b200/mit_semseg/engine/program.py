@@ -208,22 +208,36 @@ class SegProgram:
         npart = sum(2 * b.Cp for b in self.bns.values())
         import os
         if self.dist is not None and self.training and os.environ.get("SSEG_PEER_SYNC", "1") != "0":
+            # ONE arena (and one step counter, at its end) per module, shared by the programs of every input shape: its
+            # layout depends on the BatchNorm channel counts only. Ranks of a job draw different batch shapes (the
+            # reference's loader), so they build / reuse programs at different times - a collective in program
+            # construction, or handshake flags living in per-shape arenas, would hang or mis-pair them. The arena is
+            # created with the FIRST program (step 1, all ranks together); later programs only look it up.
             from .peer import PeerArena
             nflag = 16 * len(self.bns) + 16
-            try:
-                self.peer = PeerArena(ns + npart + nflag, self.dist, dev)
-                ok = 1.0
-            except Exception as exc:  # e.g. CUDA IPC unavailable between the ranks
-                self.peer, ok = None, 0.0
-                import warnings
-                warnings.warn("peer-memory SyncBN unavailable (%s); using NCCL all-reduces" % exc)
-            agree = torch.tensor([ok], device=dev)
-            self.dist.all_reduce(agree, op=self.dist.ReduceOp.MIN)  # every rank takes the same path
-            if agree.item() < 1.0:
-                self.peer = None
+            need = ns + npart + nflag
+            owner = self.seg if self.seg is not None else (self.enc if self.enc is not None else self.dec)
+            shared = owner.__dict__.get("_b200_peer")
+            if shared is None:
+                try:
+                    self.peer = PeerArena(need, self.dist, dev)
+                    ok = 1.0
+                except Exception as exc:  # e.g. CUDA IPC unavailable between the ranks
+                    self.peer, ok = None, 0.0
+                    import warnings
+                    warnings.warn("peer-memory SyncBN unavailable (%s); using NCCL all-reduces" % exc)
+                agree = torch.tensor([ok], device=dev)
+                self.dist.all_reduce(agree, op=self.dist.ReduceOp.MIN)  # every rank takes the same path
+                if agree.item() < 1.0:
+                    self.peer = None
+                if self.peer is not None:
+                    self.peer.floats[:ns + npart].zero_()
+                owner.__dict__["_b200_peer"] = (self.peer, need)
+            else:
+                self.peer, have = shared
+                assert have == need, "the module's BatchNorm layers changed after its first step program was built"
         if self.peer is not None:
             self.sflat = self.peer.floats[:ns + npart]
-            self.sflat.zero_()
         else:
             self.sflat = torch.zeros(ns, device=dev, dtype=torch.float32)
         self.sinit = torch.zeros(self.sflat.numel(), device=dev, dtype=torch.float32)
@@ -296,8 +310,19 @@ class SegProgram:
     def _prep_weights(self):
         """One launch re-lays out every conv weight (fp32 OIHW master -> bf16 GEMM operands)."""
         convs = [c for c in self.convs.values() if c.I != 3]  # the stem conv reads the fp32 master weight directly
-        for c in convs:
-            c.pg = torch.empty_like(c.mod.weight) if self.with_grad else None
+        # parameter-layout (OIHW) gradients of all convolutions live in ONE flat buffer (16-byte aligned slots), so that
+        # autograd's grad_output scaling is a single launch over it (engine/functional.py)
+        if self.with_grad:
+            sizes = [_pad(c.mod.weight.numel(), 4) for c in self.convs.values()]
+            self.pg_flat = torch.zeros(sum(sizes), device=self.dev, dtype=torch.float32)
+            off = 0
+            for c, n in zip(self.convs.values(), sizes):
+                c.pg = self.pg_flat[off:off + c.mod.weight.numel()].view_as(c.mod.weight)
+                off += n
+        else:
+            self.pg_flat = None
+            for c in self.convs.values():
+                c.pg = None
         self._late_convs, self._late_pending = set(), False
         if not self.overlap_relayout:
             self.wtable = ops.WeightTable([self._wentry(c) for c in convs], self.dev)
@@ -772,7 +797,7 @@ class SegProgram:
             self.bwd.append(lambda: self.gflat[:self.g_small].mul_(scale))
         for c in self.convs.values():
             if c.I == 3:
-                g = torch.empty_like(c.mod.weight)
+                g = c.pg
                 self._pg[id(c)] = g
 
                 def stem_grad(g=g, c=c):
@@ -894,20 +919,25 @@ class SegProgram:
         for f in self.bwd:
             f()
 
-    def capture(self):
-        """Capture the whole step into one CUDA graph (after a warm-up run on a side stream)."""
-        # the warm-up executes the step: keep it side-effect free on the module (BN running statistics)
-        bufs = [b for m in self._modules() if isinstance(m, _BatchNorm) for b in m.buffers(recurse=False)]
-        saved = [b.clone() for b in bufs]
-        s = torch.cuda.Stream(self.dev)
-        s.wait_stream(torch.cuda.current_stream(self.dev))
-        with torch.cuda.stream(s):
-            self.run_eager()
-            self.run_eager()
-        torch.cuda.current_stream(self.dev).wait_stream(s)
-        torch.cuda.synchronize(self.dev)
-        for b, v in zip(bufs, saved):
-            b.copy_(v)
+    def capture(self, warm=True):
+        """Capture the whole step into one CUDA graph. warm=True: two warm-up executions on a side stream first (lazy
+        one-time initialisation - kernel attributes, tensor-map cache - must not happen inside the capture).
+        warm=False: the caller has already run this program eagerly; nothing is executed here, so no SyncBN handshake /
+        NCCL call is issued - under torch.distributed ranks may then capture at different steps (they see different batch
+        shapes)."""
+        if warm:
+            # the warm-up executes the step: keep it side-effect free on the module (BN running statistics)
+            bufs = [b for m in self._modules() if isinstance(m, _BatchNorm) for b in m.buffers(recurse=False)]
+            saved = [b.clone() for b in bufs]
+            s = torch.cuda.Stream(self.dev)
+            s.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(s):
+                self.run_eager()
+                self.run_eager()
+            torch.cuda.current_stream(self.dev).wait_stream(s)
+            torch.cuda.synchronize(self.dev)
+            for b, v in zip(bufs, saved):
+                b.copy_(v)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.run_eager()

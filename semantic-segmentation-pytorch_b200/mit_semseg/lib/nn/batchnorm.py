@@ -2,9 +2,9 @@
 
 Reference: mit_semseg/lib/nn/modules/batchnorm.py:37-139 (vacancy/Synchronized-BatchNorm-PyTorch).
 The reference synchronises replicas of ONE process through Python queues (comm.py) and torch.cuda.comm; here every
-GPU is its own process and the statistics exchange is a stream-ordered NCCL all-reduce of [sum, sum^2, count]
-issued by the engine (mit_semseg/engine/program.py) between the conv kernel that produced the sums and the
-kernel that applies them.  Which formula is used follows the reference's switch (batchnorm.py:58):
+GPU is its own process. Inside a SegmentationModule step program (mit_semseg/engine/program.py) the [sum, sum^2, count]
+message of a layer is pooled over NVLink peer memory by the finalize kernel itself (csrc/peer.cu; NCCL all-reduces with
+SSEG_PEER_SYNC=0). Which formula is used follows the reference's switch (batchnorm.py:58):
 
   * not parallel, or eval  -> F.batch_norm semantics: biased var + eps, running stats with `momentum`
   * parallel and training  -> pooled statistics, clamp(var, eps)^-0.5, accumulator-style running stats
@@ -13,7 +13,8 @@ kernel that applies them.  Which formula is used follows the reference's switch 
 `patch_replication_callback`, see parallel.py).
 
 When the module is called on its own (outside a SegmentationModule program) it runs the same CUDA kernels through
-`mit_semseg.engine.functional.batch_norm`.
+`mit_semseg.engine.functional.batch_norm` (bf16 storage, fp32 statistics; the message is all-reduced with
+torch.distributed when synchronised), forward and backward.
 """
 import torch
 from torch.nn.modules.batchnorm import _BatchNorm

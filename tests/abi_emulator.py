@@ -716,6 +716,12 @@ class EmuLib:
         return 0
 
     # ---- optimiser
+    def sseg_scale_by_scalar(self, x, n, scalar, stream):
+        v = flat(scalar, 1, torch.float32)[0].item()
+        if v != 1.0:
+            flat(x, n, torch.float32).mul_(v)
+        return 0
+
     def sseg_sgd_step(self, chunks, nchunks, lr, momentum, first_step, stream):
         from mit_semseg.engine import _C
         for c in (_C.SgdChunk * nchunks).from_address(_addr(chunks)):

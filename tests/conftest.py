@@ -136,7 +136,7 @@ def install_cuda_stand_in(setattr_, mode):
             _real(self, *a, **k)
             self.dry_run, self.serial = False, True
         setattr_(cls, "__init__", init)
-        setattr_(cls, "capture", lambda self: None)
+        setattr_(cls, "capture", lambda self, warm=True: None)
 
 
 @pytest.fixture(autouse=True)

@@ -10,6 +10,7 @@
 //     (a deadlock on the GPU box costs a strike; here it costs a test failure).
 // It checks control flow, indexing, barrier phases and arithmetic -- not timing, not the memory model.
 #pragma once
+#include <time.h>
 #define __CUSIM__ 1
 
 #include <cuda.h>
@@ -68,6 +69,11 @@ static inline void __threadfence() { __sync_synchronize(); }
 static inline void __threadfence_system() { __sync_synchronize(); }
 static inline void __nanosleep(unsigned) { ::cusim::spin_pause(); }
 static inline void __trap() { ::cusim::trap(); }
+static inline long long clock64() {   // "SM cycles": host nanoseconds x 2 (a 2 GHz clock), monotonic
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (static_cast<long long>(ts.tv_sec) * 1000000000ll + ts.tv_nsec) * 2;
+}
 
 template <typename T>
 static inline T __shfl_sync(unsigned, T v, int src, int = 32) {

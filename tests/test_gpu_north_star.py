@@ -102,3 +102,11 @@ def test_sync_batchnorm_two_processes_matches_batchnorm_on_the_concatenated_batc
     sys.stderr.write(out.stderr[-3000:])
     assert out.returncode == 0
     assert "SYNCBN-TEST OK" in out.stdout
+    # the same exchange inside the step program (peer-memory SyncBN + gradient buckets) against the oracle on the
+    # concatenated batch: tools/dist_check.py without the flag
+    cmd = cmd[:-1]
+    cmd[cmd.index(str(port))] = str(port + 1)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    sys.stdout.write(out.stdout[-3000:])
+    sys.stderr.write(out.stderr[-3000:])
+    assert out.returncode == 0 and "DIST_CHECK_OK" in out.stdout

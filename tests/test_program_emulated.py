@@ -207,7 +207,7 @@ def test_training_loss_curve_follows_the_oracle(emu, monkeypatch):
         prog.dry_run, prog.serial = False, True
         return prog
     monkeypatch.setattr(EF, "SegProgram", factory)
-    monkeypatch.setattr(real, "capture", lambda self: None)
+    monkeypatch.setattr(real, "capture", lambda self, warm=True: None)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     enc, dec, fc = "resnet18dilated", "c1_deepsup", 512
     seg = _seg(enc, dec, fc)

@@ -139,7 +139,7 @@ def null_engine(null_lib, monkeypatch):
         prog.dry_run, prog.serial = False, True
         return prog
     monkeypatch.setattr(EF, "SegProgram", factory)
-    monkeypatch.setattr(real, "capture", lambda self: None)
+    monkeypatch.setattr(real, "capture", lambda self, warm=True: None)
     monkeypatch.setattr(torch.Tensor, "is_cuda", property(lambda self: True))
     from mit_semseg.engine import accurate as ACC
     real_acc = ACC.AccurateInference

@@ -18,10 +18,56 @@ import torch.nn as nn  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
 
+def syncbn_module_test(rank, world):
+    """lib/nn/modules/tests/test_sync_batchnorm.py:98-108 (testSyncBatchNorm2DSyncTrain) with the replicas as processes:
+    each rank feeds its slice of the batch through SynchronizedBatchNorm2d; outputs and input gradients must equal
+    nn.BatchNorm2d on the WHOLE batch (one bf16 rounding of the value scale), the parameter gradients must sum to its."""
+    from mit_semseg.lib.nn import SynchronizedBatchNorm2d
+    g = torch.Generator().manual_seed(0)
+    N, C = 16, 16
+    full = torch.rand(N, C, 16, 16, generator=g).bfloat16().float()
+    gout = torch.randn(N, C, 16, 16, generator=g).bfloat16().float()
+    gamma, beta = 0.5 + torch.rand(C, generator=g), torch.randn(C, generator=g) * 0.1
+    bn, sbn = nn.BatchNorm2d(C).cuda(), SynchronizedBatchNorm2d(C).cuda()
+    for m in (bn, sbn):
+        m.weight.data.copy_(gamma)
+        m.bias.data.copy_(beta)
+    assert sbn.is_synchronized()
+    per = N // world
+    lo, hi = rank * per, (rank + 1) * per
+    x = full[lo:hi].cuda().requires_grad_(True)
+    out = sbn(x)
+    (out * gout[lo:hi].cuda()).sum().backward()
+    xr = full.cuda().requires_grad_(True)
+    ref = bn(xr)
+    (ref * gout.cuda()).sum().backward()
+
+    def close(a, b, what, rel=2 ** -8):
+        tol = rel * max(b.abs().max().item(), 1e-3)
+        err = (a - b).abs().max().item()
+        assert err <= tol, "rank %d %s: %.3e > %.3e" % (rank, what, err, tol)
+    close(out.detach(), ref.detach()[lo:hi], "output")
+    close(x.grad, xr.grad[lo:hi], "input gradient")
+    gw, gb = sbn.weight.grad.clone(), sbn.bias.grad.clone()
+    dist.all_reduce(gw)
+    dist.all_reduce(gb)
+    close(gw, bn.weight.grad, "weight gradient (summed over ranks)", rel=2 ** -7)
+    close(gb, bn.bias.grad, "bias gradient (summed over ranks)", rel=2 ** -7)
+    ok = torch.ones(1, device="cuda")
+    dist.all_reduce(ok)
+    if rank == 0:
+        print("SYNCBN-TEST OK (world %d)" % world, flush=True)
+
+
 def main():
     rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if "--syncbn-test" in sys.argv:
+        syncbn_module_test(rank, world)
+        import bench
+        bench.shutdown_distributed()
+        return
     from test_gpu_e2e import _build
     from mit_semseg.engine.program import SegProgram
     from mit_semseg.engine import ops
