@@ -161,6 +161,14 @@ int sseg_bn_running_from_tmp(const float* tmp_running_mean, const float* tmp_run
                              float* running_mean, float* running_var, int C, sseg_stream_t stream);
 int sseg_conv_bn_train(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                        const sseg_act_t* a_out, const sseg_bn_fused_t* bn, sseg_stream_t stream);
+/* sseg_conv_igemm with the layer's BatchNorm statistics AND their finalisation (train mode, one GPU: F.batch_norm's
+ * training branch, lib/nn/modules/batchnorm.py:58-61) in the same launch: every CTA adds its tile's per-channel sum / sum
+ * of squares to bn->stat_sum / stat_sqsum and takes a ticket from bn->counter (one zeroed uint32); the CTA that takes the
+ * last ticket computes mean / inv_std / scale / shift for all channels and updates running_mean / running_var (both may be
+ * NULL). Replaces sseg_conv_igemm(stats) + sseg_bn_finalize(SSEG_BN_TRAIN); the res / relu / peer fields of *bn are not
+ * used (the normalisation itself stays in sseg_bn_apply). out: bf16, the raw convolution output. */
+int sseg_conv_igemm_bnfin(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
+                          const sseg_bn_fused_t* bn, sseg_stream_t stream);
 int sseg_conv_bn_train_fits(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout, const sseg_act_t* y,
                             const sseg_act_t* a_out, const sseg_bn_fused_t* bn);
 

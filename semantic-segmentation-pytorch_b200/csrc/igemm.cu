@@ -79,6 +79,14 @@ struct IgemmParams {
   const float* bw_fshift;
   float* bw_s1;
   float* bw_s2;
+  // BatchNorm finalize by the LAST CTA of the launch (train-mode, single GPU; sseg_conv_igemm_bnfin): once every CTA has
+  // added its tile's statistics, the CTA that takes the last ticket turns (sum, sum of squares) into mean / inv_std /
+  // scale / shift and updates the running statistics - the separate bn_finalize launch of every layer disappears
+  unsigned int* fin_counter;
+  const float* fin_gamma;
+  const float* fin_beta;
+  float fin_eps, fin_momentum, fin_count;
+  float *fin_mean, *fin_invstd, *fin_scale, *fin_shift, *fin_rmean, *fin_rvar;
 };
 
 template <int BLOCK_N, int STAGES>
@@ -102,6 +110,7 @@ __global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint32_t* tmem_ptr_smem2 = tmem_ptr_smem + 1;  // "this CTA took the last ticket" flag of the fused BN finalize
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -140,7 +149,10 @@ __global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_consta
 
   if (warp == 0 || warp == 6) {
     // ===================== TMA producers: warp 0 the activation boxes (A), warp 6 the weight boxes (B) =====================
-    if (lane == 0) {
+    // The WHOLE warp walks the loop and one elected lane issues: with warp-uniform control flow the coordinates and
+    // barrier addresses stay in uniform registers; issuing from a divergent `if (lane == 0)` region made the compiler wrap
+    // every uniform-datapath instruction in an election loop (measured: ~400 cycles per box issue).
+    {
       const bool is_a = warp == 0;
       int stage = 0, phase = 0;
       for (int t = 0; t < p.ntaps; ++t) {
@@ -157,42 +169,50 @@ __global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_consta
           }
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::kStageBytes;
-          if (is_a) {
-            mbar_expect_tx(&full_bar[stage], kABytes);
-            tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
-            if (t == 0 && b == 0) SSEG_STAMP(3);
-          } else {
-            // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
-            // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
-            const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
-            mbar_expect_tx(&full_bar[stage], L::kBBytes);
-            tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
+          // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
+          // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
+          const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+          if (elect_one()) {
+            if (is_a) {
+              mbar_expect_tx(&full_bar[stage], kABytes);
+              tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
+              if (t == 0 && b == 0) SSEG_STAMP(3);
+            } else {
+              mbar_expect_tx(&full_bar[stage], L::kBBytes);
+              tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) stage = 0, phase ^= 1;
         }
       }
-      if (is_a) SSEG_STAMP(4);
+      if (is_a && lane == 0) SSEG_STAMP(4);
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, kBlockM, BLOCK_N);
-      int stage = 0, phase = 0;
-      for (int ks = 0; ks < num_k_steps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
-        if (ks == 0) SSEG_STAMP(5);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-        const uint32_t b_addr = a_addr + kABytes;
+    // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues =====================
+    // (same reason as above; the shared-memory descriptors are stepped by adding to their low word instead of being
+    // re-encoded for every instruction: the issue loop, not the tensor core, was the limit - ~140 cycles per MMA
+    // instruction against 64 needed)
+    constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, kBlockM, BLOCK_N);
+    constexpr uint32_t dhi = smem_desc_hi_sw128(1024);
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16);
+    int stage = 0, phase = 0;
+    for (int ks = 0; ks < num_k_steps; ++ks) {
+      mbar_wait(&full_bar[stage], phase);
+      if (ks == 0 && lane == 0) SSEG_STAMP(5);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
+      const uint32_t b_lo = a_lo + (kABytes >> 4);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (ks | k) != 0);
-        }
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_bf16(tmem_base, smem_desc_join(a_lo + 2 * k, dhi), smem_desc_join(b_lo + 2 * k, dhi), idesc, (ks | k) != 0);
         umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
-        if (++stage == STAGES) stage = 0, phase ^= 1;
       }
+      __syncwarp();
+      if (++stage == STAGES) stage = 0, phase ^= 1;
+    }
+    if (elect_one()) {
       umma_commit(tmem_full_bar);  // accumulator complete
       SSEG_STAMP(6);
     }
@@ -377,6 +397,36 @@ __global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_consta
   }
 
   if (threadIdx.x == 64) SSEG_STAMP(12);
+  if (p.fin_counter != nullptr && warp >= 2 && warp < 6) {
+    // every epilogue thread's statistics atomics are ordered before its arrival at the barrier; one thread then takes the
+    // launch-wide ticket (the pattern of the threadFenceReduction sample); the flag travels through the tmem-pointer word
+    __threadfence();
+    bar_sync_epilogue();
+    if (threadIdx.x == 64) {
+      const unsigned int ticket = atomicAdd(p.fin_counter, 1u);
+      *tmem_ptr_smem2 = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
+    bar_sync_epilogue();
+    if (*tmem_ptr_smem2 != 0u) {
+      __threadfence();
+      const float cnt = p.fin_count;
+      for (int c = threadIdx.x - 64; c < p.cout; c += 128) {
+        const float s = __ldcg(p.stat_sum + c), q = __ldcg(p.stat_sqsum + c);
+        const float mean = s / cnt;
+        const float sumvar = q - s * mean;
+        const float bias_var = sumvar / cnt, unbias_var = sumvar / (cnt - 1.f);
+        const float inv_std = rsqrtf(fmaxf(bias_var, 0.f) + p.fin_eps);
+        if (p.fin_rmean != nullptr) {
+          p.fin_rmean[c] = (1.f - p.fin_momentum) * p.fin_rmean[c] + p.fin_momentum * mean;
+          p.fin_rvar[c] = (1.f - p.fin_momentum) * p.fin_rvar[c] + p.fin_momentum * unbias_var;
+        }
+        const float g = p.fin_gamma ? p.fin_gamma[c] : 1.f, b = p.fin_beta ? p.fin_beta[c] : 0.f;
+        p.fin_mean[c] = mean, p.fin_invstd[c] = inv_std;
+        p.fin_scale[c] = g * inv_std;
+        p.fin_shift[c] = b - mean * g * inv_std;
+      }
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (threadIdx.x == 0) SSEG_STAMP(13);
@@ -1588,7 +1638,8 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
                            int out_f32, const float* bias, const sseg_act_t* addend, float* stat_sum, float* stat_sqsum,
                            const sseg_act_t* bw_y, const float* bw_fscale, const float* bw_fshift, float* bw_s1,
                            float* bw_s2, sseg_stream_t stream_, const EpilogueAffine* ep = nullptr,
-                           IgemmParams* params_out = nullptr, int* block_n_out = nullptr) {
+                           IgemmParams* params_out = nullptr, int* block_n_out = nullptr,
+                           const sseg_bn_fused_t* fin = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SSEG_REQUIRE(g != nullptr && out != nullptr && w_bf16 != nullptr, "sseg_conv_igemm: null argument");
   const int n_store = out->c;
@@ -1670,6 +1721,17 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     p.bw_ld = bw_y->ld, p.bw_row_stride = bw_y->row_stride, p.bw_img_stride = bw_y->img_stride;
     p.bw_fscale = bw_fscale, p.bw_fshift = bw_fshift, p.bw_s1 = bw_s1, p.bw_s2 = bw_s2;
   }
+  if (fin != nullptr) {
+    SSEG_REQUIRE(stat_sum != nullptr && fin->counter != nullptr && fin->mean_out && fin->invstd_out && fin->scale_out &&
+                     fin->shift_out && fin->count > 1.f,
+                 "sseg_conv_igemm_bnfin: statistics, counter and the four output vectors are required");
+    SSEG_REQUIRE((fin->running_mean == nullptr) == (fin->running_var == nullptr), "sseg_conv_igemm_bnfin: running stats must pair");
+    p.fin_counter = fin->counter;
+    p.fin_gamma = fin->gamma, p.fin_beta = fin->beta;
+    p.fin_eps = fin->eps, p.fin_momentum = fin->momentum, p.fin_count = fin->count;
+    p.fin_mean = fin->mean_out, p.fin_invstd = fin->invstd_out, p.fin_scale = fin->scale_out, p.fin_shift = fin->shift_out;
+    p.fin_rmean = fin->running_mean, p.fin_rvar = fin->running_var;
+  }
   const int grid = gh.vn * p.tiles_h * p.tiles_w * p.n_tiles;
   if (params_out != nullptr) {  // the caller launches a different kernel over the same operands / geometry
     *params_out = p;
@@ -1678,7 +1740,7 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   }
   // persistent CTAs (one per SM, double-buffered accumulators) once there are clearly more tiles than SMs
   static const int persistent_min_tiles = env_int("SSEG_IGEMM_PERSISTENT", 0);  // 0 = off; e.g. 200 = on for >= 200 tiles
-  if (persistent_min_tiles > 0 && grid >= persistent_min_tiles && block_n != 256) {
+  if (persistent_min_tiles > 0 && grid >= persistent_min_tiles && block_n != 256 && fin == nullptr) {
     static int num_sms = 0;
     if (num_sms == 0) {
       int dev = 0;
@@ -1708,6 +1770,13 @@ extern "C" int sseg_conv_igemm(const sseg_conv_geom_t* g, const void* w_bf16, lo
                                float* stat_sum, float* stat_sqsum, sseg_stream_t stream) {
   return conv_igemm_impl(g, w_bf16, w_ld, cout, out, out_f32, bias, addend, stat_sum, stat_sqsum, nullptr, nullptr, nullptr,
                          nullptr, nullptr, stream);
+}
+
+extern "C" int sseg_conv_igemm_bnfin(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                                     const sseg_act_t* out, const sseg_bn_fused_t* bn, sseg_stream_t stream) {
+  SSEG_REQUIRE(bn != nullptr, "sseg_conv_igemm_bnfin: null BatchNorm description");
+  return conv_igemm_impl(g, w_bf16, w_ld, cout, out, 0, nullptr, nullptr, bn->stat_sum, bn->stat_sqsum, nullptr, nullptr,
+                         nullptr, nullptr, nullptr, stream, nullptr, nullptr, nullptr, bn);
 }
 
 extern "C" int sseg_conv_igemm_affine(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
@@ -1981,8 +2050,9 @@ __global__ void __launch_bounds__(kNumThreads2) wgrad_kernel(const __grid_consta
   pdl_sync();
 
   if (warp == 0 || warp == 6) {
-    // warp 0 issues the two dy boxes (A, 128 output channels), warp 6 the x boxes (B, BLOCK_N input channels) of every k-step
-    if (lane == 0) {
+    // warp 0 issues the two dy boxes (A, 128 output channels), warp 6 the x boxes (B, BLOCK_N input channels) of every k-step;
+    // the whole warp walks the loop (warp-uniform control flow), one elected lane issues
+    {
       const bool is_a = warp == 0;
       // resolve, once, which source / channel offset each 64-channel B box comes from
       int bsrc[BLOCK_N / 64], bchan[BLOCK_N / 64];
@@ -2011,39 +2081,44 @@ __global__ void __launch_bounds__(kNumThreads2) wgrad_kernel(const __grid_consta
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes_;
-        if (is_a) {
-          mbar_expect_tx(&full_bar[stage], L::kABytes_);
-          tma_load_4d(sa, &p.tmDY, &full_bar[stage], co0, w0, h0, img);
-          tma_load_4d(sa + kWgBoxBytes, &p.tmDY, &full_bar[stage], co0 + 64, w0, h0, img);
-        } else {
-          mbar_expect_tx(&full_bar[stage], L::kBBytes_);
+        if (elect_one()) {
+          if (is_a) {
+            mbar_expect_tx(&full_bar[stage], L::kABytes_);
+            tma_load_4d(sa, &p.tmDY, &full_bar[stage], co0, w0, h0, img);
+            tma_load_4d(sa + kWgBoxBytes, &p.tmDY, &full_bar[stage], co0 + 64, w0, h0, img);
+          } else {
+            mbar_expect_tx(&full_bar[stage], L::kBBytes_);
 #pragma unroll
-          for (int j = 0; j < BLOCK_N / 64; ++j)
-            tma_load_4d(sb + j * kWgBoxBytes, &p.tmX[bsrc[j]], &full_bar[stage], bchan[j], w0 + dw, h0 + dh, img);
+            for (int j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_4d(sb + j * kWgBoxBytes, &p.tmX[bsrc[j]], &full_bar[stage], bchan[j], w0 + dw, h0 + dh, img);
+          }
         }
+        __syncwarp();
         if (++stage == STAGES) stage = 0, phase ^= 1;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1, 128, BLOCK_N);
-      int stage = 0, phase = 0;
-      for (int ks = 0; ks < num_k_steps; ++ks) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + stage * L::kStageBytes);
-        const uint32_t b_addr = a_addr + L::kABytes_;
+    // MMA issuer: the whole warp walks the loop, one elected lane issues; descriptors stepped through their low words
+    constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, /*A MN-major*/ 1, /*B MN-major*/ 1, 128, BLOCK_N);
+    constexpr uint32_t dhi = smem_desc_hi_sw128(1024);
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), kWgBoxBytes);
+    int stage = 0, phase = 0;
+    for (int ks = 0; ks < num_k_steps; ++ks) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
+      const uint32_t b_lo = a_lo + (L::kABytes_ >> 4);
+      if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < kWgKPix / 16; ++k) {
-          const uint64_t da = make_smem_desc_sw128(a_addr + k * 2048, kWgBoxBytes, 1024);
-          const uint64_t db = make_smem_desc_sw128(b_addr + k * 2048, kWgBoxBytes, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (ks | k) != 0);
-        }
+        for (int k = 0; k < kWgKPix / 16; ++k)
+          umma_bf16(tmem_base, smem_desc_join(a_lo + k * (2048 >> 4), dhi), smem_desc_join(b_lo + k * (2048 >> 4), dhi), idesc,
+                    (ks | k) != 0);
         umma_commit(&empty_bar[stage]);
-        if (++stage == STAGES) stage = 0, phase ^= 1;
       }
-      umma_commit(tmem_full_bar);
+      __syncwarp();
+      if (++stage == STAGES) stage = 0, phase ^= 1;
     }
+    if (elect_one()) umma_commit(tmem_full_bar);
     __syncwarp();
   } else {
     const int quarter = warp & 3;

@@ -198,6 +198,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   return d;
 }
 
+// The same descriptor in two 32-bit halves: only the start-address field changes inside a main loop, so the loops keep
+// `lo` in a register, add (bytes >> 4) to step through stages / K slices, and never re-encode the constant half.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return ((smem_addr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__host__ __device__ constexpr uint32_t smem_desc_hi_sw128(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint64_t smem_desc_join(uint32_t lo, uint32_t hi) {
+  return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
 // Instruction descriptor for kind::f16 / kind::tf32 (cute::UMMA::InstrDescriptor):
 //   [4,6) c_format (1 = F32) | [7,10) a_format | [10,13) b_format (0 F16, 1 BF16, 2 TF32)
 //   [15] a_major (0 K, 1 MN) | [16] b_major | [17,23) N>>3 | [24,29) M>>4

@@ -1,6 +1,9 @@
 // Batched weight re-layout: ONE launch converts every conv of the model.
-//   prep : fp32 OIHW master weights -> bf16 [O][T*I] (forward operand) and bf16 [I][T*Opad] (data-gradient operand)
-//   grad : fp32 [O][T*I] weight gradients (sseg_conv_wgrad layout) -> fp32 OIHW, times scale
+//   prep : fp32 master weights -> bf16 [O][T*I] (forward operand) and bf16 [I][T*Opad] (data-gradient operand). The master
+//          is OIHW-contiguous, or (descriptor flag `reserved` = 1) channels-last = [O][T][I] in memory: then the forward
+//          operand is a plain cast and the weight gradient the GEMM produces IS the parameter's gradient layout - the
+//          engine keeps its convolution parameters that way, which removes the gradient re-layout below from the step
+//   grad : fp32 [O][T*I] weight gradients (sseg_conv_wgrad layout) -> fp32 OIHW, times scale (OIHW masters only)
 // Each CTA owns a 32(o) x 32(i) x T tile, staged through shared memory so that global reads AND writes are coalesced
 // in both layouts. The per-conv descriptors live in a device table built once by the caller.
 #include "common.h"
@@ -44,7 +47,35 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
   const int row = ni * T;
   __syncthreads();  // the shared tile is reused across iterations
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (mode == 0) {
+  if (mode == 0 && d->reserved == 1) {
+    // ---- channels-last master [O][T][I]: rows of 32 consecutive i (128 B) per (o, t); tile[ol][t * 32 + il]
+    const float* w = d->w;
+    for (int ol = warp; ol < no; ol += 8) {
+      const float* src = w + (long)(o0 + ol) * T * I + i0 + lane;
+#pragma unroll
+      for (int t = 0; t < kMaxT; ++t)
+        if (t < T && lane < ni) tile[ol][t * kTile + lane] = src[(long)t * I];
+    }
+    __syncthreads();
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d->wf);
+    if (wf && lane < ni) {
+      for (int ol = warp; ol < no; ol += 8) {
+        __nv_bfloat16* dst = wf + (long)(o0 + ol) * d->fwd_ld + i0 + lane;
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t)
+          if (t < T) dst[(long)t * I] = __float2bfloat16(tile[ol][t * kTile + lane]);
+      }
+    }
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d->wd);
+    if (wd && lane < no) {
+      for (int il = warp; il < ni; il += 8) {
+        __nv_bfloat16* dst = wd + (long)(i0 + il) * d->dgrad_ld + o0 + lane;
+#pragma unroll
+        for (int t = 0; t < kMaxT; ++t)
+          if (t < T) dst[(long)t * d->o_pad] = __float2bfloat16(tile[lane][t * kTile + il]);
+      }
+    }
+  } else if (mode == 0) {
     // ---- load OIHW: for a fixed o the (i, t) range is contiguous
     const float* w = d->w;
     for (int ol = warp; ol < no; ol += 8) {

@@ -110,6 +110,7 @@ _ip = POINTER(c_int)
 _SIGNATURES = {
     "sseg_conv_igemm": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), c_int, _p, POINTER(Act), _p, _p, _p],
     "sseg_conv_igemm_affine": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), _p, _p, c_int, POINTER(Act), _p],
+    "sseg_conv_igemm_bnfin": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(BnFused), _p],
     "sseg_conv_bn_train": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(BnFused), _p],
     "sseg_conv_bn_train_fits": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(BnFused)],
     "sseg_conv_dgrad_bn": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), _p, _p, _p, _p, c_float, _p, _p, _p,

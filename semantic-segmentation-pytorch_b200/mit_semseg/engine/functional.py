@@ -102,12 +102,15 @@ class _TrainStep(torch.autograd.Function):
         # scalar (no host sync); `loss.backward()` seeds exactly 1, for which the kernel exits without touching memory.
         from . import ops
         g = g_loss.detach().to(torch.float32).reshape(1).contiguous()
-        ops.scale_by_scalar(prog.pg_flat, g)
-        if prog.g_small:
-            ops.scale_by_scalar(prog.gflat[:prog.g_small], g)
+        ops.scale_by_scalar(prog.gflat, g)   # every parameter gradient is a view of this one buffer
         grads = prog.param_grads()
         # fresh views: autograd then adopts the static buffers as .grad instead of cloning 200 MB per step
-        return (None,) + tuple(grads[p].view_as(grads[p]) if p in grads else None for p in ctx.params)
+        return (None,) + tuple(_alias(grads[p]) if p in grads else None for p in ctx.params)
+
+
+def _alias(t):
+    """A new tensor object over the same memory and strides (autograd adopts it as .grad without a copy)."""
+    return t.as_strided(t.shape, t.stride())
 
 
 def _unalias_grads(prog, params):

@@ -116,6 +116,14 @@ def make_bn_fused(gamma, beta, eps, momentum, count, stat_sum, stat_sqsum, count
     return b
 
 
+def conv_igemm_bnfin(geom, w_bf16, cout, y, bn):
+    """conv -> y (bf16) with the BatchNorm statistics and their finalisation (train mode, one GPU) in the same launch: the
+    last CTA to finish writes mean / inv_std / scale / shift and the running statistics. bn: make_bn_fused(...)."""
+    n_store = (cout + 7) // 8 * 8
+    _C.check(_C.lib().sseg_conv_igemm_bnfin(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, act(y[..., :n_store]), bn, _stream()))
+    return y
+
+
 def conv_bn_train(geom, w_bf16, cout, y, a_out, bn):
     """conv + train-mode BN (+shortcut, ReLU, dropout mask) in one kernel; y may be None. bn: make_bn_fused(...)."""
     n_store = (cout + 7) // 8 * 8
@@ -223,7 +231,8 @@ def prep_conv_weight(w, w_fwd=None, w_dgrad=None, o_pad=None):
     """fp32 OIHW -> bf16 [O, T*I] and/or bf16 [I, T*o_pad] (w_dgrad must have been zero-initialised)."""
     O, I, kh, kw = w.shape
     T = kh * kw
-    assert w.is_contiguous() and w.dtype == torch.float32
+    assert w.dtype == torch.float32
+    w = w.contiguous()   # a channels-last master (engine/program.py::ConvW) is re-packed to OIHW for this single-conv entry
     if o_pad is None:
         o_pad = (O + 63) // 64 * 64
     _C.check(_C.lib().sseg_prep_conv_weight(_C.ptr(w), O, I, T, _C.ptr(w_fwd), w_fwd.stride(0) if w_fwd is not None else 0,
@@ -441,7 +450,8 @@ def bilinear_pair_fwd(x, out):
 
 def prep_conv_weight_split(w, out):
     O, I, kh, kw = w.shape
-    assert w.is_contiguous() and w.dtype == torch.float32 and out.dtype == torch.bfloat16
+    assert w.dtype == torch.float32 and out.dtype == torch.bfloat16
+    w = w.contiguous()   # (a channels-last master is re-packed to OIHW first)
     _C.check(_C.lib().sseg_prep_conv_weight_split(_C.ptr(w), O, I, kh * kw, _C.ptr(out), out.stride(0), _stream()))
 
 
@@ -532,6 +542,15 @@ class WeightTable:
             d.g_ld = e["g_src"].stride(0) if e.get("g_src") is not None else 0
             d.O, d.I, d.T, d.o_pad = e["O"], e["I"], e["T"], e["o_pad"]
             assert d.T <= 9
+            w = e.get("w")
+            if e.get("channels_last") and d.T > 1:
+                # master weight [O][kh][kw][I] in memory (torch.channels_last): the kernel reads rows of I
+                assert w is not None and w.is_contiguous(memory_format=torch.channels_last), "expected a channels-last master"
+                assert e.get("g_dst") is None, "channels-last masters need no gradient re-layout"
+                d.reserved = 1
+            else:
+                assert w is None or w.is_contiguous(), "expected an OIHW-contiguous master weight"
+                d.reserved = 0
             d.first_tile = tiles
             rep = 8 if d.T == 1 else 1  # i-tiles per CTA, must match i_tiles_per_cta() in csrc/weights.cu
             tiles += ((d.O + 31) // 32) * ((((d.I + 31) // 32) + rep - 1) // rep)

@@ -9,6 +9,10 @@ import torch
 
 from . import _C
 
+def _dense(t):
+    return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
+
+
 _CHUNK = 16384   # elements per block: 4 iterations of 4 float4 triples in flight per thread
 
 
@@ -23,11 +27,15 @@ class FusedSGD(torch.optim.Optimizer):
         for p in group["params"]:
             if p.grad is None:
                 continue
-            assert p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.grad.is_contiguous()
+            # element i of param / grad / momentum must be the same logical element: all three dense with equal strides
+            # (OIHW-contiguous, or channels-last for the engine's convolution masters and their gradient views)
+            assert p.is_cuda and p.dtype == torch.float32 and p.stride() == p.grad.stride() and _dense(p), \
+                "FusedSGD needs dense parameters whose .grad has the same memory layout"
             st = self.state[p]
             if "momentum_buffer" not in st:
-                st["momentum_buffer"] = torch.zeros_like(p)
+                st["momentum_buffer"] = torch.zeros_like(p)   # preserve_format: same strides as the parameter
             buf = st["momentum_buffer"]
+            assert buf.stride() == p.stride()
             n = p.numel()
             sig.append((p.data_ptr(), p.grad.data_ptr()))
             for off in range(0, n, _CHUNK):

@@ -80,6 +80,14 @@ class ConvW:
         self.Opad = _pad(self.O, 64)
         self.ldf = _pad(self.T * self.I, 8)   # forward operand row pitch (TMA wants 16-byte multiples)
         self.wf = self.wd = self.gw = self.gb = None  # views, assigned by SegProgram._alloc_params
+        # Every convolution the GEMM kernels run keeps its fp32 MASTER weight channels-last in memory ([O][kh][kw][I]; the
+        # logical shape, state-dict values and checkpoints are unchanged - torch.channels_last is an ordinary memory
+        # format): that is the layout the weight-gradient GEMM writes ([O][tap * I]), so `weight.grad` is a VIEW of the
+        # flat gradient buffer and the per-step gradient re-layout pass (0.2 ms of a 6.4 ms step) does not exist; the
+        # forward operand becomes a plain fp32 -> bf16 cast. (The 3-channel stem conv is read by its own kernel as OIHW.)
+        self.cl = self.I != 3
+        if self.cl and self.T > 1 and not mod.weight.data.is_contiguous(memory_format=torch.channels_last):
+            mod.weight.data = mod.weight.data.contiguous(memory_format=torch.channels_last)
 
 
 class BNS:
@@ -160,6 +168,9 @@ class SegProgram:
         # (sseg_conv_bn_train) for every layer whose tiles fit the SMs' tensor memory; single-GPU F.batch_norm branch only.
         # Opt-in until it has run on B200.
         self.coop_bn = _os.environ.get("SSEG_COOP_BN", "0") == "1"
+        # BatchNorm finalize by the last CTA of the conv launch (single-GPU train mode): SSEG_FUSE_BNFIN=0 restores the
+        # separate bn_finalize launch
+        self.fuse_bnfin = _os.environ.get("SSEG_FUSE_BNFIN", "1") == "1"
         self._branch_streams = {}
         self._open_branches = []   # branches forked since the last join (build-time bookkeeping)
 
@@ -305,24 +316,21 @@ class SegProgram:
     # ------------------------------------------------------------------------------------------ forward pieces
     def _wentry(self, c, wf=True, wd=True):
         return dict(w=c.mod.weight.detach(), wf=c.wf if wf else None, wd=c.wd if (wd and self.with_grad) else None,
-                    g_src=c.gw if self.with_grad else None, g_dst=c.pg, O=c.O, I=c.I, T=c.T, o_pad=c.Opad)
+                    g_src=None, g_dst=None, O=c.O, I=c.I, T=c.T, o_pad=c.Opad, channels_last=c.cl)
 
     def _prep_weights(self):
         """One launch re-lays out every conv weight (fp32 OIHW master -> bf16 GEMM operands)."""
         convs = [c for c in self.convs.values() if c.I != 3]  # the stem conv reads the fp32 master weight directly
-        # parameter-layout (OIHW) gradients of all convolutions live in ONE flat buffer (16-byte aligned slots), so that
-        # autograd's grad_output scaling is a single launch over it (engine/functional.py)
-        if self.with_grad:
-            sizes = [_pad(c.mod.weight.numel(), 4) for c in self.convs.values()]
-            self.pg_flat = torch.zeros(sum(sizes), device=self.dev, dtype=torch.float32)
-            off = 0
-            for c, n in zip(self.convs.values(), sizes):
-                c.pg = self.pg_flat[off:off + c.mod.weight.numel()].view_as(c.mod.weight)
-                off += n
-        else:
-            self.pg_flat = None
-            for c in self.convs.values():
+        # parameter gradients are views of the flat gradient buffer: channels-last masters have the GEMM's [O][tap * I]
+        # layout (see ConvW), the stem kernel accumulates OIHW directly
+        for c in self.convs.values():
+            if not self.with_grad:
                 c.pg = None
+            elif c.cl:
+                k = c.k
+                c.pg = c.gw.as_strided((c.O, c.I, k, k), (c.T * c.I, 1, k * c.I, c.I))
+            else:
+                c.pg = c.gw.view_as(c.mod.weight)
         self._late_convs, self._late_pending = set(), False
         if not self.overlap_relayout:
             self.wtable = ops.WeightTable([self._wentry(c) for c in convs], self.dev)
@@ -738,16 +746,9 @@ class SegProgram:
             end = self.gflat.numel()
             buckets = [(dec_ids, self.gflat[dec_off:end]), (dec_ids | l4_ids, self.gflat[l4_off:dec_off])]
             rest = self.gflat[:l4_off]
-        scale = 1.0 / self.world
+        # 1 / world_size (= the reference's mean over per-GPU losses, train.py:42) is applied ONCE, to the loss gradient
+        # (LossRec.backward): every gradient of the step then comes out already divided, the bucket all-reduces sum them
         gtables = None
-        if self.overlap_relayout and buckets:
-            # gradient re-layout tables per bucket (decoder | last encoder stage | rest), same partition as the all-reduces
-            parts = ([], [], [])
-            for c in self.convs.values():
-                if c.I == 3:
-                    continue
-                parts[0 if id(c.mod) in dec_ids else (1 if id(c.mod) in l4_ids else 2)].append(self._wentry(c))
-            gtables = [ops.WeightTable(e, self.dev) if e else None for e in parts]
         pending = list(buckets)
         nclosed = 0
         for rec in reversed(self.records):
@@ -761,8 +762,6 @@ class SegProgram:
                 def close_bucket(sl=sl, gt=gt):
                     if self.dist is not None:
                         self.dist.all_reduce(sl)
-                    if gt is not None:
-                        gt.grads(scale)
                 self.bwd.append(self.on_side(close_bucket))
             k = getattr(rec, "branch", None) if self.use_branches else None
             if isinstance(rec, AvgPoolRec):
@@ -790,29 +789,7 @@ class SegProgram:
                 self.bwd.append(lambda: self.dist.all_reduce(rest))
             else:
                 self.bwd.append(lambda: self.dist.all_reduce(self.gflat))
-        # gradients into each parameter's own layout (static buffers, so they are part of the captured graph);
-        # 1/world_size = the reference's mean over per-GPU losses (train.py:42)
-        self._pg = {}
-        if scale != 1.0:
-            self.bwd.append(lambda: self.gflat[:self.g_small].mul_(scale))
-        for c in self.convs.values():
-            if c.I == 3:
-                g = c.pg
-                self._pg[id(c)] = g
-
-                def stem_grad(g=g, c=c):
-                    g.copy_(c.gw.view_as(g))  # the stem kernel accumulates in OIHW directly
-                    if scale != 1.0:
-                        g.mul_(scale)
-                self.bwd.append(stem_grad)
-            else:
-                self._pg[id(c)] = c.pg
-        if gtables is None:
-            self.bwd.append(lambda: self.wtable.grads(scale))
-        else:
-            for gt in gtables[nclosed:]:   # buckets whose re-layout has not been issued behind their GEMMs
-                if gt is not None:
-                    self.bwd.append(lambda gt=gt: gt.grads(scale))
+        self._pg = {id(c): c.pg for c in self.convs.values()}
 
     def on_side(self, fn):
         """Closure that runs `fn` on the side stream, ordered after everything enqueued so far on the main stream."""
@@ -1010,7 +987,13 @@ class StemRec:
         P.bwd.append(P.on_side(lambda: ops.stem_conv_wgrad(P.img, dy, gw.view(64, 3, 3, 3))))
 
 
-def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, chanmul, res_after_relu=False):
+def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, chanmul, res_after_relu=False, finalized=False):
+    """finalized: the producing conv launch already wrote mean / inv_std / scale / shift (sseg_conv_igemm_bnfin)."""
+    if finalized:
+        if out is not None:
+            P.fwd.append(lambda: ops.bn_apply(y, bns.scale, bns.shift, out, relu=relu, res=res, rscale=rscale, rshift=rshift,
+                                              chanmul=chanmul, res_after_relu=res_after_relu))
+        return
     m = bns.mod
     C, Cp = bns.C, bns.Cp
     st = bns.stats
@@ -1136,8 +1119,22 @@ class ConvBNRec:
         C = cw.O
         geom, wf, y = self.geom, cw.wf, self.y
         P._need_weights(cw)
-        P.fwd.append(lambda: ops.conv_igemm(geom, wf, C, y, stat_sum=st[:C] if train else None,
-                                            stat_sqsum=st[C:2 * C] if train else None))
+        m = bns.mod
+        # single-GPU train mode: the LAST CTA of the conv launch finalises the statistics it has just completed
+        # (sseg_conv_igemm_bnfin) - one dependent launch less per layer on the step's critical path
+        self.bnfin = (P.fuse_bnfin and self.mode == ops.BN_TRAIN and bns.counter is not None and not P.fuse_finalize)
+        if self.bnfin:
+            upd = m.track_running_stats and m.running_mean is not None
+            bn = ops.make_bn_fused(m.weight.detach() if m.weight is not None else None,
+                                   m.bias.detach() if m.bias is not None else None, m.eps,
+                                   m.momentum if m.momentum is not None else 0.1, self.count, st[:C], st[C:2 * C],
+                                   bns.counter, bns.mean[:C], bns.invstd[:C], bns.scale[:C], bns.shift[:C],
+                                   running_mean=m.running_mean if upd else None, running_var=m.running_var if upd else None)
+            P.keep.append(bn)
+            P.fwd.append(lambda: ops.conv_igemm_bnfin(geom, wf, C, y, bn))
+        else:
+            P.fwd.append(lambda: ops.conv_igemm(geom, wf, C, y, stat_sum=st[:C] if train else None,
+                                                stat_sqsum=st[C:2 * C] if train else None))
         if apply:
             self.a = P._new_act(n, ho, wo, cw.O)
             self.a.producer = self
@@ -1150,10 +1147,10 @@ class ConvBNRec:
             if post_add is not None:
                 r = post_add.tp
             _emit_bn_forward(P, bns, self.mode, self.count, y, self.a.tp, relu, r, rs, rb, chanmul,
-                             res_after_relu=post_add is not None)
+                             res_after_relu=post_add is not None, finalized=self.bnfin)
         else:
             self.a = None
-            _emit_bn_forward(P, bns, self.mode, self.count, y, None, False, None, None, None, None)
+            _emit_bn_forward(P, bns, self.mode, self.count, y, None, False, None, None, None, None, finalized=self.bnfin)
 
     def _try_coop(self, n, ho, wo):
         """Training, single-GPU BN: conv + statistics + normalise (+shortcut, ReLU, dropout mask) in one launch when the
@@ -1540,5 +1537,6 @@ class LossRec:
             n, h, w, _ = head.logits.shape
             head.dlogits = P._new(n, h, w, head.cw.Opad)
             lg, dl = head.logits[..., :_pad(C, 8)], head.dlogits
+            wgt = wgt / P.world   # mean over the ranks' losses (train.py:42): every gradient below inherits the factor
             P.bwd.append(lambda lg=lg, lse=lse, acc=acc, wgt=wgt, dl=dl: ops.softmax_nll_bwd(lg, C, P.label, lse, acc,
                                                                                             wgt, dl))

@@ -182,6 +182,27 @@ class EmuLib:
         """sum over the ranks of the n floats at `off` (4-byte units) inside every rank's arena"""
         return sum(flat(peer.bases[r] + 4 * off, n, torch.float32).clone() for r in range(peer.world))
 
+    def sseg_conv_igemm_bnfin(self, g, w, w_ld, cout, out, bn, stream):
+        bn = bn.contents if hasattr(bn, "contents") else bn
+        v = _bf(_conv(g, w, w_ld, cout)).float()                      # y as stored
+        _store(out, v, cout)
+        ssum, ssq = vec(bn.stat_sum, cout), vec(bn.stat_sqsum, cout)
+        ssum.add_(v.sum((0, 1, 2)))
+        ssq.add_((v * v).sum((0, 1, 2)))
+        flat(bn.counter, 1, torch.int32).add_(1)                      # the tickets leave a non-zero counter
+        mean = ssum / bn.count
+        sumvar = ssq - ssum * mean
+        inv = torch.rsqrt((sumvar / bn.count).clamp(min=0) + bn.eps)
+        gm = vec(bn.gamma, cout) if _addr(bn.gamma) else torch.ones(cout)
+        bt = vec(bn.beta, cout) if _addr(bn.beta) else torch.zeros(cout)
+        for ptr, val in ((bn.mean_out, mean), (bn.invstd_out, inv), (bn.scale_out, gm * inv), (bn.shift_out, bt - mean * gm * inv)):
+            vec(ptr, cout).copy_(val)
+        if _addr(bn.running_mean):
+            rm, rv = vec(bn.running_mean, cout), vec(bn.running_var, cout)
+            rm.mul_(1 - bn.momentum).add_(bn.momentum * mean)
+            rv.mul_(1 - bn.momentum).add_(bn.momentum * sumvar / (bn.count - 1))
+        return 0
+
     def sseg_conv_bn_train(self, g, w, w_ld, cout, y, a_out, bn, stream):
         v = _bf(_conv(g, w, w_ld, cout)).float()                      # y as stored
         if y is not None:
@@ -288,7 +309,8 @@ class EmuLib:
 
     def sseg_prep_conv_weights_batched(self, table, n, tiles, stream):
         for d in self._descs(table, n):
-            w = flat(d.w, d.O * d.I * d.T, torch.float32).view(d.O, d.I, d.T)
+            w = flat(d.w, d.O * d.I * d.T, torch.float32)
+            w = w.view(d.O, d.T, d.I).permute(0, 2, 1) if d.reserved == 1 else w.view(d.O, d.I, d.T)   # 1: channels-last master
             if d.wf:
                 wf = flat(d.wf, (d.O - 1) * d.fwd_ld + d.T * d.I, torch.bfloat16).as_strided((d.O, d.T, d.I), (d.fwd_ld, d.I, 1))
                 wf.copy_(w.permute(0, 2, 1))

@@ -302,6 +302,31 @@ def test_batched_weight_prep_and_grad_layout():
         assert torch.equal(e["g_dst"], ref_g.contiguous())
 
 
+def test_batched_weight_prep_from_channels_last_masters():
+    """The engine keeps its convolution masters channels-last ([O][kh][kw][I] in memory): same operands out of the batched
+    prep kernel as from OIHW masters, including ragged 32-tiles (I = 48, O = 150) and a pointwise entry next to 3x3 ones."""
+    from mit_semseg.engine import ops
+    g = _gen(10)
+    specs = [(150, 512, 1), (64, 48, 9), (256, 128, 9), (96, 200, 9)]
+    entries = []
+    for O_, I_, T_ in specs:
+        k = int(T_ ** 0.5)
+        w = torch.randn(O_, I_, k, k, device=DEV, generator=g).contiguous(memory_format=torch.channels_last)
+        opad = (O_ + 63) // 64 * 64
+        entries.append(dict(w=w, wf=torch.empty(O_, T_ * I_, device=DEV, dtype=torch.bfloat16),
+                            wd=torch.zeros(I_, T_ * opad, device=DEV, dtype=torch.bfloat16), g_src=None, g_dst=None,
+                            O=O_, I=I_, T=T_, o_pad=opad, channels_last=True))
+    tab = ops.WeightTable(entries, DEV)
+    tab.prep()
+    torch.cuda.synchronize()
+    for e in entries:
+        w, O_, I_, T_, opad = e["w"], e["O"], e["I"], e["T"], e["o_pad"]
+        assert torch.equal(e["wf"], w.permute(0, 2, 3, 1).reshape(O_, -1).bfloat16())
+        ref_d = torch.zeros(I_, T_, opad, device=DEV)
+        ref_d[:, :, :O_] = w.permute(1, 2, 3, 0).reshape(I_, T_, O_)
+        assert torch.equal(e["wd"], ref_d.reshape(I_, -1).bfloat16())
+
+
 def test_fused_sgd_matches_torch_sgd():
     """One-launch multi-tensor SGD == torch.optim.SGD(momentum, weight_decay) with train.py's two parameter groups."""
     from mit_semseg.engine.optim import FusedSGD

@@ -257,3 +257,43 @@ def test_dgrad_with_fused_bn_backward_reduce(k, hw, cprod, cout_next):
     torch.cuda.synchronize()
     assert (dgam - s2b).abs().max().item() <= 2e-3 * s2b.abs().max().item() + 1e-3
     assert (dya.float() - dyb.float()).abs().max().item() <= 2 ** -6 * dya.float().abs().max().item()
+
+
+@pytest.mark.parametrize("n,hw,cin,cout,k", [(2, 32, 64, 128, 1), (2, 24, 96, 200, 3), (1, 64, 256, 512, 1)])
+def test_conv_with_bn_finalize_by_the_last_cta(n, hw, cin, cout, k):
+    """sseg_conv_igemm_bnfin = sseg_conv_igemm(stats) + sseg_bn_finalize(SSEG_BN_TRAIN): same y (bit for bit), same
+    statistics, and mean / inv_std / scale / shift / running statistics equal to the separate finalize kernel's up to the
+    summation order of the atomics (F.batch_norm training branch, lib/nn/modules/batchnorm.py:58-61)."""
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = _acts(n, hw, hw, [cin], g)
+    K = k * k * cin
+    wt = (torch.randn(cout, K, device="cuda", generator=g) * (2.0 / K) ** 0.5).bfloat16()
+    cp = (cout + 7) // 8 * 8
+    gamma, beta = 0.5 + torch.rand(cout, device="cuda", generator=g), torch.randn(cout, device="cuda", generator=g) * 0.1
+    geom = ops.make_geom(xs, ops.conv_taps(k, 1))
+    count = float(n * hw * hw)
+    # reference: two launches
+    y0 = torch.zeros(n, hw, hw, cp, device="cuda", dtype=torch.bfloat16)
+    s0, q0 = torch.zeros(cout, device="cuda"), torch.zeros(cout, device="cuda")
+    ops.conv_igemm(geom, wt, cout, y0, stat_sum=s0, stat_sqsum=q0)
+    v0 = torch.zeros(4, cout, device="cuda")
+    rm0, rv0 = torch.full((cout,), 0.25, device="cuda"), torch.full((cout,), 1.5, device="cuda")
+    ops.bn_finalize(s0, q0, count, gamma, beta, 1e-5, 0.1, ops.BN_TRAIN, v0[0], v0[1], v0[2], v0[3],
+                    running=(rm0, rv0, None, None, None), update_running=True)
+    # fused
+    y1 = torch.zeros_like(y0)
+    s1, q1 = torch.zeros(cout, device="cuda"), torch.zeros(cout, device="cuda")
+    v1 = torch.zeros(4, cout, device="cuda")
+    rm1, rv1 = torch.full((cout,), 0.25, device="cuda"), torch.full((cout,), 1.5, device="cuda")
+    counter = torch.zeros(1, device="cuda", dtype=torch.float32)
+    bn = ops.make_bn_fused(gamma, beta, 1e-5, 0.1, count, s1, q1, counter, v1[0], v1[1], v1[2], v1[3], running_mean=rm1,
+                           running_var=rv1)
+    ops.conv_igemm_bnfin(geom, wt, cout, y1, bn)
+    torch.cuda.synchronize()
+    assert torch.equal(y0, y1)
+    assert torch.allclose(s0, s1, rtol=1e-5, atol=1e-3) and torch.allclose(q0, q1, rtol=1e-5, atol=1e-3)
+    assert counter.view(torch.int32).item() > 0
+    for a, b, what in ((v0[0], v1[0], "mean"), (v0[1], v1[1], "inv_std"), (v0[2], v1[2], "scale"), (v0[3], v1[3], "shift"),
+                       (rm0, rm1, "running_mean"), (rv0, rv1, "running_var")):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), what

@@ -82,10 +82,8 @@ def main():
     os.unlink(path)
     ks = [e for e in tr["traceEvents"] if e.get("cat") == "kernel" and e.get("ph") == "X"]
     ks.sort(key=lambda e: e["ts"])
-    # the second step = the kernels after the largest gap
-    gaps = [(ks[i + 1]["ts"] - (ks[i]["ts"] + ks[i]["dur"]), i) for i in range(len(ks) - 1)]
-    cut = max(gaps)[1] + 1
-    ks = ks[cut:]
+    # two identical steps were recorded: keep the second one
+    ks = ks[len(ks) // 2:]
     t0 = ks[0]["ts"]
     end = max(e["ts"] + e["dur"] for e in ks)
     os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
