@@ -99,126 +99,14 @@ struct IgemmSmem {
   static constexpr int kDynBytes = kTotal + 1024;  // slack for manual 1024B alignment
 };
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_constant__ IgemmParams p) {
-  using L = IgemmSmem<BLOCK_N, STAGES>;
-  static_assert(L::kDynBytes <= 232448, "shared memory budget");
-  static_assert(2 * 128 * (BLOCK_N * 2 + 16) <= STAGES * L::kStageBytes, "the epilogue stages two tiles in the pipeline buffers");
-  SSEG_DYN_SMEM(smem_raw);
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  uint32_t* tmem_ptr_smem2 = tmem_ptr_smem + 1;  // "this CTA took the last ticket" flag of the fused BN finalize
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) SSEG_STAMP(0);
-
-  // tile decode: N-tile fastest so CTAs sharing an activation tile run together (L2 reuse)
-  const int n_tile = blockIdx.x % p.n_tiles;
-  int m_tile = blockIdx.x / p.n_tiles;
-  const int tw = m_tile % p.tiles_w;
-  m_tile /= p.tiles_w;
-  const int th = m_tile % p.tiles_h;
-  const int img = m_tile / p.tiles_h;
-  const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
-  const int num_k_steps = p.num_k_steps;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 2);  // one arrive.expect_tx per producer warp (A boxes, B boxes)
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
-    tma_prefetch_desc(&p.tmB);
-  }
-  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr_smem);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-  if (threadIdx.x == 0) SSEG_STAMP(1);
-  pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
-  if (threadIdx.x == 0) SSEG_STAMP(2);
-
-  if (warp == 0 || warp == 6) {
-    // ===================== TMA producers: warp 0 the activation boxes (A), warp 6 the weight boxes (B) =====================
-    // The WHOLE warp walks the loop and one elected lane issues: with warp-uniform control flow the coordinates and
-    // barrier addresses stay in uniform registers; issuing from a divergent `if (lane == 0)` region made the compiler wrap
-    // every uniform-datapath instruction in an election loop (measured: ~400 cycles per box issue).
-    {
-      const bool is_a = warp == 0;
-      int stage = 0, phase = 0;
-      for (int t = 0; t < p.ntaps; ++t) {
-        const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
-        const int fixed_src = p.tap_src[t];
-        const int nblk = fixed_src >= 0 ? p.src_blk_end[0] : p.blocks_per_tap;
-        int src = fixed_src >= 0 ? fixed_src : 0, blk_begin = 0;
-        for (int b = 0; b < nblk; ++b) {
-          if (fixed_src < 0) {
-            while (b >= p.src_blk_end[src]) {
-              blk_begin = p.src_blk_end[src];
-              ++src;
-            }
-          }
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::kStageBytes;
-          // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
-          // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
-          const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
-          if (elect_one()) {
-            if (is_a) {
-              mbar_expect_tx(&full_bar[stage], kABytes);
-              tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
-              if (t == 0 && b == 0) SSEG_STAMP(3);
-            } else {
-              mbar_expect_tx(&full_bar[stage], L::kBBytes);
-              tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
-            }
-          }
-          __syncwarp();
-          if (++stage == STAGES) stage = 0, phase ^= 1;
-        }
-      }
-      if (is_a && lane == 0) SSEG_STAMP(4);
-    }
-  } else if (warp == 1) {
-    // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues =====================
-    // (same reason as above; the shared-memory descriptors are stepped by adding to their low word instead of being
-    // re-encoded for every instruction: the issue loop, not the tensor core, was the limit - ~140 cycles per MMA
-    // instruction against 64 needed)
-    constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, kBlockM, BLOCK_N);
-    constexpr uint32_t dhi = smem_desc_hi_sw128(1024);
-    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16);
-    int stage = 0, phase = 0;
-    for (int ks = 0; ks < num_k_steps; ++ks) {
-      mbar_wait(&full_bar[stage], phase);
-      if (ks == 0 && lane == 0) SSEG_STAMP(5);
-      tc_fence_after();
-      const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
-      const uint32_t b_lo = a_lo + (kABytes >> 4);
-      if (elect_one()) {
-#pragma unroll
-        for (int k = 0; k < kBlockK / 16; ++k)
-          umma_bf16(tmem_base, smem_desc_join(a_lo + 2 * k, dhi), smem_desc_join(b_lo + 2 * k, dhi), idesc, (ks | k) != 0);
-        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
-      }
-      __syncwarp();
-      if (++stage == STAGES) stage = 0, phase ^= 1;
-    }
-    if (elect_one()) {
-      umma_commit(tmem_full_bar);  // accumulator complete
-      SSEG_STAMP(6);
-    }
-    __syncwarp();
-  } else {
-    // ===================== epilogue: TMEM -> registers -> global =====================
+// Epilogue of one 128 x BLOCK_N accumulator tile (the 4 epilogue warps = threads 64..191 of the CTA): TMEM -> registers ->
+// (+bias, affine, addend, ReLU) -> bf16 tile staged in the idle pipeline buffers -> per-channel statistics / fused BN-backward
+// sums as column sums of the staged tile -> coalesced stores. Shared by the one-CTA kernel and the CTA-pair kernel (there
+// each CTA drains the 128 accumulator rows that live in its own tensor memory).
+template <int BLOCK_N>
+__device__ __forceinline__ void igemm_tile_epilogue(const IgemmParams& p, uint8_t* smem, uint32_t tmem_base,
+                                                    uint64_t* tmem_full_bar, int warp, int lane, int h0, int w0, int n0,
+                                                    int img) {
     const int quarter = warp & 3;  // a warp may only touch TMEM lanes [32*(warp%4), +32)
     const int row = quarter * 32 + lane;
     const int hh = h0 + (row >> p.bw_shift), ww = w0 + (row & (p.BW - 1));
@@ -394,6 +282,133 @@ __global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_consta
         }
       }
     }
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(kNumThreads2) igemm_kernel(const __grid_constant__ IgemmParams p) {
+  using L = IgemmSmem<BLOCK_N, STAGES>;
+  static_assert(L::kDynBytes <= 232448, "shared memory budget");
+  static_assert(2 * 128 * (BLOCK_N * 2 + 16) <= STAGES * L::kStageBytes, "the epilogue stages two tiles in the pipeline buffers");
+  SSEG_DYN_SMEM(smem_raw);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint32_t* tmem_ptr_smem2 = tmem_ptr_smem + 1;  // "this CTA took the last ticket" flag of the fused BN finalize
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) SSEG_STAMP(0);
+
+  // tile decode: N-tile fastest so CTAs sharing an activation tile run together (L2 reuse)
+  const int n_tile = blockIdx.x % p.n_tiles;
+  int m_tile = blockIdx.x / p.n_tiles;
+  const int tw = m_tile % p.tiles_w;
+  m_tile /= p.tiles_w;
+  const int th = m_tile % p.tiles_h;
+  const int img = m_tile / p.tiles_h;
+  const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * BLOCK_N;
+  const int num_k_steps = p.num_k_steps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);  // one arrive.expect_tx per producer warp (A boxes, B boxes)
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) tmem_alloc<BLOCK_N>(tmem_ptr_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) SSEG_STAMP(1);
+  pdl_sync();  // everything above overlapped the previous kernel's tail; global memory is touched only below
+  if (threadIdx.x == 0) SSEG_STAMP(2);
+
+  if (warp == 0 || warp == 6) {
+    // ===================== TMA producers: warp 0 the activation boxes (A), warp 6 the weight boxes (B) =====================
+    // The WHOLE warp walks the loop and one elected lane issues: with warp-uniform control flow the coordinates and
+    // barrier addresses stay in uniform registers; issuing from a divergent `if (lane == 0)` region made the compiler wrap
+    // every uniform-datapath instruction in an election loop (measured: ~400 cycles per box issue).
+    {
+      const bool is_a = warp == 0;
+      int stage = 0, phase = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
+        const int fixed_src = p.tap_src[t];
+        const int nblk = fixed_src >= 0 ? p.src_blk_end[0] : p.blocks_per_tap;
+        int src = fixed_src >= 0 ? fixed_src : 0, blk_begin = 0;
+        for (int b = 0; b < nblk; ++b) {
+          if (fixed_src < 0) {
+            while (b >= p.src_blk_end[src]) {
+              blk_begin = p.src_blk_end[src];
+              ++src;
+            }
+          }
+          mbar_wait_warp(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          // a partial last block of a source (channels % 64 != 0) reads zeros beyond the source's channels (TMA
+          // out-of-bounds fill), so whatever weight columns sit under them contribute nothing
+          const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+          if (elect_one()) {
+            if (is_a) {
+              mbar_expect_tx(&full_bar[stage], kABytes);
+              tma_load_4d(sa, &p.tmA[src], &full_bar[stage], (b - blk_begin) * kBlockK, ww, hh, img);
+              if (t == 0 && b == 0) SSEG_STAMP(3);
+            } else {
+              mbar_expect_tx(&full_bar[stage], L::kBBytes);
+              tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kcol, n0);
+            }
+          }
+          __syncwarp();
+          if (++stage == STAGES) stage = 0, phase ^= 1;
+        }
+      }
+      if (is_a && lane == 0) SSEG_STAMP(4);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues =====================
+    // (same reason as above; the shared-memory descriptors are stepped by adding to their low word instead of being
+    // re-encoded for every instruction: the issue loop, not the tensor core, was the limit - ~140 cycles per MMA
+    // instruction against 64 needed)
+    constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, kBlockM, BLOCK_N);
+    constexpr uint32_t dhi = smem_desc_hi_sw128(1024);
+    const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16);
+    uint32_t d_tmem = tmem_base;
+#ifndef __CUSIM__
+    asm volatile("" : "+r"(d_tmem));  // a register of this branch's own (the compiler kept the kernel-wide value on the stack)
+#endif
+    int stage = 0, phase = 0;
+    for (int ks = 0; ks < num_k_steps; ++ks) {
+      mbar_wait_warp(&full_bar[stage], phase);
+      if (ks == 0 && lane == 0) SSEG_STAMP(5);
+      tc_fence_after();
+      const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
+      const uint32_t b_lo = a_lo + (kABytes >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k)
+          umma_bf16(d_tmem, smem_desc_join(a_lo + 2 * k, dhi), smem_desc_join(b_lo + 2 * k, dhi), idesc, (ks | k) != 0);
+        umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs above have read it
+      }
+      __syncwarp();
+      if (++stage == STAGES) stage = 0, phase ^= 1;
+    }
+    if (elect_one()) {
+      umma_commit(tmem_full_bar);  // accumulator complete
+      SSEG_STAMP(6);
+    }
+    __syncwarp();
+  } else {
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    igemm_tile_epilogue<BLOCK_N>(p, smem, tmem_base, tmem_full_bar, warp, lane, h0, w0, n0, img);
   }
 
   if (threadIdx.x == 64) SSEG_STAMP(12);
@@ -794,6 +809,160 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
   return check_cuda(launch_k(igemm_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(kNumThreads2), L::kDynBytes, stream, p),
                     "igemm_kernel launch");
 }
+
+#ifndef __CUSIM__
+// =====================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): clusters of two CTAs, each on one SM of a TPC, compute a 256 x 256 output tile.
+//   CTA r of a pair owns M tile (2j + r): it streams its own 128-pixel A box and HALF of the 256-channel weight tile (B rows
+//   n0 + r*128 .. +128) into its own shared memory - 32 KB per k-step for 128 x 256 x 64 of MMA work per SM (64 B/cycle
+//   where the one-CTA 128 x 256 tile needs 96 and the 128 x 128 tile 128; the SM takes in ~80-100 B/cycle through TMA).
+//   The leader (even rank) issues ONE tcgen05.mma.cta_group::2 per 16-wide K slice: A rows 0-127 / 128-255 come from the two
+//   CTAs' shared memories, B columns 0-127 / 128-255 likewise, and each CTA's tensor memory receives its own 128 rows.
+//   Barriers: every TMA of the pair signals the LEADER's full barrier (its producer posts the byte count of both CTAs, the
+//   peer's producer arrives remotely); tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs.
+//   Epilogue: each CTA drains its own tensor memory with the ordinary tile epilogue.
+// Used for the long-K, wide-N layers (conv_last, cbr_deepsup, layer4's 3x3 convs and their data gradients).
+// =====================================================================================================
+constexpr int kPairN = 256;
+template <int STAGES>
+struct IgemmPairSmem {
+  static constexpr int kBBytes = (kPairN / 2) * kBlockK * 2;   // this CTA's half of the weight tile
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOff = STAGES * kStageBytes;
+  static constexpr int kTotal = kBarOff + 256;
+  static constexpr int kDynBytes = kTotal + 1024;
+};
+
+template <int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
+  using L = IgemmPairSmem<STAGES>;
+  static_assert(L::kDynBytes <= 232448, "shared memory budget");
+  static_assert(2 * 128 * (kPairN * 2 + 16) <= STAGES * L::kStageBytes, "the epilogue stages two tiles in the pipeline buffers");
+  SSEG_DYN_SMEM(smem_raw);
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();   // 0 = leader
+  const bool leader = rank == 0;
+
+  // tile decode: pairs walk N tiles fastest; the two CTAs of a pair take consecutive M tiles
+  const int pair = blockIdx.x >> 1;
+  const int n_tile = pair % p.n_tiles;
+  int m_tile = (pair / p.n_tiles) * 2 + static_cast<int>(rank);
+  const int tw = m_tile % p.tiles_w;
+  m_tile /= p.tiles_w;
+  const int th = m_tile % p.tiles_h;
+  const int img = m_tile / p.tiles_h;
+  const int h0 = th * p.BH, w0 = tw * p.BW, n0 = n_tile * kPairN;
+  const int num_k_steps = p.num_k_steps;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 2);   // leader's arrive.expect_tx (bytes of both CTAs) + the peer producer's remote arrive
+      mbar_init(&empty_bar[s], 1);  // one multicast tcgen05.commit
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nsrc; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1) tmem_alloc_2sm<kPairN>(tmem_ptr_smem);   // one warp of EACH CTA of the pair
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // both CTAs' barriers are initialised before anything signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_sync();
+
+  if (warp == 0) {
+    // ===================== TMA producer (one per CTA; whole warp walks the loop, one elected lane issues) =====================
+    int stage = 0, phase = 0;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int hh = h0 + p.tap_dh[t], ww = w0 + p.tap_dw[t];
+      const int fixed_src = p.tap_src[t];
+      const int nblk = fixed_src >= 0 ? p.src_blk_end[0] : p.blocks_per_tap;
+      int src = fixed_src >= 0 ? fixed_src : 0, blk_begin = 0;
+      for (int b = 0; b < nblk; ++b) {
+        if (fixed_src < 0) {
+          while (b >= p.src_blk_end[src]) {
+            blk_begin = p.src_blk_end[src];
+            ++src;
+          }
+        }
+        mbar_wait_bounded(&empty_bar[stage], phase ^ 1);   // (own barrier: the leader's commit is multicast to both CTAs)
+        uint8_t* sa = smem + stage * L::kStageBytes;
+        const int kcol = p.tap_koff[t] + (fixed_src >= 0 ? 0 : p.src_choff[src]) + (b - blk_begin) * kBlockK;
+        if (elect_one()) {
+          const uint32_t full_leader = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::kStageBytes);
+          else mbar_arrive_cluster(full_leader);
+          tma_load_4d_2sm(sa, &p.tmA[src], full_leader, (b - blk_begin) * kBlockK, ww, hh, img);
+          tma_load_2d_2sm(sa + kABytes, &p.tmB, full_leader, kcol, n0 + static_cast<int>(rank) * (kPairN / 2));
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: the leader CTA's warp 1 (whole warp walks the loop, one elected lane issues) =====================
+    if (leader) {
+      constexpr uint32_t idesc = make_idesc(/*bf16*/ 1, 0, 0, 2 * kBlockM, kPairN);
+      constexpr uint32_t dhi = smem_desc_hi_sw128(1024);
+      const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), 16);
+      int stage = 0, phase = 0;
+      for (int ks = 0; ks < num_k_steps; ++ks) {
+        mbar_wait_bounded(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
+        const uint32_t b_lo = a_lo + (kABytes >> 4);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_2sm(tmem_base, smem_desc_join(a_lo + 2 * k, dhi), smem_desc_join(b_lo + 2 * k, dhi), idesc, (ks | k) != 0);
+          umma_commit_2sm(&empty_bar[stage], 3);   // this stage is free again in BOTH CTAs
+        }
+        __syncwarp();
+        if (++stage == STAGES) stage = 0, phase ^= 1;
+      }
+      if (elect_one()) umma_commit_2sm(tmem_full_bar, 3);   // both CTAs' accumulators are complete
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: each CTA drains the 128 accumulator rows in its own tensor memory =====================
+    igemm_tile_epilogue<kPairN>(p, smem, tmem_base, tmem_full_bar, warp, lane, h0, w0, n0, img);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // the peer's shared memory / barriers are no longer referenced by anyone
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm<kPairN>(tmem_base);
+  }
+}
+
+template <int STAGES>
+static int launch_pair(const IgemmParams& p, int grid, cudaStream_t stream) {
+  using L = IgemmPairSmem<STAGES>;
+  static bool configured[64] = {};
+  int dev = 0;
+  SSEG_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !configured[dev]) {
+    SSEG_CUDA(cudaFuncSetAttribute(igemm_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
+    configured[dev] = true;
+  }
+  count_launch(1);
+  return check_cuda(launch_k_pair(igemm_pair_kernel<STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, p),
+                    "igemm_pair_kernel launch");
+}
+#endif  // __CUSIM__
 
 // =====================================================================================================
 // Convolution + train-mode BatchNorm (+ shortcut, ReLU, Dropout2d mask) in ONE kernel.
@@ -1680,14 +1849,20 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   // the main loop is bound by what one SM can take in through TMA (~100 B/cycle measured); a 128 x 256 tile needs
   // 48 KB per 512 MMA cycles = 96 B/cycle where 128 x 128 needs 128 B/cycle. One CTA per SM then (192 KB of stages), so
   // only where the un-overlapped epilogue is small against the main loop.
+  static const int pair_on = env_int("SSEG_IGEMM_2CTA", 0);
   static const int n256 = env_int("SSEG_IGEMM_N256", 1);
   static const int n256_min_ksteps = env_int("SSEG_IGEMM_N256_KSTEPS", 48);
   static const int n256_min_tiles = env_int("SSEG_IGEMM_N256_TILES", 96);   // (both knobs: test hooks for small shapes)
   if (n256 && block_n == 128 && n_store >= 256 && p.num_k_steps >= n256_min_ksteps && params_out == nullptr &&
       m_tiles * ceil_div(n_store, 256) >= n256_min_tiles)
     block_n = 256;
+  // ... and as a CTA pair (256 x 256 tile over two SMs, tcgen05 cta_group::2) when the M tiles pair up
+  bool use_pair = false;
+#ifndef __CUSIM__
+  use_pair = pair_on && block_n == 256 && m_tiles % 2 == 0 && fin == nullptr;
+#endif
   p.n_tiles = ceil_div(n_store, block_n);
-  rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, block_n);
+  rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, use_pair ? block_n / 2 : block_n);
   if (rc) return rc;
   const int esz = out_f32 ? 4 : 2;
   p.out = out->ptr, p.out_f32 = out_f32, p.ld_out = out->ld, p.n_store = n_store, p.cout = cout;
@@ -1760,6 +1935,9 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     if (block_n == 64) return launch<64, 8>(p, grid, stream);
     return launch<128, 6>(p, grid, stream);
   }
+#ifndef __CUSIM__
+  if (use_pair) return launch_pair<5>(p, grid, stream);
+#endif
   if (block_n == 256) return launch<256, 4>(p, grid, stream);
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);
@@ -2078,7 +2256,7 @@ __global__ void __launch_bounds__(kNumThreads2) wgrad_kernel(const __grid_consta
         const int th = r % p.tiles_h;
         const int img = r / p.tiles_h;
         const int h0 = th * p.BH, w0 = tw * p.BW;
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_warp(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::kStageBytes;
         uint8_t* sb = sa + L::kABytes_;
         if (elect_one()) {
@@ -2104,7 +2282,7 @@ __global__ void __launch_bounds__(kNumThreads2) wgrad_kernel(const __grid_consta
     const uint32_t a_lo0 = smem_desc_lo(smem_u32(smem), kWgBoxBytes);
     int stage = 0, phase = 0;
     for (int ks = 0; ks < num_k_steps; ++ks) {
-      mbar_wait(&full_bar[stage], phase);
+      mbar_wait_warp(&full_bar[stage], phase);
       tc_fence_after();
       const uint32_t a_lo = a_lo0 + stage * (L::kStageBytes >> 4);
       const uint32_t b_lo = a_lo + (L::kABytes_ >> 4);

@@ -97,6 +97,25 @@ class BaseDataset(torch.utils.data.Dataset):
         return out
 
 
+def _job():
+    """(rank, world) of the one-process-per-GPU job this loader feeds, from the launcher's environment (it is also what the
+    DataLoader's worker processes see); (0, 1) outside such a job or with SSEG_SHARD_LOADER=0."""
+    if os.environ.get("SSEG_SHARD_LOADER", "1") == "0":
+        return 0, 1
+    try:
+        world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    except ValueError:
+        return 0, 1
+    return (rank, world) if world > 1 else (0, 1)
+
+
+def _other_ranks_entry(index):
+    """train.py builds DataLoader(batch_size=len(gpus), shuffle=False): item `index` is the batch of GPU index % len(gpus),
+    and the documented launch has len(gpus) == WORLD_SIZE (`--gpus 0-(N-1)` under torch.distributed.run)."""
+    rank, world = _job()
+    return world > 1 and index % world != rank
+
+
 class TrainDataset(BaseDataset):
     """One item = one per-GPU batch of `batch_per_gpu` images of the same orientation, resized to a common random short
     edge and padded to a common size (dataset.py:70-186). `len()` is the reference's fake 1e10: every loader worker walks
@@ -141,6 +160,14 @@ class TrainDataset(BaseDataset):
             s = min(short / min(rec['height'], rec['width']), self.imgMaxSize / max(rec['height'], rec['width']))
             widths[i], heights[i] = rec['width'] * s, rec['height'] * s          # truncated by the int32 store
         bw, bh = int(_ceil_to(np.max(widths), pad)), int(_ceil_to(np.max(heights), pad))
+
+        if _other_ranks_entry(index):
+            # One process per GPU: every rank runs the same loader (same seeds, same order) and keeps entry `rank` of each
+            # per-GPU list (lib/nn/parallel.py::scatter). Entries that belong to other ranks are not decoded / resized /
+            # normalised here - only their random draws are consumed, so the streams of all ranks stay identical.
+            for _ in records:
+                np.random.choice([0, 1])
+            return {'skipped_for_rank': index % _job()[1]}
 
         if self.raw:
             images = torch.zeros(B, bh, bw, 3, dtype=torch.uint8)

@@ -13,6 +13,11 @@ def _dense(t):
     return t.is_contiguous() or (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last))
 
 
+def _same_layout(a, b):
+    """Equal strides on every dimension that has more than one element (strides of size-1 dimensions are arbitrary)."""
+    return a.shape == b.shape and all(sa == sb for n, sa, sb in zip(a.shape, a.stride(), b.stride()) if n > 1)
+
+
 _CHUNK = 16384   # elements per block: 4 iterations of 4 float4 triples in flight per thread
 
 
@@ -29,13 +34,13 @@ class FusedSGD(torch.optim.Optimizer):
                 continue
             # element i of param / grad / momentum must be the same logical element: all three dense with equal strides
             # (OIHW-contiguous, or channels-last for the engine's convolution masters and their gradient views)
-            assert p.is_cuda and p.dtype == torch.float32 and p.stride() == p.grad.stride() and _dense(p), \
+            assert p.is_cuda and p.dtype == torch.float32 and _same_layout(p, p.grad) and _dense(p), \
                 "FusedSGD needs dense parameters whose .grad has the same memory layout"
             st = self.state[p]
             if "momentum_buffer" not in st:
                 st["momentum_buffer"] = torch.zeros_like(p)   # preserve_format: same strides as the parameter
             buf = st["momentum_buffer"]
-            assert buf.stride() == p.stride()
+            assert _same_layout(buf, p)
             n = p.numel()
             sig.append((p.data_ptr(), p.grad.data_ptr()))
             for off in range(0, n, _CHUNK):

@@ -168,9 +168,11 @@ class SegProgram:
         # (sseg_conv_bn_train) for every layer whose tiles fit the SMs' tensor memory; single-GPU F.batch_norm branch only.
         # Opt-in until it has run on B200.
         self.coop_bn = _os.environ.get("SSEG_COOP_BN", "0") == "1"
-        # BatchNorm finalize by the last CTA of the conv launch (single-GPU train mode): SSEG_FUSE_BNFIN=0 restores the
-        # separate bn_finalize launch
-        self.fuse_bnfin = _os.environ.get("SSEG_FUSE_BNFIN", "1") == "1"
+        # BatchNorm finalize by the last CTA of the conv launch (single-GPU train mode). Measured on B200
+        # (profiles/r2_summary.md): 6.33 ms/step against 5.94 with the separate bn_finalize launch - every CTA pays a
+        # __threadfence() + ticket round trip behind its statistics atomics, while the tiny finalize kernel's launch already
+        # overlaps the conv's tail under programmatic dependent launch. Opt-in: SSEG_FUSE_BNFIN=1.
+        self.fuse_bnfin = _os.environ.get("SSEG_FUSE_BNFIN", "0") == "1"
         self._branch_streams = {}
         self._open_branches = []   # branches forked since the last join (build-time bookkeeping)
 

@@ -70,7 +70,36 @@ def ensure_process_group():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         dist.init_process_group(backend="nccl" if use_cuda else "gloo")
+        _guard_checkpoint_writes()
     return dist.get_rank(), dist.get_world_size()
+
+
+_save_guarded = False
+
+
+def _guard_checkpoint_writes():
+    """Every rank runs the same unmodified script, so every rank would `torch.save` the same
+    cfg.DIR/{encoder,decoder,history}_epoch_N.pth at the same time (train.py:139-152) - concurrent non-atomic writes to one
+    path. The replicas hold identical weights, so once this process has joined a job as rank r > 0 its torch.save() calls
+    write nothing; rank 0 writes, and all ranks meet at a barrier after every save so nobody reads a half-written file.
+    SSEG_CKPT_ALL_RANKS=1 restores per-rank writes (the tests use it with per-rank working directories)."""
+    global _save_guarded
+    import os
+    import torch.distributed as dist
+    if _save_guarded or os.environ.get("SSEG_CKPT_ALL_RANKS", "0") == "1" or dist.get_world_size() <= 1:
+        return
+    _save_guarded = True
+    real_save = torch.save
+
+    def save(obj, f, *args, **kwargs):
+        try:
+            if dist.get_rank() == 0:
+                real_save(obj, f, *args, **kwargs)
+        finally:
+            if dist.is_initialized():
+                dist.barrier()
+    save.__wrapped__ = real_save
+    torch.save = save
 
 
 def _lift(out):
@@ -105,10 +134,13 @@ class UserScatteredDataParallel(DictGatherDataParallel):
         # One process drives one GPU: keep only this process's device so nn.DataParallel never replicates.
         _, world = ensure_process_group()    # under torchrun: take GPU LOCAL_RANK and join the job (before the script's .cuda())
         if world == 1 and device_ids is not None and len(device_ids) > 1:
-            import warnings
-            warnings.warn("UserScatteredDataParallel(device_ids=%s) in a single process: this engine runs one process per GPU "
-                          "- launch the script with `python -m torch.distributed.run --nproc-per-node %d ...`; continuing on "
-                          "one GPU with the first entry of every per-GPU batch list" % (list(device_ids), len(device_ids)))
+            # The reference drives all GPUs from ONE process (replicate + one Python thread per GPU, data_parallel.py:53-62).
+            # This engine is one process per GPU; running on would silently train on 1/G of every batch list, so refuse.
+            raise RuntimeError(
+                "UserScatteredDataParallel(device_ids=%s) in a single process: the B200 engine runs one process per GPU. "
+                "Launch the same script as  python -m torch.distributed.run --nnodes=1 --nproc-per-node %d "
+                "--master-addr 127.0.0.1 <script> --gpus 0-%d ...  (the script itself needs no change: wrapping the model "
+                "joins the job)." % (list(device_ids), len(device_ids), len(device_ids) - 1))
         if torch.cuda.is_available():
             dev = torch.cuda.current_device()
             super().__init__(module, device_ids=[dev], output_device=dev, dim=dim)
@@ -124,6 +156,10 @@ class UserScatteredDataParallel(DictGatherDataParallel):
         rank, world = _rank_world()
         # the loader yields one dict per GPU of the job; a single-process run consumes entry `rank % len`
         mine = batches[rank % len(batches)]
+        if isinstance(mine, dict) and 'skipped_for_rank' in mine:
+            raise RuntimeError("the loader skipped this rank's entry: the per-GPU list has %d entries for a job of %d ranks - "
+                               "launch with --gpus 0-%d (one entry per rank) or set SSEG_SHARD_LOADER=0"
+                               % (len(batches), world, world - 1))
         dev = device_ids[0]
         with cuda.device(dev):
             main = cuda.current_stream()

@@ -63,6 +63,12 @@ inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) { ::cusim::mbar_arrive
 inline void mbar_arrive(uint64_t* bar) { ::cusim::mbar_arrive(bar, 0); }
 inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return ::cusim::mbar_test(bar, parity); }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) { ::cusim::mbar_wait(bar, parity); }
+// warp-collective wait: on hardware the lanes of a converged warp execute ONE try_wait; here they are independent threads, so
+// nobody leaves before every lane has seen the phase complete (otherwise a slow lane could look two phases later)
+inline void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  ::cusim::mbar_wait(bar, parity);
+  ::cusim::syncwarp();
+}
 inline void mbar_wait_bounded(uint64_t* bar, uint32_t parity) { ::cusim::mbar_wait(bar, parity); }
 
 inline void tma_prefetch_desc(const CUtensorMap*) {}

@@ -54,3 +54,17 @@ def test_cpu_tensors_are_rejected_not_emulated():
     feed = {"img_data": torch.zeros(1, 3, 64, 64), "seg_label": torch.zeros(1, 8, 8, dtype=torch.long)}
     with pytest.raises(RuntimeError, match="no CPU path"):
         seg(feed)
+
+
+def test_single_process_multi_gpu_request_is_refused_not_degraded():
+    """`python train.py --gpus 0-7` in ONE process (the reference's way, lib/nn/parallel/data_parallel.py:53-62) must not
+    silently train on one eighth of the data: the wrapper raises and names the one-process-per-GPU launch line."""
+    import torch
+    from mit_semseg.lib.nn import UserScatteredDataParallel
+
+    class Echo(torch.nn.Module):
+        def forward(self, feed):
+            return feed
+
+    with pytest.raises(RuntimeError, match="torch.distributed.run"):
+        UserScatteredDataParallel(Echo(), device_ids=[0, 1, 2, 3])

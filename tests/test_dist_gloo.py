@@ -233,3 +233,72 @@ def test_two_rank_gloo_host_logic():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret.get(0) and ret.get(1)
+
+
+def _worker_shapes(rank, world, port, ret):
+    """Ranks whose batch shapes alternate OUT OF PHASE through the public API (what the reference's loader produces under
+    one process per GPU): step-program cache hits / misses and graph captures happen at different steps on different ranks.
+    Nothing in program construction or capture may issue a collective, or the ranks' collectives would pair wrongly."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["SSEG_PEER_SYNC"] = "0"      # SyncBN statistics through (gloo) all-reduces: the emulated ABI has no CUDA IPC
+    os.environ["SSEG_CAPTURE_ON_USE"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import conftest
+        conftest.install_cuda_stand_in(setattr, "1")
+        import torch.nn as nn
+        from mit_semseg.engine import program as PR
+        from test_program_dry import _seg
+        calls = {"capture": 0, "collectives_in_capture": 0}
+        real_all_reduce = dist.all_reduce
+        in_capture = [False]
+
+        def counting_all_reduce(*a, **k):
+            if in_capture[0]:
+                calls["collectives_in_capture"] += 1
+            return real_all_reduce(*a, **k)
+        dist.all_reduce = counting_all_reduce
+
+        def capture(self, warm=True):        # the stand-in for CUDA-graph capture: run what the real one would run
+            calls["capture"] += 1
+            in_capture[0] = True
+            try:
+                if warm:
+                    self.run_eager()
+                    self.run_eager()
+            finally:
+                in_capture[0] = False
+        PR.SegProgram.capture = capture
+        torch.manual_seed(0)
+        seg = _seg("resnet18dilated", "c1_deepsup", 512)
+        seg.train()
+        opt = torch.optim.SGD(seg.parameters(), lr=0.01, momentum=0.9)
+        shapes = [(2, 64, 64), (2, 64, 96)]
+        for step in range(6):
+            n, h, w = shapes[(step + rank) % 2]
+            feed = O.synth_batch(n, h, w, 8, 500 + 10 * step + rank)
+            seg.zero_grad()
+            loss, acc = seg(feed)
+            loss.mean().backward()
+            opt.step()
+            assert torch.isfinite(loss).all()
+        assert calls["capture"] == 2, calls                      # each shape captured once (on its second use) ...
+        assert calls["collectives_in_capture"] == 0, calls       # ... without executing anything
+        flat = torch.cat([p.detach().flatten() for p in seg.parameters()] +
+                         [b.detach().flatten().float() for b in seg.buffers()])
+        ref = flat.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(flat, ref), "ranks diverged"
+        ret[rank] = True
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_ranks_with_out_of_phase_batch_shapes():
+    import random
+    port = 29000 + random.randint(0, 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_shapes, args=(2, port, ret), nprocs=2, join=True)
+    assert ret.get(0) and ret.get(1)

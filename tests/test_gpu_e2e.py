@@ -133,8 +133,14 @@ def test_train_mode_bn_forward_and_loss_r50_ppm_deepsup():
     assert abs(m["loss"] - m["loss_ref"]) <= 3e-3 * abs(m["loss_ref"])
     assert abs(m["acc"] - m["acc_ref"]) <= 1e-2
     assert m["logp_rel"] <= 3e-2 and max(m["feat_rel"]) <= 8e-2
-    # gradients: ill-conditioned through the PPM's tiny-batch BN (see module docstring) - direction must still agree
+    # gradients on this fixture are dominated by the engine's own run-to-run noise (2-sample BatchNorm in the 1x1-pooled
+    # pyramid branch amplifies atomics-order differences to ~28 % of the gradient, tools/grad_parity.py --repeat 3): the
+    # conditioned fixture below is where they are checked; here only the direction
     assert m["grad_cos"] >= 0.5, m["grad_cos"]
+    # same network, conditioned fixture (4 images -> 4 samples per channel in the 1x1-pooled branch, BN biases +2)
+    m = _step_metrics("resnet50dilated", "ppm_deepsup", 2048, 4, 128, bias_shift=2.0)
+    assert abs(m["loss"] - m["loss_ref"]) <= 3e-3 * abs(m["loss_ref"])
+    assert m["grad_cos"] >= 0.98, m["grad_cos"]
 
 
 def test_train_mode_bn_gradients_r18_c1_deepsup():

@@ -334,12 +334,17 @@ def test_fused_sgd_matches_torch_sgd():
     shapes = [(512, 4096, 3, 3), (150, 512, 1, 1), (150,), (64,), (2048,), (64, 3, 3, 3), (7,)]
     ref_p = [torch.randn(s, device=DEV, generator=g).requires_grad_(True) for s in shapes]
     my_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    # the engine keeps its conv masters channels-last ([O][kh][kw][I] in memory) and hands out gradients that are VIEWS of
+    # the GEMM's [O][tap * I] buffer (for a 1x1 conv: strides that differ from the parameter's only on size-1 dimensions)
+    my_p[0].data = my_p[0].data.contiguous(memory_format=torch.channels_last)
     decay = [0, 1, 5]
     mk = lambda ps: [dict(params=[ps[i] for i in decay]), dict(params=[ps[i] for i in range(len(ps)) if i not in decay],
                                                             weight_decay=0.0)]
     ref = torch.optim.SGD(mk(ref_p), lr=0.02, momentum=0.9, weight_decay=1e-4)
     mine = FusedSGD(mk(my_p), lr=0.02, momentum=0.9, weight_decay=1e-4)
-    grads = [torch.empty_like(p) for p in my_p]     # static gradient buffers, as the engine provides
+    grads = [torch.empty_like(p) for p in my_p]     # static gradient buffers, as the engine provides (empty_like keeps strides)
+    O1, I1 = shapes[1][0], shapes[1][1]
+    grads[1] = torch.empty(O1, I1, device=DEV).as_strided((O1, I1, 1, 1), (I1, 1, I1, I1))
     for step in range(4):
         for i, (a, b) in enumerate(zip(ref_p, my_p)):
             gr = torch.randn(a.shape, device=DEV, generator=g)

@@ -72,19 +72,23 @@ def test_config1_full_size_inference_matches_the_fp32_reference(monkeypatch):
     assert n_mism <= 1e-4 * mism.numel()
 
 
-def _train_metrics(enc_arch, dec_arch, fc, n, hw, emulate):
+def test_train_mode_gradients_tight_bounds_on_well_conditioned_fixtures():
+    """Train-mode BatchNorm everywhere, whole step against the oracle with the engine's storage rounding. The fixtures are
+    conditioned so that a comparison is meaningful at all: BN biases +2 (ReLU masks do not flip under rounding-level
+    perturbations), residual_gain 0.25, and >= 8 samples per channel in every BatchNorm. On the plain random-init fixture
+    the engine's own gradient differs by 16 % (C1) .. 28 % (PPM, 2-sample BatchNorm) between two runs on identical inputs
+    (atomics order -> bf16 rounding flips -> chaotic amplification; tools/grad_parity.py --repeat 3,
+    profiles/r2_summary.md), which is what the 1.10 norm ratio of round 1 was. Bounds: global cosine >= 0.995 (measured
+    0.9998 / 0.9996); per-parameter median error <= 5 % with the C1 decoder (measured 3.7 %) and <= 12 % with the pyramid
+    decoder (measured 8.9 %: half of its parameters are BatchNorm scales / shifts whose gradients are sums of a few hundred
+    bf16-rounded terms; the weight tensors, which carry the gradient's norm, agree to the cosine above)."""
     from test_gpu_e2e import _step_metrics
-    return _step_metrics(enc_arch, dec_arch, fc, n, hw, gain=0.25, emulate=emulate, bn_eval=False, seed=7)
-
-
-def test_train_mode_gradients_tight_bounds_on_a_well_conditioned_fixture():
-    """Train-mode BatchNorm, every BatchNorm sees >= 512 samples per channel (C1_deepsup decoder: no 1x1 / 2x2 pooled
-    pyramid branches whose 2..72-sample statistics make the gradient chaotic), residual_gain 0.25. Against the oracle with
-    the engine's storage rounding: global cosine >= 0.99, norm ratio within 3 %, per-parameter median <= 5 %."""
-    m = _train_metrics("resnet18dilated", "c1_deepsup", 512, 2, 128, "bf16")
-    assert abs(m["loss"] - m["loss_ref"]) <= 2e-3 * abs(m["loss_ref"])
-    assert m["grad_cos"] >= 0.99
-    assert m["grad_rel_median"] <= 5e-2
+    for dec, n, hw, med in (("c1_deepsup", 2, 128, 5e-2), ("ppm_deepsup", 8, 96, 12e-2)):
+        m = _step_metrics("resnet18dilated", dec, 512, n, hw, gain=0.25, emulate="bf16", bn_eval=False, seed=7,
+                          bias_shift=2.0)
+        assert abs(m["loss"] - m["loss_ref"]) <= 2e-3 * abs(m["loss_ref"]), dec
+        assert m["grad_cos"] >= 0.995, (dec, m["grad_cos"])
+        assert m["grad_rel_median"] <= med, (dec, m["grad_rel_median"])
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")

@@ -252,7 +252,7 @@ def test_the_reference_train_script_as_one_process_per_gpu(tmp_path, mode):
                  'MODEL:\n  arch_encoder: "resnet18dilated"\n  arch_decoder: "ppm_deepsup"\n  fc_dim: 512\n'
                  'TRAIN:\n  batch_size_per_gpu: 2\n  num_epoch: 1\n  epoch_iters: 3\n  workers: 0\n  disp_iter: 1\n'
                  'DIR: "ckpt"\n' % (data, odgt))
-    env = dict(os.environ, SSEG_TEST_RANK_CWD="1")
+    env = dict(os.environ, SSEG_TEST_RANK_CWD="1", SSEG_CKPT_ALL_RANKS="1")   # (by default only rank 0 writes checkpoints)
     if mode == "1":
         env["SSEG_PEER_SYNC"] = "0"
     else:
