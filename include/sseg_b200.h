@@ -219,6 +219,14 @@ int sseg_conv_igemm_affine(const sseg_conv_geom_t* g, const void* w_bf16, long w
 int sseg_conv_igemm_bnbwd(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
                           const sseg_act_t* addend, const sseg_act_t* y, const float* fscale, const float* fshift,
                           float* s1, float* s2_raw, sseg_stream_t stream);
+/* The same for a producer WITH a shortcut (Bottleneck / BasicBlock output a = relu(bn(y) + shortcut), models/resnet.py:37-53,
+ * 72-92): the ReLU mask is not a function of y alone, so it is taken from the producer's saved output,
+ *     g' = out * [a > 0],   s1[c] += sum g',   s2_raw[c] += sum g' * y.
+ * `out` must be the COMPLETE gradient of a: this is the launch that adds the last contribution (addend = the gradient
+ * accumulated so far). Replaces sseg_bn_bwd_reduce for the block outputs of the residual stages. */
+int sseg_conv_igemm_bnbwd_res(const sseg_conv_geom_t* geom, const void* w_bf16, long w_ld, int cout, const sseg_act_t* out,
+                              const sseg_act_t* addend, const sseg_act_t* y, const sseg_act_t* a, float* s1, float* s2_raw,
+                              sseg_stream_t stream);
 
 /*
  * Weight gradient of the same convolution (autograd of nn.Conv2d w.r.t. weight):

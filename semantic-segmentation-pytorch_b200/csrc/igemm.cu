@@ -79,6 +79,11 @@ struct IgemmParams {
   const float* bw_fshift;
   float* bw_s1;
   float* bw_s2;
+  // ... or, for a producer with a shortcut (a = relu(bn(y) + shortcut): the mask is not a function of y alone), the ReLU
+  // mask comes from the producer's saved OUTPUT a (same geometry as y): g' = out * [a > 0]   (bw_fscale / bw_fshift unused)
+  const __nv_bfloat16* bw_a;
+  int bw_a_ld;
+  long bw_a_row_stride, bw_a_img_stride;
   // BatchNorm finalize by the LAST CTA of the launch (train-mode, single GPU; sseg_conv_igemm_bnfin): once every CTA has
   // added its tile's statistics, the CTA that takes the last ticket turns (sum, sum of squares) into mean / inv_std /
   // scale / shift and updates the running statistics - the separate bn_finalize launch of every layer disappears
@@ -215,11 +220,11 @@ __device__ __forceinline__ void igemm_tile_epilogue(const IgemmParams& p, uint8_
       }
       if (threadIdx.x == 64) SSEG_STAMP(10);
       if (p.bw_s1 != nullptr) {
-        // BN-backward partial sums of the producer layer. Its saved conv output y (same tile geometry) is first copied
-        // into shared memory with fully coalesced 16-byte loads (all loads of a thread in flight together), then the
+        // BN-backward partial sums of the producer layer. A tile of its saved tensors (same geometry as this output tile) is
+        // copied into shared memory with fully coalesced 16-byte loads (batches of loads in flight per thread), then the
         // per-channel sums run from shared memory next to the staged gradient tile.
         uint8_t* ytile = stg + 128 * kPitch;
-        {
+        auto copy_tile = [&](const __nv_bfloat16* src, int ld, long row_stride, long img_stride) {
           constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow, kPasses = 128 / kRowsPerPass;
           constexpr int kBatch = kPasses < 16 ? kPasses : 16;   // loads in flight per thread (registers: 4 per load)
           const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
@@ -232,36 +237,79 @@ __device__ __forceinline__ void igemm_tile_epilogue(const IgemmParams& p, uint8_
               const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
               q[j] = make_uint4(0u, 0u, 0u, 0u);
               if (rh < p.H && rw < p.W && n0 + seg * 8 < p.cout)
-                q[j] = __ldg(reinterpret_cast<const uint4*>(p.bw_y + img * p.bw_img_stride + rh * p.bw_row_stride +
-                                                            static_cast<size_t>(rw) * p.bw_ld + n0 + seg * 8));
+                q[j] = __ldg(reinterpret_cast<const uint4*>(src + img * img_stride + rh * row_stride +
+                                                            static_cast<size_t>(rw) * ld + n0 + seg * 8));
             }
 #pragma unroll
             for (int j = 0; j < kBatch; ++j)
               *reinterpret_cast<uint4*>(ytile + ((pb + j) * kRowsPerPass + r0) * kPitch + seg * 16) = q[j];
           }
-        }
-        bar_sync_epilogue();
+        };
         constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
         const int cp = t % kPairs, slab = t / kPairs;
         const int col = n0 + cp * 2;
-        if (col < p.cout) {
-          const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
-          const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
+        const uint8_t* gbase = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
+        const uint8_t* ybase = ytile + (slab * kRowsPerSlab) * kPitch + cp * 4;
+        if (p.bw_a != nullptr) {
+          // mask from the producer's saved output a (shortcut layers): pass 1 over the a tile builds one mask bit per
+          // (row, column) of this thread's slab in registers and the sums of g' = g * [a > 0]; pass 2 brings the y tile
+          // into the same buffer for the sums of g' * y
+          copy_tile(p.bw_a, p.bw_a_ld, p.bw_a_row_stride, p.bw_a_img_stride);
+          bar_sync_epilogue();
+          uint32_t m0[kRowsPerSlab / 32], m1[kRowsPerSlab / 32];
           float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-          const uint8_t* gbase = stg + (slab * kRowsPerSlab) * kPitch + cp * 4;
-          const uint8_t* ybase = ytile + (slab * kRowsPerSlab) * kPitch + cp * 4;
+#pragma unroll
+          for (int w = 0; w < kRowsPerSlab / 32; ++w) {
+            uint32_t bits0 = 0u, bits1 = 0u;
 #pragma unroll 8
-          for (int r = 0; r < kRowsPerSlab; ++r) {
-            // rows outside the image hold zeros in the staged gradient tile: they contribute nothing
-            const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
-            const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
-            const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
-            const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
-            a0 += g0, a1 += g1;
-            b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r = w * 32 + rr;
+              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
+              const float2 av = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
+              const bool on0 = av.x > 0.f, on1 = av.y > 0.f;
+              bits0 |= (on0 ? 1u : 0u) << rr, bits1 |= (on1 ? 1u : 0u) << rr;
+              a0 += on0 ? g.x : 0.f, a1 += on1 ? g.y : 0.f;
+            }
+            m0[w] = bits0, m1[w] = bits1;
           }
-          atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
-          if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
+          bar_sync_epilogue();  // every thread has read the a tile: the buffer may be overwritten
+          copy_tile(p.bw_y, p.bw_ld, p.bw_row_stride, p.bw_img_stride);
+          bar_sync_epilogue();
+#pragma unroll
+          for (int w = 0; w < kRowsPerSlab / 32; ++w) {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+              const int r = w * 32 + rr;
+              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
+              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
+              b0 = fmaf(((m0[w] >> rr) & 1u) ? g.x : 0.f, y.x, b0);
+              b1 = fmaf(((m1[w] >> rr) & 1u) ? g.y : 0.f, y.y, b1);
+            }
+          }
+          if (col < p.cout) {
+            atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
+            if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
+          }
+        } else {
+          copy_tile(p.bw_y, p.bw_ld, p.bw_row_stride, p.bw_img_stride);
+          bar_sync_epilogue();
+          if (col < p.cout) {
+            const float fs0 = p.bw_fscale[col], fb0 = p.bw_fshift[col];
+            const float fs1 = col + 1 < p.cout ? p.bw_fscale[col + 1] : 0.f, fb1 = col + 1 < p.cout ? p.bw_fshift[col + 1] : -1.f;
+            float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll 8
+            for (int r = 0; r < kRowsPerSlab; ++r) {
+              // rows outside the image hold zeros in the staged gradient tile: they contribute nothing
+              const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gbase + r * kPitch));
+              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(ybase + r * kPitch));
+              const float g0 = fmaf(y.x, fs0, fb0) > 0.f ? g.x : 0.f;
+              const float g1 = fmaf(y.y, fs1, fb1) > 0.f ? g.y : 0.f;
+              a0 += g0, a1 += g1;
+              b0 = fmaf(g0, y.x, b0), b1 = fmaf(g1, y.y, b1);
+            }
+            atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
+            if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
+          }
         }
       }
       // coalesced store: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass
@@ -823,8 +871,7 @@ static int launch(const IgemmParams& p, int grid, cudaStream_t stream) {
 //   Epilogue: each CTA drains its own tensor memory with the ordinary tile epilogue.
 // Used for the long-K, wide-N layers (conv_last, cbr_deepsup, layer4's 3x3 convs and their data gradients).
 // =====================================================================================================
-constexpr int kPairN = 256;
-template <int STAGES>
+template <int kPairN, int STAGES>
 struct IgemmPairSmem {
   static constexpr int kBBytes = (kPairN / 2) * kBlockK * 2;   // this CTA's half of the weight tile
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -833,9 +880,9 @@ struct IgemmPairSmem {
   static constexpr int kDynBytes = kTotal + 1024;
 };
 
-template <int STAGES>
+template <int kPairN, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1) igemm_pair_kernel(const __grid_constant__ IgemmParams p) {
-  using L = IgemmPairSmem<STAGES>;
+  using L = IgemmPairSmem<kPairN, STAGES>;
   static_assert(L::kDynBytes <= 232448, "shared memory budget");
   static_assert(2 * 128 * (kPairN * 2 + 16) <= STAGES * L::kStageBytes, "the epilogue stages two tiles in the pipeline buffers");
   SSEG_DYN_SMEM(smem_raw);
@@ -948,18 +995,18 @@ __global__ void __launch_bounds__(kNumThreads, 1) igemm_pair_kernel(const __grid
   }
 }
 
-template <int STAGES>
+template <int kPairN, int STAGES>
 static int launch_pair(const IgemmParams& p, int grid, cudaStream_t stream) {
-  using L = IgemmPairSmem<STAGES>;
+  using L = IgemmPairSmem<kPairN, STAGES>;
   static bool configured[64] = {};
   int dev = 0;
   SSEG_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !configured[dev]) {
-    SSEG_CUDA(cudaFuncSetAttribute(igemm_pair_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
+    SSEG_CUDA(cudaFuncSetAttribute(igemm_pair_kernel<kPairN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynBytes));
     configured[dev] = true;
   }
   count_launch(1);
-  return check_cuda(launch_k_pair(igemm_pair_kernel<STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, p),
+  return check_cuda(launch_k_pair(igemm_pair_kernel<kPairN, STAGES>, dim3(grid), dim3(kNumThreads), L::kDynBytes, stream, p),
                     "igemm_pair_kernel launch");
 }
 #endif  // __CUSIM__
@@ -1808,7 +1855,7 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
                            const sseg_act_t* bw_y, const float* bw_fscale, const float* bw_fshift, float* bw_s1,
                            float* bw_s2, sseg_stream_t stream_, const EpilogueAffine* ep = nullptr,
                            IgemmParams* params_out = nullptr, int* block_n_out = nullptr,
-                           const sseg_bn_fused_t* fin = nullptr) {
+                           const sseg_bn_fused_t* fin = nullptr, const sseg_act_t* bw_a = nullptr) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   SSEG_REQUIRE(g != nullptr && out != nullptr && w_bf16 != nullptr, "sseg_conv_igemm: null argument");
   const int n_store = out->c;
@@ -1860,6 +1907,8 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   bool use_pair = false;
 #ifndef __CUSIM__
   use_pair = pair_on && block_n == 256 && m_tiles % 2 == 0 && fin == nullptr;
+  // SSEG_IGEMM_2CTA=2: also the 128-wide tiles of mid-size layers as 256 x 128 pair tiles (24 KB per CTA and k-step)
+  if (pair_on >= 2 && block_n == 128 && m_tiles % 2 == 0 && fin == nullptr && p.num_k_steps >= 8) use_pair = true;
 #endif
   p.n_tiles = ceil_div(n_store, block_n);
   rc = get_tmap_2d(&p.tmB, w_bf16, 2, cout, w_ld, w_ld, kBlockK, use_pair ? block_n / 2 : block_n);
@@ -1887,7 +1936,16 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
     p.ep_scale = ep->scale, p.ep_shift = ep->shift, p.ep_relu = ep->relu;
   }
   if (bw_y != nullptr) {
-    SSEG_REQUIRE(!out_f32 && bw_fscale && bw_fshift && bw_s1 && bw_s2, "sseg_conv_igemm_bnbwd: null argument");
+    SSEG_REQUIRE(!out_f32 && bw_s1 && bw_s2 && ((bw_fscale && bw_fshift) || bw_a), "sseg_conv_igemm_bnbwd: null argument");
+    if (bw_a != nullptr) {
+      SSEG_REQUIRE(bw_a->n == out->n && bw_a->h == out->h && bw_a->w == out->w && bw_a->c >= cout && bw_a->ld % 8 == 0 &&
+                       (reinterpret_cast<uintptr_t>(bw_a->ptr) & 15) == 0 && bw_a->row_stride % 8 == 0 &&
+                       bw_a->img_stride % 8 == 0,
+                   "sseg_conv_igemm_bnbwd_res: saved output shape / alignment mismatch");
+      SSEG_REQUIRE(gh.flat == act_is_dense(*bw_a) || !gh.flat, "sseg_conv_igemm_bnbwd_res: a must be dense for 1x1 launches");
+      p.bw_a = static_cast<const __nv_bfloat16*>(bw_a->ptr);
+      p.bw_a_ld = bw_a->ld, p.bw_a_row_stride = bw_a->row_stride, p.bw_a_img_stride = bw_a->img_stride;
+    }
     SSEG_REQUIRE(bw_y->n == out->n && bw_y->h == out->h && bw_y->w == out->w && bw_y->c >= cout && cout % 8 == 0 &&
                      bw_y->ld % 8 == 0 && (reinterpret_cast<uintptr_t>(bw_y->ptr) & 15) == 0,
                  "sseg_conv_igemm_bnbwd: y shape / alignment mismatch");
@@ -1930,14 +1988,15 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   }
   // At most one CTA per SM (grid <= #SMs): the kernel is bound by TMA round trips (measured: ~35 B/cycle/SM with 96 KB in
   // flight, profiles/r2_summary.md), so the whole shared memory of the SM goes to pipeline stages (192 KB in flight).
+#ifndef __CUSIM__
+  if (use_pair && block_n == 256) return launch_pair<256, 5>(p, grid, stream);
+  if (use_pair) return launch_pair<128, 6>(p, grid, stream);
+#endif
   static const int deep = env_int("SSEG_IGEMM_DEEP", 1);
   if (deep && grid <= sm_count() && block_n != 256) {
     if (block_n == 64) return launch<64, 8>(p, grid, stream);
     return launch<128, 6>(p, grid, stream);
   }
-#ifndef __CUSIM__
-  if (use_pair) return launch_pair<5>(p, grid, stream);
-#endif
   if (block_n == 256) return launch<256, 4>(p, grid, stream);
   if (block_n == 64) return launch<64, 4>(p, grid, stream);
   return launch<128, 3>(p, grid, stream);
@@ -1972,6 +2031,14 @@ extern "C" int sseg_conv_igemm_bnbwd(const sseg_conv_geom_t* g, const void* w_bf
   SSEG_REQUIRE(y != nullptr, "sseg_conv_igemm_bnbwd: y required");
   return conv_igemm_impl(g, w_bf16, w_ld, cout, out, 0, nullptr, addend, nullptr, nullptr, y, fscale, fshift, s1, s2_raw,
                          stream);
+}
+
+extern "C" int sseg_conv_igemm_bnbwd_res(const sseg_conv_geom_t* g, const void* w_bf16, long w_ld, int cout,
+                                         const sseg_act_t* out, const sseg_act_t* addend, const sseg_act_t* y,
+                                         const sseg_act_t* a, float* s1, float* s2_raw, sseg_stream_t stream) {
+  SSEG_REQUIRE(y != nullptr && a != nullptr, "sseg_conv_igemm_bnbwd_res: y and a required");
+  return conv_igemm_impl(g, w_bf16, w_ld, cout, out, 0, nullptr, addend, nullptr, nullptr, y, nullptr, nullptr, s1, s2_raw,
+                         stream, nullptr, nullptr, nullptr, nullptr, a);
 }
 
 static int num_sms_of_current_device(int* out) {
@@ -2389,7 +2456,14 @@ extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, 
   }
   p.ragged = gh.ragged ? 1 : 0;
   for (int s = 0; s < g->nsrc; ++s) p.src_choff[s] = gh.src_choff[s], p.src_c[s] = gh.src_c[s];
-  const int block_n = (!gh.ragged && p.ci_span % 128 == 0) ? 128 : 64;
+  int block_n = (!gh.ragged && p.ci_span % 128 == 0) ? 128 : 64;
+  // 256 input channels per tile where that still leaves enough tiles: 48 KB per 512 MMA cycles instead of 32 KB per 256
+  // (the main loop is bound by what the SM takes in through TMA, see conv_igemm_impl)
+  static const int wg256 = env_int("SSEG_WGRAD_N256", 1);
+  static const int wg256_min_tiles = env_int("SSEG_WGRAD_N256_TILES", 74);
+  if (wg256 && block_n == 128 && p.ci_span % 256 == 0 && !fixed &&
+      ceil_div(cout, 128) * g->ntaps * (p.ci_span / 256) >= wg256_min_tiles)
+    block_n = 256;
   p.ci_tiles_per_tap = fixed ? ceil_div(gh.chan_per_src, block_n) : (gh.ragged ? gh.blocks_per_tap : p.ci_span / block_n);
   SSEG_REQUIRE(cout >= 1 && cout <= dy->c, "sseg_conv_wgrad: cout %d vs dy channels %d", cout, dy->c);
   p.cout = cout;
@@ -2407,6 +2481,7 @@ extern "C" int sseg_conv_wgrad(const sseg_conv_geom_t* g, const sseg_act_t* dy, 
   splits = ceil_div(p.total_boxes, p.boxes_per_split);
   p.dw = dw, p.dw_ld = dw_ld;
   const int grid = p.num_tiles * splits;
+  if (block_n == 256) return launch_wgrad<256, 4>(p, grid, stream);
   if (block_n == 64) return launch_wgrad<64, 4>(p, grid, stream);
   return launch_wgrad<128, 3>(p, grid, stream);
 }

@@ -119,6 +119,7 @@ _SIGNATURES = {
     "sseg_conv_dgrad_bn_fits": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), _p, _p, _p, _p, c_float, _p, _p,
                                 _p, _p],
     "sseg_conv_igemm_bnbwd": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(Act), _p, _p, _p, _p, _p],
+    "sseg_conv_igemm_bnbwd_res": [POINTER(Geom), _p, c_long, c_int, POINTER(Act), POINTER(Act), POINTER(Act), POINTER(Act), _p, _p, _p],
     "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
     "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],
     "sseg_prep_conv_weights_batched": [_p, c_int, c_int, _p],

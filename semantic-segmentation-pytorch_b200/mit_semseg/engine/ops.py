@@ -190,6 +190,18 @@ def conv_igemm_bnbwd(geom, w_bf16, cout, out, y, fscale, fshift, s1, s2_raw, add
     return out
 
 
+def conv_igemm_bnbwd_res(geom, w_bf16, cout, out, y, a_saved, s1, s2_raw, addend=None):
+    """Data gradient into `out` (the COMPLETE gradient of the producer's output) + the producer's BN-backward partial sums
+    with the ReLU mask taken from its saved output `a_saved` (shortcut layers; see sseg_conv_igemm_bnbwd_res)."""
+    assert out.dtype == torch.bfloat16 and w_bf16.dim() == 2 and w_bf16.stride(1) == 1
+    n_store = (cout + 7) // 8 * 8
+    o = act(out[..., :n_store])
+    ad = act(addend) if addend is not None else None
+    _C.check(_C.lib().sseg_conv_igemm_bnbwd_res(geom, _C.ptr(w_bf16), w_bf16.stride(0), cout, o, ad, act(y), act(a_saved),
+                                                _C.ptr(s1), _C.ptr(s2_raw), _stream()))
+    return out
+
+
 def conv_wgrad(geom, dy, cout, dw):
     """dw[co, koff_t + ci] += sum_pixels dy[.., co] * x_t[.., ci]; dw: fp32 2-D [cout, K], pre-zeroed by the caller."""
     assert dw.dtype == torch.float32 and dw.dim() == 2 and dw.stride(1) == 1

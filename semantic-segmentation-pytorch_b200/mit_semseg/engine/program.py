@@ -56,7 +56,7 @@ def _coop_fits_estimate(n, h, w, k, channels):
 
 class Act:
     """An activation tensor (NHWC bf16) plus, during backward construction, its gradient buffer."""
-    __slots__ = ("t", "tp", "g", "gw", "uses", "producer")
+    __slots__ = ("t", "tp", "g", "gw", "uses", "producer", "gcount")
 
     def __init__(self, t, tp=None):
         # t: the logical tensor (c channels; what convolutions read). tp: the same storage with the channel count
@@ -64,6 +64,7 @@ class Act:
         # writers see. They differ only for widths like HRNet+C1's 180-channel hidden layer.
         self.t, self.tp, self.g, self.gw = t, (t if tp is None else tp), None, False
         self.uses = 0          # number of consumers in the forward schedule
+        self.gcount = 0        # gradient contributions scheduled so far (backward construction): complete at == uses
         self.producer = None   # the ConvBNRec / StemRec that wrote it (if any)
 
 
@@ -142,6 +143,7 @@ class SegProgram:
         self.pool_groups = {}
         import os as _os
         self.fuse_bnbwd = _os.environ.get("SSEG_FUSE_BNBWD", "1") != "0"
+        self.fuse_bnbwd_res = _os.environ.get("SSEG_FUSE_BNBWD_RES", "1") != "0"   # ... also for residual-block outputs
         # measured on B200: fusing finalize into apply does NOT pay (6.92 vs 6.79 ms/step): with programmatic dependent
         # launch the tiny finalize kernel already overlaps the conv's tail, while the fused prologue delays every
         # block's streaming phase. Kept as an opt-in.
@@ -878,6 +880,7 @@ class SegProgram:
             act.g = torch.empty_like(act.tp if shape_like is None else shape_like)
         acc = act.gw
         act.gw = True
+        act.gcount += 1
         return act.g, acc
 
     # ------------------------------------------------------------------------------------------ execution
@@ -1042,16 +1045,17 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from
     sc = bns.scale
     fs = bns.shift if (mask_from_y and a is None) else None
     if fused:
-        # the consumer's dgrad epilogue already accumulated s1 (= dbeta) and the raw sum g'*y (sseg_conv_igemm_bnbwd)
-        assert a is None and fs is not None and chanmul is None and dres is None
+        # the consumer's dgrad epilogue already accumulated s1 (= dbeta) and the raw sum g'*y (sseg_conv_igemm_bnbwd, or,
+        # for a layer with a shortcut - mask from its saved output `a`, shortcut gradient `dres` - sseg_conv_igemm_bnbwd_res)
+        assert (a is None) != (fs is None) and chanmul is None and (dres is None or a is not None)
         if mode == ops.BN_TRAIN_SYNC and P.peer is not None:
             t1, t2, cnt = bns.tot[:C], bns.tot[C:2 * C], bns.tot[2 * C:2 * C + 1]
             P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, t1, t2, bns.dbeta,
                                                      bns.dgamma, mean=bns.mean, invstd=bns.invstd, s2_raw=True))
-            P.bwd.append(lambda: ops.bn_bwd_apply(g, None, y, bns.mean, bns.invstd, sc, t1, t2, count, dy, count_dev=cnt,
-                                                  fshift=fs))
+            P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, sc, t1, t2, count, dy, dres=dres,
+                                                  count_dev=cnt, fshift=fs))
         else:
-            P.bwd.append(lambda: ops.bn_bwd_apply(g, None, y, bns.mean, bns.invstd, sc, bns.dbeta, bns.s2y, count, dy,
+            P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, sc, bns.dbeta, bns.s2y, count, dy, dres=dres,
                                                   eval_mode=(mode == ops.BN_EVAL), fshift=fs, s2_raw=True,
                                                   dgamma_out=bns.dgamma))
         return
@@ -1302,10 +1306,25 @@ class ConvBNRec:
                 acc = False
             wd, I = cw.wd, cw.I
             prod = xs[0].producer if len(xs) == 1 else None
-            fuse = (P.fuse_bnbwd and prod is not None and not acc and xs[0].uses == 1 and prod.apply and prod.relu and
-                    prod.res is None and prod.post_add is None and prod.chanmul is None and I % 8 == 0 and
-                    not (prod.mode == ops.BN_TRAIN_SYNC and P.peer is None and P.dist is not None))
-            if fuse:
+            common = (P.fuse_bnbwd and prod is not None and prod.apply and prod.relu and prod.post_add is None and
+                      prod.chanmul is None and I % 8 == 0 and
+                      not (prod.mode == ops.BN_TRAIN_SYNC and P.peer is None and P.dist is not None))
+            fuse = common and not acc and xs[0].uses == 1 and prod.res is None
+            # a producer WITH a shortcut (the output of a residual block): its gradient has several contributions (the next
+            # block's first conv and its shortcut); the launch that adds the LAST one holds the complete gradient in its
+            # epilogue and can reduce it there, the ReLU mask coming from the producer's saved output
+            fuse_res = (common and P.fuse_bnbwd_res and not fuse and isinstance(prod, ConvBNRec) and prod.res is not None and
+                        xs[0].gcount == xs[0].uses and not prod.folded)
+            if fuse_res:
+                prod.fused = True
+                pb = prod.bns
+                if prod.mode == ops.BN_TRAIN_SYNC and P.peer is not None:
+                    s1, s2 = pb.part[:pb.Cp], pb.part[pb.Cp:2 * pb.Cp]
+                else:
+                    s1, s2 = pb.dbeta, pb.s2y
+                py, pa = prod.y, xs[0].tp
+                P.bwd.append(lambda: ops.conv_igemm_bnbwd_res(gd, wd, I, buf, py, pa, s1, s2, addend=buf if acc else None))
+            elif fuse:
                 # single consumer, no shortcut: the BN-backward reduction of the producer rides in this dgrad's epilogue
                 prod.fused = True
                 pb = prod.bns

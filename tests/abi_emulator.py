@@ -161,6 +161,14 @@ class EmuLib:
         vec(s2raw, cout).add_((gp * yv).sum((0, 1, 2)))
         return 0
 
+    def sseg_conv_igemm_bnbwd_res(self, g, w, w_ld, cout, out, addend, y, a, s1, s2raw, stream):
+        gr = self._epilogue(g, w, w_ld, cout, out, 0, None, addend, None, None)
+        yv = act_view(y).float()[..., :cout]
+        gp = gr * (act_view(a).float()[..., :cout] > 0)
+        vec(s1, cout).add_(gp.sum((0, 1, 2)))
+        vec(s2raw, cout).add_((gp * yv).sum((0, 1, 2)))
+        return 0
+
     def sseg_conv_wgrad(self, g, dy, cout, dw, dw_ld, stream):
         d = act_view(dy).float()[..., :cout]
         kmax = max(g.tap_koff[t] for t in range(g.ntaps)) + sum(g.srcs[i].c for i in range(g.nsrc))

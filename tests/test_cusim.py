@@ -77,8 +77,9 @@ def test_cooperative_kernels_with_uneven_tile_distribution_and_the_persistent_ge
     # the 128 x 256 tile variant (long-K layers on B200) forced onto the small test shapes: 8 accumulator chunks, the batched
     # y-tile copy of the fused BN-backward epilogue, a ragged last N tile
     _run_gpu_tests_on_sim("test_pointwise_wide_k_and_stats or test_3x3_cout256_cin512 or test_ragged or addend or "
-                          "test_dgrad_with_fused_bn_backward_reduce or test_virtual_concat_3x3", sms=8,
-                          extra_env={"SSEG_IGEMM_N256_KSTEPS": "1", "SSEG_IGEMM_N256_TILES": "1"})
+                          "test_dgrad_with_fused_bn_backward_reduce or test_virtual_concat_3x3 or test_wgrad_pointwise or "
+                          "test_wgrad_concat or test_wgrad_classifier_padded", sms=8,
+                          extra_env={"SSEG_IGEMM_N256_KSTEPS": "1", "SSEG_IGEMM_N256_TILES": "1", "SSEG_WGRAD_N256_TILES": "1"})
 
 
 # ------------------------------------------------------------------------------------------------ two ranks, one process

@@ -259,6 +259,52 @@ def test_dgrad_with_fused_bn_backward_reduce(k, hw, cprod, cout_next):
     assert (dya.float() - dyb.float()).abs().max().item() <= 2 ** -6 * dya.float().abs().max().item()
 
 
+@pytest.mark.parametrize("k,hw,cprod,cout_next", [(1, 64, 256, 64), (1, 38, 128, 256), (3, 32, 64, 64), (1, 16, 512, 128)])
+def test_dgrad_with_fused_bn_backward_reduce_of_a_shortcut_layer(k, hw, cprod, cout_next):
+    """sseg_conv_igemm_bnbwd_res: the data-gradient launch that ADDS THE LAST CONTRIBUTION to the gradient of a residual
+    block's output a = relu(bn(y) + shortcut) also reduces that block's BN backward, the ReLU mask coming from the saved
+    output: out = dgrad + addend (bit-identical to the plain accumulate launch), s1 = sum out*[a>0], s2 = sum out*[a>0]*y;
+    then sseg_bn_bwd_apply(a=..., dres=..., s2_raw) reproduces the separate reduce + apply pair (dy, shortcut gradient,
+    dgamma). Reference: autograd of models/resnet.py:37-53,72-92 through lib/nn/modules/batchnorm.py:58-61."""
+    from mit_semseg.engine import ops
+    g = torch.Generator(device="cuda").manual_seed(22)
+    n = 2
+    y = torch.randn(n, hw, hw, cprod, device="cuda", generator=g).bfloat16()        # producer's saved conv output
+    a = torch.relu(torch.randn(n, hw, hw, cprod, device="cuda", generator=g)).bfloat16()   # its saved block output
+    prev = (torch.randn(n, hw, hw, cprod, device="cuda", generator=g) * 0.1).bfloat16()    # gradient accumulated so far
+    dy_next = (torch.randn(n, hw, hw, cout_next, device="cuda", generator=g) * 0.1).bfloat16()
+    w = (torch.randn(cout_next, cprod, k, k, device="cuda", generator=g) * 0.05).bfloat16()
+    wd = torch.zeros(cprod, k * k * cout_next, device="cuda", dtype=torch.bfloat16)
+    ops.prep_conv_weight(w.float().contiguous(), None, wd, o_pad=cout_next)
+    dh, dw = ops.conv_taps(k, 1)
+    gd = ops.make_geom([dy_next], ([-v for v in dh], [-v for v in dw]), tap_koff=[t * cout_next for t in range(k * k)])
+    gout = prev.clone()
+    s1, s2 = torch.zeros(cprod, device="cuda"), torch.zeros(cprod, device="cuda")
+    ops.conv_igemm_bnbwd_res(gd, wd, cprod, gout, y, a, s1, s2, addend=gout)
+    ref_g = prev.clone()
+    ops.conv_igemm(gd, wd, cprod, ref_g, n_store=cprod, addend=ref_g)
+    torch.cuda.synchronize()
+    assert torch.equal(gout, ref_g)
+    gp = ref_g.float() * (a.float() > 0)
+    r1, r2 = gp.sum(dim=(0, 1, 2)), (gp * y.float()).sum(dim=(0, 1, 2))
+    assert (s1 - r1).abs().max().item() <= 1e-3 * r1.abs().max().item() + 1e-4
+    assert (s2 - r2).abs().max().item() <= 1e-3 * r2.abs().max().item() + 1e-4
+    mean = torch.randn(cprod, device="cuda", generator=g) * 0.2
+    invstd = torch.rand(cprod, device="cuda", generator=g) + 0.5
+    scale = torch.rand(cprod, device="cuda", generator=g) + 0.5
+    s1b, s2b = torch.zeros(cprod, device="cuda"), torch.zeros(cprod, device="cuda")
+    ops.bn_bwd_reduce(ref_g, a, y, mean, invstd, s1b, s2b)
+    dya, dyb, dra, drb = torch.empty_like(y), torch.empty_like(y), torch.empty_like(y), torch.empty_like(y)
+    dgam = torch.zeros(cprod, device="cuda")
+    cnt = n * hw * hw
+    ops.bn_bwd_apply(ref_g, a, y, mean, invstd, scale, s1b, s2b, cnt, dya, dres=dra)
+    ops.bn_bwd_apply(gout, a, y, mean, invstd, scale, s1, s2, cnt, dyb, dres=drb, s2_raw=True, dgamma_out=dgam)
+    torch.cuda.synchronize()
+    assert torch.equal(dra, drb)
+    assert (dgam - s2b).abs().max().item() <= 2e-3 * s2b.abs().max().item() + 1e-3
+    assert (dya.float() - dyb.float()).abs().max().item() <= 2 ** -6 * dya.float().abs().max().item()
+
+
 @pytest.mark.parametrize("n,hw,cin,cout,k", [(2, 32, 64, 128, 1), (2, 24, 96, 200, 3), (1, 64, 256, 512, 1)])
 def test_conv_with_bn_finalize_by_the_last_cta(n, hw, cin, cout, k):
     """sseg_conv_igemm_bnfin = sseg_conv_igemm(stats) + sseg_bn_finalize(SSEG_BN_TRAIN): same y (bit for bit), same

@@ -83,7 +83,7 @@ def test_training_schedule_executes(enc, dec, fc, stride, switches, null_lib, mo
     nconv = sum(isinstance(m, nn.Conv2d) for m in seg.modules())
     assert calls["sseg_conv_wgrad"] == 2 * (nconv - 1) and calls["sseg_stem_conv_wgrad"] == 2   # two runs
     fwd_convs = sum(calls.get(k, 0) for k in ("sseg_conv_igemm", "sseg_conv_bn_train", "sseg_conv_igemm_bnbwd",
-                                              "sseg_conv_dgrad_bn"))
+                                              "sseg_conv_igemm_bnbwd_res", "sseg_conv_igemm_bnfin", "sseg_conv_dgrad_bn"))
     assert fwd_convs >= 2 * 2 * (nconv - 1) - 8          # forward + data gradient of every conv but the stem (first layers have no dgrad)
     if "SSEG_COOP_BN" in switches:
         assert calls["sseg_conv_bn_train"] > 0 and calls["sseg_conv_dgrad_bn"] > 0

@@ -26,7 +26,12 @@ def main():
     from mit_semseg.engine import functional as EF
     from mit_semseg.models import ModelBuilder, SegmentationModule
     from mit_semseg.models import hrnet as HR, models as M, resnet as R
-    dev = torch.device("cuda", 0)
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:   # under torch.distributed.run the scales of --multiscale are sharded scale k -> rank k mod world
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
     torch.manual_seed(304)
     if args.net == "hrnet":
         enc, dec = HR.hrnetv2(pretrained=False), ModelBuilder.build_decoder("c1", fc_dim=720, num_class=150, use_softmax=True)
@@ -62,9 +67,19 @@ def main():
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.iters
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
     units = 1 if args.multiscale else args.batch
-    print("%s %s: %.3f ms / call, %.1f images/s (fold_bn_eval=%s)" % (args.net, what, ms, units / ms * 1e3,
-                                                                     os.environ.get("SSEG_FOLD_BN_EVAL", "0")))
+    if rank == 0:
+        print("%s %s: %.3f ms / call, %.1f images/s (fold_bn_eval=%s, %d GPU%s)" % (
+            args.net, what, ms, units / ms * 1e3, os.environ.get("SSEG_FOLD_BN_EVAL", "0"), world, "s" if world > 1 else ""))
+    if world > 1:
+        for q in seg.__dict__.get("_b200_programs", {}).values():
+            q.graph = None
+        import bench
+        bench.shutdown_distributed()
 
 
 if __name__ == "__main__":

@@ -12,3 +12,6 @@ echo "== bench N=2"
 timeout 400 $RUN 29513 bench.py --gpus 2 --steps 40 --warmup 5 2>&1 | tail -1 | cut -c1-900
 echo "== bench N=2, NCCL SyncBN (SSEG_PEER_SYNC=0)"
 SSEG_PEER_SYNC=0 timeout 400 $RUN 29514 bench.py --gpus 2 --steps 40 --warmup 5 2>&1 | tail -1 | cut -c1-500
+echo "== config 5: HRNetV2-W48 + C1 multi-scale inference, scales sharded over the two GPUs (and on one GPU for comparison)"
+timeout 300 python tools/infer_bench.py --net hrnet --multiscale 2>&1 | tail -1
+timeout 300 $RUN 29515 tools/infer_bench.py --net hrnet --multiscale 2>&1 | tail -1
