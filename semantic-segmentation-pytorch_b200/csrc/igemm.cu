@@ -202,6 +202,26 @@ __device__ __forceinline__ void igemm_tile_epilogue(const IgemmParams& p, uint8_
       bar_sync_epilogue();  // the 4 epilogue warps only: the staged tile is complete
       const int t = threadIdx.x - 64;
       if (threadIdx.x == 64) SSEG_STAMP(9);
+      // coalesced store first: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass. The stores are
+      // fire-and-forget, so the column sums below (shared-memory reads only) run while they drain.
+      {
+      constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
+      const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
+            if (n0 + seg * 8 < p.n_store) {
+#pragma unroll 4
+        for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
+          const int r = pass * kRowsPerPass + r0;
+          const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
+          if (rh < p.H && rw < p.W) {
+            const uint4 q = *reinterpret_cast<const uint4*>(stg + r * kPitch + seg * 16);
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride + rh * p.out_row_stride +
+                                static_cast<size_t>(rw) * p.ld_out + n0 + seg * 8;
+            *reinterpret_cast<uint4*>(op) = q;
+          }
+        }
+      }
+      }
+      if (threadIdx.x == 64) SSEG_STAMP(11);
       if (do_stats) {
         // thread = one pair of adjacent columns x one slab of rows; fp32 sums of the bf16 values as stored
         constexpr int kPairs = BLOCK_N / 2, kSlabs = 128 / kPairs, kRowsPerSlab = 128 / kSlabs;
@@ -309,23 +329,6 @@ __device__ __forceinline__ void igemm_tile_epilogue(const IgemmParams& p, uint8_
             }
             atomicAdd(p.bw_s1 + col, a0), atomicAdd(p.bw_s2 + col, b0);
             if (col + 1 < p.cout) atomicAdd(p.bw_s1 + col + 1, a1), atomicAdd(p.bw_s2 + col + 1, b1);
-          }
-        }
-      }
-      // coalesced store: BLOCK_N/8 lanes cover one row (16 B each), several rows per pass
-      constexpr int kLanesPerRow = BLOCK_N / 8, kRowsPerPass = 128 / kLanesPerRow;
-      const int seg = t % kLanesPerRow, r0 = t / kLanesPerRow;
-      if (threadIdx.x == 64) SSEG_STAMP(11);
-      if (n0 + seg * 8 < p.n_store) {
-#pragma unroll 4
-        for (int pass = 0; pass < 128 / kRowsPerPass; ++pass) {
-          const int r = pass * kRowsPerPass + r0;
-          const int rh = h0 + (r >> p.bw_shift), rw = w0 + (r & (p.BW - 1));
-          if (rh < p.H && rw < p.W) {
-            const uint4 q = *reinterpret_cast<const uint4*>(stg + r * kPitch + seg * 16);
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.out_img_stride + rh * p.out_row_stride +
-                                static_cast<size_t>(rw) * p.ld_out + n0 + seg * 8;
-            *reinterpret_cast<uint4*>(op) = q;
           }
         }
       }

@@ -26,7 +26,7 @@ SHAPES = [  # name, n, h, w, cin, cout, k, dil, stats
     ("conv_last 3x3 4096->512", 2, 64, 64, 4096, 512, 3, 1, True),
 ]
 NAMES = ["entry", "prologue", "dep-wait", "1st TMA", "last TMA", "1st full", "last MMA", "acc seen", "staged", "bar", "stats",
-         "bnbwd", "stored", "sync", "dealloc"]
+         "stores issued", "epilogue end", "sync", "dealloc"]   # (stamp 11 = after the tile stores, which now precede the sums)
 
 
 def main():
