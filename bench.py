@@ -211,34 +211,41 @@ def run_gpu(args):
     roof = conv_roofline(prog, world)
     barrier(world)
 
-    # ---------------- end-to-end arm: the public API with host inputs (H2D) and a loss read-back (D2H) every step
-    for p in seg.parameters():
-        p.grad = None
-    opts = make_optimizers(seg)               # end-to-end arm: exactly train.py's torch.optim.SGD pair
+    # ---------------- end-to-end arm: the public API with host inputs (H2D) and a loss read-back (D2H) every step.
+    # Twice: with the optimizer this package ships (mit_semseg.engine.optim.FusedSGD, a torch.optim.Optimizer with
+    # torch.optim.SGD's arithmetic: the headline `e2e`) and with exactly train.py's torch.optim.SGD pair (`e2e.torch_optim_sgd`).
     feed_host = {"img_data": img_h, "seg_label": lab_h}
 
-    def e2e_step():
-        seg.zero_grad()
-        # pinned HOST tensors go straight into the public call: SegmentationModule copies them (cudaMemcpyAsync) into the
-        # step's static device buffers - this is the H2D traffic counted below
-        loss, acc = seg(feed_host)
-        loss = loss.mean()
-        loss.backward()
-        for o in opts:
-            o.step()
-        return loss.item()
+    def e2e_run(fused):
+        for p in seg.parameters():
+            p.grad = None
+        e_opts = make_optimizers(seg, fused=fused)
 
-    for _ in range(max(3, args.warmup)):
-        e2e_step()
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        last = e2e_step()
-    e1.record()
-    barrier(world)
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1), world)
-    e2e_value = BATCH * world * args.steps / (e2e_ms / 1e3)
+        def e2e_step():
+            seg.zero_grad()
+            # pinned HOST tensors go straight into the public call: SegmentationModule copies them (cudaMemcpyAsync) into the
+            # step's static device buffers - this is the H2D traffic counted below
+            loss, acc = seg(feed_host)
+            loss = loss.mean()
+            loss.backward()
+            for o in e_opts:
+                o.step()
+            return loss.item()
+
+        for _ in range(max(3, args.warmup)):
+            e2e_step()
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            last_ = e2e_step()
+        e1.record()
+        barrier(world)
+        ms_ = max_over_ranks(e0.elapsed_time(e1), world)
+        return ms_, BATCH * world * args.steps / (ms_ / 1e3), last_
+
+    e2e_ms, e2e_value, last = e2e_run(fused=True)
+    e2e_ms_t, e2e_value_t, last_t = e2e_run(fused=False)
 
     prog.graph = None
     seg.__dict__.pop("_b200_programs", None)
@@ -259,7 +266,10 @@ def run_gpu(args):
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 3), "unit": "images/s", "ms_per_step": round(e2e_ms / args.steps, 4),
                 "h2d_bytes_per_step": img_h.numel() * 4 + lab_h.numel() * 8, "d2h_bytes_per_step": 4,
-                "loss_last": round(last, 5)},
+                "loss_last": round(last, 5),
+                "api": "SegmentationModule(host feed) -> loss.mean().backward() -> FusedSGD.step() x2 -> loss.item()",
+                "torch_optim_sgd": {"value": round(e2e_value_t, 3), "ms_per_step": round(e2e_ms_t / args.steps, 4),
+                                    "loss_last": round(last_t, 5)}},
         "gpu_launches": (launches_per_step + 2) * args.steps,
         "launches_per_step": launches_per_step + 2,
         "model_flops_frac": round(value / world * TRAIN_GFLOP_PER_IMG / 1e3 / sustained, 4),
