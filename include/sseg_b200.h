@@ -360,6 +360,16 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
 int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
                          float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
                          int s2_raw, int C, sseg_stream_t stream);
+/* sseg_bn_bwd_peer_sum + sseg_bn_bwd_apply in ONE launch (one dependent kernel less per BatchNorm layer on the backward
+ * chain of a multi-GPU step): every block runs the flag handshake, pools this layer's partial sums [s1 | s2] (at part_off /
+ * part_off + C of every rank's arena; s2 raw when s2_raw) straight out of peer memory, applies
+ * dy = scale * (g' - s1/M - xhat * s2/M) with M = *count_dev (the pooled pixel count), and block column 0 stores
+ * dbeta_out = s1 / world, dgamma_out = s2 / world. Arguments as for the two functions it replaces. */
+int sseg_bn_bwd_apply_peer(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
+                           const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
+                           const float* invstd, const float* scale, const float* fshift, const float* chanmul,
+                           const float* count_dev, void* dy, long dy_ld, void* dres, long dres_ld, long P, long pix_per_img,
+                           int C, int s2_raw, float* dbeta_out, float* dgamma_out, sseg_stream_t stream);
 
 /* ---- pooling / resize ------------------------------------------------------------------- */
 /* nn.MaxPool2d(3, 2, 1) (models/resnet.py:109). Dense bf16 NHWC; idx (1 byte / output element) feeds the backward. */

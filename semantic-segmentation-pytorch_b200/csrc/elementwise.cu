@@ -3,6 +3,7 @@
 // All activations are NHWC bf16 (C contiguous) accessed with 16-byte vectors (8 channels per thread).
 #include "common.h"
 #include "ptx.cuh"
+#include "peer.cuh"
 #include <cuda_bf16.h>
 
 namespace sseg {
@@ -401,6 +402,14 @@ struct BnBwdParams {
   // s2 = invstd * (s2_raw - mean * s1) on the fly and block column 0 stores the converted value to dgamma_out
   int s2_raw;
   float* dgamma_out;
+  // SyncBN across GPUs folded into the apply pass (sseg_bn_bwd_apply_peer): s1 / s2 are then THIS rank's partial sums at
+  // part_off / part_off + C inside its peer arena; the kernel runs the flag handshake of csrc/peer.cu itself, pools the
+  // partials of all ranks straight out of peer memory (one NVLink round trip) and block column 0 stores dbeta / dgamma
+  // divided by world (the gradient bucket all-reduce sums them again)
+  PeerTable pt;   // pt.world <= 1: single-GPU behaviour
+  long part_off, flag_off;
+  const int* step;
+  float* dbeta_out;
 };
 
 template <bool kApply>
@@ -421,20 +430,42 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
     fs[e] = p.scale ? p.scale[c0 + e] : 1.f, fb[e] = p.fshift ? p.fshift[c0 + e] : 0.f;
   }
   if (kApply) {
+    float s1p[8], s2p[8];
+    if (p.pt.world > 1) {
+      // pooled sums of this block's channels: thread (tcol, trow < 8) fetches channel 8 * group + trow from every rank (all
+      // loads of the thread in flight together), the block shares them through shared memory
+      __shared__ float pooled[2][256];
+      peer_handshake(p.pt, p.flag_off, *p.step, blockIdx.x == 0 && blockIdx.y == 0);
+      if (trow < 8 && active) {
+        float a, b;
+        peer_sum2(p.pt, p.part_off + c0 + trow, p.part_off + p.C + c0 + trow, &a, &b);
+        pooled[0][tcol * 8 + trow] = a, pooled[1][tcol * 8 + trow] = b;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s1p[e] = pooled[0][tcol * 8 + e], s2p[e] = pooled[1][tcol * 8 + e];
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        s1p[e] = (p.s1 != nullptr && active) ? p.s1[c0 + e] : 0.f;
+        s2p[e] = (p.s2 != nullptr && active) ? p.s2[c0 + e] : 0.f;
+      }
+    }
     const float inv_m = 1.f / (p.count_dev ? *p.count_dev : p.count_host);
+    const float inv_w = p.pt.world > 1 ? 1.f / (float)p.pt.world : 1.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float s2v = 0.f;
-      if (p.s2 != nullptr && active) {
-        s2v = p.s2[c0 + e];
-        if (p.s2_raw) s2v = inv[e] * (s2v - mu[e] * p.s1[c0 + e]);
+      float s2v = s2p[e];
+      if (p.s2_raw) s2v = inv[e] * (s2v - mu[e] * s1p[e]);
+      if (active && blockIdx.x == 0 && trow == 0) {
+        if ((p.s2_raw || p.pt.world > 1) && p.dgamma_out != nullptr) p.dgamma_out[c0 + e] = s2v * inv_w;
+        if (p.pt.world > 1 && p.dbeta_out != nullptr) p.dbeta_out[c0 + e] = s1p[e] * inv_w;
       }
-      if (p.s2_raw && p.dgamma_out != nullptr && active && blockIdx.x == 0 && trow == 0) p.dgamma_out[c0 + e] = s2v;
       if (p.eval_mode) {
         ka[e] = fs[e], kb[e] = 0.f, kc[e] = 0.f;
       } else {
         const float t = fs[e] * inv[e] * s2v * inv_m;
-        ka[e] = fs[e], kb[e] = -t, kc[e] = t * mu[e] - fs[e] * p.s1[c0 + e] * inv_m;
+        ka[e] = fs[e], kb[e] = -t, kc[e] = t * mu[e] - fs[e] * s1p[e] * inv_m;
       }
     }
   }
@@ -1236,7 +1267,8 @@ static int fill_bwd(BnBwdParams& p, const void* g, long g_ld, const void* a, lon
   *t = bn_tiling(P, C, reduce);
   p = BnBwdParams{(const __nv_bfloat16*)g, g_ld, (const __nv_bfloat16*)a, a_ld, (const __nv_bfloat16*)y, y_ld, mean,
                   invstd, scale, fshift, chanmul, s1, s2, count_dev, count_host, (__nv_bfloat16*)dy, dy_ld,
-                  (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode, t->cgb, t->rows, s2_raw, dgamma_out};
+                  (__nv_bfloat16*)dres, dres_ld, P, pix_per_img, C, eval_mode, t->cgb, t->rows, s2_raw, dgamma_out,
+                  PeerTable{}, 0, 0, nullptr, nullptr};
   return 0;
 }
 
@@ -1269,6 +1301,26 @@ int sseg_bn_bwd_apply(const void* g, long g_ld, const void* a, long a_ld, const 
   SSEG_REQUIRE(eval_mode || (y && mean && invstd && s1 && s2), "sseg_bn_bwd_apply: training mode needs y/mean/invstd/s1/s2");
   launch_k(bn_bwd_kernel<true>, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("bn_bwd_apply_kernel");
+}
+
+int sseg_bn_bwd_apply_peer(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
+                           const void* g, long g_ld, const void* a, long a_ld, const void* y, long y_ld, const float* mean,
+                           const float* invstd, const float* scale, const float* fshift, const float* chanmul,
+                           const float* count_dev, void* dy, long dy_ld, void* dres, long dres_ld, long P, long pix_per_img,
+                           int C, int s2_raw, float* dbeta_out, float* dgamma_out, sseg_stream_t st) {
+  BnBwdParams p;
+  BnTiling t;
+  int rc = fill_bwd(p, g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, fshift, chanmul, nullptr, nullptr, count_dev, 1.f, dy,
+                    dy_ld, dres, dres_ld, P, pix_per_img, C, 0, &t, false, s2_raw, dgamma_out);
+  if (rc) return rc;
+  SSEG_REQUIRE(step && count_dev && y && mean && invstd && scale && dy && dbeta_out && dgamma_out && dy_ld % 8 == 0 &&
+                   (!dres || dres_ld % 8 == 0),
+               "sseg_bn_bwd_apply_peer: bad argument");
+  rc = make_peer_table(&p.pt, bases, world, rank, "sseg_bn_bwd_apply_peer");
+  if (rc) return rc;
+  p.part_off = part_off, p.flag_off = flag_off, p.step = step, p.dbeta_out = dbeta_out;
+  launch_k(bn_bwd_kernel<true>, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
+  LAUNCH_CHECK("bn_bwd_apply_peer_kernel");
 }
 
 int sseg_maxpool_fwd(const void* x, int N, int H, int W, int C, void* out, void* idx, sseg_stream_t st) {

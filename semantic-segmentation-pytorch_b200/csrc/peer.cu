@@ -13,57 +13,9 @@
 // Broadcast) and the host-side SyncMaster/SlavePipe rendezvous (comm.py:18-131).
 #include "common.h"
 #include "ptx.cuh"
+#include "peer.cuh"
 
 namespace sseg {
-
-struct PeerTable {
-  float* base[SSEG_MAX_PEERS];
-  int world, rank;
-};
-
-// All threads of every block call this. Block 0 publishes; every block waits for all peers. The wait is bounded: a peer
-// that never publishes (a dead or diverged rank) ends the launch with a trap after ~10 s of SM clocks instead of hanging
-// the job for ever (the reference's host-side rendezvous, comm.py:113, blocks without a timeout).
-__device__ __forceinline__ void peer_handshake(const PeerTable& pt, long flag_off, int step) {
-  if (blockIdx.x == 0 && threadIdx.x < pt.world) {
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<int*>(pt.base[threadIdx.x]) + flag_off + pt.rank, step);
-  }
-  if (threadIdx.x < pt.world) {
-    const int* mine = reinterpret_cast<const int*>(pt.base[pt.rank]) + flag_off + threadIdx.x;
-    const long long t0 = clock64();
-    while (ld_acquire_sys(mine) < step) {
-      __nanosleep(32);
-      if (clock64() - t0 > 20000000000ll) __trap();
-    }
-  }
-  __syncthreads();
-}
-
-// Sum of one value per rank, read straight out of the peers' arenas. All loads are issued before the first use (one NVLink
-// round trip, not `world` of them: with a data-dependent loop the eight loads of an 8-GPU job serialise, ~1 us each) and
-// added in rank order, so every rank computes bit-identical totals.
-__device__ __forceinline__ float peer_sum(const PeerTable& pt, long off) {
-  float v[SSEG_MAX_PEERS];
-#pragma unroll
-  for (int r = 0; r < SSEG_MAX_PEERS; ++r) v[r] = r < pt.world ? __ldcv(pt.base[r] + off) : 0.f;
-  float s = 0.f;
-#pragma unroll
-  for (int r = 0; r < SSEG_MAX_PEERS; ++r) s += v[r];
-  return s;
-}
-__device__ __forceinline__ void peer_sum2(const PeerTable& pt, long off_a, long off_b, float* a, float* b) {
-  float va[SSEG_MAX_PEERS], vb[SSEG_MAX_PEERS];
-#pragma unroll
-  for (int r = 0; r < SSEG_MAX_PEERS; ++r) {
-    va[r] = r < pt.world ? __ldcv(pt.base[r] + off_a) : 0.f;
-    vb[r] = r < pt.world ? __ldcv(pt.base[r] + off_b) : 0.f;
-  }
-  float sa = 0.f, sb = 0.f;
-#pragma unroll
-  for (int r = 0; r < SSEG_MAX_PEERS; ++r) sa += va[r], sb += vb[r];
-  *a = sa, *b = sb;
-}
 
 __global__ void peer_step_kernel(int* step) {
   pdl_sync();
@@ -81,7 +33,7 @@ __global__ void __launch_bounds__(256) bn_finalize_peer_kernel(const PeerTable p
                                                                float* __restrict__ scale, float* __restrict__ shift,
                                                                float* __restrict__ count_out, int C) {
   pdl_sync();
-  peer_handshake(pt, flag_off, *step_ptr);
+  peer_handshake(pt, flag_off, *step_ptr, blockIdx.x == 0);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int cc = c < C ? c : 0;
   float s, q;
@@ -126,7 +78,7 @@ __global__ void __launch_bounds__(256) bn_bwd_peer_sum_kernel(const PeerTable pt
                                                               float* __restrict__ dgamma, const float* __restrict__ mean,
                                                               const float* __restrict__ invstd, int s2_raw, int C) {
   pdl_sync();
-  peer_handshake(pt, flag_off, *step_ptr);
+  peer_handshake(pt, flag_off, *step_ptr, blockIdx.x == 0);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a, b;
@@ -137,7 +89,7 @@ __global__ void __launch_bounds__(256) bn_bwd_peer_sum_kernel(const PeerTable pt
   dbeta[c] = a * inv_w, dgamma[c] = b * inv_w;
 }
 
-static int make_table(PeerTable* t, void* const* bases, int world, int rank, const char* who) {
+int make_peer_table(PeerTable* t, void* const* bases, int world, int rank, const char* who) {
   SSEG_REQUIRE(bases != nullptr && world >= 1 && world <= SSEG_MAX_PEERS && rank >= 0 && rank < world,
                "%s: bad peer table (world %d rank %d)", who, world, rank);
   memset(t, 0, sizeof(*t));
@@ -196,7 +148,7 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
                           float* mean_out, float* invstd_out, float* scale, float* shift, float* count_out, int C,
                           sseg_stream_t st) {
   PeerTable t;
-  int rc = make_table(&t, bases, world, rank, "sseg_bn_finalize_peer");
+  int rc = make_peer_table(&t, bases, world, rank, "sseg_bn_finalize_peer");
   if (rc) return rc;
   SSEG_REQUIRE(step && mean_out && invstd_out && scale && shift && count_out && C > 0, "sseg_bn_finalize_peer: null");
   SSEG_REQUIRE(!update_running || (running_mean && running_var && tmp_mean && tmp_var && running_iter),
@@ -230,7 +182,7 @@ int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off,
                          float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
                          int s2_raw, int C, sseg_stream_t st) {
   PeerTable t;
-  int rc = make_table(&t, bases, world, rank, "sseg_bn_bwd_peer_sum");
+  int rc = make_peer_table(&t, bases, world, rank, "sseg_bn_bwd_peer_sum");
   if (rc) return rc;
   SSEG_REQUIRE(step && s1_tot && s2_tot && dbeta && dgamma && C > 0, "sseg_bn_bwd_peer_sum: null");
   SSEG_REQUIRE(!s2_raw || (mean && invstd), "sseg_bn_bwd_peer_sum: raw partials need mean and invstd");

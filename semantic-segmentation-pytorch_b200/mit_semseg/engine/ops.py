@@ -351,6 +351,19 @@ def bn_bwd_apply(g, a, y, mean, invstd, scale, s1, s2, count, dy, dres=None, cha
                                         ppi, g.shape[3], int(eval_mode), int(s2_raw), _C.ptr(dgamma_out), _stream()))
 
 
+def bn_bwd_apply_peer(arena, part_off, flag_off, step, g, a, y, mean, invstd, scale, count_dev, dy, dbeta, dgamma, dres=None,
+                      chanmul=None, fshift=None, s2_raw=False):
+    """bn_bwd_peer_sum + bn_bwd_apply in one launch (multi-GPU SyncBN backward; see sseg_bn_bwd_apply_peer)."""
+    P, ppi, g_ld = _pix(g)
+    a_ld = _pix(a)[2] if a is not None else 0
+    dres_ld = _pix(dres)[2] if dres is not None else 0
+    _C.check(_C.lib().sseg_bn_bwd_apply_peer(arena.bases, arena.world, arena.rank, part_off, flag_off, _C.ptr(step), _C.ptr(g),
+                                             g_ld, _C.ptr(a), a_ld, _C.ptr(y), _pix(y)[2], _C.ptr(mean), _C.ptr(invstd),
+                                             _C.ptr(scale), _C.ptr(fshift), _C.ptr(chanmul), _C.ptr(count_dev), _C.ptr(dy),
+                                             _pix(dy)[2], _C.ptr(dres), dres_ld, P, ppi, g.shape[3], int(s2_raw),
+                                             _C.ptr(dbeta), _C.ptr(dgamma), _stream()))
+
+
 def maxpool_fwd(x, out, idx):
     n, h, w, c = x.shape
     assert x.is_contiguous() and out.is_contiguous()

@@ -144,6 +144,9 @@ class SegProgram:
         import os as _os
         self.fuse_bnbwd = _os.environ.get("SSEG_FUSE_BNBWD", "1") != "0"
         self.fuse_bnbwd_res = _os.environ.get("SSEG_FUSE_BNBWD_RES", "1") != "0"   # ... also for residual-block outputs
+        # multi-GPU: the SyncBN backward exchange (flag handshake + pooling of the partial sums out of peer memory) runs
+        # inside the BN-backward apply kernel instead of a kernel of its own (SSEG_PEER_FUSE_BWD=0: separate kernels)
+        self.peer_fuse_bwd = _os.environ.get("SSEG_PEER_FUSE_BWD", "1") != "0"
         # measured on B200: fusing finalize into apply does NOT pay (6.92 vs 6.79 ms/step): with programmatic dependent
         # launch the tiny finalize kernel already overlaps the conv's tail, while the fused prologue delays every
         # block's streaming phase. Kept as an opt-in.
@@ -1048,7 +1051,13 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from
         # the consumer's dgrad epilogue already accumulated s1 (= dbeta) and the raw sum g'*y (sseg_conv_igemm_bnbwd, or,
         # for a layer with a shortcut - mask from its saved output `a`, shortcut gradient `dres` - sseg_conv_igemm_bnbwd_res)
         assert (a is None) != (fs is None) and chanmul is None and (dres is None or a is not None)
-        if mode == ops.BN_TRAIN_SYNC and P.peer is not None:
+        if mode == ops.BN_TRAIN_SYNC and P.peer is not None and P.peer_fuse_bwd:
+            # handshake + pooling over NVLink inside the apply pass (one dependent launch less per layer)
+            cnt = bns.tot[2 * C:2 * C + 1]
+            P.bwd.append(lambda: ops.bn_bwd_apply_peer(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, g, a, y, bns.mean,
+                                                       bns.invstd, sc, cnt, dy, bns.dbeta, bns.dgamma, dres=dres, fshift=fs,
+                                                       s2_raw=True))
+        elif mode == ops.BN_TRAIN_SYNC and P.peer is not None:
             t1, t2, cnt = bns.tot[:C], bns.tot[C:2 * C], bns.tot[2 * C:2 * C + 1]
             P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, t1, t2, bns.dbeta,
                                                      bns.dgamma, mean=bns.mean, invstd=bns.invstd, s2_raw=True))
@@ -1071,6 +1080,11 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from
         p1, p2 = bns.part[:C], bns.part[C:2 * C]
         t1, t2, cnt = bns.tot[:C], bns.tot[C:2 * C], bns.tot[2 * C:2 * C + 1]
         P.bwd.append(lambda: ops.bn_bwd_reduce(g, a, y, bns.mean, bns.invstd, p1, p2, chanmul=chanmul, scale=sc, fshift=fs))
+        if P.peer_fuse_bwd:
+            P.bwd.append(lambda: ops.bn_bwd_apply_peer(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, g, a, y, bns.mean,
+                                                       bns.invstd, sc, cnt, dy, bns.dbeta, bns.dgamma, dres=dres,
+                                                       chanmul=chanmul, fshift=fs))
+            return
         P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, t1, t2, bns.dbeta,
                                                  bns.dgamma))
         P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, sc, t1, t2, count, dy, dres=dres,

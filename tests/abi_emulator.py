@@ -745,6 +745,21 @@ class EmuLib:
         vec(dgamma, C).copy_(b / world)
         return 0
 
+    def sseg_bn_bwd_apply_peer(self, bases, world, rank, part_off, flag_off, step, g, g_ld, a, a_ld, y, y_ld, mean, invstd,
+                               scale, fshift, chanmul, count_dev, dy, dy_ld, dres, dres_ld, P, ppi, C, s2_raw, dbeta_out,
+                               dgamma_out, stream):
+        pr = self._Peers(bases, world)
+        s1 = self._pool(pr, part_off, C).clone()
+        s2 = self._pool(pr, part_off + C, C).clone()
+        if s2_raw:
+            s2 = vec(invstd, C) * (s2 - vec(mean, C) * s1)
+        vec(dbeta_out, C).copy_(s1 / world)
+        vec(dgamma_out, C).copy_(s2 / world)
+        keep = (s1.contiguous(), s2.contiguous())
+        return self.sseg_bn_bwd_apply(g, g_ld, a, a_ld, y, y_ld, mean, invstd, scale, fshift, chanmul,
+                                      ctypes.c_void_p(keep[0].data_ptr()), ctypes.c_void_p(keep[1].data_ptr()), count_dev, 1.0, dy,
+                                      dy_ld, dres, dres_ld, P, ppi, C, 0, 0, None, stream)
+
     # ---- optimiser
     def sseg_scale_by_scalar(self, x, n, scalar, stream):
         v = flat(scalar, 1, torch.float32)[0].item()

@@ -423,7 +423,20 @@ def test_peer_memory_syncbn_kernels_two_ranks(sim):
                                  out[r]["v"][3], out[r]["cnt"], running=(s["rm"], s["rv"], s["tm"], s["tv"], s["it"]), update_running=True)
             ops.bn_bwd_peer_sum(ns, PART, FLAGS + 8, steps[r], out[r]["tot"][0], out[r]["tot"][1], out[r]["tot"][2], out[r]["tot"][3],
                                 mean=out[r]["v"][0], invstd=out[r]["v"][1], s2_raw=True)
+            # the same exchange folded into the BN-backward apply pass (its own flag slots), against peer_sum + apply
+            ops.bn_bwd_apply_peer(ns, PART, FLAGS + 16, steps[r], bw[r]["g"], None, bw[r]["y"], out[r]["v"][0], out[r]["v"][1],
+                                  out[r]["v"][2], out[r]["cnt"], bw[r]["dy_fused"], bw[r]["db"], bw[r]["dg"], fshift=out[r]["v"][3],
+                                  s2_raw=True)
+            ops.bn_bwd_apply(bw[r]["g"], None, bw[r]["y"], out[r]["v"][0], out[r]["v"][1], out[r]["v"][2], out[r]["tot"][0],
+                             out[r]["tot"][1], 1.0, bw[r]["dy_ref"], count_dev=out[r]["cnt"], fshift=out[r]["v"][3])
+        bw = [dict(g=torch.randn(1, 6, 10, C, generator=g).bfloat16(), y=torch.randn(1, 6, 10, C, generator=g).bfloat16(),
+                   dy_fused=torch.zeros(1, 6, 10, C, dtype=torch.bfloat16), dy_ref=torch.zeros(1, 6, 10, C, dtype=torch.bfloat16),
+                   db=torch.zeros(C), dg=torch.zeros(C)) for _ in range(world)]
         _both_ranks(rank_step)
+        for r in range(world):
+            assert torch.equal(bw[r]["dy_fused"], bw[r]["dy_ref"])
+            assert torch.allclose(bw[r]["db"], out[r]["tot"][2], rtol=1e-6, atol=1e-7)
+            assert torch.allclose(bw[r]["dg"], out[r]["tot"][3], rtol=1e-6, atol=1e-7)
         assert all(int(s) == step_no for s in steps)
         for r in range(world):
             ns = _arena_ns(arenas, r)
