@@ -1319,6 +1319,13 @@ int sseg_bn_bwd_apply_peer(void* const* bases, int world, int rank, long part_of
   rc = make_peer_table(&p.pt, bases, world, rank, "sseg_bn_bwd_apply_peer");
   if (rc) return rc;
   p.part_off = part_off, p.flag_off = flag_off, p.step = step, p.dbeta_out = dbeta_out;
+  // every block pays the handshake + one NVLink round trip before it streams: ONE wave of blocks (the pixel loop is
+  // grid-strided), or each further wave pays it again (measured: 4 waves cost +20 us per layer)
+  {
+    static const int waves = getenv("SSEG_PEER_APPLY_BLOCKS") ? atoi(getenv("SSEG_PEER_APPLY_BLOCKS")) : 2;
+    const int cap = (148 * waves + t.gy - 1) / t.gy;
+    if (t.gx > cap) t.gx = cap < 1 ? 1 : cap;
+  }
   launch_k(bn_bwd_kernel<true>, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("bn_bwd_apply_peer_kernel");
 }

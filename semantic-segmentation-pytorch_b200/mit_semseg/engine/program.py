@@ -144,9 +144,12 @@ class SegProgram:
         import os as _os
         self.fuse_bnbwd = _os.environ.get("SSEG_FUSE_BNBWD", "1") != "0"
         self.fuse_bnbwd_res = _os.environ.get("SSEG_FUSE_BNBWD_RES", "1") != "0"   # ... also for residual-block outputs
-        # multi-GPU: the SyncBN backward exchange (flag handshake + pooling of the partial sums out of peer memory) runs
-        # inside the BN-backward apply kernel instead of a kernel of its own (SSEG_PEER_FUSE_BWD=0: separate kernels)
-        self.peer_fuse_bwd = _os.environ.get("SSEG_PEER_FUSE_BWD", "1") != "0"
+        # multi-GPU, opt-in: the SyncBN backward exchange (flag handshake + pooling of the partial sums out of peer memory)
+        # inside the BN-backward apply kernel instead of a kernel of its own. Correct (dist_check, two-process tests) but
+        # SLOWER on 2 x B200: 7.50 ms/step (one wave of blocks) / 8.19 (four waves) against 6.91 with the one-block exchange
+        # kernel - every block of a full-GPU kernel then sits on the handshake + NVLink round trip, and the spinning blocks
+        # take the SM slots the side-stream weight-gradient GEMMs would use (profiles/r2_summary.md section 6)
+        self.peer_fuse_bwd = _os.environ.get("SSEG_PEER_FUSE_BWD", "0") != "0"
         # measured on B200: fusing finalize into apply does NOT pay (6.92 vs 6.79 ms/step): with programmatic dependent
         # launch the tiny finalize kernel already overlaps the conv's tail, while the fused prologue delays every
         # block's streaming phase. Kept as an opt-in.
@@ -736,10 +739,11 @@ class SegProgram:
     # ------------------------------------------------------------------------------------------ backward
     def _build_backward(self):
         self.bwd.append(lambda: self.gflat.zero_())
-        # The data-parallel gradient bucket (reference: backward of nn.DataParallel's Broadcast) as THREE
+        self._bucket_works = []
+        # The data-parallel gradient bucket (reference: backward of nn.DataParallel's Broadcast) as FOUR
         # NCCL all-reduces of contiguous slices of the flat fp32 gradient buffer, issued in backward order on the side
         # stream right behind the weight-gradient GEMMs that fill them, so they overlap the rest of the backward pass:
-        #   [ small (BN, biases) | encoder stem..layer3 | encoder layer4 | decoder ]
+        #   [ small (BN, biases) | encoder stem..layer2 | encoder layer3 | encoder layer4 | decoder ]
         buckets = []
         if self.overlap_relayout:
             self.bwd.append(self.join_side)   # the data-gradient operands were produced on the side stream
@@ -753,6 +757,14 @@ class SegProgram:
             end = self.gflat.numel()
             buckets = [(dec_ids, self.gflat[dec_off:end]), (dec_ids | l4_ids, self.gflat[l4_off:dec_off])]
             rest = self.gflat[:l4_off]
+            if hasattr(self.enc, "layer4") and hasattr(self.enc, "layer3") and self.dist is not None:
+                # a fourth slice (layer3: 28 MB of ResNet50's remaining 34 MB) keeps the all-reduce that is exposed at the
+                # very end of the step small
+                l3_ids = {id(m) for m in self.enc.layer3.modules()}
+                l3_off = off(l3_ids)
+                if 0 < l3_off < l4_off:
+                    buckets.append((dec_ids | l4_ids | l3_ids, self.gflat[l3_off:l4_off]))
+                    rest = self.gflat[:l3_off]
         # 1 / world_size (= the reference's mean over per-GPU losses, train.py:42) is applied ONCE, to the loss gradient
         # (LossRec.backward): every gradient of the step then comes out already divided, the bucket all-reduces sum them
         gtables = None
@@ -768,7 +780,10 @@ class SegProgram:
 
                 def close_bucket(sl=sl, gt=gt):
                     if self.dist is not None:
-                        self.dist.all_reduce(sl)
+                        # asynchronous: the collective runs on the communicator's own stream behind the side stream's
+                        # work so far, the weight-gradient GEMMs enqueued after it do NOT wait for it (a synchronous
+                        # call parks the side stream until the all-reduce has finished); joined at the end of the step
+                        self._bucket_works.append(self.dist.all_reduce(sl, async_op=True))
                 self.bwd.append(self.on_side(close_bucket))
             k = getattr(rec, "branch", None) if self.use_branches else None
             if isinstance(rec, AvgPoolRec):
@@ -790,6 +805,11 @@ class SegProgram:
         self.join_branches(into=self.bwd)
         self.bwd.append(self.join_side)
         if self.dist is not None:
+            def join_buckets():
+                for w in self._bucket_works:
+                    w.wait()       # NCCL: the current stream waits for the communicator's stream (capturable)
+                del self._bucket_works[:]
+            self.bwd.append(join_buckets)
             if buckets:
                 for _, sl in pending:  # (degenerate nets: buckets never closed)
                     self.bwd.append(lambda sl=sl: self.dist.all_reduce(sl))
