@@ -349,7 +349,10 @@ int sseg_peer_free(void* ptr);
 int sseg_peer_step(int* step, sseg_stream_t stream);
 /* Forward of the synchronised branch (lib/nn/modules/batchnorm.py:98-139) without a collective call: handshake with all
  * peers on flag slots [flag_off, flag_off + world), then pool [sum C | sqsum C | count] found at stats_off in EVERY
- * rank's arena and finish like sseg_bn_finalize(SSEG_BN_TRAIN_SYNC). count_out receives the pooled pixel count. */
+ * rank's arena and finish like sseg_bn_finalize(SSEG_BN_TRAIN_SYNC). count_out receives the pooled pixel count.
+ * update_running: 0 = leave the running statistics alone; 1 = advance the accumulators / running_iter and refresh
+ * running_mean / running_var (a second tiny launch); 2 = advance only - the caller refreshes them later with
+ * sseg_bn_running_from_tmp (e.g. on another stream, off the forward pass's dependency chain). */
 int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_off, long flag_off, const int* step,
                           const float* gamma, const float* beta, float eps, float momentum, int update_running,
                           float* running_mean, float* running_var, float* tmp_running_mean, float* tmp_running_var,

@@ -159,7 +159,9 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
                            running_iter, mean_out, invstd_out, scale, shift, count_out, C),
                   "bn_finalize_peer_kernel");
   count_launch(1);
-  if (rc == 0 && update_running) {
+  // update_running == 2: the accumulators and running_iter are advanced here, running_mean / running_var are refreshed by
+  // the caller (sseg_bn_running_from_tmp, off the forward pass's dependency chain)
+  if (rc == 0 && update_running == 1) {
     rc = check_cuda(launch_k(bn_running_from_tmp_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st,
                              (const float*)tmp_mean, (const float*)tmp_var, (const float*)running_iter, running_mean,
                              running_var, C),

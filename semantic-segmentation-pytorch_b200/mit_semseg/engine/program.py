@@ -149,6 +149,8 @@ class SegProgram:
         # SLOWER on 2 x B200: 7.50 ms/step (one wave of blocks) / 8.19 (four waves) against 6.91 with the one-block exchange
         # kernel - every block of a full-GPU kernel then sits on the handshake + NVLink round trip, and the spinning blocks
         # take the SM slots the side-stream weight-gradient GEMMs would use (profiles/r2_summary.md section 6)
+        self.defer_running = _os.environ.get("SSEG_DEFER_RUNNING", "1") != "0"
+        self.deferred_running = []
         self.peer_fuse_bwd = _os.environ.get("SSEG_PEER_FUSE_BWD", "0") != "0"
         # measured on B200: fusing finalize into apply does NOT pay (6.92 vs 6.79 ms/step): with programmatic dependent
         # launch the tiny finalize kernel already overlaps the conv's tail, while the fused prologue delays every
@@ -195,6 +197,16 @@ class SegProgram:
         self._alloc_params()
         self.img = torch.zeros(img_shape, device=self.dev, dtype=torch.float32) if part != "decoder" else None
         self._build_forward()
+        if self.deferred_running:
+            mods = list(self.deferred_running)
+
+            def refresh_running():
+                for m in mods:
+                    ops.bn_running_from_tmp(m._tmp_running_mean, m._tmp_running_var, m._running_iter, m.running_mean,
+                                            m.running_var)
+            self.fwd.append(self.on_side(refresh_running))
+            if not self.with_grad:
+                self.fwd.append(self.join_side)
         if self.with_grad:
             self._build_backward()
         elif self.peer is not None:
@@ -1038,9 +1050,15 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
         P.sinit[bns.stats_off + 2 * C] = float(count)
     if mode == ops.BN_TRAIN_SYNC and P.peer is not None:
         cnt_out = bns.tot[2 * Cp:2 * Cp + 1]
+        # running_mean / running_var (= accumulators / running_iter, batchnorm.py:136-137) are outputs of the step only: their
+        # refresh is collected and runs on the side stream after the forward pass instead of as a second launch per layer
+        # on the forward chain
+        defer = upd and P.defer_running
         P.fwd.append(lambda: ops.bn_finalize_peer(P.peer, bns.stats_off, bns.flag_off, P.peer_step, w, b, m.eps, mom,
                                                   mean, invstd, scale, shift, cnt_out, running=running,
-                                                  update_running=upd))
+                                                  update_running=upd, defer_running=defer))
+        if defer:
+            P.deferred_running.append(m)
     elif mode == ops.BN_TRAIN and out is not None and P.fuse_finalize and C == Cp:
         # single-GPU training: finalize fused into the apply kernel (one kernel boundary less per layer)
         rmean, rvar = (m.running_mean, m.running_var) if upd else (None, None)

@@ -725,8 +725,9 @@ class EmuLib:
             i.mul_(frac).add_(1)
             vec(tm, C).mul_(frac).add_(mean)
             vec(tv, C).mul_(frac).add_(sumvar / (cnt - 1))
-            vec(rm, C).copy_(vec(tm, C) / i)
-            vec(rv, C).copy_(vec(tv, C) / i)
+            if update == 1:
+                vec(rm, C).copy_(vec(tm, C) / i)
+                vec(rv, C).copy_(vec(tv, C) / i)
         g = vec(gamma, C) if _addr(gamma) else torch.ones(C)
         b = vec(beta, C) if _addr(beta) else torch.zeros(C)
         for ptr, val in ((mean_out, mean), (invstd_out, inv), (scale, g * inv), (shift, b - mean * g * inv)):
