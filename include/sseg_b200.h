@@ -363,6 +363,20 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
 int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
                          float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
                          int s2_raw, int C, sseg_stream_t stream);
+/* The same two exchanges with a PUSH protocol (the default of the step programs): rank r owns, in every rank's arena, the
+ * 8-byte slots [inbox_off/2 + r*n, +n) of the layer's inbox (n = 2C+1 forward, 2C backward; inbox_off in 4-byte units,
+ * even). Each thread sends its channel's partial sums to all peers as {fp32 value, int32 step} messages (plain 64-bit stores
+ * over NVLink, no fence, no separate flag) and polls the peers' messages in LOCAL memory until their tag is the current
+ * step: one NVLink one-way latency per exchange instead of flag + fence + a remote-load round trip. Results are
+ * bit-identical to the flag protocol's (same rank-ordered sums). Inbox space per layer: world * n * 8 bytes, zero at start. */
+int sseg_bn_finalize_peer_ll(void* const* bases, int world, int rank, long stats_off, long inbox_off, const int* step,
+                             const float* gamma, const float* beta, float eps, float momentum, int update_running,
+                             float* running_mean, float* running_var, float* tmp_running_mean, float* tmp_running_var,
+                             float* running_iter, float* mean_out, float* invstd_out, float* scale, float* shift,
+                             float* count_out, int C, sseg_stream_t stream);
+int sseg_bn_bwd_peer_sum_ll(void* const* bases, int world, int rank, long part_off, long inbox_off, const int* step,
+                            float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean,
+                            const float* invstd, int s2_raw, int C, sseg_stream_t stream);
 /* sseg_bn_bwd_peer_sum + sseg_bn_bwd_apply in ONE launch (one dependent kernel less per BatchNorm layer on the backward
  * chain of a multi-GPU step): every block runs the flag handshake, pools this layer's partial sums [s1 | s2] (at part_off /
  * part_off + C of every rank's arena; s2 raw when s2_raw) straight out of peer memory, applies

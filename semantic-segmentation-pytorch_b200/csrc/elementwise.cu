@@ -434,7 +434,10 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_kernel(const BnBwdParams p) {
     if (p.pt.world > 1) {
       // pooled sums of this block's channels: thread (tcol, trow < 8) fetches channel 8 * group + trow from every rank (all
       // loads of the thread in flight together), the block shares them through shared memory
-      __shared__ float pooled[2][256];
+      // (dynamic shared memory, 2 KB, passed by sseg_bn_bwd_apply_peer only: the CPU simulator models static __shared__
+      // arrays as one static object, which two "GPUs" of one test process would share)
+      SSEG_DYN_SMEM(pooled_raw);
+      float (*pooled)[256] = reinterpret_cast<float (*)[256]>(pooled_raw);
       peer_handshake(p.pt, p.flag_off, *p.step, blockIdx.x == 0 && blockIdx.y == 0);
       if (trow < 8 && active) {
         float a, b;
@@ -1326,7 +1329,7 @@ int sseg_bn_bwd_apply_peer(void* const* bases, int world, int rank, long part_of
     const int cap = (148 * waves + t.gy - 1) / t.gy;
     if (t.gx > cap) t.gx = cap < 1 ? 1 : cap;
   }
-  launch_k(bn_bwd_kernel<true>, dim3(dim3(t.gx, t.gy)), dim3(256), 0, (cudaStream_t)st, p);
+  launch_k(bn_bwd_kernel<true>, dim3(dim3(t.gx, t.gy)), dim3(256), 2 * 256 * sizeof(float), (cudaStream_t)st, p);
   LAUNCH_CHECK("bn_bwd_apply_peer_kernel");
 }
 

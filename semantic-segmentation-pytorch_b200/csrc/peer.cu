@@ -31,14 +31,27 @@ __global__ void __launch_bounds__(256) bn_finalize_peer_kernel(const PeerTable p
                                                                float* tmp_mean, float* tmp_var, float* running_iter,
                                                                float* __restrict__ mean_out, float* __restrict__ invstd_out,
                                                                float* __restrict__ scale, float* __restrict__ shift,
-                                                               float* __restrict__ count_out, int C) {
+                                                               float* __restrict__ count_out, int C, long inbox_off) {
   pdl_sync();
-  peer_handshake(pt, flag_off, *step_ptr, blockIdx.x == 0);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int cc = c < C ? c : 0;
-  float s, q;
-  peer_sum2(pt, stats_off + cc, stats_off + C + cc, &s, &q);   // in flight together with the count loads below
-  const float cnt = peer_sum(pt, stats_off + 2 * C);
+  float s, q, cnt;
+  if (inbox_off >= 0) {
+    // push protocol: no block-level handshake; every thread sends its channel's two sums (thread 0 also the pixel count) to
+    // all peers, then polls the peers' messages for the same slots in local memory
+    const int step = *step_ptr, n = 2 * C + 1;
+    const float* mine = pt.base[pt.rank] + stats_off;
+    const float ms = mine[cc], mq = mine[C + cc], mc = mine[2 * C];
+    if (c < C) ll_push(pt, inbox_off, n, c, ms, step), ll_push(pt, inbox_off, n, C + c, mq, step);
+    if (c == 0) ll_push(pt, inbox_off, n, 2 * C, mc, step);
+    s = ll_pool(pt, inbox_off, n, cc, ms, step);
+    q = ll_pool(pt, inbox_off, n, C + cc, mq, step);
+    cnt = ll_pool(pt, inbox_off, n, 2 * C, mc, step);
+  } else {
+    peer_handshake(pt, flag_off, *step_ptr, blockIdx.x == 0);
+    peer_sum2(pt, stats_off + cc, stats_off + C + cc, &s, &q);   // in flight together with the count loads below
+    cnt = peer_sum(pt, stats_off + 2 * C);
+  }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     *count_out = cnt;
     if (update_running) running_iter[0] = running_iter[0] * (1.f - momentum) + 1.f;
@@ -76,13 +89,24 @@ __global__ void __launch_bounds__(256) bn_bwd_peer_sum_kernel(const PeerTable pt
                                                               const int* step_ptr, float* __restrict__ s1_tot,
                                                               float* __restrict__ s2_tot, float* __restrict__ dbeta,
                                                               float* __restrict__ dgamma, const float* __restrict__ mean,
-                                                              const float* __restrict__ invstd, int s2_raw, int C) {
+                                                              const float* __restrict__ invstd, int s2_raw, int C,
+                                                              long inbox_off) {
   pdl_sync();
-  peer_handshake(pt, flag_off, *step_ptr, blockIdx.x == 0);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
   float a, b;
-  peer_sum2(pt, part_off + c, part_off + C + c, &a, &b);
+  if (inbox_off >= 0) {
+    if (c >= C) return;
+    const int step = *step_ptr, n = 2 * C;
+    const float* mine = pt.base[pt.rank] + part_off;
+    const float ma = mine[c], mb = mine[C + c];
+    ll_push(pt, inbox_off, n, c, ma, step), ll_push(pt, inbox_off, n, C + c, mb, step);
+    a = ll_pool(pt, inbox_off, n, c, ma, step);
+    b = ll_pool(pt, inbox_off, n, C + c, mb, step);
+  } else {
+    peer_handshake(pt, flag_off, *step_ptr, blockIdx.x == 0);
+    if (c >= C) return;
+    peer_sum2(pt, part_off + c, part_off + C + c, &a, &b);
+  }
   if (s2_raw) b = invstd[c] * (b - mean[c] * a);  // partials were sum g'*y (fused dgrad epilogue): convert to sum g'*xhat
   s1_tot[c] = a, s2_tot[c] = b;
   const float inv_w = 1.f / (float)pt.world;
@@ -142,11 +166,11 @@ int sseg_peer_step(int* step, sseg_stream_t st) {
   return check_cuda(launch_k(peer_step_kernel, dim3(1), dim3(32), 0, (cudaStream_t)st, step), "peer_step_kernel");
 }
 
-int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_off, long flag_off, const int* step,
-                          const float* gamma, const float* beta, float eps, float momentum, int update_running,
-                          float* running_mean, float* running_var, float* tmp_mean, float* tmp_var, float* running_iter,
-                          float* mean_out, float* invstd_out, float* scale, float* shift, float* count_out, int C,
-                          sseg_stream_t st) {
+static int bn_finalize_peer_impl(void* const* bases, int world, int rank, long stats_off, long flag_off, long inbox_off,
+                                 const int* step, const float* gamma, const float* beta, float eps, float momentum,
+                                 int update_running, float* running_mean, float* running_var, float* tmp_mean,
+                                 float* tmp_var, float* running_iter, float* mean_out, float* invstd_out, float* scale,
+                                 float* shift, float* count_out, int C, sseg_stream_t st) {
   PeerTable t;
   int rc = make_peer_table(&t, bases, world, rank, "sseg_bn_finalize_peer");
   if (rc) return rc;
@@ -156,7 +180,7 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
   const int grid = (C + 255) / 256;
   rc = check_cuda(launch_k(bn_finalize_peer_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)st, t, stats_off, flag_off,
                            step, gamma, beta, eps, momentum, update_running, running_mean, running_var, tmp_mean, tmp_var,
-                           running_iter, mean_out, invstd_out, scale, shift, count_out, C),
+                           running_iter, mean_out, invstd_out, scale, shift, count_out, C, inbox_off),
                   "bn_finalize_peer_kernel");
   count_launch(1);
   // update_running == 2: the accumulators and running_iter are advanced here, running_mean / running_var are refreshed by
@@ -171,6 +195,27 @@ int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_of
   return rc;
 }
 
+int sseg_bn_finalize_peer(void* const* bases, int world, int rank, long stats_off, long flag_off, const int* step,
+                          const float* gamma, const float* beta, float eps, float momentum, int update_running,
+                          float* running_mean, float* running_var, float* tmp_mean, float* tmp_var, float* running_iter,
+                          float* mean_out, float* invstd_out, float* scale, float* shift, float* count_out, int C,
+                          sseg_stream_t st) {
+  return bn_finalize_peer_impl(bases, world, rank, stats_off, flag_off, -1, step, gamma, beta, eps, momentum, update_running,
+                               running_mean, running_var, tmp_mean, tmp_var, running_iter, mean_out, invstd_out, scale,
+                               shift, count_out, C, st);
+}
+
+int sseg_bn_finalize_peer_ll(void* const* bases, int world, int rank, long stats_off, long inbox_off, const int* step,
+                             const float* gamma, const float* beta, float eps, float momentum, int update_running,
+                             float* running_mean, float* running_var, float* tmp_mean, float* tmp_var,
+                             float* running_iter, float* mean_out, float* invstd_out, float* scale, float* shift,
+                             float* count_out, int C, sseg_stream_t st) {
+  SSEG_REQUIRE(inbox_off >= 0 && inbox_off % 2 == 0, "sseg_bn_finalize_peer_ll: the inbox must be 8-byte aligned");
+  return bn_finalize_peer_impl(bases, world, rank, stats_off, 0, inbox_off, step, gamma, beta, eps, momentum, update_running,
+                               running_mean, running_var, tmp_mean, tmp_var, running_iter, mean_out, invstd_out, scale,
+                               shift, count_out, C, st);
+}
+
 int sseg_bn_running_from_tmp(const float* tmp_mean, const float* tmp_var, const float* running_iter, float* running_mean,
                              float* running_var, int C, sseg_stream_t st) {
   SSEG_REQUIRE(tmp_mean && tmp_var && running_iter && running_mean && running_var && C > 0, "sseg_bn_running_from_tmp: null");
@@ -180,9 +225,9 @@ int sseg_bn_running_from_tmp(const float* tmp_mean, const float* tmp_var, const 
                     "bn_running_from_tmp_kernel");
 }
 
-int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
-                         float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
-                         int s2_raw, int C, sseg_stream_t st) {
+static int bn_bwd_peer_sum_impl(void* const* bases, int world, int rank, long part_off, long flag_off, long inbox_off,
+                                const int* step, float* s1_tot, float* s2_tot, float* dbeta, float* dgamma,
+                                const float* mean, const float* invstd, int s2_raw, int C, sseg_stream_t st) {
   PeerTable t;
   int rc = make_peer_table(&t, bases, world, rank, "sseg_bn_bwd_peer_sum");
   if (rc) return rc;
@@ -190,8 +235,23 @@ int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off,
   SSEG_REQUIRE(!s2_raw || (mean && invstd), "sseg_bn_bwd_peer_sum: raw partials need mean and invstd");
   count_launch(1);
   return check_cuda(launch_k(bn_bwd_peer_sum_kernel, dim3((C + 255) / 256), dim3(256), 0, (cudaStream_t)st, t, part_off,
-                             flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean, invstd, s2_raw, C),
+                             flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean, invstd, s2_raw, C, inbox_off),
                     "bn_bwd_peer_sum_kernel");
+}
+
+int sseg_bn_bwd_peer_sum(void* const* bases, int world, int rank, long part_off, long flag_off, const int* step,
+                         float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean, const float* invstd,
+                         int s2_raw, int C, sseg_stream_t st) {
+  return bn_bwd_peer_sum_impl(bases, world, rank, part_off, flag_off, -1, step, s1_tot, s2_tot, dbeta, dgamma, mean, invstd,
+                              s2_raw, C, st);
+}
+
+int sseg_bn_bwd_peer_sum_ll(void* const* bases, int world, int rank, long part_off, long inbox_off, const int* step,
+                            float* s1_tot, float* s2_tot, float* dbeta, float* dgamma, const float* mean,
+                            const float* invstd, int s2_raw, int C, sseg_stream_t st) {
+  SSEG_REQUIRE(inbox_off >= 0 && inbox_off % 2 == 0, "sseg_bn_bwd_peer_sum_ll: the inbox must be 8-byte aligned");
+  return bn_bwd_peer_sum_impl(bases, world, rank, part_off, 0, inbox_off, step, s1_tot, s2_tot, dbeta, dgamma, mean, invstd,
+                              s2_raw, C, st);
 }
 
 }  // extern "C"

@@ -55,6 +55,48 @@ __device__ __forceinline__ void peer_sum2(const PeerTable& pt, long off_a, long 
   *a = sa, *b = sb;
 }
 
+// ---- push protocol ("LL": every 8-byte message carries its own flag). Rank r owns, in EVERY rank's arena, the slots
+// inbox[r * n + i], i < n, of a layer's inbox; a message is {fp32 value, int32 step}. The sender writes its n values into
+// all peers' arenas with plain 64-bit stores (fire and forget: no fence, no separate flag); the receiver polls its LOCAL
+// copies until their tag equals the step. One NVLink one-way latency per exchange instead of flag + fence + a remote
+// load round trip. Tags are step numbers (monotonic, never reset): a slot is rewritten one step later, after the reader
+// has long moved on (it has itself pushed every later layer of the step, which the writer had to receive first).
+__device__ __forceinline__ void ll_push(const PeerTable& pt, long inbox_off, int n, int i, float v, int step) {
+  const unsigned long long msg =
+      (static_cast<unsigned long long>(static_cast<unsigned int>(step)) << 32) | static_cast<unsigned long long>(__float_as_uint(v));
+#pragma unroll
+  for (int r = 0; r < SSEG_MAX_PEERS; ++r)
+    if (r < pt.world && r != pt.rank)
+      st_relaxed_sys_u64(reinterpret_cast<unsigned long long*>(pt.base[r] + inbox_off) + (long)pt.rank * n + i, msg);
+}
+// Sum over ranks of slot i (this rank's own value passed in `mine`), added in rank order: bit-identical on all ranks.
+// Bounded wait: a peer that never sends (dead / diverged rank) ends the launch with a trap after ~10 s of SM clocks.
+__device__ __forceinline__ float ll_pool(const PeerTable& pt, long inbox_off, int n, int i, float mine, int step) {
+  const unsigned long long* box = reinterpret_cast<const unsigned long long*>(pt.base[pt.rank] + inbox_off);
+  float v[SSEG_MAX_PEERS];
+  const long long t0 = clock64();
+#pragma unroll
+  for (int r = 0; r < SSEG_MAX_PEERS; ++r) {
+    v[r] = 0.f;
+    if (r < pt.world) {
+      if (r == pt.rank) {
+        v[r] = mine;
+      } else {
+        unsigned long long m = ld_relaxed_sys_u64(box + (long)r * n + i);
+        while (static_cast<int>(m >> 32) != step) {
+          if (clock64() - t0 > 20000000000ll) __trap();
+          m = ld_relaxed_sys_u64(box + (long)r * n + i);
+        }
+        v[r] = __uint_as_float(static_cast<unsigned int>(m));
+      }
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int r = 0; r < SSEG_MAX_PEERS; ++r) s += v[r];
+  return s;
+}
+
 int make_peer_table(PeerTable* t, void* const* bases, int world, int rank, const char* who);
 
 }  // namespace sseg

@@ -59,6 +59,15 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// 8-byte {value, tag} messages written into a peer's memory / polled in local memory (single-copy atomic 64-bit accesses)
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   unsigned int v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");

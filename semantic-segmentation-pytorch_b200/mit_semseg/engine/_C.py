@@ -149,6 +149,9 @@ _SIGNATURES = {
     "sseg_bn_bwd_apply_peer": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, c_long, _p, c_long, _p, c_long, _p, _p, _p,
                                _p, _p, _p, _p, c_long, _p, c_long, c_long, c_long, c_int, c_int, _p, _p, _p],
     "sseg_bn_bwd_peer_sum": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, _p, _p, _p, _p, c_int, c_int, _p],
+    "sseg_bn_finalize_peer_ll": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, c_float, c_float, c_int, _p, _p,
+                              _p, _p, _p, _p, _p, _p, _p, _p, c_int, _p],
+    "sseg_bn_bwd_peer_sum_ll": [POINTER(c_void_p), c_int, c_int, c_long, c_long, _p, _p, _p, _p, _p, _p, _p, c_int, c_int, _p],
     "sseg_maxpool_fwd": [_p, c_int, c_int, c_int, c_int, _p, _p, _p],
     "sseg_maxpool_bwd": [_p, _p, _p, c_int, c_int, c_int, c_int, _p],
     "sseg_avgpool_fwd": [_p, c_long, c_int, c_int, c_int, c_int, c_int, _p, _p],

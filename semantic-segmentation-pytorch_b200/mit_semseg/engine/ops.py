@@ -289,23 +289,24 @@ def peer_step(step):
 
 
 def bn_finalize_peer(arena, stats_off, flag_off, step, gamma, beta, eps, momentum, mean, invstd, scale, shift, count_out,
-                     running=None, update_running=False, defer_running=False):
+                     running=None, update_running=False, defer_running=False, ll=False):
     """defer_running: advance the accumulators only; the caller refreshes running_mean / running_var later
     (bn_running_from_tmp)."""
     rm = rv = tm = tv = it = None
     if running is not None:
         rm, rv, tm, tv, it = running
     upd = (2 if defer_running else 1) if update_running else 0
-    _C.check(_C.lib().sseg_bn_finalize_peer(arena.bases, arena.world, arena.rank, stats_off, flag_off, _C.ptr(step),
-                                            _C.ptr(gamma), _C.ptr(beta), eps, momentum, upd, _C.ptr(rm),
-                                            _C.ptr(rv), _C.ptr(tm), _C.ptr(tv), _C.ptr(it), _C.ptr(mean), _C.ptr(invstd),
-                                            _C.ptr(scale), _C.ptr(shift), _C.ptr(count_out), scale.numel(), _stream()))
+    fn = _C.lib().sseg_bn_finalize_peer_ll if ll else _C.lib().sseg_bn_finalize_peer   # ll: flag_off is the inbox offset
+    _C.check(fn(arena.bases, arena.world, arena.rank, stats_off, flag_off, _C.ptr(step), _C.ptr(gamma), _C.ptr(beta), eps,
+                momentum, upd, _C.ptr(rm), _C.ptr(rv), _C.ptr(tm), _C.ptr(tv), _C.ptr(it), _C.ptr(mean), _C.ptr(invstd),
+                _C.ptr(scale), _C.ptr(shift), _C.ptr(count_out), scale.numel(), _stream()))
 
 
-def bn_bwd_peer_sum(arena, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean=None, invstd=None, s2_raw=False):
-    _C.check(_C.lib().sseg_bn_bwd_peer_sum(arena.bases, arena.world, arena.rank, part_off, flag_off, _C.ptr(step),
-                                           _C.ptr(s1_tot), _C.ptr(s2_tot), _C.ptr(dbeta), _C.ptr(dgamma), _C.ptr(mean),
-                                           _C.ptr(invstd), int(s2_raw), s1_tot.numel(), _stream()))
+def bn_bwd_peer_sum(arena, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean=None, invstd=None, s2_raw=False,
+                    ll=False):
+    fn = _C.lib().sseg_bn_bwd_peer_sum_ll if ll else _C.lib().sseg_bn_bwd_peer_sum   # ll: flag_off is the inbox offset
+    _C.check(fn(arena.bases, arena.world, arena.rank, part_off, flag_off, _C.ptr(step), _C.ptr(s1_tot), _C.ptr(s2_tot),
+                _C.ptr(dbeta), _C.ptr(dgamma), _C.ptr(mean), _C.ptr(invstd), int(s2_raw), s1_tot.numel(), _stream()))
 
 
 def bn_apply(y, scale, shift, out, relu=True, res=None, rscale=None, rshift=None, chanmul=None, res_after_relu=False):

@@ -149,6 +149,9 @@ class SegProgram:
         # SLOWER on 2 x B200: 7.50 ms/step (one wave of blocks) / 8.19 (four waves) against 6.91 with the one-block exchange
         # kernel - every block of a full-GPU kernel then sits on the handshake + NVLink round trip, and the spinning blocks
         # take the SM slots the side-stream weight-gradient GEMMs would use (profiles/r2_summary.md section 6)
+        # SyncBN exchange protocol between the GPUs: push ("LL": 8-byte {value, step} messages into the peers' inboxes, one
+        # NVLink one-way latency) or, SSEG_PEER_LL=0, flag handshake + loads out of peer memory
+        self.peer_ll = _os.environ.get("SSEG_PEER_LL", "1") != "0"
         self.defer_running = _os.environ.get("SSEG_DEFER_RUNNING", "1") != "0"
         self.deferred_running = []
         self.peer_fuse_bwd = _os.environ.get("SSEG_PEER_FUSE_BWD", "0") != "0"
@@ -248,7 +251,11 @@ class SegProgram:
             # created with the FIRST program (step 1, all ranks together); later programs only look it up.
             from .peer import PeerArena
             nflag = 16 * len(self.bns) + 16
-            need = ns + npart + nflag
+            # push-protocol inboxes behind the flags (csrc/peer.cuh: 8-byte {value, step} messages, one slot range per
+            # sender): forward 2C+1 messages per layer and sender, backward 2Cp
+            world = self.dist.get_world_size()
+            ninbox = sum(2 * world * (_pad(2 * b.C + 1, 2) + 2 * b.Cp) for b in self.bns.values())
+            need = _pad(ns + npart + nflag, 4) + ninbox
             owner = self.seg if self.seg is not None else (self.enc if self.enc is not None else self.dec)
             shared = owner.__dict__.get("_b200_peer")
             if shared is None:
@@ -291,6 +298,7 @@ class SegProgram:
                     ogs += _pad(c.O, 4)
         os_, ov = 0, 0
         op_, ofl = ns, ns + npart
+        oin = _pad(ns + npart + 16 * len(self.bns) + 16, 4)   # inboxes: behind the flags and the step counter
         for b in self.bns.values():
             b.stats = self.sflat[os_:os_ + 2 * b.C + 1]
             b.stats_off = os_
@@ -306,6 +314,10 @@ class SegProgram:
                 b.part_off, b.flag_off = op_, ofl
                 op_ += 2 * b.Cp
                 ofl += 16
+                b.inbox_off = oin
+                oin += 2 * self.world * _pad(2 * b.C + 1, 2)
+                b.inbox_bwd_off = oin
+                oin += 2 * self.world * 2 * b.Cp
                 b.tot = torch.zeros(2 * b.Cp + 1, device=dev, dtype=torch.float32)  # s1_tot | s2_tot | pooled count
             b.mean, b.invstd, b.scale, b.shift = (self.vflat[ov + i * b.Cp: ov + (i + 1) * b.Cp] for i in range(4))
             ov += 4 * b.Cp
@@ -1054,9 +1066,10 @@ def _emit_bn_forward(P, bns, mode, count, y, out, relu, res, rscale, rshift, cha
         # refresh is collected and runs on the side stream after the forward pass instead of as a second launch per layer
         # on the forward chain
         defer = upd and P.defer_running
-        P.fwd.append(lambda: ops.bn_finalize_peer(P.peer, bns.stats_off, bns.flag_off, P.peer_step, w, b, m.eps, mom,
+        flag_or_inbox = bns.inbox_off if P.peer_ll else bns.flag_off
+        P.fwd.append(lambda: ops.bn_finalize_peer(P.peer, bns.stats_off, flag_or_inbox, P.peer_step, w, b, m.eps, mom,
                                                   mean, invstd, scale, shift, cnt_out, running=running,
-                                                  update_running=upd, defer_running=defer))
+                                                  update_running=upd, defer_running=defer, ll=P.peer_ll))
         if defer:
             P.deferred_running.append(m)
     elif mode == ops.BN_TRAIN and out is not None and P.fuse_finalize and C == Cp:
@@ -1097,8 +1110,10 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from
                                                        s2_raw=True))
         elif mode == ops.BN_TRAIN_SYNC and P.peer is not None:
             t1, t2, cnt = bns.tot[:C], bns.tot[C:2 * C], bns.tot[2 * C:2 * C + 1]
-            P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, t1, t2, bns.dbeta,
-                                                     bns.dgamma, mean=bns.mean, invstd=bns.invstd, s2_raw=True))
+            fo = bns.inbox_bwd_off if P.peer_ll else bns.flag_off + 8
+            P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, fo, P.peer_step, t1, t2, bns.dbeta,
+                                                     bns.dgamma, mean=bns.mean, invstd=bns.invstd, s2_raw=True,
+                                                     ll=P.peer_ll))
             P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, sc, t1, t2, count, dy, dres=dres,
                                                   count_dev=cnt, fshift=fs))
         else:
@@ -1123,8 +1138,9 @@ def _emit_bn_backward(P, bns, mode, count, g, a, y, dy, dres, chanmul, mask_from
                                                        bns.invstd, sc, cnt, dy, bns.dbeta, bns.dgamma, dres=dres,
                                                        chanmul=chanmul, fshift=fs))
             return
-        P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, bns.flag_off + 8, P.peer_step, t1, t2, bns.dbeta,
-                                                 bns.dgamma))
+        fo = bns.inbox_bwd_off if P.peer_ll else bns.flag_off + 8
+        P.bwd.append(lambda: ops.bn_bwd_peer_sum(P.peer, bns.part_off, fo, P.peer_step, t1, t2, bns.dbeta,
+                                                 bns.dgamma, ll=P.peer_ll))
         P.bwd.append(lambda: ops.bn_bwd_apply(g, a, y, bns.mean, bns.invstd, sc, t1, t2, count, dy, dres=dres,
                                               chanmul=chanmul, count_dev=cnt, fshift=fs))
         return

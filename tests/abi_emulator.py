@@ -734,6 +734,13 @@ class EmuLib:
             vec(ptr, C).copy_(val)
         return 0
 
+    # push-protocol variants: same pooled results (the emulator reads the partials out of every rank's arena either way)
+    def sseg_bn_finalize_peer_ll(self, bases, world, rank, stats_off, inbox_off, *rest):
+        return self.sseg_bn_finalize_peer(bases, world, rank, stats_off, 0, *rest)
+
+    def sseg_bn_bwd_peer_sum_ll(self, bases, world, rank, part_off, inbox_off, *rest):
+        return self.sseg_bn_bwd_peer_sum(bases, world, rank, part_off, 0, *rest)
+
     def sseg_bn_bwd_peer_sum(self, bases, world, rank, part_off, flag_off, step, s1_tot, s2_tot, dbeta, dgamma, mean, invstd,
                              s2_raw, C, stream):
         pr = self._Peers(bases, world)

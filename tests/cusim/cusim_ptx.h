@@ -51,6 +51,11 @@ inline int ld_acquire_sys(const int* p) {
   ::cusim::spin_pause();
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 }
+inline void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELAXED); }
+inline unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  ::cusim::spin_pause();
+  return __atomic_load_n(p, __ATOMIC_RELAXED);
+}
 inline unsigned int ld_acquire_gpu(const unsigned int* p) {
   ::cusim::spin_pause();
   return __atomic_load_n(p, __ATOMIC_ACQUIRE);

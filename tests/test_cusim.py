@@ -391,7 +391,7 @@ def test_peer_memory_syncbn_kernels_two_ranks(sim):
     ptrs, handles = [], []
     for r in range(world):        # every rank allocates its arena and exports a handle; the peers open it
         p, h = ctypes.c_void_p(), (ctypes.c_ubyte * 64)()
-        _C.check(lib.sseg_peer_alloc(4 * 4096, ctypes.byref(p), h))
+        _C.check(lib.sseg_peer_alloc(4 * 8192, ctypes.byref(p), h))
         ptrs.append(p), handles.append(h)
     opened = []
     for r in range(world):
@@ -399,9 +399,10 @@ def test_peer_memory_syncbn_kernels_two_ranks(sim):
         _C.check(lib.sseg_peer_open(handles[r], ctypes.byref(q)))
         assert q.value == ptrs[r].value        # one process here: the mapping is the allocation itself
         opened.append(q)
-    arenas = [torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * 4096).from_address(p.value))) for p in ptrs]
+    arenas = [torch.from_numpy(np.ctypeslib.as_array((ctypes.c_float * 8192).from_address(p.value))) for p in ptrs]
     assert all(float(a.abs().sum()) == 0.0 for a in arenas)        # zero-initialised
     STATS, PART, FLAGS = 0, 1024, 3000
+    INBOX, INBOX_B = 4100, 4100 + 2 * world * (2 * C + 2)   # push protocol: 8-byte {value, step} slots per sender
     gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
     steps = [torch.zeros(1, dtype=torch.int32) for _ in range(world)]
     state = [dict(rm=torch.zeros(C), rv=torch.ones(C), tm=torch.zeros(C), tv=torch.zeros(C), it=torch.zeros(1)) for _ in range(world)]
@@ -414,6 +415,7 @@ def test_peer_memory_syncbn_kernels_two_ranks(sim):
             arenas[r][STATS + 2 * C] = x.shape[0]
             arenas[r][PART:PART + 2 * C] = torch.randn(2 * C, generator=g)
         out = [dict(v=torch.zeros(4, C), cnt=torch.zeros(1), tot=torch.zeros(4, C)) for _ in range(world)]
+        ll = [dict(v=torch.zeros(4, C), cnt=torch.zeros(1), tot=torch.zeros(4, C)) for _ in range(world)]
 
         def rank_step(r):
             ns = _arena_ns(arenas, r)
@@ -423,6 +425,11 @@ def test_peer_memory_syncbn_kernels_two_ranks(sim):
                                  out[r]["v"][3], out[r]["cnt"], running=(s["rm"], s["rv"], s["tm"], s["tv"], s["it"]), update_running=True)
             ops.bn_bwd_peer_sum(ns, PART, FLAGS + 8, steps[r], out[r]["tot"][0], out[r]["tot"][1], out[r]["tot"][2], out[r]["tot"][3],
                                 mean=out[r]["v"][0], invstd=out[r]["v"][1], s2_raw=True)
+            # the push protocol (messages into the peers' inboxes, no flags): bit-identical totals
+            ops.bn_finalize_peer(ns, STATS, INBOX, steps[r], gamma, beta, 1e-5, 0.1, ll[r]["v"][0], ll[r]["v"][1], ll[r]["v"][2],
+                                 ll[r]["v"][3], ll[r]["cnt"], ll=True)
+            ops.bn_bwd_peer_sum(ns, PART, INBOX_B, steps[r], ll[r]["tot"][0], ll[r]["tot"][1], ll[r]["tot"][2], ll[r]["tot"][3],
+                                mean=ll[r]["v"][0], invstd=ll[r]["v"][1], s2_raw=True, ll=True)
             # the same exchange folded into the BN-backward apply pass (its own flag slots), against peer_sum + apply
             ops.bn_bwd_apply_peer(ns, PART, FLAGS + 16, steps[r], bw[r]["g"], None, bw[r]["y"], out[r]["v"][0], out[r]["v"][1],
                                   out[r]["v"][2], out[r]["cnt"], bw[r]["dy_fused"], bw[r]["db"], bw[r]["dg"], fshift=out[r]["v"][3],
@@ -434,6 +441,8 @@ def test_peer_memory_syncbn_kernels_two_ranks(sim):
                    db=torch.zeros(C), dg=torch.zeros(C)) for _ in range(world)]
         _both_ranks(rank_step)
         for r in range(world):
+            assert torch.equal(ll[r]["v"], out[r]["v"]) and torch.equal(ll[r]["tot"], out[r]["tot"])
+            assert ll[r]["cnt"].item() == out[r]["cnt"].item()
             assert torch.equal(bw[r]["dy_fused"], bw[r]["dy_ref"])
             assert torch.allclose(bw[r]["db"], out[r]["tot"][2], rtol=1e-6, atol=1e-7)
             assert torch.allclose(bw[r]["dg"], out[r]["tot"][3], rtol=1e-6, atol=1e-7)
