@@ -80,69 +80,111 @@ __global__ void grad_to_oihw_kernel(const float* __restrict__ g, long g_ld, int 
   }
 }
 
+// Flat index over [n][h][w][channel group] -> coordinates. 32-bit divisions whenever the index fits: a 64-bit integer
+// division costs ~100 instructions on the GPU, and four of them per 32 bytes of traffic made these memory-bound kernels
+// instruction-bound (maxpool backward: 40 us for a 50 MB pass).
+__device__ __forceinline__ void split_idx(long idx, int cg, int W, int H, int& c0, int& w, int& h, int& n) {
+  if (idx < (1L << 31)) {
+    unsigned r = (unsigned)idx;
+    unsigned q = r / (unsigned)cg;
+    c0 = (int)(r - q * (unsigned)cg) << 3, r = q;
+    q = r / (unsigned)W;
+    w = (int)(r - q * (unsigned)W), r = q;
+    q = r / (unsigned)H;
+    h = (int)(r - q * (unsigned)H), n = (int)q;
+  } else {
+    long r = idx;
+    c0 = (int)(r % cg) << 3, r /= cg;
+    w = (int)(r % W), r /= W;
+    h = (int)(r % H), n = (int)(r / H);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // stem conv: fp32 NCHW image [N,3,H,W] -> bf16 NHWC [N,Ho,Wo,64], 3x3 stride 2 pad 1 (models/resnet.py:100)
-// + batch-norm statistics. One thread per output pixel, 64 accumulators, weights broadcast from shared memory.
+// + batch-norm statistics. (0.06 % of the step's FLOPs, on CUDA cores - but on the step's critical path at both ends.)
+// One block per output row (n, ho), walking it in tiles of 64 pixels. The three input rows x three colour planes the tile
+// needs are staged in shared memory with coalesced loads; thread = 4 pixels x 8 output channels (register tile: 6 shared
+// loads per 32 FMAs; the first version's one-pixel-per-thread layout was bound by shared-memory loads and by 640 shuffles
+// per thread for the statistics: 60 us, now ~15). Every output is one FMA chain over the 27 taps in the same order as before.
+constexpr int kStemTW = 64;                 // output pixels per tile
+constexpr int kStemInW = 2 * kStemTW + 4;   // staged input columns (2*64 + 1 used), padded
 __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w,
                                                             __nv_bfloat16* __restrict__ out, float* __restrict__ ssum,
                                                             float* __restrict__ ssq, int N, int H, int W, int Ho,
                                                             int Wo) {
   pdl_sync();
-  __shared__ float sw[27][64];
+  __shared__ __align__(16) float sw[27][64];
+  __shared__ float s_in[9][kStemInW];
   __shared__ float bsum[64], bsq[64];
   for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) {
     const int co = i % 64, k = i / 64;  // k = ci*9 + r*3 + s, OIHW source index = co*27 + k
     sw[k][co] = w[co * 27 + k];
   }
   if (threadIdx.x < 64) bsum[threadIdx.x] = 0.f, bsq[threadIdx.x] = 0.f;
-  __syncthreads();
-  const long P = (long)N * Ho * Wo;
-  const long pidx = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  const bool valid = pidx < P;
-  float acc[64];
+  const int ho = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int cog = threadIdx.x & 7, pxg = threadIdx.x >> 3;   // 8 channel groups x 16 pixel groups
+  float st_s[8], st_q[8];
 #pragma unroll
-  for (int c = 0; c < 64; ++c) acc[c] = 0.f;
-  if (valid) {
-    const int wo = pidx % Wo;
-    const long r = pidx / Wo;
-    const int ho = r % Ho;
-    const int n = r / Ho;
+  for (int c = 0; c < 8; ++c) st_s[c] = 0.f, st_q[c] = 0.f;
+  for (int wo0 = 0; wo0 < Wo; wo0 += kStemTW) {
+    __syncthreads();  // the previous tile's readers are done (first pass: sw / bsum are complete)
+    for (int v = threadIdx.x; v < 9 * (2 * kStemTW + 1); v += blockDim.x) {
+      const int row = v / (2 * kStemTW + 1), col = v - row * (2 * kStemTW + 1);
+      const int ci = row / 3, kr = row - ci * 3;
+      const int h = 2 * ho + kr - 1, ww = 2 * wo0 - 1 + col;
+      float x = 0.f;
+      if (h >= 0 && h < H && ww >= 0 && ww < W) x = __ldg(img + (((long)n * 3 + ci) * H + h) * W + ww);
+      s_in[row][col] = x;
+    }
+    __syncthreads();
+    float acc[4][8];
 #pragma unroll
-    for (int ci = 0; ci < 3; ++ci) {
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int kr = 0; kr < 3; ++kr) {
-        const int h = 2 * ho + kr - 1;
+      for (int c = 0; c < 8; ++c) acc[i][c] = 0.f;
 #pragma unroll
-        for (int ks = 0; ks < 3; ++ks) {
-          const int ww = 2 * wo + ks - 1;
-          float x = 0.f;
-          if (h >= 0 && h < H && ww >= 0 && ww < W) x = __ldg(img + (((long)n * 3 + ci) * H + h) * W + ww);
-          const int k = ci * 9 + kr * 3 + ks;
+    for (int row = 0; row < 9; ++row) {
+      float xv[9];  // input columns 2*px0 .. 2*px0 + 8 of this (ci, kr) row: the three taps of four neighbouring pixels
 #pragma unroll
-          for (int c = 0; c < 64; ++c) acc[c] = fmaf(x, sw[k][c], acc[c]);
+      for (int q = 0; q < 9; ++q) xv[q] = s_in[row][8 * pxg + q];
+#pragma unroll
+      for (int ks = 0; ks < 3; ++ks) {
+        const float4 wa = *reinterpret_cast<const float4*>(&sw[row * 3 + ks][cog * 8]);
+        const float4 wb = *reinterpret_cast<const float4*>(&sw[row * 3 + ks][cog * 8 + 4]);
+        const float wv[8] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[i][c] = fmaf(xv[2 * i + ks], wv[c], acc[i][c]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int wo = wo0 + pxg * 4 + i;
+      if (wo < Wo) {
+        store8(out + (((long)n * Ho + ho) * Wo + wo) * 64 + cog * 8, acc[i]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float v = __bfloat162float(__float2bfloat16(acc[i][c]));  // statistics of the stored values
+          st_s[c] += v, st_q[c] = fmaf(v, v, st_q[c]);
         }
       }
     }
-    __nv_bfloat16* op = out + pidx * 64;
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = acc[g * 8 + e];
-      store8(op + g * 8, f);
-    }
   }
   if (ssum != nullptr) {
-    const int lane = threadIdx.x & 31;
+    // lanes of a warp: 8 channel groups x 4 pixel groups -> fold the pixel groups (lane bits 3, 4), then the 4 warps
 #pragma unroll
-    for (int c = 0; c < 64; ++c) {
-      float s = valid ? __bfloat162float(__float2bfloat16(acc[c])) : 0.f, q = s * s;  // statistics of the stored values
+    for (int c = 0; c < 8; ++c) {
 #pragma unroll
-      for (int off = 16; off >= 1; off >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, off);
-        q += __shfl_xor_sync(0xffffffffu, q, off);
+      for (int off = 8; off <= 16; off <<= 1) {
+        st_s[c] += __shfl_xor_sync(0xffffffffu, st_s[c], off);
+        st_q[c] += __shfl_xor_sync(0xffffffffu, st_q[c], off);
       }
-      if (lane == 0) atomicAdd(&bsum[c], s), atomicAdd(&bsq[c], q);
+    }
+    if ((threadIdx.x & 31) < 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) atomicAdd(&bsum[cog * 8 + c], st_s[c]), atomicAdd(&bsq[cog * 8 + c], st_q[c]);
     }
     __syncthreads();
     if (threadIdx.x < 64) atomicAdd(ssum + threadIdx.x, bsum[threadIdx.x]), atomicAdd(ssq + threadIdx.x, bsq[threadIdx.x]);
@@ -150,61 +192,72 @@ __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(const float* __restr
 }
 
 // stem conv weight gradient: dW[co][ci][r][s] += sum_pixels dy[p, co] * x[n, ci, 2ho+r-1, 2wo+s-1]
-// 256 threads = 64 co x 4 tap groups (7 of the 27 (ci,r,s) taps each). Tiles of 64 pixels are staged in shared memory
-// (dy tile 64x64 bf16, input patch 64x27 fp32), so the inner product runs from smem with conflict-free / broadcast reads.
+// One block per output row, tiles of 64 pixels: the input rows are staged as in the forward kernel, the dy tile (64 px x
+// 64 co, bf16) next to them. 256 threads = 4 pixel lanes x 16 channel groups (4 co) x 4 tap groups (8 of the 27 taps, padded
+// to 32): a 4 x 8 register tile per thread, 9 shared loads per 32 FMAs (the first version: 8 per 7, and 64-bit index
+// arithmetic per staged element: 110 us at the very end of the step). Pixel lanes are folded with shuffles at the end.
 __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img,
                                                               const __nv_bfloat16* __restrict__ dy,
-                                                              float* __restrict__ dw, int N, int H, int W, int Ho, int Wo,
-                                                              int pix_per_block) {
+                                                              float* __restrict__ dw, int N, int H, int W, int Ho, int Wo) {
   pdl_sync();
-  __shared__ __nv_bfloat16 s_dy[64][64];
-  __shared__ float s_x[64][28];
-  const int co = threadIdx.x & 63, grp = threadIdx.x >> 6;
-  float acc[7];
+  __shared__ __align__(16) __nv_bfloat16 s_dy[kStemTW][96];   // rows padded to 192 B: the 4 pixel lanes hit disjoint banks
+  __shared__ float s_in[9 * kStemInW + 8];
+  const int ho = blockIdx.x % Ho, n = blockIdx.x / Ho;
+  const int pxl = threadIdx.x & 3, cog = (threadIdx.x >> 2) & 15, tg = threadIdx.x >> 6;
+  int off[8];   // shared-memory offset of tap k = tg*8 + j for pixel 0: row (ci, kr) * pitch + ks
 #pragma unroll
-  for (int j = 0; j < 7; ++j) acc[j] = 0.f;
-  const long P = (long)N * Ho * Wo;
-  const long p0 = (long)blockIdx.x * pix_per_block;
-  const long p1 = min(p0 + pix_per_block, P);
-  for (long base = p0; base < p1; base += 64) {
-    const int npx = (int)min((long)64, p1 - base);
+  for (int j = 0; j < 8; ++j) {
+    const int k = tg * 8 + j;
+    off[j] = k < 27 ? (k / 3) * kStemInW + (k % 3) : 0;
+  }
+  float acc[4][8];
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[c][j] = 0.f;
+  for (int wo0 = 0; wo0 < Wo; wo0 += kStemTW) {
+    const int npx = min(kStemTW, Wo - wo0);
     __syncthreads();
-    // dy tile: 64 px x 64 co bf16 = 8 KB, 16-byte vectors
-    for (int v = threadIdx.x; v < 64 * 8; v += 256) {
+    for (int v = threadIdx.x; v < 9 * (2 * kStemTW + 1); v += blockDim.x) {
+      const int row = v / (2 * kStemTW + 1), col = v - row * (2 * kStemTW + 1);
+      const int ci = row / 3, kr = row - ci * 3;
+      const int h = 2 * ho + kr - 1, ww = 2 * wo0 - 1 + col;
+      float x = 0.f;
+      if (h >= 0 && h < H && ww >= 0 && ww < W) x = __ldg(img + (((long)n * 3 + ci) * H + h) * W + ww);
+      s_in[row * kStemInW + col] = x;
+    }
+    for (int v = threadIdx.x; v < kStemTW * 8; v += blockDim.x) {
       const int px = v >> 3, part = v & 7;
-      uint4 q = make_uint4(0, 0, 0, 0);
-      if (px < npx) q = *reinterpret_cast<const uint4*>(dy + (base + px) * 64 + part * 8);
+      uint4 q = make_uint4(0, 0, 0, 0);   // pixels beyond the row contribute zeros
+      if (px < npx) q = *reinterpret_cast<const uint4*>(dy + (((long)n * Ho + ho) * Wo + wo0 + px) * 64 + part * 8);
       *reinterpret_cast<uint4*>(&s_dy[px][part * 8]) = q;
     }
-    for (int v = threadIdx.x; v < 64 * 27; v += 256) {
-      const int px = v / 27, k = v % 27;
-      float x = 0.f;
-      if (px < npx) {
-        const long p = base + px;
-        const int wo = p % Wo;
-        const long r = p / Wo;
-        const int ho = r % Ho;
-        const int n = r / Ho;
-        const int ci = k / 9, kr = (k % 9) / 3, ks = k % 3;
-        const int h = 2 * ho + kr - 1, ww = 2 * wo + ks - 1;
-        if (h >= 0 && h < H && ww >= 0 && ww < W) x = __ldg(img + (((long)n * 3 + ci) * H + h) * W + ww);
-      }
-      s_x[px][k] = x;
-    }
-    if (threadIdx.x < 64) s_x[threadIdx.x][27] = 0.f;
     __syncthreads();
 #pragma unroll 4
-    for (int px = 0; px < 64; ++px) {
-      const float g = __bfloat162float(s_dy[px][co]);
+    for (int px = pxl; px < kStemTW; px += 4) {
+      const uint2 gq = *reinterpret_cast<const uint2*>(&s_dy[px][cog * 4]);
+      const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq.x));
+      const float2 g23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq.y));
+      const float g[4] = {g01.x, g01.y, g23.x, g23.y};
+      float x[8];
 #pragma unroll
-      for (int j = 0; j < 7; ++j) acc[j] = fmaf(g, s_x[px][grp * 7 + j], acc[j]);
+      for (int j = 0; j < 8; ++j) x[j] = s_in[off[j] + 2 * px];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[c][j] = fmaf(g[c], x[j], acc[c][j]);
     }
   }
 #pragma unroll
-  for (int j = 0; j < 7; ++j) {
-    const int k = grp * 7 + j;
-    if (k < 27) atomicAdd(dw + co * 27 + k, acc[j]);
-  }
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = acc[c][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      const int k = tg * 8 + j;
+      if (pxl == 0 && k < 27) atomicAdd(dw + (cog * 4 + c) * 27 + k, v);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -549,12 +602,8 @@ __global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfl
   const int cg = C >> 3;
   const long total = (long)N * Ho * Wo * cg;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (i % cg) << 3;
-    long r = i / cg;
-    const int wo = r % Wo;
-    r /= Wo;
-    const int ho = r % Ho;
-    const int n = r / Ho;
+    int c0, wo, ho, n;
+    split_idx(i, cg, Wo, Ho, c0, wo, ho, n);
     float best[8];
     int bidx[8];
 #pragma unroll
@@ -591,12 +640,8 @@ __global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const
   const int cg = C >> 3;
   const long total = (long)N * H * W * cg;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int c0 = (i % cg) << 3;
-    long r = i / cg;
-    const int w = r % W;
-    r /= W;
-    const int h = r % H;
-    const int n = r / H;
+    int c0, w, h, n;
+    split_idx(i, cg, W, H, c0, w, h, n);
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -680,45 +725,75 @@ struct AvgPoolBwdParams {
   long dx_ld;
   int N, H, W, C;
 };
-__global__ void avgpool_bwd_kernel(const AvgPoolBwdParams p) {
+// One block = one image row segment (n, h, kAvgWT consecutive w): the bins of every scale that contain row h are found once
+// per block, and all index arithmetic is 32-bit (the first version spent its time in 64-bit divisions: 143 us for a 67 MB
+// pass). Threads: channel groups fastest (16-byte vectors, coalesced), the remaining lanes walk the pixels of the segment.
+constexpr int kAvgWT = 16;
+__global__ void __launch_bounds__(256) avgpool_bwd_kernel(const AvgPoolBwdParams p) {
   pdl_sync();
   const int cg = p.C >> 3;
-  const long total = (long)p.N * p.H * p.W * cg;
-  for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c0 = (idx % cg) << 3;
-    long r = idx / cg;
-    const int w = r % p.W;
-    r /= p.W;
-    const int h = r % p.H;
-    const int n = r / p.H;
-    const long pix = ((long)n * p.H + h) * p.W + w;
-    float acc[8];
-    if (p.base)
-      load8(p.base + pix * p.base_ld + c0, acc);
-    else {
+  const int wtiles = (p.W + kAvgWT - 1) / kAvgWT;
+  int b = blockIdx.x;
+  const int w_base = (b % wtiles) * kAvgWT;
+  b /= wtiles;
+  const int h = b % p.H, n = b / p.H;
+  // rows of bins containing h: candidates ic-1 .. ic+1 around ic = floor(h*S/H) (ATen's adaptive bins
+  // [floor(i*H/S), ceil((i+1)*H/S)) overlap their neighbours by at most one row)
+  int bi[4][3], bh[4][3];   // bin row index, bin height (0 = not a bin of this row)
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-    }
-    for (int k = 0; k < p.nscales; ++k) {
-      const int S = p.scales[k];
-      // candidate bins: i with floor(i*H/S) <= h < ceil((i+1)*H/S)
-      const int ic = (int)(((long)h * S) / p.H);
-      for (int i = max(ic - 1, 0); i <= min(ic + 1, S - 1); ++i) {
+  for (int k = 0; k < 4; ++k) {
+    const int S = k < p.nscales ? p.scales[k] : 1;
+    const int ic = (h * S) / p.H;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const int i = ic - 1 + d;
+      bi[k][d] = i, bh[k][d] = 0;
+      if (k < p.nscales && i >= 0 && i < S) {
         const int h0 = (i * p.H) / S, h1 = ((i + 1) * p.H + S - 1) / S;
-        if (h < h0 || h >= h1) continue;
-        const int jc = (int)(((long)w * S) / p.W);
-        for (int j = max(jc - 1, 0); j <= min(jc + 1, S - 1); ++j) {
-          const int w0 = (j * p.W) / S, w1 = ((j + 1) * p.W + S - 1) / S;
-          if (w < w0 || w >= w1) continue;
-          float g[8];
-          load8(p.dpool[k] + (((long)n * S + i) * S + j) * p.C + c0, g);
-          const float inv = 1.f / ((h1 - h0) * (w1 - w0));
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] += g[e] * inv;
-        }
+        if (h >= h0 && h < h1) bh[k][d] = h1 - h0;
       }
     }
-    store8(p.dx + pix * p.dx_ld + c0, acc);
+  }
+  int cgb = cg < 256 ? cg : 256;
+  while (256 % cgb != 0) --cgb;
+  const int tcol = threadIdx.x % cgb, trow = threadIdx.x / cgb, lanes_w = 256 / cgb;
+  for (int cgi = tcol; cgi < cg; cgi += cgb) {
+    const int c0 = cgi << 3;
+    for (int wl = trow; wl < kAvgWT; wl += lanes_w) {
+      const int w = w_base + wl;
+      if (w >= p.W) break;
+      const long pix = ((long)n * p.H + h) * p.W + w;
+      float acc[8];
+      if (p.base)
+        load8(p.base + pix * p.base_ld + c0, acc);
+      else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (k >= p.nscales) break;
+        const int S = p.scales[k];
+        const int jc = (w * S) / p.W;
+#pragma unroll
+        for (int dj = 0; dj < 3; ++dj) {
+          const int j = jc - 1 + dj;
+          if (j < 0 || j >= S) continue;
+          const int w0 = (j * p.W) / S, w1 = ((j + 1) * p.W + S - 1) / S;
+          if (w < w0 || w >= w1) continue;
+#pragma unroll
+          for (int d = 0; d < 3; ++d) {
+            if (bh[k][d] == 0) continue;
+            float g[8];
+            load8(p.dpool[k] + (((long)n * S + bi[k][d]) * S + j) * p.C + c0, g);
+            const float inv = 1.f / (bh[k][d] * (w1 - w0));
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += g[e] * inv;
+          }
+        }
+      }
+      store8(p.dx + pix * p.dx_ld + c0, acc);
+    }
   }
 }
 
@@ -739,12 +814,8 @@ __global__ void bilinear_fwd_kernel(const __nv_bfloat16* __restrict__ x, long x_
   const int cg = C >> 3;
   const long total = (long)N * Ho * Wo * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c0 = (idx % cg) << 3;
-    long r = idx / cg;
-    const int wo = r % Wo;
-    r /= Wo;
-    const int ho = r % Ho;
-    const int n = r / Ho;
+    int c0, wo, ho, n;
+    split_idx(idx, cg, Wo, Ho, c0, wo, ho, n);
     int h0, h1, w0, w1;
     float lh, lw;
     bilinear_coeff(ho, Hi, Ho, h0, h1, lh);
@@ -784,12 +855,8 @@ __global__ void __launch_bounds__(256) sum_terms_kernel(const SumTermsParams p) 
   const int cg = p.C >> 3;
   const long total = (long)p.N * p.Ho * p.Wo * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c0 = (idx % cg) << 3;
-    long r = idx / cg;
-    const int wo = r % p.Wo;
-    r /= p.Wo;
-    const int ho = r % p.Ho;
-    const int n = r / p.Ho;
+    int c0, wo, ho, n;
+    split_idx(idx, cg, p.Wo, p.Ho, c0, wo, ho, n);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < SSEG_MAX_SUM_TERMS; ++k) {
@@ -885,12 +952,8 @@ __global__ void bilinear_bwd_w_kernel(const __nv_bfloat16* __restrict__ dout, lo
   const int cg = C >> 3;
   const long total = (long)N * Ho * Wi * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c0 = (idx % cg) << 3;
-    long r = idx / cg;
-    const int wi = r % Wi;
-    r /= Wi;
-    const int ho = r % Ho;
-    const int n = r / Ho;
+    int c0, wi, ho, n;
+    split_idx(idx, cg, Wi, Ho, c0, wi, ho, n);
     int lo, hi;
     bilinear_src_window(wi, Wi, Wo, lo, hi);
     float acc[8];
@@ -921,12 +984,8 @@ __global__ void bilinear_bwd_h_kernel(const float* __restrict__ tmp, int N, int 
   const int cg = C >> 3;
   const long total = (long)N * Hi * Wi * cg;
   for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int c0 = (idx % cg) << 3;
-    long r = idx / cg;
-    const int wi = r % Wi;
-    r /= Wi;
-    const int hi = r % Hi;
-    const int n = r / Hi;
+    int c0, wi, hi, n;
+    split_idx(idx, cg, Wi, Hi, c0, wi, hi, n);
     int lo, hi_;
     bilinear_src_window(hi, Hi, Ho, lo, hi_);
     float acc[8];
@@ -1184,8 +1243,8 @@ int sseg_stem_conv_fwd(const float* img, int N, int H, int W, const float* w, vo
   SSEG_REQUIRE(img && w && out, "sseg_stem_conv_fwd: null argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long P = (long)N * Ho * Wo;
-  launch_k(stem_conv_fwd_kernel, dim3((int)((P + 127) / 128)), dim3(128), 0, (cudaStream_t)st, img, w, (__nv_bfloat16*)out, stat_sum,
-                                                                             stat_sqsum, N, H, W, Ho, Wo);
+  launch_k(stem_conv_fwd_kernel, dim3(N * Ho), dim3(128), 0, (cudaStream_t)st, img, w, (__nv_bfloat16*)out, stat_sum, stat_sqsum, N, H,
+           W, Ho, Wo);
   LAUNCH_CHECK("stem_conv_fwd_kernel");
 }
 
@@ -1193,9 +1252,7 @@ int sseg_stem_conv_wgrad(const float* img, int N, int H, int W, const void* dy, 
   SSEG_REQUIRE(img && dy && dw, "sseg_stem_conv_wgrad: null argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long P = (long)N * Ho * Wo;
-  const int ppb = 256;
-  launch_k(stem_conv_wgrad_kernel, dim3((int)((P + ppb - 1) / ppb)), dim3(256), 0, (cudaStream_t)st, img, (const __nv_bfloat16*)dy, dw, N,
-                                                                                   H, W, Ho, Wo, ppb);
+  launch_k(stem_conv_wgrad_kernel, dim3(N * Ho), dim3(256), 0, (cudaStream_t)st, img, (const __nv_bfloat16*)dy, dw, N, H, W, Ho, Wo);
   LAUNCH_CHECK("stem_conv_wgrad_kernel");
 }
 
@@ -1365,7 +1422,7 @@ int sseg_avgpool_bwd(const void* base, long base_ld, const void* const* dpool, c
   p.base = (const __nv_bfloat16*)base, p.base_ld = base_ld;
   for (int k = 0; k < nscales; ++k) p.dpool[k] = (const __nv_bfloat16*)dpool[k], p.scales[k] = scales[k];
   p.nscales = nscales, p.dx = (__nv_bfloat16*)dx, p.dx_ld = dx_ld, p.N = N, p.H = H, p.W = W, p.C = C;
-  launch_k(avgpool_bwd_kernel, dim3(grid_for((long)N * H * W * (C / 8), 256)), dim3(256), 0, (cudaStream_t)st, p);
+  launch_k(avgpool_bwd_kernel, dim3(N * H * ((W + kAvgWT - 1) / kAvgWT)), dim3(256), 0, (cudaStream_t)st, p);
   LAUNCH_CHECK("avgpool_bwd_kernel");
 }
 

@@ -177,6 +177,7 @@ class SegProgram:
         # layers and ALL data-gradient operands are produced on the side stream while the stem / first stages run, and
         # the gradient re-layout of a bucket follows its weight-gradient GEMMs on the side stream instead of the end.
         self.overlap_relayout = _os.environ.get("SSEG_OVERLAP_RELAYOUT", "0") == "1" and part == "full"
+        self.split_prep = _os.environ.get("SSEG_SPLIT_PREP", "1") != "0" and not self.overlap_relayout
         # conv + train-mode BN (+shortcut, ReLU, dropout) as ONE persistent kernel with an in-kernel grid barrier
         # (sseg_conv_bn_train) for every layer whose tiles fit the SMs' tensor memory; single-GPU F.batch_norm branch only.
         # Opt-in until it has run on B200.
@@ -367,6 +368,15 @@ class SegProgram:
                 c.pg = c.gw.view_as(c.mod.weight)
         self._late_convs, self._late_pending = set(), False
         if not self.overlap_relayout:
+            if self.with_grad and self.split_prep:
+                # the data-gradient operands (the transposing half of the pass) are first read ~2 ms later, by the backward
+                # pass: they are produced on the side stream while the forward pass runs, only the forward operands (a
+                # plain cast of the channels-last masters) stay in front of the stem
+                self.wtable = ops.WeightTable([self._wentry(c, wd=False) for c in convs], self.dev)
+                self.wtable_d = ops.WeightTable([self._wentry(c, wf=False) for c in convs], self.dev)
+                self.fwd.append(self.wtable.prep)
+                self.fwd.append(self.on_side(self.wtable_d.prep))
+                return
             self.wtable = ops.WeightTable([self._wentry(c) for c in convs], self.dev)
             self.fwd.append(self.wtable.prep)
             return
@@ -769,7 +779,7 @@ class SegProgram:
         # stream right behind the weight-gradient GEMMs that fill them, so they overlap the rest of the backward pass:
         #   [ small (BN, biases) | encoder stem..layer2 | encoder layer3 | encoder layer4 | decoder ]
         buckets = []
-        if self.overlap_relayout:
+        if self.overlap_relayout or self.split_prep:
             self.bwd.append(self.join_side)   # the data-gradient operands were produced on the side stream
         if (self.dist is not None or self.overlap_relayout) and self.enc is not None and self.dec is not None:
             dec_ids = {id(m) for m in self.dec.modules()}

@@ -46,10 +46,11 @@ def test_prep_weight_and_grad_layout():
     _close(out, ref, 1e-6, "grad_to_oihw")
 
 
-def test_stem_conv_fwd_and_wgrad():
+@pytest.mark.parametrize("H,W", [(70, 96), (33, 300), (64, 256)])   # one partial tile of the 64-pixel row tiles / several
+def test_stem_conv_fwd_and_wgrad(H, W):
     from mit_semseg.engine import ops
     g = _gen(1)
-    img = torch.randn(2, 3, 70, 96, device=DEV, generator=g)
+    img = torch.randn(2, 3, H, W, device=DEV, generator=g)
     w = torch.randn(64, 3, 3, 3, device=DEV, generator=g) * 0.2
     ref = F.conv2d(img, w, stride=2, padding=1)
     ho, wo = ref.shape[2:]
