@@ -266,6 +266,10 @@ typedef struct {
   int reserved;
 } sseg_weight_desc_t;
 int sseg_prep_conv_weights_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, sseg_stream_t stream);
+/* The same pass on at most max_blocks thread blocks (0 = one block per tile): a thin grid for a side stream, so that the
+ * pass does not keep the main stream's kernels waiting behind thousands of pending blocks. */
+int sseg_prep_conv_weights_batched_ex(const sseg_weight_desc_t* table_dev, int n, int total_tiles, int max_blocks,
+                                      sseg_stream_t stream);
 int sseg_grads_to_oihw_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, float scale,
                                sseg_stream_t stream);
 

@@ -29,12 +29,16 @@ __device__ __forceinline__ const sseg_weight_desc_t* find_desc(const sseg_weight
 // i-tiles handled by one CTA: pointwise convs (T = 1) have tiny 32x32 tiles, so a CTA walks 8 of them
 __host__ __device__ inline int i_tiles_per_cta(int T) { return T == 1 ? 8 : 1; }
 
+// The grid may be smaller than the number of tiles (blocks then walk the tiles with a grid stride): a thin grid on a side
+// stream leaves the SMs to the main stream's kernels - a launch with thousands of pending blocks would make every later
+// kernel of the other stream wait until its last block has been dispatched.
 __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_desc_t* __restrict__ table, int n,
-                                                              int mode, float scale) {
+                                                              int total_tiles, int mode, float scale) {
   pdl_sync();
   __shared__ float tile[kTile][kTile * kMaxT + 1];
+  for (int tile_id = blockIdx.x; tile_id < total_tiles; tile_id += gridDim.x) {
   int local;
-  const sseg_weight_desc_t* d = find_desc(table, n, blockIdx.x, local);
+  const sseg_weight_desc_t* d = find_desc(table, n, tile_id, local);
   const int O = d->O, I = d->I, T = d->T;
   const int tiles_i = (I + kTile - 1) / kTile;
   const int rep = i_tiles_per_cta(T);
@@ -47,7 +51,25 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
   const int row = ni * T;
   __syncthreads();  // the shared tile is reused across iterations
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (mode == 0 && d->reserved == 1) {
+  if (mode == 0 && d->wd == nullptr && d->wf != nullptr && (d->reserved == 1 || T == 1) && (ni & 7) == 0 && (I & 7) == 0 &&
+      (d->fwd_ld & 7) == 0) {
+    // ---- forward operand only, rows of i contiguous in the master ([O][T][I], or OIHW with T = 1): a plain cast, 8
+    //      elements per thread and step straight from registers (two 16-byte loads -> one 16-byte store), no staging
+    const int nv = ni >> 3;
+    const float* w = d->w;
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d->wf);
+    for (int v = threadIdx.x; v < no * T * nv; v += 256) {
+      const int iv = v % nv, r = v / nv;
+      const int t = r % T, ol = r / T;
+      const float* src = w + ((long)(o0 + ol) * T + t) * I + i0 + iv * 8;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      uint4 q;
+      __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&q);
+      h[0] = __floats2bfloat162_rn(a.x, a.y), h[1] = __floats2bfloat162_rn(a.z, a.w);
+      h[2] = __floats2bfloat162_rn(b.x, b.y), h[3] = __floats2bfloat162_rn(b.z, b.w);
+      *reinterpret_cast<uint4*>(wf + (long)(o0 + ol) * d->fwd_ld + (long)t * I + i0 + iv * 8) = q;
+    }
+  } else if (mode == 0 && d->reserved == 1) {
     // ---- channels-last master [O][T][I]: rows of 32 consecutive i (128 B) per (o, t); tile[ol][t * 32 + il]
     const float* w = d->w;
     for (int ol = warp; ol < no; ol += 8) {
@@ -128,26 +150,33 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
     }
   }
   }  // i-tile loop
+  }  // grid-stride loop over the tiles
 }
 
 }  // namespace sseg
 
 using namespace sseg;
 
-static int launch_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, int mode, float scale,
-                          cudaStream_t st, const char* who) {
-  SSEG_REQUIRE(table_dev != nullptr && n >= 1 && total_tiles >= 1, "%s: bad argument", who);
-  launch_k(weights_batched_kernel, dim3(total_tiles), dim3(256), 0, st, table_dev, n, mode, scale);
+static int launch_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, int max_blocks, int mode,
+                          float scale, cudaStream_t st, const char* who) {
+  SSEG_REQUIRE(table_dev != nullptr && n >= 1 && total_tiles >= 1 && max_blocks >= 0, "%s: bad argument", who);
+  const int grid = (max_blocks > 0 && max_blocks < total_tiles) ? max_blocks : total_tiles;
+  launch_k(weights_batched_kernel, dim3(grid), dim3(256), 0, st, table_dev, n, total_tiles, mode, scale);
   count_launch(1);
   return check_cuda(cudaGetLastError(), who);
 }
 
 extern "C" int sseg_prep_conv_weights_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles,
                                               sseg_stream_t st) {
-  return launch_batched(table_dev, n, total_tiles, 0, 1.f, (cudaStream_t)st, "sseg_prep_conv_weights_batched");
+  return launch_batched(table_dev, n, total_tiles, 0, 0, 1.f, (cudaStream_t)st, "sseg_prep_conv_weights_batched");
+}
+
+extern "C" int sseg_prep_conv_weights_batched_ex(const sseg_weight_desc_t* table_dev, int n, int total_tiles,
+                                                 int max_blocks, sseg_stream_t st) {
+  return launch_batched(table_dev, n, total_tiles, max_blocks, 0, 1.f, (cudaStream_t)st, "sseg_prep_conv_weights_batched_ex");
 }
 
 extern "C" int sseg_grads_to_oihw_batched(const sseg_weight_desc_t* table_dev, int n, int total_tiles, float scale,
                                           sseg_stream_t st) {
-  return launch_batched(table_dev, n, total_tiles, 1, scale, (cudaStream_t)st, "sseg_grads_to_oihw_batched");
+  return launch_batched(table_dev, n, total_tiles, 0, 1, scale, (cudaStream_t)st, "sseg_grads_to_oihw_batched");
 }

@@ -123,6 +123,7 @@ _SIGNATURES = {
     "sseg_conv_wgrad": [POINTER(Geom), POINTER(Act), c_int, _p, c_long, _p],
     "sseg_prep_conv_weight": [_p, c_int, c_int, c_int, _p, c_long, _p, c_long, c_int, _p],
     "sseg_prep_conv_weights_batched": [_p, c_int, c_int, _p],
+    "sseg_prep_conv_weights_batched_ex": [_p, c_int, c_int, c_int, _p],
     "sseg_grads_to_oihw_batched": [_p, c_int, c_int, c_float, _p],
     "sseg_sgd_step": [_p, c_int, c_float, c_float, c_int, _p],
     "sseg_scale_by_scalar": [_p, c_long, _p, _p],

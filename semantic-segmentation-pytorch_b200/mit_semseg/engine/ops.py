@@ -588,8 +588,12 @@ class WeightTable:
         self.dev = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(device)
         self.keep = entries
 
-    def prep(self):
-        _C.check(_C.lib().sseg_prep_conv_weights_batched(_C.ptr(self.dev), self.n, self.tiles, _stream()))
+    def prep(self, max_blocks=0):
+        """max_blocks > 0: a thin grid (blocks walk the tiles) - for a pass that runs next to the main stream's kernels"""
+        if max_blocks > 0:
+            _C.check(_C.lib().sseg_prep_conv_weights_batched_ex(_C.ptr(self.dev), self.n, self.tiles, int(max_blocks), _stream()))
+        else:
+            _C.check(_C.lib().sseg_prep_conv_weights_batched(_C.ptr(self.dev), self.n, self.tiles, _stream()))
 
     def grads(self, scale=1.0):
         _C.check(_C.lib().sseg_grads_to_oihw_batched(_C.ptr(self.dev), self.n, self.tiles, float(scale), _stream()))

@@ -32,6 +32,10 @@ def _pad(x, m):
     return (x + m - 1) // m * m
 
 
+def _os_environ_get(k, d):
+    return os.environ.get(k, d)
+
+
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -375,7 +379,10 @@ class SegProgram:
                 self.wtable = ops.WeightTable([self._wentry(c, wd=False) for c in convs], self.dev)
                 self.wtable_d = ops.WeightTable([self._wentry(c, wf=False) for c in convs], self.dev)
                 self.fwd.append(self.wtable.prep)
-                self.fwd.append(self.on_side(self.wtable_d.prep))
+                # ... on a THIN grid: behind a launch with thousands of pending blocks the main stream's next kernels would
+                # wait until its last block has been dispatched (measured: the stem started only when the pass had ended)
+                nblk = int(_os_environ_get("SSEG_PREP_SIDE_BLOCKS", "32"))
+                self.fwd.append(self.on_side(lambda: self.wtable_d.prep(max_blocks=nblk)))
                 return
             self.wtable = ops.WeightTable([self._wentry(c) for c in convs], self.dev)
             self.fwd.append(self.wtable.prep)

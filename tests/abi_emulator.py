@@ -315,6 +315,9 @@ class EmuLib:
         o.copy_(o + gs if accumulate else gs)
         return 0
 
+    def sseg_prep_conv_weights_batched_ex(self, table, n, tiles, max_blocks, stream):
+        return self.sseg_prep_conv_weights_batched(table, n, tiles, stream)
+
     def sseg_prep_conv_weights_batched(self, table, n, tiles, stream):
         for d in self._descs(table, n):
             w = flat(d.w, d.O * d.I * d.T, torch.float32)

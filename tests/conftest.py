@@ -12,6 +12,11 @@ for p in (ROOT, PKG):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # the torch references of the kernel tests are fp32: no TF32 in cuDNN / cuBLAS (their 10-bit mantissa is coarser than
+    # several of the tolerances, e.g. 1e-4 on the stem weight gradient)
+    import torch
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
 
 
 # "1": the Python restatement of the C ABI (tests/abi_emulator.py); "sim": the REAL kernel sources compiled for the CPU

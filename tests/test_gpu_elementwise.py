@@ -326,6 +326,15 @@ def test_batched_weight_prep_from_channels_last_masters():
         ref_d = torch.zeros(I_, T_, opad, device=DEV)
         ref_d[:, :, :O_] = w.permute(1, 2, 3, 0).reshape(I_, T_, O_)
         assert torch.equal(e["wd"], ref_d.reshape(I_, -1).bfloat16())
+    # the split the step programs use: forward operands alone (the direct cast path where the tile allows it) and the
+    # data-gradient operands alone on a thin grid (3 blocks walking all tiles)
+    fwd_only = [dict(e, wf=torch.zeros_like(e["wf"]), wd=None) for e in entries]
+    dgrad_only = [dict(e, wf=None, wd=torch.zeros_like(e["wd"])) for e in entries]
+    ops.WeightTable(fwd_only, DEV).prep()
+    ops.WeightTable(dgrad_only, DEV).prep(max_blocks=3)
+    torch.cuda.synchronize()
+    for e, f, d in zip(entries, fwd_only, dgrad_only):
+        assert torch.equal(f["wf"], e["wf"]) and torch.equal(d["wd"], e["wd"])
 
 
 def test_fused_sgd_matches_torch_sgd():
