@@ -45,6 +45,41 @@ __global__ void __launch_bounds__(256) weights_batched_kernel(const sseg_weight_
   const int ctas_i = (tiles_i + rep - 1) / rep;
   const int o0 = (local / ctas_i) * kTile;
   const int no = min(kTile, O - o0);
+  if (mode == 0 && T == 1) {
+    // ---- pointwise convolutions ([O][I] master): the CTA's `rep` consecutive 32-wide i-tiles are staged AT ONCE, as if
+    //      they were taps - one load phase with 8 loads in flight per row, one barrier, one store phase. (Walking them one
+    //      after the other - load, barrier, store, barrier, eight times - made these CTAs live 24 us for 64 KB of traffic.)
+    const int it0 = (local % ctas_i) * rep;
+    const int K = min(rep, tiles_i - it0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ibase = it0 * kTile + lane;
+    __syncthreads();  // the shared tile is reused across the grid-stride loop
+    const float* w = d->w;
+    for (int ol = warp; ol < no; ol += 8) {
+      const float* src = w + (long)(o0 + ol) * I + ibase;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < K && ibase + k * kTile < I) tile[ol][k * kTile + lane] = src[k * kTile];
+    }
+    __syncthreads();
+    __nv_bfloat16* wf = static_cast<__nv_bfloat16*>(d->wf);
+    if (wf) {
+      for (int ol = warp; ol < no; ol += 8) {
+        __nv_bfloat16* dst = wf + (long)(o0 + ol) * d->fwd_ld + ibase;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < K && ibase + k * kTile < I) dst[k * kTile] = __float2bfloat16(tile[ol][k * kTile + lane]);
+      }
+    }
+    __nv_bfloat16* wd = static_cast<__nv_bfloat16*>(d->wd);
+    if (wd && lane < no) {
+      for (int il = warp; il < K * kTile; il += 8) {
+        const int i = it0 * kTile + il;
+        if (i < I) wd[(long)i * d->dgrad_ld + o0 + lane] = __float2bfloat16(tile[lane][il]);
+      }
+    }
+    continue;
+  }
   for (int it = (local % ctas_i) * rep; it < min(tiles_i, (local % ctas_i) * rep + rep); ++it) {
   const int i0 = it * kTile;
   const int ni = min(kTile, I - i0);

@@ -181,7 +181,7 @@ class SegProgram:
         # layers and ALL data-gradient operands are produced on the side stream while the stem / first stages run, and
         # the gradient re-layout of a bucket follows its weight-gradient GEMMs on the side stream instead of the end.
         self.overlap_relayout = _os.environ.get("SSEG_OVERLAP_RELAYOUT", "0") == "1" and part == "full"
-        self.split_prep = _os.environ.get("SSEG_SPLIT_PREP", "1") != "0" and not self.overlap_relayout
+        self.split_prep = _os.environ.get("SSEG_SPLIT_PREP", "0") != "0" and not self.overlap_relayout
         # conv + train-mode BN (+shortcut, ReLU, dropout) as ONE persistent kernel with an in-kernel grid barrier
         # (sseg_conv_bn_train) for every layer whose tiles fit the SMs' tensor memory; single-GPU F.batch_norm branch only.
         # Opt-in until it has run on B200.

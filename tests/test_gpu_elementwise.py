@@ -308,7 +308,7 @@ def test_batched_weight_prep_from_channels_last_masters():
     prep kernel as from OIHW masters, including ragged 32-tiles (I = 48, O = 150) and a pointwise entry next to 3x3 ones."""
     from mit_semseg.engine import ops
     g = _gen(10)
-    specs = [(150, 512, 1), (64, 48, 9), (256, 128, 9), (96, 200, 9)]
+    specs = [(150, 512, 1), (64, 48, 9), (256, 128, 9), (96, 200, 9), (96, 200, 1), (40, 72, 1), (2048, 1024, 1)]
     entries = []
     for O_, I_, T_ in specs:
         k = int(T_ ** 0.5)
