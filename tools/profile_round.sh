@@ -35,16 +35,11 @@ cap() {  # cap <name> <kernel regex> <skip> <count>
 }
 cap igemm256   "igemm_kernel<256"      0 3     # conv_last / deepsup / layer4 3x3 (128 x 256 tiles)
 cap igemm128   "igemm_kernel<128, 3"   20 3    # mid-size convolutions
-cap igemm128d  "igemm_kernel<128, 6"   4 3     # <= 148 CTAs: deep pipeline
 cap igemm64    "igemm_kernel<64"       6 3
 cap wgrad256   "wgrad_kernel<256"      0 2
 cap wgrad128   "wgrad_kernel<128"      20 3
 cap bnapply    "bn_apply_kernel"       2 3
 cap bnbwdapply "bn_bwd_kernel<1>"      4 3
-cap bnbwdred   "bn_bwd_kernel<0>"      2 3
-cap bnfinal    "bn_finalize_kernel"    10 2
 cap weights    "weights_batched_kernel" 0 1
 cap avgpoolbwd "avgpool_bwd_kernel"    0 1
-cap bilinbwd   "bilinear_bwd"          0 2
 cap stem       "stem_conv"             0 2
-cap softmax    "softmax_nll"           0 2
