@@ -379,7 +379,14 @@ def conv_roofline(prog, world):
         timed("igemm", lambda: orig_bnbwd(geom, w_bf16, cout, out, *a, **kw), flops_geom(geom, cout, n, h, w))
         return out
 
-    ops.conv_igemm, ops.conv_wgrad, ops.conv_igemm_bnbwd = igemm, wgrad, igemm_bnbwd
+    orig_bnbwd_res = ops.conv_igemm_bnbwd_res
+
+    def igemm_bnbwd_res(geom, w_bf16, cout, out, *a, **kw):   # the same for residual-block outputs (mask from the saved output)
+        n, h, w = out.shape[0], out.shape[1], out.shape[2]
+        timed("igemm", lambda: orig_bnbwd_res(geom, w_bf16, cout, out, *a, **kw), flops_geom(geom, cout, n, h, w))
+        return out
+
+    ops.conv_igemm, ops.conv_wgrad, ops.conv_igemm_bnbwd, ops.conv_igemm_bnbwd_res = igemm, wgrad, igemm_bnbwd, igemm_bnbwd_res
     prog.serial = True  # weight gradients inline on the main stream: one kernel at a time between each event pair
     try:
         stream = torch.cuda.current_stream()
@@ -394,6 +401,7 @@ def conv_roofline(prog, world):
     finally:
         prog.serial = False
         ops.conv_igemm, ops.conv_wgrad, ops.conv_igemm_bnbwd = orig_igemm, orig_wgrad, orig_bnbwd
+        ops.conv_igemm_bnbwd_res = orig_bnbwd_res
     tot = {"igemm": [0.0, 0.0, 0], "wgrad": [0.0, 0.0, 0]}
     top = None
     for kind, a, b, fl in records:

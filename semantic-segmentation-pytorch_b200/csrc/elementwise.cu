@@ -739,21 +739,39 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const AvgPoolBwdParams
   const int h = b % p.H, n = b / p.H;
   // rows of bins containing h: candidates ic-1 .. ic+1 around ic = floor(h*S/H) (ATen's adaptive bins
   // [floor(i*H/S), ceil((i+1)*H/S)) overlap their neighbours by at most one row)
-  int bi[4][3], bh[4][3];   // bin row index, bin height (0 = not a bin of this row)
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int S = k < p.nscales ? p.scales[k] : 1;
-    const int ic = (h * S) / p.H;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-      const int i = ic - 1 + d;
-      bi[k][d] = i, bh[k][d] = 0;
-      if (k < p.nscales && i >= 0 && i < S) {
+  __shared__ int bi[4][3], bh[4][3];   // bin row index, bin height (0 = not a bin of this row)
+  if (threadIdx.x >= 224 && threadIdx.x < 236) {
+    const int k = (threadIdx.x - 224) / 3, d = (threadIdx.x - 224) % 3;
+    int i = 0, hh = 0;
+    if (k < p.nscales) {
+      const int S = p.scales[k];
+      i = (h * S) / p.H - 1 + d;
+      if (i >= 0 && i < S) {
         const int h0 = (i * p.H) / S, h1 = ((i + 1) * p.H + S - 1) / S;
-        if (h >= h0 && h < h1) bh[k][d] = h1 - h0;
+        if (h >= h0 && h < h1) hh = h1 - h0;
       }
     }
+    bi[k][d] = i, bh[k][d] = hh;
   }
+  // ... and the columns of bins containing each of the segment's pixels, once per block (table in shared memory: the
+  // per-pixel loop below is then free of integer divisions - with them it still ran at 90 us for a 67 MB pass)
+  __shared__ int s_j[kAvgWT][4][3];    // bin column index
+  __shared__ int s_bw[kAvgWT][4][3];   // bin width, 0 = not a bin of this column
+  if (threadIdx.x < kAvgWT * 12) {
+    const int wl = threadIdx.x / 12, k = (threadIdx.x % 12) / 3, dj = threadIdx.x % 3;
+    const int w = w_base + wl;
+    int j = 0, bwid = 0;
+    if (k < p.nscales && w < p.W) {
+      const int S = p.scales[k];
+      j = (w * S) / p.W - 1 + dj;
+      if (j >= 0 && j < S) {
+        const int w0 = (j * p.W) / S, w1 = ((j + 1) * p.W + S - 1) / S;
+        if (w >= w0 && w < w1) bwid = w1 - w0;
+      }
+    }
+    s_j[wl][k][dj] = j, s_bw[wl][k][dj] = bwid;
+  }
+  __syncthreads();
   int cgb = cg < 256 ? cg : 256;
   while (256 % cgb != 0) --cgb;
   const int tcol = threadIdx.x % cgb, trow = threadIdx.x / cgb, lanes_w = 256 / cgb;
@@ -774,19 +792,17 @@ __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const AvgPoolBwdParams
       for (int k = 0; k < 4; ++k) {
         if (k >= p.nscales) break;
         const int S = p.scales[k];
-        const int jc = (w * S) / p.W;
 #pragma unroll
         for (int dj = 0; dj < 3; ++dj) {
-          const int j = jc - 1 + dj;
-          if (j < 0 || j >= S) continue;
-          const int w0 = (j * p.W) / S, w1 = ((j + 1) * p.W + S - 1) / S;
-          if (w < w0 || w >= w1) continue;
+          const int bwid = s_bw[wl][k][dj];
+          if (bwid == 0) continue;
+          const int j = s_j[wl][k][dj];
 #pragma unroll
           for (int d = 0; d < 3; ++d) {
             if (bh[k][d] == 0) continue;
             float g[8];
             load8(p.dpool[k] + (((long)n * S + bi[k][d]) * S + j) * p.C + c0, g);
-            const float inv = 1.f / (bh[k][d] * (w1 - w0));
+            const float inv = 1.f / (bh[k][d] * bwid);
 #pragma unroll
             for (int e = 0; e < 8; ++e) acc[e] += g[e] * inv;
           }

@@ -29,7 +29,8 @@ for k, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:24]:
 PY
 
 cap() {  # cap <name> <kernel regex> <skip> <count>
-  timeout 200 $NCU --set full --import-source on -k regex:$2 -s $3 -c $4 -f -o $OUT/$1_${TAG} python tools/one_step.py 1 > /dev/null 2>&1
+  # template kernels are told apart by their arguments: match on the demangled name
+  timeout 200 $NCU --set full --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c $4 -f -o $OUT/$1_${TAG} python tools/one_step.py 1 > /dev/null 2>&1
   ncu -i $OUT/$1_${TAG}.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py > $OUT/ncu_$1_${TAG}.csv
   echo "== $1"; cut -d, -f1-9 $OUT/ncu_$1_${TAG}.csv | head -5
 }
@@ -39,7 +40,7 @@ cap igemm64    "igemm_kernel<64"       6 3
 cap wgrad256   "wgrad_kernel<256"      0 2
 cap wgrad128   "wgrad_kernel<128"      20 3
 cap bnapply    "bn_apply_kernel"       2 3
-cap bnbwdapply "bn_bwd_kernel<1>"      4 3
+cap bnbwdapply "bn_bwd_kernel<true>|bn_bwd_kernel<1>" 4 3
 cap weights    "weights_batched_kernel" 0 1
 cap avgpoolbwd "avgpool_bwd_kernel"    0 1
 cap stem       "stem_conv"             0 2
