@@ -1976,7 +1976,8 @@ static int conv_igemm_impl(const sseg_conv_geom_t* g, const void* w_bf16, long w
   }
   // persistent CTAs (one per SM, double-buffered accumulators) once there are clearly more tiles than SMs
   static const int persistent_min_tiles = env_int("SSEG_IGEMM_PERSISTENT", 0);  // 0 = off; e.g. 200 = on for >= 200 tiles
-  if (persistent_min_tiles > 0 && grid >= persistent_min_tiles && block_n != 256 && fin == nullptr) {
+  // (its sliced epilogue knows neither the fused finalize nor the mask-from-saved-output reduction: those launches keep the plain kernel)
+  if (persistent_min_tiles > 0 && grid >= persistent_min_tiles && block_n != 256 && fin == nullptr && bw_a == nullptr) {
     static int num_sms = 0;
     if (num_sms == 0) {
       int dev = 0;

@@ -24,6 +24,9 @@ void set_error(const char* fmt, ...) {
 int check_cuda(cudaError_t e, const char* what) {
   if (e == cudaSuccess) return 0;
   set_error("CUDA error %s (%d) at %s", cudaGetErrorString(e), (int)e, what);
+  // the runtime also keeps a failed launch as its "last error": consume it, or the next entry point that checks
+  // cudaGetLastError() after its own (successful) launch would report this failure a second time under its own name
+  (void)cudaGetLastError();
   return SSEG_ERR_CUDA;
 }
 

@@ -34,13 +34,13 @@ cap() {  # cap <name> <kernel regex> <skip> <count>
   ncu -i $OUT/$1_${TAG}.ncu-rep --page raw --csv 2>/dev/null | python tools/ncu_pick.py > $OUT/ncu_$1_${TAG}.csv
   echo "== $1"; cut -d, -f1-9 $OUT/ncu_$1_${TAG}.csv | head -5
 }
-cap igemm256   "igemm_kernel<256"      0 3     # conv_last / deepsup / layer4 3x3 (128 x 256 tiles)
-cap igemm128   "igemm_kernel<128, 3"   20 3    # mid-size convolutions
-cap igemm64    "igemm_kernel<64"       6 3
-cap wgrad256   "wgrad_kernel<256"      0 2
-cap wgrad128   "wgrad_kernel<128"      20 3
+cap igemm256   "igemm_kernel<.int.256"      0 3     # conv_last / deepsup / layer4 3x3 (128 x 256 tiles)
+cap igemm128   "igemm_kernel<.int.128, .int.3"   20 3    # mid-size convolutions
+cap igemm64    "igemm_kernel<.int.64"       6 3
+cap wgrad256   "wgrad_kernel<.int.256"      0 2
+cap wgrad128   "wgrad_kernel<.int.128"      20 3
 cap bnapply    "bn_apply_kernel"       2 3
-cap bnbwdapply "bn_bwd_kernel<true>|bn_bwd_kernel<1>" 4 3
+cap bnbwdapply "bn_bwd_kernel<.bool.1" 4 3
 cap weights    "weights_batched_kernel" 0 1
 cap avgpoolbwd "avgpool_bwd_kernel"    0 1
 cap stem       "stem_conv"             0 2
