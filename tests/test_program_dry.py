@@ -46,8 +46,9 @@ def test_training_schedule_wiring(enc, dec, fc, hw, nsum, monkeypatch):
     monkeypatch.setattr(PR.SegProgram, "on_side", counting)
     P = PR.SegProgram(seg, (2, 3, hw, hw), training=True, with_grad=True, dry_run=True)
     nconv = sum(isinstance(m, nn.Conv2d) for m in seg.modules())
-    # one weight-gradient task per convolution (stem and classifiers included) + the data-gradient operand prep
-    assert side[0] == nconv + 1
+    # one weight-gradient task per convolution (stem and classifiers included); + the data-gradient operand prep when that
+    # runs on the side stream (SSEG_SPLIT_PREP=1, off by default: measured slower)
+    assert side[0] == nconv + (1 if P.split_prep else 0)
     assert sum(isinstance(r, PR.SumRec) for r in P.records) == nsum
     for r in P.records:
         a = getattr(r, "a", None)
@@ -160,9 +161,12 @@ def test_overlapped_relayout_schedule(monkeypatch):
     assert t_early.n + t_late.n == t_dgrad.n == len(P.convs) - 1            # every conv but the 3-channel stem conv
     early = [c for c in P.convs.values() if c.I != 3 and id(c) not in P._late_convs]
     assert sum(c.O * c.T * c.I for c in early) <= 2_000_000 and not P._late_pending
-    # the default schedule already produces the data-gradient operands on the side stream (one closure, one join)
-    assert len(P.fwd) == len(Q.fwd) + 1      # + one wait before the first late convolution
-    assert len(P.bwd) == len(Q.bwd) + 2      # 2 bucket closes
+    assert len(P.fwd) == len(Q.fwd) + 2      # side-stream prep + one wait
+    assert len(P.bwd) == len(Q.bwd) + 3      # join for the dgrad operands, 2 bucket closes
+    monkeypatch.delenv("SSEG_OVERLAP_RELAYOUT")
+    monkeypatch.setenv("SSEG_SPLIT_PREP", "1")   # only the data-gradient operands on the side stream (thin grid)
+    R = PR.SegProgram(seg, (2, 3, 64, 64), training=True, with_grad=True, dry_run=True)
+    assert R.split_prep and len(R.fwd) == len(Q.fwd) + 1 and len(R.bwd) == len(Q.bwd) + 1
     assert set(P.param_grads()) == set(Q.param_grads())
 
 
