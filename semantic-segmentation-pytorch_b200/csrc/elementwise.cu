@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(128) stem_conv_fwd_kernel(const float* __restr
 // 64 co, bf16) next to them. 256 threads = 4 pixel lanes x 16 channel groups (4 co) x 4 tap groups (8 of the 27 taps, padded
 // to 32): a 4 x 8 register tile per thread, 9 shared loads per 32 FMAs (the first version: 8 per 7, and 64-bit index
 // arithmetic per staged element: 110 us at the very end of the step). Pixel lanes are folded with shuffles at the end.
-__global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __restrict__ img,
+__global__ void __launch_bounds__(256, 3) stem_conv_wgrad_kernel(const float* __restrict__ img,
                                                               const __nv_bfloat16* __restrict__ dy,
                                                               float* __restrict__ dw, int N, int H, int W, int Ho, int Wo) {
   pdl_sync();
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(256) stem_conv_wgrad_kernel(const float* __res
       *reinterpret_cast<uint4*>(&s_dy[px][part * 8]) = q;
     }
     __syncthreads();
-#pragma unroll 4
+#pragma unroll 2
     for (int px = pxl; px < kStemTW; px += 4) {
       const uint2 gq = *reinterpret_cast<const uint2*>(&s_dy[px][cog * 4]);
       const float2 g01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gq.x));
@@ -728,7 +728,7 @@ struct AvgPoolBwdParams {
 // One block = one image row segment (n, h, kAvgWT consecutive w): the bins of every scale that contain row h are found once
 // per block, and all index arithmetic is 32-bit (the first version spent its time in 64-bit divisions: 143 us for a 67 MB
 // pass). Threads: channel groups fastest (16-byte vectors, coalesced), the remaining lanes walk the pixels of the segment.
-constexpr int kAvgWT = 16;
+constexpr int kAvgWT = 8;
 __global__ void __launch_bounds__(256) avgpool_bwd_kernel(const AvgPoolBwdParams p) {
   pdl_sync();
   const int cg = p.C >> 3;

@@ -58,6 +58,12 @@ class SegmentationModule(SegmentationModuleBase):
             return EF.segmentation_train_step(self, feed_dict['img_data'], feed_dict['seg_label'])
         return EF.segmentation_inference(self, feed_dict['img_data'], segSize)
 
+    def zero_grad(self, set_to_none=True):
+        """nn.Module.zero_grad (train.py:41), over a cached flat parameter list: the generic implementation walks the
+        module tree through nested generators, 0.3 ms of host time per step during which the GPU is idle."""
+        from ..engine import functional as EF
+        EF.fast_zero_grad(self, set_to_none)
+
 
 class ModelBuilder:
     @staticmethod
