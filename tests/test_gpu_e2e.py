@@ -194,6 +194,37 @@ def test_graph_replay_matches_eager_and_autograd_path():
     assert abs(prog.out[0].item() - l1) <= 1e-4 * abs(l1)
 
 
+def test_host_batches_as_the_reference_loader_hands_them_over():
+    """`python train.py --gpus 0` (train.py:176-183): the loader's one-element list of HOST tensors goes straight into the
+    module. Pinned or pageable, wrapped in the list or not, the step equals the one fed with device tensors."""
+    from oracle import segnet_oracle as O
+    seg, esd, dsd, ds = _build("resnet18dilated", "c1_deepsup", 512, residual_gain=0.25)
+    seg.cuda().train()
+    for m in seg.modules():
+        if isinstance(m, nn.modules.batchnorm._BatchNorm):
+            m.eval()            # frozen statistics: the three runs are comparable to the last bits of the atomics
+    host = O.synth_batch(2, 96, 128, 8, 21)
+    assert conftest_emulated() or not host["img_data"].is_cuda    # (the emulator run patches is_cuda)
+    want, _ = seg({k: v.cuda() for k, v in host.items()})
+    want.backward()
+    g_ref = seg.encoder.layer3[0].conv1.weight.grad.clone()
+    feeds = [[dict(host)], {k: v.pin_memory() for k, v in host.items()} if torch.cuda.is_available() and not conftest_emulated()
+             else dict(host)]
+    for feed in feeds:
+        seg.zero_grad()
+        loss, acc = seg(feed)
+        loss.backward()
+        assert loss.is_cuda or conftest_emulated()
+        assert abs(loss.item() - want.item()) <= 1e-4 * abs(want.item())
+        g = seg.encoder.layer3[0].conv1.weight.grad
+        assert torch.allclose(g, g_ref, rtol=1e-3, atol=1e-4 * g_ref.abs().max().item())
+
+
+def conftest_emulated():
+    import conftest
+    return conftest.EMULATE
+
+
 def test_train_mode_replay_updates_running_stats_once_per_step():
     """F.batch_norm semantics (batchnorm.py:58-61, momentum 0.001): the capture warm-up must not leak extra updates."""
     from oracle import segnet_oracle as O
