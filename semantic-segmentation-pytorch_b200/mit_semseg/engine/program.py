@@ -32,10 +32,6 @@ def _pad(x, m):
     return (x + m - 1) // m * m
 
 
-def _os_environ_get(k, d):
-    return os.environ.get(k, d)
-
-
 def _dist():
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
@@ -373,15 +369,16 @@ class SegProgram:
         self._late_convs, self._late_pending = set(), False
         if not self.overlap_relayout:
             if self.with_grad and self.split_prep:
-                # the data-gradient operands (the transposing half of the pass) are first read ~2 ms later, by the backward
-                # pass: they are produced on the side stream while the forward pass runs, only the forward operands (a
-                # plain cast of the channels-last masters) stay in front of the stem
+                # (opt-in SSEG_SPLIT_PREP=1; measured slower than the single pass for every side-grid size, profiles/
+                # r2_summary.md section 8) the data-gradient operands (the transposing half of the pass) are first read
+                # ~2 ms later, by the backward pass: they are produced on the side stream while the forward pass runs, only
+                # the forward operands (a plain cast of the channels-last masters) stay in front of the stem
                 self.wtable = ops.WeightTable([self._wentry(c, wd=False) for c in convs], self.dev)
                 self.wtable_d = ops.WeightTable([self._wentry(c, wf=False) for c in convs], self.dev)
                 self.fwd.append(self.wtable.prep)
                 # ... on a THIN grid: behind a launch with thousands of pending blocks the main stream's next kernels would
                 # wait until its last block has been dispatched (measured: the stem started only when the pass had ended)
-                nblk = int(_os_environ_get("SSEG_PREP_SIDE_BLOCKS", "32"))
+                nblk = int(os.environ.get("SSEG_PREP_SIDE_BLOCKS", "32"))
                 self.fwd.append(self.on_side(lambda: self.wtable_d.prep(max_blocks=nblk)))
                 return
             self.wtable = ops.WeightTable([self._wentry(c) for c in convs], self.dev)
