@@ -299,10 +299,6 @@ def decoder_forward(dec, conv_out, seg_size):
     return outs[0] if len(outs) == 1 else tuple(outs)
 
 
-def run_block(block, x):
-    raise NotImplementedError("residual blocks run inside a SegmentationModule program on the B200 engine")
-
-
 class _ModuleBatchNorm(torch.autograd.Function):
     """SynchronizedBatchNorm{1,2,3}d called on its own (reference lib/nn/modules/batchnorm.py:56-86), on the engine's BN
     kernels: NCHW fp32 -> NHWC bf16, per-channel [sum | sum of squares] (the backward-reduce kernel with g = y = x,

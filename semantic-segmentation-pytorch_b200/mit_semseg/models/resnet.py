@@ -58,8 +58,13 @@ class _Block(nn.Module):
         return [(getattr(self, 'conv%d' % i), getattr(self, 'bn%d' % i)) for i in range(1, len(self._SPEC) + 1)]
 
     def forward(self, x):
-        from ..engine import functional as EF
-        return EF.run_block(self, x)
+        # A block owns parameters and describes its stages; it is scheduled (fused with its neighbours' BN / shortcut / ReLU)
+        # by the step program of the network that contains it. The smallest callable units on the engine are the encoder and
+        # the decoder (engine/functional.py: encoder_forward / decoder_forward); the reference's per-block forward
+        # (models/resnet.py:37-53,72-92) has no stand-alone counterpart.
+        raise RuntimeError("%s is executed as part of its network's step program (call the encoder, the decoder or the "
+                           "SegmentationModule); a residual block cannot be called on its own on the B200 engine"
+                           % type(self).__name__)
 
 
 class BasicBlock(_Block):

@@ -275,7 +275,7 @@ def _worker_shapes(rank, world, port, ret):
         seg.train()
         opt = torch.optim.SGD(seg.parameters(), lr=0.01, momentum=0.9)
         shapes = [(2, 64, 64), (2, 64, 96)]
-        for step in range(6):
+        for step in range(4):     # every shape twice on every rank: its program is captured on the second use
             n, h, w = shapes[(step + rank) % 2]
             feed = O.synth_batch(n, h, w, 8, 500 + 10 * step + rank)
             seg.zero_grad()
